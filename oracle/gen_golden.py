@@ -1,0 +1,253 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python -m oracle.gen_golden            # all sets
+    python -m oracle.gen_golden update rsirfo
+
+The produced files are committed; the GPU box and the CPU test-suite only read
+the .npz files.  Inputs come from ``multioptpy_b200.synthetic`` (seeded).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from oracle.np_oracle import UPDATE_DISPATCH  # noqa: E402  (ids/names only)
+from multioptpy_b200 import synthetic  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+# ---------------------------------------------------------------- update ----
+REF_UPDATE_FN = {
+    1: ("M", "flowchart_hessian_update"),
+    2: ("B", "block_CFD_FSB_hessian_update_dd"),
+    3: ("B", "block_CFD_FSB_hessian_update_weighted"),
+    4: ("B", "block_CFD_FSB_hessian_update"),
+    5: ("B", "block_CFD_Bofill_hessian_update_weighted"),
+    6: ("B", "block_CFD_Bofill_hessian_update"),
+    7: ("B", "block_BFGS_hessian_update_dd"),
+    8: ("B", "block_BFGS_hessian_update"),
+    9: ("B", "block_FSB_hessian_update_dd"),
+    10: ("B", "block_FSB_hessian_update_weighted"),
+    11: ("B", "block_FSB_hessian_update"),
+    12: ("B", "block_Bofill_hessian_update_weighted"),
+    13: ("B", "block_Bofill_hessian_update"),
+    14: ("M", "BFGS_hessian_update_dd"),
+    15: ("M", "BFGS_hessian_update"),
+    16: ("M", "SR1_hessian_update"),
+    18: ("M", "CFD_FSB_hessian_update_dd"),
+    19: ("M", "CFD_FSB_hessian_update"),
+    20: ("M", "CFD_Bofill_hessian_update"),
+    21: ("M", "FSB_hessian_update_dd"),
+    22: ("M", "FSB_hessian_update"),
+    23: ("M", "Bofill_hessian_update"),
+    24: ("M", "PSB_hessian_update"),
+    25: ("M", "MSP_hessian_update"),
+}
+
+
+def update_inputs(n, rng, kind):
+    H = synthetic.spd_hessian(n, rng)
+    s = rng.normal(0.0, 0.05, size=n)
+    if kind == "normal":
+        y = H @ s + rng.normal(0.0, 5e-3, size=n)
+    elif kind == "near_secant":      # y ~ H s : tiny SR1 / phi denominators
+        y = H @ s + rng.normal(0.0, 1e-9, size=n)
+    elif kind == "low_curvature":    # 0 < s.y < 0.2 s.s : double damping active
+        y = 0.05 * s + rng.normal(0.0, 1e-4, size=n)
+    elif kind == "negative":         # s.y < 0
+        y = -(H @ s)
+    elif kind == "tiny_step":        # ||s|| below the block rank guards
+        s = s * 1e-8
+        y = H @ s
+    elif kind == "flow_sr1":         # flowchart: z.s strongly negative
+        H = H * 8.0
+        y = H @ s * 0.3
+    else:
+        raise ValueError(kind)
+    return H, s, y
+
+
+def gen_update():
+    hu = ref_shim.ref("Optimizer.hessian_update")
+    bu = ref_shim.ref("Optimizer.block_hessian_update")
+    kinds = ["normal", "near_secant", "low_curvature", "negative", "tiny_step", "flow_sr1"]
+    mids, Hs, ss, ys, ds, ks = [], [], [], [], [], []
+    n = 18
+    for mid, (cls, fname) in sorted(REF_UPDATE_FN.items()):
+        for ki, kind in enumerate(kinds):
+            for rep in range(2):
+                rng = np.random.default_rng(77000 + 100 * mid + 10 * ki + rep)
+                H, s, y = update_inputs(n, rng, kind)
+                obj = hu.ModelHessianUpdate() if cls == "M" else bu.BlockHessianUpdate()
+                args = (H.copy(), s.reshape(-1, 1).copy(), y.reshape(-1, 1).copy())
+                if mid == 1:
+                    args = args + ("auto",)
+                with quiet():
+                    d = getattr(obj, fname)(*args)
+                mids.append(mid); Hs.append(H); ss.append(s); ys.append(y)
+                ds.append(np.asarray(d, dtype=np.float64)); ks.append(ki)
+    np.savez_compressed(os.path.join(GOLD, "update_deltas.npz"), method=np.array(mids, np.int32),
+                        kind=np.array(ks, np.int32), H=np.stack(Hs), s=np.stack(ss), y=np.stack(ys),
+                        delta=np.stack(ds), kinds=np.array(kinds))
+    print("update_deltas:", len(mids), "cases")
+
+
+# ---------------------------------------------------------------- rsirfo ----
+RSIRFO_CASES = [
+    # (name, method, saddle_order, natoms, nsteps, bias, neb_mode, seed)
+    ("bfgs_min_n24", "rsirfo_bfgs", 0, 8, 5, False, False, 1),
+    ("bofill_min_n33", "rsirfo_bofill", 0, 11, 5, True, False, 2),
+    ("fsb_min_n30", "rsirfo_fsb", 0, 10, 4, False, False, 3),
+    ("msp_min_n24", "rsirfo_msp", 0, 8, 4, False, False, 4),
+    ("psb_min_n24", "rsirfo_psb", 0, 8, 4, True, False, 5),
+    ("sr1_min_n24", "rsirfo_sr1", 0, 8, 4, False, False, 6),
+    ("cfd_bofill_min_n24", "rsirfo_cfd_bofill", 0, 8, 4, False, False, 7),
+    ("cfd_fsb_min_n24", "rsirfo_cfd_fsb", 0, 8, 4, False, False, 8),
+    ("blockfsb_min_n36", "rsirfo_block_fsb", 0, 12, 5, True, False, 9),
+    ("blockbofill_ts_n36", "rsirfo_block_bofill", 1, 12, 5, False, False, 10),
+    ("bofill_ts_n33", "rsirfo_bofill", 1, 11, 5, True, False, 11),
+    ("blockbofill_neb_n30", "rsirfo_block_bofill", 1, 10, 4, False, True, 12),
+    ("blockfsb_neb0_n30", "rsirfo_block_fsb", 0, 10, 4, False, True, 13),
+    ("bofill_ts2_n24", "rsirfo_bofill", 2, 8, 4, False, False, 14),
+    ("auto_min_n24", "rsirfo", 0, 8, 4, False, False, 15),
+    ("blockbfgs_min_n24", "rsirfo_block_bfgs", 0, 8, 4, False, False, 16),
+    ("bfgs_min_n72", "rsirfo_bfgs", 0, 24, 4, False, False, 17),
+    ("bfgs_min_n150", "rsirfo_bfgs", 0, 50, 3, False, False, 18),
+    ("fsb_dd_min_n24", "rsirfo_fsb_dd", 0, 8, 4, False, False, 19),
+    ("blockcfdbofill_min_n24", "rsirfo_block_cfd_bofill", 0, 8, 4, False, False, 20),
+]
+
+
+class QuadraticPES:
+    """E(x) = E0 + g0.(x-x0) + 1/2 (x-x0)^T Ht (x-x0) + c3 * sum((x-x0)^3) and a
+    constant-Hessian harmonic bias; only used to feed consistent (E, g)."""
+
+    def __init__(self, x0, g0, Ht, Hb, rng):
+        self.x0, self.g0, self.Ht, self.Hb = x0, g0, Ht, Hb
+        self.xc = x0 + rng.normal(0.0, 0.05, size=x0.size)
+        self.c3 = 0.02
+
+    def raw(self, x):
+        d = x - self.x0
+        e = self.g0 @ d + 0.5 * d @ self.Ht @ d + self.c3 * np.sum(d ** 3)
+        g = self.g0 + self.Ht @ d + 3 * self.c3 * d ** 2
+        return e, g
+
+    def bias(self, x):
+        d = x - self.xc
+        return 0.5 * d @ self.Hb @ d, self.Hb @ d
+
+
+def run_rsirfo_case(case):
+    name, method, so, natoms, nsteps, bias, neb, seed = case
+    rs = ref_shim.ref("Optimizer.rsirfo")
+    rng = np.random.default_rng(424200 + seed)
+    n = 3 * natoms
+    x0 = synthetic.grid_geometry(natoms, rng).reshape(-1)
+    H0 = synthetic.spd_hessian(n, rng, neg_lowest=so > 0)
+    if so > 1:
+        w, V = np.linalg.eigh(H0)
+        w[1] = -0.02
+        H0 = (V * w) @ V.T
+        H0 = 0.5 * (H0 + H0.T)
+    E = rng.standard_normal((n, n))
+    Ht = H0 + 0.05 * (E + E.T) / np.sqrt(n)
+    g0 = rng.normal(0.0, 2e-2, size=n)
+    if bias:
+        Bm = rng.standard_normal((n, 4))
+        Hb = 0.02 * (Bm @ Bm.T)
+    else:
+        Hb = np.zeros((n, n))
+    pes = QuadraticPES(x0, g0, Ht, Hb, rng)
+    opt = rs.RSIRFO(method=method, saddle_order=so, element_list=["C"] * natoms,
+                    trust_radius_max=(0.1 if so > 0 else 0.5), trust_radius_min=0.01)
+    if neb:
+        opt.switch_NEB_mode()
+    opt.set_hessian(H0.copy())
+    opt.set_bias_hessian(Hb.copy())
+    rec = {k: [] for k in ("x", "Bg", "g", "Be", "move", "H_after", "trust", "pred")}
+    x = x0.copy()
+    x_prev = g_prev = None
+    for k in range(nsteps):
+        e, g = pes.raw(x)
+        eb, gb = pes.bias(x)
+        Be, Bg = e + eb, g + gb
+        col = lambda a: a.reshape(-1, 1).copy()
+        with quiet():
+            if x_prev is None:
+                mv = opt.run(col(x), col(Bg), [], [], Be, 0.0, [], col(x0), col(g), [])
+            else:
+                mv = opt.run(col(x), col(Bg), [], col(x_prev), Be, 0.0, [], col(x0), col(g), col(g_prev))
+        mv = np.asarray(mv, float).ravel()
+        rec["x"].append(x.copy()); rec["Bg"].append(Bg); rec["g"].append(g); rec["Be"].append(Be)
+        rec["move"].append(mv); rec["H_after"].append(np.array(opt.hessian, float))
+        rec["trust"].append(float(opt.trust_radius)); rec["pred"].append(float(opt.predicted_energy_changes[-1]))
+        x_prev, g_prev = x.copy(), g.copy()
+        step_cap = 0.1 if so > 0 else 0.5           # caller clamp, optimizer.py:792
+        nrm = np.linalg.norm(mv)
+        x = x - (mv * (step_cap / nrm) if nrm > step_cap else mv)
+    out = {f"{name}/{k}": np.array(v) for k, v in rec.items()}
+    out[f"{name}/H0"] = H0
+    out[f"{name}/Hb"] = Hb
+    out[f"{name}/meta"] = np.array([so, natoms, nsteps, int(bias), int(neb)], np.int64)
+    out[f"{name}/method"] = np.array(method)
+    return out
+
+
+def gen_rsirfo():
+    blob = {}
+    for case in RSIRFO_CASES:
+        blob.update(run_rsirfo_case(case))
+        print("rsirfo case", case[0])
+    blob["names"] = np.array([c[0] for c in RSIRFO_CASES])
+    np.savez_compressed(os.path.join(GOLD, "rsirfo_traces.npz"), **blob)
+
+
+def gen_projection():
+    """TR/ROT projection of gradient and Hessian (calc_tools.py:249, rsirfo.py:128)."""
+    rs = ref_shim.ref("Optimizer.rsirfo")
+    ct = ref_shim.ref("Utils.calc_tools")
+    xs, Hs, gs, Hps, gps = [], [], [], [], []
+    for seed, natoms in enumerate([3, 5, 8, 11]):
+        rng = np.random.default_rng(9100 + seed)
+        n = 3 * natoms
+        x = synthetic.grid_geometry(natoms, rng).reshape(-1)
+        H = synthetic.spd_hessian(n, rng)
+        g = rng.standard_normal(n)
+        opt = rs.RSIRFO(method="rsirfo_bfgs", saddle_order=0)
+        gp = opt._project_grad_tr_rot(g.copy(), x.reshape(-1, 1).copy())
+        Hp = ct.Calculationtools().project_out_hess_tr_and_rot_for_coord(
+            H.copy(), x.reshape(-1, 3).copy(), x.reshape(-1, 3).copy(), False)
+        pad = 33 - n
+        xs.append(np.pad(x, (0, pad))); gs.append(np.pad(g, (0, pad))); gps.append(np.pad(gp, (0, pad)))
+        Hs.append(np.pad(H, ((0, pad), (0, pad)))); Hps.append(np.pad(Hp, ((0, pad), (0, pad))))
+    np.savez_compressed(os.path.join(GOLD, "projection.npz"), natoms=np.array([3, 5, 8, 11]),
+                        x=np.stack(xs), H=np.stack(Hs), g=np.stack(gs), Hp=np.stack(Hps), gp=np.stack(gps))
+    print("projection: 4 cases")
+
+
+SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection}
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or list(SETS)
+    for w in which:
+        SETS[w]()

@@ -1,0 +1,747 @@
+"""NumPy restatement of the reference optimizer-step hot path (CPU oracle).
+
+TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.  Never imported by the
+product path.  Parity status: PINNED against outputs of the unmodified
+reference (``tests/golden/*.npz`` produced by ``oracle/gen_golden.py``).
+
+Every function cites the reference file:line it follows (paths relative to
+``/root/reference/multioptpy``).  Third-party arithmetic the reference calls
+and which is therefore also called here: ``numpy.linalg.eigh`` / ``qr``
+(LAPACK; reference pins numpy~=2.2, this image has 2.3) and
+``scipy.optimize.brentq`` (reference pins scipy~=1.13, image has 1.18).
+
+All arrays are float64, flat ``(n,)`` vectors and ``(n, n)`` row-major
+matrices, ``n = 3 * natoms``; geometry is in Bohr.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# Hessian-update method ids — shared with include/mop_b200.h (MOP_UPD_*).
+# Order = the prioritised substring list of Optimizer/rsirfo.py:208-251.
+# --------------------------------------------------------------------------
+UPDATE_DISPATCH = [
+    ("flowchart", 1),
+    ("block_cfd_fsb_dd", 2),
+    ("block_cfd_fsb_weighted", 3),
+    ("block_cfd_fsb", 4),
+    ("block_cfd_bofill_weighted", 5),
+    ("block_cfd_bofill", 6),
+    ("block_bfgs_dd", 7),
+    ("block_bfgs", 8),
+    ("block_fsb_dd", 9),
+    ("block_fsb_weighted", 10),
+    ("block_fsb", 11),
+    ("block_bofill_weighted", 12),
+    ("block_bofill", 13),
+    ("bfgs_dd", 14),
+    ("bfgs", 15),
+    ("sr1", 16),
+    ("pcfd_bofill", 17),
+    ("cfd_fsb_dd", 18),
+    ("cfd_fsb", 19),
+    ("cfd_bofill", 20),
+    ("fsb_dd", 21),
+    ("fsb", 22),
+    ("bofill", 23),
+    ("psb", 24),
+    ("msp", 25),
+]
+UPD_NONE = 0
+UPD_FLOWCHART = 1
+UPDATE_NAMES = {mid: key for key, mid in UPDATE_DISPATCH}
+
+
+def resolve_update_method(name: str) -> int:
+    """First substring hit in priority order, else the 'auto' flowchart
+    (Optimizer/rsirfo.py:1341-1356)."""
+    low = name.lower()
+    for key, mid in UPDATE_DISPATCH:
+        if key in low:
+            return mid
+    return UPD_FLOWCHART
+
+
+TAU = 1e-10        # ModelHessianUpdate.denom_threshold (hessian_update.py:25)
+TAU_BLOCK = 1e-12  # BlockHessianUpdate.denom_threshold (block_hessian_update.py:24)
+
+
+def _outer(a, b):
+    return np.outer(a, b)
+
+
+def _bfgs(H, s, y, u):
+    """hessian_update.py:35-65.  (Hs) s^T H^T == u u^T."""
+    n = s.size
+    d = np.zeros((n, n))
+    sy = s @ y
+    if abs(sy) >= TAU:
+        d = d + _outer(y, y) / sy
+    shs = s @ u
+    if abs(shs) >= TAU:
+        d = d - _outer(u, u) / shs
+    return d
+
+
+def _sr1(A, s):
+    """hessian_update.py:67-85."""
+    den = A @ s
+    if abs(den) >= TAU:
+        return _outer(A, A) / den
+    return np.zeros((s.size, s.size))
+
+
+def _psb(s, y, u):
+    """hessian_update.py:87-104 (always uses r = y - Hs, never the CFD factor)."""
+    r = y - u
+    ss = s @ s
+    if abs(ss) >= TAU:
+        return -(r @ s) * _outer(s, s) / ss ** 2 + (_outer(r, s) + _outer(s, r)) / ss
+    return np.zeros((s.size, s.size))
+
+
+def _phi2(A, s):
+    """hessian_update.py:106-130."""
+    num = (A @ s) * (A @ s)
+    den = (A @ A) * (s @ s)
+    return num / den if abs(den) >= TAU else 0.0
+
+
+def _dd(s, y, thr):
+    """Powell damping with B = I ("double damping step 2"),
+    hessian_update.py:200-242 / block_hessian_update.py:565-595."""
+    sy = s @ y
+    ss = s @ s
+    if sy < 0.2 * ss:
+        den = ss - sy
+        theta = 0.1 if abs(den) < thr else 0.8 * ss / den
+        theta = min(1.0, max(0.0, theta))
+        y = theta * y + (1.0 - theta) * s
+    return y
+
+
+def _symm(A):
+    return 0.5 * (A + A.T)
+
+
+def _inv1(x, reg=1e-10):
+    """1x1 numpy.linalg.inv with the safe_inv fallback
+    (block_hessian_update.py:12-21): singular only when exactly zero."""
+    if x == 0.0:
+        return 1.0 / (x + reg)
+    return 1.0 / x
+
+
+def _blk_bfgs(B, s, y, u, curvature_guard=True):
+    """block_hessian_update.py:75-118 with q = 1 (history is popped every call,
+    :447-450).  Returns the updated matrix."""
+    if not (np.linalg.norm(s) > 1e-8):
+        return B.copy()
+    if curvature_guard and (y @ s) <= TAU_BLOCK:
+        return B.copy()
+    t1 = _outer(u, u) * _inv1(s @ u)
+    t2 = _outer(y, y) * _inv1(s @ y)
+    return _symm(B - t1 + t2)
+
+
+def _blk_sr1(B, s, y, u, c):
+    """block_hessian_update.py:159-184 with q = 1."""
+    R = c * (y - u)
+    return _symm(B + _outer(R, R) * _inv1(s @ R))
+
+
+def _blk_psb(B, s, y, u, thr=1e-8):
+    """block_hessian_update.py:120-157 with q = 1."""
+    if not (np.linalg.norm(s) > thr):
+        return B.copy()
+    ss = float(s @ s)
+    if abs(ss) >= thr:
+        r = y - u
+        return B + (-(r @ s) * _outer(s, s) / ss ** 2 + (_outer(r, s) + _outer(s, r)) / ss)
+    return B.copy()
+
+
+def _blk_weight(s, y, u, cfd):
+    """block_hessian_update.py:190-231 with q = 1 -> phi^2 clipped to [0, 1]."""
+    A = y - u
+    if cfd:
+        A = 2.0 * A
+    num = (A @ s) ** 2
+    den = (A @ A) * (s @ s)
+    c = num / den if abs(den) > TAU_BLOCK else 0.0
+    if math.isnan(c):
+        c = 0.0
+    return float(max(0.0, min(1.0, c)))
+
+
+def hessian_update_delta(method: int, H: np.ndarray, s: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """Delta-Hessian of every supported update (the operator contract
+    ``f(hess, displacement, delta_grad) -> delta_hess`` of
+    Optimizer/hessian_update.py:248-433 and block_hessian_update.py:443-709)."""
+    n = s.size
+    u = H @ s
+    if method == 1:  # flowchart, hessian_update.py:163-194 (z = y - H y, sic)
+        z = y - H @ y
+        zs_den = np.linalg.norm(s) * np.linalg.norm(z)
+        if abs(zs_den) < TAU:
+            zs_den += TAU
+        zs = (z @ s) / zs_den
+        ys_den = np.linalg.norm(s) * np.linalg.norm(y)
+        if abs(ys_den) < TAU:
+            ys_den += TAU
+        ys = (y @ s) / ys_den
+        if zs < -0.1:
+            return hessian_update_delta(16, H, s, y)
+        if ys > 0.1:
+            return hessian_update_delta(15, H, s, y)
+        return hessian_update_delta(22, H, s, y)
+    if method in (14, 15):  # bfgs(_dd)
+        if method == 14:
+            y = _dd(s, y, TAU)
+        return _bfgs(H, s, y, u)
+    if method == 16:
+        return _sr1(y - u, s)
+    if method == 24:
+        return _psb(s, y, u)
+    if method in (18, 19, 21, 22):  # (cfd_)fsb(_dd)
+        if method in (18, 21):
+            y = _dd(s, y, TAU)
+        c = 2.0 if method in (18, 19) else 1.0
+        A = c * (y - u)
+        phi = math.sqrt(_phi2(A, s))
+        return (1.0 - phi) * _bfgs(H, s, y, u) + phi * _sr1(A, s)
+    if method in (20, 23):  # (cfd_)bofill
+        c = 2.0 if method == 20 else 1.0
+        A = c * (y - u)
+        p2 = _phi2(A, s)
+        return (1.0 - p2) * _psb(s, y, u) + p2 * _sr1(A, s)
+    if method == 25:  # msp, hessian_update.py:345-368
+        A = y - u
+        den = np.linalg.norm(A) * np.linalg.norm(s)
+        arg = 0.0
+        if den >= TAU:
+            arg = min(1.0, max(-1.0, (s @ A) / den))
+        phi = 1.0 - arg ** 2
+        return phi * _psb(s, y, u) + (1.0 - phi) * _sr1(A, s)
+    # ---- block family (q = 1) -------------------------------------------
+    B = H
+    if method == 8:
+        return _blk_bfgs(B, s, y, u) - B
+    if method == 7:  # block_bfgs_dd: rank guard, damping, no curvature guard (:619-641)
+        if not (np.linalg.norm(s) > 1e-8):
+            return np.zeros((n, n))
+        yt = _dd(s, y, TAU_BLOCK)
+        return _blk_bfgs(B, s, yt, u, curvature_guard=False) - B
+    if method in (11, 9, 4, 2):  # block_fsb / _dd / block_cfd_fsb / _dd
+        if method in (9, 2):
+            y = _dd(s, y, TAU_BLOCK)
+        cfd = method in (4, 2)
+        d_sr1 = _blk_sr1(B, s, y, u, 2.0 if cfd else 1.0) - B
+        d_bfgs = _blk_bfgs(B, s, y, u) - B
+        c = _blk_weight(s, y, u, cfd)
+        w = c if cfd else math.sqrt(c)  # CFD-FSB uses c, FSB sqrt(c) (:249-251,:269-271)
+        return _symm(B + w * d_sr1 + (1.0 - w) * d_bfgs) - B
+    if method in (13, 6):  # block_bofill / block_cfd_bofill
+        cfd = method == 6
+        d_psb = _blk_psb(B, s, y, u) - B
+        d_sr1 = _blk_sr1(B, s, y, u, 2.0 if cfd else 1.0) - B
+        w = _blk_weight(s, y, u, cfd)
+        return _symm(B + w * d_sr1 + (1.0 - w) * d_psb) - B
+    if method in (10, 3, 12, 5):  # "weighted subspace" variants (:319-437)
+        cfd = method in (3, 5)
+        c = _blk_weight(s, y, u, cfd)
+        w = c if (cfd or method in (12, 5)) else math.sqrt(c)
+        d_sr1 = _blk_sr1(B, w * s, w * y, w * u, 2.0 if cfd else 1.0) - B
+        a = 1.0 - w
+        if method in (10, 3):
+            d_other = _blk_bfgs(B, a * s, a * y, a * u) - B
+        else:
+            d_other = _blk_psb(B, a * s, a * y, a * u) - B
+        return _symm(B + d_sr1 + d_other) - B
+    raise NotImplementedError(f"update method id {method} ({UPDATE_NAMES.get(method)})")
+
+
+def rsirfo_update_hessian(H, x, g, x_prev, g_prev, method: int):
+    """RSIRFO.update_hessian, Optimizer/rsirfo.py:1316-1372.
+    Returns (H_new, updated: bool).  H_new is symmetrised only when updated."""
+    s = (x - x_prev).ravel()
+    y = (g - g_prev).ravel()
+    if np.linalg.norm(s) < 1e-10 or np.linalg.norm(y) < 1e-10:
+        return H, False
+    if (s @ y) <= 0:
+        return H, False
+    Hn = H + hessian_update_delta(method, H, s, y)
+    return 0.5 * (Hn + Hn.T), True
+
+
+# --------------------------------------------------------------------------
+# translation / rotation projection
+# --------------------------------------------------------------------------
+def trrot_vectors(x):
+    """Six un-normalised TR/ROT vectors about the plain mean of the coordinates
+    (Utils/calc_tools.py:261-288, Optimizer/rsirfo.py:134-167)."""
+    c = x.reshape(-1, 3)
+    c = c - _plain_mean(c)
+    N = c.shape[0]
+    v = np.zeros((6, 3 * N))
+    for k in range(3):
+        v[k, k::3] = 1.0
+    v[3, 1::3] = -c[:, 2]
+    v[3, 2::3] = c[:, 1]
+    v[4, 0::3] = c[:, 2]
+    v[4, 2::3] = -c[:, 0]
+    v[5, 0::3] = -c[:, 1]
+    v[5, 1::3] = c[:, 0]
+    return v
+
+
+def _plain_mean(c):
+    """calc_center: sequential sum then divide (Utils/calc_tools.py:138-145)."""
+    acc = np.zeros(3)
+    for row in c:
+        acc = acc + row
+    return acc / c.shape[0]
+
+
+def gram_schmidt_cgs(vectors, drop=1e-10):
+    """Classical Gram-Schmidt with drop threshold (Utils/calc_tools.py:250-259):
+    projections use the ORIGINAL vector v, not the running w."""
+    basis = []
+    for v in vectors:
+        w = v.copy()
+        for b in basis:
+            w = w - (v @ b) * b
+        nrm = np.linalg.norm(w)
+        if nrm > drop:
+            basis.append(w / nrm)
+    return np.array(basis)
+
+
+def project_hessian_trrot(H, x):
+    """Calculationtools.project_out_hess_tr_and_rot_for_coord,
+    Utils/calc_tools.py:249-304 (dense P^T H P, then symmetrise)."""
+    T = gram_schmidt_cgs(trrot_vectors(x))
+    n = H.shape[0]
+    P = np.eye(n)
+    for t in T:
+        P = P - np.outer(t, t)
+    Hp = P.T @ H @ P
+    return (Hp + Hp.T) / 2
+
+
+def project_grad_trrot(g, x):
+    """RSIRFO._project_grad_tr_rot, Optimizer/rsirfo.py:128-190 (reduced QR)."""
+    A = trrot_vectors(x).T
+    Q, _ = np.linalg.qr(A, mode="reduced")
+    return g - Q @ (Q.T @ g)
+
+
+# --------------------------------------------------------------------------
+# eigendecomposition with conditional level shift
+# --------------------------------------------------------------------------
+def hessian_is_ill_conditioned(lam, thresh=1e8):
+    """check_hessian_conditioning, Optimizer/rsirfo.py:492-551 -> bool."""
+    if lam.size < 2:
+        return False
+    nz = lam[np.abs(lam) > 1e-10]
+    if nz.size < 2:
+        return True
+    mx = np.max(np.abs(nz))
+    mn = np.min(np.abs(nz))
+    if mn < 1e-15:
+        return True
+    return (mx / mn) > thresh
+
+
+def eigh_with_shift(H, shift=1e-5):
+    """compute_eigendecomposition_with_shift (auto_level_shift=True default),
+    Optimizer/rsirfo.py:553-657.  Returns (lam, V, shifted: bool)."""
+    lam, V = np.linalg.eigh(H)
+    if hessian_is_ill_conditioned(lam):
+        lam_s, V = np.linalg.eigh(H + shift * np.eye(H.shape[0]))
+        return lam_s - shift, V, True
+    return lam, V, False
+
+
+# --------------------------------------------------------------------------
+# RFO secular equation
+# --------------------------------------------------------------------------
+def _f_secular(lmd, lam_p, g2):
+    den = lam_p - lmd
+    safe = np.where(np.abs(den) < 1e-30, np.sign(den) * 1e-30, den)
+    safe[safe == 0] = 1e-30
+    return lmd + np.sum(g2 / safe)
+
+
+def _fp_secular(lmd, lam_p, g2):
+    den = lam_p - lmd
+    safe = np.where(np.abs(den) < 1e-30, np.sign(den) * 1e-30, den)
+    safe[safe == 0] = 1e-30
+    return 1.0 + np.sum(g2 / safe ** 2)
+
+
+def secular_safeguarded(lam_p, g2, pole, guess):
+    """_solve_secular_safeguarded, Optimizer/rsirfo.py:1374-1503."""
+    b = pole
+    a = guess
+    fa = _f_secular(a, lam_p, g2)
+    gnorm = math.sqrt(np.sum(g2))
+    limit = 10
+    while fa > 0 and limit > 0:
+        a = a - max(gnorm, abs(a) * 0.1, 1e-8)
+        fa = _f_secular(a, lam_p, g2)
+        limit -= 1
+    if fa > 0:
+        return guess
+    lk = guess
+    if lk <= a or lk >= b:
+        lk = (a + b) / 2.0
+    tol = 1e-10 * abs(pole) + 1e-12
+    for _ in range(250):
+        f = _f_secular(lk, lam_p, g2)
+        if abs(f) < tol:
+            return lk
+        fp = _fp_secular(lk, lam_p, g2)
+        dn = -f / fp if abs(fp) > 1e-20 else 0.0
+        ln = lk + dn
+        lb = (a + b) / 2.0
+        nxt = ln if (dn != 0.0 and a < ln < b) else lb
+        if f > 0:
+            b = lk
+        else:
+            a = lk
+        lk = nxt
+        if abs(b - a) < tol:
+            return (a + b) / 2.0
+    return (a + b) / 2.0
+
+
+def secular_root(lam, gam, alpha):
+    """_solve_secular_more_sorensen, Optimizer/rsirfo.py:1505-1575 (the code
+    after the first ``return`` at :1575 is only reached on an exception)."""
+    lam_p = lam / alpha
+    gp = gam / alpha
+    g2 = gp ** 2
+    pole = None
+    gsum = 0.0
+    for i in range(lam_p.size):
+        gsum += g2[i]
+        if pole is None and g2[i] > 1e-20:
+            pole = lam_p[i]
+    if pole is None:
+        return lam_p[0]
+    guess = 0.5 * (pole - math.sqrt(max(0.0, pole ** 2 + 4 * gsum)))
+    return secular_safeguarded(lam_p, g2, pole, guess)
+
+
+def solve_rfo(lam, gam, alpha):
+    """RSIRFO.solve_rfo, Optimizer/rsirfo.py:1688-1715 -> (step, lambda_aug)."""
+    mu = secular_root(lam, gam, alpha)
+    den = lam / alpha - mu
+    safe = np.where(np.abs(den) < 1e-20, np.sign(den) * 1e-20, den)
+    safe[safe == 0] = 1e-20
+    return -(gam / alpha) / safe, mu
+
+
+def step_derivative(alpha, lam, gam, mu):
+    """get_step_derivative, Optimizer/rsirfo.py:1250-1313."""
+    den = lam - mu * alpha
+    small = np.abs(den) < 1e-8
+    if np.any(small):
+        den = den.copy()
+        den[small] = np.sign(den[small]) * np.maximum(1e-8, np.abs(den[small]))
+        # (:1275-1277 writes to a temporary: exact zeros stay zero)
+    num = gam ** 2
+    d3 = den ** 3
+    valid = np.abs(d3) > 1e-10
+    if not np.any(valid):
+        return 1e-8
+    terms = np.zeros_like(num)
+    terms[valid] = num[valid] / d3[valid]
+    big = np.abs(terms) > 1e20
+    if np.any(big):
+        terms[big] = np.sign(terms[big]) * 1e20
+    d = 2.0 * mu * np.sum(terms)
+    if not np.isfinite(d) or abs(d) > 1e20:
+        d = np.sign(d) * 1e20 if d != 0 else 1e-8
+    return d
+
+
+def alpha_search(lam, gam, trust, alpha0=1.0, alpha_max=1000.0, alpha_step_max=10.0,
+                 max_micro=40, step_tol=1e-3):
+    """compute_rsprfo_step, Optimizer/rsirfo.py:986-1248.  Because solve_rfo
+    scales eigenvalues AND gradient by 1/alpha the step does not depend on
+    alpha analytically; the loop is restated iteration for
+    iteration because its exit decides which (rounding-different) step is
+    returned.  Returns (step, info) with info in {'brent','newton'}."""
+    r2 = trust ** 2
+    alpha = alpha0
+    try:
+        s_lo, _ = solve_rfo(lam, gam, 1e-6)
+        s_hi, _ = solve_rfo(lam, gam, alpha_max)
+        o_lo = np.linalg.norm(s_lo) ** 2 - r2
+        o_hi = np.linalg.norm(s_hi) ** 2 - r2
+        if o_lo * o_hi < 0:
+            from scipy.optimize import brentq
+
+            def obj(a):
+                st, _ = solve_rfo(lam, gam, a)
+                return st @ st - r2
+
+            a_b = brentq(obj, 1e-6, alpha_max, xtol=1e-6, rtol=1e-6, maxiter=50)
+            st, _ = solve_rfo(lam, gam, a_b)
+            if abs(np.linalg.norm(st) - trust) < step_tol:
+                return st, "brent"
+            alpha = a_b
+    except Exception:
+        alpha = alpha0
+    hist = []
+    best = None
+    best_diff = float("inf")
+    a_left = a_right = None
+    step = None
+    for _mu in range(max_micro):
+        step, mu_aug = solve_rfo(lam, gam, alpha)
+        nrm = np.linalg.norm(step)
+        diff = abs(nrm - trust)
+        if diff < best_diff:
+            best = step.copy()
+            best_diff = diff
+        obj = nrm ** 2 - r2
+        if obj < 0 and (a_left is None or alpha > a_left):
+            a_left = alpha
+        elif obj > 0 and (a_right is None or alpha < a_right):
+            a_right = alpha
+        if abs(obj) < 1e-8 or diff < step_tol:
+            return step, "newton"
+        hist.append(nrm)
+        d = step_derivative(alpha, lam, gam, mu_aug)
+        if abs(d) < 1e-10:
+            if a_left is not None and a_right is not None:
+                a_new = (a_left + a_right) / 2
+            elif obj > 0:
+                a_new = max(alpha / 2, 1e-6)
+            else:
+                a_new = min(alpha * 2, alpha_max)
+        else:
+            a_step = min(alpha_step_max, max(-alpha_step_max, -obj / d))
+            a_new = alpha + a_step
+            if a_left is not None and a_right is not None:
+                a_new = max(min(a_new, a_right * 0.99), a_left * 1.01)
+        alpha = min(max(a_new, 1e-6), alpha_max)
+        if alpha == alpha_max or alpha == 1e-6:
+            return step, "newton"
+        if len(hist) >= 3 and abs(hist[-1] - hist[-2]) < 1e-6 and abs(hist[-2] - hist[-3]) < 1e-6:
+            return step, "newton"
+    # micro-cycles exhausted (:1213-1246)
+    if best is not None and abs(np.linalg.norm(best) - trust) < step_tol * 1.1:
+        return best, "newton"
+    sd = -gam
+    nrm = np.linalg.norm(sd)
+    sd = sd / nrm * trust if nrm > 1e-10 else np.zeros_like(gam)
+    return sd, "newton"
+
+
+def rs_step(lam, V, g, trust):
+    """RSIRFO.get_rs_step, Optimizer/rsirfo.py:924-985 (no-exception path)."""
+    gam = V.T @ g
+    step0, _ = solve_rfo(lam, gam, 1.0)
+    if np.linalg.norm(step0) <= trust:
+        return V @ step0, False
+    step, _ = alpha_search(lam, gam, trust)
+    return V @ step, True
+
+
+# --------------------------------------------------------------------------
+# inner trust radius of RSIRFO (state only)
+# --------------------------------------------------------------------------
+def adjust_trust_radius(trust, actual, predicted, min_eig, gnorm, saddle_order,
+                        trust_min, trust_max):
+    """RSIRFO.adjust_trust_radius(+_adaptive), Optimizer/rsirfo.py:660-887."""
+    if gnorm < 1e-2:  # adaptive rule (:835)
+        if abs(predicted) < 1e-10:
+            return trust
+        ratio = actual / predicted
+        a = abs(min_eig)
+        cf = min(2.5, 1.0 / max(a, 0.1)) if a > 1e-6 else 1.5
+        if saddle_order > 0 and min_eig < -1e-6:
+            cf *= 0.8
+        if ratio > 0.75:
+            trust = min(trust * min(1.5 * cf, 2.5), trust_max)
+        elif ratio > 0.5:
+            trust = min(trust * min(1.1 * cf, 1.5), trust_max)
+        elif ratio > 0.25:
+            if cf > 1.2:
+                trust = min(trust * 1.05, trust_max)
+        elif ratio > 0.1:
+            trust = max(trust * 0.5, trust_min)
+        else:
+            trust = max(trust * 0.25, trust_min)
+        return float(min(max(trust, trust_min), trust_max))
+    if abs(predicted) < 1e-10:
+        return trust
+    ratio = actual / predicted
+    if ratio > 0.75:
+        trust = min(trust * 1.2, trust_max)
+    elif ratio < 0.25:
+        trust = max(trust * 0.5, trust_min)
+    return trust
+
+
+class RSIRFOOracle:
+    """State + ``run`` of the reference RSIRFO (Optimizer/rsirfo.py:9-490) for
+    ONE structure, default configuration as constructed by
+    CalculateMoveVector.initialization (optimizer.py:452-453)."""
+
+    def __init__(self, method="rsirfo_bofill", saddle_order=0, trust_radius_max=None,
+                 trust_radius_min=0.01, **_):
+        self.method_id = resolve_update_method(method)
+        self.saddle_order = saddle_order
+        default = 0.5 if saddle_order == 0 else 0.1
+        self.trust_radius = default                      # (:36-43)
+        self.trust_radius_max = default if trust_radius_max is None else trust_radius_max
+        self.trust_radius_min = 0.01 if trust_radius_min is None else trust_radius_min
+        self.hessian = None
+        self.bias_hessian = None
+        self.have_prev = False
+        self.prev_energy = None
+        self.pred = []
+        self.act = []
+        self.NEB_mode = False
+        self.iteration = 0
+        self.last = {}
+
+    def set_hessian(self, H):
+        self.hessian = H
+
+    def set_bias_hessian(self, H):
+        self.bias_hessian = H
+
+    def run(self, x, Bg, g, x_prev=None, g_prev=None, Be=0.0):
+        """Returns the reference's return value (= minus the RFO step, (n,))."""
+        x = np.asarray(x, float).ravel()
+        Bg = np.asarray(Bg, float).ravel()
+        g = np.asarray(g, float).ravel()
+        info = {"updated": False, "shift1": False, "shift2": False, "alpha_search": False,
+                "nan_fallback": False}
+        if self.have_prev and x_prev is not None and g_prev is not None and len(x_prev) > 0 and len(g_prev) > 0:
+            self.hessian, info["updated"] = rsirfo_update_hessian(
+                self.hessian, x, g, np.asarray(x_prev, float).ravel(), np.asarray(g_prev, float).ravel(),
+                self.method_id)
+        gnorm = np.linalg.norm(Bg)
+        gp = project_grad_trrot(Bg, x)
+        Hsum = self.hessian + self.bias_hessian if self.bias_hessian is not None else self.hessian
+        Hp = project_hessian_trrot(Hsum, x)
+        Hp = 0.5 * (Hp + Hp.T)
+        lam, V, info["shift1"] = eigh_with_shift(Hp)
+        if not (np.all(np.isfinite(lam)) and np.all(np.isfinite(V))):
+            lam = np.ones_like(lam)
+            V = np.eye(lam.size)
+        if self.prev_energy is not None:                   # (:381-398)
+            actual = Be - self.prev_energy
+            if len(self.act) >= 3:
+                self.act.pop(0)
+            self.act.append(actual)
+            if self.pred:
+                self.trust_radius = adjust_trust_radius(
+                    self.trust_radius, actual, self.pred[-1], lam[0], gnorm, self.saddle_order,
+                    self.trust_radius_min, self.trust_radius_max)
+        n = lam.size
+        P = np.eye(n)                                       # (:408-421)
+        found = 0
+        i = 0
+        while found < self.saddle_order:
+            if abs(lam[i]) > 1e-10:
+                f = 1.0 if self.NEB_mode else 2.0
+                P = P - f * np.outer(V[:, i], V[:, i])
+                found += 1
+            i += 1
+        Hs = P @ Hp
+        Hs = 0.5 * (Hs + Hs.T)
+        gs = P @ gp
+        lam_s, V_s, info["shift2"] = eigh_with_shift(Hs)
+        if not (np.all(np.isfinite(lam_s)) and np.all(np.isfinite(V_s))):
+            lam_s = np.ones_like(lam_s)
+            V_s = np.eye(lam_s.size)
+        keep = ~(np.abs(lam_s) < 1e-6)                      # (:265-283)
+        lam_k = lam_s[keep]
+        V_k = V_s[:, keep]
+        step, info["alpha_search"] = rs_step(lam_k, V_k, gs, self.trust_radius)
+        if not np.all(np.isfinite(step)):                   # (:456-462)
+            info["nan_fallback"] = True
+            step = -gp
+            nrm = np.linalg.norm(step)
+            if nrm > self.trust_radius:
+                step = step * (self.trust_radius / nrm)
+        pred = gp @ step + 0.5 * (step @ Hp @ step)         # (:469, :1717-1720)
+        if len(self.pred) >= 3:
+            self.pred.pop(0)
+        self.pred.append(pred)
+        self.have_prev = True
+        self.prev_energy = Be
+        self.iteration += 1
+        info.update(eigvals=lam, pred=pred, trust=self.trust_radius, gproj=gp, Hproj=Hp)
+        self.last = info
+        return -step
+
+
+# --------------------------------------------------------------------------
+# caller side: CalculateMoveVector.calc_move_vector + TrustRadius
+# --------------------------------------------------------------------------
+BOHR2ANG = 0.52917721067  # Parameters/unit_values.py:26
+
+
+def clamp_and_move(x, move, trust_outer):
+    """optimizer.py:792-798,812 -> (new_geometry[Angstrom], move[Bohr])."""
+    nrm = np.linalg.norm(move)
+    if nrm > trust_outer:
+        move = trust_outer * move / nrm
+    return (x - move) * BOHR2ANG, move
+
+
+class TrustRadiusOracle:
+    """Optimizer/trust_radius.py:120-206 (composite outer trust radius)."""
+
+    def __init__(self, min_trust_radius=0.01, max_trust_radius=0.5):
+        self.min = min_trust_radius
+        self.max = max_trust_radius
+        self.ratios = []
+        self.changes = []
+        self.count = 0
+
+    def _adaptive_factor(self):
+        if not self.ratios:
+            return 2.0
+        rec = self.ratios[-min(5, len(self.ratios)):]
+        var = float(np.var(rec)) if len(rec) > 1 else 0.0
+        f = 2.0 * math.exp(-var)
+        if len(self.changes) >= 2:
+            ch = np.abs(self.changes[-min(3, len(self.changes)):])
+            if np.all(ch < 0.01) and np.mean(ch) < 0.005:
+                f *= 0.8
+        return max(1.1, min(f, 3.0))
+
+    def update(self, Be, pre_Be, pre_Bg, pre_move, H, trust):
+        if self.count == 0:
+            self.count += 1
+            return trust
+        Ce = float(pre_Bg @ pre_move + 0.5 * (pre_move @ H @ pre_move))
+        eps = 1e-8
+        if abs(Ce) < eps:
+            Ce += np.sign(Ce) * eps
+            if abs(Ce) < eps:
+                Ce = eps
+        r = (pre_Be - Be) / Ce
+        self.ratios.append(float(r))
+        self.changes.append(float(pre_Be - Be))
+        f = self._adaptive_factor()
+        if r <= 0.25 or r >= 1.75:
+            trust /= f
+        elif 0.75 <= r <= 1.25:
+            if abs(np.linalg.norm(pre_move) - trust) < eps:
+                trust *= f ** 0.5
+        self.count += 1
+        return float(np.clip(trust, self.min, self.max))
