@@ -1,0 +1,165 @@
+/*
+ * mop_b200.h — C ABI of the B200-native optimizer-step hot path.
+ *
+ * Drop-in boundary for the per-structure optimizer step of ss0832/MultiOptPy
+ * (pure Python; it has no FFI of its own, so every entry point names the
+ * Python method(s) it replaces, paths relative to multioptpy/ in the
+ * reference tree).  INTEGRATION.md shows the ctypes stubs a maintainer adds.
+ *
+ * Conventions
+ *  - every pointer is a CALLER-OWNED DEVICE pointer (cudaMalloc / torch CUDA
+ *    tensor) unless marked "host"; the library allocates nothing and keeps no
+ *    global state, so calls are thread-safe and CUDA-graph capturable;
+ *  - FP64 everywhere, row-major, batch-major: H is [B][n][n], vectors [B][n],
+ *    n = 3 * natoms, geometry in Bohr, energies in Hartree;
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*,
+ *    NULL = legacy default stream);
+ *  - return value: MOP_OK or a negative MOP_ERR_*; never throws.
+ *    mop_last_error() (host, thread-local) describes the last failure;
+ *  - data-dependent branches taken per structure are reported in the
+ *    int32 status word (MOP_ST_* bits), [B] on the device.
+ */
+#ifndef MOP_B200_H
+#define MOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOP_VERSION 100
+
+#define MOP_OK 0
+#define MOP_ERR_INVALID (-1)     /* bad argument (null pointer, n <= 0, ...) */
+#define MOP_ERR_CUDA (-2)        /* CUDA runtime error, see mop_last_error() */
+#define MOP_ERR_UNSUPPORTED (-3) /* method / size not implemented on device  */
+#define MOP_ERR_WORKSPACE (-4)   /* work_bytes smaller than *_workspace_bytes */
+
+/* Hessian-update method ids: the prioritised substring table of
+ * Optimizer/rsirfo.py:208-251 (first hit wins; no hit -> FLOWCHART). */
+enum {
+  MOP_UPD_NONE = 0,
+  MOP_UPD_FLOWCHART = 1,
+  MOP_UPD_BLOCK_CFD_FSB_DD = 2,
+  MOP_UPD_BLOCK_CFD_FSB_WEIGHTED = 3,
+  MOP_UPD_BLOCK_CFD_FSB = 4,
+  MOP_UPD_BLOCK_CFD_BOFILL_WEIGHTED = 5,
+  MOP_UPD_BLOCK_CFD_BOFILL = 6,
+  MOP_UPD_BLOCK_BFGS_DD = 7,
+  MOP_UPD_BLOCK_BFGS = 8,
+  MOP_UPD_BLOCK_FSB_DD = 9,
+  MOP_UPD_BLOCK_FSB_WEIGHTED = 10,
+  MOP_UPD_BLOCK_FSB = 11,
+  MOP_UPD_BLOCK_BOFILL_WEIGHTED = 12,
+  MOP_UPD_BLOCK_BOFILL = 13,
+  MOP_UPD_BFGS_DD = 14,
+  MOP_UPD_BFGS = 15,
+  MOP_UPD_SR1 = 16,
+  MOP_UPD_PCFD_BOFILL = 17, /* O(n^4) null-space variant: MOP_ERR_UNSUPPORTED */
+  MOP_UPD_CFD_FSB_DD = 18,
+  MOP_UPD_CFD_FSB = 19,
+  MOP_UPD_CFD_BOFILL = 20,
+  MOP_UPD_FSB_DD = 21,
+  MOP_UPD_FSB = 22,
+  MOP_UPD_BOFILL = 23,
+  MOP_UPD_PSB = 24,
+  MOP_UPD_MSP = 25
+};
+
+/* per-structure status bits */
+#define MOP_ST_UPDATED (1 << 0)         /* Hessian update applied                         */
+#define MOP_ST_UPD_SKIP_SMALL (1 << 1)  /* ||s|| or ||y|| < 1e-10 (rsirfo.py:1326)        */
+#define MOP_ST_UPD_SKIP_CURV (1 << 2)   /* s.y <= 0 (rsirfo.py:1333)                      */
+#define MOP_ST_UPD_TERM_ZEROED (1 << 3) /* a guarded denominator fired, term dropped      */
+#define MOP_ST_LEVEL_SHIFT (1 << 4)     /* kappa > 1e8: +1e-5 level shift (rsirfo.py:618) */
+#define MOP_ST_EIG_NONFINITE (1 << 5)   /* NaN/Inf spectrum -> identity (rsirfo.py:365)   */
+#define MOP_ST_ALPHA_SEARCH (1 << 6)    /* ||step|| > inner trust: alpha loop ran         */
+#define MOP_ST_STEP_NAN_SD (1 << 7)     /* NaN step -> steepest descent (rsirfo.py:456)   */
+#define MOP_ST_HARD_CASE (1 << 8)       /* all gradient components zero (rsirfo.py:1559)  */
+#define MOP_ST_TRROT_RANKDEF (1 << 9)   /* < 6 independent TR/ROT vectors (linear)        */
+#define MOP_ST_BRENT_BRACKET (1 << 10)  /* alpha bracket seen; Brent branch not replayed  */
+#define MOP_ST_EIG_NOCONV (1 << 11)     /* eigensolver hit its sweep / iteration limit    */
+#define MOP_ST_EIG_FALLBACK (1 << 12)   /* robust Jacobi fallback produced the spectrum   */
+#define MOP_ST_NO_HISTORY (1 << 13)     /* first call: no previous point, update skipped  */
+
+/* eigensolver selection */
+#define MOP_EIGH_AUTO 0
+#define MOP_EIGH_JACOBI 1  /* two-sided cyclic Jacobi, matrix resident in shared memory */
+#define MOP_EIGH_TRIDIAG 2 /* Householder tridiagonalisation + bisection + inverse iteration */
+
+/* RSIRFO per-structure state: [B][MOP_RSIRFO_STATE] doubles (RSIRFO attributes
+ * of Optimizer/rsirfo.py:97-112 that survive between run() calls). */
+#define MOP_RSIRFO_STATE 16
+#define MOP_RS_TRUST 0        /* self.trust_radius                          */
+#define MOP_RS_HAVE_PREV 1    /* prev_geometry/prev_gradient set (0/1)      */
+#define MOP_RS_PREV_ENERGY 2  /* self.prev_energy                           */
+#define MOP_RS_HAVE_ENERGY 3  /* prev_energy is not None (0/1)              */
+#define MOP_RS_NPRED 4        /* len(predicted_energy_changes) <= 3         */
+#define MOP_RS_PRED0 5        /* .. 7 : predicted_energy_changes, oldest first */
+#define MOP_RS_NACT 8         /* len(actual_energy_changes) <= 3            */
+#define MOP_RS_ACT0 9         /* .. 11                                      */
+#define MOP_RS_ITER 12        /* self.iteration                             */
+
+int mop_version(void);
+const char* mop_last_error(void);
+
+/* ---- (1) Hessian update ------------------------------------------------
+ * Replaces ModelHessianUpdate.*_hessian_update (Optimizer/hessian_update.py:
+ * 248-433) and BlockHessianUpdate.block_*_hessian_update
+ * (Optimizer/block_hessian_update.py:443-709; history depth is always 1).
+ * mode 0: delta_out[B][n][n] = delta_hess (the operator contract; H untouched)
+ * mode 1: H <- 1/2 ((H + delta) + (H + delta)^T) in place, as
+ *         RSIRFO.update_hessian does (Optimizer/rsirfo.py:1361-1372), with its
+ *         skip rules (:1326,:1333) when rsirfo_guards != 0.
+ * s, y: [B][n] displacement and gradient difference. */
+int mop_hessian_update(int B, int n, int method, int mode, int rsirfo_guards, double* H,
+                       const double* s, const double* y, double* delta_out, int32_t* status,
+                       void* stream);
+
+/* ---- (2a) TR/ROT projection ---------------------------------------------
+ * Replaces Calculationtools.project_out_hess_tr_and_rot_for_coord
+ * (Utils/calc_tools.py:249-316) and RSIRFO._project_grad_tr_rot
+ * (Optimizer/rsirfo.py:128-190).  Hp_out = sym(P^T (H + Hbias) P); Hbias,
+ * g, gp_out may be NULL. */
+int mop_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
+                      const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                      void* stream);
+
+/* ---- (2b) batched symmetric eigensolver -----------------------------------
+ * Replaces numpy.linalg.eigh at Optimizer/rsirfo.py:606,626,652.
+ * evals[B][n] ascending; evecs[B][n][n] with ROW k = eigenvector k. */
+size_t mop_eigh_workspace_bytes(int B, int n, int algo);
+int mop_eigh(int B, int n, int algo, const double* A, double* evals, double* evecs,
+             int32_t* status, void* work, size_t work_bytes, void* stream);
+
+/* ---- (2c) one RS-I-RFO step ---------------------------------------------
+ * Replaces RSIRFO.run (Optimizer/rsirfo.py:285-490): Hessian update from
+ * (x - x_prev, g - g_prev) with RAW gradients, TR/ROT projection of gradient
+ * and Hessian, eigendecomposition with conditional level shift, image
+ * projection for `saddle_order` roots (factor 1 instead of 2 when neb_mode),
+ * small-eigenvalue filter, secular-equation RFO solve, alpha loop when the
+ * step exceeds the inner trust radius, NaN fallbacks, predicted energy change
+ * and inner trust-radius bookkeeping.
+ * move_out[B][n] = the value RSIRFO.run returns (minus the RFO step; the
+ * caller computes x_new = x - move, optimizer.py:798).
+ * x_prev / g_prev may be NULL (no history).  Hbias may be NULL. */
+size_t mop_rsirfo_workspace_bytes(int B, int n, int algo);
+int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode, int eigh_algo,
+                    double trust_min, double trust_max, double* H, const double* Hbias,
+                    const double* x, const double* Bg, const double* g, const double* x_prev,
+                    const double* g_prev, const double* Be, double* state, double* move_out,
+                    double* eigvals_out, double* pred_out, int32_t* status, void* work,
+                    size_t work_bytes, void* stream);
+
+/* ---- caller side: CalculateMoveVector.calc_move_vector clamp -------------
+ * Replaces optimizer.py:792-798,812: scale move to trust_outer[B] if longer,
+ * x_new_ang = (x - move) * 0.52917721067. */
+int mop_clamp_and_move(int B, int n, const double* x, double* move, const double* trust_outer,
+                       double* x_new_ang, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOP_B200_H */

@@ -1,0 +1,63 @@
+"""ctypes binding of libmop_b200.so (the C ABI in include/mop_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or a tensor is not a
+CUDA tensor the call raises.  Build with ``python -m multioptpy_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmop_b200.so")
+
+MOP_OK = 0
+
+
+class MopError(RuntimeError):
+    pass
+
+
+_p = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/mop_b200.h
+SIGNATURES = {
+    "mop_version": (_i, []),
+    "mop_last_error": (C.c_char_p, []),
+    "mop_hessian_update": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "mop_project_trrot": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mop_eigh_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mop_eigh": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "mop_rsirfo_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mop_rsirfo_step": (_i, [_i, _i, _i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                             _p, _p, _p, _p, _sz, _p]),
+    "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MopError(
+            f"{LIB_PATH} not found: the CUDA library is required (no CPU fallback). "
+            "Build it with `python -m multioptpy_b200.build`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != MOP_OK:
+        msg = load().mop_last_error().decode("utf-8", "replace")
+        raise MopError(f"{what or 'mop call'} failed (code {rc}): {msg}")

@@ -1,0 +1,155 @@
+// Host side of the C ABI (include/mop_b200.h): argument checks, workspace
+// carving and kernel sequencing.  No allocation, no synchronisation.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+// launchers implemented next to their kernels
+int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, double* H,
+                              const double* s, const double* y, const double* x, const double* xp,
+                              const double* g, const double* gp, const double* state,
+                              double* delta_out, int32_t* status, cudaStream_t stream);
+int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             cudaStream_t stream);
+size_t mop_jacobi_workspace_bytes(int B, int n);
+int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double* evecs,
+                           int32_t* status, const int32_t* only_flagged, void* work,
+                           size_t work_bytes, cudaStream_t stream);
+size_t mop_tridiag_workspace_bytes(int B, int n);
+int mop_tridiag_supported(int n);
+int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double* evecs,
+                            int32_t* status, void* work, size_t work_bytes, cudaStream_t stream);
+int mop_launch_rfo_step(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
+                        const double* evals, const double* evecs, const double* gp,
+                        const double* Bg, const double* Hp, const double* Be, double* state,
+                        double* move, double* evals_out, double* pred, int32_t* status,
+                        cudaStream_t stream);
+
+static thread_local char g_err[512] = "";
+
+void mop_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int mop_version(void) { return MOP_VERSION; }
+extern "C" const char* mop_last_error(void) { return g_err; }
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int pick_algo(int algo, int n) {
+  if (algo == MOP_EIGH_AUTO) return mop_tridiag_supported(n) ? MOP_EIGH_TRIDIAG : MOP_EIGH_JACOBI;
+  return algo;
+}
+
+static size_t eigh_work_bytes(int B, int n, int algo) {
+  algo = pick_algo(algo, n);
+  size_t jac = align256(mop_jacobi_workspace_bytes(B, n));  // also the fallback of the fast path
+  if (algo == MOP_EIGH_TRIDIAG) return jac + align256(mop_tridiag_workspace_bytes(B, n));
+  return jac;
+}
+
+extern "C" size_t mop_eigh_workspace_bytes(int B, int n, int algo) {
+  if (B <= 0 || n <= 0) return 0;
+  return eigh_work_bytes(B, n, algo);
+}
+
+static int run_eigh(int B, int n, int algo, const double* A, double* evals, double* evecs,
+                    int32_t* status, void* work, size_t work_bytes, cudaStream_t stream) {
+  algo = pick_algo(algo, n);
+  if (work_bytes < eigh_work_bytes(B, n, algo)) {
+    mop_set_error("eigh: workspace too small (%zu < %zu bytes)", work_bytes,
+                  eigh_work_bytes(B, n, algo));
+    return MOP_ERR_WORKSPACE;
+  }
+  const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
+  if (algo == MOP_EIGH_JACOBI)
+    return mop_launch_eigh_jacobi(B, n, A, evals, evecs, status, nullptr, work, jac, stream);
+  if (algo == MOP_EIGH_TRIDIAG) {
+    if (!mop_tridiag_supported(n)) {
+      mop_set_error("eigh: tridiagonal path does not support n = %d", n);
+      return MOP_ERR_UNSUPPORTED;
+    }
+    if (!status) {
+      mop_set_error("eigh: the tridiagonal path needs a status array (fallback flags)");
+      return MOP_ERR_INVALID;
+    }
+    int rc = mop_launch_eigh_tridiag(B, n, A, evals, evecs, status, (char*)work + jac,
+                                     work_bytes - jac, stream);
+    if (rc != MOP_OK) return rc;
+    // robust fallback for structures the fast path flagged (no host sync: CTAs of
+    // unflagged structures exit immediately)
+    return mop_launch_eigh_jacobi(B, n, A, evals, evecs, status, status, work, jac, stream);
+  }
+  mop_set_error("eigh: unknown algorithm id %d", algo);
+  return MOP_ERR_INVALID;
+}
+
+extern "C" int mop_eigh(int B, int n, int algo, const double* A, double* evals, double* evecs,
+                        int32_t* status, void* work, size_t work_bytes, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0, "mop_eigh: B >= 0 and n > 0 required");
+  MOP_REQUIRE(A && evals && evecs && work, "mop_eigh: A, evals, evecs, work must be device pointers");
+  if (B == 0) return MOP_OK;
+  return run_eigh(B, n, algo, A, evals, evecs, status, work, work_bytes, (cudaStream_t)stream);
+}
+
+// workspace of mop_rsirfo_step: Hp | evecs | evals | gp | eigh work
+extern "C" size_t mop_rsirfo_workspace_bytes(int B, int n, int algo) {
+  if (B <= 0 || n <= 0) return 0;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  return 2 * nn + 2 * nv + eigh_work_bytes(B, n, algo);
+}
+
+extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode,
+                               int eigh_algo, double trust_min, double trust_max, double* H,
+                               const double* Hbias, const double* x, const double* Bg,
+                               const double* g, const double* x_prev, const double* g_prev,
+                               const double* Be, double* state, double* move_out,
+                               double* eigvals_out, double* pred_out, int32_t* status, void* work,
+                               size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && n > 0 && n % 3 == 0, "mop_rsirfo_step: n must be a positive multiple of 3");
+  MOP_REQUIRE(H && x && Bg && g && state && move_out && status && work,
+              "mop_rsirfo_step: H, x, Bg, g, state, move_out, status, work must be device pointers");
+  MOP_REQUIRE(saddle_order >= 0 && saddle_order < n, "mop_rsirfo_step: bad saddle_order");
+  MOP_REQUIRE((x_prev == nullptr) == (g_prev == nullptr),
+              "mop_rsirfo_step: x_prev and g_prev must both be given or both be NULL");
+  if (B == 0) return MOP_OK;
+  if (work_bytes < mop_rsirfo_workspace_bytes(B, n, eigh_algo)) {
+    mop_set_error("mop_rsirfo_step: workspace too small (%zu < %zu bytes)", work_bytes,
+                  mop_rsirfo_workspace_bytes(B, n, eigh_algo));
+    return MOP_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  char* w = (char*)work;
+  double* Hp = (double*)w;
+  double* evecs = (double*)(w + nn);
+  double* evals = (double*)(w + 2 * nn);
+  double* gp = (double*)(w + 2 * nn + nv);
+  void* ework = w + 2 * nn + 2 * nv;
+  const size_t ebytes = work_bytes - (2 * nn + 2 * nv);
+
+  MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
+  int rc;
+  // (1) Hessian update with RAW gradients (rsirfo.py:308-309,1316-1372)
+  if (x_prev && method != MOP_UPD_NONE) {
+    rc = mop_launch_hessian_update(B, n, method, 1, 1, H, nullptr, nullptr, x, x_prev, g, g_prev,
+                                   state, nullptr, status, stream);
+    if (rc != MOP_OK) return rc;
+  }
+  // (2) TR/ROT projection of gradient and effective Hessian (rsirfo.py:337,349-358)
+  rc = mop_launch_project_trrot(B, n, H, Hbias, x, Bg, Hp, gp, status, stream);
+  if (rc != MOP_OK) return rc;
+  // (3) eigendecomposition (rsirfo.py:360)
+  rc = run_eigh(B, n, eigh_algo, Hp, evals, evecs, status, ework, ebytes, stream);
+  if (rc != MOP_OK) return rc;
+  // (4) image function, secular solve, step, bookkeeping (rsirfo.py:365-490)
+  return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, gp,
+                             Bg, Hp, Be, state, move_out, eigvals_out, pred_out, status, stream);
+}

@@ -1,0 +1,231 @@
+// Fused quasi-Newton Hessian update, generic-n streaming path.
+//
+// One CTA per structure.  Pass 1 streams H once for u = H s (and H y for the
+// flowchart selector), pass 2 streams it again (L2-resident: the CTA's own
+// 8 n^2 bytes) applying  H <- 1/2 (H + H^T) + sum_ab C_ab v_a v_b^T  tile pair by
+// tile pair, so every global access is a coalesced 256-byte row segment.
+// HBM-bound: algorithmic traffic 16 n^2 bytes per structure (read + write H).
+#include "update_coef.cuh"
+
+namespace mop {
+
+constexpr int UPD_THREADS = 256;
+constexpr int TILE = 32;
+
+// smem: v[4][np] (s, y, u, r), hy[np], scratch[40], tiles 2 x 32 x 33
+__global__ void __launch_bounds__(UPD_THREADS)
+k_hessian_update(int n, int method, int mode, int guards, double* __restrict__ Hall,
+                 const double* __restrict__ s_all, const double* __restrict__ y_all,
+                 const double* __restrict__ x_all, const double* __restrict__ xp_all,
+                 const double* __restrict__ g_all, const double* __restrict__ gp_all,
+                 const double* __restrict__ state, int state_stride,
+                 double* __restrict__ delta_all, int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int np = (n + 3) & ~3;
+  double* vs = sm;
+  double* vy = vs + np;
+  double* vu = vy + np;
+  double* vr = vu + np;
+  double* hy = vr + np;
+  double* scratch = hy + np;             // 40
+  double* tA = scratch + 40;             // 32 x 33
+  double* tB = tA + TILE * (TILE + 1);   // 32 x 33
+  __shared__ UpdCoef coef;
+  __shared__ int s_apply, s_flags, s_method;
+
+  double* H = Hall + (size_t)b * n * n;
+  int st = status ? status[b] : 0;
+  st &= ~(MOP_ST_UPDATED | MOP_ST_UPD_SKIP_SMALL | MOP_ST_UPD_SKIP_CURV | MOP_ST_UPD_TERM_ZEROED |
+          MOP_ST_NO_HISTORY);
+
+  // ---- s, y ---------------------------------------------------------------
+  const bool from_points = (x_all != nullptr);
+  bool have_prev = true;
+  if (from_points) {
+    have_prev = (xp_all != nullptr) && (gp_all != nullptr) &&
+                (state == nullptr || state[(size_t)b * state_stride + MOP_RS_HAVE_PREV] != 0.0);
+  }
+  if (!have_prev) {
+    if (tid == 0 && status) status[b] = st | MOP_ST_NO_HISTORY;
+    return;
+  }
+  for (int i = tid; i < n; i += UPD_THREADS) {
+    double s, y;
+    if (from_points) {
+      s = x_all[(size_t)b * n + i] - xp_all[(size_t)b * n + i];
+      y = g_all[(size_t)b * n + i] - gp_all[(size_t)b * n + i];
+    } else {
+      s = s_all[(size_t)b * n + i];
+      y = y_all[(size_t)b * n + i];
+    }
+    vs[i] = s;
+    vy[i] = y;
+  }
+  __syncthreads();
+  double pss = 0, psy = 0, pyy = 0;
+  for (int i = tid; i < n; i += UPD_THREADS) {
+    pss = fma(vs[i], vs[i], pss);
+    psy = fma(vs[i], vy[i], psy);
+    pyy = fma(vy[i], vy[i], pyy);
+  }
+  const double ss = block_sum(pss, scratch);
+  double sy = block_sum(psy, scratch);
+  const double yy = block_sum(pyy, scratch);
+
+  if (guards) {  // RSIRFO.update_hessian, rsirfo.py:1326,1333
+    int skip = 0;
+    if (sqrt(ss) < 1e-10 || sqrt(yy) < 1e-10) skip = MOP_ST_UPD_SKIP_SMALL;
+    else if (sy <= 0.0) skip = MOP_ST_UPD_SKIP_CURV;
+    if (skip) {
+      if (tid == 0 && status) status[b] = st | skip;
+      return;
+    }
+  }
+
+  // ---- Powell damping (replaces y) -----------------------------------------
+  if (method_has_dd(method)) {
+    bool active = true;
+    if (method == MOP_UPD_BLOCK_BFGS_DD && !(sqrt(ss) > 1e-8)) active = false;  // rank guard first
+    if (active) {
+      const double th = dd_theta(ss, sy, method_dd_thr(method));
+      if (th != 1.0) {
+        for (int i = tid; i < n; i += UPD_THREADS) vy[i] = th * vy[i] + (1.0 - th) * vs[i];
+        __syncthreads();
+        double p = 0;
+        for (int i = tid; i < n; i += UPD_THREADS) p = fma(vs[i], vy[i], p);
+        sy = block_sum(p, scratch);
+      }
+    }
+  }
+
+  // ---- u = H s (and H y for the flowchart) ----------------------------------
+  block_matvec(H, n, n, vs, vu);
+  if (method == MOP_UPD_FLOWCHART) block_matvec(H, n, n, vy, hy);
+  __syncthreads();
+  int m = method;
+  if (method == MOP_UPD_FLOWCHART) {
+    double pzz = 0, pzs = 0;
+    for (int i = tid; i < n; i += UPD_THREADS) {
+      const double z = vy[i] - hy[i];
+      pzz = fma(z, z, pzz);
+      pzs = fma(z, vs[i], pzs);
+    }
+    const double zz = block_sum(pzz, scratch);
+    const double zs = block_sum(pzs, scratch);
+    m = flowchart_select(ss, yy, sy, zz, zs);
+  }
+  double psu = 0, prs = 0, prr = 0;
+  for (int i = tid; i < n; i += UPD_THREADS) {
+    const double r = vy[i] - vu[i];
+    vr[i] = r;
+    psu = fma(vs[i], vu[i], psu);
+    prs = fma(r, vs[i], prs);
+    prr = fma(r, r, prr);
+  }
+  UpdScalars q;
+  q.ss = ss;
+  q.sy = sy;
+  q.su = block_sum(psu, scratch);
+  q.rs = block_sum(prs, scratch);
+  q.rr = block_sum(prr, scratch);
+  if (tid == 0) {
+    update_coefficients(m, q, coef);
+    s_flags = coef.flags;
+  }
+  __syncthreads();
+
+  // ---- apply, tile pair by tile pair ----------------------------------------
+  const int T = (n + TILE - 1) / TILE;
+  double* D = (mode == 0) ? delta_all + (size_t)b * n * n : nullptr;
+  for (int I = 0; I < T; ++I) {
+    for (int J = I; J < T; ++J) {
+      const int i0 = I * TILE, j0 = J * TILE;
+      if (mode == 1) {
+        for (int e = tid; e < TILE * TILE; e += UPD_THREADS) {
+          const int r = e >> 5, c = e & 31;
+          const int gi = i0 + r, gj = j0 + c;
+          tA[r * (TILE + 1) + c] = (gi < n && gj < n) ? H[(size_t)gi * n + gj] : 0.0;
+          const int hi = j0 + r, hj = i0 + c;
+          tB[r * (TILE + 1) + c] = (hi < n && hj < n) ? H[(size_t)hi * n + hj] : 0.0;
+        }
+        __syncthreads();
+      }
+      for (int e = tid; e < TILE * TILE; e += UPD_THREADS) {
+        const int r = e >> 5, c = e & 31;
+        {  // element (i0 + r, j0 + c)
+          const int gi = i0 + r, gj = j0 + c;
+          if (gi < n && gj < n) {
+            const double vi[4] = {vs[gi], vy[gi], vu[gi], vr[gi]};
+            const double vj[4] = {vs[gj], vy[gj], vu[gj], vr[gj]};
+            const double d = 0.5 * (coef_delta(coef, vi, vj) + coef_delta(coef, vj, vi));
+            if (mode == 1)
+              H[(size_t)gi * n + gj] = 0.5 * (tA[r * (TILE + 1) + c] + tB[c * (TILE + 1) + r]) + d;
+            else
+              D[(size_t)gi * n + gj] = d;
+          }
+        }
+        if (J != I) {  // mirrored element (j0 + r, i0 + c)
+          const int gi = j0 + r, gj = i0 + c;
+          if (gi < n && gj < n) {
+            const double vi[4] = {vs[gi], vy[gi], vu[gi], vr[gi]};
+            const double vj[4] = {vs[gj], vy[gj], vu[gj], vr[gj]};
+            const double d = 0.5 * (coef_delta(coef, vi, vj) + coef_delta(coef, vj, vi));
+            if (mode == 1)
+              H[(size_t)gi * n + gj] = 0.5 * (tB[r * (TILE + 1) + c] + tA[c * (TILE + 1) + r]) + d;
+            else
+              D[(size_t)gi * n + gj] = d;
+          }
+        }
+      }
+      if (mode == 1) __syncthreads();
+    }
+  }
+  if (tid == 0 && status) status[b] = st | MOP_ST_UPDATED | s_flags;
+}
+
+}  // namespace mop
+
+static size_t upd_smem_bytes(int n) {
+  const int np = (n + 3) & ~3;
+  return sizeof(double) * (5 * (size_t)np + 40 + 2 * mop::TILE * (mop::TILE + 1));
+}
+
+// Internal launcher shared with mop_rsirfo_step (s, y formed from the points).
+int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, double* H,
+                              const double* s, const double* y, const double* x, const double* xp,
+                              const double* g, const double* gp, const double* state,
+                              double* delta_out, int32_t* status, cudaStream_t stream) {
+  if (method == MOP_UPD_PCFD_BOFILL) {
+    mop_set_error("pcfd_bofill (O(n^4) null-space perturbation) is not implemented on the device");
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (method < 0 || method > MOP_UPD_MSP) {
+    mop_set_error("unknown Hessian update method id %d", method);
+    return MOP_ERR_INVALID;
+  }
+  if (method == MOP_UPD_NONE || B == 0) return MOP_OK;
+  const size_t smem = upd_smem_bytes(n);
+  if (smem > 200 * 1024) {
+    mop_set_error("n = %d too large for the update kernel's vector staging", n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_hessian_update,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_hessian_update<<<B, mop::UPD_THREADS, smem, stream>>>(
+      n, method, mode, guards, H, s, y, x, xp, g, gp, state, MOP_RSIRFO_STATE, delta_out, status);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+extern "C" int mop_hessian_update(int B, int n, int method, int mode, int rsirfo_guards, double* H,
+                                  const double* s, const double* y, double* delta_out,
+                                  int32_t* status, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0, "mop_hessian_update: B >= 0 and n > 0 required");
+  MOP_REQUIRE(H && s && y, "mop_hessian_update: H, s, y must be device pointers");
+  MOP_REQUIRE(mode == 0 || mode == 1, "mop_hessian_update: mode must be 0 (delta) or 1 (in place)");
+  MOP_REQUIRE(mode == 1 || delta_out, "mop_hessian_update: delta_out required in mode 0");
+  return mop_launch_hessian_update(B, n, method, mode, rsirfo_guards, H, s, y, nullptr, nullptr,
+                                   nullptr, nullptr, nullptr, delta_out, status,
+                                   (cudaStream_t)stream);
+}

@@ -1,0 +1,245 @@
+// Translation/rotation projection of Hessian and gradient.
+//
+// Reference: Calculationtools.project_out_hess_tr_and_rot_for_coord
+// (Utils/calc_tools.py:249-316) forms the dense P = I - sum t t^T and two n^3
+// matmuls.  Here the rank-6 structure is used:
+//     Hp = S - Y T^T - T Y^T,   S = sym(H + Hbias),  W = S T,  Y = W - 1/2 T (T^T W)
+// which is O(n^2) and streams the matrix twice (W pass + output pass).
+// T (n x k, k <= 6) is the reference's CLASSICAL Gram-Schmidt basis (drop 1e-10).
+// The gradient projection g - Q Q^T g (Optimizer/rsirfo.py:128-190, reduced QR)
+// spans the same space when the six vectors are independent; for rank-deficient
+// sets (linear molecules) the GS basis is used and MOP_ST_TRROT_RANKDEF is set.
+#include "common.cuh"
+
+namespace mop {
+
+constexpr int PRJ_THREADS = 256;
+constexpr int PT = 32;
+
+// Build the TR/ROT basis of one structure into T[6][np]; returns rank k.
+// Must be called by the whole CTA.  scratch >= 40 doubles.
+__device__ int build_trrot_basis(int n, const double* __restrict__ x, double* T, int np,
+                                 double* raw, double* scratch) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int N = n / 3;
+  // plain mean, sequential per component as calc_center does (calc_tools.py:138-145)
+  __shared__ double cen[3];
+  if (tid < 3) {
+    double acc = 0.0;
+    for (int a = 0; a < N; ++a) acc += x[3 * a + tid];
+    cen[tid] = acc / N;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) {
+    const int a = i / 3, c = i - 3 * a;
+    const double cx = x[3 * a] - cen[0], cy = x[3 * a + 1] - cen[1], cz = x[3 * a + 2] - cen[2];
+    raw[0 * np + i] = (c == 0) ? 1.0 : 0.0;
+    raw[1 * np + i] = (c == 1) ? 1.0 : 0.0;
+    raw[2 * np + i] = (c == 2) ? 1.0 : 0.0;
+    raw[3 * np + i] = (c == 0) ? 0.0 : (c == 1 ? -cz : cy);
+    raw[4 * np + i] = (c == 0) ? cz : (c == 1 ? 0.0 : -cx);
+    raw[5 * np + i] = (c == 0) ? -cy : (c == 1 ? cx : 0.0);
+  }
+  __syncthreads();
+  int k = 0;
+  for (int v = 0; v < 6; ++v) {
+    // classical GS: coefficients from the ORIGINAL vector (calc_tools.py:252-256)
+    double cf[6];
+    for (int j = 0; j < k; ++j) {
+      double p = 0.0;
+      for (int i = tid; i < n; i += nt) p = fma(raw[v * np + i], T[j * np + i], p);
+      cf[j] = block_sum(p, scratch);
+    }
+    double p2 = 0.0;
+    for (int i = tid; i < n; i += nt) {
+      double w = raw[v * np + i];
+      for (int j = 0; j < k; ++j) w -= cf[j] * T[j * np + i];
+      T[k * np + i] = w;
+      p2 = fma(w, w, p2);
+    }
+    const double nrm = sqrt(block_sum(p2, scratch));
+    if (nrm > 1e-10) {
+      for (int i = tid; i < n; i += nt) T[k * np + i] /= nrm;
+      ++k;
+    }
+    __syncthreads();
+  }
+  return k;
+}
+
+__global__ void __launch_bounds__(PRJ_THREADS)
+k_project_trrot(int n, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
+                const double* __restrict__ x_all, const double* __restrict__ g_all,
+                double* __restrict__ Hp_all, double* __restrict__ gp_all,
+                int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = PRJ_THREADS >> 5;
+  const int np = (n + 3) & ~3;
+  double* T = sm;                 // 6 x np
+  double* raw = T + 6 * np;       // 6 x np   (later reused as W -> Y)
+  double* scratch = raw + 6 * np; // 40
+  double* M = scratch + 40;       // 36 : T^T W
+  double* tA = M + 36;            // 32 x 33
+  double* tB = tA + PT * (PT + 1);
+  const double* H = Hall + (size_t)b * n * n;
+  const double* Hb = Hb_all ? Hb_all + (size_t)b * n * n : nullptr;
+  const double* x = x_all + (size_t)b * n;
+
+  const int k = build_trrot_basis(n, x, T, np, raw, scratch);
+  if (tid == 0 && status) {
+    int st = status[b] & ~MOP_ST_TRROT_RANKDEF;
+    if (k < 6) st |= MOP_ST_TRROT_RANKDEF;
+    status[b] = st;
+  }
+
+  // ---- gradient: gp = g - T (T^T g) -----------------------------------------
+  if (g_all && gp_all) {
+    const double* g = g_all + (size_t)b * n;
+    double cf[6];
+    for (int j = 0; j < k; ++j) {
+      double p = 0.0;
+      for (int i = tid; i < n; i += PRJ_THREADS) p = fma(T[j * np + i], g[i], p);
+      cf[j] = block_sum(p, scratch);
+    }
+    for (int i = tid; i < n; i += PRJ_THREADS) {
+      double part = 0.0;
+      for (int j = 0; j < k; ++j) part = fma(T[j * np + i], cf[j], part);
+      gp_all[(size_t)b * n + i] = g[i] - part;
+    }
+  }
+  if (!Hp_all) return;
+  __syncthreads();
+
+  // ---- W = S T, S = 1/2 (M0 + M0^T): row pass (M0 T) + column pass (M0^T T) ----
+  double* W = raw;  // raw vectors are dead now
+  for (int i = tid; i < 6 * np; i += PRJ_THREADS) W[i] = 0.0;
+  __syncthreads();
+  for (int i = w; i < n; i += nw) {  // (M0 T)_i = sum_j M0[i][j] T[j]
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = lane; j < n; j += 32) {
+      double a = H[(size_t)i * n + j];
+      if (Hb) a += Hb[(size_t)i * n + j];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) acc[v] = fma(a, T[v * np + j], acc[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < 6; ++v) acc[v] = warp_sum(acc[v]);
+    if (lane == 0)
+      for (int v = 0; v < k; ++v) W[v * np + i] = 0.5 * acc[v];
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += PRJ_THREADS) {  // (M0^T T)_j = sum_i M0[i][j] T[i]
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+      double a = H[(size_t)i * n + j];
+      if (Hb) a += Hb[(size_t)i * n + j];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) acc[v] = fma(a, T[v * np + i], acc[v]);
+    }
+    for (int v = 0; v < k; ++v) W[v * np + j] += 0.5 * acc[v];
+  }
+  __syncthreads();
+  // M = T^T W (k x k), then Y = W - 1/2 T M  (in place in W)
+  for (int e = w; e < k * k; e += nw) {
+    const int a = e / k, c = e - a * k;
+    double p = 0.0;
+    for (int i = lane; i < n; i += 32) p = fma(T[a * np + i], W[c * np + i], p);
+    p = warp_sum(p);
+    if (lane == 0) M[a * 6 + c] = p;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += PRJ_THREADS) {
+    double tv[6];
+    for (int a = 0; a < k; ++a) tv[a] = T[a * np + i];
+    for (int c = 0; c < k; ++c) {
+      double corr = 0.0;
+      for (int a = 0; a < k; ++a) corr = fma(tv[a], 0.5 * (M[a * 6 + c] + M[c * 6 + a]), corr);
+      W[c * np + i] -= 0.5 * corr;
+    }
+  }
+  __syncthreads();
+  const double* Y = W;
+
+  // ---- output pass: Hp = S - Y T^T - T Y^T, tile pairs ------------------------
+  double* Hp = Hp_all + (size_t)b * n * n;
+  const int TT = (n + PT - 1) / PT;
+  for (int I = 0; I < TT; ++I) {
+    for (int J = I; J < TT; ++J) {
+      const int i0 = I * PT, j0 = J * PT;
+      for (int e = tid; e < PT * PT; e += PRJ_THREADS) {
+        const int r = e >> 5, c = e & 31;
+        int gi = i0 + r, gj = j0 + c;
+        double a = 0.0;
+        if (gi < n && gj < n) {
+          a = H[(size_t)gi * n + gj];
+          if (Hb) a += Hb[(size_t)gi * n + gj];
+        }
+        tA[r * (PT + 1) + c] = a;
+        gi = j0 + r;
+        gj = i0 + c;
+        a = 0.0;
+        if (gi < n && gj < n) {
+          a = H[(size_t)gi * n + gj];
+          if (Hb) a += Hb[(size_t)gi * n + gj];
+        }
+        tB[r * (PT + 1) + c] = a;
+      }
+      __syncthreads();
+      for (int e = tid; e < PT * PT; e += PRJ_THREADS) {
+        const int r = e >> 5, c = e & 31;
+        {
+          const int gi = i0 + r, gj = j0 + c;
+          if (gi < n && gj < n) {
+            double v = 0.5 * (tA[r * (PT + 1) + c] + tB[c * (PT + 1) + r]);
+            for (int a = 0; a < k; ++a)
+              v -= __dadd_rn(__dmul_rn(Y[a * np + gi], T[a * np + gj]),
+                             __dmul_rn(T[a * np + gi], Y[a * np + gj]));  // bit-symmetric
+            Hp[(size_t)gi * n + gj] = v;
+          }
+        }
+        if (J != I) {
+          const int gi = j0 + r, gj = i0 + c;
+          if (gi < n && gj < n) {
+            double v = 0.5 * (tB[r * (PT + 1) + c] + tA[c * (PT + 1) + r]);
+            for (int a = 0; a < k; ++a)
+              v -= __dadd_rn(__dmul_rn(Y[a * np + gi], T[a * np + gj]),
+                             __dmul_rn(T[a * np + gi], Y[a * np + gj]));  // bit-symmetric
+            Hp[(size_t)gi * n + gj] = v;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace mop
+
+int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  const int np = (n + 3) & ~3;
+  const size_t smem = sizeof(double) * (12 * (size_t)np + 40 + 36 + 2 * mop::PT * (mop::PT + 1));
+  if (smem > 200 * 1024) {
+    mop_set_error("n = %d too large for the projection kernel", n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_project_trrot,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_project_trrot<<<B, mop::PRJ_THREADS, smem, stream>>>(n, H, Hbias, x, g, Hp_out, gp_out,
+                                                            status);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+extern "C" int mop_project_trrot(int B, int n, const double* H, const double* Hbias,
+                                 const double* x, const double* g, double* Hp_out, double* gp_out,
+                                 int32_t* status, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0 && n % 3 == 0, "mop_project_trrot: n must be a positive multiple of 3");
+  MOP_REQUIRE(x, "mop_project_trrot: x must be a device pointer");
+  MOP_REQUIRE((H && Hp_out) || (g && gp_out), "mop_project_trrot: nothing to project");
+  MOP_REQUIRE(!Hp_out || H, "mop_project_trrot: H required with Hp_out");
+  return mop_launch_project_trrot(B, n, H, Hbias, x, g, Hp_out, gp_out, status,
+                                  (cudaStream_t)stream);
+}

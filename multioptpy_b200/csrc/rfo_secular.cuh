@@ -1,0 +1,214 @@
+// RFO secular-equation machinery of RSIRFO (Optimizer/rsirfo.py:924-1313,
+// 1374-1575, 1688-1715), executed by ONE WARP: every lane runs the same scalar
+// control flow on identical values (butterfly reductions give all lanes the
+// same sums), the O(k) term loops are strided over the lanes.
+//
+// The reference stops its iterations at loose tolerances and the alpha loop
+// returns the step of whichever alpha it ended on, so the control flow is
+// replayed iteration for iteration (SURVEY hazards H3, H8).
+#pragma once
+#include "common.cuh"
+
+namespace mop {
+
+struct RfoWork {
+  const double* lam;  // kept eigenvalues, ascending, [k]
+  const double* gam;  // gradient components in the kept eigenbasis, [k]
+  double* lamp;       // scratch [k]: lam / alpha
+  double* g2;         // scratch [k]: (gam / alpha)^2
+  double* step;       // out [k]
+  int k;
+};
+
+__device__ __forceinline__ double safe_den(double den, double tiny) {
+  // np.where(|den| < tiny, sign(den) * tiny, den); exact zeros -> +tiny
+  if (fabs(den) < tiny) den = sgn(den) * tiny;
+  if (den == 0.0) den = tiny;
+  return den;
+}
+
+__device__ __forceinline__ double sec_f(const RfoWork& w, double lmd, int lane) {
+  double acc = 0.0;
+  for (int i = lane; i < w.k; i += 32) acc += w.g2[i] / safe_den(w.lamp[i] - lmd, 1e-30);
+  return lmd + warp_sum(acc);
+}
+__device__ __forceinline__ double sec_fp(const RfoWork& w, double lmd, int lane) {
+  double acc = 0.0;
+  for (int i = lane; i < w.k; i += 32) {
+    const double d = safe_den(w.lamp[i] - lmd, 1e-30);
+    acc += w.g2[i] / (d * d);
+  }
+  return 1.0 + warp_sum(acc);
+}
+
+// _solve_secular_safeguarded, rsirfo.py:1374-1503
+__device__ __forceinline__ double secular_safeguarded(const RfoWork& w, double pole, double guess,
+                                                     double gsum, int lane) {
+  double b = pole, a = guess;
+  double fa = sec_f(w, a, lane);
+  const double gnorm = sqrt(gsum);
+  int limit = 10;
+  while (fa > 0.0 && limit > 0) {
+    a = a - fmax(gnorm, fmax(fabs(a) * 0.1, 1e-8));
+    fa = sec_f(w, a, lane);
+    --limit;
+  }
+  if (fa > 0.0) return guess;
+  double lk = guess;
+  if (lk <= a || lk >= b) lk = (a + b) / 2.0;
+  const double tol = 1e-10 * fabs(pole) + 1e-12;
+  for (int it = 0; it < 250; ++it) {
+    const double f = sec_f(w, lk, lane);
+    if (fabs(f) < tol) return lk;
+    const double fp = sec_fp(w, lk, lane);
+    const double dn = fabs(fp) > 1e-20 ? -f / fp : 0.0;
+    const double ln = lk + dn;
+    const double lb = (a + b) / 2.0;
+    const double nxt = (dn != 0.0 && ln > a && ln < b) ? ln : lb;
+    if (f > 0.0) b = lk; else a = lk;
+    lk = nxt;
+    if (fabs(b - a) < tol) return (a + b) / 2.0;
+  }
+  return (a + b) / 2.0;
+}
+
+// solve_rfo + _solve_secular_more_sorensen, rsirfo.py:1505-1575,1688-1715.
+// Writes w.step, returns lambda_aug (in the 1/alpha-scaled frame); *hard set when
+// every gradient component is (numerically) zero.
+__device__ __forceinline__ double solve_rfo(const RfoWork& w, double alpha, int lane, bool* hard) {
+  double gs = 0.0;
+  int first = 0x7fffffff;
+  for (int i = lane; i < w.k; i += 32) {
+    const double lp = w.lam[i] / alpha;
+    const double gp = w.gam[i] / alpha;
+    const double q = gp * gp;
+    w.lamp[i] = lp;
+    w.g2[i] = q;
+    gs += q;
+    if (q > 1e-20 && i < first) first = i;
+  }
+  __syncwarp();
+  gs = warp_sum(gs);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(MOP_FULL_MASK, first, o));
+  double mu;
+  if (first == 0x7fffffff) {
+    mu = w.k > 0 ? w.lamp[0] : 0.0;
+    if (hard) *hard = true;
+  } else {
+    const double pole = w.lamp[first];
+    const double guess = 0.5 * (pole - sqrt(fmax(0.0, pole * pole + 4.0 * gs)));
+    mu = secular_safeguarded(w, pole, guess, gs, lane);
+  }
+  for (int i = lane; i < w.k; i += 32) {
+    const double den = safe_den(w.lam[i] / alpha - mu, 1e-20);
+    w.step[i] = -(w.gam[i] / alpha) / den;
+  }
+  __syncwarp();
+  return mu;
+}
+
+__device__ __forceinline__ double warp_norm2(const double* v, int k, int lane) {
+  double acc = 0.0;
+  for (int i = lane; i < k; i += 32) acc = fma(v[i], v[i], acc);
+  return warp_sum(acc);
+}
+
+// get_step_derivative, rsirfo.py:1250-1313
+__device__ __forceinline__ double step_derivative(const RfoWork& w, double alpha, double mu, int lane) {
+  double acc = 0.0;
+  int any_valid = 0;
+  for (int i = lane; i < w.k; i += 32) {
+    double den = w.lam[i] - mu * alpha;
+    if (fabs(den) < 1e-8) den = sgn(den) * fmax(1e-8, fabs(den));  // exact zero stays zero
+    const double d3 = den * den * den;
+    if (fabs(d3) > 1e-10) {
+      any_valid = 1;
+      double t = (w.gam[i] * w.gam[i]) / d3;
+      if (fabs(t) > 1e20) t = sgn(t) * 1e20;
+      acc += t;
+    }
+  }
+  any_valid = __any_sync(MOP_FULL_MASK, any_valid);
+  if (!any_valid) return 1e-8;
+  double d = 2.0 * mu * warp_sum(acc);
+  if (!isfinite(d) || fabs(d) > 1e20) d = (d != 0.0) ? sgn(d) * 1e20 : 1e-8;
+  return d;
+}
+
+// compute_rsprfo_step, rsirfo.py:986-1248.  Leaves the returned step in w.step.
+// `best` is scratch [k].  Returns status bits to OR in.
+__device__ __forceinline__ int alpha_search(const RfoWork& w, double trust, double* best, int lane) {
+  const double alpha0 = 1.0, alpha_max = 1000.0, alpha_step_max = 10.0, step_tol = 1e-3;
+  const int max_micro = 40;
+  int flags = 0;
+  const double r2 = trust * trust;
+  double alpha = alpha0;
+  {
+    solve_rfo(w, 1e-6, lane, nullptr);
+    const double nlo = sqrt(warp_norm2(w.step, w.k, lane));
+    solve_rfo(w, alpha_max, lane, nullptr);
+    const double nhi = sqrt(warp_norm2(w.step, w.k, lane));
+    const double olo = nlo * nlo - r2, ohi = nhi * nhi - r2;
+    if (olo * ohi < 0.0) flags |= MOP_ST_BRENT_BRACKET;  // Brent branch not replayed (rounding-only event)
+  }
+  double hist0 = 0.0, hist1 = 0.0;  // last two recorded norms
+  int nhist = 0;
+  bool have_best = false;
+  double best_diff = INFINITY;
+  bool has_left = false, has_right = false;
+  double a_left = 0.0, a_right = 0.0;
+  for (int it = 0; it < max_micro; ++it) {
+    const double mu = solve_rfo(w, alpha, lane, nullptr);
+    const double nrm = sqrt(warp_norm2(w.step, w.k, lane));
+    const double diff = fabs(nrm - trust);
+    if (diff < best_diff) {
+      for (int i = lane; i < w.k; i += 32) best[i] = w.step[i];
+      best_diff = diff;
+      have_best = true;
+    }
+    const double obj = nrm * nrm - r2;
+    if (obj < 0.0 && (!has_left || alpha > a_left)) {
+      a_left = alpha;
+      has_left = true;
+    } else if (obj > 0.0 && (!has_right || alpha < a_right)) {
+      a_right = alpha;
+      has_right = true;
+    }
+    if (fabs(obj) < 1e-8 || diff < step_tol) return flags;
+    // history (fixed-size array in the reference; max_micro entries always fit)
+    const double prev0 = hist0, prev1 = hist1;
+    hist0 = hist1;
+    hist1 = nrm;
+    ++nhist;
+    const double d = step_derivative(w, alpha, mu, lane);
+    double a_new;
+    if (fabs(d) < 1e-10) {
+      if (has_left && has_right) a_new = (a_left + a_right) / 2.0;
+      else if (obj > 0.0) a_new = fmax(alpha / 2.0, 1e-6);
+      else a_new = fmin(alpha * 2.0, alpha_max);
+    } else {
+      const double a_step = fmin(alpha_step_max, fmax(-alpha_step_max, -obj / d));
+      a_new = alpha + a_step;
+      if (has_left && has_right) a_new = fmax(fmin(a_new, a_right * 0.99), a_left * 1.01);
+    }
+    alpha = fmin(fmax(a_new, 1e-6), alpha_max);
+    if (alpha == alpha_max || alpha == 1e-6) return flags;
+    if (nhist >= 3 && fabs(hist1 - hist0) < 1e-6 && fabs(prev1 - prev0) < 1e-6) return flags;
+  }
+  // micro-cycles exhausted (rsirfo.py:1213-1246)
+  if (have_best) {
+    const double bn = sqrt(warp_norm2(best, w.k, lane));
+    if (fabs(bn - trust) < step_tol * 1.1) {
+      for (int i = lane; i < w.k; i += 32) w.step[i] = best[i];
+      __syncwarp();
+      return flags;
+    }
+  }
+  const double gn = sqrt(warp_norm2(w.gam, w.k, lane));
+  for (int i = lane; i < w.k; i += 32) w.step[i] = gn > 1e-10 ? -w.gam[i] / gn * trust : 0.0;
+  __syncwarp();
+  return flags;
+}
+
+}  // namespace mop

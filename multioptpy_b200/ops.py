@@ -1,0 +1,215 @@
+"""Thin torch-facing wrappers over the C ABI (device memory + streams only).
+
+Every function takes float64 CUDA tensors (batch-major, contiguous) and
+launches the hand-written sm_100a kernels asynchronously on the current torch
+stream.  Nothing here computes on the CPU and nothing falls back to torch
+linear algebra.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import MopError
+
+# ---- ids shared with include/mop_b200.h -----------------------------------
+UPDATE_DISPATCH = [
+    ("flowchart", 1), ("block_cfd_fsb_dd", 2), ("block_cfd_fsb_weighted", 3), ("block_cfd_fsb", 4),
+    ("block_cfd_bofill_weighted", 5), ("block_cfd_bofill", 6), ("block_bfgs_dd", 7), ("block_bfgs", 8),
+    ("block_fsb_dd", 9), ("block_fsb_weighted", 10), ("block_fsb", 11), ("block_bofill_weighted", 12),
+    ("block_bofill", 13), ("bfgs_dd", 14), ("bfgs", 15), ("sr1", 16), ("pcfd_bofill", 17),
+    ("cfd_fsb_dd", 18), ("cfd_fsb", 19), ("cfd_bofill", 20), ("fsb_dd", 21), ("fsb", 22),
+    ("bofill", 23), ("psb", 24), ("msp", 25),
+]
+UPD_NONE, UPD_FLOWCHART = 0, 1
+EIGH_AUTO, EIGH_JACOBI, EIGH_TRIDIAG = 0, 1, 2
+EIGH_ALGOS = {"auto": EIGH_AUTO, "jacobi": EIGH_JACOBI, "tridiag": EIGH_TRIDIAG}
+RSIRFO_STATE = 16
+RS_TRUST, RS_HAVE_PREV, RS_PREV_ENERGY, RS_HAVE_ENERGY, RS_NPRED, RS_PRED0, RS_NACT, RS_ACT0, RS_ITER = (
+    0, 1, 2, 3, 4, 5, 8, 9, 12)
+
+ST_UPDATED = 1 << 0
+ST_UPD_SKIP_SMALL = 1 << 1
+ST_UPD_SKIP_CURV = 1 << 2
+ST_UPD_TERM_ZEROED = 1 << 3
+ST_LEVEL_SHIFT = 1 << 4
+ST_EIG_NONFINITE = 1 << 5
+ST_ALPHA_SEARCH = 1 << 6
+ST_STEP_NAN_SD = 1 << 7
+ST_HARD_CASE = 1 << 8
+ST_TRROT_RANKDEF = 1 << 9
+ST_BRENT_BRACKET = 1 << 10
+ST_EIG_NOCONV = 1 << 11
+ST_EIG_FALLBACK = 1 << 12
+ST_NO_HISTORY = 1 << 13
+
+
+def resolve_update_method(name: str) -> int:
+    """Prioritised substring dispatch of Optimizer/rsirfo.py:208-251,1341-1356."""
+    low = name.lower()
+    for key, mid in UPDATE_DISPATCH:
+        if key in low:
+            return mid
+    return UPD_FLOWCHART
+
+
+# ---- helpers -----------------------------------------------------------------
+def _chk(t: torch.Tensor, name: str, shape=None, dtype=torch.float64) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise MopError(f"{name}: expected a torch tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise MopError(f"{name}: must be a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise MopError(f"{name}: dtype {t.dtype}, expected {dtype}")
+    if not t.is_contiguous():
+        raise MopError(f"{name}: must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise MopError(f"{name}: shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+_WORK: dict = {}
+
+
+def workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (caller-owned memory for the C ABI)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _WORK.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _WORK[key] = buf
+    return buf
+
+
+# ---- (1) Hessian update --------------------------------------------------------
+def hessian_update(H, s, y, method: int, *, inplace: bool = False, rsirfo_guards: bool = False,
+                   status=None):
+    """delta_hess of one quasi-Newton update for each structure of the batch, or the
+    in-place symmetrised update (RSIRFO.update_hessian) when ``inplace``."""
+    lib = _lib.load()
+    B, n, _ = H.shape
+    _chk(H, "H", (B, n, n)); _chk(s, "s", (B, n)); _chk(y, "y", (B, n))
+    if status is None:
+        status = torch.zeros(B, dtype=torch.int32, device=H.device)
+    _chk(status, "status", (B,), torch.int32)
+    delta = None if inplace else torch.empty_like(H)
+    with torch.cuda.device(H.device):
+        rc = lib.mop_hessian_update(B, n, int(method), 1 if inplace else 0, int(rsirfo_guards),
+                                    _ptr(H), _ptr(s), _ptr(y), _ptr(delta), _ptr(status),
+                                    _stream(H.device))
+    _lib.check(rc, "mop_hessian_update")
+    return (H if inplace else delta), status
+
+
+# ---- (2a) TR/ROT projection ------------------------------------------------------
+def project_trrot(H, x, Hbias=None, g=None, status=None):
+    lib = _lib.load()
+    B, n = x.shape
+    _chk(x, "x", (B, n))
+    Hp = gp = None
+    if H is not None:
+        _chk(H, "H", (B, n, n))
+        Hp = torch.empty_like(H)
+    if Hbias is not None:
+        _chk(Hbias, "Hbias", (B, n, n))
+    if g is not None:
+        _chk(g, "g", (B, n))
+        gp = torch.empty_like(g)
+    if status is None:
+        status = torch.zeros(B, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.mop_project_trrot(B, n, _ptr(H), _ptr(Hbias), _ptr(x), _ptr(g), _ptr(Hp), _ptr(gp),
+                                   _ptr(status), _stream(x.device))
+    _lib.check(rc, "mop_project_trrot")
+    return Hp, gp, status
+
+
+# ---- (2b) eigensolver ---------------------------------------------------------------
+def eigh(A, algo="auto", status=None):
+    """Batched symmetric eigendecomposition.  Returns (evals [B,n] ascending,
+    evecs [B,n,n] with ROW k = eigenvector k, status)."""
+    lib = _lib.load()
+    B, n, _ = A.shape
+    _chk(A, "A", (B, n, n))
+    algo_id = EIGH_ALGOS[algo] if isinstance(algo, str) else int(algo)
+    evals = torch.empty(B, n, dtype=torch.float64, device=A.device)
+    evecs = torch.empty_like(A)
+    if status is None:
+        status = torch.zeros(B, dtype=torch.int32, device=A.device)
+    nbytes = lib.mop_eigh_workspace_bytes(B, n, algo_id)
+    work = workspace(A.device, nbytes)
+    with torch.cuda.device(A.device):
+        rc = lib.mop_eigh(B, n, algo_id, _ptr(A), _ptr(evals), _ptr(evecs), _ptr(status), _ptr(work),
+                          nbytes, _stream(A.device))
+    _lib.check(rc, "mop_eigh")
+    return evals, evecs, status
+
+
+# ---- (2c) RS-I-RFO step ---------------------------------------------------------------
+def new_rsirfo_state(B: int, trust0: float, device) -> torch.Tensor:
+    st = torch.zeros(B, RSIRFO_STATE, dtype=torch.float64, device=device)
+    st[:, RS_TRUST] = trust0
+    return st
+
+
+def rsirfo_step(H, x, Bg, g, state, *, method: int, saddle_order: int = 0, neb_mode: bool = False,
+                Hbias=None, x_prev=None, g_prev=None, Be=None, trust_min: float = 0.01,
+                trust_max: float = 0.5, eigh_algo="auto", out=None):
+    """One RSIRFO.run for every structure of the batch.  H is updated in place.
+    Returns dict(move, eigvals, pred, status)."""
+    lib = _lib.load()
+    B, n = x.shape
+    dev = x.device
+    _chk(H, "H", (B, n, n)); _chk(x, "x", (B, n)); _chk(Bg, "Bg", (B, n)); _chk(g, "g", (B, n))
+    _chk(state, "state", (B, RSIRFO_STATE))
+    if Hbias is not None:
+        _chk(Hbias, "Hbias", (B, n, n))
+    if (x_prev is None) != (g_prev is None):
+        raise MopError("x_prev and g_prev must be given together")
+    if x_prev is not None:
+        _chk(x_prev, "x_prev", (B, n)); _chk(g_prev, "g_prev", (B, n))
+    if Be is not None:
+        _chk(Be, "Be", (B,))
+    algo_id = EIGH_ALGOS[eigh_algo] if isinstance(eigh_algo, str) else int(eigh_algo)
+    if out is None:
+        out = {
+            "move": torch.empty(B, n, dtype=torch.float64, device=dev),
+            "eigvals": torch.empty(B, n, dtype=torch.float64, device=dev),
+            "pred": torch.empty(B, dtype=torch.float64, device=dev),
+            "status": torch.empty(B, dtype=torch.int32, device=dev),
+        }
+    nbytes = lib.mop_rsirfo_workspace_bytes(B, n, algo_id)
+    work = workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        rc = lib.mop_rsirfo_step(B, n, int(method), int(saddle_order), int(bool(neb_mode)), algo_id,
+                                 float(trust_min), float(trust_max), _ptr(H), _ptr(Hbias), _ptr(x),
+                                 _ptr(Bg), _ptr(g), _ptr(x_prev), _ptr(g_prev), _ptr(Be), _ptr(state),
+                                 _ptr(out["move"]), _ptr(out["eigvals"]), _ptr(out["pred"]),
+                                 _ptr(out["status"]), _ptr(work), nbytes, _stream(dev))
+    _lib.check(rc, "mop_rsirfo_step")
+    return out
+
+
+def clamp_and_move(x, move, trust_outer, want_geometry: bool = True):
+    """optimizer.py:792-798,812: clamp ||move|| to trust_outer (in place) and return
+    the new geometry in Angstrom."""
+    lib = _lib.load()
+    B, n = move.shape
+    _chk(move, "move", (B, n)); _chk(trust_outer, "trust_outer", (B,))
+    xnew = None
+    if want_geometry:
+        _chk(x, "x", (B, n))
+        xnew = torch.empty_like(x)
+    with torch.cuda.device(move.device):
+        rc = lib.mop_clamp_and_move(B, n, _ptr(x), _ptr(move), _ptr(trust_outer), _ptr(xnew),
+                                    _stream(move.device))
+    _lib.check(rc, "mop_clamp_and_move")
+    return xnew, move

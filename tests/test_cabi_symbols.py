@@ -1,0 +1,44 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mop_b200.h declares."""
+import ctypes
+import os
+import re
+
+from multioptpy_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mop_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mop_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        from multioptpy_b200 import build
+        build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 9
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in mop_b200.h but not exported"
+    # and the ctypes table covers the header exactly
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_error_string():
+    lib = _lib.load()
+    assert lib.mop_version() == 100
+    # argument validation happens on the host before any CUDA call
+    rc = lib.mop_hessian_update(1, 0, 15, 0, 0, None, None, None, None, None, None)
+    assert rc == -1
+    assert b"n > 0" in lib.mop_last_error()
+
+
+def test_method_table_matches_oracle():
+    from multioptpy_b200 import ops
+    from oracle import np_oracle as O
+    assert ops.UPDATE_DISPATCH == O.UPDATE_DISPATCH
+    for name in ["rsirfo_bofill", "rsirfo_block_fsb", "RSIRFO_BFGS", "rsirfo", "rsirfo_block_cfd_fsb_dd"]:
+        assert ops.resolve_update_method(name) == O.resolve_update_method(name)

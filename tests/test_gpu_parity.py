@@ -1,0 +1,189 @@
+"""GPU parity: CUDA kernels (through the C ABI) vs the NumPy oracle and the golden
+vectors produced by the unmodified reference.  Tolerance: 1e-10 relative on
+Hessians, step vectors, energies; max|dlambda| <= 1e-10 max|lambda| on spectra
+(north_star / SURVEY §8c)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from multioptpy_b200 import ops, synthetic
+from multioptpy_b200.Optimizer.rsirfo import RSIRFO
+from multioptpy_b200.Optimizer.hessian_update import ModelHessianUpdate, BlockHessianUpdate
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# --------------------------------------------------------------------------- update
+def test_update_deltas_vs_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "update_deltas.npz"))
+    for mid in np.unique(z["method"]):
+        sel = np.where(z["method"] == mid)[0]
+        H, s, y, ref = z["H"][sel], z["s"][sel], z["y"][sel], z["delta"][sel]
+        d, st = ops.hessian_update(T(H), T(s), T(y), int(mid))
+        d = d.cpu().numpy()
+        for i in range(len(sel)):
+            scale = max(np.linalg.norm(ref[i]), 1e-3 * np.linalg.norm(H[i]))
+            err = np.linalg.norm(d[i] - ref[i]) / scale
+            assert err < RTOL, (int(mid), O.UPDATE_NAMES[int(mid)], int(z["kind"][sel[i]]), err)
+
+
+@pytest.mark.parametrize("n", [9, 33, 150, 200])
+@pytest.mark.parametrize("method", [15, 23, 11, 13, 22, 25, 1])
+def test_update_inplace_vs_oracle(n, method):
+    rng = np.random.default_rng(n * 100 + method)
+    B = 5
+    H = np.stack([synthetic.spd_hessian(n, rng) for _ in range(B)])
+    s = rng.normal(0, 0.05, (B, n))
+    y = np.einsum("bij,bj->bi", H, s) + rng.normal(0, 5e-3, (B, n))
+    y[1] = -y[1]            # negative curvature -> skipped
+    s[2] *= 1e-12           # tiny step -> skipped
+    Hd = T(H)
+    _, st = ops.hessian_update(Hd, T(s), T(y), method, inplace=True, rsirfo_guards=True)
+    got, st = Hd.cpu().numpy(), st.cpu().numpy()
+    for b in range(B):
+        exp, upd = O.rsirfo_update_hessian(H[b], s[b], y[b], np.zeros(n), np.zeros(n), method)
+        assert bool(st[b] & ops.ST_UPDATED) == upd
+        assert rel(got[b], exp) < RTOL
+    assert st[1] & ops.ST_UPD_SKIP_CURV and st[2] & ops.ST_UPD_SKIP_SMALL
+
+
+def test_hessian_update_operator_classes(golden_dir):
+    z = np.load(os.path.join(golden_dir, "update_deltas.npz"))
+    i = int(np.where((z["method"] == 23) & (z["kind"] == 0))[0][0])
+    d = ModelHessianUpdate(device=DEV).Bofill_hessian_update(z["H"][i], z["s"][i].reshape(-1, 1), z["y"][i].reshape(-1, 1))
+    assert rel(d, z["delta"][i]) < RTOL
+    i = int(np.where((z["method"] == 11) & (z["kind"] == 0))[0][0])
+    d = BlockHessianUpdate(device=DEV).block_FSB_hessian_update(z["H"][i], z["s"][i].reshape(-1, 1), z["y"][i].reshape(-1, 1))
+    assert np.linalg.norm(d - z["delta"][i]) / np.linalg.norm(z["H"][i]) < RTOL
+
+
+# ----------------------------------------------------------------------- projection
+def test_projection_vs_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "projection.npz"))
+    for i, na in enumerate(z["natoms"]):
+        n = 3 * int(na)
+        x, H, g = z["x"][i, :n], z["H"][i, :n, :n], z["g"][i, :n]
+        Hp, gp, st = ops.project_trrot(T(H[None]), T(x[None]), g=T(g[None]))
+        assert rel(Hp[0].cpu().numpy(), z["Hp"][i, :n, :n]) < 1e-12
+        assert rel(gp[0].cpu().numpy(), z["gp"][i, :n]) < 1e-12
+        Hp_np = Hp[0].cpu().numpy()
+        assert np.array_equal(Hp_np, Hp_np.T)
+
+
+def test_projection_with_bias_and_asymmetric_input():
+    rng = np.random.default_rng(5)
+    n = 90
+    x = synthetic.grid_geometry(30, rng).reshape(-1)
+    H = synthetic.spd_hessian(n, rng) + 1e-3 * rng.standard_normal((n, n))   # not symmetric
+    Hb = 0.05 * synthetic.spd_hessian(n, rng)
+    Hp, _, _ = ops.project_trrot(T(H[None]), T(x[None]), Hbias=T(Hb[None]))
+    assert rel(Hp[0].cpu().numpy(), O.project_hessian_trrot(H + Hb, x)) < 1e-12
+
+
+# --------------------------------------------------------------------------- eigh
+@pytest.mark.parametrize("algo", ["jacobi", "auto"])
+@pytest.mark.parametrize("n", [3, 24, 33, 90, 149, 150, 200])
+def test_eigh_vs_lapack(n, algo):
+    rng = np.random.default_rng(n)
+    B = 6
+    A = rng.standard_normal((B, n, n))
+    A = 0.5 * (A + A.transpose(0, 2, 1))
+    if n % 3 == 0:       # projected Hessian: exact 6-dimensional null space
+        x = synthetic.grid_geometry(n // 3, rng).reshape(-1)
+        A[0] = O.project_hessian_trrot(synthetic.spd_hessian(n, rng), x)
+    A[1] = np.diag(np.arange(n, dtype=float))            # already diagonal
+    w, V = np.linalg.eigh(A[2]); w[: n // 2] = 0.5       # heavy degeneracy
+    A[2] = (V * w) @ V.T; A[2] = 0.5 * (A[2] + A[2].T)
+    evals, evecs, st = ops.eigh(T(A), algo)
+    evals, evecs = evals.cpu().numpy(), evecs.cpu().numpy()
+    assert not (st.cpu().numpy() & ops.ST_EIG_NOCONV).any()
+    for b in range(B):
+        ref = np.linalg.eigvalsh(A[b])
+        scale = np.abs(ref).max()
+        assert np.abs(evals[b] - ref).max() <= 1e-13 * scale * max(1, n / 10)
+        Vb = evecs[b].T                                   # columns = eigenvectors
+        assert np.abs(Vb.T @ Vb - np.eye(n)).max() < 1e-12
+        assert np.abs(A[b] @ Vb - Vb * evals[b]).max() < 1e-12 * scale * n
+
+
+# ------------------------------------------------------------------------ rsirfo
+def _trace_names(golden_dir):
+    z = np.load(os.path.join(golden_dir, "rsirfo_traces.npz"))
+    return z, [str(s) for s in z["names"]]
+
+
+@pytest.mark.parametrize("idx", range(20))
+def test_rsirfo_trace_vs_reference_golden(golden_dir, idx):
+    """Drop-in class, reference calling convention (NumPy (n,1) arrays)."""
+    z, names = _trace_names(golden_dir)
+    name = names[idx]
+    so, natoms, nsteps, bias, neb = [int(v) for v in z[f"{name}/meta"]]
+    opt = RSIRFO(method=str(z[f"{name}/method"]), saddle_order=so, element_list=["C"] * natoms,
+                 trust_radius_max=(0.1 if so > 0 else 0.5), trust_radius_min=0.01, device=DEV)
+    if neb:
+        opt.switch_NEB_mode()
+    Hstate = z[f"{name}/H0"].copy()
+    opt.set_hessian(Hstate)
+    opt.set_bias_hessian(z[f"{name}/Hb"].copy())
+    X, BG, G, BE = z[f"{name}/x"], z[f"{name}/Bg"], z[f"{name}/g"], z[f"{name}/Be"]
+    col = lambda a: a.reshape(-1, 1).copy()
+    for k in range(nsteps):
+        if k == 0:
+            mv = opt.run(col(X[k]), col(BG[k]), [], [], float(BE[k]), 0.0, [], col(X[0]), col(G[k]), [])
+        else:
+            mv = opt.run(col(X[k]), col(BG[k]), [], col(X[k - 1]), float(BE[k]), 0.0, [], col(X[0]),
+                         col(G[k]), col(G[k - 1]))
+        assert mv.shape == (3 * natoms, 1)
+        assert rel(mv.ravel(), z[f"{name}/move"][k]) < RTOL, (name, k)
+        assert rel(opt.hessian, z[f"{name}/H_after"][k]) < RTOL, (name, k)
+        assert opt.hessian is Hstate                      # aliasing kept
+        assert abs(opt.trust_radius - z[f"{name}/trust"][k]) < 1e-14, (name, k)
+        p = z[f"{name}/pred"][k]
+        assert abs(opt.predicted_energy_changes[-1] - p) <= RTOL * abs(p) + 1e-16, (name, k)
+
+
+@pytest.mark.parametrize("natoms,saddle,method", [(50, 0, "rsirfo_bfgs"), (30, 1, "rsirfo_block_bofill"),
+                                                    (24, 0, "rsirfo_block_fsb"), (8, 0, "rsirfo_bofill")])
+def test_rsirfo_batched_vs_oracle(natoms, saddle, method):
+    """Tensor mode: B structures per launch, two consecutive steps, vs the oracle."""
+    B = 24
+    n = 3 * natoms
+    x0, H0, g0, rngs = synthetic.batch(2, B, natoms, saddle=saddle > 0)
+    opt = RSIRFO(method=method, saddle_order=saddle, device=DEV)
+    Hd = T(H0)
+    opt.set_hessian(Hd)
+    opt.set_bias_hessian(None)
+    mv0 = opt.run(T(x0), T(g0), B_e=torch.zeros(B, dtype=torch.float64, device=DEV), g=T(g0)).cpu().numpy().copy()
+    x1 = np.empty_like(x0); g1 = np.empty_like(g0)
+    oracles = []
+    for b in range(B):
+        o = O.RSIRFOOracle(method=method, saddle_order=saddle)
+        o.set_hessian(H0[b].copy()); o.set_bias_hessian(None)
+        m = o.run(x0[b], g0[b], g0[b], None, None, 0.0)
+        assert rel(mv0[b], m) < RTOL, ("step0", b)
+        x1[b], g1[b] = synthetic.second_point(x0[b], H0[b], g0[b], m, rngs[b])
+        oracles.append(o)
+    mv1 = opt.run(T(x1), T(g1), pre_geom=T(x0), B_e=torch.full((B,), -1e-3, dtype=torch.float64, device=DEV),
+                  g=T(g1), pre_g=T(g0)).cpu().numpy()
+    Hn = Hd.cpu().numpy()
+    lam = opt._out["eigvals"].cpu().numpy()
+    for b, o in enumerate(oracles):
+        m = o.run(x1[b], g1[b], g1[b], x0[b], g0[b], -1e-3)
+        assert rel(mv1[b], m) < RTOL, ("step1", b)
+        assert rel(Hn[b], o.hessian) < RTOL
+        ref = o.last["eigvals"]
+        assert np.abs(lam[b] - ref).max() <= RTOL * np.abs(ref).max()
