@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py — batched RS-I-RFO + Hessian-update steps/s (FP64) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): B = 1024 independent structures per GPU,
+N = 50 atoms (n = 150), `rsirfo_bfgs`, FP64; the timed unit is "step 1" of a
+two-step sequence (history present, Hessian update active, s.y > 0), SURVEY §8d.
+One bench "step" = one pass of the hot path over the whole batch; `value` counts
+structure-steps per second over all ranks (weak scaling: per-GPU batch fixed).
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "batched RFO+Hessian-update steps/sec (FP64)"
+UNIT = "structure-steps/s"
+NATOMS = 50
+BATCH = 1024
+METHOD = "rsirfo_bfgs"
+CONFIG_ID = 2
+
+
+def workload_config(B, extra=None):
+    cfg = {"workload": f"configs[1]: synthetic batch {B} independent RFO-BFGS minimisation steps, "
+                       f"N={NATOMS} atoms (3N={3 * NATOMS}), FP64, step 1 of 2 (update active)",
+           "batch_per_gpu": B, "natoms": NATOMS, "n": 3 * NATOMS, "method": METHOD,
+           "saddle_order": 0, "parallelism": "independent structures sharded by rank, no collective",
+           "l2": "inputs larger than L2 (per-step Hessian batch 184 MB, rotating pristine copies)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------- inputs
+def make_inputs(B, rank):
+    """Step-1 inputs for B structures (seed = 1000*config + global index).  Step 0 is
+    run through the NumPy oracle on a few structures and through the CUDA path on all
+    of them by the caller; here only the seeded raw data is produced."""
+    from multioptpy_b200 import synthetic
+    x0 = np.empty((B, 3 * NATOMS)); H0 = np.empty((B, 3 * NATOMS, 3 * NATOMS)); g0 = np.empty((B, 3 * NATOMS))
+    rngs = []
+    for b in range(B):
+        x0[b], H0[b], g0[b], rng = synthetic.structure(CONFIG_ID, rank * B + b, NATOMS)
+        rngs.append(rng)
+    return x0, H0, g0, rngs
+
+
+# ---------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import contextlib, io
+    from oracle import np_oracle as O
+    from multioptpy_b200 import synthetic
+    idx_list = args
+    prepared = []
+    for gi in idx_list:
+        x0, H0, g0, rng = synthetic.structure(CONFIG_ID, gi, NATOMS)
+        o = O.RSIRFOOracle(method=METHOD, saddle_order=0)
+        o.set_hessian(H0.copy()); o.set_bias_hessian(None)
+        m = o.run(x0, g0, g0, None, None, 0.0)
+        x1, g1 = synthetic.second_point(x0, H0, g0, m, rng)
+        prepared.append((o, x0, g0, x1, g1))
+    t0 = time.perf_counter()
+    for o, x0, g0, x1, g1 in prepared:
+        o.run(x1, g1, g1, x0, g0, -1e-3)
+    return time.perf_counter() - t0, len(prepared)
+
+
+def cpu_baseline(sample, cores):
+    """Oracle port (NumPy restatement of RSIRFO.run) on `cores` host processes, one
+    BLAS thread each; returns structure-steps/s over the timed step-1 calls."""
+    import multiprocessing as mp
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    chunks = [list(range(w, sample, cores)) for w in range(cores)]
+    chunks = [c for c in chunks if c]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(len(chunks)) as pool:
+        res = pool.map(_cpu_worker, chunks)
+    wall = max(t for t, _ in res)          # workers run concurrently
+    done = sum(k for _, k in res)
+    return done / wall, len(chunks)
+
+
+# ------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.t = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks", 0x100: "display"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=1)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = min(BATCH, max(cores * 8, 64))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(min(sample, cores * 2), cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, used = cpu_baseline(sample, cores)
+        vals.append(v)
+    v = statistics.median(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(BATCH),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port",
+                             "sample": f"{sample} structures of the same seeded batch per step, step-1 calls timed, "
+                                       f"one process per core, 1 BLAS thread each (oracle/np_oracle.py; "
+                                       f"/root/reference is not present on the GPU box)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ B200 arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    from multioptpy_b200 import _lib, ops
+    from multioptpy_b200.Optimizer.rsirfo import RSIRFO
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lib = _lib.load()
+    B, n = BATCH, 3 * NATOMS
+    K, W = args.steps, args.warmup
+    f64 = torch.float64
+
+    # ---- inputs: step 0 on the device for every structure, then the step-1 points ----
+    x0, H0, g0, rngs = make_inputs(B, rank)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    from multioptpy_b200 import synthetic
+    opt0 = RSIRFO(method=METHOD, saddle_order=0, device=dev)
+    H_d0 = T(H0)
+    opt0.set_hessian(H_d0); opt0.set_bias_hessian(None)
+    zero = torch.zeros(B, dtype=f64, device=dev)
+    mv0 = opt0.run(T(x0), T(g0), B_e=zero, g=T(g0)).cpu().numpy().copy()
+    state1 = opt0.state_tensor.clone()              # RSIRFO state after step 0
+    x1 = np.empty_like(x0); g1 = np.empty_like(g0)
+    for b in range(B):
+        x1[b], g1[b] = synthetic.second_point(x0[b], H0[b], g0[b], mv0[b], rngs[b])
+    x0_d, g0_d, x1_d, g1_d = T(x0), T(g0), T(x1), T(g1)
+    Be1 = zero - 1e-3
+
+    # parity spot check against the oracle (checker only, not timed, not shipped)
+    from oracle import np_oracle as O
+    chk = min(4, B)
+    Hc = H_d0[:chk].clone(); stc = state1[:chk].clone()
+    outc = ops.rsirfo_step(Hc, x1_d[:chk].contiguous(), g1_d[:chk].contiguous(), g1_d[:chk].contiguous(), stc,
+                           method=ops.resolve_update_method(METHOD), x_prev=x0_d[:chk].contiguous(),
+                           g_prev=g0_d[:chk].contiguous(), Be=Be1[:chk].contiguous())
+    worst = 0.0
+    for b in range(chk):
+        o = O.RSIRFOOracle(method=METHOD, saddle_order=0)
+        o.set_hessian(H0[b].copy()); o.set_bias_hessian(None)
+        o.run(x0[b], g0[b], g0[b], None, None, 0.0)
+        m = o.run(x1[b], g1[b], g1[b], x0[b], g0[b], -1e-3)
+        worst = max(worst, float(np.linalg.norm(outc["move"][b].cpu().numpy() - m) / np.linalg.norm(m)))
+    if not worst < 1e-10:
+        raise SystemExit(f"bench.py: parity check failed before timing ({worst:.3e})")
+
+    # ---- rotating pristine copies (each timed step sees an un-updated Hessian batch) ----
+    ncopy = max(2, min(K + W, 24))
+    Hs = [H_d0.clone() for _ in range(ncopy)]
+    sts = [state1.clone() for _ in range(ncopy)]
+    method_id = ops.resolve_update_method(METHOD)
+    out = None
+
+    def one_step(i):
+        nonlocal out
+        j = i % ncopy
+        out = ops.rsirfo_step(Hs[j], x1_d, g1_d, g1_d, sts[j], method=method_id, x_prev=x0_d,
+                              g_prev=g0_d, Be=Be1, out=out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        one_step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=f64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- e2e: host buffers -> C ABI -> host buffers, copies inside the timed region ----
+    nchunk = 8
+    cb = B // nchunk
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hH, hx1, hg1, hx0, hg0 = pin(H0), pin(x1), pin(g1), pin(x0), pin(g0)
+    hBe = pin(np.full(B, -1e-3)); hst = state1.cpu().pin_memory()
+    h_move = torch.empty(B, n, dtype=f64).pin_memory()
+    h_Hout = torch.empty(B, n, n, dtype=f64).pin_memory()
+    h_stat = torch.empty(B, dtype=torch.int32).pin_memory()
+    streams = [torch.cuda.Stream(dev) for _ in range(3)]
+    dbuf = [dict(H=torch.empty(cb, n, n, dtype=f64, device=dev), x1=torch.empty(cb, n, dtype=f64, device=dev),
+                 g1=torch.empty(cb, n, dtype=f64, device=dev), x0=torch.empty(cb, n, dtype=f64, device=dev),
+                 g0=torch.empty(cb, n, dtype=f64, device=dev), Be=torch.empty(cb, dtype=f64, device=dev),
+                 st=torch.empty(cb, ops.RSIRFO_STATE, dtype=f64, device=dev), out=None) for _ in range(3)]
+    h2d = (hH.numel() + hx1.numel() * 4 + hBe.numel() + hst.numel()) * 8
+    d2h = (h_move.numel() + h_Hout.numel()) * 8 + h_stat.numel() * 4
+
+    def e2e_step():
+        for c in range(nchunk):
+            s = streams[c % 3]; d = dbuf[c % 3]; sl = slice(c * cb, (c + 1) * cb)
+            with torch.cuda.stream(s):
+                d["H"].copy_(hH[sl], non_blocking=True); d["x1"].copy_(hx1[sl], non_blocking=True)
+                d["g1"].copy_(hg1[sl], non_blocking=True); d["x0"].copy_(hx0[sl], non_blocking=True)
+                d["g0"].copy_(hg0[sl], non_blocking=True); d["Be"].copy_(hBe[sl], non_blocking=True)
+                d["st"].copy_(hst[sl], non_blocking=True)
+                d["out"] = ops.rsirfo_step(d["H"], d["x1"], d["g1"], d["g1"], d["st"], method=method_id,
+                                           x_prev=d["x0"], g_prev=d["g0"], Be=d["Be"], out=d["out"])
+                h_move[sl].copy_(d["out"]["move"], non_blocking=True)
+                h_Hout[sl].copy_(d["H"], non_blocking=True)
+                h_stat[sl].copy_(d["out"]["status"], non_blocking=True)
+        for s in streams:
+            s.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    Ke = max(3, min(K, 10))
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=f64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * B * Ke / e2e_s
+    e2e_ok = bool(np.isfinite(h_move.numpy()).all())
+
+    # ---- e2e with the Hessian batch resident on the device (steady-state drop-in) -------
+    d_x1, d_g1 = torch.empty_like(x1_d), torch.empty_like(g1_d)
+    h_mv2 = torch.empty(B, n, dtype=f64).pin_memory()
+
+    def e2e_resident(i):
+        nonlocal out
+        j = i % ncopy
+        d_x1.copy_(hx1, non_blocking=True); d_g1.copy_(hg1, non_blocking=True)
+        out = ops.rsirfo_step(Hs[j], d_x1, d_g1, d_g1, sts[j], method=method_id, x_prev=x0_d, g_prev=g0_d,
+                              Be=Be1, out=out)
+        h_mv2.copy_(out["move"], non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_resident(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_resident(i + 1)
+    res_s = time.perf_counter() - t0
+    e2e_res_val = world * B * Ke / res_s
+
+    line = None
+    if rank == 0:
+        # ---- FP64 peak probe + roofline of the dominant kernel (eigensolver) -------------
+        probe = torch.empty(148 * 16 * 256, dtype=f64, device=dev)
+        iters = 4096
+        for _ in range(2):
+            _lib.check(lib.mop_bench_dfma(148 * 16, iters, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        best = 1e30
+        for _ in range(5):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.mop_bench_dfma(148 * 16, iters, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            b_.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b_))
+        fp64_peak = 148 * 16 * 256 * iters * 64 * 2 / (best * 1e-3) / 1e12   # TFLOP/s
+
+        Hp, gp_, _ = ops.project_trrot(H_d0, x1_d, g=g1_d)
+        for _ in range(2):
+            ops.eigh(Hp)
+        torch.cuda.synchronize()
+        reps = max(3, min(K, 10))
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            ops.eigh(Hp)
+        b_.record(); torch.cuda.synchronize()
+        eig_ms = a.elapsed_time(b_) / reps
+        WF = 9.0 * n ** 3                      # algorithmic flops of one eigh with vectors
+        eig_tflops = B * WF / (eig_ms * 1e-3) / 1e12
+        # streaming update kernel against the HBM roofline
+        sd = (x1_d - x0_d).contiguous(); yd = (g1_d - g0_d).contiguous()
+        Hu = H_d0.clone()
+        ops.hessian_update(Hu, sd, yd, method_id, inplace=True, rsirfo_guards=True)
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for j in range(reps):
+            ops.hessian_update(Hs[j % ncopy], sd, yd, method_id, inplace=True, rsirfo_guards=True)
+        b_.record(); torch.cuda.synchronize()
+        upd_ms = a.elapsed_time(b_) / reps
+        upd_gbs = B * (16.0 * n * n + 32.0 * n) / (upd_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+        cores = os.cpu_count() or 1
+        sample = min(B, max(64, cores * 4))
+        cpu_val, used = cpu_baseline(sample, cores)
+
+        step_tflops_alg = value / world * (9.0 * n ** 3 + 40.0 * n * n) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(B, {"eigh": "auto", "parity_vs_oracle": worst}),
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "pinned host buffers incl. the Hessian batch both ways, 8 chunks on 3 streams",
+                    "finite": e2e_ok},
+            "e2e_hessian_resident": {"value": e2e_res_val, "unit": UNIT,
+                                     "h2d_bytes_per_step": 2 * B * n * 8, "d2h_bytes_per_step": B * n * 8},
+            "gpu_launches": 4 * K,
+            "roofline": {"bound": "fp64", "kernel": "batched symmetric eigensolver (dominant kernel of the step)",
+                         "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": eig_tflops / fp64_peak, "traffic": None,
+                         "algorithmic_flops_per_launch": B * WF, "kernel_ms": eig_ms,
+                         "peak_source": "in-run DFMA probe (mop_bench_dfma); MEASURED_PEAKS.json has no FP64 figure",
+                         "whole_step_algorithmic_tflops": step_tflops_alg,
+                         "whole_step_frac": step_tflops_alg / fp64_peak},
+            "roofline_hbm": {"bound": "hbm", "kernel": "fused Hessian update (k_hessian_update)",
+                             "achieved": upd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": upd_gbs / hbm_peak,
+                             "traffic": None, "kernel_ms": upd_ms, "peak_source": hbm_src},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": used, "kind": "port",
+                             "sample": f"{sample} structures of the same batch, step-1 calls timed, one process per "
+                                       f"core, 1 BLAS thread each (oracle/np_oracle.py)"},
+        }
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,12 @@ int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode, in
 int mop_clamp_and_move(int B, int n, const double* x, double* move, const double* trust_outer,
                        double* x_new_ang, void* stream);
 
+/* ---- measurement helpers (bench.py) -----------------------------------------
+ * mop_bench_dfma: FP64 FMA peak probe; one launch = blocks*256*iters*64*2 FLOPs.
+ * mop_bench_fill: write `count` doubles (L2 flush when the buffer exceeds L2). */
+int mop_bench_dfma(int blocks, int iters, double* out, void* stream);
+int mop_bench_fill(double* buf, size_t count, double value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

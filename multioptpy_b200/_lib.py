@@ -35,6 +35,8 @@ SIGNATURES = {
     "mop_rsirfo_step": (_i, [_i, _i, _i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                              _p, _p, _p, _p, _sz, _p]),
     "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
+    "mop_bench_dfma": (_i, [_i, _i, _p, _p]),
+    "mop_bench_fill": (_i, [_p, _sz, _d, _p]),
 }
 
 _lib = None
