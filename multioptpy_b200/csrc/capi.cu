@@ -23,9 +23,13 @@ int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double
                             int32_t* status, void* work, size_t work_bytes, cudaStream_t stream);
 int mop_launch_rfo_step(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
                         const double* evals, const double* evecs, const double* gp,
-                        const double* Bg, const double* Hp, const double* Be, double* state,
+                        const double* Bg, const double* Be, double* state,
                         double* move, double* evals_out, double* pred, int32_t* status,
-                        cudaStream_t stream);
+                        int only_flagged, cudaStream_t stream);
+int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
+                            const double* Hp, const double* gp, const double* Bg, const double* Be,
+                            double* state, double* move, double* evals_out, double* pred,
+                            int32_t* status, void* work, size_t work_bytes, cudaStream_t stream);
 
 static thread_local char g_err[512] = "";
 
@@ -146,10 +150,27 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   // (2) TR/ROT projection of gradient and effective Hessian (rsirfo.py:337,349-358)
   rc = mop_launch_project_trrot(B, n, H, Hbias, x, Bg, Hp, gp, status, stream);
   if (rc != MOP_OK) return rc;
+  if (pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG) {
+    // (3+4 fused) tridiagonalise, solve and step in one shared-memory-resident kernel;
+    // structures it flags (tight eigenvalue clusters) are redone by the robust path.
+    if (!mop_tridiag_supported(n)) {
+      mop_set_error("mop_rsirfo_step: tridiagonal path does not support n = %d", n);
+      return MOP_ERR_UNSUPPORTED;
+    }
+    const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
+    rc = mop_launch_rsirfo_fused(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,
+                                 state, move_out, eigvals_out, pred_out, status, (char*)ework + jac,
+                                 ebytes - jac, stream);
+    if (rc != MOP_OK) return rc;
+    rc = mop_launch_eigh_jacobi(B, n, Hp, evals, evecs, status, status, ework, jac, stream);
+    if (rc != MOP_OK) return rc;
+    return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, gp,
+                               Bg, Be, state, move_out, eigvals_out, pred_out, status, 1, stream);
+  }
   // (3) eigendecomposition (rsirfo.py:360)
   rc = run_eigh(B, n, eigh_algo, Hp, evals, evecs, status, ework, ebytes, stream);
   if (rc != MOP_OK) return rc;
   // (4) image function, secular solve, step, bookkeeping (rsirfo.py:365-490)
   return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, gp,
-                             Bg, Hp, Be, state, move_out, eigvals_out, pred_out, status, stream);
+                             Bg, Be, state, move_out, eigvals_out, pred_out, status, 0, stream);
 }

@@ -95,7 +95,7 @@ def test_projection_with_bias_and_asymmetric_input():
 
 
 # --------------------------------------------------------------------------- eigh
-@pytest.mark.parametrize("algo", ["jacobi", "auto"])
+@pytest.mark.parametrize("algo", ["jacobi", "tridiag", "auto"])
 @pytest.mark.parametrize("n", [3, 24, 33, 90, 149, 150, 200])
 def test_eigh_vs_lapack(n, algo):
     rng = np.random.default_rng(n)
@@ -108,6 +108,8 @@ def test_eigh_vs_lapack(n, algo):
     A[1] = np.diag(np.arange(n, dtype=float))            # already diagonal
     w, V = np.linalg.eigh(A[2]); w[: n // 2] = 0.5       # heavy degeneracy
     A[2] = (V * w) @ V.T; A[2] = 0.5 * (A[2] + A[2].T)
+    if algo == "tridiag" and n > 158:
+        pytest.skip("shared-memory tridiagonal path supports n <= 158")
     evals, evecs, st = ops.eigh(T(A), algo)
     evals, evecs = evals.cpu().numpy(), evecs.cpu().numpy()
     assert not (st.cpu().numpy() & ops.ST_EIG_NOCONV).any()
