@@ -164,6 +164,9 @@ int mop_clamp_and_move(int B, int n, const double* x, double* move, const double
  * mop_bench_fill: write `count` doubles (L2 flush when the buffer exceeds L2). */
 int mop_bench_dfma(int blocks, int iters, double* out, void* stream);
 int mop_bench_fill(double* buf, size_t count, double value, void* stream);
+/* diagnostics: device buffer [B][8] int64 receiving per-phase SM clock counts of the
+ * tridiagonal / fused kernel (NULL switches it off).  Not thread-safe; tools only. */
+int mop_debug_tri_timing(void* buf);
 
 #ifdef __cplusplus
 }

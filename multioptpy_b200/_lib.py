@@ -37,6 +37,7 @@ SIGNATURES = {
     "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "mop_bench_dfma": (_i, [_i, _i, _p, _p]),
     "mop_bench_fill": (_i, [_p, _sz, _d, _p]),
+    "mop_debug_tri_timing": (_i, [_p]),
 }
 
 _lib = None

@@ -54,6 +54,7 @@ struct TriArgs {
   double* pred;      // [B]
   int saddle_order, neb_mode;
   double tmin, tmax;
+  long long* dbg;    // optional [B][8] phase clocks (diagnostics)
 };
 
 // number of eigenvalues of the unreduced block rows [s, t) that are < x
@@ -114,6 +115,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   int st_in = a.status ? a.status[b] : 0;
   st_in &= ~(MOP_ST_EIG_FALLBACK | MOP_ST_EIG_NOCONV);
 
+  long long t_prev = clock64();
+  int t_slot = 0;
+#define TRI_MARK()                                                      \
+  do {                                                                  \
+    if (a.dbg && tid == 0) {                                            \
+      const long long t_now = clock64();                                \
+      a.dbg[(size_t)b * 8 + (t_slot++)] = t_now - t_prev;               \
+      t_prev = t_now;                                                   \
+    }                                                                   \
+  } while (0)
   // ---- load (symmetrised) ---------------------------------------------------------
   double pn = 0.0;
   for (int idx = tid; idx < n * n; idx += THREADS) {
@@ -131,6 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   double* v = X;
   double* w = X + np;
   double* part = X + 2 * np;
+  TRI_MARK();  // 0: load
 
   // ---- phase 1: tridiagonalisation ---------------------------------------------------
   if (!trivial) {
@@ -211,6 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     __syncthreads();
   }
 
+  TRI_MARK();  // 1: tridiagonalisation
   // ---- fused: gq = Q^T gp by the last warp (overlaps with the spill below) ----------------
   if (a.fused) {
     for (int i = tid; i < n; i += THREADS) gq[i] = a.gp[(size_t)b * n + i];
@@ -267,6 +280,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     }
     __syncthreads();
 
+    TRI_MARK();  // 2: Q^T g, spill, scale, split
     // ---- phase 2: multisection on the Sturm count --------------------------------------------
     double* lo = X;
     double* hi = X + np;
@@ -327,6 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     for (int i = tid; i < n; i += THREADS) lam[i] = 0.5 * (lo[i] + hi[i]);
     __syncthreads();
 
+    TRI_MARK();  // 3: multisection
     // ---- phase 3: twisted-factorisation eigenvectors, thread i -> column i of S ----------------
     for (int i = tid; i < n; i += THREADS) {
       const int s = blk_s[i], t = blk_e[i];
@@ -404,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     }
     __syncthreads();
 
+    TRI_MARK();  // 4: twisted vectors
     // ---- phase 4: CGS2 inside clusters, one warp per cluster -------------------------------------
     double* dots = X;  // NW * 64
     for (int c0 = wid; c0 < n; c0 += NW) {
@@ -458,6 +474,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     __syncthreads();
   }
 
+  TRI_MARK();  // 5: cluster re-orthogonalisation
   if (s_fallback) {  // robust path will redo this structure; leave state untouched
     if (tid == 0 && a.status) a.status[b] = st_in | MOP_ST_EIG_FALLBACK;
     return;
@@ -498,6 +515,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
       const int r = idx / n, k = idx - r * n;
       evecs[idx] = S[k * lds + inv[r]];
     }
+    TRI_MARK();  // 6: back-transform + output
     if (tid == 0 && a.status) a.status[b] = st_in;
     return;
   }
@@ -553,6 +571,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     }
     for (int j = lane; j < n; j += 32) a.move[(size_t)b * n + j] = -y[j];
   }
+  TRI_MARK();  // 6: eigenbasis RFO + back-transform
   if (tid == 0 && a.status) {
     const int keep = st_in & (MOP_ST_UPDATED | MOP_ST_UPD_SKIP_SMALL | MOP_ST_UPD_SKIP_CURV |
                               MOP_ST_UPD_TERM_ZEROED | MOP_ST_NO_HISTORY | MOP_ST_TRROT_RANKDEF);
@@ -563,6 +582,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
 }  // namespace mop
 
 // ---------------------------------------------------------------------------------------------
+static long long* g_tri_dbg = nullptr;
+// diagnostics: device buffer [B][8] receiving per-phase clock counts of the next launches
+extern "C" int mop_debug_tri_timing(void* buf) {
+  g_tri_dbg = (long long*)buf;
+  return MOP_OK;
+}
+
 static int tri_threads(int n) {
   if (3 * n <= 128) return 128;
   if (3 * n <= 256) return 256;
@@ -614,6 +640,7 @@ int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double
   a.evals = evals;
   a.evecs = evecs;
   a.status = status;
+  a.dbg = g_tri_dbg;
   return launch_tri_any(B, a, stream);
 }
 
@@ -648,5 +675,6 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
   a.neb_mode = neb_mode;
   a.tmin = tmin;
   a.tmax = tmax;
+  a.dbg = g_tri_dbg;
   return launch_tri_any(B, a, stream);
 }
