@@ -167,6 +167,8 @@ int mop_bench_fill(double* buf, size_t count, double value, void* stream);
 /* diagnostics: device buffer [B][8] int64 receiving per-phase SM clock counts of the
  * tridiagonal / fused kernel (NULL switches it off).  Not thread-safe; tools only. */
 int mop_debug_tri_timing(void* buf);
+/* diagnostics: out[i] = the kernels' division-free reciprocal of x[i] (accuracy test). */
+int mop_debug_fast_rcp(const double* x, double* out, size_t count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ SIGNATURES = {
     "mop_bench_dfma": (_i, [_i, _i, _p, _p]),
     "mop_bench_fill": (_i, [_p, _sz, _d, _p]),
     "mop_debug_tri_timing": (_i, [_p]),
+    "mop_debug_fast_rcp": (_i, [_p, _p, _sz, _p]),
 }
 
 _lib = None

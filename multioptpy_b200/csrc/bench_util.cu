@@ -25,6 +25,11 @@ __global__ void k_fill(double* p, size_t n, double v) {
     p[i] = v;
 }
 
+__global__ void k_fast_rcp(const double* x, double* out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = fast_rcp(x[i]);
+}
+
 }  // namespace mop
 
 // Launches blocks x 256 threads, each doing iters * 64 dependent-chain-interleaved DFMAs.
@@ -40,6 +45,14 @@ extern "C" int mop_bench_dfma(int blocks, int iters, double* out, void* stream) 
 extern "C" int mop_bench_fill(double* buf, size_t count, double value, void* stream) {
   MOP_REQUIRE(buf && count > 0, "mop_bench_fill: bad arguments");
   mop::k_fill<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(buf, count, value);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+// out[i] = fast_rcp(x[i]) (the division-free reciprocal used by the twisted factorisation)
+extern "C" int mop_debug_fast_rcp(const double* x, double* out, size_t count, void* stream) {
+  MOP_REQUIRE(x && out && count > 0, "mop_debug_fast_rcp: bad arguments");
+  mop::k_fast_rcp<<<148, 256, 0, (cudaStream_t)stream>>>(x, out, count);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }

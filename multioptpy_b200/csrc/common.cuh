@@ -57,6 +57,39 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
   return scratch[32];
 }
 
+// Single-barrier block reductions.  `buf` is a [2][32*K] double scratch in shared
+// memory and `parity` a per-thread counter toggled on every call: consecutive
+// reductions alternate buffers, so one __syncthreads per reduction is enough (the
+// barrier of call i+1 orders the reads of call i before the writes of call i+2).
+// Every warp re-reduces the per-warp partials, so all threads get the result.
+template <int K>
+__device__ __forceinline__ void block_sum_k(double (&v)[K], double* buf, int& parity) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  double* b = buf + (parity & 1) * (32 * K);
+  parity ^= 1;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) b[k * 32 + w] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(lane < nw ? b[k * 32 + lane] : 0.0);
+}
+
+// ~1 ulp reciprocal without the IEEE slow path: MUFU seed + two Newton steps.
+// Valid for normal, non-tiny |x| (callers clamp pivots away from zero).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 __device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); }
 
 // y[i] = sum_j A[i][j] * v[j] for a row-major n x n matrix (lda) in global or

@@ -42,6 +42,7 @@ struct TriArgs {
   int fused;  // 0: eigh (evals/evecs out)   1: fused RS-I-RFO step
   const double* A;   // [B][n][n] input matrix (projected Hessian in fused mode)
   double* Vh;        // [B][n][n] scratch: reflector rows
+  double* Dm;        // [B][n][n] scratch: backward reciprocal pivots
   double* evals;     // [B][n] out (ascending)
   double* evecs;     // [B][n][n] out (eigh mode), row k = vector k
   int32_t* status;
@@ -59,24 +60,44 @@ struct TriArgs {
 
 // number of eigenvalues of the unreduced block rows [s, t) that are < x
 // (sign changes of p_k = (d_k - x) p_{k-1} - e_{k-1}^2 p_{k-2}); d, e2 scaled to ||T|| <= 1.
+// The dependent chain is one DFMA per row: (d_k - x) and the loads are hoisted four rows
+// ahead, signs are compared on the high word, and the magnitude is checked (and both
+// iterates rescaled) once per four rows.  An exact zero needs no special case: whichever
+// sign it is given, the pair (k-1, k+1) contributes exactly one sign change.
 __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2,
                                            int s, int t, double x) {
   double pm1 = 1.0;
   double p = d[s] - x;
-  if (p == 0.0) p = -1e-300;
-  int cnt = p < 0.0;
-  for (int k = s + 1; k < t; ++k) {
-    double pn = fma(d[k] - x, p, -(e2[k - 1] * pm1));
-    if (pn == 0.0) pn = (p < 0.0) ? 1e-300 * fabs(p) + 1e-320 : -(1e-300 * fabs(p) + 1e-320);
-    cnt += ((pn < 0.0) != (p < 0.0));
+  int cnt = (unsigned)__double2hiint(p) >> 31;
+  int k = s + 1;
+  for (; k + 3 < t; k += 4) {
+    const double a0 = d[k] - x, a1 = d[k + 1] - x, a2 = d[k + 2] - x, a3 = d[k + 3] - x;
+    const double b0 = e2[k - 1], b1 = e2[k], b2 = e2[k + 1], b3 = e2[k + 2];
+    const double p0 = fma(a0, p, -(b0 * pm1));
+    const double p1 = fma(a1, p0, -(b1 * p));
+    const double p2 = fma(a2, p1, -(b2 * p0));
+    const double p3 = fma(a3, p2, -(b3 * p1));
+    const int h = __double2hiint(p), h0 = __double2hiint(p0), h1 = __double2hiint(p1),
+              h2 = __double2hiint(p2), h3 = __double2hiint(p3);
+    cnt += ((unsigned)(h ^ h0) >> 31) + ((unsigned)(h0 ^ h1) >> 31) + ((unsigned)(h1 ^ h2) >> 31) +
+           ((unsigned)(h2 ^ h3) >> 31);
+    pm1 = p2;
+    p = p3;
+    const unsigned ex = ((unsigned)h3 >> 20) & 0x7ffu;
+    if (ex - 823u > 400u) {  // |p| outside [2^-200, 2^200]
+      const double a = fmax(fabs(p), fabs(pm1));
+      if (a > 0.0 && a < INFINITY) {
+        const double sc = 1.0 / a;
+        p *= sc;
+        pm1 *= sc;
+      }
+    }
+  }
+  for (; k < t; ++k) {
+    const double pn = fma(d[k] - x, p, -(e2[k - 1] * pm1));
+    cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31;
     pm1 = p;
     p = pn;
-    const double a = fabs(p);
-    if (!(a < 1e100 && a > 1e-100)) {  // rescale both (also catches inf/nan -> stays nan)
-      const double sc = 1.0 / a;
-      p *= sc;
-      pm1 *= sc;
-    }
   }
   return cnt;
 }
@@ -89,7 +110,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   const int np = (n + 3) & ~3;
   const int lds = n | 1;
   // ---- shared memory carve-up --------------------------------------------------
-  double* S = sm;                       // n x lds : A, then pivots, then Z
+  double* S = sm;                       // n x lds : A, then reciprocal pivots, then Z
   double* d = S + (size_t)n * lds;      // np
   double* e = d + np;                   // np   e[k] couples k, k+1
   double* e2 = e + np;                  // np
@@ -99,6 +120,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   double* X = gq + np;                  // phase scratch (aliased):
   //   phase 1: v[np], w[np], part[TRI_GMAX*np]
   //   phase 2: lo[np], hi[np], cnt[3*np] ints
+  //   phase 3: nrm2 parts [2*np], twist index [np] ints
   //   phase 4: dots (NW * 64 doubles)
   //   fused  : lam_s[np], gam_s[np], RfoArrays
   int* blk_s = (int*)(X + tri_x_doubles(n));  // np
@@ -107,11 +129,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   int* rank = cl_s + np;                // np   ascending rank of thread-row i
   int* inv = rank + np;                 // np   inverse permutation
   __shared__ double s_red[40];
+  __shared__ double s_rbuf[2 * 32 * 2];   // reduction (C)
+  __shared__ double s_rbuf1[2 * 32];      // reduction (E)
   __shared__ double s_tnorm;
   __shared__ int s_fallback;
+  int parity = 0;
 
   const double* Ain = a.A + (size_t)b * n * n;
   double* Vh = a.Vh + (size_t)b * n * n;
+  double* Dm = a.Dm + (size_t)b * n * n;
   int st_in = a.status ? a.status[b] : 0;
   st_in &= ~(MOP_ST_EIG_FALLBACK | MOP_ST_EIG_NOCONV);
 
@@ -125,14 +151,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
       t_prev = t_now;                                                   \
     }                                                                   \
   } while (0)
-  // ---- load (symmetrised) ---------------------------------------------------------
+
+  // ---- load.  Fused mode: the projection kernel writes a bit-symmetric matrix, read it
+  // row-wise (coalesced); eigh mode symmetrises arbitrary input. -------------------------
   double pn = 0.0;
-  for (int idx = tid; idx < n * n; idx += THREADS) {
-    const int i = idx / n, j = idx - i * n;
-    const double v = 0.5 * (Ain[idx] + Ain[(size_t)j * n + i]);
-    S[i * lds + j] = v;
-    pn = fma(v, v, pn);
+  if (a.fused) {
+    for (int idx = tid; idx < n * n; idx += THREADS) {
+      const int i = idx / n, j = idx - i * n;
+      const double v = Ain[idx];
+      S[i * lds + j] = v;
+      pn = fma(v, v, pn);
+    }
+  } else {
+    for (int idx = tid; idx < n * n; idx += THREADS) {
+      const int i = idx / n, j = idx - i * n;
+      const double v = 0.5 * (Ain[idx] + Ain[(size_t)j * n + i]);
+      S[i * lds + j] = v;
+      pn = fma(v, v, pn);
+    }
   }
+  if (a.fused)
+    for (int i = tid; i < n; i += THREADS) gq[i] = a.gp[(size_t)b * n + i];
   if (tid == 0) s_fallback = 0;
   const double fro = sqrt(block_sum(pn, s_red));
   const bool finite_in = isfinite(fro);
@@ -144,13 +183,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   double* part = X + 2 * np;
   TRI_MARK();  // 0: load
 
-  // ---- phase 1: tridiagonalisation ---------------------------------------------------
-  if (!trivial) {
+  // ---- phase 1: tridiagonalisation (5 barriers per column) ------------------------------
+  if (!trivial && n > 2) {
+    // norm of the first column below the sub-diagonal
+    double r1[1] = {0.0};
+    for (int j = 2 + tid; j < n; j += THREADS) r1[0] = fma(S[j], S[j], r1[0]);
+    block_sum_k<1>(r1, s_rbuf1, parity);
+    double xn2 = r1[0];
     for (int k = 0; k < n - 2; ++k) {
       double* ak = S + k * lds;
-      double ps = 0.0;
-      for (int j = k + 2 + tid; j < n; j += THREADS) ps = fma(ak[j], ak[j], ps);
-      const double xn2 = block_sum(ps, s_red);
       const double alpha = ak[k + 1];
       double beta = alpha, tk = 0.0, scal = 0.0;
       if (xn2 > 0.0) {
@@ -158,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
         tk = (beta - alpha) / beta;
         scal = 1.0 / (alpha - beta);
       }
-      __syncthreads();  // everyone has read ak[k+1]
+      __syncthreads();  // (A0) everyone has read alpha before row k is overwritten
       for (int j = k + 1 + tid; j < n; j += THREADS) {
         const double vj = (j == k + 1) ? 1.0 : ak[j] * scal;
         v[j] = vj;
@@ -169,46 +210,90 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
         e[k] = beta;
         tau[k] = tk;
       }
-      __syncthreads();
+      const int m = n - k - 1;
+      const int cols = (m + 31) & ~31;
+      int G = THREADS / cols;
+      if (G > TRI_GMAX) G = TRI_GMAX;
+      if (G < 1) G = 1;
+      const int jc = tid % cols, q = tid / cols;
+      const int j = k + 1 + jc;
+      const bool act = (q < G) && (jc < m);
+      __syncthreads();  // (A) v complete
+      double nxt[1] = {0.0};
       if (tk != 0.0) {
-        const int m = n - k - 1;
-        const int cols = (m + 31) & ~31;
-        int G = THREADS / cols;
-        if (G > TRI_GMAX) G = TRI_GMAX;
-        if (G < 1) G = 1;
-        const int jc = tid % cols, q = tid / cols;
-        const int j = k + 1 + jc;
-        const bool act = (q < G) && (jc < m);
         // p = tau * A22 v   (column split: thread (j, q) sums rows i = k+1+q, +G, ...)
         if (act) {
-          double acc = 0.0;
-          for (int i = k + 1 + q; i < n; i += G) acc = fma(S[i * lds + j], v[i], acc);
-          part[q * np + j] = acc;
+          double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+          const double* __restrict__ Sc = S + j;
+          int i = k + 1 + q;
+          for (; i + 3 * G < n; i += 4 * G) {
+            const double s0 = Sc[i * lds], s1 = Sc[(i + G) * lds], s2 = Sc[(i + 2 * G) * lds],
+                         s3 = Sc[(i + 3 * G) * lds];
+            const double v0 = v[i], v1 = v[i + G], v2 = v[i + 2 * G], v3 = v[i + 3 * G];
+            acc0 = fma(s0, v0, acc0);
+            acc1 = fma(s1, v1, acc1);
+            acc2 = fma(s2, v2, acc2);
+            acc3 = fma(s3, v3, acc3);
+          }
+          for (; i < n; i += G) acc0 = fma(Sc[i * lds], v[i], acc0);
+          part[q * np + j] = (acc0 + acc1) + (acc2 + acc3);
         }
-        __syncthreads();
-        double pv = 0.0;
-        for (int jj = k + 1 + tid; jj < n; jj += THREADS) {
-          double s = 0.0;
-          for (int qq = 0; qq < G; ++qq) s += part[qq * np + jj];
-          s *= tk;
-          w[jj] = s;
-          pv = fma(s, v[jj], pv);
-        }
-        pv = block_sum(pv, s_red);
-        const double alpha2 = -0.5 * tk * pv;
-        for (int jj = k + 1 + tid; jj < n; jj += THREADS) w[jj] = fma(alpha2, v[jj], w[jj]);
-        __syncthreads();
-        // A22 -= v w^T + w v^T
-        if (act) {
-          const double vj = v[j], wj = w[j];
-          for (int i = k + 1 + q; i < n; i += G) {
-            double* pa = S + i * lds + j;
-            *pa = *pa - fma(v[i], wj, w[i] * vj);
+        __syncthreads();  // (B) partial sums complete
+        double red[2] = {0.0, 0.0};
+        double pj = 0.0, vj = 0.0;
+        if (act) {  // every (j, q) thread rebuilds p_j (cheap) so it can form w_j itself
+          for (int qq = 0; qq < G; ++qq) pj += part[qq * np + j];
+          pj *= tk;
+          vj = v[j];
+          if (q == 0) {
+            red[0] = pj * vj;
+            if (a.fused) red[1] = vj * gq[j];
           }
         }
-        __syncthreads();
+        block_sum_k<2>(red, s_rbuf, parity);  // (C)
+        const double alpha2 = -0.5 * tk * red[0];
+        double wj = 0.0;
+        if (act) {
+          wj = fma(alpha2, vj, pj);
+          if (q == 0) {
+            w[j] = wj;
+            if (a.fused) gq[j] = fma(-tk * red[1], vj, gq[j]);  // gq <- H_k gq
+          }
+        }
+        __syncthreads();  // (D) w complete
+        // A22 -= v w^T + w v^T ; also the squared norm of the next column
+        if (act) {
+          double* __restrict__ Sc = S + j;
+          int i = k + 1 + q;
+          if (q == 0) {  // first row of A22: its tail is the next Householder column
+            const double nv = Sc[i * lds] - fma(v[i], wj, w[i] * vj);
+            Sc[i * lds] = nv;
+            if (j >= k + 3) nxt[0] = nv * nv;
+            i += G;
+          }
+          for (; i + 3 * G < n; i += 4 * G) {
+            const double s0 = Sc[i * lds], s1 = Sc[(i + G) * lds], s2 = Sc[(i + 2 * G) * lds],
+                         s3 = Sc[(i + 3 * G) * lds];
+            const double v0 = v[i], v1 = v[i + G], v2 = v[i + 2 * G], v3 = v[i + 3 * G];
+            const double w0 = w[i], w1 = w[i + G], w2 = w[i + 2 * G], w3 = w[i + 3 * G];
+            Sc[i * lds] = s0 - fma(v0, wj, w0 * vj);
+            Sc[(i + G) * lds] = s1 - fma(v1, wj, w1 * vj);
+            Sc[(i + 2 * G) * lds] = s2 - fma(v2, wj, w2 * vj);
+            Sc[(i + 3 * G) * lds] = s3 - fma(v3, wj, w3 * vj);
+          }
+          for (; i < n; i += G) Sc[i * lds] = Sc[i * lds] - fma(v[i], wj, w[i] * vj);
+        }
+      } else {
+        for (int jj = k + 3 + tid; jj < n; jj += THREADS) {
+          const double x = S[(k + 1) * lds + jj];
+          nxt[0] = fma(x, x, nxt[0]);
+        }
       }
+      block_sum_k<1>(nxt, s_rbuf1, parity);  // (E) also publishes the updated A22
+      xn2 = nxt[0];
     }
+  }
+  if (!trivial) {
     if (tid == 0) {
       if (n >= 2) {
         d[n - 2] = S[(n - 2) * lds + (n - 2)];
@@ -218,29 +303,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
       d[n - 1] = S[(n - 1) * lds + (n - 1)];
       e[n - 1] = 0.0;
       tau[n - 1] = 0.0;
-      if (n == 1) tau[0] = 0.0;
     }
     __syncthreads();
   }
+  TRI_MARK();  // 1: tridiagonalisation (+ Q^T gp)
 
-  TRI_MARK();  // 1: tridiagonalisation
-  // ---- fused: gq = Q^T gp by the last warp (overlaps with the spill below) ----------------
-  if (a.fused) {
-    for (int i = tid; i < n; i += THREADS) gq[i] = a.gp[(size_t)b * n + i];
-    __syncthreads();
-    if (!trivial && wid == NW - 1) {
-      for (int k = 0; k < n - 2; ++k) {
-        const double tk = tau[k];
-        if (tk == 0.0) continue;
-        const double* vk = S + k * lds;
-        double dot = 0.0;
-        for (int j = k + 1 + lane; j < n; j += 32) dot = fma(vk[j], gq[j], dot);
-        dot = warp_sum(dot) * tk;
-        for (int j = k + 1 + lane; j < n; j += 32) gq[j] = fma(-dot, vk[j], gq[j]);
-        __syncwarp();
-      }
-    }
-  }
   // spill the reflector rows (needed after S is recycled)
   if (!trivial)
     for (int idx = tid; idx < n * n; idx += THREADS) {
@@ -279,8 +346,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
       }
     }
     __syncthreads();
+    TRI_MARK();  // 2: spill, scale, split
 
-    TRI_MARK();  // 2: Q^T g, spill, scale, split
     // ---- phase 2: multisection on the Sturm count --------------------------------------------
     double* lo = X;
     double* hi = X + np;
@@ -303,12 +370,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     const bool worker = tid < P * n;
     for (int round = 0; round < 80; ++round) {
       int active = 0;
-      double x = 0.0;
       if (worker) {
         const double l = lo[i_own], h = hi[i_own];
         const double width = h - l;
         if (width > 2.0 * TRI_EPS * fmax(fabs(l), fabs(h)) + 4e-3 * TRI_EPS) {  // abs floor ~1e-18 ||T||
-          x = l + width * ((double)(jpt + 1) / (double)(P + 1));
+          const double x = l + width * ((double)(jpt + 1) / (double)(P + 1));
           if (x > l && x < h) {
             active = 1;
             cnts[jpt * np + i_own] = sturm_count(d, e2, blk_s[i_own], blk_e[i_own], x);
@@ -323,10 +389,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
         const double l = lo[i], h = hi[i];
         const double width = h - l;
         double nl = l, nh = h;
-        for (int j = 0; j < P; ++j) {
-          const int c = cnts[j * np + i];
+        for (int jj = 0; jj < P; ++jj) {
+          const int c = cnts[jj * np + i];
           if (c < 0) continue;
-          const double xj = l + width * ((double)(j + 1) / (double)(P + 1));
+          const double xj = l + width * ((double)(jj + 1) / (double)(P + 1));
           if (c >= want) {
             nh = fmin(nh, xj);
             break;
@@ -340,86 +406,113 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     }
     for (int i = tid; i < n; i += THREADS) lam[i] = 0.5 * (lo[i] + hi[i]);
     __syncthreads();
-
     TRI_MARK();  // 3: multisection
-    // ---- phase 3: twisted-factorisation eigenvectors, thread i -> column i of S ----------------
-    for (int i = tid; i < n; i += THREADS) {
-      const int s = blk_s[i], t = blk_e[i];
-      for (int k = 0; k < n; ++k)
-        if (k < s || k >= t) S[k * lds + i] = 0.0;
-      if (t - s == 1) {
-        S[s * lds + i] = 1.0;
-        continue;
-      }
-      const double l = lam[i];
+
+    // ---- phase 3: twisted-factorisation eigenvectors; column i of S <- vector i --------------
+    // Reciprocal pivots: forward 1/D+ in S (shared), backward 1/D- in Dm (global, L2).
+    // Thread i runs the forward sweep, thread n + i the backward sweep (same thread when
+    // the CTA has fewer than 2n threads).
+    {
       const double piv = TRI_EPS * 1e-3;
-      // forward pivots D+ (stored), backward pivots D- (streamed) -> twist index r
-      double q = d[s] - l;
-      S[s * lds + i] = q;
-      for (int k = s + 1; k < t; ++k) {
-        if (fabs(q) < piv) q = (q <= 0.0) ? -piv : piv;
-        q = (d[k] - l) - e2[k - 1] / q;
-        S[k * lds + i] = q;
-      }
-      double dm = d[t - 1] - l;
-      double best = fabs(S[(t - 1) * lds + i]);  // gamma_{t-1} = D+_{t-1}
-      int r = t - 1;
-      for (int k = t - 2; k >= s; --k) {
-        if (fabs(dm) < piv) dm = (dm <= 0.0) ? -piv : piv;
-        dm = (d[k] - l) - e2[k] / dm;
-        const double gam = fabs(S[k * lds + i] + dm - (d[k] - l));
-        if (gam < best) {
-          best = gam;
-          r = k;
+      const bool two = (2 * n <= THREADS);
+      double* nrm_up = X;          // np
+      double* nrm_dn = X + np;     // np
+      int* twist = (int*)(X + 2 * np);
+      for (int tt = tid; tt < (two ? 2 * n : n); tt += THREADS) {
+        const int i = tt < n ? tt : tt - n;
+        const int s = blk_s[i], t = blk_e[i];
+        const double l = lam[i];
+        if (tt < n) {  // forward: q_k = (d_k - l) - e2_{k-1} / q_{k-1}
+          for (int k = 0; k < n; ++k)
+            if (k < s || k >= t) S[k * lds + i] = 0.0;
+          double q = d[s] - l;
+          for (int k = s; k < t; ++k) {
+            if (fabs(q) < piv) q = (q <= 0.0) ? -piv : piv;
+            const double r = fast_rcp(q);
+            S[k * lds + i] = r;
+            if (k + 1 < t) q = fma(-e2[k], r, d[k + 1] - l);
+          }
+        }
+        if (tt >= n || !two) {  // backward: q_k = (d_k - l) - e2_k / q_{k+1}
+          double q = d[t - 1] - l;
+          for (int k = t - 1; k >= s; --k) {
+            if (fabs(q) < piv) q = (q <= 0.0) ? -piv : piv;
+            const double r = fast_rcp(q);
+            Dm[(size_t)k * n + i] = r;
+            if (k > s) q = fma(-e2[k - 1], r, d[k - 1] - l);
+          }
         }
       }
-      // recompute D- for k > r and store it over D+ (no longer needed there)
-      if (r < t - 1) {
-        dm = d[t - 1] - l;
-        S[(t - 1) * lds + i] = dm;
-        for (int k = t - 2; k > r; --k) {
-          if (fabs(dm) < piv) dm = (dm <= 0.0) ? -piv : piv;
-          dm = (d[k] - l) - e2[k] / dm;
-          S[k * lds + i] = dm;
+      __syncthreads();
+      // twist index: gamma_k = D+_k - e2_k / D-_{k+1}
+      for (int i = tid; i < n; i += THREADS) {
+        const int s = blk_s[i], t = blk_e[i];
+        const double l = lam[i];
+        double best = INFINITY;
+        int r = s;
+        for (int k = s; k < t; ++k) {
+          double dp = d[k] - l;
+          if (k > s) dp = fma(-e2[k - 1], S[(k - 1) * lds + i], dp);
+          double gam = dp;
+          if (k + 1 < t) gam = fma(-e2[k], Dm[(size_t)(k + 1) * n + i], gam);
+          gam = fabs(gam);
+          if (gam < best) {
+            best = gam;
+            r = k;
+          }
+        }
+        twist[i] = r;
+      }
+      __syncthreads();
+      // z_r = 1; z_k = -e_k z_{k+1} / D+_k (k < r); z_k = -e_{k-1} z_{k-1} / D-_k (k > r)
+      for (int tt = tid; tt < (two ? 2 * n : n); tt += THREADS) {
+        const int i = tt < n ? tt : tt - n;
+        const int s = blk_s[i], t = blk_e[i];
+        const int r = twist[i];
+        if (tt < n) {
+          double z = 1.0, acc = 0.0;
+          for (int k = r - 1; k >= s; --k) {
+            z = -(e[k] * S[k * lds + i]) * z;
+            S[k * lds + i] = z;
+            acc = fma(z, z, acc);
+          }
+          nrm_up[i] = acc;
+        }
+        if (tt >= n || !two) {
+          double z = 1.0, acc = 0.0;
+          for (int k = r + 1; k < t; ++k) {
+            z = -(e[k - 1] * Dm[(size_t)k * n + i]) * z;
+            S[k * lds + i] = z;
+            acc = fma(z, z, acc);
+          }
+          nrm_dn[i] = acc;
         }
       }
-      // z_r = 1, outward recurrences, in place
-      double z = 1.0, nrm2 = 1.0;
-      for (int k = r - 1; k >= s; --k) {
-        double dp = S[k * lds + i];
-        if (fabs(dp) < piv) dp = (dp <= 0.0) ? -piv : piv;
-        z = -(e[k] / dp) * z;
-        S[k * lds + i] = z;
-        nrm2 = fma(z, z, nrm2);
+      __syncthreads();
+      for (int i = tid; i < n; i += THREADS) {
+        const int s = blk_s[i], t = blk_e[i];
+        S[twist[i] * lds + i] = 1.0;
+        const double sc = 1.0 / sqrt(1.0 + nrm_up[i] + nrm_dn[i]);
+        for (int k = s; k < t; ++k) S[k * lds + i] *= sc;
+        if (!isfinite(sc) || sc == 0.0) s_fallback = 1;
       }
-      z = 1.0;
-      for (int k = r + 1; k < t; ++k) {
-        double dq = S[k * lds + i];
-        if (fabs(dq) < piv) dq = (dq <= 0.0) ? -piv : piv;
-        z = -(e[k - 1] / dq) * z;
-        S[k * lds + i] = z;
-        nrm2 = fma(z, z, nrm2);
-      }
-      S[r * lds + i] = 1.0;
-      const double sc = 1.0 / sqrt(nrm2);
-      for (int k = s; k < t; ++k) S[k * lds + i] *= sc;
-      if (!isfinite(sc) || sc == 0.0) s_fallback = 1;
     }
-    // clusters: consecutive rows of one block whose eigenvalues are closer than GAPTOL
+    // clusters: consecutive rows of one block whose eigenvalues are closer than GAPTOL.
+    // Fused mode: modes that the RFO step filters anyway (|lambda| < 1e-7 absolute, rsirfo.py:30
+    // drops < 1e-6) are left alone and break clusters (the TR/ROT null space lands here).
     if (tid == 0) {
       int cs = 0;
+      const double dead = a.fused ? 1e-7 / s_tnorm : -1.0;
       for (int i = 0; i < n; ++i) {
-        if (i > 0 && blk_s[i] == blk_s[i - 1] && (lam[i] - lam[i - 1]) < TRI_GAPTOL) {
-          // same cluster
-        } else {
-          cs = i;
-        }
+        const bool chain = i > 0 && blk_s[i] == blk_s[i - 1] && (lam[i] - lam[i - 1]) < TRI_GAPTOL &&
+                           !(fabs(lam[i]) < dead) && !(fabs(lam[i - 1]) < dead);
+        if (!chain) cs = i;
         cl_s[i] = cs;
       }
     }
     __syncthreads();
-
     TRI_MARK();  // 4: twisted vectors
+
     // ---- phase 4: CGS2 inside clusters, one warp per cluster -------------------------------------
     double* dots = X;  // NW * 64
     for (int c0 = wid; c0 < n; c0 += NW) {
@@ -452,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
           for (int k = s + lane; k < t; k += 32) nn = fma(S[k * lds + c], S[k * lds + c], nn);
           nn = sqrt(warp_sum(nn));
           if (rep == 0) nfirst = nn;
-          if (!(nn > 1e-3) ) {
+          if (!(nn > 1e-2)) {
             if (lane == 0) s_fallback = 1;  // vector (nearly) inside the span of its cluster
           }
           const double sc = nn > 0.0 ? 1.0 / nn : 0.0;
@@ -472,6 +565,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
       for (int k = 0; k < n; ++k) S[k * lds + i] = (k == i) ? 1.0 : 0.0;
     }
     __syncthreads();
+    TRI_MARK();
+    TRI_MARK();
+    TRI_MARK();
   }
 
   TRI_MARK();  // 5: cluster re-orthogonalisation
@@ -545,7 +641,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   int flags = identity ? MOP_ST_EIG_NONFINITE : 0;
   flags |= rfo_core(n, a.saddle_order, a.neb_mode, a.tmin, a.tmax, lam_s, gam_s, identity, gnorm_raw,
                     a.Be ? a.Be[b] : 0.0, stp, R, a.pred ? a.pred + b : nullptr);
-  // y = Z c  (thread k), then step = Q y by one warp, move = -step
+  TRI_MARK();  // 6: eigenbasis RFO
+  // y = Z c  (thread k)
   double* y = gq;
   for (int k = tid; k < n; k += THREADS) {
     double acc = 0.0;
@@ -556,12 +653,69 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     y[k] = acc;
   }
   __syncthreads();
+  // step = Q y = H_0 ... H_{n-3} y.  Z is dead now: the reflector rows come back from L2
+  // into S (coalesced), then ONE warp applies four reflectors per reduction round:
+  // with u_i = v_i^T y and G_ij = v_i^T v_j all taken from the SAME y, the sequential
+  // coefficients are c_3 = t_3 u_3, c_2 = t_2 (u_2 - c_3 G_23), ... (applied high k first).
+  if (!trivial) {
+    for (int idx = tid; idx < n * n; idx += THREADS) {
+      const int i = idx / n, j = idx - i * n;
+      if (j > i) S[i * lds + j] = Vh[idx];
+    }
+  }
+  __syncthreads();
   if (wid == 0) {
     if (!trivial) {
-      for (int k = n - 3; k >= 0; --k) {
+      constexpr int MAXJ = (TRI_MAX_N + 31) / 32;
+      int k = n - 3;
+      for (; k >= 3; k -= 4) {
+        // reflectors k (index 3) .. k-3 (index 0); v_i lives on rows > k-3+i
+        const double* v0 = S + (k - 3) * lds;
+        const double* v1 = S + (k - 2) * lds;
+        const double* v2 = S + (k - 1) * lds;
+        const double* v3 = S + k * lds;
+        double r[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double A0[MAXJ], A1[MAXJ], A2[MAXJ], A3[MAXJ], Y[MAXJ];
+#pragma unroll
+        for (int u = 0; u < MAXJ; ++u) {
+          const int j = k - 2 + lane + 32 * u;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, yj = 0.0;
+          if (j < n) {
+            yj = y[j];
+            a0 = (j == k - 2) ? 1.0 : v0[j];
+            a1 = (j <= k - 2) ? 0.0 : ((j == k - 1) ? 1.0 : v1[j]);
+            a2 = (j <= k - 1) ? 0.0 : ((j == k) ? 1.0 : v2[j]);
+            a3 = (j <= k) ? 0.0 : ((j == k + 1) ? 1.0 : v3[j]);
+          }
+          A0[u] = a0; A1[u] = a1; A2[u] = a2; A3[u] = a3; Y[u] = yj;
+          r[0] = fma(a0, yj, r[0]);
+          r[1] = fma(a1, yj, r[1]);
+          r[2] = fma(a2, yj, r[2]);
+          r[3] = fma(a3, yj, r[3]);
+          r[4] = fma(a0, a1, r[4]);  // G01
+          r[5] = fma(a0, a2, r[5]);  // G02
+          r[6] = fma(a0, a3, r[6]);  // G03
+          r[7] = fma(a1, a2, r[7]);  // G12
+          r[8] = fma(a1, a3, r[8]);  // G13
+          r[9] = fma(a2, a3, r[9]);  // G23
+        }
+#pragma unroll
+        for (int q = 0; q < 10; ++q) r[q] = warp_sum(r[q]);
+        const double c3 = tau[k] * r[3];
+        const double c2 = tau[k - 1] * (r[2] - c3 * r[9]);
+        const double c1 = tau[k - 2] * (r[1] - c3 * r[8] - c2 * r[7]);
+        const double c0 = tau[k - 3] * (r[0] - c3 * r[6] - c2 * r[5] - c1 * r[4]);
+#pragma unroll
+        for (int u = 0; u < MAXJ; ++u) {
+          const int j = k - 2 + lane + 32 * u;
+          if (j < n) y[j] = Y[u] - (c0 * A0[u] + c1 * A1[u] + c2 * A2[u] + c3 * A3[u]);
+        }
+        __syncwarp();
+      }
+      for (; k >= 0; --k) {
         const double tk = tau[k];
         if (tk == 0.0) continue;
-        const double* vk = Vh + (size_t)k * n;
+        const double* vk = S + k * lds;
         double dot = 0.0;
         for (int j = k + 1 + lane; j < n; j += 32) dot = fma(j == k + 1 ? 1.0 : vk[j], y[j], dot);
         dot = warp_sum(dot) * tk;
@@ -571,12 +725,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
     }
     for (int j = lane; j < n; j += 32) a.move[(size_t)b * n + j] = -y[j];
   }
-  TRI_MARK();  // 6: eigenbasis RFO + back-transform
+  TRI_MARK();  // 7: back-transform
   if (tid == 0 && a.status) {
     const int keep = st_in & (MOP_ST_UPDATED | MOP_ST_UPD_SKIP_SMALL | MOP_ST_UPD_SKIP_CURV |
                               MOP_ST_UPD_TERM_ZEROED | MOP_ST_NO_HISTORY | MOP_ST_TRROT_RANKDEF);
     a.status[b] = keep | flags;
   }
+#undef TRI_MARK
 }
 
 }  // namespace mop
@@ -601,7 +756,7 @@ static size_t tri_smem_bytes(int n) {
 }
 
 int mop_tridiag_supported(int n) { return n >= 1 && n <= mop::TRI_MAX_N && tri_smem_bytes(n) <= 227 * 1024; }
-size_t mop_tridiag_workspace_bytes(int B, int n) { return sizeof(double) * (size_t)B * n * n; }
+size_t mop_tridiag_workspace_bytes(int B, int n) { return 2 * sizeof(double) * (size_t)B * n * n; }
 
 template <int T>
 static int launch_tri(int B, const mop::TriArgs& a, size_t smem, cudaStream_t stream) {
@@ -637,6 +792,7 @@ int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double
   a.fused = 0;
   a.A = A;
   a.Vh = (double*)work;
+  a.Dm = (double*)work + (size_t)B * n * n;
   a.evals = evals;
   a.evecs = evecs;
   a.status = status;
@@ -662,6 +818,7 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
   a.fused = 1;
   a.A = Hp;
   a.Vh = (double*)work;
+  a.Dm = (double*)work + (size_t)B * n * n;
   a.evals = evals_out;
   a.evecs = nullptr;
   a.status = status;

@@ -39,7 +39,7 @@ out = ops.rsirfo_step(Hs[3], x1d, g1d, g1d, sts[3], method=m, x_prev=x0d, g_prev
 torch.cuda.synchronize()
 lib.mop_debug_tri_timing(None)
 d = dbg.cpu().numpy().astype(float)
-names = ["load", "tridiag", "Qtg/spill/split", "multisection", "twisted", "cluster MGS", "rfo+backtransform"]
+names = ["load", "tridiag(+Qtg)", "spill/scale/split", "multisection", "twisted", "cluster MGS", "rfo core", "Zc + Qy"]
 print("phase cycles (median over CTAs):")
 for i, nm in enumerate(names):
     print(f"  {nm:20s} {np.median(d[:, i]):12.0f}  max {d[:, i].max():12.0f}")
