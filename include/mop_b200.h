@@ -153,6 +153,20 @@ int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode, in
                     double* eigvals_out, double* pred_out, int32_t* status, void* work,
                     size_t work_bytes, void* stream);
 
+/* ---- (2d) RS-I-RFO step from an already projected Hessian ---------------------
+ * The part of RSIRFO.run after the projections (Optimizer/rsirfo.py:358-490): one
+ * shared-memory-resident kernel per structure that tridiagonalises Hp, finds the
+ * spectrum, solves the RFO secular equation in the eigenbasis and transforms the step
+ * back (n <= 158); structures with tight eigenvalue clusters are redone by the Jacobi
+ * path.  Hp [B][n][n] must be symmetric; gp = projected gradient, Bg = raw biased
+ * gradient (its norm drives the inner trust-radius rule, rsirfo.py:312,835). */
+size_t mop_rsirfo_spectral_workspace_bytes(int B, int n);
+int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_mode, double trust_min,
+                             double trust_max, const double* Hp, const double* gp,
+                             const double* Bg, const double* Be, double* state, double* move_out,
+                             double* eigvals_out, double* pred_out, int32_t* status, void* work,
+                             size_t work_bytes, void* stream);
+
 /* ---- caller side: CalculateMoveVector.calc_move_vector clamp -------------
  * Replaces optimizer.py:792-798,812: scale move to trust_outer[B] if longer,
  * x_new_ang = (x - move) * 0.52917721067. */
@@ -167,8 +181,18 @@ int mop_bench_fill(double* buf, size_t count, double value, void* stream);
 /* diagnostics: device buffer [B][8] int64 receiving per-phase SM clock counts of the
  * tridiagonal / fused kernel (NULL switches it off).  Not thread-safe; tools only. */
 int mop_debug_tri_timing(void* buf);
+/* diagnostics / tuning: force the CTA size (128/256/512/1024) of the tridiagonal kernels; 0 = auto. */
+int mop_debug_tri_threads(int threads);
+/* diagnostics: skip parts of the tridiagonalisation (timing ablations; results invalid). */
+int mop_debug_tri_ablate(int mask);
 /* diagnostics: out[i] = the kernels' division-free reciprocal of x[i] (accuracy test). */
 int mop_debug_fast_rcp(const double* x, double* out, size_t count, void* stream);
+/* diagnostics: out[0..7] = dependent-chain latencies in SM cycles of DFMA, DADD, DMUL,
+ * shared load, 64-bit shuffle, fast reciprocal, sqrt(+add), divide (out: >= 9 doubles). */
+int mop_debug_latency(double* out, void* stream);
+/* diagnostics: out[0..2] = cycles per bare barrier / reduce-publish-barrier-broadcast round /
+ * the same plus a dependent sqrt and two reciprocals, for one CTA of `threads` threads. */
+int mop_debug_barrier_latency(int threads, double* out, void* stream);
 
 #ifdef __cplusplus
 }

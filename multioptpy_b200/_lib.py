@@ -34,11 +34,17 @@ SIGNATURES = {
     "mop_rsirfo_workspace_bytes": (_sz, [_i, _i, _i]),
     "mop_rsirfo_step": (_i, [_i, _i, _i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                              _p, _p, _p, _p, _sz, _p]),
+    "mop_rsirfo_spectral_workspace_bytes": (_sz, [_i, _i]),
+    "mop_rsirfo_spectral_step": (_i, [_i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "mop_bench_dfma": (_i, [_i, _i, _p, _p]),
     "mop_bench_fill": (_i, [_p, _sz, _d, _p]),
     "mop_debug_tri_timing": (_i, [_p]),
+    "mop_debug_tri_threads": (_i, [_i]),
+    "mop_debug_tri_ablate": (_i, [_i]),
     "mop_debug_fast_rcp": (_i, [_p, _p, _sz, _p]),
+    "mop_debug_latency": (_i, [_p, _p]),
+    "mop_debug_barrier_latency": (_i, [_i, _p, _p]),
 }
 
 _lib = None

@@ -31,6 +31,13 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
                             double* state, double* move, double* evals_out, double* pred,
                             int32_t* status, void* work, size_t work_bytes, cudaStream_t stream);
 
+extern "C" size_t mop_rsirfo_spectral_workspace_bytes(int B, int n);
+extern "C" int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_mode, double trust_min,
+                                        double trust_max, const double* Hp, const double* gp,
+                                        const double* Bg, const double* Be, double* state,
+                                        double* move_out, double* eigvals_out, double* pred_out,
+                                        int32_t* status, void* work, size_t work_bytes, void* stream_);
+
 static thread_local char g_err[512] = "";
 
 void mop_set_error(const char* fmt, ...) {
@@ -101,12 +108,62 @@ extern "C" int mop_eigh(int B, int n, int algo, const double* A, double* evals, 
   return run_eigh(B, n, algo, A, evals, evecs, status, work, work_bytes, (cudaStream_t)stream);
 }
 
+// workspace of mop_rsirfo_spectral_step: evecs | evals | jacobi work | tridiag work
+extern "C" size_t mop_rsirfo_spectral_workspace_bytes(int B, int n) {
+  if (B <= 0 || n <= 0) return 0;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  return nn + nv + align256(mop_jacobi_workspace_bytes(B, n)) + align256(mop_tridiag_workspace_bytes(B, n));
+}
+
+extern "C" int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_mode, double trust_min,
+                                        double trust_max, const double* Hp, const double* gp,
+                                        const double* Bg, const double* Be, double* state,
+                                        double* move_out, double* eigvals_out, double* pred_out,
+                                        int32_t* status, void* work, size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && n > 0, "mop_rsirfo_spectral_step: B >= 0 and n > 0 required");
+  MOP_REQUIRE(Hp && gp && Bg && state && move_out && status && work,
+              "mop_rsirfo_spectral_step: Hp, gp, Bg, state, move_out, status, work must be device pointers");
+  if (B == 0) return MOP_OK;
+  if (!mop_tridiag_supported(n)) {
+    mop_set_error("mop_rsirfo_spectral_step: n = %d exceeds the shared-memory path", n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (work_bytes < mop_rsirfo_spectral_workspace_bytes(B, n)) {
+    mop_set_error("mop_rsirfo_spectral_step: workspace too small (%zu < %zu bytes)", work_bytes,
+                  mop_rsirfo_spectral_workspace_bytes(B, n));
+    return MOP_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
+  char* w = (char*)work;
+  double* evecs = (double*)w;
+  double* evals = (double*)(w + nn);
+  void* jwork = w + nn + nv;
+  void* twork = w + nn + nv + jac;
+  // tridiagonalise, solve and step in one shared-memory-resident kernel; structures it
+  // flags (tight eigenvalue clusters) are redone by the robust Jacobi path (no host sync:
+  // CTAs of unflagged structures exit immediately).
+  int rc = mop_launch_rsirfo_fused(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,
+                                   state, move_out, eigvals_out, pred_out, status, twork,
+                                   work_bytes - (nn + nv + jac), stream);
+  if (rc != MOP_OK) return rc;
+  rc = mop_launch_eigh_jacobi(B, n, Hp, evals, evecs, status, status, jwork, jac, stream);
+  if (rc != MOP_OK) return rc;
+  return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, gp, Bg,
+                             Be, state, move_out, eigvals_out, pred_out, status, 1, stream);
+}
+
 // workspace of mop_rsirfo_step: Hp | evecs | evals | gp | eigh work
 extern "C" size_t mop_rsirfo_workspace_bytes(int B, int n, int algo) {
   if (B <= 0 || n <= 0) return 0;
   const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
   const size_t nv = align256(sizeof(double) * (size_t)B * n);
-  return 2 * nn + 2 * nv + eigh_work_bytes(B, n, algo);
+  const size_t generic = nn + nv + eigh_work_bytes(B, n, algo);        // evecs | evals | eigh work
+  const size_t fused = mop_rsirfo_spectral_workspace_bytes(B, n);
+  return nn + nv + (generic > fused ? generic : fused);                  // Hp | gp | rest
 }
 
 extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode,
@@ -132,12 +189,15 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
   const size_t nv = align256(sizeof(double) * (size_t)B * n);
   char* w = (char*)work;
+  // layout: Hp | gp | rest ; rest = spectral workspace (fused path) or evecs | evals | eigh work
   double* Hp = (double*)w;
-  double* evecs = (double*)(w + nn);
-  double* evals = (double*)(w + 2 * nn);
-  double* gp = (double*)(w + 2 * nn + nv);
-  void* ework = w + 2 * nn + 2 * nv;
-  const size_t ebytes = work_bytes - (2 * nn + 2 * nv);
+  double* gp = (double*)(w + nn);
+  char* rest = w + nn + nv;
+  const size_t rest_bytes = work_bytes - (nn + nv);
+  double* evecs = (double*)rest;
+  double* evals = (double*)(rest + nn);
+  void* ework = rest + nn + nv;
+  const size_t ebytes = rest_bytes - (nn + nv);
 
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   int rc;
@@ -150,23 +210,10 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   // (2) TR/ROT projection of gradient and effective Hessian (rsirfo.py:337,349-358)
   rc = mop_launch_project_trrot(B, n, H, Hbias, x, Bg, Hp, gp, status, stream);
   if (rc != MOP_OK) return rc;
-  if (pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG) {
-    // (3+4 fused) tridiagonalise, solve and step in one shared-memory-resident kernel;
-    // structures it flags (tight eigenvalue clusters) are redone by the robust path.
-    if (!mop_tridiag_supported(n)) {
-      mop_set_error("mop_rsirfo_step: tridiagonal path does not support n = %d", n);
-      return MOP_ERR_UNSUPPORTED;
-    }
-    const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
-    rc = mop_launch_rsirfo_fused(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,
-                                 state, move_out, eigvals_out, pred_out, status, (char*)ework + jac,
-                                 ebytes - jac, stream);
-    if (rc != MOP_OK) return rc;
-    rc = mop_launch_eigh_jacobi(B, n, Hp, evals, evecs, status, status, ework, jac, stream);
-    if (rc != MOP_OK) return rc;
-    return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, gp,
-                               Bg, Be, state, move_out, eigvals_out, pred_out, status, 1, stream);
-  }
+  if (pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG)
+    return mop_rsirfo_spectral_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,
+                                    state, move_out, eigvals_out, pred_out, status, rest, rest_bytes,
+                                    stream_);
   // (3) eigendecomposition (rsirfo.py:360)
   rc = run_eigh(B, n, eigh_algo, Hp, evals, evecs, status, ework, ebytes, stream);
   if (rc != MOP_OK) return rc;

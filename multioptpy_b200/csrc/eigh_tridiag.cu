@@ -23,7 +23,7 @@
 namespace mop {
 
 constexpr int TRI_MAX_N = 160;
-constexpr int TRI_GMAX = 8;          // max row-groups in the column-split symv / update
+constexpr int TRI_GMAX = 16;         // max row-groups in the column-split symv / update
 constexpr double TRI_EPS = 2.220446049250313e-16;
 constexpr double TRI_GAPTOL = 1e-3;  // cluster gap relative to ||T|| (LAPACK dstein ORTOL)
 
@@ -33,7 +33,7 @@ __host__ __device__ inline size_t tri_x_doubles(int n) {
   size_t x = (size_t)(TRI_GMAX + 2) * np + 48;                               // phase 1 / 2
   const size_t fused = 2 * np + rfo_core_smem_bytes(n) / sizeof(double) + 8;  // fused RFO arrays
   if (fused > x) x = fused;
-  if (16 * 64 > x) x = 16 * 64;                                              // phase 4 dots
+  if (32 * 64 > x) x = 32 * 64;                                              // phase 4 dots (<= 32 warps)
   return (x + 1) & ~(size_t)1;
 }
 
@@ -56,6 +56,7 @@ struct TriArgs {
   int saddle_order, neb_mode;
   double tmin, tmax;
   long long* dbg;    // optional [B][8] phase clocks (diagnostics)
+  int ablate;        // diagnostics only: bit0 skip symv loop, bit1 skip update loop (results invalid)
 };
 
 // number of eigenvalues of the unreduced block rows [s, t) that are < x
@@ -84,10 +85,11 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
     pm1 = p2;
     p = p3;
     const unsigned ex = ((unsigned)h3 >> 20) & 0x7ffu;
-    if (ex - 823u > 400u) {  // |p| outside [2^-200, 2^200]
+    if (ex - 523u > 1000u) {  // |p| outside [2^-500, 2^500]: rare, even per warp
       const double a = fmax(fabs(p), fabs(pm1));
       if (a > 0.0 && a < INFINITY) {
-        const double sc = 1.0 / a;
+        const int ea = (__double2hiint(a) >> 20) & 0x7ff;          // biased exponent of a
+        const double sc = __hiloint2double((2046 - ea) << 20, 0);   // 2^(1023 - ea)
         p *= sc;
         pm1 *= sc;
       }
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   do {                                                                  \
     if (a.dbg && tid == 0) {                                            \
       const long long t_now = clock64();                                \
-      a.dbg[(size_t)b * 8 + (t_slot++)] = t_now - t_prev;               \
+      a.dbg[(size_t)b * 16 + (t_slot++)] = t_now - t_prev;               \
       t_prev = t_now;                                                   \
     }                                                                   \
   } while (0)
@@ -183,115 +185,222 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   double* part = X + 2 * np;
   TRI_MARK();  // 0: load
 
-  // ---- phase 1: tridiagonalisation (5 barriers per column) ------------------------------
+  // ---- phase 1: tridiagonalisation -------------------------------------------------------
+  // Column step k: v from row k, p = tau A22 v, w = p - tau/2 (p.v) v, A22 -= v w^T + w v^T.
+  // Thread (jc, q) owns the two columns jA = k+1+jc, jB = jA + cols2 and the rows
+  // i = k+1+q, +G, ... ; block reductions are done by the warps that hold the q == 0
+  // threads only (<= 3 warps), everyone else just adds their published partials.
   if (!trivial && n > 2) {
-    // norm of the first column below the sub-diagonal
-    double r1[1] = {0.0};
-    for (int j = 2 + tid; j < n; j += THREADS) r1[0] = fma(S[j], S[j], r1[0]);
-    block_sum_k<1>(r1, s_rbuf1, parity);
-    double xn2 = r1[0];
+    double* rb = s_rbuf;  // [2][8] partials: (value, warp)
+    int par = 0;
+    double xn2;
+    {
+      double r = 0.0;
+      for (int j = 2 + tid; j < n; j += THREADS) r = fma(S[j], S[j], r);
+      xn2 = block_sum(r, s_red);
+    }
+    int cols2 = -1, G = 1, jc = 0, q = 0;
+    long long seg[5] = {0, 0, 0, 0, 0}, ts = clock64();
+#define SEG(i)                              \
+  do {                                      \
+    if (a.dbg) {                            \
+      const long long tn_ = clock64();      \
+      seg[i] += tn_ - ts;                   \
+      ts = tn_;                             \
+    }                                       \
+  } while (0)
+    double* P = w;  // p = tau A22 v (w_i = p_i + alpha2 v_i is formed on the fly)
     for (int k = 0; k < n - 2; ++k) {
       double* ak = S + k * lds;
-      const double alpha = ak[k + 1];
+      const double alpha = ak[k + 1];   // stays in place: the reflector's unit entry is implicit
       double beta = alpha, tk = 0.0, scal = 0.0;
       if (xn2 > 0.0) {
         beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
-        tk = (beta - alpha) / beta;
-        scal = 1.0 / (alpha - beta);
+        tk = (beta - alpha) * fast_rcp(beta);
+        scal = fast_rcp(alpha - beta);
       }
-      __syncthreads();  // (A0) everyone has read alpha before row k is overwritten
+      const int m = n - k - 1;
+      const int c2 = (((m + 1) >> 1) + 31) & ~31;
+      if (c2 != cols2) {
+        cols2 = c2;
+        G = THREADS / cols2;
+        if (G > TRI_GMAX) G = TRI_GMAX;
+        jc = tid % cols2;
+        q = tid / cols2;
+      }
+      const int nredw = cols2 >> 5;
+      const int jA = k + 1 + jc, jB = jA + cols2;
+      const bool actA = (q < G) && (jA < n), actB = (q < G) && (jB < n);
       for (int j = k + 1 + tid; j < n; j += THREADS) {
-        const double vj = (j == k + 1) ? 1.0 : ak[j] * scal;
-        v[j] = vj;
-        ak[j] = vj;  // reflector kept in row k
+        if (j == k + 1) {
+          v[j] = 1.0;
+        } else {
+          const double vj = ak[j] * scal;
+          v[j] = vj;
+          ak[j] = vj;  // reflector kept in row k (columns > k+1)
+        }
       }
       if (tid == 0) {
         d[k] = ak[k];
         e[k] = beta;
         tau[k] = tk;
       }
-      const int m = n - k - 1;
-      const int cols = (m + 31) & ~31;
-      int G = THREADS / cols;
-      if (G > TRI_GMAX) G = TRI_GMAX;
-      if (G < 1) G = 1;
-      const int jc = tid % cols, q = tid / cols;
-      const int j = k + 1 + jc;
-      const bool act = (q < G) && (jc < m);
       __syncthreads();  // (A) v complete
-      double nxt[1] = {0.0};
+      SEG(0);
+      double nx = 0.0;
       if (tk != 0.0) {
-        // p = tau * A22 v   (column split: thread (j, q) sums rows i = k+1+q, +G, ...)
-        if (act) {
-          double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-          const double* __restrict__ Sc = S + j;
+        const int rstep = G * lds;
+        // ---- partial sums of A22 v over this thread's rows (4 rows x 2 columns in flight) ----
+        if (actA && !(a.ablate & 1)) {
+          const double* pa = S + (k + 1 + q) * lds + jA;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
           int i = k + 1 + q;
-          for (; i + 3 * G < n; i += 4 * G) {
-            const double s0 = Sc[i * lds], s1 = Sc[(i + G) * lds], s2 = Sc[(i + 2 * G) * lds],
-                         s3 = Sc[(i + 3 * G) * lds];
+          for (; i + 3 * G < n; i += 4 * G, pa += 4 * rstep) {
             const double v0 = v[i], v1 = v[i + G], v2 = v[i + 2 * G], v3 = v[i + 3 * G];
-            acc0 = fma(s0, v0, acc0);
-            acc1 = fma(s1, v1, acc1);
-            acc2 = fma(s2, v2, acc2);
-            acc3 = fma(s3, v3, acc3);
+            const double sa0 = pa[0], sa1 = pa[rstep], sa2 = pa[2 * rstep], sa3 = pa[3 * rstep];
+            a0 = fma(sa0, v0, a0);
+            a1 = fma(sa1, v1, a1);
+            a2 = fma(sa2, v2, a2);
+            a3 = fma(sa3, v3, a3);
+            if (actB) {
+              const double sb0 = pa[cols2], sb1 = pa[rstep + cols2], sb2 = pa[2 * rstep + cols2],
+                           sb3 = pa[3 * rstep + cols2];
+              b0 = fma(sb0, v0, b0);
+              b1 = fma(sb1, v1, b1);
+              b2 = fma(sb2, v2, b2);
+              b3 = fma(sb3, v3, b3);
+            }
           }
-          for (; i < n; i += G) acc0 = fma(Sc[i * lds], v[i], acc0);
-          part[q * np + j] = (acc0 + acc1) + (acc2 + acc3);
+          for (; i < n; i += G, pa += rstep) {
+            const double v0 = v[i];
+            a0 = fma(pa[0], v0, a0);
+            if (actB) b0 = fma(pa[cols2], v0, b0);
+          }
+          part[q * np + jA] = (a0 + a1) + (a2 + a3);
+          if (actB) part[q * np + jB] = (b0 + b1) + (b2 + b3);
         }
         __syncthreads();  // (B) partial sums complete
-        double red[2] = {0.0, 0.0};
-        double pj = 0.0, vj = 0.0;
-        if (act) {  // every (j, q) thread rebuilds p_j (cheap) so it can form w_j itself
-          for (int qq = 0; qq < G; ++qq) pj += part[qq * np + j];
-          pj *= tk;
-          vj = v[j];
-          if (q == 0) {
-            red[0] = pj * vj;
-            if (a.fused) red[1] = vj * gq[j];
+        SEG(1);
+        // ---- q == 0 threads: p_j, published; reduction (C): p.v and (fused) v.gq ----
+        if (wid < nredw) {
+          double r0 = 0.0, r1 = 0.0;
+          if (actA) {
+            double pj = 0.0, pk = 0.0;
+            int qq = 0;
+            for (; qq + 1 < G; qq += 2) {
+              pj += part[qq * np + jA];
+              pk += part[(qq + 1) * np + jA];
+            }
+            if (qq < G) pj += part[qq * np + jA];
+            pj = (pj + pk) * tk;
+            P[jA] = pj;
+            const double vj = v[jA];
+            r0 = pj * vj;
+            if (a.fused) r1 = vj * gq[jA];
+          }
+          if (actB) {
+            double pj = 0.0, pk = 0.0;
+            int qq = 0;
+            for (; qq + 1 < G; qq += 2) {
+              pj += part[qq * np + jB];
+              pk += part[(qq + 1) * np + jB];
+            }
+            if (qq < G) pj += part[qq * np + jB];
+            pj = (pj + pk) * tk;
+            P[jB] = pj;
+            const double vj = v[jB];
+            r0 = fma(pj, vj, r0);
+            if (a.fused) r1 = fma(vj, gq[jB], r1);
+          }
+          r0 = warp_sum(r0);
+          r1 = warp_sum(r1);
+          if (lane == 0) {
+            rb[par * 8 + wid] = r0;
+            rb[par * 8 + 4 + wid] = r1;
           }
         }
-        block_sum_k<2>(red, s_rbuf, parity);  // (C)
-        const double alpha2 = -0.5 * tk * red[0];
-        double wj = 0.0;
-        if (act) {
-          wj = fma(alpha2, vj, pj);
-          if (q == 0) {
-            w[j] = wj;
-            if (a.fused) gq[j] = fma(-tk * red[1], vj, gq[j]);  // gq <- H_k gq
-          }
+        __syncthreads();  // (C) p and the partial dot products are visible
+        SEG(2);
+        double pv = 0.0, gd = 0.0;
+        for (int ww = 0; ww < nredw; ++ww) {
+          pv += rb[par * 8 + ww];
+          gd += rb[par * 8 + 4 + ww];
         }
-        __syncthreads();  // (D) w complete
-        // A22 -= v w^T + w v^T ; also the squared norm of the next column
-        if (act) {
-          double* __restrict__ Sc = S + j;
+        par ^= 1;
+        const double alpha2 = -0.5 * tk * pv;
+        // ---- A22 -= v w^T + w v^T, w = p + alpha2 v ; next column norm on the fly ----
+        if (actA) {
+          const double vA = v[jA], wA = fma(alpha2, vA, P[jA]);
+          double vB = 0.0, wB = 0.0;
+          if (actB) {
+            vB = v[jB];
+            wB = fma(alpha2, vB, P[jB]);
+          }
+          if (q == 0 && a.fused) {  // gq <- H_k gq
+            gq[jA] = fma(-tk * gd, vA, gq[jA]);
+            if (actB) gq[jB] = fma(-tk * gd, vB, gq[jB]);
+          }
+          double* pa = S + (k + 1 + q) * lds + jA;
           int i = k + 1 + q;
           if (q == 0) {  // first row of A22: its tail is the next Householder column
-            const double nv = Sc[i * lds] - fma(v[i], wj, w[i] * vj);
-            Sc[i * lds] = nv;
-            if (j >= k + 3) nxt[0] = nv * nv;
+            const double v0 = v[i], w0 = fma(alpha2, v0, P[i]);
+            const double na = pa[0] - fma(v0, wA, w0 * vA);
+            pa[0] = na;
+            if (jA >= k + 3) nx = na * na;
+            if (actB) {
+              const double nb = pa[cols2] - fma(v0, wB, w0 * vB);
+              pa[cols2] = nb;
+              nx = fma(nb, nb, nx);  // jB >= k + 33
+            }
             i += G;
+            pa += rstep;
           }
-          for (; i + 3 * G < n; i += 4 * G) {
-            const double s0 = Sc[i * lds], s1 = Sc[(i + G) * lds], s2 = Sc[(i + 2 * G) * lds],
-                         s3 = Sc[(i + 3 * G) * lds];
+          if (a.ablate & 2) i = n;
+          for (; i + 3 * G < n; i += 4 * G, pa += 4 * rstep) {
             const double v0 = v[i], v1 = v[i + G], v2 = v[i + 2 * G], v3 = v[i + 3 * G];
-            const double w0 = w[i], w1 = w[i + G], w2 = w[i + 2 * G], w3 = w[i + 3 * G];
-            Sc[i * lds] = s0 - fma(v0, wj, w0 * vj);
-            Sc[(i + G) * lds] = s1 - fma(v1, wj, w1 * vj);
-            Sc[(i + 2 * G) * lds] = s2 - fma(v2, wj, w2 * vj);
-            Sc[(i + 3 * G) * lds] = s3 - fma(v3, wj, w3 * vj);
+            const double w0 = fma(alpha2, v0, P[i]), w1 = fma(alpha2, v1, P[i + G]),
+                         w2 = fma(alpha2, v2, P[i + 2 * G]), w3 = fma(alpha2, v3, P[i + 3 * G]);
+            const double sa0 = pa[0], sa1 = pa[rstep], sa2 = pa[2 * rstep], sa3 = pa[3 * rstep];
+            if (actB) {
+              const double sb0 = pa[cols2], sb1 = pa[rstep + cols2], sb2 = pa[2 * rstep + cols2],
+                           sb3 = pa[3 * rstep + cols2];
+              pa[cols2] = sb0 - fma(v0, wB, w0 * vB);
+              pa[rstep + cols2] = sb1 - fma(v1, wB, w1 * vB);
+              pa[2 * rstep + cols2] = sb2 - fma(v2, wB, w2 * vB);
+              pa[3 * rstep + cols2] = sb3 - fma(v3, wB, w3 * vB);
+            }
+            pa[0] = sa0 - fma(v0, wA, w0 * vA);
+            pa[rstep] = sa1 - fma(v1, wA, w1 * vA);
+            pa[2 * rstep] = sa2 - fma(v2, wA, w2 * vA);
+            pa[3 * rstep] = sa3 - fma(v3, wA, w3 * vA);
           }
-          for (; i < n; i += G) Sc[i * lds] = Sc[i * lds] - fma(v[i], wj, w[i] * vj);
+          for (; i < n; i += G, pa += rstep) {
+            const double v0 = v[i], w0 = fma(alpha2, v0, P[i]);
+            if (actB) pa[cols2] = pa[cols2] - fma(v0, wB, w0 * vB);
+            pa[0] = pa[0] - fma(v0, wA, w0 * vA);
+          }
         }
       } else {
-        for (int jj = k + 3 + tid; jj < n; jj += THREADS) {
-          const double x = S[(k + 1) * lds + jj];
-          nxt[0] = fma(x, x, nxt[0]);
+        if (q == 0) {
+          if (actA && jA >= k + 3) nx = S[(k + 1) * lds + jA] * S[(k + 1) * lds + jA];
+          if (actB) nx = fma(S[(k + 1) * lds + jB], S[(k + 1) * lds + jB], nx);
         }
       }
-      block_sum_k<1>(nxt, s_rbuf1, parity);  // (E) also publishes the updated A22
-      xn2 = nxt[0];
+      // ---- reduction (E): next column norm; also publishes the updated A22 ----
+      if (wid < nredw) {
+        nx = warp_sum(nx);
+        if (lane == 0) rb[par * 8 + wid] = nx;
+      }
+      SEG(3);
+      __syncthreads();  // (E)
+      SEG(4);
+      xn2 = 0.0;
+      for (int ww = 0; ww < nredw; ++ww) xn2 += rb[par * 8 + ww];
+      par ^= 1;
     }
+    if (a.dbg && (tid == 0 || tid == THREADS - 32))
+      for (int i = 0; i < 5; ++i) a.dbg[(size_t)b * 16 + 8 + (tid == 0 ? 0 : 5) + i] = seg[i];
+#undef SEG
   }
   if (!trivial) {
     if (tid == 0) {
@@ -444,21 +553,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
         }
       }
       __syncthreads();
-      // twist index: gamma_k = D+_k - e2_k / D-_{k+1}
+      // twist index: gamma_k = D+_k - e2_k / D-_{k+1}   (Dm loads batched 8 deep: L2 latency)
       for (int i = tid; i < n; i += THREADS) {
         const int s = blk_s[i], t = blk_e[i];
         const double l = lam[i];
         double best = INFINITY;
         int r = s;
-        for (int k = s; k < t; ++k) {
-          double dp = d[k] - l;
-          if (k > s) dp = fma(-e2[k - 1], S[(k - 1) * lds + i], dp);
-          double gam = dp;
-          if (k + 1 < t) gam = fma(-e2[k], Dm[(size_t)(k + 1) * n + i], gam);
-          gam = fabs(gam);
-          if (gam < best) {
-            best = gam;
-            r = k;
+        for (int k0 = s; k0 < t; k0 += 8) {
+          double rm[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) rm[u] = (k0 + u + 1 < t) ? Dm[(size_t)(k0 + u + 1) * n + i] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u;
+            if (k < t) {
+              double dp = d[k] - l;
+              if (k > s) dp = fma(-e2[k - 1], S[(k - 1) * lds + i], dp);
+              const double gam = fabs(fma(-e2[k], rm[u], dp));  // e2[t-1] == 0 closes the block
+              if (gam < best) {
+                best = gam;
+                r = k;
+              }
+            }
           }
         }
         twist[i] = r;
@@ -480,10 +596,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
         }
         if (tt >= n || !two) {
           double z = 1.0, acc = 0.0;
-          for (int k = r + 1; k < t; ++k) {
-            z = -(e[k - 1] * Dm[(size_t)k * n + i]) * z;
-            S[k * lds + i] = z;
-            acc = fma(z, z, acc);
+          for (int k0 = r + 1; k0 < t; k0 += 8) {
+            double f[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] = (k0 + u < t) ? -(e[k0 + u - 1] * Dm[(size_t)(k0 + u) * n + i]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (k0 + u < t) {
+                z *= f[u];
+                S[(k0 + u) * lds + i] = z;
+                acc = fma(z, z, acc);
+              }
+            }
           }
           nrm_dn[i] = acc;
         }
@@ -744,7 +868,21 @@ extern "C" int mop_debug_tri_timing(void* buf) {
   return MOP_OK;
 }
 
+static int g_tri_threads_override = 0;
+static int g_tri_ablate = 0;
+extern "C" int mop_debug_tri_ablate(int mask) {
+  g_tri_ablate = mask;
+  return MOP_OK;
+}
+// diagnostics / tuning: force the CTA size of the tridiagonal kernels (0 = automatic)
+extern "C" int mop_debug_tri_threads(int threads) {
+  g_tri_threads_override = threads;
+  return MOP_OK;
+}
 static int tri_threads(int n) {
+  if (g_tri_threads_override == 128 || g_tri_threads_override == 256 || g_tri_threads_override == 512 ||
+      g_tri_threads_override == 1024)
+    return g_tri_threads_override;
   if (3 * n <= 128) return 128;
   if (3 * n <= 256) return 256;
   return 512;
@@ -772,6 +910,7 @@ static int launch_tri_any(int B, const mop::TriArgs& a, cudaStream_t stream) {
   switch (tri_threads(a.n)) {
     case 128: return launch_tri<128>(B, a, smem, stream);
     case 256: return launch_tri<256>(B, a, smem, stream);
+    case 1024: return launch_tri<1024>(B, a, smem, stream);
     default: return launch_tri<512>(B, a, smem, stream);
   }
 }
@@ -797,6 +936,7 @@ int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double
   a.evecs = evecs;
   a.status = status;
   a.dbg = g_tri_dbg;
+  a.ablate = g_tri_ablate;
   return launch_tri_any(B, a, stream);
 }
 
@@ -833,5 +973,6 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
   a.tmin = tmin;
   a.tmax = tmax;
   a.dbg = g_tri_dbg;
+  a.ablate = g_tri_ablate;
   return launch_tri_any(B, a, stream);
 }

@@ -198,6 +198,35 @@ def rsirfo_step(H, x, Bg, g, state, *, method: int, saddle_order: int = 0, neb_m
     return out
 
 
+def rsirfo_spectral_step(Hp, gp, Bg, state, *, saddle_order: int = 0, neb_mode: bool = False, Be=None,
+                         trust_min: float = 0.01, trust_max: float = 0.5, out=None):
+    """RSIRFO.run after the projections: fused tridiagonal eigensolve + RFO step (n <= 158)."""
+    lib = _lib.load()
+    B, n = gp.shape
+    dev = gp.device
+    _chk(Hp, "Hp", (B, n, n)); _chk(gp, "gp", (B, n)); _chk(Bg, "Bg", (B, n))
+    _chk(state, "state", (B, RSIRFO_STATE))
+    if Be is not None:
+        _chk(Be, "Be", (B,))
+    if out is None:
+        out = {
+            "move": torch.empty(B, n, dtype=torch.float64, device=dev),
+            "eigvals": torch.empty(B, n, dtype=torch.float64, device=dev),
+            "pred": torch.empty(B, dtype=torch.float64, device=dev),
+            "status": torch.zeros(B, dtype=torch.int32, device=dev),
+        }
+    nbytes = lib.mop_rsirfo_spectral_workspace_bytes(B, n)
+    work = workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        rc = lib.mop_rsirfo_spectral_step(B, n, int(saddle_order), int(bool(neb_mode)), float(trust_min),
+                                          float(trust_max), _ptr(Hp), _ptr(gp), _ptr(Bg), _ptr(Be),
+                                          _ptr(state), _ptr(out["move"]), _ptr(out["eigvals"]),
+                                          _ptr(out["pred"]), _ptr(out["status"]), _ptr(work), nbytes,
+                                          _stream(dev))
+    _lib.check(rc, "mop_rsirfo_spectral_step")
+    return out
+
+
 def clamp_and_move(x, move, trust_outer, want_geometry: bool = True):
     """optimizer.py:792-798,812: clamp ||move|| to trust_outer (in place) and return
     the new geometry in Angstrom."""

@@ -33,7 +33,11 @@ print("step1 status:", bits(out["status"].cpu().numpy()))
 
 from multioptpy_b200 import _lib
 lib = _lib.load()
-dbg = torch.zeros(B, 8, dtype=torch.int64, device=dev)
+if os.environ.get('TRI_THREADS'):
+    lib.mop_debug_tri_threads(int(os.environ['TRI_THREADS']))
+if os.environ.get('TRI_ABLATE'):
+    lib.mop_debug_tri_ablate(int(os.environ['TRI_ABLATE']))
+dbg = torch.zeros(B, 16, dtype=torch.int64, device=dev)
 lib.mop_debug_tri_timing(dbg.data_ptr())
 out = ops.rsirfo_step(Hs[3], x1d, g1d, g1d, sts[3], method=m, x_prev=x0d, g_prev=g0d, Be=zero - 1e-3)
 torch.cuda.synchronize()
@@ -43,4 +47,6 @@ names = ["load", "tridiag(+Qtg)", "spill/scale/split", "multisection", "twisted"
 print("phase cycles (median over CTAs):")
 for i, nm in enumerate(names):
     print(f"  {nm:20s} {np.median(d[:, i]):12.0f}  max {d[:, i].max():12.0f}")
-print("  total median", np.median(d.sum(1)))
+print("  total median", np.median(d[:, :8].sum(1)))
+print("phase-1 segments warp0   [top..A, A..B(symv), B..C(reduce), C..E-arrive(update), E wait]:", [int(np.median(d[:, 8 + i])) for i in range(5)])
+print("phase-1 segments warp15  [top..A, A..B(symv), B..C(reduce), C..E-arrive(update), E wait]:", [int(np.median(d[:, 13 + i])) for i in range(3)])
