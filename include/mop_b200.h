@@ -167,6 +167,38 @@ int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_mode, doubl
                              double* eigvals_out, double* pred_out, int32_t* status, void* work,
                              size_t work_bytes, void* stream);
 
+/* ---- (3a) connectivity tables ------------------------------------------------
+ * Replaces BondConnectivity.connectivity_table (Utils/bond_connectivity.py:7-134):
+ * bonds [B][capB][2] (i <= j), angles [B][capA][3] as [j, i, n] with centre i, dihedrals
+ * [B][capD][4]; counts [B][3].  Index values and ORDER are bit-exact with the reference.
+ * radii: covalent radii in Bohr, [B][natoms] (radii_stride = natoms) or one molecule shared
+ * by the batch (radii_stride = 0); factor = 1.1 in the reference.  status[b] = 1 when a
+ * table overflowed its capacity. */
+int mop_connectivity(int B, int natoms, const double* xyz, const double* radii, int radii_stride,
+                     double factor, int capB, int capA, int capD, int32_t* bonds, int32_t* angles,
+                     int32_t* dihedrals, int32_t* counts, int32_t* status, void* stream);
+
+/* ---- (3b) Fischer model Hessian ------------------------------------------------
+ * Replaces FischerApproxHessian.main (ModelHessian/fischer.py:212-236), i.e.
+ * ApproxHessian().main(coord, element_list, cart_gradient, "fischer"): bond / angle /
+ * dihedral force constants, sum k b b^T with the Wilson vectors of
+ * ModelHessian/calc_params.py, upper-to-lower symmetrisation, TR/ROT projection.
+ * H_out [B][3N][3N]; counts_out (optional) [B][3] = table sizes. */
+size_t mop_fischer_workspace_bytes(int B, int natoms);
+int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radii, int radii_stride,
+                        double* H_out, int32_t* counts_out, int32_t* status, void* work,
+                        size_t work_bytes, void* stream);
+
+/* ---- (3c) AFIR bias potential ---------------------------------------------------
+ * Replaces AFIRPotential.calc_energy (Potential/AFIR_potential.py:18-55) and the
+ * torch.func.jacrev / hessian calls of BiasPotentialCalculation.main
+ * (Potential/potential.py:127-152) for AFIR terms: E [B], grad [B][3N], H [B][3N][3N]
+ * (any of them may be NULL).  frag1 / frag2: 0-based atom indices; radii_f32: covalent
+ * radii in Bohr ROUNDED TO FLOAT32 (the reference builds float32 tensors); gamma [B] kJ/mol. */
+int mop_afir(int B, int natoms, const double* xyz, int n1, const int32_t* frag1, int n2,
+             const int32_t* frag2, const float* radii_f32, const double* gamma, double* E,
+             double* grad, double* H, void* stream);
+
 /* ---- caller side: CalculateMoveVector.calc_move_vector clamp -------------
  * Replaces optimizer.py:792-798,812: scale move to trust_outer[B] if longer,
  * x_new_ang = (x - move) * 0.52917721067. */

@@ -1,0 +1,55 @@
+"""Drop-in for the AFIR part of ``multioptpy.Potential.potential.BiasPotentialCalculation``
+(Potential/potential.py:53-202): sums the bias energy / gradient / Hessian of every AFIR term
+of ``force_data`` (the only bias potential the north-star path names; other potentials raise).
+The reference's side effects (.npy / .log files, :144,191-192) are not reproduced."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .._lib import MopError
+from .AFIR_potential import AFIRPotential
+
+_OTHER_KEYS = ["linear_mechano_force", "linear_mechano_force_v2", "flux_pot_const", "keep_pot_v2_spring_const",
+               "keep_angle_v2_spring_const", "keep_dihedral_angle_v2_spring_const", "repulsive_potential_well_scale",
+               "gaussian_potential_target", "nano_reactor_potential", "asymmetric_ellipsoidal_repulsive_potential_eps"]
+
+
+def gradually_change_param(param_1, param_2, iter):
+    """potential.py:218-226: linear ramp over 300 iterations."""
+    parameter = param_1 + ((param_2 - param_1) / 300) * int(iter)
+    if param_1 < param_2:
+        return min(parameter, param_2)
+    if param_1 > param_2:
+        return max(parameter, param_2)
+    return parameter
+
+
+class BiasPotentialCalculation:
+    def __init__(self, FOLDER_DIRECTORY="", device="cuda"):
+        self.BPA_FOLDER_DIRECTORY = FOLDER_DIRECTORY
+        self.device = device
+        self.bias_pot_obj_list = []
+
+    def main(self, e, g, geom_num_list, element_list, force_data, pre_B_g="", iter="", initial_geom_num_list=""):
+        """-> (bias_grad (N,3), B_e, B_g (N,3), bias_hessian (3N,3N)), potential.py:202."""
+        for key in _OTHER_KEYS:
+            if len(force_data.get(key, [])) > 0 and any(np.ravel(np.asarray(force_data[key], dtype=object)) != 0):
+                raise MopError(f"bias potential '{key}' is outside the B200 hot-path scope (AFIR only)")
+        geom = np.asarray(geom_num_list, dtype=np.float64)
+        N = geom.shape[0]
+        bias_grad = np.zeros_like(geom)
+        bias_hess = np.zeros((3 * N, 3 * N))
+        B_e = 0.0
+        for i in range(len(force_data.get("AFIR_gamma", []))):
+            gam = force_data["AFIR_gamma"][i]
+            if 0.0 in gam:                                   # potential.py:469
+                continue
+            gval = gradually_change_param(gam[0], gam[1], iter) if (len(gam) == 2 and iter != "") else gam[0]
+            pot = AFIRPotential(AFIR_Fragm_1=force_data["AFIR_Fragm_1"][i], AFIR_Fragm_2=force_data["AFIR_Fragm_2"][i],
+                                element_list=element_list, device=self.device)
+            E, gr, H = pot.calc_energy_grad_hess(geom, [gval])
+            B_e += float(E.item())
+            bias_grad = bias_grad + gr.cpu().numpy()
+            bias_hess = bias_hess + H.cpu().numpy()
+        return bias_grad, B_e + e, g + bias_grad, bias_hess

@@ -36,6 +36,10 @@ SIGNATURES = {
                              _p, _p, _p, _p, _sz, _p]),
     "mop_rsirfo_spectral_workspace_bytes": (_sz, [_i, _i]),
     "mop_rsirfo_spectral_step": (_i, [_i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mop_connectivity": (_i, [_i, _i, _p, _p, _i, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "mop_fischer_workspace_bytes": (_sz, [_i, _i]),
+    "mop_fischer_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mop_afir": (_i, [_i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "mop_bench_dfma": (_i, [_i, _i, _p, _p]),
     "mop_bench_fill": (_i, [_p, _sz, _d, _p]),

@@ -1,0 +1,321 @@
+// Model-Hessian assembly: connectivity tables, Fischer and Lindh
+// model Hessians as sums of  k_t b_t b_t^T  over internal coordinates.
+//
+// One CTA per structure.  Phase 1: connectivity (connectivity.cuh, bit-exact tables);
+// phase 2: one thread per internal coordinate evaluates its force constant and Wilson
+// b-vectors (restating ModelHessian/calc_params.py stretch2/bend2/torsion2) into an L2
+// scratch record; phase 3: one thread per ATOM-PAIR block gathers the records that touch
+// both atoms IN TABLE ORDER (bonds, angles, dihedrals) — deterministic, no atomics, the
+// reference's accumulation order — and writes the 3x3 block and its mirror.
+// The TR/ROT projection that ends every reference model (calc_tools.py:249) is the
+// separate k_project_trrot launch.  HBM-bound: 8 n^2 bytes written per structure.
+#include "connectivity.cuh"
+
+namespace mop {
+
+constexpr int MH_THREADS = 512;
+constexpr double PI_D = 3.141592653589793;
+
+struct ICRec {      // one internal coordinate
+  int atom[4];      // -1 padded
+  double k;         // force constant (0: skipped)
+  double b[12];     // Wilson vectors, b[3*p + c] for atom slot p
+};
+
+// stretch2 (calc_params.py:220-227): b0 = -(x0 - x1)/r, b1 = +(x0 - x1)/r
+__device__ __forceinline__ double stretch2(const double* x0, const double* x1, double b0[3], double b1[3]) {
+  const double d0 = x0[0] - x1[0], d1 = x0[1] - x1[1], d2 = x0[2] - x1[2];
+  const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
+  b0[0] = -1.0 * d0 / r; b0[1] = -1.0 * d1 / r; b0[2] = -1.0 * d2 / r;
+  b1[0] = d0 / r; b1[1] = d1 / r; b1[2] = d2 / r;
+  return r;
+}
+
+// bend2 (calc_params.py:183-218) for atoms (0, 1, 2), centre 1.  Returns the angle.
+__device__ __forceinline__ double bend2(const double* x0, const double* x1, const double* x2,
+                                        double bf[9], double* r01, double* r12) {
+  double bij0[3], bij1[3], bjk0[3], bjk1[3];
+  const double rij = stretch2(x0, x1, bij0, bij1);
+  const double rjk = stretch2(x1, x2, bjk0, bjk1);
+  double co = 0.0, crap = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    co += bij0[i] * bjk1[i];
+    crap += bij0[i] * bij0[i];
+    crap += bjk1[i] * bjk1[i];
+  }
+  double fir, si;
+  if (sqrt(crap) < 1e-12) {
+    fir = PI_D - asin(sqrt(crap));
+    si = sqrt(crap);
+  } else {
+    fir = acos(co);
+    si = sqrt(1.0 - co * co);
+  }
+  if (fabs(fir - PI_D) < 1e-12) fir = PI_D;
+  const double den1 = rij * si, den2 = rjk * si;
+  for (int i = 0; i < 3; ++i) {
+    bf[i] = den1 < 1e-12 ? 0.0 : (co * bij0[i] - bjk1[i]) / den1;
+    bf[6 + i] = den2 < 1e-12 ? 0.0 : (co * bjk1[i] - bij0[i]) / den2;
+    bf[3 + i] = -1.0 * (bf[i] + bf[6 + i]);
+  }
+  if (r01) *r01 = rij;
+  if (r12) *r12 = rjk;
+  return fir;
+}
+
+// torsion2 (calc_params.py:137-181): b-vectors of the dihedral 0-1-2-3.
+__device__ __forceinline__ void torsion2(const double* x0, const double* x1, const double* x2,
+                                         const double* x3, double bt[12]) {
+  double brij0[3], brij1[3], brjk0[3], brjk1[3], brkl0[3], brkl1[3], tmp[9];
+  const double r1 = stretch2(x0, x1, brij0, brij1);
+  const double r2 = stretch2(x1, x2, brjk0, brjk1);
+  const double r3 = stretch2(x2, x3, brkl0, brkl1);
+  const double fi2 = bend2(x0, x1, x2, tmp, nullptr, nullptr);
+  const double fi3 = bend2(x1, x2, x3, tmp, nullptr, nullptr);
+  const double s2 = sin(fi2), s3 = sin(fi3), c2 = cos(fi2), c3 = cos(fi3);
+  for (int ix = 1; ix <= 3; ++ix) {
+    int iy = ix + 1;
+    if (iy > 3) iy -= 3;
+    int iz = iy + 1;
+    if (iz > 3) iz -= 3;
+    const double t0 = (brij1[iy - 1] * brjk1[iz - 1] - brij1[iz - 1] * brjk1[iy - 1]) / (r1 * (s2 * s2));
+    const double t3 = (brkl0[iy - 1] * brjk0[iz - 1] - brkl0[iz - 1] * brjk0[iy - 1]) / (r3 * (s3 * s3));
+    const double t1 = -1.0 * ((r2 - r1 * c2) * t0 + r3 * c3 * t3) / r2;
+    bt[ix - 1] = t0;
+    bt[9 + ix - 1] = t3;
+    bt[3 + ix - 1] = t1;
+    bt[6 + ix - 1] = -1.0 * (t0 + t1 + t3);
+  }
+}
+
+// sin^2 of the angle a-b-c (fischer.py:155-165)
+__device__ __forceinline__ double sin_sq_angle(const double* xa, const double* xb, const double* xc) {
+  const double v1[3] = {xa[0] - xb[0], xa[1] - xb[1], xa[2] - xb[2]};
+  const double v2[3] = {xc[0] - xb[0], xc[1] - xb[1], xc[2] - xb[2]};
+  const double cx = v1[1] * v2[2] - v1[2] * v2[1], cy = v1[2] * v2[0] - v1[0] * v2[2],
+               cz = v1[0] * v2[1] - v1[1] * v2[0];
+  const double cs = cx * cx + cy * cy + cz * cz;
+  const double n1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  const double n2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  if (n1 * n2 < 1e-12) return 0.0;
+  return cs / (n1 * n2);
+}
+
+// ---------------------------------------------------------------------------------------
+// kind 0: connectivity tables only; kind 1: Fischer (ModelHessian/fischer.py)
+__global__ void __launch_bounds__(MH_THREADS, 1)
+k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const double* __restrict__ rad_all,
+                int rad_stride, double factor, int capB, int capA, int capD, int* __restrict__ bonds_all,
+                int* __restrict__ angles_all, int* __restrict__ dihs_all, int* __restrict__ counts_all,
+                ICRec* __restrict__ rec_all, double* __restrict__ H_all, int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* xyz = sm;              // 3N
+  double* rad = xyz + 3 * N;     // N
+  int* cnt = (int*)(rad + N);    // 4
+  int* wtot = cnt + 4;           // 36
+  int* nb13 = wtot + 36;         // N : neighbour count with the 1.3 factor (Fischer bond_sum)
+  unsigned char* bm = (unsigned char*)(nb13 + N + (N & 1));  // N*N
+  for (int i = tid; i < 3 * N; i += MH_THREADS) xyz[i] = xyz_all[(size_t)b * 3 * N + i];
+  for (int i = tid; i < N; i += MH_THREADS) rad[i] = rad_all[(size_t)b * rad_stride + i];
+  __syncthreads();
+  bond_matrix(N, xyz, rad, factor, bm);
+  ConnTables T;
+  T.bonds = bonds_all + (size_t)b * capB * 2;
+  T.angles = angles_all + (size_t)b * capA * 3;
+  T.dihs = dihs_all + (size_t)b * capD * 4;
+  T.capB = capB; T.capA = capA; T.capD = capD;
+  enumerate_tables(N, bm, T, cnt, wtot);
+  if (tid == 0) {
+    counts_all[3 * b] = T.nb;
+    counts_all[3 * b + 1] = T.na;
+    counts_all[3 * b + 2] = T.nd;
+    if (status) status[b] = T.overflow ? 1 : 0;
+  }
+  if (kind == 0) return;
+
+  // ---- Fischer: records -------------------------------------------------------------
+  ICRec* rec = rec_all + (size_t)b * (capB + capA + capD);
+  const int nrec = T.nb + T.na + T.nd;
+  // bond_sum uses a SECOND connectivity with factor 1.3 (fischer.py:17,63)
+  for (int i = tid; i < N; i += MH_THREADS) {
+    int c = 0;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const int lo = i < j ? i : j, hi = i < j ? j : i;  // dist = ||coord[lo] - coord[hi]||
+      const double d = np_dist(xyz + 3 * lo, xyz + 3 * hi);
+      const double cs = __dadd_rn(rad[lo], rad[hi]);
+      c += d <= __dmul_rn(cs, 1.3);
+    }
+    nb13[i] = c;
+  }
+  __syncthreads();
+  for (int t = tid; t < nrec; t += MH_THREADS) {
+    ICRec r;
+    for (int q = 0; q < 4; ++q) r.atom[q] = -1;
+    for (int q = 0; q < 12; ++q) r.b[q] = 0.0;
+    r.k = 0.0;
+    if (t < T.nb) {  // fischer_bond (fischer.py:73-98)
+      const int i = T.bonds[2 * t], j = T.bonds[2 * t + 1];
+      r.atom[0] = i; r.atom[1] = j;
+      const double rij = np_dist(xyz + 3 * i, xyz + 3 * j);
+      const double rcov = __dadd_rn(rad[i], rad[j]);
+      r.k = 0.3601 * exp(-1.944 * (rij - rcov));
+      stretch2(xyz + 3 * i, xyz + 3 * j, r.b, r.b + 3);
+    } else if (t < T.nb + T.na) {  // fischer_angle (:100-131)
+      const int* a = T.angles + 3 * (t - T.nb);
+      const int i = a[0], j = a[1], k = a[2];
+      r.atom[0] = i; r.atom[1] = j; r.atom[2] = k;
+      const double rij = np_dist(xyz + 3 * i, xyz + 3 * j), rjk = np_dist(xyz + 3 * j, xyz + 3 * k);
+      const double cij = __dadd_rn(rad[i], rad[j]), cjk = __dadd_rn(rad[j], rad[k]);
+      const double val = cij * cjk;
+      r.k = fabs(val) < 1e-10 ? 0.0
+                              : 0.089 + 0.11 / pow(val, -0.42) * exp(-0.44 * (rij + rjk - cij - cjk));
+      bend2(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k, r.b, nullptr, nullptr);
+    } else {  // fischer_dihedral (:133-210)
+      const int* a = T.dihs + 4 * (t - T.nb - T.na);
+      const int i = a[0], j = a[1], k = a[2], l = a[3];
+      r.atom[0] = i; r.atom[1] = j; r.atom[2] = k; r.atom[3] = l;
+      const double s1 = sin_sq_angle(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k);
+      const double s2 = sin_sq_angle(xyz + 3 * j, xyz + 3 * k, xyz + 3 * l);
+      if (!(s1 < 1.0e-3 || s2 < 1.0e-3)) {
+        const double rjk = np_dist(xyz + 3 * j, xyz + 3 * k);
+        const double cjk = __dadd_rn(rad[j], rad[k]);
+        const int bond_sum = nb13[j] + nb13[k] - 2;
+        const double val = rjk * cjk;
+        r.k = fabs(val) < 1e-10
+                  ? 0.0
+                  : 0.0015 + 14.0 * pow((double)max(bond_sum, 0), 0.57) / pow(val, 4.0) * exp(-2.85 * (rjk - cjk));
+        torsion2(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k, xyz + 3 * l, r.b);
+      }
+    }
+    rec[t] = r;
+  }
+  __syncthreads();
+
+  // ---- gather per atom-pair block (a <= c), table order --------------------------------
+  double* H = H_all + (size_t)b * 9 * N * N;
+  const int n = 3 * N;
+  for (int e = tid; e < N * N; e += MH_THREADS) {
+    const int a = e / N, c = e - a * N;
+    if (a > c) continue;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < nrec; ++t) {
+      const ICRec* r = rec + t;
+      int pa = -1, pc = -1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int at = r->atom[q];
+        if (at == a) pa = q;
+        if (at == c) pc = q;
+      }
+      if (pa < 0 || pc < 0) continue;
+      const double k = r->k;
+      if (k == 0.0) continue;  // skipped dihedral (reference `continue`s before accumulating)
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) acc[3 * p + m] += k * r->b[3 * pa + p] * r->b[3 * pc + m];
+    }
+    // upper triangle is authoritative: cart_hess[i, j] = cart_hess[j, i] for j < i (fischer.py:229-231)
+    for (int p = 0; p < 3; ++p)
+      for (int m = 0; m < 3; ++m) {
+        const int row = 3 * a + p, col = 3 * c + m;
+        if (row <= col) {
+          H[(size_t)row * n + col] = acc[3 * p + m];
+          H[(size_t)col * n + row] = acc[3 * p + m];
+        }
+      }
+  }
+}
+
+}  // namespace mop
+
+// forward declaration (project.cu)
+int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             cudaStream_t stream);
+
+static size_t mh_smem(int N) {
+  return sizeof(double) * (4 * (size_t)N) + sizeof(int) * (40 + (size_t)N + 1) + (size_t)N * N + 16;
+}
+
+extern "C" int mop_connectivity(int B, int natoms, const double* xyz, const double* radii,
+                                int radii_stride, double factor, int capB, int capA, int capD,
+                                int32_t* bonds, int32_t* angles, int32_t* dihedrals, int32_t* counts,
+                                int32_t* status, void* stream) {
+  MOP_REQUIRE(B >= 0 && natoms > 0, "mop_connectivity: B >= 0 and natoms > 0 required");
+  MOP_REQUIRE(xyz && radii && bonds && angles && dihedrals && counts,
+              "mop_connectivity: xyz, radii, bonds, angles, dihedrals, counts must be device pointers");
+  MOP_REQUIRE(radii_stride == 0 || radii_stride == natoms, "mop_connectivity: radii_stride must be 0 or natoms");
+  if (B == 0) return MOP_OK;
+  const size_t smem = mh_smem(natoms);
+  if (smem > 200 * 1024) {
+    mop_set_error("mop_connectivity: natoms = %d too large", natoms);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_model_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_model_hessian<<<B, mop::MH_THREADS, smem, (cudaStream_t)stream>>>(
+      0, natoms, xyz, radii, radii_stride, factor, capB, capA, capD, bonds, angles, dihedrals, counts,
+      nullptr, nullptr, status);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+static void fischer_caps(int N, int* capB, int* capA, int* capD) {
+  *capB = N * 8 < N * (N - 1) / 2 + 1 ? N * 8 : N * (N - 1) / 2 + 1;
+  *capA = N * 28;
+  *capD = N * 64;
+}
+
+extern "C" size_t mop_fischer_workspace_bytes(int B, int natoms) {
+  if (B <= 0 || natoms <= 0) return 0;
+  int cb, ca, cd;
+  fischer_caps(natoms, &cb, &ca, &cd);
+  size_t bytes = (size_t)B * (2 * cb + 3 * ca + 4 * cd + 4) * sizeof(int32_t);
+  bytes = (bytes + 255) & ~(size_t)255;
+  bytes += (size_t)B * (cb + ca + cd) * sizeof(mop::ICRec);
+  bytes = (bytes + 255) & ~(size_t)255;
+  bytes += (size_t)B * 9 * natoms * natoms * sizeof(double);  // unprojected Hessian
+  return bytes;
+}
+
+// FischerApproxHessian.main (ModelHessian/fischer.py:212-236): H_out [B][3N][3N], TR/ROT projected.
+extern "C" int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radii,
+                                   int radii_stride, double* H_out, int32_t* counts_out,
+                                   int32_t* status, void* work, size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && natoms > 0, "mop_fischer_hessian: B >= 0 and natoms > 0 required");
+  MOP_REQUIRE(xyz && radii && H_out && work, "mop_fischer_hessian: xyz, radii, H_out, work must be device pointers");
+  MOP_REQUIRE(radii_stride == 0 || radii_stride == natoms, "mop_fischer_hessian: radii_stride must be 0 or natoms");
+  if (B == 0) return MOP_OK;
+  if (work_bytes < mop_fischer_workspace_bytes(B, natoms)) {
+    mop_set_error("mop_fischer_hessian: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int cb, ca, cd;
+  fischer_caps(natoms, &cb, &ca, &cd);
+  char* w = (char*)work;
+  int32_t* bonds = (int32_t*)w;
+  int32_t* angles = bonds + (size_t)B * 2 * cb;
+  int32_t* dihs = angles + (size_t)B * 3 * ca;
+  int32_t* counts = dihs + (size_t)B * 4 * cd;
+  size_t off = ((size_t)B * (2 * cb + 3 * ca + 4 * cd + 4) * sizeof(int32_t) + 255) & ~(size_t)255;
+  mop::ICRec* rec = (mop::ICRec*)(w + off);
+  off += ((size_t)B * (cb + ca + cd) * sizeof(mop::ICRec) + 255) & ~(size_t)255;
+  double* Hraw = (double*)(w + off);
+  const size_t smem = mh_smem(natoms);
+  if (smem > 200 * 1024) {
+    mop_set_error("mop_fischer_hessian: natoms = %d too large", natoms);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_model_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_model_hessian<<<B, mop::MH_THREADS, smem, stream>>>(1, natoms, xyz, radii, radii_stride, 1.1, cb, ca,
+                                                           cd, bonds, angles, dihs, counts, rec, Hraw,
+                                                           status);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  if (counts_out)
+    MOP_CHECK_CUDA(cudaMemcpyAsync(counts_out, counts, sizeof(int32_t) * 3 * (size_t)B,
+                                   cudaMemcpyDeviceToDevice, stream));
+  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, stream);
+}

@@ -242,3 +242,72 @@ def clamp_and_move(x, move, trust_outer, want_geometry: bool = True):
                                     _stream(move.device))
     _lib.check(rc, "mop_clamp_and_move")
     return xnew, move
+
+
+# ---- (3) producers -------------------------------------------------------------------------
+def _radii_arg(radii, B, N, dev):
+    """radii: (N,) shared by the batch or (B, N); returns (tensor, stride)."""
+    r = radii if isinstance(radii, torch.Tensor) else torch.as_tensor(radii, dtype=torch.float64)
+    r = r.to(dev, torch.float64).contiguous()
+    if r.dim() == 1:
+        _chk(r, "radii", (N,))
+        return r, 0
+    _chk(r, "radii", (B, N))
+    return r, N
+
+
+def connectivity(xyz, radii, factor: float = 1.1, caps=None):
+    """Bond / angle / dihedral tables of every structure.  xyz: (B, N, 3) Bohr.
+    Returns (bonds, angles, dihedrals, counts, status) int32 tensors (padded to the capacity)."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    r, stride = _radii_arg(radii, B, N, xyz.device)
+    capB, capA, capD = caps if caps else (min(8 * N, N * (N - 1) // 2 + 1), 28 * N, 64 * N)
+    i32 = dict(dtype=torch.int32, device=xyz.device)
+    bonds = torch.full((B, capB, 2), -1, **i32); angles = torch.full((B, capA, 3), -1, **i32)
+    dihs = torch.full((B, capD, 4), -1, **i32); counts = torch.zeros(B, 3, **i32)
+    status = torch.zeros(B, **i32)
+    with torch.cuda.device(xyz.device):
+        rc = lib.mop_connectivity(B, N, _ptr(xyz), _ptr(r), stride, float(factor), capB, capA, capD,
+                                  _ptr(bonds), _ptr(angles), _ptr(dihs), _ptr(counts), _ptr(status),
+                                  _stream(xyz.device))
+    _lib.check(rc, "mop_connectivity")
+    return bonds, angles, dihs, counts, status
+
+
+def fischer_hessian(xyz, radii):
+    """FischerApproxHessian.main for every structure: (B, 3N, 3N) projected model Hessians."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    r, stride = _radii_arg(radii, B, N, xyz.device)
+    H = torch.empty(B, 3 * N, 3 * N, dtype=torch.float64, device=xyz.device)
+    counts = torch.zeros(B, 3, dtype=torch.int32, device=xyz.device)
+    status = torch.zeros(B, dtype=torch.int32, device=xyz.device)
+    nbytes = lib.mop_fischer_workspace_bytes(B, N)
+    work = workspace(xyz.device, nbytes)
+    with torch.cuda.device(xyz.device):
+        rc = lib.mop_fischer_hessian(B, N, _ptr(xyz), _ptr(r), stride, _ptr(H), _ptr(counts), _ptr(status),
+                                     _ptr(work), nbytes, _stream(xyz.device))
+    _lib.check(rc, "mop_fischer_hessian")
+    return H, counts, status
+
+
+def afir(xyz, frag1, frag2, radii_f32, gamma, want_grad: bool = True, want_hess: bool = True):
+    """AFIR energy / gradient / Hessian.  xyz (B, N, 3); frag1/frag2 0-based int32 index tensors;
+    radii_f32 (N,) float32 Bohr; gamma (B,) kJ/mol.  Returns (E (B,), grad (B, 3N), H (B, 3N, 3N))."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    dev = xyz.device
+    _chk(xyz, "xyz", (B, N, 3)); _chk(gamma, "gamma", (B,))
+    _chk(radii_f32, "radii_f32", (N,), torch.float32)
+    _chk(frag1, "frag1", None, torch.int32); _chk(frag2, "frag2", None, torch.int32)
+    E = torch.empty(B, dtype=torch.float64, device=dev)
+    g = torch.empty(B, 3 * N, dtype=torch.float64, device=dev) if want_grad else None
+    H = torch.empty(B, 3 * N, 3 * N, dtype=torch.float64, device=dev) if want_hess else None
+    with torch.cuda.device(dev):
+        rc = lib.mop_afir(B, N, _ptr(xyz), frag1.numel(), _ptr(frag1), frag2.numel(), _ptr(frag2),
+                          _ptr(radii_f32), _ptr(gamma), _ptr(E), _ptr(g), _ptr(H), _stream(dev))
+    _lib.check(rc, "mop_afir")
+    return E, g, H

@@ -244,7 +244,82 @@ def gen_projection():
     print("projection: 4 cases")
 
 
-SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection}
+def read_xyz(path):
+    """Minimal xyz reader (Angstrom) -> (elements, coords in Bohr)."""
+    lines = [l.split() for l in open(path).read().strip().splitlines()]
+    rows = [l for l in lines if len(l) >= 4 and l[0][0].isalpha()]
+    elems = [r[0] for r in rows]
+    xyz = np.array([[float(v) for v in r[1:4]] for r in rows]) / 0.52917721067
+    return elems, xyz
+
+
+PRODUCER_CASES = [
+    ("aldol_rxn", "test/aldol_rxn.xyz"), ("s8", "test/s8_for_confomation_search_test.xyz"),
+    ("aldol_rxn_PT", "test/aldol_rxn_PT.xyz"), ("reductive_elimination", "test/reductive_elimination.xyz"),
+    ("claisen", "test/claisen_rearrengment.xyz"), ("SN2", "test/SN2.xyz"),
+    ("grid24", None), ("grid50", None),
+]
+
+
+def producer_geometry(name, path):
+    if path is not None:
+        return read_xyz(os.path.join(ref_shim.REF_ROOT, path))
+    natoms = int(name[4:])
+    rng = np.random.default_rng(5150 + natoms)
+    # a compact, chemically plausible cloud: grid spacing 2.6 Bohr so that bonds/angles/dihedrals exist
+    xyz = synthetic.grid_geometry(natoms, rng, spacing=2.6, jitter=0.25)
+    return synthetic.elements(natoms), xyz
+
+
+def pad_table(tab, width):
+    a = np.full((max(len(tab), 1), width), -1, np.int32)
+    for i, row in enumerate(tab):
+        a[i] = row
+    return a
+
+
+def gen_producers():
+    import torch
+    bc = ref_shim.ref("Utils.bond_connectivity")
+    fi = ref_shim.ref("ModelHessian.fischer")
+    af = ref_shim.ref("Potential.AFIR_potential")
+    blob = {"names": np.array([c[0] for c in PRODUCER_CASES])}
+    for name, path in PRODUCER_CASES:
+        elems, xyz = producer_geometry(name, path)
+        N = len(elems)
+        with quiet():
+            tabs = bc.BondConnectivity().connectivity_table(xyz.copy(), elems)
+            Hf = fi.FischerApproxHessian().main(xyz.copy(), elems, np.zeros((N, 3)))
+        blob[f"{name}/elements"] = np.array(elems)
+        blob[f"{name}/xyz"] = xyz
+        blob[f"{name}/counts"] = np.array([len(t) for t in tabs], np.int32)
+        blob[f"{name}/bonds"] = pad_table(tabs[0], 2)
+        blob[f"{name}/angles"] = pad_table(tabs[1], 3)
+        blob[f"{name}/dihedrals"] = pad_table(tabs[2], 4)
+        blob[f"{name}/fischer"] = np.asarray(Hf, float)
+        # AFIR: a single atom pair and a half/half fragment split (1-based indices as on the CLI)
+        half = N // 2
+        afir_cases = [([1], [min(5, N)], 95.0), (list(range(1, half + 1)), list(range(half + 1, N + 1)), 100.0),
+                      ([2, 3], [N], -40.0)]
+        Es, Gs, Hs, F1, F2, GAM = [], [], [], [], [], []
+        for f1, f2, gamma in afir_cases:
+            pot = af.AFIRPotential(AFIR_Fragm_1=f1, AFIR_Fragm_2=f2, element_list=elems)
+            geom = torch.tensor(xyz, dtype=torch.float64, requires_grad=True)
+            par = torch.tensor([gamma], dtype=torch.float64, requires_grad=True)
+            E = pot.calc_energy(geom, par)
+            g = torch.func.jacrev(pot.calc_energy, argnums=0)(geom, par)
+            H = torch.func.hessian(pot.calc_energy, argnums=0)(geom, par).reshape(3 * N, 3 * N)
+            Es.append(float(E)); Gs.append(g.detach().numpy()); Hs.append(H.detach().numpy())
+            F1.append(np.pad(np.array(f1, np.int32), (0, N - len(f1)), constant_values=-1))
+            F2.append(np.pad(np.array(f2, np.int32), (0, N - len(f2)), constant_values=-1))
+            GAM.append(gamma)
+        blob[f"{name}/afir_E"] = np.array(Es); blob[f"{name}/afir_g"] = np.stack(Gs); blob[f"{name}/afir_H"] = np.stack(Hs)
+        blob[f"{name}/afir_f1"] = np.stack(F1); blob[f"{name}/afir_f2"] = np.stack(F2); blob[f"{name}/afir_gamma"] = np.array(GAM)
+        print("producers case", name, N, "atoms, tables", [len(t) for t in tabs])
+    np.savez_compressed(os.path.join(GOLD, "producers.npz"), **blob)
+
+
+SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

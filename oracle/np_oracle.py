@@ -745,3 +745,208 @@ class TrustRadiusOracle:
                 trust *= f ** 0.5
         self.count += 1
         return float(np.clip(trust, self.min, self.max))
+
+
+# --------------------------------------------------------------------------
+# connectivity tables (integer, bit-exact part of the contract)
+# --------------------------------------------------------------------------
+def bond_matrix(coord, radii, factor=1.1):
+    """BondConnectivity.bond_connect_matrix, Utils/bond_connectivity.py:13-41."""
+    n = len(coord)
+    m = np.zeros((n, n), dtype=int)
+    for i in range(n):
+        d = np.linalg.norm(coord - coord[i], axis=1)
+        d[i] = 0.0
+        thr = (radii + radii[i]) * factor
+        thr[i] = -1.0
+        m[i] = np.where(d <= thr, 1, 0)
+    return m
+
+
+def connectivity_tables(coord, radii, factor=1.1):
+    """bond / angle / dihedral tables, Utils/bond_connectivity.py:43-134."""
+    m = bond_matrix(coord, radii, factor)
+    n = len(m)
+    bonds = [[i, j] for i in range(n) for j in range(n) if i <= j and m[i, j] == 1]
+    angles = []
+    for i in range(n):
+        for j in range(n):
+            if m[i][j] == 1:
+                for k in range(j + 1, n):
+                    if m[i][k] == 1 and m[j][k] == 0:
+                        angles.append([j, i, k])
+    dihs = []
+    for i in range(len(angles)):
+        a = angles[i]
+        for j in range(i + 1, len(angles)):
+            b = angles[j]
+            hit = None
+            if (a[1] == b[1] and a[2] == b[2]) or (a[1] == b[2] and a[2] == b[1]):
+                c = [a[0], a[1], a[2], b[0]]
+                if m[c[2]][c[3]] == 1:
+                    hit = c
+                else:
+                    c = [b[0], a[0], a[1], a[2]]
+                    if m[c[1]][c[0]] == 1:
+                        hit = c
+            if hit is None and ((a[1] == b[1] and a[0] == b[0]) or (a[1] == b[0] and a[0] == b[1])):
+                c = [b[2], a[0], a[1], a[2]]
+                if m[c[1]][c[0]] == 1:
+                    hit = c
+                else:
+                    c = [a[0], a[1], a[2], b[2]]
+                    if m[c[2]][c[3]] == 1:
+                        hit = c
+            if hit is None and ((a[1] == b[0] and a[2] == b[1]) or (a[1] == b[1] and a[2] == b[0])):
+                c = [a[0], a[1], a[2], b[2]]
+                if m[c[2]][c[3]] == 1:
+                    hit = c
+                else:
+                    c = [b[2], a[0], a[1], a[2]]
+                    if m[c[1]][c[0]] == 1:
+                        hit = c
+            if hit is None and ((a[0] == b[1] and a[1] == b[2]) or (a[0] == b[2] and a[1] == b[1])):
+                c = [b[0], a[0], a[1], a[2]]
+                if m[c[1]][c[0]] == 1:
+                    hit = c
+                else:
+                    c = [a[0], a[1], a[2], b[0]]
+                    if m[c[2]][c[3]] == 1:
+                        hit = c
+            if hit is not None:
+                dihs.append(hit)
+    return bonds, angles, dihs
+
+
+# --------------------------------------------------------------------------
+# Wilson vectors (ModelHessian/calc_params.py) and the Fischer model Hessian
+# --------------------------------------------------------------------------
+def w_stretch(x0, x1):
+    """stretch2, calc_params.py:220-227."""
+    d = x0 - x1
+    r = np.linalg.norm(d)
+    return r, np.array([-1 * d / r, d / r])
+
+
+def w_bend(x0, x1, x2):
+    """bend2, calc_params.py:183-218."""
+    r1, b1 = w_stretch(x0, x1)
+    r2, b2 = w_stretch(x1, x2)
+    co = float(b1[0] @ b2[1])
+    crap = float(b1[0] @ b1[0] + b2[1] @ b2[1])
+    if math.sqrt(crap) < 1e-12:
+        fir = math.pi - math.asin(math.sqrt(crap))
+        si = math.sqrt(crap)
+    else:
+        fir = math.acos(co)
+        si = math.sqrt(1 - co ** 2)
+    if abs(fir - math.pi) < 1e-12:
+        fir = math.pi
+    bf = np.zeros((3, 3))
+    d1, d2 = r1 * si, r2 * si
+    for i in range(3):
+        bf[0][i] = 0.0 if d1 < 1e-12 else (co * b1[0][i] - b2[1][i]) / d1
+        bf[2][i] = 0.0 if d2 < 1e-12 else (co * b2[1][i] - b1[0][i]) / d2
+        bf[1][i] = -1 * (bf[0][i] + bf[2][i])
+    return fir, bf
+
+
+def w_torsion(x0, x1, x2, x3):
+    """torsion2 b-vectors, calc_params.py:137-181."""
+    r1, bij = w_stretch(x0, x1)
+    r2, bjk = w_stretch(x1, x2)
+    r3, bkl = w_stretch(x2, x3)
+    f2, _ = w_bend(x0, x1, x2)
+    f3, _ = w_bend(x1, x2, x3)
+    s2, s3, c2, c3 = math.sin(f2), math.sin(f3), math.cos(f2), math.cos(f3)
+    bt = np.zeros((4, 3))
+    for ix in range(3):
+        iy = (ix + 1) % 3
+        iz = (iy + 1) % 3
+        bt[0][ix] = (bij[1][iy] * bjk[1][iz] - bij[1][iz] * bjk[1][iy]) / (r1 * s2 ** 2)
+        bt[3][ix] = (bkl[0][iy] * bjk[0][iz] - bkl[0][iz] * bjk[0][iy]) / (r3 * s3 ** 2)
+        bt[1][ix] = -1 * ((r2 - r1 * c2) * bt[0][ix] + r3 * c3 * bt[3][ix]) / r2
+        bt[2][ix] = -1 * (bt[0][ix] + bt[1][ix] + bt[3][ix])
+    return bt
+
+
+def fischer_hessian(coord, radii):
+    """FischerApproxHessian.main, ModelHessian/fischer.py:212-236 (radii: covalent, Bohr)."""
+    coord = np.asarray(coord, float)
+    N = len(coord)
+    H = np.zeros((3 * N, 3 * N))
+    bonds, angles, dihs = connectivity_tables(coord, radii, 1.1)
+    bm13 = np.zeros((N, N), bool)                          # second connectivity, factor 1.3 (:43-66)
+    for i in range(N):
+        for j in range(i + 1, N):
+            bm13[i, j] = bm13[j, i] = np.linalg.norm(coord[i] - coord[j]) <= (radii[i] + radii[j]) * 1.3
+
+    def add(atoms, k, b):
+        for a in range(len(atoms)):
+            for c in range(len(atoms)):
+                for p in range(3):
+                    for q in range(3):
+                        H[3 * atoms[a] + p, 3 * atoms[c] + q] += k * b[a][p] * b[c][q]
+
+    for i, j in bonds:
+        r = np.linalg.norm(coord[i] - coord[j])
+        k = 0.3601 * math.exp(-1.944 * (r - (radii[i] + radii[j])))
+        add([i, j], k, w_stretch(coord[i], coord[j])[1])
+    for i, j, k_ in angles:
+        r1 = np.linalg.norm(coord[i] - coord[j]); r2 = np.linalg.norm(coord[j] - coord[k_])
+        c1 = radii[i] + radii[j]; c2 = radii[j] + radii[k_]
+        val = c1 * c2
+        k = 0.0 if abs(val) < 1e-10 else 0.089 + 0.11 / val ** (-0.42) * math.exp(-0.44 * (r1 + r2 - c1 - c2))
+        add([i, j, k_], k, w_bend(coord[i], coord[j], coord[k_])[1])
+
+    def sin_sq(a, b, c):
+        v1 = coord[a] - coord[b]; v2 = coord[c] - coord[b]
+        cr = np.cross(v1, v2)
+        n1 = v1 @ v1; n2 = v2 @ v2
+        return 0.0 if n1 * n2 < 1e-12 else (cr @ cr) / (n1 * n2)
+
+    for i, j, k_, l in dihs:
+        if sin_sq(i, j, k_) < 1e-3 or sin_sq(j, k_, l) < 1e-3:
+            continue
+        r = np.linalg.norm(coord[j] - coord[k_]); rc = radii[j] + radii[k_]
+        bond_sum = int(bm13[j].sum() + bm13[k_].sum() - 2)
+        val = r * rc
+        k = 0.0 if abs(val) < 1e-10 else 0.0015 + 14.0 * max(bond_sum, 0) ** 0.57 / val ** 4.0 * math.exp(-2.85 * (r - rc))
+        add([i, j, k_, l], k, w_torsion(coord[i], coord[j], coord[k_], coord[l]))
+    for i in range(3 * N):
+        for j in range(i):
+            H[i, j] = H[j, i]
+    return project_hessian_trrot(H, coord.reshape(-1))
+
+
+# --------------------------------------------------------------------------
+# AFIR bias potential (Potential/AFIR_potential.py:18-55 + autograd, potential.py:130-135)
+# --------------------------------------------------------------------------
+def afir_energy_torch(geom, frag1, frag2, radii_f32, gamma):
+    """Energy as a torch expression (float64 geometry, FLOAT32 radii added in float32)."""
+    import torch
+    hartree2kjmol, bohr2ang = 2625.5, 0.52917721067
+    R0 = 3.8164 / bohr2ang
+    EPS = 1.0061 / hartree2kjmol
+    if gamma != 0.0:
+        gh = gamma / hartree2kjmol
+        alpha = gh / ((2 ** (-1 / 6) - (1 + math.sqrt(1 + abs(gh) / EPS)) ** (-1 / 6)) * R0)
+    else:
+        alpha = 0.0
+    i_idx = torch.tensor(frag1); j_idx = torch.tensor(frag2)
+    Ri = radii_f32[i_idx]; Rj = radii_f32[j_idx]
+    vec = torch.linalg.norm(geom[i_idx].unsqueeze(1) - geom[j_idx].unsqueeze(0), dim=2)
+    omega = ((Ri.unsqueeze(1) + Rj.unsqueeze(0)) / vec) ** 6.0
+    return alpha * ((omega * vec).sum() / omega.sum())
+
+
+def afir_egh(coord, frag1, frag2, radii, gamma):
+    """(E, grad (N,3), hess (3N,3N)); frag indices 0-based; radii float64 Bohr (rounded here)."""
+    import torch
+    geom = torch.tensor(np.asarray(coord, float), dtype=torch.float64, requires_grad=True)
+    rf = torch.tensor([float(r) for r in radii])          # float32, as in the reference
+    f = lambda x: afir_energy_torch(x, list(frag1), list(frag2), rf, float(gamma))
+    E = f(geom)
+    g = torch.func.jacrev(f)(geom)
+    H = torch.func.hessian(f)(geom).reshape(geom.numel(), geom.numel())
+    return float(E), g.detach().numpy(), H.detach().numpy()

@@ -201,3 +201,82 @@ def test_fast_reciprocal_accuracy():
     torch.cuda.synchronize()
     err = np.abs(out.cpu().numpy() * x - 1.0)
     assert err.max() < 4 * 2.220446049250313e-16, err.max()
+
+
+# ------------------------------------------------------------------------ producers
+def _producers(golden_dir):
+    z = np.load(os.path.join(golden_dir, "producers.npz"))
+    return z, [str(s) for s in z["names"]]
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_connectivity_bit_exact_vs_reference(golden_dir, idx):
+    from multioptpy_b200.Utils.bond_connectivity import BondConnectivity
+    z, names = _producers(golden_dir)
+    name = names[idx]
+    elems = [str(e) for e in z[f"{name}/elements"]]
+    tabs = BondConnectivity(device=DEV).connectivity_table(z[f"{name}/xyz"], elems)
+    c = z[f"{name}/counts"]
+    assert [len(t) for t in tabs] == list(c)
+    assert tabs[0] == z[f"{name}/bonds"][:c[0]].tolist()
+    assert tabs[1] == z[f"{name}/angles"][:c[1]].tolist()
+    assert tabs[2] == z[f"{name}/dihedrals"][:c[2]].tolist()
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_fischer_vs_reference(golden_dir, idx):
+    from multioptpy_b200.ModelHessian.approx_hessian import ApproxHessian
+    z, names = _producers(golden_dir)
+    name = names[idx]
+    elems = [str(e) for e in z[f"{name}/elements"]]
+    xyz = z[f"{name}/xyz"]
+    H = ApproxHessian(device=DEV).main(xyz, elems, np.zeros_like(xyz), "fischer")
+    assert rel(H, z[f"{name}/fischer"]) < RTOL
+    assert np.array_equal(H, H.T)
+
+
+def test_fischer_batched_jittered():
+    """A batch of distinct conformers in one launch vs the oracle."""
+    from multioptpy_b200.ModelHessian.fischer import FischerApproxHessian
+    from multioptpy_b200.Parameters.tables import covalent_radius
+    rng = np.random.default_rng(12)
+    N, B = 24, 16
+    elems = synthetic.elements(N)
+    radii = np.array([covalent_radius(e) for e in elems])
+    xyz = np.stack([synthetic.grid_geometry(N, rng, spacing=2.6, jitter=0.25) for _ in range(B)])
+    H = FischerApproxHessian(device=DEV).main(T(xyz), elems).cpu().numpy()
+    for b in range(0, B, 5):
+        assert rel(H[b], O.fischer_hessian(xyz[b], radii)) < RTOL
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_afir_vs_reference(golden_dir, idx):
+    from multioptpy_b200.Potential.AFIR_potential import AFIRPotential
+    z, names = _producers(golden_dir)
+    name = names[idx]
+    elems = [str(e) for e in z[f"{name}/elements"]]
+    xyz = z[f"{name}/xyz"]
+    for c in range(3):
+        f1 = [int(v) for v in z[f"{name}/afir_f1"][c] if v > 0]
+        f2 = [int(v) for v in z[f"{name}/afir_f2"][c] if v > 0]
+        pot = AFIRPotential(AFIR_Fragm_1=f1, AFIR_Fragm_2=f2, element_list=elems, device=DEV)
+        gam = torch.tensor([float(z[f"{name}/afir_gamma"][c])], dtype=torch.float64)
+        E, g, H = pot.calc_energy_grad_hess(xyz, gam)
+        Eref = z[f"{name}/afir_E"][c]
+        assert abs(float(E) - Eref) <= RTOL * abs(Eref)
+        assert abs(float(pot.calc_energy(torch.tensor(xyz), gam)) - Eref) <= RTOL * abs(Eref)
+        assert rel(g.cpu().numpy(), z[f"{name}/afir_g"][c]) < RTOL
+        assert rel(H.cpu().numpy(), z[f"{name}/afir_H"][c]) < RTOL
+
+
+def test_bias_potential_aggregator_aldol(golden_dir):
+    """BiasPotentialCalculation.main with `-ma 95 1 5 50 3 11` on aldol_rxn.xyz."""
+    from multioptpy_b200.Potential.potential import BiasPotentialCalculation
+    z, _ = _producers(golden_dir)
+    elems = [str(e) for e in z["aldol_rxn/elements"]]
+    xyz = z["aldol_rxn/xyz"]
+    fd = {"AFIR_gamma": [[95.0], [50.0]], "AFIR_Fragm_1": [[1], [3]], "AFIR_Fragm_2": [[5], [11]]}
+    bg, Be, Bg, Hb = BiasPotentialCalculation(device=DEV).main(0.0, np.zeros_like(xyz), xyz, elems, fd)
+    assert abs(Be - 3.794394592266868e-01) < 1e-10
+    assert abs(np.linalg.norm(Bg) - 3.827240360969133e-02) < 1e-11
+    assert abs(np.linalg.norm(Hb) - 7.463054721281174e-03) < 1e-12
