@@ -199,6 +199,35 @@ int mop_afir(int B, int natoms, const double* xyz, int n1, const int32_t* frag1,
              const int32_t* frag2, const float* radii_f32, const double* gamma, double* E,
              double* grad, double* H, void* stream);
 
+/* ---- (5) NEB: tangent projection, Ayala curvature update, step limits -----------------
+ * Images [first, first + nloc) of an nimg-image chain live on this GPU.  *_halo arrays have
+ * nloc + 2 entries: slot l + 1 = local image l, slots 0 and nloc + 1 = images first - 1 and
+ * first + nloc (received over NCCL when the chain is sharded; ignored at the chain ends).
+ * mop_bneb_force  replaces CaluculationBNEB.calc_force (MEP/pathopt_bneb_force.py:33-117):
+ *                 force [nloc][n] = -(g + projection), tau [nloc][n] = projection (get_tau).
+ * mop_neb_ayala   replaces calculate_gamma (pathopt_bneb_force.py:161-222) and the rank-1
+ *                 update H += gamma t t^T of RFOOptimizer (Optimizer/rfo_neb.py:43-73).
+ * mop_neb_limit_tr replaces _limit_step_size (rfo_neb.py:76-83) and TR_NEB.TR_calc
+ *                 (Optimizer/trust_radius_neb.py:17-98); delta [nloc][n] in place. */
+int mop_bneb_force(int nimg, int first, int nloc, int n, const double* x_halo, const double* E_halo,
+                   const double* g, double* force, double* tau, void* stream);
+int mop_neb_ayala(int nimg, int first, int nloc, int n, const double* x_halo, const double* E_halo,
+                  const double* g_halo, const double* tau, double* H, double* gamma_out, void* stream);
+int mop_neb_limit_tr(int nimg, int first, int nloc, int n, int fix_init_edge, int fix_end_edge,
+                     const double* x_halo, const double* g, double* delta, void* stream);
+
+/* ---- caller side: composite outer trust radius -----------------------------------
+ * Replaces TrustRadius.update_trust_radii (Optimizer/trust_radius.py:120-206) as called
+ * from CalculateMoveVector.update_trust_radius_conditionally (optimizer.py:534-553):
+ * r = (pre_Be - Be) / (pre_Bg.pre_move + 1/2 pre_move^T (H + Hbias) pre_move), adaptive
+ * factor from the ratio history, clip to [trust_min, trust_max].  trust [B] in/out;
+ * state [B][MOP_TR_STATE] doubles, zero-initialised by the caller. */
+#define MOP_TR_STATE 12
+int mop_outer_trust_radius(int B, int n, const double* H, const double* Hbias, const double* pre_Bg,
+                           const double* pre_move, const double* Be, const double* pre_Be,
+                           double* trust, double* state, double trust_min, double trust_max,
+                           void* stream);
+
 /* ---- caller side: CalculateMoveVector.calc_move_vector clamp -------------
  * Replaces optimizer.py:792-798,812: scale move to trust_outer[B] if longer,
  * x_new_ang = (x - move) * 0.52917721067. */

@@ -40,6 +40,10 @@ SIGNATURES = {
     "mop_fischer_workspace_bytes": (_sz, [_i, _i]),
     "mop_fischer_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "mop_afir": (_i, [_i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "mop_bneb_force": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "mop_neb_ayala": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "mop_neb_limit_tr": (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mop_outer_trust_radius": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _p]),
     "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "mop_bench_dfma": (_i, [_i, _i, _p, _p]),
     "mop_bench_fill": (_i, [_p, _sz, _d, _p]),

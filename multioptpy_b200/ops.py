@@ -311,3 +311,62 @@ def afir(xyz, frag1, frag2, radii_f32, gamma, want_grad: bool = True, want_hess:
                           _ptr(radii_f32), _ptr(gamma), _ptr(E), _ptr(g), _ptr(H), _stream(dev))
     _lib.check(rc, "mop_afir")
     return E, g, H
+
+
+TR_STATE = 12
+
+
+def outer_trust_radius(H, Hbias, pre_Bg, pre_move, Be, pre_Be, trust, state, trust_min=0.01, trust_max=0.5):
+    """TrustRadius.update_trust_radii for a batch (trust and state updated in place)."""
+    lib = _lib.load()
+    B, n = pre_move.shape
+    _chk(H, "H", (B, n, n)); _chk(pre_Bg, "pre_Bg", (B, n)); _chk(pre_move, "pre_move", (B, n))
+    _chk(Be, "Be", (B,)); _chk(pre_Be, "pre_Be", (B,)); _chk(trust, "trust", (B,)); _chk(state, "state", (B, TR_STATE))
+    if Hbias is not None:
+        _chk(Hbias, "Hbias", (B, n, n))
+    with torch.cuda.device(H.device):
+        rc = lib.mop_outer_trust_radius(B, n, _ptr(H), _ptr(Hbias), _ptr(pre_Bg), _ptr(pre_move), _ptr(Be),
+                                        _ptr(pre_Be), _ptr(trust), _ptr(state), float(trust_min),
+                                        float(trust_max), _stream(H.device))
+    _lib.check(rc, "mop_outer_trust_radius")
+    return trust
+
+
+# ---- (5) NEB -------------------------------------------------------------------------------
+def bneb_force(nimg, first, x_halo, E_halo, g):
+    """force, tau for the local images (x_halo (nloc+2, n), E_halo (nloc+2,), g (nloc, n))."""
+    lib = _lib.load()
+    nloc, n = g.shape
+    _chk(x_halo, "x_halo", (nloc + 2, n)); _chk(E_halo, "E_halo", (nloc + 2,)); _chk(g, "g", (nloc, n))
+    force = torch.empty_like(g); tau = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        rc = lib.mop_bneb_force(int(nimg), int(first), nloc, n, _ptr(x_halo), _ptr(E_halo), _ptr(g), _ptr(force),
+                                _ptr(tau), _stream(g.device))
+    _lib.check(rc, "mop_bneb_force")
+    return force, tau
+
+
+def neb_ayala(nimg, first, x_halo, E_halo, g_halo, tau, H):
+    """H (nloc, n, n) += gamma t t^T in place; returns gamma (nloc,)."""
+    lib = _lib.load()
+    nloc, n = tau.shape
+    _chk(x_halo, "x_halo", (nloc + 2, n)); _chk(E_halo, "E_halo", (nloc + 2,)); _chk(g_halo, "g_halo", (nloc + 2, n))
+    _chk(tau, "tau", (nloc, n)); _chk(H, "H", (nloc, n, n))
+    gamma = torch.zeros(nloc, dtype=torch.float64, device=tau.device)
+    with torch.cuda.device(tau.device):
+        rc = lib.mop_neb_ayala(int(nimg), int(first), nloc, n, _ptr(x_halo), _ptr(E_halo), _ptr(g_halo), _ptr(tau),
+                               _ptr(H), _ptr(gamma), _stream(tau.device))
+    _lib.check(rc, "mop_neb_ayala")
+    return gamma
+
+
+def neb_limit_tr(nimg, first, x_halo, g, delta, fix_init_edge=False, fix_end_edge=False):
+    """_limit_step_size + TR_calc on delta (nloc, n), in place."""
+    lib = _lib.load()
+    nloc, n = delta.shape
+    _chk(x_halo, "x_halo", (nloc + 2, n)); _chk(g, "g", (nloc, n)); _chk(delta, "delta", (nloc, n))
+    with torch.cuda.device(delta.device):
+        rc = lib.mop_neb_limit_tr(int(nimg), int(first), nloc, n, int(bool(fix_init_edge)), int(bool(fix_end_edge)),
+                                  _ptr(x_halo), _ptr(g), _ptr(delta), _stream(delta.device))
+    _lib.check(rc, "mop_neb_limit_tr")
+    return delta

@@ -319,7 +319,161 @@ def gen_producers():
     np.savez_compressed(os.path.join(GOLD, "producers.npz"), **blob)
 
 
-SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers}
+def gen_c1_trace():
+    """Config 1 (optmain test/aldol_rxn.xyz -ma 95 1 5 50 3 11 -opt rsirfo_bofill -modelhess fischer):
+    the reference CalculateMoveVector.calc_move_vector boundary replayed on recorded gradients.
+    GFN2-xTB is not installable offline, so the raw (E, g) come from a seeded analytic PES; the
+    bias, the model Hessian, the optimizer and the caller are the unmodified reference."""
+    import torch
+    opt_mod = ref_shim.ref("optimizer")
+    fi = ref_shim.ref("ModelHessian.fischer")
+    af = ref_shim.ref("Potential.AFIR_potential")
+    elems, xyz0 = read_xyz(os.path.join(ref_shim.REF_ROOT, "test/aldol_rxn.xyz"))
+    N = len(elems); n = 3 * N
+    rng = np.random.default_rng(20260101)
+    with quiet():
+        H0 = np.asarray(fi.FischerApproxHessian().main(xyz0.copy(), elems, np.zeros((N, 3))), float)
+    E = rng.standard_normal((n, n))
+    Ht = H0 + 0.02 * (E + E.T) / np.sqrt(n) + 0.05 * np.eye(n)
+    g0 = rng.normal(0.0, 5e-3, size=n)
+    pes = QuadraticPES(xyz0.reshape(-1).copy(), g0, Ht, np.zeros((n, n)), rng)
+    terms = [([1], [5], 95.0), ([3], [11], 50.0)]
+    pots = [af.AFIRPotential(AFIR_Fragm_1=f1, AFIR_Fragm_2=f2, element_list=elems) for f1, f2, _ in terms]
+
+    def bias(x):
+        Eb, gb, Hb = 0.0, np.zeros((N, 3)), np.zeros((n, n))
+        for pot, (_, _, gam) in zip(pots, terms):
+            geom = torch.tensor(x.reshape(N, 3), dtype=torch.float64, requires_grad=True)
+            par = torch.tensor([gam], dtype=torch.float64, requires_grad=True)
+            Eb += float(pot.calc_energy(geom, par))
+            gb = gb + torch.func.jacrev(pot.calc_energy, argnums=0)(geom, par).detach().numpy()
+            Hb = Hb + torch.func.hessian(pot.calc_energy, argnums=0)(geom, par).reshape(n, n).detach().numpy()
+        return Eb, gb, Hb
+
+    with quiet():
+        CMV = opt_mod.CalculateMoveVector(0.5, elems, saddle_order=0, FC_COUNT=-1, temperature=0.0,
+                                          model_hess_flag="fischer", max_trust_radius=None, min_trust_radius=None)
+        insts = CMV.initialization(["rsirfo_bofill"])
+    Model_hess = H0.copy()
+    geom = xyz0.copy()
+    pre = dict(B_g=np.zeros((N, 3)), geom=np.zeros((N, 3)), B_e=0.0, move=np.zeros((N, 3)), g=np.zeros((N, 3)))
+    rec = {k: [] for k in ("geom", "B_g", "g", "B_e", "Hb", "new_geom", "move", "trust", "H_after")}
+    for it in range(6):
+        e, g = pes.raw(geom.reshape(-1))
+        g = g.reshape(N, 3)
+        Eb, gb, Hb = bias(geom.reshape(-1))
+        B_e, B_g = e + Eb, g + gb
+        with quiet():
+            insts[0].set_hessian(Model_hess)          # every iteration, by reference (SURVEY H4)
+            insts[0].set_bias_hessian(Hb)
+            new_geom, move, insts = CMV.calc_move_vector(it, geom.copy(), B_g.copy(), pre["B_g"].copy(), pre["geom"].copy(),
+                                                         B_e, pre["B_e"], pre["move"].copy(), xyz0.copy(), g.copy(),
+                                                         pre["g"].copy(), insts, print_flag=False)
+        rec["geom"].append(geom.copy()); rec["B_g"].append(B_g.copy()); rec["g"].append(g.copy()); rec["B_e"].append(B_e)
+        rec["Hb"].append(Hb.copy()); rec["new_geom"].append(np.asarray(new_geom, float).copy())
+        rec["move"].append(np.asarray(move, float).copy()); rec["trust"].append(float(CMV.trust_radii))
+        rec["H_after"].append(np.asarray(insts[0].hessian, float).copy())
+        pre = dict(B_g=B_g, geom=geom.copy(), B_e=B_e, move=np.asarray(move, float).copy(), g=g)
+        geom = np.asarray(new_geom, float) / 0.52917721067
+    blob = {k: np.array(v) for k, v in rec.items()}
+    blob["elements"] = np.array(elems); blob["H0"] = H0; blob["xyz0"] = xyz0
+    np.savez_compressed(os.path.join(GOLD, "c1_calc_move_vector.npz"), **blob)
+    print("c1 trace: move norms", [float(np.linalg.norm(m)) for m in rec["move"]], "trust", rec["trust"])
+    print("first move row", rec["move"][0][0])
+
+
+def neb_chain(nimg, natoms, seed):
+    """Synthetic NEB chain (SURVEY §8d, config 3 shape): linear interpolation between two
+    jittered endpoints + noise; double-well energies so that up-hill, down-hill and extremum
+    tangent branches all occur; gradients consistent with a quadratic model + noise."""
+    rng = np.random.default_rng(seed)
+    a = synthetic.grid_geometry(natoms, rng).reshape(-1)
+    b = a + rng.normal(0.0, 0.6, size=a.size)
+    t = np.linspace(0.0, 1.0, nimg)
+    X = np.stack([(1 - s) * a + s * b for s in t]) + rng.normal(0.0, 0.05, size=(nimg, a.size))
+    E = 0.05 * np.sin(2.5 * np.pi * t) + 0.02 * t + rng.normal(0.0, 1e-4, size=nimg)
+    G = rng.normal(0.0, 2e-2, size=(nimg, a.size))
+    return X, E, G
+
+
+def gen_neb():
+    import tempfile, types
+    bn = ref_shim.ref("MEP.pathopt_bneb_force")
+    rn = ref_shim.ref("Optimizer.rfo_neb")
+    rs = ref_shim.ref("Optimizer.rsirfo")
+    trn = ref_shim.ref("Optimizer.trust_radius_neb")
+    nimg, natoms = 9, 10
+    n = 3 * natoms
+    elems = synthetic.elements(natoms)
+    tmp = tempfile.mkdtemp() + "/"
+
+    class Helper(rn.OptimizationAlgorithm):
+        def optimize(self, *a, **k):
+            pass
+    helper = Helper()
+    calc = bn.CaluculationBNEB()
+    tr = trn.TR_NEB(NEB_FOLDER_DIRECTORY=tmp, fix_init_edge=False, fix_end_edge=False, apply_convergence_criteria=False)
+    opts = []
+    for num in range(nimg):
+        with quiet():
+            if num == 0 or num == nimg - 1:
+                o = rs.RSIRFO(method="rsirfo_block_fsb", saddle_order=0, trust_radius=0.5)
+            else:
+                o = rs.RSIRFO(method="rsirfo_block_bofill", saddle_order=0, trust_radius=0.2)
+                o.switch_NEB_mode()
+        opts.append(o)
+    rngH = np.random.default_rng(77)
+    H = [synthetic.spd_hessian(n, rngH) for _ in range(nimg)]
+    rec = {k: [] for k in ("X", "E", "G", "force", "tau", "gamma", "H_after", "rfo_delta", "rfo_move")}
+    X, E, G = neb_chain(nimg, natoms, 31)
+    prevX = prevG = None
+    for it in range(3):
+        geoms = X.reshape(nimg, natoms, 3)
+        grads = G.reshape(nimg, natoms, 3)
+        with quiet():
+            force = calc.calc_force(geoms, E, grads, it, elems)
+        taus = np.array([calc.get_tau(i).reshape(-1) for i in range(nimg)])
+        gammas, deltas = [], []
+        for num in range(nimg):
+            h0 = H[num].copy()
+            with quiet():
+                hess = helper._apply_ayala_hessian_update(H[num], num, nimg, geoms, E, grads, calc)
+            gammas.append(0.0 if num in (0, nimg - 1) else float(np.sum((hess - h0) * np.outer(taus[num], taus[num])) / max(np.sum(np.outer(taus[num], taus[num]) ** 2), 1e-300)))
+            o = opts[num]
+            o.set_hessian(hess)
+            o.set_bias_hessian(np.zeros((n, n)))
+            col = lambda v: v.reshape(-1, 1).copy()
+            with quiet():
+                if it == 0:
+                    mv = o.run(col(X[num]), col(G[num]), None, None, 0.0, 0.0, [], [], col(G[num]), None)
+                else:
+                    mv = o.run(col(X[num]), col(G[num]), col(prevG[num]), col(prevX[num]), 0.0, 0.0, [], [], col(G[num]), col(prevG[num]))
+                mv = helper._limit_step_size(mv, num == 0 or num == nimg - 1)
+            deltas.append(np.asarray(mv, float).reshape(natoms, 3))
+            H[num] = np.asarray(o.get_hessian(), float).copy()
+            o.set_hessian(None); o.set_bias_hessian(None)
+        with quiet():
+            mvs = tr.TR_calc(geoms, grads, [d.copy() for d in deltas], E, E, None)
+        rec["X"].append(X.copy()); rec["E"].append(E.copy()); rec["G"].append(G.copy())
+        rec["force"].append(np.asarray(force, float).reshape(nimg, n)); rec["tau"].append(taus)
+        rec["gamma"].append(np.array(gammas)); rec["H_after"].append(np.stack(H))
+        rec["rfo_delta"].append(np.stack(deltas).reshape(nimg, n)); rec["rfo_move"].append(np.stack([np.asarray(m, float) for m in mvs]).reshape(nimg, n))
+        prevX, prevG = X.copy(), G.copy()
+        # next point of the chain: move against the RFO vectors, new seeded energies / gradients
+        Xn, En, Gn = neb_chain(nimg, natoms, 32 + it)
+        X = X - np.stack([np.asarray(m, float) for m in mvs]).reshape(nimg, n)
+        E = En; G = G + 0.3 * (Gn - G)
+    blob = {k: np.array(v) for k, v in rec.items()}
+    blob["H0"] = np.stack([synthetic.spd_hessian(n, np.random.default_rng(77)) for _ in range(1)])
+    rngH = np.random.default_rng(77)
+    blob["H_init"] = np.stack([synthetic.spd_hessian(n, rngH) for _ in range(nimg)])
+    blob["meta"] = np.array([nimg, natoms], np.int64)
+    np.savez_compressed(os.path.join(GOLD, "neb_rfo.npz"), **blob)
+    print("neb: gammas", np.round(rec["gamma"][0], 4), "move norms", np.round(np.linalg.norm(rec["rfo_move"][1], axis=1), 4))
+
+
+SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+        "c1": gen_c1_trace, "neb": gen_neb}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

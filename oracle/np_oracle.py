@@ -950,3 +950,165 @@ def afir_egh(coord, frag1, frag2, radii, gamma):
     g = torch.func.jacrev(f)(geom)
     H = torch.func.hessian(f)(geom).reshape(geom.numel(), geom.numel())
     return float(E), g.detach().numpy(), H.detach().numpy()
+
+
+class CalcMoveVectorOracle:
+    """CalculateMoveVector.calc_move_vector with one RSIRFO instance (optimizer.py:259-309,
+    534-553, 740-818): outer trust radius (only when a model Hessian / FC_COUNT is configured),
+    RSIRFO.run, norm clamp, geometry update in Angstrom."""
+
+    def __init__(self, method, saddle_order=0, model_hess_flag=None, FC_COUNT=-1):
+        self.trust = 0.1 if saddle_order > 0 else 0.5
+        self.max_trust = self.trust
+        self.opt = RSIRFOOracle(method=method, saddle_order=saddle_order, trust_radius_max=self.max_trust,
+                                trust_radius_min=0.01)
+        self.tr = TrustRadiusOracle(0.01, 0.5)
+        self.update_outer = not (FC_COUNT == -1 and model_hess_flag is None)
+
+    def step(self, x, Bg, g, Be, pre=None):
+        """pre: dict(x, g, Bg, Be, move) of the previous call or None.  Returns (x_new_ang, move)."""
+        if self.update_outer:
+            Hm = self.opt.hessian + (self.opt.bias_hessian if self.opt.bias_hessian is not None else 0.0)
+            if pre is None:
+                n = x.size
+                self.trust = self.tr.update(Be, 0.0, np.zeros(n), np.zeros(n), Hm, self.trust)
+            else:
+                self.trust = self.tr.update(Be, pre["Be"], pre["Bg"], pre["move"], Hm, self.trust)
+        if pre is None:
+            move = self.opt.run(x, Bg, g, None, None, Be)
+        else:
+            move = self.opt.run(x, Bg, g, pre["x"], pre["g"], Be)
+        return clamp_and_move(x, move, self.trust)
+
+
+# --------------------------------------------------------------------------
+# NEB: BNEB tangent projection, Ayala curvature, step limits (config 3)
+# --------------------------------------------------------------------------
+def _bneb_unit_projection(xa, xb, g, w):
+    """-w * sum_atoms u_hat (u_hat . g) through the SVD pseudo-inverse of B^T B
+    (MEP/pathopt_bneb_force.py:104-117, Coordinate/redundant_coordinate.py:377-439)."""
+    out = np.zeros_like(g)
+    A = xa.reshape(-1, 3); Bc = xb.reshape(-1, 3); G = g.reshape(-1, 3)
+    for i in range(A.shape[0]):
+        u = (Bc[i] - A[i]) / (np.linalg.norm(A[i] - Bc[i]) + 1e-15)
+        s = u @ u
+        if s > 1e-6:
+            out[3 * i:3 * i + 3] = -w * ((u @ G[i]) / s) * u
+    return out
+
+
+def bneb_force(X, E, G):
+    """CaluculationBNEB.calc_force without the CI branches -> (force, tau), (nimg, n) each."""
+    nimg = X.shape[0]
+    F = np.zeros_like(G); T = np.zeros_like(G)
+    for i in range(nimg):
+        if i == 0 or i == nimg - 1:
+            F[i] = -G[i]
+            continue
+        e = E[i - 1:i + 2]
+        if e[0] < e[1] < e[2]:
+            proj = _bneb_unit_projection(X[i], X[i + 1], G[i], 1.0)
+        elif e[0] > e[1] > e[2]:
+            proj = _bneb_unit_projection(X[i - 1], X[i], G[i], 1.0)
+        else:
+            mx = max(abs(e[2] - e[1]), abs(e[1] - e[0])); mn = min(abs(e[2] - e[1]), abs(e[1] - e[0]))
+            a = mx / (mx + mn + 1e-8); b = mn / (mx + mn + 1e-8)
+            wp, wm = (a, b) if e[0] < e[2] else (b, a)
+            proj = _bneb_unit_projection(X[i], X[i + 1], G[i], wp) + _bneb_unit_projection(X[i - 1], X[i], G[i], wm)
+        F[i] = -(G[i] + proj)
+        T[i] = proj
+    return F, T
+
+
+def ayala_gamma(qp, qc, qn, Ep, Ec, En, gp, gc, gn, tangent):
+    """calculate_gamma, MEP/pathopt_bneb_force.py:161-222."""
+    dp = np.linalg.norm(qc - qp); dn = np.linalg.norm(qn - qc)
+    if dp < 1e-6 or dn < 1e-6:
+        return 0.0
+    s = [-dp, 0.0, dn]
+    A = np.array([[1, v, v ** 2, v ** 3, v ** 4, v ** 5] for v in s] +
+                 [[0, 1, 2 * v, 3 * v ** 2, 4 * v ** 3, 5 * v ** 4] for v in s], float)
+    b = np.array([Ep, Ec, En, gp @ ((qc - qp) / dp), gc @ tangent, gn @ ((qn - qc) / dn)])
+    try:
+        return 2.0 * np.linalg.solve(A, b)[2]
+    except np.linalg.LinAlgError:
+        return 0.0
+
+
+def neb_limit_tr(X, G, delta):
+    """_limit_step_size (Optimizer/rfo_neb.py:76-83) + TR_NEB.TR_calc
+    (Optimizer/trust_radius_neb.py:17-98), free end images."""
+    nimg = X.shape[0]
+    out = np.zeros_like(delta)
+    for i in range(nimg):
+        d = delta[i].copy()
+        end = i == 0 or i == nimg - 1
+        nrm = np.linalg.norm(d)
+        if nrm > 1e-8:
+            d = d / nrm * min(0.2 if end else 0.1, nrm)
+        nrm = np.linalg.norm(d)
+        if end:
+            out[i] = 0.0 if nrm < 1e-15 else min(0.5, nrm) * d / nrm
+            continue
+        t1 = np.linalg.norm(X[i] - X[i - 1]) / 2.0; t2 = np.linalg.norm(X[i] - X[i + 1]) / 2.0
+        v1 = (X[i - 1] - X[i]) / (np.linalg.norm(X[i - 1] - X[i]) + 1e-15)
+        v2 = (X[i + 1] - X[i]) / (np.linalg.norm(X[i + 1] - X[i]) + 1e-15)
+        with np.errstate(all="ignore"):
+            nd = d / nrm
+            c1 = np.sum(v1 * nd); c2 = np.sum(v2 * nd)
+            fc = np.sum(G[i] * d) / (np.linalg.norm(G[i]) * nrm)
+        if fc >= 0:
+            if (c1 > 0 and c2 < 0) or (c1 < 0 and c2 > 0):
+                if nrm > t1 and c1 > 0:
+                    d = d * t1 / nrm
+                elif nrm > t2 and c2 > 0:
+                    d = d * t2 / nrm
+            elif c1 < 0 and c2 < 0:
+                pass
+            else:
+                if nrm > t1:
+                    d = d * t1 / nrm
+                elif nrm > t2:
+                    d = d * t2 / nrm
+            out[i] = d
+        else:
+            out[i] = 0.0
+    return out
+
+
+class NEBRFOOracle:
+    """RFOOptimizer.optimize steps 1-3 (Optimizer/rfo_neb.py:104-182): tangents, Ayala update,
+    per-image RSIRFO.run with B_e = pre_B_e = 0, step limits, TR_calc.  FIRE blend excluded."""
+
+    def __init__(self, H_init):
+        nimg = H_init.shape[0]
+        self.H = [h.copy() for h in H_init]
+        self.opts = []
+        for i in range(nimg):
+            if i == 0 or i == nimg - 1:
+                o = RSIRFOOracle(method="rsirfo_block_fsb", saddle_order=0)
+                o.trust_radius = 0.5
+            else:
+                o = RSIRFOOracle(method="rsirfo_block_bofill", saddle_order=0)
+                o.trust_radius = 0.2
+                o.NEB_mode = True
+            self.opts.append(o)
+        self.prev = None
+
+    def step(self, X, E, G):
+        nimg = X.shape[0]
+        F, T = bneb_force(X, E, G)
+        gam = np.zeros(nimg); delta = np.zeros_like(X)
+        for i in range(nimg):
+            if 0 < i < nimg - 1:
+                gam[i] = ayala_gamma(X[i - 1], X[i], X[i + 1], E[i - 1], E[i], E[i + 1], G[i - 1], G[i], G[i + 1], T[i])
+                self.H[i] = self.H[i] + gam[i] * np.outer(T[i], T[i])
+            o = self.opts[i]
+            o.set_hessian(self.H[i]); o.set_bias_hessian(np.zeros_like(self.H[i]))
+            if self.prev is None:
+                delta[i] = o.run(X[i], G[i], G[i], None, None, 0.0)
+            else:
+                delta[i] = o.run(X[i], G[i], G[i], self.prev[0][i], self.prev[1][i], 0.0)
+            self.H[i] = o.hessian
+        self.prev = (X.copy(), G.copy())
+        return F, T, gam, delta, neb_limit_tr(X, G, delta)

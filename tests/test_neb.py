@@ -1,0 +1,103 @@
+"""NEB (config 3 shape): tangent projection, Ayala curvature update, per-image RFO step and
+step limits vs the golden trace recorded from the reference; halo exchange over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+
+RTOL = 1e-10
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
+
+
+def test_oracle_replays_reference_neb_trace(golden_dir):
+    z = np.load(os.path.join(golden_dir, "neb_rfo.npz"))
+    neb = O.NEBRFOOracle(z["H_init"])
+    for it in range(z["X"].shape[0]):
+        F, T, gam, delta, mv = neb.step(z["X"][it], z["E"][it], z["G"][it])
+        assert rel(F, z["force"][it]) < RTOL, it
+        assert rel(T, z["tau"][it]) < RTOL, it
+        assert np.abs(gam - z["gamma"][it]).max() <= 1e-8 * max(1.0, np.abs(z["gamma"][it]).max()), it
+        assert rel(np.stack(neb.H), z["H_after"][it]) < 1e-9, it
+        assert rel(mv, z["rfo_move"][it]) < 1e-9, it
+
+
+@pytest.mark.gpu
+def test_gpu_neb_rfo_vs_reference_trace(golden_dir):
+    from multioptpy_b200.Optimizer.rfo_neb import RFOOptimizer
+    z = np.load(os.path.join(golden_dir, "neb_rfo.npz"))
+    nimg, natoms = [int(v) for v in z["meta"]]
+    dev = "cuda:0"
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    opt = RFOOptimizer(nimg, natoms, device=dev)
+    opt.set_hessians(T(z["H_init"]))
+    for it in range(z["X"].shape[0]):
+        mv = opt.rfo_move_vectors(T(z["X"][it]), T(z["E"][it]), T(z["G"][it])).cpu().numpy()
+        assert rel(opt.last["force"].cpu().numpy(), z["force"][it]) < RTOL, it
+        assert rel(opt.last["tau"].cpu().numpy(), z["tau"][it]) < RTOL, it
+        g = opt.last["gamma"].cpu().numpy()
+        assert np.abs(g - z["gamma"][it]).max() <= 1e-8 * max(1.0, np.abs(z["gamma"][it]).max()), it
+        assert rel(opt.hessian.cpu().numpy(), z["H_after"][it]) < 1e-9, it
+        assert rel(mv, z["rfo_move"][it]) < 1e-9, it
+
+
+@pytest.mark.gpu
+def test_gpu_bneb_dropin_class(golden_dir):
+    from multioptpy_b200.MEP.pathopt_bneb_force import CaluculationBNEB
+    z = np.load(os.path.join(golden_dir, "neb_rfo.npz"))
+    nimg, natoms = [int(v) for v in z["meta"]]
+    calc = CaluculationBNEB(device="cuda:0")
+    F = calc.calc_force(z["X"][0].reshape(nimg, natoms, 3), z["E"][0], z["G"][0].reshape(nimg, natoms, 3), 0, ["C"] * natoms)
+    assert F.shape == (nimg, natoms, 3)
+    assert rel(F.reshape(nimg, -1), z["force"][0]) < RTOL
+    assert rel(calc.get_tau(3).ravel(), z["tau"][0][3]) < RTOL
+
+
+# ---------------------------------------------------------------- halo over gloo (world_size 2, 3)
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _halo_worker(rank, world, port, nimg, n, q):
+    import torch.distributed as dist
+    from multioptpy_b200.neb_halo import exchange_halo, image_partition
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    X = torch.from_numpy(rng.standard_normal((nimg, n))); E = torch.from_numpy(rng.standard_normal(nimg))
+    G = torch.from_numpy(rng.standard_normal((nimg, n)))
+    first, nloc = image_partition(nimg, world)[rank]
+    xh, Eh, gh = exchange_halo(X[first:first + nloc].contiguous(), E[first:first + nloc].contiguous(),
+                               G[first:first + nloc].contiguous())
+    ok = True
+    for l in range(nloc + 2):
+        gi = first + l - 1
+        if 0 <= gi < nimg:
+            ok &= bool(torch.equal(xh[l], X[gi]) and torch.equal(gh[l], G[gi]) and Eh[l] == E[gi])
+        else:
+            ok &= bool((xh[l] == 0).all())
+    q.put((rank, ok, first, nloc))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, 11, 12, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res)
+    assert sorted(f for _, _, f, _ in res)[0] == 0 and sum(nl for _, _, _, nl in res) == 11
