@@ -189,6 +189,21 @@ int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radi
                         double* H_out, int32_t* counts_out, int32_t* status, void* work,
                         size_t work_bytes, void* stream);
 
+/* ---- (3b') Lindh model Hessian ---------------------------------------------------
+ * Replaces LindhApproxHessian.main (ModelHessian/lindh.py:145-165) up to its K term:
+ * H_out = project(B^T diag(k) B) with the all-pairs distance B matrix
+ * (Coordinate/redundant_coordinate.py:15-43) and the diagonal force constants of
+ * guess_lindh_hessian (lindh.py:79-143); kdiag_out (optional) returns them,
+ * [B][N(N-1)/2] in itertools.combinations order.  The reference's K term multiplies
+ * second derivatives by an internal gradient obtained from a singular solve and is
+ * ill-posed in the reference itself; it is not added.
+ * atom_params [B or 1][natoms][6] = {covalent radius (Bohr), period index 0/1/2
+ * (H-He / Li-Ne / other), atomic mass, UFF VDW distance, UFF well depth, UFF charge}. */
+size_t mop_lindh_workspace_bytes(int B, int natoms);
+int mop_lindh_hessian(int B, int natoms, const double* xyz, const double* atom_params, int param_stride,
+                      double* H_out, double* kdiag_out, int32_t* counts_out, int32_t* status, void* work,
+                      size_t work_bytes, void* stream);
+
 /* ---- (3c) AFIR bias potential ---------------------------------------------------
  * Replaces AFIRPotential.calc_energy (Potential/AFIR_potential.py:18-55) and the
  * torch.func.jacrev / hessian calls of BiasPotentialCalculation.main

@@ -1,0 +1,53 @@
+"""Drop-in for ``multioptpy.ModelHessian.lindh.LindhApproxHessian`` (ModelHessian/lindh.py:11-165).
+
+Implemented on the device: the connectivity tables, the diagonal redundant-internal force
+constants (bond / angle / dihedral decay terms, reduced-mass scaling of bonds, Lennard-Jones and
+electrostatic terms of non-bonded pairs) and ``B^T diag(k) B`` with the all-pairs distance
+B matrix, then the TR/ROT projection.  NOT added: the reference's ``K`` term, which multiplies
+second derivatives by an internal-coordinate gradient obtained from ``np.linalg.solve`` on the
+singular ``B B^T`` and indexes it by a bond/angle/dihedral counter although its rows are atom
+pairs — a 1e-13 shift of the coordinates changes it by O(1), so it has no
+reproducible value.  ``main`` therefore equals the reference for a zero gradient only."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..Parameters.tables import (ATOMIC_MASS, UFF_EFFECTIVE_CHARGE, UFF_VDW_DISTANCE, UFF_VDW_WELL_DEPTH,
+                                 covalent_radius)
+
+_FIRST = {"H", "He"}
+_SECOND = {"Li", "Be", "B", "C", "N", "O", "F", "Ne"}
+
+
+def lindh_atom_params(element_list):
+    """(N, 6): covalent radius, period index, mass, UFF distance, UFF well depth, UFF charge."""
+    rows = []
+    for e in element_list:
+        per = 0 if e in _FIRST else (1 if e in _SECOND else 2)
+        rows.append([covalent_radius(e), float(per), ATOMIC_MASS[e], UFF_VDW_DISTANCE[e], UFF_VDW_WELL_DEPTH[e],
+                     UFF_EFFECTIVE_CHARGE[e]])
+    return np.array(rows, dtype=np.float64)
+
+
+class LindhApproxHessian:
+    def __init__(self, device="cuda"):
+        self.force_const_list = [0.45, 0.15, 0.005]
+        self.device = torch.device(device)
+
+    def guess_lindh_diagonal(self, coord, element_list):
+        """Diagonal of guess_lindh_hessian (lindh.py:79-143): force constant per atom pair."""
+        xyz = torch.as_tensor(np.ascontiguousarray(np.asarray(coord, dtype=np.float64)).reshape(1, -1, 3)).to(self.device)
+        _, kd, _, _ = ops.lindh_hessian(xyz, lindh_atom_params(element_list), want_kdiag=True)
+        return kd[0].cpu().numpy()
+
+    def main(self, coord, element_list, cart_gradient=None):
+        prm = lindh_atom_params(element_list)
+        if isinstance(coord, torch.Tensor):
+            return ops.lindh_hessian(coord, prm)[0]
+        xyz = torch.as_tensor(np.ascontiguousarray(np.asarray(coord, dtype=np.float64)).reshape(1, -1, 3)).to(self.device)
+        H, _, _, status = ops.lindh_hessian(xyz, prm)
+        if int(status[0].item()) != 0:
+            raise ops.MopError("Lindh model Hessian: connectivity table capacity exceeded")
+        return H[0].cpu().numpy()

@@ -229,6 +229,143 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Lindh model Hessian (ModelHessian/lindh.py:79-165): diagonal force constants k_p over ALL
+// atom pairs p = (i < j) (itertools.combinations order), then  H = B^T diag(k) B  with the
+// all-pairs distance B matrix (Coordinate/redundant_coordinate.py:15-43), i.e. block (i,i)
+// += k e e^T, block (i,j) = -k e e^T with e = (x_i - x_j)/r.  The reference adds a K term
+// built from an internal-coordinate gradient obtained by solving the SINGULAR system
+// (B B^T) q = B g and indexed inconsistently; it is numerically ill-posed in the
+// reference itself, so it is not part of this kernel (kdiag_out exposes k for the
+// decomposed parity check).
+// atom parameters prm[a][6] = {cov radius, period index 0/1/2, mass, UFF distance, UFF well
+// depth, UFF effective charge}.
+__global__ void __launch_bounds__(MH_THREADS, 1)
+k_lindh(int N, const double* __restrict__ xyz_all, const double* __restrict__ prm_all, int prm_stride,
+        int capB, int capA, int capD, int* __restrict__ bonds_all, int* __restrict__ angles_all,
+        int* __restrict__ dihs_all, int* __restrict__ counts_all, double* __restrict__ fc_all,
+        double* __restrict__ kdiag_all, double* __restrict__ H_all, int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int M = N * (N - 1) / 2;
+  double* xyz = sm;               // 3N
+  double* prm = xyz + 3 * N;      // 6N
+  double* rad = prm + 6 * N;      // N
+  double* kd = rad + N;           // M
+  int* cnt = (int*)(kd + M);      // 4
+  int* wtot = cnt + 4;            // 36
+  unsigned char* bm = (unsigned char*)(wtot + 36);  // N*N
+  for (int i = tid; i < 3 * N; i += MH_THREADS) xyz[i] = xyz_all[(size_t)b * 3 * N + i];
+  for (int i = tid; i < 6 * N; i += MH_THREADS) prm[i] = prm_all[(size_t)b * prm_stride * 6 + i];
+  __syncthreads();
+  for (int i = tid; i < N; i += MH_THREADS) rad[i] = prm[6 * i];
+  for (int i = tid; i < M; i += MH_THREADS) kd[i] = 0.0;
+  __syncthreads();
+  bond_matrix(N, xyz, rad, 1.1, bm);
+  ConnTables T;
+  T.bonds = bonds_all + (size_t)b * capB * 2;
+  T.angles = angles_all + (size_t)b * capA * 3;
+  T.dihs = dihs_all + (size_t)b * capD * 4;
+  T.capB = capB; T.capA = capA; T.capD = capD;
+  enumerate_tables(N, bm, T, cnt, wtot);
+  if (tid == 0) {
+    counts_all[3 * b] = T.nb; counts_all[3 * b + 1] = T.na; counts_all[3 * b + 2] = T.nd;
+    if (status) status[b] = T.overflow ? 1 : 0;
+  }
+  const double alpha_tab[3][3] = {{1.0000, 0.3949, 0.3949}, {0.3949, 0.2800, 0.2800}, {0.3949, 0.2800, 0.2800}};
+  const int nrec = T.nb + T.na + T.nd;
+  double* fc = fc_all + (size_t)b * (capB + capA + capD);
+  // force constant of every internal coordinate (lindh.py:89-98)
+  for (int t = tid; t < nrec; t += MH_THREADS) {
+    int at[4], len;
+    double f;
+    if (t < T.nb) { len = 2; f = 0.45; at[0] = T.bonds[2 * t]; at[1] = T.bonds[2 * t + 1]; }
+    else if (t < T.nb + T.na) { len = 3; f = 0.15; const int* a = T.angles + 3 * (t - T.nb); at[0] = a[0]; at[1] = a[1]; at[2] = a[2]; }
+    else { len = 4; f = 0.005; const int* a = T.dihs + 4 * (t - T.nb - T.na); at[0] = a[0]; at[1] = a[1]; at[2] = a[2]; at[3] = a[3]; }
+    for (int q = 0; q + 1 < len; ++q) {
+      const int i = at[q], j = at[q + 1];
+      const double cR = __dadd_rn(rad[i], rad[j]);
+      const double al = alpha_tab[(int)prm[6 * i + 1]][(int)prm[6 * j + 1]];
+      const double R = np_dist(xyz + 3 * i, xyz + 3 * j);
+      f *= exp(al * (cR * cR - R * R));
+    }
+    fc[t] = f;
+  }
+  __syncthreads();
+  // accumulate into the pair diagonal in table order (one thread: deterministic, as the reference)
+  if (tid == 0) {
+    auto pidx = [N](int i, int j) { if (i > j) { const int t = i; i = j; j = t; } return i * N - i * (i + 1) / 2 + (j - i - 1); };
+    for (int t = 0; t < nrec; ++t) {
+      const double f = fc[t];
+      if (t < T.nb) {
+        const int i = T.bonds[2 * t], j = T.bonds[2 * t + 1];
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        const double m1 = prm[6 * lo + 2], m2 = prm[6 * hi + 2];
+        kd[pidx(i, j)] += f / ((m1 * m2) / (m1 + m2));
+      } else if (t < T.nb + T.na) {
+        const int* a = T.angles + 3 * (t - T.nb);
+        kd[pidx(a[0], a[1])] += f;
+        kd[pidx(a[1], a[2])] += f;
+      } else {
+        const int* a = T.dihs + 4 * (t - T.nb - T.na);
+        kd[pidx(a[0], a[1])] += f;
+        kd[pidx(a[1], a[2])] += f;
+        kd[pidx(a[2], a[3])] += f;
+      }
+    }
+  }
+  __syncthreads();
+  // non-bonded pairs: Lennard-Jones + electrostatic force constants (lindh.py:19-41,133-137)
+  for (int e = tid; e < N * N; e += MH_THREADS) {
+    const int i = e / N, j = e - i * N;
+    if (i >= j || bm[e] == 1) continue;
+    const double d = np_dist(xyz + 3 * i, xyz + 3 * j);
+    const double eps = sqrt(prm[6 * i + 4] * prm[6 * j + 4]);
+    const double sig = sqrt(prm[6 * i + 3] * prm[6 * j + 3]);
+    const double lj = -12.0 * eps * (-7.0 * (pow(sig, 6.0) / pow(d, 8.0)) + 13.0 * (pow(sig, 12.0) / pow(d, 14.0)));
+    const double q = prm[6 * i + 5] * prm[6 * j + 5];
+    const double es = 664.12 * (q / pow(d, 3.0)) * (0.52917721067 * 0.52917721067 / 627.509);
+    const int p = i * N - i * (i + 1) / 2 + (j - i - 1);
+    kd[p] = (kd[p] + lj) + es;
+  }
+  __syncthreads();
+  if (kdiag_all)
+    for (int p = tid; p < M; p += MH_THREADS) kdiag_all[(size_t)b * M + p] = kd[p];
+  // H = B^T diag(k) B, one thread per atom-pair block (a <= c)
+  double* H = H_all + (size_t)b * 9 * N * N;
+  const int n = 3 * N;
+  for (int e = tid; e < N * N; e += MH_THREADS) {
+    const int a = e / N, c = e - a * N;
+    if (a > c) continue;
+    double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (a != c) {
+      const double dx = xyz[3 * a] - xyz[3 * c], dy = xyz[3 * a + 1] - xyz[3 * c + 1], dz = xyz[3 * a + 2] - xyz[3 * c + 2];
+      const double r = np_dist(xyz + 3 * a, xyz + 3 * c);
+      const double ev[3] = {dx / r, dy / r, dz / r};
+      const double k = kd[a * N - a * (a + 1) / 2 + (c - a - 1)];
+      for (int p = 0; p < 3; ++p)
+        for (int m = 0; m < 3; ++m) blk[3 * p + m] = -k * ev[p] * ev[m];
+    } else {
+      for (int o = 0; o < N; ++o) {
+        if (o == a) continue;
+        const int lo = a < o ? a : o, hi = a < o ? o : a;
+        const double dx = xyz[3 * lo] - xyz[3 * hi], dy = xyz[3 * lo + 1] - xyz[3 * hi + 1], dz = xyz[3 * lo + 2] - xyz[3 * hi + 2];
+        const double r = np_dist(xyz + 3 * lo, xyz + 3 * hi);
+        const double ev[3] = {dx / r, dy / r, dz / r};
+        const double k = kd[lo * N - lo * (lo + 1) / 2 + (hi - lo - 1)];
+        for (int p = 0; p < 3; ++p)
+          for (int m = 0; m < 3; ++m) blk[3 * p + m] += k * ev[p] * ev[m];
+      }
+    }
+    for (int p = 0; p < 3; ++p)
+      for (int m = 0; m < 3; ++m) {
+        H[(size_t)(3 * a + p) * n + 3 * c + m] = blk[3 * p + m];
+        H[(size_t)(3 * c + m) * n + 3 * a + p] = blk[3 * p + m];
+      }
+  }
+}
+
 }  // namespace mop
 
 // forward declaration (project.cu)
@@ -313,6 +450,65 @@ extern "C" int mop_fischer_hessian(int B, int natoms, const double* xyz, const d
   mop::k_model_hessian<<<B, mop::MH_THREADS, smem, stream>>>(1, natoms, xyz, radii, radii_stride, 1.1, cb, ca,
                                                            cd, bonds, angles, dihs, counts, rec, Hraw,
                                                            status);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  if (counts_out)
+    MOP_CHECK_CUDA(cudaMemcpyAsync(counts_out, counts, sizeof(int32_t) * 3 * (size_t)B,
+                                   cudaMemcpyDeviceToDevice, stream));
+  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, stream);
+}
+
+
+static size_t lindh_smem(int N) {
+  const size_t M = (size_t)N * (N - 1) / 2;
+  return sizeof(double) * (10 * (size_t)N + M) + sizeof(int) * 40 + (size_t)N * N + 16;
+}
+
+extern "C" size_t mop_lindh_workspace_bytes(int B, int natoms) {
+  if (B <= 0 || natoms <= 0) return 0;
+  int cb, ca, cd;
+  fischer_caps(natoms, &cb, &ca, &cd);
+  size_t bytes = (size_t)B * (2 * cb + 3 * ca + 4 * cd + 4) * sizeof(int32_t);
+  bytes = (bytes + 255) & ~(size_t)255;
+  bytes += (size_t)B * (cb + ca + cd) * sizeof(double);
+  bytes = (bytes + 255) & ~(size_t)255;
+  bytes += (size_t)B * 9 * natoms * natoms * sizeof(double);
+  return bytes;
+}
+
+// LindhApproxHessian.main without the ill-posed K term (ModelHessian/lindh.py:145-165):
+// H_out = project(B^T diag(k) B).  atom_params [B or 1][natoms][6]; kdiag_out (optional)
+// [B][natoms (natoms - 1) / 2] = the diagonal RIC force constants of guess_lindh_hessian.
+extern "C" int mop_lindh_hessian(int B, int natoms, const double* xyz, const double* atom_params,
+                                 int param_stride, double* H_out, double* kdiag_out, int32_t* counts_out,
+                                 int32_t* status, void* work, size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && natoms > 1, "mop_lindh_hessian: B >= 0 and natoms > 1 required");
+  MOP_REQUIRE(xyz && atom_params && H_out && work, "mop_lindh_hessian: xyz, atom_params, H_out, work required");
+  MOP_REQUIRE(param_stride == 0 || param_stride == natoms, "mop_lindh_hessian: param_stride must be 0 or natoms");
+  if (B == 0) return MOP_OK;
+  if (work_bytes < mop_lindh_workspace_bytes(B, natoms)) {
+    mop_set_error("mop_lindh_hessian: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  const size_t smem = lindh_smem(natoms);
+  if (smem > 200 * 1024) {
+    mop_set_error("mop_lindh_hessian: natoms = %d too large for the shared-memory pair table", natoms);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int cb, ca, cd;
+  fischer_caps(natoms, &cb, &ca, &cd);
+  char* w = (char*)work;
+  int32_t* bonds = (int32_t*)w;
+  int32_t* angles = bonds + (size_t)B * 2 * cb;
+  int32_t* dihs = angles + (size_t)B * 3 * ca;
+  int32_t* counts = dihs + (size_t)B * 4 * cd;
+  size_t off = ((size_t)B * (2 * cb + 3 * ca + 4 * cd + 4) * sizeof(int32_t) + 255) & ~(size_t)255;
+  double* fc = (double*)(w + off);
+  off += ((size_t)B * (cb + ca + cd) * sizeof(double) + 255) & ~(size_t)255;
+  double* Hraw = (double*)(w + off);
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lindh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_lindh<<<B, mop::MH_THREADS, smem, stream>>>(natoms, xyz, atom_params, param_stride, cb, ca, cd, bonds,
+                                                   angles, dihs, counts, fc, kdiag_out, Hraw, status);
   MOP_CHECK_CUDA(cudaGetLastError());
   if (counts_out)
     MOP_CHECK_CUDA(cudaMemcpyAsync(counts_out, counts, sizeof(int32_t) * 3 * (size_t)B,

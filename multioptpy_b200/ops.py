@@ -370,3 +370,26 @@ def neb_limit_tr(nimg, first, x_halo, g, delta, fix_init_edge=False, fix_end_edg
                                   _ptr(x_halo), _ptr(g), _ptr(delta), _stream(delta.device))
     _lib.check(rc, "mop_neb_limit_tr")
     return delta
+
+
+def lindh_hessian(xyz, atom_params, want_kdiag: bool = False):
+    """Lindh model Hessian without the ill-posed K term: (B, 3N, 3N) projected; atom_params (N, 6) or
+    (B, N, 6).  Returns (H, kdiag or None, counts, status)."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    p = atom_params if isinstance(atom_params, torch.Tensor) else torch.as_tensor(atom_params, dtype=torch.float64)
+    p = p.to(xyz.device, torch.float64).contiguous()
+    stride = 0 if p.dim() == 2 else N
+    _chk(p, "atom_params", (N, 6) if p.dim() == 2 else (B, N, 6))
+    H = torch.empty(B, 3 * N, 3 * N, dtype=torch.float64, device=xyz.device)
+    kd = torch.empty(B, N * (N - 1) // 2, dtype=torch.float64, device=xyz.device) if want_kdiag else None
+    counts = torch.zeros(B, 3, dtype=torch.int32, device=xyz.device)
+    status = torch.zeros(B, dtype=torch.int32, device=xyz.device)
+    nbytes = lib.mop_lindh_workspace_bytes(B, N)
+    work = workspace(xyz.device, nbytes)
+    with torch.cuda.device(xyz.device):
+        rc = lib.mop_lindh_hessian(B, N, _ptr(xyz), _ptr(p), stride, _ptr(H), _ptr(kd), _ptr(counts), _ptr(status),
+                                   _ptr(work), nbytes, _stream(xyz.device))
+    _lib.check(rc, "mop_lindh_hessian")
+    return H, kd, counts, status

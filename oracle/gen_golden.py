@@ -472,8 +472,36 @@ def gen_neb():
     print("neb: gammas", np.round(rec["gamma"][0], 4), "move norms", np.round(np.linalg.norm(rec["rfo_move"][1], axis=1), 4))
 
 
+def gen_lindh():
+    """Lindh model Hessian, decomposed parity: diagonal RIC force constants,
+    B^T diag(k) B projected, and main() with a zero gradient (its K term vanishes there)."""
+    li = ref_shim.ref("ModelHessian.lindh")
+    ric = ref_shim.ref("Coordinate.redundant_coordinate")
+    ct = ref_shim.ref("Utils.calc_tools")
+    blob = {"names": np.array(["aldol_rxn", "s8", "claisen", "grid24"])}
+    for name, path in [c for c in PRODUCER_CASES if c[0] in ("aldol_rxn", "s8", "claisen", "grid24")]:
+        elems, xyz = producer_geometry(name, path)
+        N = len(elems)
+        L = li.LindhApproxHessian()
+        with quiet():
+            B = ric.RedundantInternalCoordinates().B_matrix(xyz)
+            L.RIC_variable_num = len(B)
+            kd = np.diag(L.guess_lindh_hessian(xyz.copy(), elems)).copy()
+            Hbkb = ct.Calculationtools().project_out_hess_tr_and_rot_for_coord(B.T @ np.diag(kd) @ B, elems, xyz.copy(), False)
+            try:
+                Hmain = np.asarray(li.LindhApproxHessian().main(xyz.copy(), elems, np.zeros((N, 3))), float)
+            except Exception as exc:
+                print("  main(zero gradient) failed:", exc)
+                Hmain = np.full((3 * N, 3 * N), np.nan)
+        blob[f"{name}/elements"] = np.array(elems); blob[f"{name}/xyz"] = xyz
+        blob[f"{name}/kdiag"] = kd; blob[f"{name}/H_bkb"] = np.asarray(Hbkb, float); blob[f"{name}/H_main0"] = Hmain
+        print("lindh case", name, "kdiag range", kd.min(), kd.max(), "main0 vs BkB",
+              np.linalg.norm(Hmain - Hbkb) / np.linalg.norm(Hbkb))
+    np.savez_compressed(os.path.join(GOLD, "lindh.npz"), **blob)
+
+
 SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
-        "c1": gen_c1_trace, "neb": gen_neb}
+        "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

@@ -1112,3 +1112,62 @@ class NEBRFOOracle:
             self.H[i] = o.hessian
         self.prev = (X.copy(), G.copy())
         return F, T, gam, delta, neb_limit_tr(X, G, delta)
+
+
+# --------------------------------------------------------------------------
+# Lindh model Hessian, decomposed (ModelHessian/lindh.py:79-165)
+# --------------------------------------------------------------------------
+LINDH_ALPHA = [[1.0000, 0.3949, 0.3949], [0.3949, 0.2800, 0.2800], [0.3949, 0.2800, 0.2800]]
+
+
+def lindh_kdiag(coord, prm):
+    """Diagonal RIC force constants of guess_lindh_hessian (lindh.py:79-143).
+    prm (N, 6): covalent radius, period index, mass, UFF distance, UFF well depth, UFF charge."""
+    coord = np.asarray(coord, float)
+    N = len(coord)
+    rad = prm[:, 0]
+    tabs = connectivity_tables(coord, rad, 1.1)
+    pairs = [(i, j) for i in range(N) for j in range(i + 1, N)]
+    index = {p: k for k, p in enumerate(pairs)}
+    kd = [0.0] * len(pairs)
+    base = [0.45, 0.15, 0.005]
+    for tab in tabs:
+        for idx in tab:
+            f = base[len(idx) - 2]
+            for q in range(len(idx) - 1):
+                i, j = idx[q], idx[q + 1]
+                cR = rad[i] + rad[j]
+                al = LINDH_ALPHA[int(prm[i, 1])][int(prm[j, 1])]
+                R = np.linalg.norm(coord[i] - coord[j])
+                f *= math.exp(al * (cR ** 2 - R ** 2))
+            if len(idx) == 2:
+                lo, hi = sorted(idx)
+                m1, m2 = prm[lo, 2], prm[hi, 2]
+                kd[index[(lo, hi)]] += f / ((m1 * m2) / (m1 + m2))
+            else:
+                for q in range(len(idx) - 1):
+                    kd[index[tuple(sorted((idx[q], idx[q + 1])))]] += f
+    bonded = {tuple(b) for b in tabs[0]}
+    for k, (i, j) in enumerate(pairs):
+        if (i, j) in bonded:
+            continue
+        d = np.linalg.norm(coord[i] - coord[j])
+        eps = math.sqrt(prm[i, 4] * prm[j, 4]); sig = math.sqrt(prm[i, 3] * prm[j, 3])
+        kd[k] += -12 * eps * (-7 * (sig ** 6 / d ** 8) + 13 * (sig ** 12 / d ** 14))
+        kd[k] += 664.12 * (prm[i, 5] * prm[j, 5] / d ** 3) * (0.52917721067 ** 2 / 627.509)
+    return np.array(kd)
+
+
+def lindh_hessian_bkb(coord, prm):
+    """project(B^T diag(k) B) with the all-pairs distance B matrix
+    (Coordinate/redundant_coordinate.py:15-43,145 without the K term)."""
+    coord = np.asarray(coord, float)
+    N = len(coord)
+    kd = lindh_kdiag(coord, prm)
+    pairs = [(i, j) for i in range(N) for j in range(i + 1, N)]
+    B = np.zeros((len(pairs), 3 * N))
+    for k, (i, j) in enumerate(pairs):
+        e = (coord[i] - coord[j]) / np.linalg.norm(coord[i] - coord[j])
+        B[k, 3 * i:3 * i + 3] = e
+        B[k, 3 * j:3 * j + 3] = -e
+    return project_hessian_trrot(B.T @ np.diag(kd) @ B, coord.reshape(-1))
