@@ -153,6 +153,26 @@ int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode, in
                     double* eigvals_out, double* pred_out, int32_t* status, void* work,
                     size_t work_bytes, void* stream);
 
+/* ---- (2e) one RS-P-RFO step ----------------------------------------------------
+ * Replaces EnhancedRSPRFO.run (Optimizer/rsprfo.py:713-886): reduction ratio of the previous
+ * step and Nocedal-Wright trust-radius update, Hessian update with the BIASED gradients (small
+ * change skip only), TR/ROT projection of the gradient, eigendecomposition of H + Hbias (not
+ * projected), eigenvalue shifting, mode following, P-RFO step from the extreme eigenpairs of
+ * the max / min arrowhead matrices, trust and gradient-based scaling, predicted energy change.
+ * move_out [B][n] = the value run() returns (the caller computes x - move).
+ * Per-structure state: state [B][MOP_PRFO_STATE] doubles (column 0 = trust radius, initialise
+ * to 0.1 for saddle searches / 0.5 for minimisations, rest 0), prev_grad / prev_move / ts_vec
+ * [B][n] scratch owned by the caller across calls.  pre_move, x_prev, Bg_prev, Hbias may be NULL.
+ * Not reproduced: the rejection of an update whose eigenvalues exceed 1e6 (rsprfo.py:1242-1250). */
+#define MOP_PRFO_STATE 8
+size_t mop_rsprfo_workspace_bytes(int B, int n, int eigh_algo);
+int mop_rsprfo_step(int B, int n, int method, int saddle_order, int eigh_algo, double trust_min,
+                    double trust_max, double* H, const double* Hbias, const double* x, const double* Bg,
+                    const double* x_prev, const double* Bg_prev, const double* pre_move, const double* Be,
+                    double* state, double* prev_grad, double* prev_move, double* ts_vec, double* move_out,
+                    double* eigvals_out, double* pred_out, int32_t* status, void* work, size_t work_bytes,
+                    void* stream);
+
 /* ---- (2d) RS-I-RFO step from an already projected Hessian ---------------------
  * The part of RSIRFO.run after the projections (Optimizer/rsirfo.py:358-490): one
  * shared-memory-resident kernel per structure that tridiagonalises Hp, finds the

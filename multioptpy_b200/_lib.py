@@ -34,6 +34,8 @@ SIGNATURES = {
     "mop_rsirfo_workspace_bytes": (_sz, [_i, _i, _i]),
     "mop_rsirfo_step": (_i, [_i, _i, _i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                              _p, _p, _p, _p, _sz, _p]),
+    "mop_rsprfo_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mop_rsprfo_step": (_i, [_i, _i, _i, _i, _i, _d, _d] + [_p] * 16 + [_sz, _p]),
     "mop_rsirfo_spectral_workspace_bytes": (_sz, [_i, _i]),
     "mop_rsirfo_spectral_step": (_i, [_i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mop_connectivity": (_i, [_i, _i, _p, _p, _i, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p]),

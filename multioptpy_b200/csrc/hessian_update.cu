@@ -73,10 +73,10 @@ k_hessian_update(int n, int method, int mode, int guards, double* __restrict__ H
   double sy = block_sum(psy, scratch);
   const double yy = block_sum(pyy, scratch);
 
-  if (guards) {  // RSIRFO.update_hessian, rsirfo.py:1326,1333
+  if (guards) {  // 1: RSIRFO.update_hessian (rsirfo.py:1326,1333); 2: EnhancedRSPRFO (rsprfo.py:1210)
     int skip = 0;
     if (sqrt(ss) < 1e-10 || sqrt(yy) < 1e-10) skip = MOP_ST_UPD_SKIP_SMALL;
-    else if (sy <= 0.0) skip = MOP_ST_UPD_SKIP_CURV;
+    else if (guards == 1 && sy <= 0.0) skip = MOP_ST_UPD_SKIP_CURV;
     if (skip) {
       if (tid == 0 && status) status[b] = st | skip;
       return;
@@ -194,7 +194,7 @@ static size_t upd_smem_bytes(int n) {
 // Internal launcher shared with mop_rsirfo_step (s, y formed from the points).
 int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, double* H,
                               const double* s, const double* y, const double* x, const double* xp,
-                              const double* g, const double* gp, const double* state,
+                              const double* g, const double* gp, const double* state, int state_stride,
                               double* delta_out, int32_t* status, cudaStream_t stream) {
   if (method == MOP_UPD_PCFD_BOFILL) {
     mop_set_error("pcfd_bofill (O(n^4) null-space perturbation) is not implemented on the device");
@@ -213,7 +213,7 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_hessian_update,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mop::k_hessian_update<<<B, mop::UPD_THREADS, smem, stream>>>(
-      n, method, mode, guards, H, s, y, x, xp, g, gp, state, MOP_RSIRFO_STATE, delta_out, status);
+      n, method, mode, guards, H, s, y, x, xp, g, gp, state, state_stride, delta_out, status);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
@@ -226,6 +226,6 @@ extern "C" int mop_hessian_update(int B, int n, int method, int mode, int rsirfo
   MOP_REQUIRE(mode == 0 || mode == 1, "mop_hessian_update: mode must be 0 (delta) or 1 (in place)");
   MOP_REQUIRE(mode == 1 || delta_out, "mop_hessian_update: delta_out required in mode 0");
   return mop_launch_hessian_update(B, n, method, mode, rsirfo_guards, H, s, y, nullptr, nullptr,
-                                   nullptr, nullptr, nullptr, delta_out, status,
+                                   nullptr, nullptr, nullptr, 0, delta_out, status,
                                    (cudaStream_t)stream);
 }

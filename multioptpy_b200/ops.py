@@ -393,3 +393,40 @@ def lindh_hessian(xyz, atom_params, want_kdiag: bool = False):
                                    _ptr(work), nbytes, _stream(xyz.device))
     _lib.check(rc, "mop_lindh_hessian")
     return H, kd, counts, status
+
+
+PRFO_STATE = 8
+
+
+def rsprfo_step(H, x, Bg, st, *, method: int, saddle_order: int = 1, Hbias=None, x_prev=None, Bg_prev=None,
+                pre_move=None, Be=None, trust_min=0.01, trust_max=0.3, eigh_algo="auto", out=None):
+    """One EnhancedRSPRFO.run for a batch.  st: dict(state (B,8), prev_grad, prev_move, ts_vec (B,n))."""
+    lib = _lib.load()
+    B, n = x.shape
+    dev = x.device
+    _chk(H, "H", (B, n, n)); _chk(x, "x", (B, n)); _chk(Bg, "Bg", (B, n)); _chk(Be, "Be", (B,))
+    _chk(st["state"], "state", (B, PRFO_STATE))
+    for k in ("prev_grad", "prev_move", "ts_vec"):
+        _chk(st[k], k, (B, n))
+    if Hbias is not None:
+        _chk(Hbias, "Hbias", (B, n, n))
+    if x_prev is not None:
+        _chk(x_prev, "x_prev", (B, n)); _chk(Bg_prev, "Bg_prev", (B, n))
+    if pre_move is not None:
+        _chk(pre_move, "pre_move", (B, n))
+    algo_id = EIGH_ALGOS[eigh_algo] if isinstance(eigh_algo, str) else int(eigh_algo)
+    if out is None:
+        out = {"move": torch.empty(B, n, dtype=torch.float64, device=dev),
+               "eigvals": torch.empty(B, n, dtype=torch.float64, device=dev),
+               "pred": torch.empty(B, dtype=torch.float64, device=dev),
+               "status": torch.empty(B, dtype=torch.int32, device=dev)}
+    nbytes = lib.mop_rsprfo_workspace_bytes(B, n, algo_id)
+    work = workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        rc = lib.mop_rsprfo_step(B, n, int(method), int(saddle_order), algo_id, float(trust_min), float(trust_max),
+                                 _ptr(H), _ptr(Hbias), _ptr(x), _ptr(Bg), _ptr(x_prev), _ptr(Bg_prev), _ptr(pre_move),
+                                 _ptr(Be), _ptr(st["state"]), _ptr(st["prev_grad"]), _ptr(st["prev_move"]),
+                                 _ptr(st["ts_vec"]), _ptr(out["move"]), _ptr(out["eigvals"]), _ptr(out["pred"]),
+                                 _ptr(out["status"]), _ptr(work), nbytes, _stream(dev))
+    _lib.check(rc, "mop_rsprfo_step")
+    return out

@@ -500,8 +500,73 @@ def gen_lindh():
     np.savez_compressed(os.path.join(GOLD, "lindh.npz"), **blob)
 
 
+RSPRFO_CASES = [
+    # (name, method, saddle_order, natoms, nsteps, bias, seed)
+    ("prfo_bofill_ts_n36", "rsprfo_bofill", 1, 12, 6, False, 1),
+    ("prfo_blockbofill_ts_n33", "rsprfo_block_bofill", 1, 11, 6, True, 2),
+    ("prfo_fsb_min_n30", "rsprfo_fsb", 0, 10, 5, False, 3),
+    ("prfo_bofill_ts2_n30", "rsprfo_bofill", 2, 10, 5, False, 4),
+    ("prfo_bofill_ts_n150", "rsprfo_bofill", 1, 50, 4, False, 5),
+    ("prfo_msp_ts_n24", "rsprfo_msp", 1, 8, 6, True, 6),
+]
+
+
+def run_rsprfo_case(case):
+    name, method, so, natoms, nsteps, bias, seed = case
+    rp = ref_shim.ref("Optimizer.rsprfo")
+    rng = np.random.default_rng(515100 + seed)
+    n = 3 * natoms
+    x0 = synthetic.grid_geometry(natoms, rng).reshape(-1)
+    H0 = synthetic.spd_hessian(n, rng, neg_lowest=so > 0)
+    if so > 1:
+        w, V = np.linalg.eigh(H0); w[1] = -0.02
+        H0 = (V * w) @ V.T; H0 = 0.5 * (H0 + H0.T)
+    E = rng.standard_normal((n, n))
+    Ht = H0 + 0.05 * (E + E.T) / np.sqrt(n)
+    g0 = rng.normal(0.0, 1e-2, size=n)
+    Hb = np.zeros((n, n))
+    if bias:
+        Bm = rng.standard_normal((n, 4)); Hb = 0.02 * (Bm @ Bm.T)
+    pes = QuadraticPES(x0, g0, Ht, Hb, rng)
+    with quiet():
+        opt = rp.EnhancedRSPRFO(method=method, saddle_order=so, element_list=["C"] * natoms,
+                                trust_radius_max=(0.3 if so > 0 else 0.5), trust_radius_min=0.01)
+        opt.set_hessian(H0.copy()); opt.set_bias_hessian(Hb.copy())
+    rec = {k: [] for k in ("x", "Bg", "Be", "move", "H_after", "trust", "pred")}
+    x = x0.copy(); x_prev = Bg_prev = mv_prev = None
+    for k in range(nsteps):
+        e, g = pes.raw(x); eb, gb = pes.bias(x)
+        Be, Bg = e + eb, g + gb
+        col = lambda a: a.reshape(-1, 1).copy()
+        with quiet():
+            if x_prev is None:
+                mv = opt.run(col(x), col(Bg), [], [], Be, 0.0, [], col(x0), col(g), [])
+            else:
+                mv = opt.run(col(x), col(Bg), col(Bg_prev), col(x_prev), Be, 0.0, col(mv_prev), col(x0), col(g), [])
+        mv = np.asarray(mv, float).ravel()
+        rec["x"].append(x.copy()); rec["Bg"].append(Bg.copy()); rec["Be"].append(Be); rec["move"].append(mv)
+        rec["H_after"].append(np.array(opt.hessian, float)); rec["trust"].append(float(opt.trust_radius))
+        rec["pred"].append(float(opt.predicted_energy_changes[-1]))
+        x_prev, Bg_prev, mv_prev = x.copy(), Bg.copy(), mv.copy()
+        x = x - mv
+    out = {f"{name}/{k}": np.array(v) for k, v in rec.items()}
+    out[f"{name}/H0"] = H0; out[f"{name}/Hb"] = Hb
+    out[f"{name}/meta"] = np.array([so, natoms, nsteps, int(bias)], np.int64)
+    out[f"{name}/method"] = np.array(method)
+    return out
+
+
+def gen_rsprfo():
+    blob = {}
+    for case in RSPRFO_CASES:
+        blob.update(run_rsprfo_case(case))
+        print("rsprfo case", case[0])
+    blob["names"] = np.array([c[0] for c in RSPRFO_CASES])
+    np.savez_compressed(os.path.join(GOLD, "rsprfo_traces.npz"), **blob)
+
+
 SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
-        "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh}
+        "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

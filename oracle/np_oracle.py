@@ -1171,3 +1171,188 @@ def lindh_hessian_bkb(coord, prm):
         B[k, 3 * i:3 * i + 3] = e
         B[k, 3 * j:3 * j + 3] = -e
     return project_hessian_trrot(B.T @ np.diag(kd) @ B, coord.reshape(-1))
+
+
+# --------------------------------------------------------------------------
+# EnhancedRSPRFO (Optimizer/rsprfo.py) — config 5
+# --------------------------------------------------------------------------
+def project_grad_trrot_qr_valid(g, x):
+    """EnhancedRSPRFO._project_grad_tr_rot, rsprfo.py:224-285 (drops |diag R| <= 1e-10 columns)."""
+    coords = x.reshape(-1, 3)
+    if coords.shape[0] < 3:
+        return g
+    A = trrot_vectors(x).T
+    Q, R = np.linalg.qr(A, mode="reduced")
+    Q = Q[:, np.abs(np.diag(R)) > 1e-10]
+    return g - Q @ (Q.T @ g)
+
+
+def arrowhead_extreme(lam, gam, mode):
+    """solve_rfo on the augmented (arrowhead) Hessian, rsprfo.py:1097-1168, alpha = 1:
+    step = -v[:-1] / v[-1] of the smallest ('min') or largest ('max') eigenpair."""
+    k = lam.size
+    Haug = np.zeros((k + 1, k + 1))
+    Haug[np.arange(k), np.arange(k)] = lam
+    Haug[:k, k] = gam
+    Haug[k, :k] = gam
+    w, V = np.linalg.eigh(Haug)
+    idx = int(np.argmin(w)) if mode == "min" else int(np.argmax(w))
+    v = V[:, idx]
+    nu = v[-1]
+    if abs(nu) < 1e-12:
+        nu = np.sign(nu) * 1e-12 if nu != 0 else 1e-12
+    return -v[:-1] / nu, w[idx]
+
+
+class RSPRFOOracle:
+    """EnhancedRSPRFO.run for one structure (default configuration).  The alpha micro-cycles are a
+    no-op analytically (eigenvalues and gradient are both divided by alpha, rsprfo.py:1116-1121,
+    SURVEY H3): every cycle reproduces the alpha = 1 step, the loop leaves through the
+    trust-radius / stagnation / bound exits and returns that step scaled to the effective trust
+    radius; this restatement evaluates the alpha = 1 step once."""
+
+    def __init__(self, method="rsprfo_bofill", saddle_order=1, trust_radius_max=None, trust_radius_min=0.01, **_):
+        self.method_id = resolve_update_method(method)
+        self.saddle_order = saddle_order
+        if saddle_order == 0:
+            self.trust0 = 0.5; self.trust_max = 0.5 if trust_radius_max is None else trust_radius_max
+        else:
+            self.trust0 = 0.1; self.trust_max = 0.3 if trust_radius_max is None else trust_radius_max
+        self.trust = self.trust0
+        self.trust_min = 0.01 if trust_radius_min is None else trust_radius_min
+        self.hessian = None
+        self.bias_hessian = None
+        self.first = True
+        self.prev_energy = None
+        self.pred = []
+        self.prev_gradient = None
+        self.prev_move = None
+        self.ts_vec = None
+        self.rejections = 0
+        self.last = {}
+
+    def set_hessian(self, H):
+        self.hessian = 0.5 * (np.asarray(H, float) + np.asarray(H, float).T)     # copies (rsprfo.py:1317-1318)
+
+    def set_bias_hessian(self, H):
+        self.bias_hessian = None if H is None else np.asarray(H, float).copy()
+
+    def _eff_trust(self, gnorm):
+        if gnorm < 1e-3:                                           # rsprfo.py:392-419
+            r = 0.5 * gnorm / 1e-3 * self.trust_max
+            return min(max(r, self.trust_min), self.trust)
+        return self.trust
+
+    def run(self, x, Bg, x_prev=None, Bg_prev=None, Be=0.0, pre_move=None):
+        x = np.asarray(x, float).ravel(); Bg = np.asarray(Bg, float).ravel()
+        info = {"updated": False, "shifted": False}
+        if self.first:
+            self.first = False
+        elif self.prev_energy is not None and self.pred:            # _process_previous_step (:908-962)
+            actual = Be - self.prev_energy
+            psn = np.linalg.norm(pre_move) if (pre_move is not None and len(pre_move) > 0) else np.linalg.norm(self.prev_move)
+            Hs = self.hessian + self.bias_hessian if self.bias_hessian is not None else self.hessian
+            Hp = project_hessian_trrot(Hs, x)
+            s = self.prev_move
+            pred_red = -(self.prev_gradient @ s + 0.5 * s @ (Hp @ s))
+            if abs(pred_red) < 1e-14:
+                ratio = 1.0 if abs(actual) < 1e-14 else 0.0
+            else:
+                ratio = actual / pred_red
+                if not np.isfinite(ratio):
+                    ratio = 0.0
+            at_boundary = psn >= self.trust * 0.95
+            if ratio < 0.25:
+                self.trust = max(0.25 * psn, self.trust_min)
+            elif ratio > 0.75 and at_boundary:
+                self.trust = min(2.0 * self.trust, self.trust_max)
+            info["ratio"] = ratio
+        # Hessian update with the BIASED gradients, no curvature sign test (:1190-1260)
+        if self.prev_gradient is not None and x_prev is not None and Bg_prev is not None and len(x_prev) > 0 and len(Bg_prev) > 0:
+            s = x - np.asarray(x_prev, float).ravel(); y = Bg - np.asarray(Bg_prev, float).ravel()
+            if not (np.linalg.norm(s) < 1e-10 or np.linalg.norm(y) < 1e-10):
+                Hn = self.hessian + hessian_update_delta(self.method_id, self.hessian, s, y)
+                Hn = 0.5 * (Hn + Hn.T)
+                if not np.max(np.abs(np.linalg.eigvalsh(Hn))) > 1e6:
+                    self.hessian = Hn
+                    info["updated"] = True
+        g = project_grad_trrot_qr_valid(Bg, x)
+        gnorm = np.linalg.norm(g)
+        H = self.hessian + self.bias_hessian if self.bias_hessian is not None else self.hessian
+        lam, V = np.linalg.eigh(H)
+        if not (np.all(np.isfinite(lam)) and np.all(np.isfinite(V))):
+            lam = np.ones_like(lam); V = np.eye(lam.size)
+        # eigenvalue shifting (:287-355)
+        so = self.saddle_order
+        lam2 = lam.copy(); shifted = False
+        if so == 0:
+            if lam.min() < 0.001:
+                lam2 = lam + (0.001 - lam.min()); shifted = True
+        else:
+            order = np.argsort(lam)
+            for i in range(so):
+                if lam[order[i]] > -0.001:
+                    lam2[order[i]] = -0.001; shifted = True
+            for i in range(so, lam.size):
+                if lam[order[i]] < 1e-6:
+                    lam2[order[i]] = 0.001; shifted = True
+        if shifted:
+            Hsh = V @ np.diag(lam2) @ V.T
+            H = 0.5 * (Hsh + Hsh.T)
+            lam, V = np.linalg.eigh(H)
+        info["shifted"] = shifted
+        n = lam.size
+        # mode selection (:964-1071)
+        if so == 0:
+            max_idx = []
+        else:
+            order = np.argsort(lam)
+            if self.ts_vec is None:
+                self.ts_vec = V[:, order[0]].copy()
+                max_idx = order[:so].tolist()
+            else:
+                ov = np.abs(V.T @ self.ts_vec)
+                best = int(np.argmax(ov))
+                if ov[best] > 0.5:
+                    self.ts_vec = V[:, best].copy()
+                    max_idx = [best] + [i for i in order if i != best][:so - 1]
+                else:
+                    sig = np.where(ov > 0.3)[0]
+                    if len(sig) == 0:
+                        self.ts_vec = V[:, order[0]].copy()
+                        max_idx = order[:so].tolist()
+                    else:
+                        wts = [ov[i] ** 2 * (1.0 if lam[i] < 0 else 0.1) for i in sig]
+                        best = int(sig[int(np.argmax(wts))])
+                        self.ts_vec = V[:, best].copy()
+                        max_idx = [best] + [i for i in order if i != best][:so - 1]
+        min_idx = [i for i in range(n) if i not in max_idx]
+        gt = V.T @ g
+        step = np.zeros(n)
+        if max_idx:
+            step[max_idx], _ = arrowhead_extreme(lam[max_idx], gt[max_idx], "max")
+        if min_idx:
+            step[min_idx], _ = arrowhead_extreme(lam[min_idx], gt[min_idx], "min")
+        eff = self._eff_trust(gnorm)
+        nrm = np.linalg.norm(step)
+        if nrm > eff:
+            step = step * (eff / nrm)
+        if not np.all(np.isfinite(step)):                          # (:833-846)
+            sd = -gt; sdn = np.linalg.norm(sd); tgt = min(sdn, self.trust)
+            step = sd * (tgt / sdn) if sdn > 1e-12 else np.zeros(n)
+        move = V @ step
+        snorm = np.linalg.norm(move)
+        if not (gnorm < 1e-10 or snorm < 1e-10):                   # gradient-based scaling (:357-390)
+            r = snorm / gnorm
+            if r > 50.0:
+                sc = max(50.0 / r, 0.1)
+                move = move * sc; snorm = snorm * sc
+        eff = self._eff_trust(gnorm)
+        if snorm > eff * 1.01:
+            move = move * (eff / snorm)
+        pred = g @ move + 0.5 * move @ (H @ move)
+        self.pred.append(pred)
+        self.prev_gradient = Bg.copy(); self.prev_energy = Be; self.prev_move = move.copy()
+        info.update(eigvals=lam, pred=pred, trust=self.trust, max_idx=list(max_idx))
+        self.last = info
+        return move

@@ -1,0 +1,101 @@
+"""EnhancedRSPRFO (P-RFO saddle search): oracle and CUDA drop-in vs golden
+traces recorded from the reference."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+RTOL = 1e-10
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
+
+
+def _load(golden_dir):
+    z = np.load(os.path.join(golden_dir, "rsprfo_traces.npz"))
+    return z, [str(s) for s in z["names"]]
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_oracle_rsprfo_trace(golden_dir, idx):
+    z, names = _load(golden_dir)
+    name = names[idx]
+    so, natoms, nsteps, bias = [int(v) for v in z[f"{name}/meta"]]
+    opt = O.RSPRFOOracle(method=str(z[f"{name}/method"]), saddle_order=so,
+                         trust_radius_max=(0.3 if so > 0 else 0.5))
+    opt.set_hessian(z[f"{name}/H0"]); opt.set_bias_hessian(z[f"{name}/Hb"])
+    X, BG, BE = z[f"{name}/x"], z[f"{name}/Bg"], z[f"{name}/Be"]
+    mv_prev = None
+    for k in range(nsteps):
+        mv = opt.run(X[k], BG[k], X[k - 1] if k else None, BG[k - 1] if k else None, float(BE[k]), mv_prev)
+        assert rel(mv, z[f"{name}/move"][k]) < RTOL, (name, k)
+        assert rel(opt.hessian, z[f"{name}/H_after"][k]) < RTOL, (name, k)
+        assert abs(opt.trust - z[f"{name}/trust"][k]) < 1e-13, (name, k)
+        p = z[f"{name}/pred"][k]
+        assert abs(opt.pred[-1] - p) <= 1e-9 * abs(p) + 1e-15, (name, k)
+        mv_prev = mv
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(6))
+def test_gpu_rsprfo_trace(golden_dir, idx):
+    from multioptpy_b200.Optimizer.rsprfo import EnhancedRSPRFO
+    z, names = _load(golden_dir)
+    name = names[idx]
+    so, natoms, nsteps, bias = [int(v) for v in z[f"{name}/meta"]]
+    opt = EnhancedRSPRFO(method=str(z[f"{name}/method"]), saddle_order=so, element_list=["C"] * natoms,
+                         trust_radius_max=(0.3 if so > 0 else 0.5), trust_radius_min=0.01, device="cuda:0",
+                         display_flag=False)
+    opt.set_hessian(z[f"{name}/H0"]); opt.set_bias_hessian(z[f"{name}/Hb"])
+    X, BG, BE = z[f"{name}/x"], z[f"{name}/Bg"], z[f"{name}/Be"]
+    col = lambda a: a.reshape(-1, 1).copy()
+    mv_prev = None
+    for k in range(nsteps):
+        if k == 0:
+            mv = opt.run(col(X[k]), col(BG[k]), [], [], float(BE[k]), 0.0, [], col(X[0]), col(BG[k]), [])
+        else:
+            mv = opt.run(col(X[k]), col(BG[k]), col(BG[k - 1]), col(X[k - 1]), float(BE[k]), 0.0, col(mv_prev),
+                         col(X[0]), col(BG[k]), [])
+        assert mv.shape == (3 * natoms, 1)
+        assert rel(mv.ravel(), z[f"{name}/move"][k]) < RTOL, (name, k)
+        assert rel(opt.hessian, z[f"{name}/H_after"][k]) < RTOL, (name, k)
+        assert abs(opt.trust_radius - z[f"{name}/trust"][k]) < 1e-13, (name, k)
+        p = z[f"{name}/pred"][k]
+        assert abs(opt.predicted_energy_changes[-1] - p) <= 1e-9 * abs(p) + 1e-15, (name, k)
+        mv_prev = mv.ravel().copy()
+
+
+@pytest.mark.gpu
+def test_gpu_rsprfo_batched_vs_oracle():
+    """Tensor mode: a batch of saddle searches, three consecutive steps, vs the oracle."""
+    import torch
+    from multioptpy_b200 import synthetic
+    from multioptpy_b200.Optimizer.rsprfo import EnhancedRSPRFO
+    B, natoms = 12, 30
+    x0, H0, g0, rngs = synthetic.batch(5, B, natoms, saddle=True)
+    dev = "cuda:0"
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    opt = EnhancedRSPRFO(method="rsprfo_bofill", saddle_order=1, device=dev, display_flag=False)
+    opt.set_hessian(T(H0)); opt.set_bias_hessian(None)
+    oracles = []
+    for b in range(B):
+        o = O.RSPRFOOracle(method="rsprfo_bofill", saddle_order=1)
+        o.set_hessian(H0[b]); oracles.append(o)
+    x, g = x0.copy(), g0.copy()
+    xp = gp = mp = None
+    for it in range(3):
+        Be = torch.full((B,), -1e-3 * it, dtype=torch.float64, device=dev)
+        if it == 0:
+            mv = opt.run(T(x), T(g), B_e=Be).cpu().numpy().copy()
+        else:
+            mv = opt.run(T(x), T(g), pre_B_g=T(gp), pre_geom=T(xp), B_e=Be, pre_move_vector=T(mp)).cpu().numpy().copy()
+        for b, o in enumerate(oracles):
+            m = o.run(x[b], g[b], xp[b] if it else None, gp[b] if it else None, -1e-3 * it, mp[b] if it else None)
+            assert rel(mv[b], m) < RTOL, (it, b)
+        xp, gp, mp = x.copy(), g.copy(), mv.copy()
+        x = x - mv
+        g = np.stack([g0[b] + H0[b] @ (x[b] - x0[b]) for b in range(B)])
