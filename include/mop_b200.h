@@ -209,6 +209,18 @@ int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radi
                         double* H_out, int32_t* counts_out, int32_t* status, void* work,
                         size_t work_bytes, void* stream);
 
+/* ---- Swart model Hessian ----------------------------------------------------------
+ * Replaces SwartApproxHessian.main (ModelHessian/swart.py:317-355): all-pairs screened stretch
+ * terms, screened bend terms with the near-linear blending, non-finite fallback to stretches
+ * only (status[b] = 1 when taken), then the TR/ROT projection.  radii [B or 1][natoms] = the
+ * model's own table in Bohr (swart.py:10-25; 1.0 for unknown elements); radii_stride 0 shares one
+ * row.  Hraw_out (optional) [B][n][n] receives the unprojected Hessian; when NULL the workspace
+ * holds it. */
+size_t mop_swart_workspace_bytes(int B, int natoms);
+int mop_swart_hessian(int B, int natoms, const double* xyz, const double* radii, int radii_stride,
+                      double* H_out, double* Hraw_out, int32_t* status, void* work, size_t work_bytes,
+                      void* stream);
+
 /* ---- (3b') Lindh model Hessian ---------------------------------------------------
  * Replaces LindhApproxHessian.main (ModelHessian/lindh.py:145-165) up to its K term:
  * H_out = project(B^T diag(k) B) with the all-pairs distance B matrix

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mop_connectivity": (_i, [_i, _i, _p, _p, _i, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_fischer_workspace_bytes": (_sz, [_i, _i]),
     "mop_fischer_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mop_swart_workspace_bytes": (_sz, [_i, _i]),
+    "mop_swart_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "mop_lindh_workspace_bytes": (_sz, [_i, _i]),
     "mop_lindh_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "mop_afir": (_i, [_i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),

@@ -430,3 +430,22 @@ def rsprfo_step(H, x, Bg, st, *, method: int, saddle_order: int = 1, Hbias=None,
                                  _ptr(out["status"]), _ptr(work), nbytes, _stream(dev))
     _lib.check(rc, "mop_rsprfo_step")
     return out
+
+
+def swart_hessian(xyz, radii, want_raw: bool = False):
+    """SwartApproxHessian.main for every structure: (B, 3N, 3N) projected model Hessians.
+    radii: (N,) or (B, N) Swart-table radii in Bohr.  Returns (H, Hraw or None, status)."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    r, stride = _radii_arg(radii, B, N, xyz.device)
+    H = torch.empty(B, 3 * N, 3 * N, dtype=torch.float64, device=xyz.device)
+    Hraw = torch.empty_like(H) if want_raw else None
+    status = torch.zeros(B, dtype=torch.int32, device=xyz.device)
+    nbytes = 0 if want_raw else lib.mop_swart_workspace_bytes(B, N)
+    work = workspace(xyz.device, nbytes) if nbytes else None
+    with torch.cuda.device(xyz.device):
+        rc = lib.mop_swart_hessian(B, N, _ptr(xyz), _ptr(r), stride, _ptr(H), _ptr(Hraw), _ptr(status),
+                                   _ptr(work), nbytes, _stream(xyz.device))
+    _lib.check(rc, "mop_swart_hessian")
+    return H, Hraw, status

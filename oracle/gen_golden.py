@@ -500,6 +500,40 @@ def gen_lindh():
     np.savez_compressed(os.path.join(GOLD, "lindh.npz"), **blob)
 
 
+def swart_extra_geometries():
+    """Geometries that exercise the near-linear branches of the Swart angle term."""
+    out = {}
+    # exactly linear along x (cross product zero -> second reference axis) and along a general direction
+    out["lin_x"] = (["O", "C", "O", "H"], np.array([[-2.2, 0, 0], [0, 0, 0], [2.2, 0, 0], [4.1, 0, 0.0]]))
+    u = np.array([1.0, 2.0, -0.5]); u /= np.linalg.norm(u)
+    out["lin_gen"] = (["H", "C", "N"], np.array([-2.0 * u, 0 * u, 2.2 * u]))
+    # nearly linear (th1 < tolth, cos < 0) plus a sharp angle (cos > 0.8) at a heavy centre
+    out["near_lin"] = (["C", "C", "C", "H", "H"], np.array([[-2.5, 0.1, 0], [0, 0, 0], [2.5, 0.25, 0.1], [0.3, 2.0, 0.2], [0.9, 1.9, 0.3]]))
+    out["sharp"] = (["Pd", "H", "H", "P", "Cl"], np.array([[0, 0, 0], [3.0, 0.7, 0], [3.0, -0.7, 0.1], [-4.0, 0.5, 0.3], [0.2, 4.2, -0.3]]))
+    rng = np.random.default_rng(5157)
+    out["cloud30"] = (synthetic.elements(30), synthetic.grid_geometry(30, rng, spacing=2.4, jitter=0.3))
+    return out
+
+
+def gen_swart():
+    """Swart model Hessian (ModelHessian/swart.py) on the producer molecules and on geometries
+    that hit the near-linear / sharp-angle branches; raw (unprojected) Hessian recorded as well."""
+    sw = ref_shim.ref("ModelHessian.swart")
+    cases = [(name,) + producer_geometry(name, path) for name, path in PRODUCER_CASES]
+    cases += [(name, e, x) for name, (e, x) in swart_extra_geometries().items()]
+    blob = {"names": np.array([c[0] for c in cases])}
+    for name, elems, xyz in cases:
+        xyz = np.asarray(xyz, float)
+        S = sw.SwartApproxHessian()
+        with quiet():
+            Hp = np.asarray(S.main(xyz.copy(), list(elems), np.zeros((len(elems), 3))), float)
+        blob[f"{name}/elements"] = np.array(elems); blob[f"{name}/xyz"] = xyz
+        blob[f"{name}/radii"] = S._get_radii_array(list(elems))
+        blob[f"{name}/H_raw"] = S.cart_hess.copy(); blob[f"{name}/H"] = Hp
+        print("swart case", name, len(elems), "|H|", np.linalg.norm(Hp))
+    np.savez_compressed(os.path.join(GOLD, "swart.npz"), **blob)
+
+
 RSPRFO_CASES = [
     # (name, method, saddle_order, natoms, nsteps, bias, seed)
     ("prfo_bofill_ts_n36", "rsprfo_bofill", 1, 12, 6, False, 1),
@@ -565,7 +599,7 @@ def gen_rsprfo():
     np.savez_compressed(os.path.join(GOLD, "rsprfo_traces.npz"), **blob)
 
 
-SETS = {"update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+SETS = {"swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo}
 
 if __name__ == "__main__":

@@ -1356,3 +1356,108 @@ class RSPRFOOracle:
         info.update(eigvals=lam, pred=pred, trust=self.trust, max_idx=list(max_idx))
         self.last = info
         return move
+
+
+# ---------------------------------------------------------------------------------------------
+# Swart model Hessian: ModelHessian/swart.py:58-355
+# ---------------------------------------------------------------------------------------------
+def swart_geometry(xyz, radii):
+    """_precompute_geometry, swart.py:64-82."""
+    diff = xyz[:, None, :] - xyz[None, :, :]
+    d = np.sqrt((diff * diff).sum(axis=2))
+    d = np.maximum(d, 1e-8)
+    np.fill_diagonal(d, 1.0)
+    cs = np.maximum(radii[:, None] + radii[None, :], 1e-8)
+    screen = np.exp(1.0 - d / cs)
+    np.fill_diagonal(screen, 0.0)
+    return diff, d, screen
+
+
+def swart_angle_rows(v1, v2, l1, l2):
+    """_calculate_batch_angle_B for one triple, swart.py:109-133: (row (9,), cos, sin^2)."""
+    l1 = max(l1, 1e-8); l2 = max(l2, 1e-8)
+    n1, n2 = v1 / l1, v2 / l2
+    c = min(max(float(n1 @ n2), -1.0), 1.0)
+    s2 = max(1e-12, 1.0 - c * c)
+    den = max(np.sqrt(s2), 1e-6)
+    bi = (c * n1 - n2) / (l1 * den)
+    bk = (c * n2 - n1) / (l2 * den)
+    return np.concatenate([bi, -(bi + bk), bk]), c, s2
+
+
+def swart_linear_rows(v1, v2, l1, l2):
+    """_calculate_batch_linear_B for one triple, swart.py:135-190: (2, 9)."""
+    l1 = max(l1, 1e-8); l2 = max(l2, 1e-8)
+    vn = np.cross(v1, v2)
+    nvn = np.linalg.norm(vn)
+    if nvn < 1e-12:
+        ref = np.array([1.0, 0.0, 0.0])
+        cand = ref - (ref @ v1) / l1 ** 2 * v1
+        cn = np.linalg.norm(cand)
+        if cn >= 1e-12:
+            vn, nvn = cand, cn
+        else:
+            ref = np.array([0.0, 1.0, 0.0])
+            cand = ref - (ref @ v1) / l1 ** 2 * v1
+            vn, nvn = cand, max(np.linalg.norm(cand), 1e-12)
+    vnn = vn / max(nvn, 1e-12)
+    vn2 = np.cross(v1 - v2, vnn)
+    vn2 = vn2 / max(np.linalg.norm(vn2), 1e-12)
+    Bm = np.zeros((2, 9))
+    for row, u in ((1, vnn), (0, vn2)):
+        Bm[row, 0:3] = u / l1
+        Bm[row, 6:9] = u / l2
+        Bm[row, 3:6] = -Bm[row, 0:3] - Bm[row, 6:9]
+    return Bm
+
+
+def swart_raw_hessian(xyz, radii, angles=True):
+    """Bond + angle terms before the TR/ROT projection (swart.py:83-107,192-315)."""
+    xyz = np.asarray(xyz, float); N = len(xyz); n = 3 * N
+    diff, d, screen = swart_geometry(xyz, np.asarray(radii, float))
+    H = np.zeros((n, n))
+    for i in range(N):
+        for j in range(i + 1, N):
+            e = diff[i, j] / d[i, j]
+            b = np.concatenate([e, -e])
+            idx = np.r_[3 * i:3 * i + 3, 3 * j:3 * j + 3]
+            H[np.ix_(idx, idx)] += 0.35 * screen[i, j] ** 3 * np.outer(b, b)
+    if not angles:
+        return H
+    f, tolth, eps1 = 0.12, 0.2, 0.3 ** 2
+    eps2 = 0.3 ** 2 / np.exp(1)
+    for j in range(N):
+        nb = np.where(screen[j] >= eps2)[0]
+        for a in range(len(nb)):
+            for c in range(a + 1, len(nb)):
+                i, k = nb[a], nb[c]
+                ss = screen[i, j] * screen[j, k]
+                if ss < eps1 or not (d[i, j] > 1e-8 and d[k, j] > 1e-8):
+                    continue
+                v1, v2, l1, l2 = diff[i, j], diff[k, j], d[i, j], d[k, j]
+                bn, cs, s2 = swart_angle_rows(v1, v2, l1, l2)
+                hb = 0.075 * ss ** 2 * (f + (1.0 - f) * np.sqrt(s2)) ** 2
+                th1 = 1.0 - cs if cs > 1.0 - tolth else 1.0 + cs
+                idx = np.r_[3 * i:3 * i + 3, 3 * j:3 * j + 3, 3 * k:3 * k + 3]
+                if th1 >= tolth:
+                    blk = hb * np.outer(bn, bn)
+                else:
+                    sl = (1.0 - (th1 / tolth) ** 2) ** 2
+                    if cs > 1.0 - tolth:
+                        bl = swart_linear_rows(v1, v2, l1, l2)
+                        bc = sl * bl[0] + (1.0 - sl) * bn
+                        blk = hb * np.outer(bl[1], bl[1]) + hb * np.outer(bc, bc)
+                    else:
+                        bs = (1.0 - sl) * bn
+                        blk = hb * np.outer(bs, bs)
+                H[np.ix_(idx, idx)] += blk
+    return H
+
+
+def swart_hessian(xyz, radii):
+    """SwartApproxHessian.main, swart.py:317-355 (NaN fallback to bonds only, then projection)."""
+    xyz = np.asarray(xyz, float)
+    H = swart_raw_hessian(xyz, radii)
+    if not np.all(np.isfinite(H)):
+        H = swart_raw_hessian(xyz, radii, angles=False)
+    return project_hessian_trrot(H, xyz.reshape(-1))
