@@ -88,6 +88,7 @@ enum {
 #define MOP_EIGH_AUTO 0
 #define MOP_EIGH_JACOBI 1  /* two-sided cyclic Jacobi, matrix resident in shared memory */
 #define MOP_EIGH_TRIDIAG 2 /* Householder tridiagonalisation + bisection + inverse iteration */
+#define MOP_EIGH_LARGE 3   /* same algorithm for 160 < n <= 1024: matrix streamed from L2 by a thread-block cluster */
 
 /* RSIRFO per-structure state: [B][MOP_RSIRFO_STATE] doubles (RSIRFO attributes
  * of Optimizer/rsirfo.py:97-112 that survive between run() calls). */
@@ -300,6 +301,7 @@ int mop_debug_fast_rcp(const double* x, double* out, size_t count, void* stream)
 int mop_debug_latency(double* out, void* stream);
 /* diagnostics: out[0..2] = cycles per bare barrier / reduce-publish-barrier-broadcast round /
  * the same plus a dependent sqrt and two reciprocals, for one CTA of `threads` threads. */
+int mop_debug_large_cluster(int cluster_ctas); /* tuning: CTAs per matrix of MOP_EIGH_LARGE (1, 2, 4, 8; 0 = auto) */
 int mop_debug_barrier_latency(int threads, double* out, void* stream);
 
 #ifdef __cplusplus

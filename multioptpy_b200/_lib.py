@@ -59,6 +59,7 @@ SIGNATURES = {
     "mop_debug_fast_rcp": (_i, [_p, _p, _sz, _p]),
     "mop_debug_latency": (_i, [_p, _p]),
     "mop_debug_barrier_latency": (_i, [_i, _p, _p]),
+    "mop_debug_large_cluster": (_i, [_i]),
 }
 
 _lib = None

@@ -21,6 +21,10 @@ size_t mop_tridiag_workspace_bytes(int B, int n);
 int mop_tridiag_supported(int n);
 int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double* evecs,
                             int32_t* status, void* work, size_t work_bytes, cudaStream_t stream);
+size_t mop_large_workspace_bytes(int B, int n);
+int mop_large_supported(int n);
+int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* evecs, int32_t* status,
+                          void* work, size_t work_bytes, cudaStream_t stream);
 int mop_launch_rfo_step(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
                         const double* evals, const double* evecs, const double* gp,
                         const double* Bg, const double* Be, double* state,
@@ -53,7 +57,8 @@ extern "C" const char* mop_last_error(void) { return g_err; }
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int pick_algo(int algo, int n) {
-  if (algo == MOP_EIGH_AUTO) return mop_tridiag_supported(n) ? MOP_EIGH_TRIDIAG : MOP_EIGH_JACOBI;
+  if (algo == MOP_EIGH_AUTO)
+    return mop_tridiag_supported(n) ? MOP_EIGH_TRIDIAG : (mop_large_supported(n) ? MOP_EIGH_LARGE : MOP_EIGH_JACOBI);
   return algo;
 }
 
@@ -61,6 +66,7 @@ static size_t eigh_work_bytes(int B, int n, int algo) {
   algo = pick_algo(algo, n);
   size_t jac = align256(mop_jacobi_workspace_bytes(B, n));  // also the fallback of the fast path
   if (algo == MOP_EIGH_TRIDIAG) return jac + align256(mop_tridiag_workspace_bytes(B, n));
+  if (algo == MOP_EIGH_LARGE) return jac + align256(mop_large_workspace_bytes(B, n));
   return jac;
 }
 
@@ -94,6 +100,15 @@ static int run_eigh(int B, int n, int algo, const double* A, double* evals, doub
     if (rc != MOP_OK) return rc;
     // robust fallback for structures the fast path flagged (no host sync: CTAs of
     // unflagged structures exit immediately)
+    return mop_launch_eigh_jacobi(B, n, A, evals, evecs, status, status, work, jac, stream);
+  }
+  if (algo == MOP_EIGH_LARGE) {
+    if (!status) {
+      mop_set_error("eigh: the large-n path needs a status array (fallback flags)");
+      return MOP_ERR_INVALID;
+    }
+    int rc = mop_launch_eigh_large(B, n, A, evals, evecs, status, (char*)work + jac, work_bytes - jac, stream);
+    if (rc != MOP_OK) return rc;
     return mop_launch_eigh_jacobi(B, n, A, evals, evecs, status, status, work, jac, stream);
   }
   mop_set_error("eigh: unknown algorithm id %d", algo);

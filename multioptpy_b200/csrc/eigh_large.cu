@@ -1,0 +1,627 @@
+// Batched symmetric eigensolver for matrices that do not fit in one SM's shared memory
+// (160 < n <= 1024; BASELINE config 5: P-RFO at N = 200 atoms, n = 600).
+//
+// The matrix stays in global memory (a batch slice that is being reduced is L2-resident) and
+// one thread-block CLUSTER reduces one matrix, so that a single matrix is streamed by the
+// L2 ports of several SMs and the per-column synchronisation is a hardware cluster barrier:
+//   1. k_lg_tridiag: Householder tridiagonalisation A = Q T Q^T, one cluster barrier per
+//      column.  The rank-2 update of column k and the product A v for column k+1 are fused
+//      into one pass over the trailing rows (each element is read and written once per
+//      column: 16 bytes instead of 24), rows are dealt to the warps of the cluster in groups
+//      of four so that v, w and v' are read from shared memory once per four rows.
+//   2. k_lg_trieig: eigenvalues of T by bisection on the Sturm count, eigenvectors by twisted
+//      factorisation, CGS2 inside clusters - the algorithm of eigh_tridiag.cu with Z in
+//      global memory (column i = vector i).
+//   3. k_lg_backtransform: V = Q Z, one warp per eigenvector held in registers, reflectors
+//      staged through shared memory once per CTA of 32 vectors; rows written in ascending order.
+// Structures whose clusters cancel are flagged MOP_ST_EIG_FALLBACK and redone by the Jacobi
+// kernel (global-memory variant).  Replaces numpy.linalg.eigh at Optimizer/rsprfo.py:783,798
+// and Optimizer/rsirfo.py:606 for large systems.
+#include <cooperative_groups.h>
+
+#include "tri_sturm.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mop {
+
+constexpr int LG_MAX_N = 1024;
+constexpr int LG_TRI_THREADS = 1024;
+constexpr int LG_EIG_THREADS = 1024;
+constexpr int LG_BT_THREADS = 512;
+constexpr int LG_ROWS = 4;  // rows per warp in the fused update + symv
+
+struct LgArgs {
+  int n;
+  double* A;     // [B][n][n] working copy (symmetric, destroyed)
+  double* Vh;    // [B][n][n] reflector k in row k, columns k+1.. (v[k+1] = 1 stored)
+  double* Z;     // [B][n][n] eigenvectors of T, column i = vector i
+  double* Dm;    // [B][n][n] backward pivots
+  double* dd;    // [B][n]
+  double* ee;    // [B][n]
+  double* tau;   // [B][n]
+  double* pbuf;  // [B][2][n] A v, double-buffered by column parity
+  int* rank;     // [B][n] ascending rank of vector i
+  double* evals; // [B][n] out
+  double* evecs; // [B][n][n] out
+  int32_t* status;
+  long long* dbg;
+};
+
+// A_out = 1/2 (A + A^T), 32 x 32 tiles
+__global__ void __launch_bounds__(256) k_lg_symcopy(int n, const double* __restrict__ Ain, double* __restrict__ Aout) {
+  __shared__ double t[32][33];
+  const size_t off = (size_t)blockIdx.z * n * n;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = j0 + r, j = i0 + tx;  // transposed tile
+    t[r][tx] = (i < n && j < n) ? Ain[off + (size_t)i * n + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + tx;
+    if (i < n && j < n) Aout[off + (size_t)i * n + j] = 0.5 * (Ain[off + (size_t)i * n + j] + t[tx][r]);
+  }
+}
+
+// ---- 1. tridiagonalisation, one cluster per matrix ---------------------------------------------
+__global__ void __launch_bounds__(LG_TRI_THREADS, 1) k_lg_tridiag(LgArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL;
+  const int n = a.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = LG_TRI_THREADS / 32;
+  const int np = (n + 3) & ~3;
+  extern __shared__ double sm[];
+  double* v = sm;        // pending reflector (indices k..n-1)
+  double* w = v + np;    // its w
+  double* vn = w + np;   // row k, then the new reflector
+  __shared__ double s_red[40];
+  double* A = a.A + (size_t)b * n * n;
+  double* Vh = a.Vh + (size_t)b * n * n;
+  double* pb0 = a.pbuf + (size_t)b * 2 * n;
+  double* pb1 = pb0 + n;
+  double tau_prev = 0.0;
+  const int W = CL * NW, gw = wid * CL + cr;
+
+  for (int k = 0; k < n; ++k) {
+    const bool pend = k > 0;
+    // (a) w = tau p - 1/2 tau^2 (p . v) v from the products the cluster wrote last column
+    if (pend) {
+      const double* p = (k & 1) ? pb1 : pb0;
+      double part = 0.0;
+      for (int j = k + tid; j < n; j += LG_TRI_THREADS) {
+        const double pj = p[j];
+        w[j] = pj;
+        part = fma(pj, v[j], part);
+      }
+      const double dot = block_sum(part, s_red);
+      const double c = 0.5 * tau_prev * tau_prev * dot;
+      for (int j = k + tid; j < n; j += LG_TRI_THREADS) w[j] = tau_prev * w[j] - c * v[j];
+      __syncthreads();
+    }
+    // (b) row k of the updated matrix, Householder vector for column k
+    const double* Ak = A + (size_t)k * n;
+    double x2 = 0.0;
+    {
+      const double vk = pend ? v[k] : 0.0, wk = pend ? w[k] : 0.0;
+      for (int j = k + tid; j < n; j += LG_TRI_THREADS) {
+        double r = Ak[j];
+        if (pend) r -= fma(vk, w[j], wk * v[j]);
+        vn[j] = r;
+        if (j >= k + 2) x2 = fma(r, r, x2);
+      }
+    }
+    x2 = block_sum(x2, s_red);
+    const double dk = vn[k];
+    const double alpha = (k + 1 < n) ? vn[k + 1] : 0.0;
+    double tau = 0.0, ek = alpha, scl = 0.0;
+    if (k <= n - 3 && x2 > 0.0) {
+      const double beta = -copysign(sqrt(fma(alpha, alpha, x2)), alpha);
+      tau = (beta - alpha) / beta;
+      scl = 1.0 / (alpha - beta);
+      ek = beta;
+    }
+    __syncthreads();
+    for (int j = k + 1 + tid; j < n; j += LG_TRI_THREADS) vn[j] = (j == k + 1) ? 1.0 : vn[j] * scl;
+    if (cr == 0 && tid == 0) {
+      a.dd[(size_t)b * n + k] = dk;
+      a.ee[(size_t)b * n + k] = (k + 1 < n) ? ek : 0.0;
+      a.tau[(size_t)b * n + k] = tau;
+    }
+    __syncthreads();
+    if (k == n - 1) break;
+    if (cr == 0)
+      for (int j = k + 1 + tid; j < n; j += LG_TRI_THREADS) Vh[(size_t)k * n + j] = vn[j];
+    // (c) own rows >= k+1: apply the pending rank-2 update, accumulate A v'
+    double* pw = ((k + 1) & 1) ? pb1 : pb0;
+    const int g0 = (k + 1) / LG_ROWS;
+    for (int g = g0 + gw; g * LG_ROWS < n; g += W) {
+      double acc[LG_ROWS], vi[LG_ROWS], wi[LG_ROWS];
+      double* Ar[LG_ROWS];
+      bool ok[LG_ROWS];
+#pragma unroll
+      for (int q = 0; q < LG_ROWS; ++q) {
+        const int r = g * LG_ROWS + q;
+        ok[q] = r >= k + 1 && r < n;
+        const int rc = ok[q] ? r : k + 1;
+        Ar[q] = A + (size_t)rc * n;
+        vi[q] = pend ? v[rc] : 0.0;
+        wi[q] = pend ? w[rc] : 0.0;
+        acc[q] = 0.0;
+      }
+      if (pend) {
+#pragma unroll 2
+        for (int j = k + 1 + lane; j < n; j += 32) {
+          const double vj = v[j], wj = w[j], vnj = vn[j];
+#pragma unroll
+          for (int q = 0; q < LG_ROWS; ++q) {
+            if (ok[q]) {
+              double x = Ar[q][j];
+              x = fma(-vi[q], wj, x);
+              x = fma(-wi[q], vj, x);
+              Ar[q][j] = x;
+              acc[q] = fma(x, vnj, acc[q]);
+            }
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int j = k + 1 + lane; j < n; j += 32) {
+          const double vnj = vn[j];
+#pragma unroll
+          for (int q = 0; q < LG_ROWS; ++q)
+            if (ok[q]) acc[q] = fma(Ar[q][j], vnj, acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < LG_ROWS; ++q) {
+        const double s = warp_sum(acc[q]);
+        if (ok[q] && lane == 0) pw[g * LG_ROWS + q] = s;
+      }
+    }
+    double* t = v;
+    v = vn;
+    vn = t;
+    tau_prev = tau;
+    cluster.sync();
+  }
+}
+
+// ---- 2. eigenpairs of T, one CTA per matrix ---------------------------------------------------
+__global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
+  constexpr int THREADS = LG_EIG_THREADS;
+  constexpr int NW = THREADS / 32;
+  extern __shared__ double sm[];
+  const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int np = (n + 3) & ~3;
+  double* d = sm;
+  double* e = d + np;
+  double* e2 = e + np;
+  double* lam = e2 + np;
+  double* X = lam + np;          // lo | hi, then nrm_up | nrm_dn, then dots (NW * 64 <= 2 np needs np >= 1024: separate)
+  double* dots = X + 2 * np;     // NW * 64
+  int* blk_s = (int*)(dots + NW * 64);
+  int* blk_e = blk_s + np;
+  int* cl_s = blk_e + np;
+  int* twist = cl_s + np;
+  int* cnts = twist + np;        // P * np
+  __shared__ double s_red[40];
+  __shared__ double s_tnorm;
+  __shared__ int s_fallback;
+  double* S = a.Z + (size_t)b * n * n;
+  double* Dm = a.Dm + (size_t)b * n * n;
+  const size_t lds = n;
+  int st_in = a.status ? a.status[b] : 0;
+  st_in &= ~(MOP_ST_EIG_FALLBACK | MOP_ST_EIG_NOCONV);
+  if (tid == 0) s_fallback = 0;
+  double tn = 0.0;
+  for (int i = tid; i < n; i += THREADS) {
+    d[i] = a.dd[(size_t)b * n + i];
+    e[i] = (i < n - 1) ? a.ee[(size_t)b * n + i] : 0.0;
+    tn = fmax(tn, fmax(fabs(d[i]), fabs(e[i])));
+    if (!isfinite(d[i]) || !isfinite(e[i])) tn = INFINITY;
+  }
+  tn = block_max(tn, s_red);
+  if (tid == 0) s_tnorm = tn;
+  const bool zero_t = tn == 0.0 || !isfinite(tn);
+  __syncthreads();
+  if (!zero_t) {
+    const double inv_tn = 1.0 / tn;
+    for (int i = tid; i < n; i += THREADS) {
+      d[i] *= inv_tn;
+      e[i] *= inv_tn;
+    }
+    __syncthreads();
+    for (int i = tid; i < n - 1; i += THREADS)
+      if (fabs(e[i]) <= TRI_EPS * (fabs(d[i]) + fabs(d[i + 1]))) e[i] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += THREADS) e2[i] = e[i] * e[i];
+    if (tid == 0) {
+      int s0 = 0;
+      for (int i = 0; i < n; ++i) {
+        blk_s[i] = s0;
+        if (i == n - 1 || e[i] == 0.0) {
+          for (int r = s0; r <= i; ++r) blk_e[r] = i + 1;
+          s0 = i + 1;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- bisection / multisection on the Sturm count ----
+    double* lo = X;
+    double* hi = X + np;
+    const int P = (3 * n <= THREADS) ? 3 : ((2 * n <= THREADS) ? 2 : 1);
+    for (int i = tid; i < n; i += THREADS) {
+      const int s = blk_s[i], t = blk_e[i];
+      double gl = INFINITY, gu = -INFINITY;
+      for (int r = s; r < t; ++r) {
+        const double rad = (r > s ? fabs(e[r - 1]) : 0.0) + (r < t - 1 ? fabs(e[r]) : 0.0);
+        gl = fmin(gl, d[r] - rad);
+        gu = fmax(gu, d[r] + rad);
+      }
+      const double pad = 4.0 * TRI_EPS * n * fmax(fabs(gl), fabs(gu)) + 1e-300;
+      lo[i] = gl - pad;
+      hi[i] = gu + pad;
+    }
+    __syncthreads();
+    const int i_own = tid % n, jpt = tid / n;
+    const bool worker = tid < P * n;
+    for (int round = 0; round < 120; ++round) {
+      int active = 0;
+      if (worker) {
+        const double l = lo[i_own], h = hi[i_own];
+        const double width = h - l;
+        if (width > 2.0 * TRI_EPS * fmax(fabs(l), fabs(h)) + 4e-3 * TRI_EPS) {
+          const double x = l + width * ((double)(jpt + 1) / (double)(P + 1));
+          if (x > l && x < h) {
+            active = 1;
+            cnts[jpt * np + i_own] = sturm_count(d, e2, blk_s[i_own], blk_e[i_own], x);
+          }
+        }
+        if (!active) cnts[jpt * np + i_own] = -1;
+      }
+      if (!__syncthreads_or(active)) break;
+      if (worker && jpt == 0) {
+        const int i = i_own;
+        const int want = i - blk_s[i] + 1;
+        const double l = lo[i], h = hi[i];
+        const double width = h - l;
+        double nl = l, nh = h;
+        for (int jj = 0; jj < P; ++jj) {
+          const int c = cnts[jj * np + i];
+          if (c < 0) continue;
+          const double xj = l + width * ((double)(jj + 1) / (double)(P + 1));
+          if (c >= want) {
+            nh = fmin(nh, xj);
+            break;
+          }
+          nl = fmax(nl, xj);
+        }
+        lo[i] = nl;
+        hi[i] = nh;
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < n; i += THREADS) lam[i] = 0.5 * (lo[i] + hi[i]);
+    __syncthreads();
+
+    // ---- twisted-factorisation eigenvectors, thread i owns column i of S ----
+    {
+      const double piv = TRI_EPS * 1e-3;
+      double* nrm_up = X;
+      double* nrm_dn = X + np;
+      for (int i = tid; i < n; i += THREADS) {
+        const int s = blk_s[i], t = blk_e[i];
+        const double l = lam[i];
+        for (int k = 0; k < n; ++k)
+          if (k < s || k >= t) S[k * lds + i] = 0.0;
+        double q = d[s] - l;
+        for (int k = s; k < t; ++k) {
+          if (fabs(q) < piv) q = (q <= 0.0) ? -piv : piv;
+          const double r = fast_rcp(q);
+          S[k * lds + i] = r;
+          if (k + 1 < t) q = fma(-e2[k], r, d[k + 1] - l);
+        }
+        q = d[t - 1] - l;
+        for (int k = t - 1; k >= s; --k) {
+          if (fabs(q) < piv) q = (q <= 0.0) ? -piv : piv;
+          const double r = fast_rcp(q);
+          Dm[k * lds + i] = r;
+          if (k > s) q = fma(-e2[k - 1], r, d[k - 1] - l);
+        }
+        // twist index: gamma_k = D+_k - e2_k / D-_{k+1}
+        double best = INFINITY;
+        int rr = s;
+        for (int k0 = s; k0 < t; k0 += 8) {
+          double rm[8], sp[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            rm[u] = (k0 + u + 1 < t) ? Dm[(k0 + u + 1) * lds + i] : 0.0;
+            sp[u] = (k0 + u > s && k0 + u < t) ? S[(k0 + u - 1) * lds + i] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u;
+            if (k < t) {
+              double dp = d[k] - l;
+              if (k > s) dp = fma(-e2[k - 1], sp[u], dp);
+              const double gam = fabs(fma(-e2[k], rm[u], dp));
+              if (gam < best) {
+                best = gam;
+                rr = k;
+              }
+            }
+          }
+        }
+        twist[i] = rr;
+        // z_r = 1; z_k = -e_k z_{k+1} / D+_k (k < r); z_k = -e_{k-1} z_{k-1} / D-_k (k > r)
+        double z = 1.0, au = 0.0;
+        for (int k0 = rr - 1; k0 >= s; k0 -= 8) {
+          double f[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] = (k0 - u >= s) ? -(e[k0 - u] * S[(k0 - u) * lds + i]) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (k0 - u >= s) {
+              z *= f[u];
+              S[(k0 - u) * lds + i] = z;
+              au = fma(z, z, au);
+            }
+          }
+        }
+        z = 1.0;
+        double ad = 0.0;
+        for (int k0 = rr + 1; k0 < t; k0 += 8) {
+          double f[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] = (k0 + u < t) ? -(e[k0 + u - 1] * Dm[(k0 + u) * lds + i]) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (k0 + u < t) {
+              z *= f[u];
+              S[(k0 + u) * lds + i] = z;
+              ad = fma(z, z, ad);
+            }
+          }
+        }
+        S[rr * lds + i] = 1.0;
+        const double sc = 1.0 / sqrt(1.0 + au + ad);
+        for (int k = s; k < t; ++k) S[k * lds + i] *= sc;
+        if (!isfinite(sc) || sc == 0.0) s_fallback = 1;
+        nrm_up[i] = au;
+        nrm_dn[i] = ad;
+      }
+    }
+    if (tid == 0) {
+      int cs = 0;
+      for (int i = 0; i < n; ++i) {
+        const bool chain = i > 0 && blk_s[i] == blk_s[i - 1] && (lam[i] - lam[i - 1]) < TRI_GAPTOL;
+        if (!chain) cs = i;
+        cl_s[i] = cs;
+      }
+    }
+    __syncthreads();
+    // ---- CGS2 inside clusters, one warp per cluster ----
+    for (int c0 = wid; c0 < n; c0 += NW) {
+      if (cl_s[c0] != c0) continue;
+      int cend = c0 + 1;
+      while (cend < n && cl_s[cend] == c0) ++cend;
+      if (cend - c0 < 2) continue;
+      const int s = blk_s[c0], t = blk_e[c0];
+      double* dw = dots + wid * 64;
+      for (int c = c0 + 1; c < cend; ++c) {
+        double nfirst = 1.0;
+        for (int rep = 0; rep < 2; ++rep) {
+          for (int p0 = c0; p0 < c; p0 += 64) {
+            const int pe = min(c, p0 + 64);
+            for (int p = p0; p < pe; ++p) {
+              double dt = 0.0;
+              for (int k = s + lane; k < t; k += 32) dt = fma(S[k * lds + p], S[k * lds + c], dt);
+              dt = warp_sum(dt);
+              if (lane == 0) dw[p - p0] = dt;
+            }
+            __syncwarp();
+            for (int k = s + lane; k < t; k += 32) {
+              double zc = S[k * lds + c];
+              for (int p = p0; p < pe; ++p) zc = fma(-dw[p - p0], S[k * lds + p], zc);
+              S[k * lds + c] = zc;
+            }
+            __syncwarp();
+          }
+          double nn = 0.0;
+          for (int k = s + lane; k < t; k += 32) nn = fma(S[k * lds + c], S[k * lds + c], nn);
+          nn = sqrt(warp_sum(nn));
+          if (rep == 0) nfirst = nn;
+          if (!(nn > 1e-2)) {
+            if (lane == 0) s_fallback = 1;
+          }
+          const double sc = nn > 0.0 ? 1.0 / nn : 0.0;
+          for (int k = s + lane; k < t; k += 32) S[k * lds + c] *= sc;
+          __syncwarp();
+          if (rep == 0 && nfirst > 0.7) break;
+        }
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int i = tid; i < n; i += THREADS) {
+      lam[i] = isfinite(tn) ? 0.0 : NAN;
+      for (int k = 0; k < n; ++k) S[k * lds + i] = (k == i) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+  }
+  // ascending rank over all blocks
+  int* rank = a.rank + (size_t)b * n;
+  const double tnorm = zero_t ? 1.0 : s_tnorm;
+  for (int i = tid; i < n; i += THREADS) {
+    const double li = lam[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += (lam[j] < li) || (lam[j] == li && j < i) || (li != li && j < i);
+    rank[i] = r;
+    a.evals[(size_t)b * n + r] = li * tnorm;
+  }
+  if (tid == 0 && a.status) a.status[b] = st_in | (s_fallback ? MOP_ST_EIG_FALLBACK : 0);
+}
+
+// ---- 3. V = Q Z, one warp per eigenvector -------------------------------------------------------
+template <int NPL>
+__global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a) {
+  constexpr int NW = LG_BT_THREADS / 32;
+  constexpr int CH = 4;  // reflectors staged per barrier
+  extern __shared__ double sm[];  // [2][CH][np]
+  const int n = a.n, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int np = (n + 3) & ~3;
+  const int i = blockIdx.x * NW + wid;  // vector (column of Z)
+  const bool live = i < n;
+  const double* S = a.Z + (size_t)b * n * n;
+  const double* Vh = a.Vh + (size_t)b * n * n;
+  const double* tau = a.tau + (size_t)b * n;
+  if (a.status && (a.status[b] & MOP_ST_EIG_FALLBACK)) return;  // the robust path redoes it
+  double z[NPL];
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    const int j = lane + 32 * q;
+    z[q] = (live && j < n) ? S[(size_t)j * n + i] : 0.0;
+  }
+  // reflectors n-3 .. 0 in chunks of CH (descending)
+  const int last = n - 3;
+  int buf = 0;
+  for (int kc = last; kc >= 0; kc -= CH) {
+    double* vb = sm + (size_t)buf * CH * np;
+    for (int u = 0; u < CH; ++u) {
+      const int k = kc - u;
+      if (k < 0) break;
+      for (int j = tid; j < n; j += LG_BT_THREADS) vb[u * np + j] = (j >= k + 1) ? Vh[(size_t)k * n + j] : 0.0;
+    }
+    __syncthreads();
+    for (int u = 0; u < CH; ++u) {
+      const int k = kc - u;
+      if (k < 0) break;
+      const double tk = tau[k];
+      if (tk == 0.0) continue;
+      const double* vk = vb + u * np;
+      const int q0 = (k + 1) >> 5;
+      double dot = 0.0;
+#pragma unroll
+      for (int q = 0; q < NPL; ++q)
+        if (q >= q0) dot = fma(lane + 32 * q < n ? vk[lane + 32 * q] : 0.0, z[q], dot);
+      dot = warp_sum(dot) * tk;
+#pragma unroll
+      for (int q = 0; q < NPL; ++q)
+        if (q >= q0) z[q] = fma(-dot, lane + 32 * q < n ? vk[lane + 32 * q] : 0.0, z[q]);
+    }
+    buf ^= 1;
+  }
+  if (!live) return;
+  const int r = a.rank[(size_t)b * n + i];
+  double* out = a.evecs + ((size_t)b * n + r) * n;
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    const int j = lane + 32 * q;
+    if (j < n) out[j] = z[q];
+  }
+}
+
+}  // namespace mop
+
+// ------------------------------------------------------------------------------------------------
+static size_t lg_al(size_t x) { return (x + 255) & ~(size_t)255; }
+static int g_lg_cluster = 0;
+extern "C" int mop_debug_large_cluster(int cl) {
+  g_lg_cluster = cl;
+  return MOP_OK;
+}
+static long long* g_lg_dbg = nullptr;
+
+int mop_large_supported(int n) { return n >= 3 && n <= mop::LG_MAX_N; }
+
+size_t mop_large_workspace_bytes(int B, int n) {
+  const size_t nn = lg_al(sizeof(double) * (size_t)B * n * n), nv = lg_al(sizeof(double) * (size_t)B * n);
+  return 4 * nn + 5 * nv + lg_al(sizeof(int) * (size_t)B * n);
+}
+
+template <int NPL>
+static int lg_launch_bt(int B, const mop::LgArgs& a, cudaStream_t stream) {
+  const int np = (a.n + 3) & ~3;
+  const size_t smem = sizeof(double) * 2 * 4 * (size_t)np;
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_backtransform<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((a.n + (mop::LG_BT_THREADS / 32) - 1) / (mop::LG_BT_THREADS / 32), B);
+  mop::k_lg_backtransform<NPL><<<grid, mop::LG_BT_THREADS, smem, stream>>>(a);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+// eigh for 160 < n <= 1024: evals ascending, evecs rows = eigenvectors.  Flags structures whose
+// clusters cancelled with MOP_ST_EIG_FALLBACK (caller runs the Jacobi kernel on those).
+int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* evecs, int32_t* status,
+                          void* work, size_t work_bytes, cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  if (!mop_large_supported(n)) {
+    mop_set_error("large-n eigensolver: n = %d not supported (3..%d)", n, mop::LG_MAX_N);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (!work || work_bytes < mop_large_workspace_bytes(B, n)) {
+    mop_set_error("large-n eigensolver: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  const size_t nn = lg_al(sizeof(double) * (size_t)B * n * n), nv = lg_al(sizeof(double) * (size_t)B * n);
+  char* w = (char*)work;
+  mop::LgArgs a{};
+  a.n = n;
+  a.A = (double*)w;
+  a.Vh = (double*)(w + nn);
+  a.Z = (double*)(w + 2 * nn);
+  a.Dm = (double*)(w + 3 * nn);
+  a.dd = (double*)(w + 4 * nn);
+  a.ee = (double*)(w + 4 * nn + nv);
+  a.tau = (double*)(w + 4 * nn + 2 * nv);
+  a.pbuf = (double*)(w + 4 * nn + 3 * nv);  // 2 nv
+  a.rank = (int*)(w + 4 * nn + 5 * nv);
+  a.evals = evals;
+  a.evecs = evecs;
+  a.status = status;
+  a.dbg = g_lg_dbg;
+  {
+    dim3 grid((n + 31) / 32, (n + 31) / 32, B);
+    mop::k_lg_symcopy<<<grid, 256, 0, stream>>>(n, A, a.A);
+    MOP_CHECK_CUDA(cudaGetLastError());
+  }
+  const int np = (n + 3) & ~3;
+  {
+    int CL = g_lg_cluster;
+    if (CL != 1 && CL != 2 && CL != 4 && CL != 8) CL = n >= 384 ? 8 : 4;
+    const size_t smem = sizeof(double) * 3 * (size_t)np;
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * CL));
+    cfg.blockDim = dim3(mop::LG_TRI_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag, a));
+  }
+  {
+    const int P = (3 * n <= mop::LG_EIG_THREADS) ? 3 : ((2 * n <= mop::LG_EIG_THREADS) ? 2 : 1);
+    const size_t smem = sizeof(double) * (6 * (size_t)np + (mop::LG_EIG_THREADS / 32) * 64) +
+                        sizeof(int) * (4 + P) * (size_t)np;
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mop::k_lg_trieig<<<B, mop::LG_EIG_THREADS, smem, stream>>>(a);
+    MOP_CHECK_CUDA(cudaGetLastError());
+  }
+  const int npl = (n + 31) / 32;
+  if (npl <= 8) return lg_launch_bt<8>(B, a, stream);
+  if (npl <= 12) return lg_launch_bt<12>(B, a, stream);
+  if (npl <= 16) return lg_launch_bt<16>(B, a, stream);
+  if (npl <= 20) return lg_launch_bt<20>(B, a, stream);
+  if (npl <= 24) return lg_launch_bt<24>(B, a, stream);
+  if (npl <= 28) return lg_launch_bt<28>(B, a, stream);
+  return lg_launch_bt<32>(B, a, stream);
+}

@@ -19,13 +19,12 @@
 //       O(n^3) work is the 4/3 n^3 of the reduction only.
 // Replaces numpy.linalg.eigh (LAPACK dsyevd) at Optimizer/rsirfo.py:606,626,652.
 #include "rfo_core.cuh"
+#include "tri_sturm.cuh"
 
 namespace mop {
 
 constexpr int TRI_MAX_N = 160;
 constexpr int TRI_GMAX = 16;         // max row-groups in the column-split symv / update
-constexpr double TRI_EPS = 2.220446049250313e-16;
-constexpr double TRI_GAPTOL = 1e-3;  // cluster gap relative to ||T|| (LAPACK dstein ORTOL)
 
 // size (in doubles) of the phase-aliased scratch region X
 __host__ __device__ inline size_t tri_x_doubles(int n) {
@@ -58,51 +57,6 @@ struct TriArgs {
   long long* dbg;    // optional [B][8] phase clocks (diagnostics)
   int ablate;        // diagnostics only: bit0 skip symv loop, bit1 skip update loop (results invalid)
 };
-
-// number of eigenvalues of the unreduced block rows [s, t) that are < x
-// (sign changes of p_k = (d_k - x) p_{k-1} - e_{k-1}^2 p_{k-2}); d, e2 scaled to ||T|| <= 1.
-// The dependent chain is one DFMA per row: (d_k - x) and the loads are hoisted four rows
-// ahead, signs are compared on the high word, and the magnitude is checked (and both
-// iterates rescaled) once per four rows.  An exact zero needs no special case: whichever
-// sign it is given, the pair (k-1, k+1) contributes exactly one sign change.
-__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2,
-                                           int s, int t, double x) {
-  double pm1 = 1.0;
-  double p = d[s] - x;
-  int cnt = (unsigned)__double2hiint(p) >> 31;
-  int k = s + 1;
-  for (; k + 3 < t; k += 4) {
-    const double a0 = d[k] - x, a1 = d[k + 1] - x, a2 = d[k + 2] - x, a3 = d[k + 3] - x;
-    const double b0 = e2[k - 1], b1 = e2[k], b2 = e2[k + 1], b3 = e2[k + 2];
-    const double p0 = fma(a0, p, -(b0 * pm1));
-    const double p1 = fma(a1, p0, -(b1 * p));
-    const double p2 = fma(a2, p1, -(b2 * p0));
-    const double p3 = fma(a3, p2, -(b3 * p1));
-    const int h = __double2hiint(p), h0 = __double2hiint(p0), h1 = __double2hiint(p1),
-              h2 = __double2hiint(p2), h3 = __double2hiint(p3);
-    cnt += ((unsigned)(h ^ h0) >> 31) + ((unsigned)(h0 ^ h1) >> 31) + ((unsigned)(h1 ^ h2) >> 31) +
-           ((unsigned)(h2 ^ h3) >> 31);
-    pm1 = p2;
-    p = p3;
-    const unsigned ex = ((unsigned)h3 >> 20) & 0x7ffu;
-    if (ex - 523u > 1000u) {  // |p| outside [2^-500, 2^500]: rare, even per warp
-      const double a = fmax(fabs(p), fabs(pm1));
-      if (a > 0.0 && a < INFINITY) {
-        const int ea = (__double2hiint(a) >> 20) & 0x7ff;          // biased exponent of a
-        const double sc = __hiloint2double((2046 - ea) << 20, 0);   // 2^(1023 - ea)
-        p *= sc;
-        pm1 *= sc;
-      }
-    }
-  }
-  for (; k < t; ++k) {
-    const double pn = fma(d[k] - x, p, -(e2[k - 1] * pm1));
-    cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31;
-    pm1 = p;
-    p = pn;
-  }
-  return cnt;
-}
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {

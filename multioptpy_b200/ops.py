@@ -23,7 +23,8 @@ UPDATE_DISPATCH = [
 ]
 UPD_NONE, UPD_FLOWCHART = 0, 1
 EIGH_AUTO, EIGH_JACOBI, EIGH_TRIDIAG = 0, 1, 2
-EIGH_ALGOS = {"auto": EIGH_AUTO, "jacobi": EIGH_JACOBI, "tridiag": EIGH_TRIDIAG}
+EIGH_LARGE = 3
+EIGH_ALGOS = {"auto": EIGH_AUTO, "jacobi": EIGH_JACOBI, "tridiag": EIGH_TRIDIAG, "large": EIGH_LARGE}
 RSIRFO_STATE = 16
 RS_TRUST, RS_HAVE_PREV, RS_PREV_ENERGY, RS_HAVE_ENERGY, RS_NPRED, RS_PRED0, RS_NACT, RS_ACT0, RS_ITER = (
     0, 1, 2, 3, 4, 5, 8, 9, 12)
