@@ -85,6 +85,16 @@ __global__ void __launch_bounds__(LG_TRI_THREADS, 1) k_lg_tridiag(LgArgs a) {
   double tau_prev = 0.0;
   const int W = CL * NW, gw = wid * CL + cr;
 
+  long long tacc[4] = {0, 0, 0, 0};
+  long long tp = clock64();
+#define LG_MARK(slot)                    \
+  do {                                   \
+    if (a.dbg) {                         \
+      const long long tnow = clock64();  \
+      tacc[slot] += tnow - tp;           \
+      tp = tnow;                         \
+    }                                    \
+  } while (0)
   for (int k = 0; k < n; ++k) {
     const bool pend = k > 0;
     // (a) w = tau p - 1/2 tau^2 (p . v) v from the products the cluster wrote last column
@@ -101,6 +111,7 @@ __global__ void __launch_bounds__(LG_TRI_THREADS, 1) k_lg_tridiag(LgArgs a) {
       for (int j = k + tid; j < n; j += LG_TRI_THREADS) w[j] = tau_prev * w[j] - c * v[j];
       __syncthreads();
     }
+    LG_MARK(0);
     // (b) row k of the updated matrix, Householder vector for column k
     const double* Ak = A + (size_t)k * n;
     double x2 = 0.0;
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(LG_TRI_THREADS, 1) k_lg_tridiag(LgArgs a) {
     if (k == n - 1) break;
     if (cr == 0)
       for (int j = k + 1 + tid; j < n; j += LG_TRI_THREADS) Vh[(size_t)k * n + j] = vn[j];
+    LG_MARK(1);
     // (c) own rows >= k+1: apply the pending rank-2 update, accumulate A v'
     double* pw = ((k + 1) & 1) ? pb1 : pb0;
     const int g0 = (k + 1) / LG_ROWS;
@@ -185,8 +197,184 @@ __global__ void __launch_bounds__(LG_TRI_THREADS, 1) k_lg_tridiag(LgArgs a) {
     v = vn;
     vn = t;
     tau_prev = tau;
+    LG_MARK(2);
     cluster.sync();
+    LG_MARK(3);
   }
+  if (a.dbg && tid == 0 && cr == 0)
+    for (int q = 0; q < 4; ++q) a.dbg[(size_t)b * 4 + q] = tacc[q];
+}
+
+
+// ---- 1'. tridiagonalisation, one cluster per matrix, rows owned by warps for the whole reduction ---
+// Warp gw = wid * CL + cr owns rows gw * R .. gw * R + R - 1 (R * CL * NW >= n), so no CTA ever
+// reads matrix elements another CTA wrote: the cluster exchanges only two n-vectors per column,
+// through distributed shared memory (A v' pushed into every CTA, the next pivot row pulled from its
+// owner), and the per-column critical path is two CTA barriers, one cluster barrier and the
+// L2 round trips of the fused update + symv, whose loads are issued UNR chunks deep.
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL;
+  const int n = a.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = THREADS / 32;
+  constexpr int UNR = (R <= 2) ? 8 : ((R <= 5) ? 4 : 2);
+  const int np = (n + 3) & ~3;
+  extern __shared__ double sm[];
+  double* vb = sm;             // [2][np] reflectors
+  double* pb = vb + 2 * np;    // [2][np] A v (filled by every warp of the cluster)
+  double* rowb = pb + 2 * np;  // [2][np] pivot row published by its owner
+  double* rcur = rowb + 2 * np;  // [np] pivot row of this column
+  __shared__ double s_rb[2 * 32];
+  int parity = 0;
+  double* A = a.A + (size_t)b * n * n;
+  double* Vh = a.Vh + (size_t)b * n * n;
+  const int gw = wid * CL + cr;
+  const int r0 = gw * R;
+  double tau_prev = 0.0;
+  int cur = 0;
+  long long tacc[4] = {0, 0, 0, 0};
+  long long tp = clock64();
+
+  if (r0 == 0) {  // owner of row 0 publishes it
+    for (int j = lane; j < n; j += 32) rowb[j] = A[j];
+  }
+  cluster.sync();
+
+  for (int k = 0; k < n; ++k) {
+    const bool pend = k > 0;
+    const double* v = vb + cur * np;
+    double* vnew = vb + (cur ^ 1) * np;
+    const double* p = pb + (k & 1) * np;
+    const int owner_cr = (k / R) % CL;
+    const double* rrow = cluster.map_shared_rank(rowb + (k & 1) * np, owner_cr);
+    // (1) pull the pivot row, p . v
+    double part[1] = {0.0};
+    for (int j = k + tid; j < n; j += THREADS) {
+      rcur[j] = rrow[j];
+      if (pend) part[0] = fma(p[j], v[j], part[0]);
+    }
+    block_sum_k<1>(part, s_rb, parity);
+    const double c = 0.5 * tau_prev * tau_prev * part[0];
+    LG_MARK(0);
+    // (2) row k through the pending reflector, its norm
+    double x2[1] = {0.0};
+    if (pend) {
+      const double vk = v[k], wk = fma(tau_prev, p[k], -c * vk);
+      for (int j = k + tid; j < n; j += THREADS) {
+        const double vj = v[j];
+        const double wj = fma(tau_prev, p[j], -c * vj);
+        const double r = rcur[j] - fma(vk, wj, wk * vj);
+        rcur[j] = r;
+        if (j >= k + 2) x2[0] = fma(r, r, x2[0]);
+      }
+    } else {
+      for (int j = k + 2 + tid; j < n; j += THREADS) x2[0] = fma(rcur[j], rcur[j], x2[0]);
+    }
+    block_sum_k<1>(x2, s_rb, parity);
+    const double dk = rcur[k];
+    const double alpha = (k + 1 < n) ? rcur[k + 1] : 0.0;
+    double tau = 0.0, ek = alpha, scl = 0.0;
+    if (k <= n - 3 && x2[0] > 0.0) {
+      const double beta = -copysign(sqrt(fma(alpha, alpha, x2[0])), alpha);
+      tau = (beta - alpha) / beta;
+      scl = 1.0 / (alpha - beta);
+      ek = beta;
+    }
+    if (cr == 0 && tid == 0) {
+      a.dd[(size_t)b * n + k] = dk;
+      a.ee[(size_t)b * n + k] = (k + 1 < n) ? ek : 0.0;
+      a.tau[(size_t)b * n + k] = tau;
+    }
+    if (k == n - 1) break;
+    for (int j = k + 1 + tid; j < n; j += THREADS) {
+      const double vj = (j == k + 1) ? 1.0 : rcur[j] * scl;
+      vnew[j] = vj;
+      if (cr == 0) Vh[(size_t)k * n + j] = vj;
+    }
+    LG_MARK(1);
+    // (3) own rows >= k+1: pending rank-2 update fused with A v'
+    if (r0 + R - 1 >= k + 1 && r0 < n) {
+      double acc[R], vi[R], wi[R];
+      double* Ar[R];
+      bool ok[R];
+      int qpub = -1;  // row k+1 is published for the next column
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int r = r0 + q;
+        ok[q] = r >= k + 1 && r < n;
+        const int rc = ok[q] ? r : k + 1;
+        Ar[q] = A + (size_t)rc * n;
+        vi[q] = pend ? v[rc] : 0.0;
+        wi[q] = pend ? fma(tau_prev, p[rc], -c * vi[q]) : 0.0;
+        acc[q] = 0.0;
+        if (r == k + 1) qpub = q;
+      }
+      double* rpub = rowb + ((k + 1) & 1) * np;
+      for (int j0 = (k + 1) & ~31; j0 < n; j0 += 32 * UNR) {
+        double x[R][UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int j = j0 + 32 * u + lane;
+          const bool inb = j >= k + 1 && j < n;
+#pragma unroll
+          for (int q = 0; q < R; ++q) x[q][u] = (inb && ok[q]) ? Ar[q][j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int j = j0 + 32 * u + lane;
+          if (j >= k + 1 && j < n) {
+            const double vnj = (j == k + 1) ? 1.0 : rcur[j] * scl;
+            double vj = 0.0, wj = 0.0;
+            if (pend) {
+              vj = v[j];
+              wj = fma(tau_prev, p[j], -c * vj);
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              if (ok[q]) {
+                double xx = x[q][u];
+                if (pend) {
+                  xx = fma(-vi[q], wj, xx);
+                  xx = fma(-wi[q], vj, xx);
+                  Ar[q][j] = xx;
+                }
+                if (q == qpub) rpub[j] = xx;
+                acc[q] = fma(xx, vnj, acc[q]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) acc[q] = warp_sum(acc[q]);
+      // push p'[own rows] into every CTA of the cluster
+      for (int idx = lane; idx < R * CL; idx += 32) {
+        const int q = idx / CL, t = idx - q * CL;
+        double val = 0.0;
+        bool okq = false;
+#pragma unroll
+        for (int qq = 0; qq < R; ++qq)
+          if (qq == q) {
+            val = acc[qq];
+            okq = ok[qq];
+          }
+        if (okq) {
+          double* dst = cluster.map_shared_rank(pb + ((k + 1) & 1) * np, t);
+          dst[r0 + q] = val;
+        }
+      }
+    }
+    cur ^= 1;
+    tau_prev = tau;
+    LG_MARK(2);
+    cluster.sync();
+    LG_MARK(3);
+  }
+  cluster.sync();  // nobody leaves while its shared memory may still be read
+  if (a.dbg && tid == 0 && cr == 0)
+    for (int q = 0; q < 4; ++q) a.dbg[(size_t)b * 4 + q] = tacc[q];
 }
 
 // ---- 2. eigenpairs of T, one CTA per matrix ---------------------------------------------------
@@ -524,6 +712,90 @@ __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a)
   }
 }
 
+
+// ---- 4. factored form: Zt (rows = eigenvectors of T, ascending) and x <- Q x / Q^T x -------------
+// Consumers that only need V^T g and V c (the RFO / P-RFO steps) rotate their vectors into the
+// basis of T instead of forming V = Q Z: O(n^2) per vector instead of the 2 n^3 back-transform.
+__global__ void __launch_bounds__(256) k_lg_transpose_sorted(int n, const double* __restrict__ Z,
+                                                             const int* __restrict__ rank, double* __restrict__ Zt) {
+  __shared__ double t[32][33];
+  const size_t off = (size_t)blockIdx.z * n * n;
+  const int* rk = rank + (size_t)blockIdx.z * n;
+  const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, i = i0 + tx;
+    t[r][tx] = (k < n && i < n) ? Z[off + (size_t)k * n + i] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, k = k0 + tx;
+    if (i < n && k < n) Zt[off + (size_t)rk[i] * n + k] = t[tx][r];
+  }
+}
+
+struct LgVecs {
+  double* x[4];  // each [B][n]
+  int m;
+};
+
+// warp w of CTA b transforms x[w][b]: trans = 1: Q^T x (reflectors ascending), 0: Q x (descending)
+template <int NPL>
+__global__ void __launch_bounds__(128) k_lg_apply_q(int n, int trans, const double* __restrict__ Vh_all,
+                                                    const double* __restrict__ tau_all, LgVecs X) {
+  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (wid >= X.m) return;
+  const double* Vh = Vh_all + (size_t)b * n * n;
+  const double* tau = tau_all + (size_t)b * n;
+  double* x = X.x[wid] + (size_t)b * n;
+  double z[NPL], vc[NPL], vn[NPL];
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    const int j = lane + 32 * q;
+    z[q] = j < n ? x[j] : 0.0;
+  }
+  const int nref = n - 2;  // reflectors 0 .. n-3
+  if (nref <= 0) return;
+  auto load = [&](int k, double* dst) {
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      const int j = lane + 32 * q;
+      dst[q] = (j >= k + 1 && j < n) ? Vh[(size_t)k * n + j] : 0.0;
+    }
+  };
+  int k = trans ? 0 : nref - 1;
+  const int step = trans ? 1 : -1;
+  load(k, vc);
+  for (int it = 0; it < nref; ++it) {
+    const int kn = k + step;
+    if (it + 1 < nref) load(kn, vn);
+    const double tk = tau[k];
+    if (tk != 0.0) {
+      double dot = 0.0;
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) dot = fma(vc[q], z[q], dot);
+      dot = warp_sum(dot) * tk;
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) z[q] = fma(-dot, vc[q], z[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) vc[q] = vn[q];
+    k = kn;
+  }
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) {
+    const int j = lane + 32 * q;
+    if (j < n) x[j] = z[q];
+  }
+}
+
+// structures redone by the Jacobi kernel get Q = I (their vectors are in the original basis)
+__global__ void k_lg_clear_tau_flagged(int n, const int32_t* __restrict__ status, double* __restrict__ tau) {
+  const int b = blockIdx.x;
+  if (!(status[b] & MOP_ST_EIG_FALLBACK)) return;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tau[(size_t)b * n + i] = 0.0;
+}
+
 }  // namespace mop
 
 // ------------------------------------------------------------------------------------------------
@@ -534,6 +806,12 @@ extern "C" int mop_debug_large_cluster(int cl) {
   return MOP_OK;
 }
 static long long* g_lg_dbg = nullptr;
+// diagnostics: device buffer [B][4] receiving the cycles one CTA of each cluster spent in the
+// column phases (w, Householder, update + symv, cluster barrier) of the next launches
+extern "C" int mop_debug_large_timing(void* buf) {
+  g_lg_dbg = (long long*)buf;
+  return MOP_OK;
+}
 
 int mop_large_supported(int n) { return n >= 3 && n <= mop::LG_MAX_N; }
 
@@ -553,22 +831,9 @@ static int lg_launch_bt(int B, const mop::LgArgs& a, cudaStream_t stream) {
   return MOP_OK;
 }
 
-// eigh for 160 < n <= 1024: evals ascending, evecs rows = eigenvectors.  Flags structures whose
-// clusters cancelled with MOP_ST_EIG_FALLBACK (caller runs the Jacobi kernel on those).
-int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* evecs, int32_t* status,
-                          void* work, size_t work_bytes, cudaStream_t stream) {
-  if (B == 0) return MOP_OK;
-  if (!mop_large_supported(n)) {
-    mop_set_error("large-n eigensolver: n = %d not supported (3..%d)", n, mop::LG_MAX_N);
-    return MOP_ERR_UNSUPPORTED;
-  }
-  if (!work || work_bytes < mop_large_workspace_bytes(B, n)) {
-    mop_set_error("large-n eigensolver: workspace too small");
-    return MOP_ERR_WORKSPACE;
-  }
+static void lg_carve(int B, int n, void* work, mop::LgArgs& a) {
   const size_t nn = lg_al(sizeof(double) * (size_t)B * n * n), nv = lg_al(sizeof(double) * (size_t)B * n);
   char* w = (char*)work;
-  mop::LgArgs a{};
   a.n = n;
   a.A = (double*)w;
   a.Vh = (double*)(w + nn);
@@ -579,8 +844,22 @@ int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* 
   a.tau = (double*)(w + 4 * nn + 2 * nv);
   a.pbuf = (double*)(w + 4 * nn + 3 * nv);  // 2 nv
   a.rank = (int*)(w + 4 * nn + 5 * nv);
+}
+
+// A = Q T Q^T and the eigenpairs of T: leaves reflectors (Vh, tau), Z (columns) and rank in `work`.
+static int lg_factor(int B, int n, const double* A, double* evals, int32_t* status, void* work, size_t work_bytes,
+                     mop::LgArgs& a, cudaStream_t stream) {
+  if (!mop_large_supported(n)) {
+    mop_set_error("large-n eigensolver: n = %d not supported (3..%d)", n, mop::LG_MAX_N);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (!work || work_bytes < mop_large_workspace_bytes(B, n)) {
+    mop_set_error("large-n eigensolver: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  lg_carve(B, n, work, a);
   a.evals = evals;
-  a.evecs = evecs;
+  a.evecs = nullptr;
   a.status = status;
   a.dbg = g_lg_dbg;
   {
@@ -591,13 +870,11 @@ int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* 
   const int np = (n + 3) & ~3;
   {
     int CL = g_lg_cluster;
-    if (CL != 1 && CL != 2 && CL != 4 && CL != 8) CL = n >= 384 ? 8 : 4;
-    const size_t smem = sizeof(double) * 3 * (size_t)np;
-    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool legacy = CL < 0;  // diagnostics: the first-generation kernel (negative cluster size)
+    if (legacy) CL = -CL;
+    if (CL != 1 && CL != 2 && CL != 4 && CL != 8) CL = 8;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CL));
-    cfg.blockDim = dim3(mop::LG_TRI_THREADS);
-    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -606,7 +883,33 @@ int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag, a));
+    constexpr int T2 = 512;
+    const int W = CL * (T2 / 32);
+    const int R = (n + W - 1) / W;
+    if (legacy || R > 8) {
+      const size_t smem = sizeof(double) * 3 * (size_t)np;
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg.blockDim = dim3(mop::LG_TRI_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag, a));
+    } else {
+      const size_t smem = sizeof(double) * 7 * (size_t)np;
+      cfg.blockDim = dim3(T2);
+      cfg.dynamicSmemBytes = smem;
+#define LG_LAUNCH2(RR)                                                                                          \
+  do {                                                                                                          \
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag2<RR, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                            \
+    MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag2<RR, T2>, a));                                     \
+  } while (0)
+      if (R <= 2) LG_LAUNCH2(2);
+      else if (R == 3) LG_LAUNCH2(3);
+      else if (R == 4) LG_LAUNCH2(4);
+      else if (R == 5) LG_LAUNCH2(5);
+      else if (R == 6) LG_LAUNCH2(6);
+      else LG_LAUNCH2(8);
+#undef LG_LAUNCH2
+    }
   }
   {
     const int P = (3 * n <= mop::LG_EIG_THREADS) ? 3 : ((2 * n <= mop::LG_EIG_THREADS) ? 2 : 1);
@@ -616,6 +919,18 @@ int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* 
     mop::k_lg_trieig<<<B, mop::LG_EIG_THREADS, smem, stream>>>(a);
     MOP_CHECK_CUDA(cudaGetLastError());
   }
+  return MOP_OK;
+}
+
+// eigh for 160 < n <= 1024: evals ascending, evecs rows = eigenvectors.  Flags structures whose
+// clusters cancelled with MOP_ST_EIG_FALLBACK (caller runs the Jacobi kernel on those).
+int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* evecs, int32_t* status,
+                          void* work, size_t work_bytes, cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  mop::LgArgs a{};
+  int rc = lg_factor(B, n, A, evals, status, work, work_bytes, a, stream);
+  if (rc != MOP_OK) return rc;
+  a.evecs = evecs;
   const int npl = (n + 31) / 32;
   if (npl <= 8) return lg_launch_bt<8>(B, a, stream);
   if (npl <= 12) return lg_launch_bt<12>(B, a, stream);
@@ -624,4 +939,49 @@ int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* 
   if (npl <= 24) return lg_launch_bt<24>(B, a, stream);
   if (npl <= 28) return lg_launch_bt<28>(B, a, stream);
   return lg_launch_bt<32>(B, a, stream);
+}
+
+// Factored eigendecomposition: evals ascending, Zt [B][n][n] rows = eigenvectors of T in the same
+// order; A = Q (Zt^T diag(evals) Zt) Q^T with Q kept in `work` for mop_launch_large_apply_q.
+// Structures flagged MOP_ST_EIG_FALLBACK get Q = I here; the caller runs the Jacobi kernel on them
+// with Zt as its eigenvector output.
+int mop_launch_eigh_large_factored(int B, int n, const double* A, double* evals, double* Zt, int32_t* status,
+                                   void* work, size_t work_bytes, cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  mop::LgArgs a{};
+  int rc = lg_factor(B, n, A, evals, status, work, work_bytes, a, stream);
+  if (rc != MOP_OK) return rc;
+  dim3 grid((n + 31) / 32, (n + 31) / 32, B);
+  mop::k_lg_transpose_sorted<<<grid, 256, 0, stream>>>(n, a.Z, a.rank, Zt);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  mop::k_lg_clear_tau_flagged<<<B, 256, 0, stream>>>(n, status, a.tau);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+template <int NPL>
+static int lg_launch_apply(int B, int n, int trans, const mop::LgArgs& a, const mop::LgVecs& X, cudaStream_t stream) {
+  mop::k_lg_apply_q<NPL><<<B, 128, 0, stream>>>(n, trans, a.Vh, a.tau, X);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+// x_i <- Q^T x_i (trans = 1) or Q x_i (trans = 0) for up to four [B][n] vectors, Q from the
+// last mop_launch_eigh_large_factored on the same workspace.
+int mop_launch_large_apply_q(int B, int n, int trans, void* work, double* x0, double* x1, double* x2, double* x3,
+                             cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  mop::LgArgs a{};
+  lg_carve(B, n, work, a);
+  mop::LgVecs X{};
+  double* xs[4] = {x0, x1, x2, x3};
+  X.m = 0;
+  for (int i = 0; i < 4; ++i)
+    if (xs[i]) X.x[X.m++] = xs[i];
+  if (X.m == 0) return MOP_OK;
+  const int npl = (n + 31) / 32;
+  if (npl <= 8) return lg_launch_apply<8>(B, n, trans, a, X, stream);
+  if (npl <= 16) return lg_launch_apply<16>(B, n, trans, a, X, stream);
+  if (npl <= 24) return lg_launch_apply<24>(B, n, trans, a, X, stream);
+  return lg_launch_apply<32>(B, n, trans, a, X, stream);
 }

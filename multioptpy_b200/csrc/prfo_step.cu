@@ -437,13 +437,28 @@ extern "C" size_t mop_eigh_workspace_bytes(int B, int n, int algo);
 extern "C" int mop_eigh(int B, int n, int algo, const double* A, double* evals, double* evecs,
                         int32_t* status, void* work, size_t work_bytes, void* stream);
 
-static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t mop_jacobi_workspace_bytes(int B, int n);
+int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double* evecs, int32_t* status,
+                           const int32_t* only_flagged, void* work, size_t work_bytes, cudaStream_t stream);
+int mop_tridiag_supported(int n);
+int mop_large_supported(int n);
+int mop_launch_eigh_large_factored(int B, int n, const double* A, double* evals, double* Zt, int32_t* status,
+                                   void* work, size_t work_bytes, cudaStream_t stream);
+int mop_launch_large_apply_q(int B, int n, int trans, void* work, double* x0, double* x1, double* x2, double* x3,
+                             cudaStream_t stream);
 
-// workspace: Hp/A | evecs | evals | gp | eigh work
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+// large systems: the step is taken in the basis of the tridiagonal matrix (eigh_large.cu, part 4)
+static bool prfo_factored(int n, int eigh_algo) {
+  if (eigh_algo == MOP_EIGH_LARGE) return mop_large_supported(n) != 0;
+  return eigh_algo == MOP_EIGH_AUTO && !mop_tridiag_supported(n) && mop_large_supported(n);
+}
+
+// workspace: Hp/A | evecs | evals | gp | 4 rotated vectors | eigh work
 extern "C" size_t mop_rsprfo_workspace_bytes(int B, int n, int eigh_algo) {
   if (B <= 0 || n <= 0) return 0;
   const size_t nn = al256(sizeof(double) * (size_t)B * n * n), nv = al256(sizeof(double) * (size_t)B * n);
-  return 2 * nn + 2 * nv + mop_eigh_workspace_bytes(B, n, eigh_algo);
+  return 2 * nn + 6 * nv + mop_eigh_workspace_bytes(B, n, prfo_factored(n, eigh_algo) ? MOP_EIGH_LARGE : eigh_algo);
 }
 
 extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int eigh_algo, double trust_min,
@@ -469,8 +484,13 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
   double* evecs = (double*)(w + nn);
   double* evals = (double*)(w + 2 * nn);
   double* gp = (double*)(w + 2 * nn + nv);
-  void* ework = w + 2 * nn + 2 * nv;
-  const size_t ebytes = work_bytes - (2 * nn + 2 * nv);
+  double* Xg = (double*)(w + 2 * nn + 2 * nv);
+  double* Xts = (double*)(w + 2 * nn + 3 * nv);
+  double* Xmv = (double*)(w + 2 * nn + 4 * nv);
+  double* Xpm = (double*)(w + 2 * nn + 5 * nv);
+  char* ework = w + 2 * nn + 6 * nv;
+  const size_t ebytes = work_bytes - (2 * nn + 6 * nv);
+  const bool factored = prfo_factored(n, eigh_algo);
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   // projected gradient (current geometry) and projected pre-update Hessian for the reduction ratio
   int rc = mop_launch_project_trrot(B, n, H, Hbias, x, Bg, A, gp, status, stream);
@@ -491,8 +511,21 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
     mop::k_sum_sym<<<grid, 256, 0, stream>>>(n, H, Hbias, A);
     MOP_CHECK_CUDA(cudaGetLastError());
   }
-  rc = mop_eigh(B, n, eigh_algo, A, evals, evecs, status, ework, ebytes, stream);
-  if (rc != MOP_OK) return rc;
+  const size_t vbytes = sizeof(double) * (size_t)B * n;
+  if (factored) {
+    const size_t jac = al256(mop_jacobi_workspace_bytes(B, n));
+    rc = mop_launch_eigh_large_factored(B, n, A, evals, evecs, status, ework + jac, ebytes - jac, stream);
+    if (rc != MOP_OK) return rc;
+    rc = mop_launch_eigh_jacobi(B, n, A, evals, evecs, status, status, ework, jac, stream);
+    if (rc != MOP_OK) return rc;
+    MOP_CHECK_CUDA(cudaMemcpyAsync(Xg, gp, vbytes, cudaMemcpyDeviceToDevice, stream));
+    MOP_CHECK_CUDA(cudaMemcpyAsync(Xts, ts_vec, vbytes, cudaMemcpyDeviceToDevice, stream));
+    rc = mop_launch_large_apply_q(B, n, 1, ework + jac, Xg, Xts, nullptr, nullptr, stream);
+    if (rc != MOP_OK) return rc;
+  } else {
+    rc = mop_eigh(B, n, eigh_algo, A, evals, evecs, status, ework, ebytes, stream);
+    if (rc != MOP_OK) return rc;
+  }
   const int np = (n + 3) & ~3;
   const size_t smem = sizeof(double) * (7 * (size_t)np + 40) + sizeof(int) * 2 * (size_t)np + (size_t)np + 16;
   if (smem > 200 * 1024) {
@@ -500,6 +533,19 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
     return MOP_ERR_UNSUPPORTED;
   }
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_prfo_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (factored) {
+    mop::k_prfo_step<<<B, mop::PRFO_THREADS, smem, stream>>>(n, saddle_order, trust_min, trust_max, evals, evecs, Xg,
+                                                           Bg, Be, state, prev_grad, Xpm, Xts, Xmv, eigvals_out,
+                                                           pred_out, status);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    const size_t jac = al256(mop_jacobi_workspace_bytes(B, n));
+    rc = mop_launch_large_apply_q(B, n, 0, ework + jac, Xmv, Xts, nullptr, nullptr, stream);
+    if (rc != MOP_OK) return rc;
+    MOP_CHECK_CUDA(cudaMemcpyAsync(move_out, Xmv, vbytes, cudaMemcpyDeviceToDevice, stream));
+    MOP_CHECK_CUDA(cudaMemcpyAsync(prev_move, Xmv, vbytes, cudaMemcpyDeviceToDevice, stream));
+    MOP_CHECK_CUDA(cudaMemcpyAsync(ts_vec, Xts, vbytes, cudaMemcpyDeviceToDevice, stream));
+    return MOP_OK;
+  }
   mop::k_prfo_step<<<B, mop::PRFO_THREADS, smem, stream>>>(n, saddle_order, trust_min, trust_max, evals, evecs, gp,
                                                          Bg, Be, state, prev_grad, prev_move, ts_vec, move_out,
                                                          eigvals_out, pred_out, status);
