@@ -19,6 +19,8 @@
 // and Optimizer/rsirfo.py:606 for large systems.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "tri_sturm.cuh"
 
 namespace cg = cooperative_groups;
@@ -30,6 +32,10 @@ constexpr int LG_TRI_THREADS = 1024;
 constexpr int LG_EIG_THREADS = 1024;
 constexpr int LG_BT_THREADS = 512;
 constexpr int LG_ROWS = 4;  // rows per warp in the fused update + symv
+// Re-orthogonalisation threshold on eigenvalue gaps relative to ||T||.  A twisted-factorisation
+// vector is accurate to about eps ||T|| / gap, so neighbours further apart than this are orthogonal
+// to ~1e-12 already; dstein's 1e-3 would chain most of a dense 600-eigenvalue spectrum.
+constexpr double LG_GAPTOL = 3e-4;
 
 struct LgArgs {
   int n;
@@ -46,6 +52,7 @@ struct LgArgs {
   double* evecs; // [B][n][n] out
   int32_t* status;
   long long* dbg;
+  int ablate;  // diagnostics: bit0 skip the trailing stores, bit1 skip the trailing loads (results invalid)
 };
 
 // A_out = 1/2 (A + A^T), 32 x 32 tiles
@@ -207,11 +214,92 @@ __global__ void __launch_bounds__(LG_TRI_THREADS, 1) k_lg_tridiag(LgArgs a) {
 
 
 // ---- 1'. tridiagonalisation, one cluster per matrix, rows owned by warps for the whole reduction ---
-// Warp gw = wid * CL + cr owns rows gw * R .. gw * R + R - 1 (R * CL * NW >= n), so no CTA ever
+// Every row of the matrix is owned by one warp of the cluster for the whole reduction, so no CTA ever
 // reads matrix elements another CTA wrote: the cluster exchanges only two n-vectors per column,
 // through distributed shared memory (A v' pushed into every CTA, the next pivot row pulled from its
-// owner), and the per-column critical path is two CTA barriers, one cluster barrier and the
+// owner), and the per-column critical path is three CTA barriers, one cluster barrier and the
 // L2 round trips of the fused update + symv, whose loads are issued UNR chunks deep.
+
+// RL live rows  first, first + rs, ...  of one warp (rs = row stride in elements), columns k+1 .. n-1:
+//   A[r][j] -= v_r w_j + w_r v_j ;  acc_r += A[r][j] vn_j ;  PUB: row `first` = k+1 is copied to rpub.
+template <int RL, bool PUB>
+__device__ __forceinline__ void lg_update_symv(double* __restrict__ base, size_t rs, int n, int k, int lane,
+                                               const double (&vi)[RL], const double (&wi)[RL],
+                                               const double* __restrict__ v, const double* __restrict__ wv,
+                                               const double* __restrict__ vn, double* __restrict__ rpub,
+                                               double (&acc)[RL], int abl = 0) {
+  // loads in flight per lane: RL * UNR doubles; the whole row set of a column in one to three round trips
+  constexpr int UNR = (RL <= 3) ? 8 : ((RL == 4) ? 6 : ((RL == 5) ? 5 : ((RL == 6) ? 4 : 3)));
+#pragma unroll
+  for (int q = 0; q < RL; ++q) acc[q] = 0.0;
+  const int jlo = k + 1;
+  auto block = [&](int j0, auto nu_tag, auto pred_tag) {
+    constexpr int NU = decltype(nu_tag)::value;
+    constexpr bool PRED = decltype(pred_tag)::value;
+    double x[RL][NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int j = j0 + 32 * u + lane;
+      const bool inb = !PRED || (j >= jlo && j < n);
+#pragma unroll
+      for (int q = 0; q < RL; ++q) x[q][u] = (inb && !(abl & 2)) ? base[(size_t)q * rs + j] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int j = j0 + 32 * u + lane;
+      const bool inb = !PRED || (j >= jlo && j < n);
+      if (inb) {
+        const double vj = v[j], wj = wv[j], vnj = vn[j];
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+          double xx = x[q][u];
+          xx = fma(-vi[q], wj, xx);
+          xx = fma(-wi[q], vj, xx);
+          if (!(abl & 1)) base[(size_t)q * rs + j] = xx;
+          if (PUB && q == 0) rpub[j] = xx;
+          acc[q] = fma(xx, vnj, acc[q]);
+        }
+      }
+    }
+  };
+  using one = std::integral_constant<int, 1>;
+  using many = std::integral_constant<int, UNR>;
+  (void)sizeof(one);
+  for (int j0 = jlo & ~31; j0 < n; j0 += 32 * UNR) block(j0, many{}, std::true_type{});
+#pragma unroll
+  for (int q = 0; q < RL; ++q) acc[q] = warp_sum(acc[q]);
+}
+
+// step (3) of one warp: RL live rows starting at `first`; pushes A v' for them into every CTA
+template <int RL>
+__device__ __forceinline__ void lg_step3(cg::cluster_group& cluster, int CL, double* A, int n, int k, int first, int W,
+                                         int lane, const double* v, const double* wv, const double* vn,
+                                         double* rpub, double* pnext, int abl) {
+  double acc[RL], vi[RL], wi[RL];
+#pragma unroll
+  for (int q = 0; q < RL; ++q) {
+    vi[q] = v[first + q * W];
+    wi[q] = wv[first + q * W];
+  }
+  double* base = A + (size_t)first * n;
+  const size_t rs = (size_t)W * n;
+  if (first == k + 1)
+    lg_update_symv<RL, true>(base, rs, n, k, lane, vi, wi, v, wv, vn, rpub, acc, abl);
+  else
+    lg_update_symv<RL, false>(base, rs, n, k, lane, vi, wi, v, wv, vn, rpub, acc, abl);
+  for (int idx = lane; idx < RL * CL; idx += 32) {
+    const int q = idx / CL, t = idx - q * CL;
+    double val = 0.0;
+#pragma unroll
+    for (int qq = 0; qq < RL; ++qq)
+      if (qq == q) val = acc[qq];
+    double* dst = cluster.map_shared_rank(pnext, t);
+    dst[first + q * W] = val;
+  }
+}
+
+// Warp gw = wid * CL + cr owns rows gw, gw + W, gw + 2 W, ... (W = CL * NW warps in the cluster, at
+// most R rows each): live rows stay evenly spread over all warps while the trailing matrix shrinks.
 template <int R, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -219,26 +307,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
   const int b = blockIdx.x / CL;
   const int n = a.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NW = THREADS / 32;
-  constexpr int UNR = (R <= 2) ? 8 : ((R <= 5) ? 4 : 2);
   const int np = (n + 3) & ~3;
   extern __shared__ double sm[];
-  double* vb = sm;             // [2][np] reflectors
-  double* pb = vb + 2 * np;    // [2][np] A v (filled by every warp of the cluster)
-  double* rowb = pb + 2 * np;  // [2][np] pivot row published by its owner
+  double* vb = sm;               // [2][np] reflectors
+  double* pb = vb + 2 * np;      // [2][np] A v (filled by every warp of the cluster)
+  double* rowb = pb + 2 * np;    // [2][np] pivot row published by its owner
   double* rcur = rowb + 2 * np;  // [np] pivot row of this column
+  double* wv = rcur + np;        // [np] w of the pending reflector
   __shared__ double s_rb[2 * 32];
   int parity = 0;
   double* A = a.A + (size_t)b * n * n;
   double* Vh = a.Vh + (size_t)b * n * n;
-  const int gw = wid * CL + cr;
-  const int r0 = gw * R;
+  const int W = CL * NW, gw = wid * CL + cr;
   double tau_prev = 0.0;
   int cur = 0;
   long long tacc[4] = {0, 0, 0, 0};
   long long tp = clock64();
 
-  if (r0 == 0) {  // owner of row 0 publishes it
+  if (gw == 0) {  // owner of row 0 publishes it
     for (int j = lane; j < n; j += 32) rowb[j] = A[j];
+  }
+  for (int j = tid; j < np; j += THREADS) {  // column 0 has no pending reflector: v = w = 0
+    vb[j] = 0.0;
+    wv[j] = 0.0;
   }
   cluster.sync();
 
@@ -247,8 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
     const double* v = vb + cur * np;
     double* vnew = vb + (cur ^ 1) * np;
     const double* p = pb + (k & 1) * np;
-    const int owner_cr = (k / R) % CL;
-    const double* rrow = cluster.map_shared_rank(rowb + (k & 1) * np, owner_cr);
+    const double* rrow = cluster.map_shared_rank(rowb + (k & 1) * np, k % CL);
     // (1) pull the pivot row, p . v
     double part[1] = {0.0};
     for (int j = k + tid; j < n; j += THREADS) {
@@ -258,13 +348,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
     block_sum_k<1>(part, s_rb, parity);
     const double c = 0.5 * tau_prev * tau_prev * part[0];
     LG_MARK(0);
-    // (2) row k through the pending reflector, its norm
+    // (2) w, row k through the pending reflector, its norm
     double x2[1] = {0.0};
     if (pend) {
       const double vk = v[k], wk = fma(tau_prev, p[k], -c * vk);
       for (int j = k + tid; j < n; j += THREADS) {
         const double vj = v[j];
         const double wj = fma(tau_prev, p[j], -c * vj);
+        wv[j] = wj;
         const double r = rcur[j] - fma(vk, wj, wk * vj);
         rcur[j] = r;
         if (j >= k + 2) x2[0] = fma(r, r, x2[0]);
@@ -293,78 +384,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
       vnew[j] = vj;
       if (cr == 0) Vh[(size_t)k * n + j] = vj;
     }
+    __syncthreads();
     LG_MARK(1);
-    // (3) own rows >= k+1: pending rank-2 update fused with A v'
-    if (r0 + R - 1 >= k + 1 && r0 < n) {
-      double acc[R], vi[R], wi[R];
-      double* Ar[R];
-      bool ok[R];
-      int qpub = -1;  // row k+1 is published for the next column
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const int r = r0 + q;
-        ok[q] = r >= k + 1 && r < n;
-        const int rc = ok[q] ? r : k + 1;
-        Ar[q] = A + (size_t)rc * n;
-        vi[q] = pend ? v[rc] : 0.0;
-        wi[q] = pend ? fma(tau_prev, p[rc], -c * vi[q]) : 0.0;
-        acc[q] = 0.0;
-        if (r == k + 1) qpub = q;
-      }
+    // (3) own live rows (>= k+1): pending rank-2 update fused with A v'
+    {
+      const int q0 = (k + 1 > gw) ? (k + 1 - gw + W - 1) / W : 0;
+      const int first = gw + q0 * W;
+      const int rl = first < n ? (n - 1 - first) / W + 1 : 0;
       double* rpub = rowb + ((k + 1) & 1) * np;
-      for (int j0 = (k + 1) & ~31; j0 < n; j0 += 32 * UNR) {
-        double x[R][UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int j = j0 + 32 * u + lane;
-          const bool inb = j >= k + 1 && j < n;
-#pragma unroll
-          for (int q = 0; q < R; ++q) x[q][u] = (inb && ok[q]) ? Ar[q][j] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int j = j0 + 32 * u + lane;
-          if (j >= k + 1 && j < n) {
-            const double vnj = (j == k + 1) ? 1.0 : rcur[j] * scl;
-            double vj = 0.0, wj = 0.0;
-            if (pend) {
-              vj = v[j];
-              wj = fma(tau_prev, p[j], -c * vj);
-            }
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-              if (ok[q]) {
-                double xx = x[q][u];
-                if (pend) {
-                  xx = fma(-vi[q], wj, xx);
-                  xx = fma(-wi[q], vj, xx);
-                  Ar[q][j] = xx;
-                }
-                if (q == qpub) rpub[j] = xx;
-                acc[q] = fma(xx, vnj, acc[q]);
-              }
-            }
-          }
-        }
+      double* pnext = pb + ((k + 1) & 1) * np;
+#define LG_CASE(RLV)                                                                                         \
+  case RLV:                                                                                                  \
+    if constexpr (RLV <= R) lg_step3<RLV>(cluster, CL, A, n, k, first, W, lane, v, wv, vnew, rpub, pnext, a.ablate);   \
+    break;
+      switch (rl) {
+        LG_CASE(1) LG_CASE(2) LG_CASE(3) LG_CASE(4) LG_CASE(5) LG_CASE(6) LG_CASE(7) LG_CASE(8)
+        default: break;
       }
-#pragma unroll
-      for (int q = 0; q < R; ++q) acc[q] = warp_sum(acc[q]);
-      // push p'[own rows] into every CTA of the cluster
-      for (int idx = lane; idx < R * CL; idx += 32) {
-        const int q = idx / CL, t = idx - q * CL;
-        double val = 0.0;
-        bool okq = false;
-#pragma unroll
-        for (int qq = 0; qq < R; ++qq)
-          if (qq == q) {
-            val = acc[qq];
-            okq = ok[qq];
-          }
-        if (okq) {
-          double* dst = cluster.map_shared_rank(pb + ((k + 1) & 1) * np, t);
-          dst[r0 + q] = val;
-        }
-      }
+#undef LG_CASE
     }
     cur ^= 1;
     tau_prev = tau;
@@ -373,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
     LG_MARK(3);
   }
   cluster.sync();  // nobody leaves while its shared memory may still be read
-  if (a.dbg && tid == 0 && cr == 0)
+  if (a.dbg && tid == 448 && cr == CL - 1)
     for (int q = 0; q < 4; ++q) a.dbg[(size_t)b * 4 + q] = tacc[q];
 }
 
@@ -404,6 +441,16 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
   int st_in = a.status ? a.status[b] : 0;
   st_in &= ~(MOP_ST_EIG_FALLBACK | MOP_ST_EIG_NOCONV);
   if (tid == 0) s_fallback = 0;
+  long long tq = clock64();
+  int tslot = 0;
+#define LG_EMARK()                                                                    \
+  do {                                                                                \
+    if (a.dbg && tid == 0) {                                                          \
+      const long long tnow = clock64();                                               \
+      a.dbg[(size_t)gridDim.x * 4 + (size_t)b * 4 + (tslot++)] = tnow - tq;           \
+      tq = tnow;                                                                      \
+    }                                                                                 \
+  } while (0)
   double tn = 0.0;
   for (int i = tid; i < n; i += THREADS) {
     d[i] = a.dd[(size_t)b * n + i];
@@ -494,6 +541,7 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
     }
     for (int i = tid; i < n; i += THREADS) lam[i] = 0.5 * (lo[i] + hi[i]);
     __syncthreads();
+    LG_EMARK();
 
     // ---- twisted-factorisation eigenvectors, thread i owns column i of S ----
     {
@@ -585,12 +633,13 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
     if (tid == 0) {
       int cs = 0;
       for (int i = 0; i < n; ++i) {
-        const bool chain = i > 0 && blk_s[i] == blk_s[i - 1] && (lam[i] - lam[i - 1]) < TRI_GAPTOL;
+        const bool chain = i > 0 && blk_s[i] == blk_s[i - 1] && (lam[i] - lam[i - 1]) < LG_GAPTOL;
         if (!chain) cs = i;
         cl_s[i] = cs;
       }
     }
     __syncthreads();
+    LG_EMARK();
     // ---- CGS2 inside clusters, one warp per cluster ----
     for (int c0 = wid; c0 < n; c0 += NW) {
       if (cl_s[c0] != c0) continue;
@@ -640,6 +689,7 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
     }
     __syncthreads();
   }
+  LG_EMARK();
   // ascending rank over all blocks
   int* rank = a.rank + (size_t)b * n;
   const double tnorm = zero_t ? 1.0 : s_tnorm;
@@ -806,6 +856,11 @@ extern "C" int mop_debug_large_cluster(int cl) {
   return MOP_OK;
 }
 static long long* g_lg_dbg = nullptr;
+static int g_lg_ablate = 0;
+extern "C" int mop_debug_large_ablate(int mask) {
+  g_lg_ablate = mask;
+  return MOP_OK;
+}
 // diagnostics: device buffer [B][4] receiving the cycles one CTA of each cluster spent in the
 // column phases (w, Householder, update + symv, cluster barrier) of the next launches
 extern "C" int mop_debug_large_timing(void* buf) {
@@ -862,6 +917,7 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
   a.evecs = nullptr;
   a.status = status;
   a.dbg = g_lg_dbg;
+  a.ablate = g_lg_ablate;
   {
     dim3 grid((n + 31) / 32, (n + 31) / 32, B);
     mop::k_lg_symcopy<<<grid, 256, 0, stream>>>(n, A, a.A);
@@ -893,7 +949,7 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
       cfg.dynamicSmemBytes = smem;
       MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag, a));
     } else {
-      const size_t smem = sizeof(double) * 7 * (size_t)np;
+      const size_t smem = sizeof(double) * 8 * (size_t)np;
       cfg.blockDim = dim3(T2);
       cfg.dynamicSmemBytes = smem;
 #define LG_LAUNCH2(RR)                                                                                          \
