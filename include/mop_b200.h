@@ -210,6 +210,41 @@ int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radi
                         double* H_out, int32_t* counts_out, int32_t* status, void* work,
                         size_t work_bytes, void* stream);
 
+/* ---- redundant internal coordinates ------------------------------------------------------
+ * Replaces Coordinate/redundant_coordinate.py: RedundantInternalCoordinates.B_matrix (:15-43),
+ * RICgrad2cartgrad (:47-50), RIChess2carthess (:63-146), partial_stretch_B_matirx /
+ * partial_bend_B_matrix / partial_torsion_B_matrix (:150-320), calc_int_grad_from_pBmat /
+ * calc_cart_grad_from_pBmat with calc_inv_B_mat / calc_inv_G_mat (:377-439).
+ * M = natoms (natoms - 1) / 2 atom pairs in itertools.combinations order, n = 3 natoms.
+ *  mop_ric_bmatrix       Bmat [B][M][n]
+ *  mop_ric_partial_rows  labels [nrows][4] int32, 1-based atom labels as in the reference, 0 = unused
+ *                        (2 / 3 / 4 labels = stretch / bend / torsion); rows_out [B][nrows][n]
+ *  mop_ric_grad_to_cart  cart_grad [B][n] = B^T ric_grad [B][M]
+ *  mop_ric_hess_to_cart  cart_hess = B^T H B + K; ric_hess [B][M][M], or [B][M] when diagonal != 0;
+ *                        K [B][n][n] or NULL
+ *  mop_ric_kmatrix       K [B][n][n] = sum_t ric_grad[t] d2 q_t / dx2, t running over the bond, angle and
+ *                        dihedral tables in that order (0-based atom indices, mop_connectivity layout;
+ *                        tables_per_structure = 0: one set of tables shared by the batch);
+ *                        ric_grad [B][ric_len], terms t >= ric_len are skipped.  The reference obtains
+ *                        ric_grad from a singular solve (cartgrad2RICgrad): it is an input here.
+ *  mop_ric_pb_int_grad   int_grad [B][m] = (G^+ pB^T)^T cart_grad, G = pB^T pB, pB [B][m][n]; the
+ *                        pseudo-inverse keeps singular values <= 1e-6 as they are, as the reference does
+ *  mop_ric_pb_cart_grad  cart_grad [B][n] = pB^T int_grad */
+int mop_ric_bmatrix(int B, int natoms, const double* xyz, double* Bmat, void* stream);
+int mop_ric_partial_rows(int B, int natoms, const double* xyz, int nrows, const int32_t* labels, double* rows_out,
+                         void* stream);
+int mop_ric_grad_to_cart(int B, int natoms, const double* xyz, const double* ric_grad, double* cart_grad, void* stream);
+size_t mop_ric_hess_workspace_bytes(int B, int natoms, int diagonal);
+int mop_ric_hess_to_cart(int B, int natoms, const double* xyz, const double* ric_hess, int diagonal, const double* K,
+                         double* cart_hess, void* work, size_t work_bytes, void* stream);
+int mop_ric_kmatrix(int B, int natoms, const double* xyz, const int32_t* bonds, const int32_t* angles,
+                    const int32_t* dihedrals, const int32_t* counts, int cap_bonds, int cap_angles, int cap_dihedrals,
+                    int tables_per_structure, const double* ric_grad, int ric_len, double* K_out, void* stream);
+size_t mop_ric_pb_workspace_bytes(int B, int n);
+int mop_ric_pb_int_grad(int B, int n, int m, const double* pB, const double* cart_grad, double* int_grad,
+                        int32_t* status, void* work, size_t work_bytes, void* stream);
+int mop_ric_pb_cart_grad(int B, int n, int m, const double* pB, const double* int_grad, double* cart_grad, void* stream);
+
 /* ---- Swart model Hessian ----------------------------------------------------------
  * Replaces SwartApproxHessian.main (ModelHessian/swart.py:317-355): all-pairs screened stretch
  * terms, screened bend terms with the near-linear blending, non-finite fallback to stretches

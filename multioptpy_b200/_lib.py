@@ -41,6 +41,15 @@ SIGNATURES = {
     "mop_connectivity": (_i, [_i, _i, _p, _p, _i, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_fischer_workspace_bytes": (_sz, [_i, _i]),
     "mop_fischer_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mop_ric_bmatrix": (_i, [_i, _i, _p, _p, _p]),
+    "mop_ric_partial_rows": (_i, [_i, _i, _p, _i, _p, _p, _p]),
+    "mop_ric_grad_to_cart": (_i, [_i, _i, _p, _p, _p, _p]),
+    "mop_ric_hess_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mop_ric_hess_to_cart": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "mop_ric_kmatrix": (_i, [_i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p]),
+    "mop_ric_pb_workspace_bytes": (_sz, [_i, _i]),
+    "mop_ric_pb_int_grad": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "mop_ric_pb_cart_grad": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "mop_swart_workspace_bytes": (_sz, [_i, _i]),
     "mop_swart_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "mop_lindh_workspace_bytes": (_sz, [_i, _i]),

@@ -450,3 +450,106 @@ def swart_hessian(xyz, radii, want_raw: bool = False):
                                    _ptr(work), nbytes, _stream(xyz.device))
     _lib.check(rc, "mop_swart_hessian")
     return H, Hraw, status
+
+
+# ------------------------------------------------------------------ redundant internal coordinates
+def _f64(B, *shape, dev):
+    return torch.empty(B, *shape, dtype=torch.float64, device=dev)
+
+
+def ric_bmatrix(xyz):
+    """All-pairs distance B matrix (B, M, 3N), rows in itertools.combinations order."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    out = _f64(B, N * (N - 1) // 2, 3 * N, dev=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.mop_ric_bmatrix(B, N, _ptr(xyz), _ptr(out), _stream(xyz.device)), "mop_ric_bmatrix")
+    return out
+
+
+def ric_partial_rows(xyz, labels):
+    """Stretch / bend / torsion Wilson rows.  labels: (nrows, 4) int32, 1-based, 0 = unused."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3)); _chk(labels, "labels", None, torch.int32)
+    nrows = labels.shape[0]
+    out = _f64(B, nrows, 3 * N, dev=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.mop_ric_partial_rows(B, N, _ptr(xyz), nrows, _ptr(labels), _ptr(out), _stream(xyz.device)),
+                   "mop_ric_partial_rows")
+    return out
+
+
+def ric_grad_to_cart(xyz, ric_grad):
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3)); _chk(ric_grad, "ric_grad", (B, N * (N - 1) // 2))
+    out = _f64(B, 3 * N, dev=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.mop_ric_grad_to_cart(B, N, _ptr(xyz), _ptr(ric_grad), _ptr(out), _stream(xyz.device)),
+                   "mop_ric_grad_to_cart")
+    return out
+
+
+def ric_hess_to_cart(xyz, ric_hess, K=None):
+    """B^T H B + K.  ric_hess: (B, M, M) dense or (B, M) diagonal."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    M = N * (N - 1) // 2
+    _chk(xyz, "xyz", (B, N, 3))
+    diag = ric_hess.dim() == 2
+    _chk(ric_hess, "ric_hess", (B, M) if diag else (B, M, M))
+    if K is not None:
+        _chk(K, "K", (B, 3 * N, 3 * N))
+    out = _f64(B, 3 * N, 3 * N, dev=xyz.device)
+    nbytes = lib.mop_ric_hess_workspace_bytes(B, N, int(diag))
+    work = workspace(xyz.device, nbytes) if nbytes else None
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.mop_ric_hess_to_cart(B, N, _ptr(xyz), _ptr(ric_hess), int(diag), _ptr(K), _ptr(out), _ptr(work),
+                                            nbytes, _stream(xyz.device)), "mop_ric_hess_to_cart")
+    return out
+
+
+def ric_kmatrix(xyz, bonds, angles, dihedrals, counts, ric_grad):
+    """K of RIChess2carthess.  Tables: int32 (capacity, 2/3/4) shared by the batch, or (B, capacity, 2/3/4)."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    per = bonds.dim() == 3
+    for t, nm in ((bonds, "bonds"), (angles, "angles"), (dihedrals, "dihedrals"), (counts, "counts")):
+        _chk(t, nm, None, torch.int32)
+    _chk(ric_grad, "ric_grad", None)
+    out = _f64(B, 3 * N, 3 * N, dev=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = lib.mop_ric_kmatrix(B, N, _ptr(xyz), _ptr(bonds), _ptr(angles), _ptr(dihedrals), _ptr(counts),
+                                 bonds.shape[-2], angles.shape[-2], dihedrals.shape[-2], int(per), _ptr(ric_grad),
+                                 ric_grad.shape[-1], _ptr(out), _stream(xyz.device))
+    _lib.check(rc, "mop_ric_kmatrix")
+    return out
+
+
+def ric_pb_int_grad(pB, cart_grad):
+    """calc_int_grad_from_pBmat for a batch: pB (B, m, n), cart_grad (B, n) -> (B, m)."""
+    lib = _lib.load()
+    B, m, n = pB.shape
+    _chk(pB, "pB", (B, m, n)); _chk(cart_grad, "cart_grad", (B, n))
+    out = _f64(B, m, dev=pB.device)
+    status = torch.zeros(B, dtype=torch.int32, device=pB.device)
+    nbytes = lib.mop_ric_pb_workspace_bytes(B, n)
+    work = workspace(pB.device, nbytes)
+    with torch.cuda.device(pB.device):
+        _lib.check(lib.mop_ric_pb_int_grad(B, n, m, _ptr(pB), _ptr(cart_grad), _ptr(out), _ptr(status), _ptr(work),
+                                           nbytes, _stream(pB.device)), "mop_ric_pb_int_grad")
+    return out
+
+
+def ric_pb_cart_grad(pB, int_grad):
+    lib = _lib.load()
+    B, m, n = pB.shape
+    _chk(pB, "pB", (B, m, n)); _chk(int_grad, "int_grad", (B, m))
+    out = _f64(B, n, dev=pB.device)
+    with torch.cuda.device(pB.device):
+        _lib.check(lib.mop_ric_pb_cart_grad(B, n, m, _ptr(pB), _ptr(int_grad), _ptr(out), _stream(pB.device)),
+                   "mop_ric_pb_cart_grad")
+    return out

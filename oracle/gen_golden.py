@@ -534,6 +534,84 @@ def gen_swart():
     np.savez_compressed(os.path.join(GOLD, "swart.npz"), **blob)
 
 
+def gen_ric():
+    """Redundant-internal-coordinate helpers (Coordinate/redundant_coordinate.py): all-pairs B matrix,
+    partial stretch / bend / torsion rows (incl. the linear and planar special branches), Wilson
+    back-transformation B^T H B + K with a supplied RIC gradient, pseudo-inverse gradient transforms."""
+    rc = ref_shim.ref("Coordinate.redundant_coordinate")
+    bc = ref_shim.ref("Utils.bond_connectivity")
+    blob = {"names": np.array(["aldol_rxn", "s8", "grid24"])}
+    rng = np.random.default_rng(181818)
+    for name, path in [c for c in PRODUCER_CASES if c[0] in ("aldol_rxn", "s8", "grid24")]:
+        elems, xyz = producer_geometry(name, path)
+        N = len(elems)
+        R = rc.RedundantInternalCoordinates()
+        with quiet():
+            Bm = R.B_matrix(xyz)
+            tabs = bc.BondConnectivity().connectivity_table(xyz.copy(), elems)
+        M = len(Bm)
+        nt = sum(len(t) for t in tabs)
+        q = rng.normal(0, 1e-2, size=M)                  # an internal gradient (input, SURVEY H2)
+        hd = np.abs(rng.normal(0.3, 0.1, size=M))
+        A = rng.standard_normal((M, 6)); Hric = np.diag(hd) + 0.01 * (A @ A.T)
+        with quiet():
+            Hc_diag = R.RIChess2carthess(xyz, tabs, np.diag(hd), Bm, q)
+            Hc_full = R.RIChess2carthess(xyz, tabs, Hric, Bm, q)
+            K = Hc_diag - Bm.T @ np.diag(hd) @ Bm
+            gq = R.RICgrad2cartgrad(q, Bm)
+        # near-planar dihedrals make K roundoff-sensitive in the reference itself (acos'' near +-1):
+        # a second K with those terms left out carries the tight parity check
+        def well_conditioned(row):
+            import torch
+            v = float(rc.TorchDerivatives().dihedral_angle(torch.tensor(xyz[list(row)], dtype=torch.float64)))
+            return 0.05 < v < np.pi - 0.05
+        dih_wc = [list(r) for r in tabs[2] if well_conditioned(r)]
+        tabs_wc = [tabs[0], tabs[1], dih_wc]
+        with quiet():
+            K_wc = R.RIChess2carthess(xyz, tabs_wc, np.diag(hd), Bm, q) - Bm.T @ np.diag(hd) @ Bm
+        blob[f"{name}/dihedrals_wc"] = pad_table(dih_wc, 4); blob[f"{name}/n_dih_wc"] = np.int32(len(dih_wc))
+        blob[f"{name}/K_wc"] = K_wc
+        labels = []
+        for t in tabs:
+            for row in t[: 6]:
+                labels.append([int(a) + 1 for a in row])
+        rows = []
+        for lab in labels:
+            f = {2: rc.partial_stretch_B_matirx, 3: rc.partial_bend_B_matrix, 4: rc.partial_torsion_B_matrix}[len(lab)]
+            rows.append(f(xyz, *lab)[0])
+        pB = np.array(rows[: min(len(rows), 5)])
+        g = rng.normal(0, 1e-2, size=3 * N)
+        ig = rc.calc_int_grad_from_pBmat(g.reshape(-1, 1), pB).ravel()
+        cg = rc.calc_cart_grad_from_pBmat(ig.reshape(-1, 1), pB).ravel()
+        blob[f"{name}/xyz"] = xyz; blob[f"{name}/elements"] = np.array(elems)
+        blob[f"{name}/Bmat"] = Bm; blob[f"{name}/q"] = q; blob[f"{name}/hdiag"] = hd; blob[f"{name}/Hric"] = Hric
+        blob[f"{name}/K"] = K; blob[f"{name}/Hc_diag"] = Hc_diag; blob[f"{name}/Hc_full"] = Hc_full; blob[f"{name}/gq"] = gq
+        blob[f"{name}/bonds"] = pad_table(tabs[0], 2); blob[f"{name}/angles"] = pad_table(tabs[1], 3)
+        blob[f"{name}/dihedrals"] = pad_table(tabs[2], 4)
+        blob[f"{name}/counts"] = np.array([len(t) for t in tabs], np.int32)
+        lab_arr = np.zeros((len(labels), 4), np.int32)
+        for r_, lab in enumerate(labels):
+            lab_arr[r_, : len(lab)] = lab
+        blob[f"{name}/labels"] = lab_arr; blob[f"{name}/rows"] = np.array(rows)
+        blob[f"{name}/pB"] = pB; blob[f"{name}/g"] = g; blob[f"{name}/int_grad"] = ig; blob[f"{name}/cart_grad"] = cg
+        print("ric case", name, "M", M, "terms", nt, "|K|", np.linalg.norm(K), "rows", len(rows))
+    # special branches of the partial rows: linear bend, planar (phi = 0, pi) torsions
+    sp = {
+        "bend_linear": (np.array([[-2.0, 0, 0], [0, 0, 0], [2.2, 0, 0.0]]), [1, 2, 3]),
+        "tors_trans": (np.array([[1.0, 1.0, 0], [0, 0, 0], [2.5, 0, 0], [3.4, -1.1, 0.0]]), [1, 2, 3, 4]),
+        "tors_cis": (np.array([[1.0, 1.0, 0], [0, 0, 0], [2.5, 0, 0], [3.4, 1.2, 0.0]]), [1, 2, 3, 4]),
+        "tors_gen": (np.array([[1.0, 1.0, 0.2], [0, 0, 0], [2.5, 0, 0], [3.4, 0.3, -1.2]]), [1, 2, 3, 4]),
+        "tors_neg": (np.array([[1.0, 1.0, 0.2], [0, 0, 0], [2.5, 0, 0], [3.4, 0.3, 1.2]]), [4, 3, 2, 1]),
+    }
+    blob["special_names"] = np.array(list(sp))
+    for name, (x, lab) in sp.items():
+        f = {3: rc.partial_bend_B_matrix, 4: rc.partial_torsion_B_matrix}[len(lab)]
+        blob[f"special/{name}/xyz"] = x
+        blob[f"special/{name}/labels"] = np.array(lab + [0] * (4 - len(lab)), np.int32)
+        blob[f"special/{name}/row"] = f(x, *lab)[0]
+    np.savez_compressed(os.path.join(GOLD, "ric.npz"), **blob)
+
+
 RSPRFO_CASES = [
     # (name, method, saddle_order, natoms, nsteps, bias, seed)
     ("prfo_bofill_ts_n36", "rsprfo_bofill", 1, 12, 6, False, 1),
@@ -599,7 +677,7 @@ def gen_rsprfo():
     np.savez_compressed(os.path.join(GOLD, "rsprfo_traces.npz"), **blob)
 
 
-SETS = {"swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+SETS = {"ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo}
 
 if __name__ == "__main__":

@@ -1461,3 +1461,122 @@ def swart_hessian(xyz, radii):
     if not np.all(np.isfinite(H)):
         H = swart_raw_hessian(xyz, radii, angles=False)
     return project_hessian_trrot(H, xyz.reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------
+# Redundant internal coordinates: Coordinate/redundant_coordinate.py
+# ---------------------------------------------------------------------------------------------
+def ric_bmatrix(xyz):
+    """All-pairs distance B matrix, rows in itertools.combinations order (:15-43)."""
+    xyz = np.asarray(xyz, float); N = len(xyz)
+    rows = []
+    for i in range(N):
+        for j in range(i + 1, N):
+            e = (xyz[i] - xyz[j]) / np.linalg.norm(xyz[i] - xyz[j])
+            r = np.zeros(3 * N); r[3 * i:3 * i + 3] = e; r[3 * j:3 * j + 3] = -e
+            rows.append(r)
+    return np.array(rows)
+
+
+def ric_partial_row(xyz, labels):
+    """partial_stretch / bend / torsion B rows (:150-320); labels are 1-based, 2 / 3 / 4 of them."""
+    xyz = np.asarray(xyz, float); N = len(xyz)
+    out = np.zeros(3 * N)
+    idx = [l - 1 for l in labels]
+    if len(idx) == 2:
+        i, j = idx
+        e = (xyz[i] - xyz[j]) / np.linalg.norm(xyz[i] - xyz[j])
+        parts = [e, -e]
+    elif len(idx) == 3:
+        i, j, k = idx
+        u, w = xyz[i] - xyz[j], xyz[k] - xyz[j]
+        lu, lw = np.linalg.norm(u), np.linalg.norm(w)
+        c = min(max(u @ w / (lu * lw), -1.0), 1.0)
+        th = np.arccos(c)
+        if abs(th) > np.pi - 1e-6:
+            parts = [(np.pi - th) / (2 * lu ** 2) * u, (1 / lu - 1 / lw) * (np.pi - th) / (2 * lu) * u,
+                     (np.pi - th) / (2 * lw ** 2) * w]
+        else:
+            ct, st = 1 / np.tan(th), np.sin(th)
+            parts = [ct * u / lu ** 2 - w / (lu * lw * st),
+                     (u + w) / (lu * lw * st) - ct * (u / lu ** 2 + w / lw ** 2),
+                     ct * w / lw ** 2 - u / (lu * lw * st)]
+    else:
+        i, j, k, l = idx
+        vij, vlk, vkj = xyz[i] - xyz[j], xyz[l] - xyz[k], xyz[k] - xyz[j]
+        nkj = np.linalg.norm(vkj); ukj = vkj / nkj
+        a1 = vij - (vij @ ukj) * ukj
+        a2 = vlk - (vlk @ ukj) * ukj
+        n1, n2 = np.linalg.norm(a1), np.linalg.norm(a2)
+        sg = np.sign(np.linalg.det(np.array([vlk, vij, vkj]))) or 1
+        c = min(max(a1 @ a2 / (n1 * n2), -1.0), 1.0)
+        phi = np.arccos(c) * sg
+        A = (vij @ ukj) / nkj; Bc = (vlk @ ukj) / nkj
+        if abs(phi) > np.pi - 1e-6 or abs(phi) < 1e-6:
+            G = np.cross(vkj, a1); uG = G / np.linalg.norm(G)
+            last = uG / n2 if abs(phi) > np.pi - 1e-6 else -uG / n2
+            parts = [uG / n1, -((1 - A) / n1 - Bc / n2) * uG, -((1 + Bc) / n2 + A / n1) * uG, last]
+        else:
+            ct, st = 1 / np.tan(phi), np.sin(phi)
+            parts = [ct * a1 / n1 ** 2 - a2 / (n1 * n2 * st),
+                     ((1 - A) * a2 - Bc * a1) / (n1 * n2 * st) - ct * ((1 - A) * a1 / n1 ** 2 - Bc * a2 / n2 ** 2),
+                     ((1 + Bc) * a1 + A * a2) / (n1 * n2 * st) - ct * ((1 + Bc) * a2 / n2 ** 2 + A * a1 / n1 ** 2),
+                     ct * a2 / n2 ** 2 - a1 / (n1 * n2 * st)]
+    for n_ in range(N):                 # the reference's chain picks the FIRST matching label
+        for a, v in zip(idx, parts):
+            if n_ == a:
+                out[3 * n_:3 * n_ + 3] = v
+                break
+    return out
+
+
+def _ric_coordinate_torch(c):
+    """TorchDerivatives.distance / angle / dihedral_angle (:442-477) on a (m, 3) tensor."""
+    import torch
+    if c.shape[0] == 2:
+        return torch.linalg.norm(c[0] - c[1])
+    if c.shape[0] == 3:
+        v1, v2 = c[0] - c[1], c[2] - c[1]
+        return torch.arccos(torch.matmul(v1, v2) / (torch.linalg.norm(v1) * torch.linalg.norm(v2) + 1e-15))
+    a1, a2, a3 = c[1] - c[0], c[2] - c[1], c[3] - c[2]
+    v1 = torch.linalg.cross(a1, a2); v1 = v1 / torch.linalg.norm(v1, ord=2)
+    v2 = torch.linalg.cross(a2, a3); v2 = v2 / torch.linalg.norm(v2, ord=2)
+    ca = torch.sum(v1 * v2) / torch.sum((v1 ** 2) * torch.sum(v2 ** 2) + 1e-15) ** 0.5
+    return torch.abs(torch.arccos(ca))
+
+
+def ric_kmatrix(xyz, tables, ricgrad):
+    """K of RIChess2carthess (:63-143): sum_t ricgrad[t] * d2 q_t / dx2 over bonds, angles, dihedrals,
+    t counting through the three tables in order (ricgrad is indexed by this counter)."""
+    import torch
+    xyz = np.asarray(xyz, float); N = len(xyz)
+    K = np.zeros((3 * N, 3 * N))
+    t = 0
+    for tab in tables:
+        for atoms in tab:
+            atoms = [int(a) for a in atoms]
+            c = torch.tensor(xyz[atoms], dtype=torch.float64)
+            h = torch.func.hessian(_ric_coordinate_torch)(c).reshape(3 * len(atoms), 3 * len(atoms)).numpy()
+            idx = np.concatenate([np.arange(3 * a, 3 * a + 3) for a in atoms])
+            K[np.ix_(idx, idx)] += h * ricgrad[t]
+            t += 1
+    return K
+
+
+def ric_inv_G(G, threshold=1e-6):
+    """calc_inv_G_mat (:381-394): SVD with s > threshold -> 1/s, otherwise s is KEPT (not zeroed)."""
+    U, s, VT = np.linalg.svd(G)
+    f = np.where(s > threshold, 1.0 / np.where(s > threshold, s, 1.0), s)
+    return VT.T @ np.diag(f) @ U.T
+
+
+def ric_int_grad(pB, cart_grad):
+    """calc_int_grad_from_pBmat (:432-435): (G^+ pB^T)^T cart_grad with G = pB^T pB."""
+    pB = np.asarray(pB, float)
+    Binv = (ric_inv_G(pB.T @ pB) @ pB.T).T
+    return Binv @ np.asarray(cart_grad, float).reshape(-1)
+
+
+def ric_cart_grad(pB, int_grad):
+    """calc_cart_grad_from_pBmat (:437-439)."""
+    return np.asarray(pB, float).T @ np.asarray(int_grad, float).reshape(-1)
