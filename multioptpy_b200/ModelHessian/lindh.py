@@ -3,11 +3,13 @@
 Implemented on the device: the connectivity tables, the diagonal redundant-internal force
 constants (bond / angle / dihedral decay terms, reduced-mass scaling of bonds, Lennard-Jones and
 electrostatic terms of non-bonded pairs) and ``B^T diag(k) B`` with the all-pairs distance
-B matrix, then the TR/ROT projection.  NOT added: the reference's ``K`` term, which multiplies
-second derivatives by an internal-coordinate gradient obtained from ``np.linalg.solve`` on the
-singular ``B B^T`` and indexes it by a bond/angle/dihedral counter although its rows are atom
-pairs — a 1e-13 shift of the coordinates changes it by O(1), so it has no
-reproducible value.  ``main`` therefore equals the reference for a zero gradient only."""
+B matrix, then the TR/ROT projection.  The reference's ``K`` term multiplies second derivatives by
+an internal-coordinate gradient obtained from ``np.linalg.solve`` on the singular ``B B^T`` and
+indexes it by a bond/angle/dihedral counter although its rows are atom pairs — a 1e-13 shift of the
+coordinates changes it by O(1), so that gradient has no reproducible value.  ``main``
+therefore adds ``K`` only when the caller supplies the internal gradient (``int_grad=``, e.g. the
+reference's own ``cartgrad2RICgrad`` output); without it ``main`` equals the reference for a zero
+gradient."""
 from __future__ import annotations
 
 import numpy as np
@@ -42,8 +44,10 @@ class LindhApproxHessian:
         _, kd, _, _ = ops.lindh_hessian(xyz, lindh_atom_params(element_list), want_kdiag=True)
         return kd[0].cpu().numpy()
 
-    def main(self, coord, element_list, cart_gradient=None):
+    def main(self, coord, element_list, cart_gradient=None, int_grad=None):
         prm = lindh_atom_params(element_list)
+        if int_grad is not None:
+            return self._main_with_int_grad(coord, element_list, prm, int_grad)
         if isinstance(coord, torch.Tensor):
             return ops.lindh_hessian(coord, prm)[0]
         xyz = torch.as_tensor(np.ascontiguousarray(np.asarray(coord, dtype=np.float64)).reshape(1, -1, 3)).to(self.device)
@@ -51,3 +55,20 @@ class LindhApproxHessian:
         if int(status[0].item()) != 0:
             raise ops.MopError("Lindh model Hessian: connectivity table capacity exceeded")
         return H[0].cpu().numpy()
+
+    def _main_with_int_grad(self, coord, element_list, prm, int_grad):
+        """B^T diag(k) B + K(int_grad), nan_to_num, TR/ROT projection (lindh.py:153-164)."""
+        from ..Utils.bond_connectivity import radii_array
+        tensor = isinstance(coord, torch.Tensor)
+        if tensor:
+            xyz, q = coord.contiguous(), int_grad.contiguous()
+        else:
+            xyz = torch.as_tensor(np.ascontiguousarray(np.asarray(coord, dtype=np.float64)).reshape(1, -1, 3)).to(self.device)
+            q = torch.as_tensor(np.asarray(int_grad, dtype=np.float64).reshape(1, -1)).to(self.device).contiguous()
+        B, N, _ = xyz.shape
+        _, kd, _, _ = ops.lindh_hessian(xyz, prm, want_kdiag=True)
+        bonds, angles, dihs, counts, _ = ops.connectivity(xyz, radii_array(element_list))
+        K = ops.ric_kmatrix(xyz, bonds, angles, dihs, counts, q)
+        raw = torch.nan_to_num(ops.ric_hess_to_cart(xyz, kd, K), nan=0.0)
+        H, _, _ = ops.project_trrot(raw.contiguous(), xyz.reshape(B, 3 * N))
+        return H if tensor else H[0].cpu().numpy()

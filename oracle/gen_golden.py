@@ -493,6 +493,16 @@ def gen_lindh():
             except Exception as exc:
                 print("  main(zero gradient) failed:", exc)
                 Hmain = np.full((3 * N, 3 * N), np.nan)
+        # main() with a gradient: the internal gradient of the singular solve is recorded as an input
+        gq = np.random.default_rng(7 + N).normal(0, 1e-2, size=(N, 3))
+        with quiet():
+            ig = ric.RedundantInternalCoordinates().cartgrad2RICgrad(gq.reshape(3 * N, 1), B)
+            try:
+                Hmain_g = np.asarray(li.LindhApproxHessian().main(xyz.copy(), elems, gq.copy()), float)
+            except Exception as exc:
+                print("  main(gradient) failed:", exc); Hmain_g = np.full((3 * N, 3 * N), np.nan)
+        blob[f"{name}/grad"] = gq; blob[f"{name}/int_grad"] = np.asarray(ig, float).ravel(); blob[f"{name}/H_main_g"] = Hmain_g
+        print("   main(g): |int_grad| max", np.abs(ig).max(), "|H|", np.linalg.norm(Hmain_g))
         blob[f"{name}/elements"] = np.array(elems); blob[f"{name}/xyz"] = xyz
         blob[f"{name}/kdiag"] = kd; blob[f"{name}/H_bkb"] = np.asarray(Hbkb, float); blob[f"{name}/H_main0"] = Hmain
         print("lindh case", name, "kdiag range", kd.min(), kd.max(), "main0 vs BkB",

@@ -41,3 +41,24 @@ def test_gpu_lindh_vs_reference(golden_dir, idx):
     H = ApproxHessian(device="cuda:0").main(xyz, elems, np.zeros_like(xyz), "lindh")
     assert rel(H, z[f"{name}/H_bkb"]) < RTOL
     assert rel(H, z[f"{name}/H_main0"]) < RTOL      # reference main() with a zero gradient
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(4))
+def test_gpu_lindh_main_with_reference_int_grad(golden_dir, idx):
+    """main() with a gradient: the reference's internal gradient (singular solve) is fed in
+    as an input; B^T k B + K, nan_to_num and the projection are then reproducible.  Near-planar
+    dihedrals make K itself roundoff-sensitive (tests/test_ric.py), hence the looser bar."""
+    from multioptpy_b200.ModelHessian.lindh import LindhApproxHessian
+    z = np.load(os.path.join(golden_dir, "lindh.npz"))
+    name = str(z["names"][idx])
+    ref = z[f"{name}/H_main_g"]
+    if not np.isfinite(ref).all():
+        pytest.skip("reference main() failed on this geometry")
+    H = LindhApproxHessian(device="cuda:0").main(z[f"{name}/xyz"], [str(e) for e in z[f"{name}/elements"]],
+                                                 z[f"{name}/grad"], int_grad=z[f"{name}/int_grad"])
+    err = np.linalg.norm(H - ref) / np.linalg.norm(ref)
+    # claisen holds a dihedral within ~1e-6 rad of planar: its acos'' term is O(1e6), swamps the Hessian
+    # and is pure roundoff in the reference too; only the order of magnitude is comparable there
+    blown_up = np.linalg.norm(ref) > 1e3 * np.linalg.norm(z[f"{name}/H_bkb"])
+    assert err < (0.2 if blown_up else 1e-5), (name, err)
