@@ -25,6 +25,10 @@ size_t mop_large_workspace_bytes(int B, int n);
 int mop_large_supported(int n);
 int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* evecs, int32_t* status,
                           void* work, size_t work_bytes, cudaStream_t stream);
+int mop_launch_eigh_large_factored(int B, int n, const double* A, double* evals, double* Zt, int32_t* status,
+                                   void* work, size_t work_bytes, cudaStream_t stream);
+int mop_launch_large_apply_q(int B, int n, int trans, void* work, double* x0, double* x1, double* x2, double* x3,
+                             cudaStream_t stream);
 int mop_launch_rfo_step(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
                         const double* evals, const double* evecs, const double* gp,
                         const double* Bg, const double* Be, double* state,
@@ -176,7 +180,7 @@ extern "C" size_t mop_rsirfo_workspace_bytes(int B, int n, int algo) {
   if (B <= 0 || n <= 0) return 0;
   const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
   const size_t nv = align256(sizeof(double) * (size_t)B * n);
-  const size_t generic = nn + nv + eigh_work_bytes(B, n, algo);        // evecs | evals | eigh work
+  const size_t generic = nn + 3 * nv + eigh_work_bytes(B, n, algo);    // evecs | evals | 2 rotated vectors | eigh work
   const size_t fused = mop_rsirfo_spectral_workspace_bytes(B, n);
   return nn + nv + (generic > fused ? generic : fused);                  // Hp | gp | rest
 }
@@ -211,8 +215,10 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   const size_t rest_bytes = work_bytes - (nn + nv);
   double* evecs = (double*)rest;
   double* evals = (double*)(rest + nn);
-  void* ework = rest + nn + nv;
-  const size_t ebytes = rest_bytes - (nn + nv);
+  double* Xg = (double*)(rest + nn + nv);
+  double* Xmv = (double*)(rest + nn + 2 * nv);
+  char* ework = rest + nn + 3 * nv;
+  const size_t ebytes = rest_bytes - (nn + 3 * nv);
 
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   int rc;
@@ -229,6 +235,26 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
     return mop_rsirfo_spectral_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,
                                     state, move_out, eigvals_out, pred_out, status, rest, rest_bytes,
                                     stream_);
+  if (pick_algo(eigh_algo, n) == MOP_EIGH_LARGE) {
+    // large systems: Hp = Q T Q^T, the step is taken in the basis of T (eigh_large.cu, part 4):
+    // gp -> Q^T gp, eigenvectors of T instead of V = Q Z, move -> Q move
+    const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
+    rc = mop_launch_eigh_large_factored(B, n, Hp, evals, evecs, status, ework + jac, ebytes - jac, stream);
+    if (rc != MOP_OK) return rc;
+    rc = mop_launch_eigh_jacobi(B, n, Hp, evals, evecs, status, status, ework, jac, stream);
+    if (rc != MOP_OK) return rc;
+    const size_t vbytes = sizeof(double) * (size_t)B * n;
+    MOP_CHECK_CUDA(cudaMemcpyAsync(Xg, gp, vbytes, cudaMemcpyDeviceToDevice, stream));
+    rc = mop_launch_large_apply_q(B, n, 1, ework + jac, Xg, nullptr, nullptr, nullptr, stream);
+    if (rc != MOP_OK) return rc;
+    rc = mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, Xg, Bg, Be, state,
+                             Xmv, eigvals_out, pred_out, status, 0, stream);
+    if (rc != MOP_OK) return rc;
+    rc = mop_launch_large_apply_q(B, n, 0, ework + jac, Xmv, nullptr, nullptr, nullptr, stream);
+    if (rc != MOP_OK) return rc;
+    MOP_CHECK_CUDA(cudaMemcpyAsync(move_out, Xmv, vbytes, cudaMemcpyDeviceToDevice, stream));
+    return MOP_OK;
+  }
   // (3) eigendecomposition (rsirfo.py:360)
   rc = run_eigh(B, n, eigh_algo, Hp, evals, evecs, status, ework, ebytes, stream);
   if (rc != MOP_OK) return rc;

@@ -88,3 +88,37 @@ def test_rsprfo_n600_vs_oracle():
         xp, gp, mp = x.copy(), g.copy(), mv.copy()
         x = x - mv
         g = np.stack([g0[b] + H0[b] @ (x[b] - x0[b]) for b in range(B)])
+
+
+def test_rsirfo_n300_vs_oracle():
+    """RS-I-RFO beyond the shared-memory eigensolver (n = 300): update + projection + factored
+    eigendecomposition, two consecutive steps, minimum and first-order saddle search."""
+    import torch
+    from multioptpy_b200 import synthetic
+    from multioptpy_b200.Optimizer.rsirfo import RSIRFO
+    B, natoms = 3, 100
+    dev = "cuda:0"
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for so in (0, 1):
+        x0, H0, g0, rngs = synthetic.batch(8 + so, B, natoms, saddle=so > 0)
+        opt = RSIRFO(method="rsirfo_bofill", saddle_order=so, device=dev)
+        opt.set_hessian(T(H0)); opt.set_bias_hessian(T(np.zeros_like(H0)))
+        oracles = []
+        for b in range(B):
+            o = O.RSIRFOOracle(method="rsirfo_bofill", saddle_order=so)
+            o.set_hessian(H0[b].copy()); oracles.append(o)
+        x, g = x0.copy(), g0.copy()
+        xp = gp = None
+        for it in range(2):
+            Be = torch.full((B,), -1e-3 * it, dtype=torch.float64, device=dev)
+            if it == 0:
+                mv = opt.run(T(x), T(g), B_e=Be, g=T(g)).cpu().numpy().copy()
+            else:
+                mv = opt.run(T(x), T(g), pre_B_g=T(gp), pre_geom=T(xp), B_e=Be, g=T(g), pre_g=T(gp)).cpu().numpy().copy()
+            for b, o in enumerate(oracles):
+                m = o.run(x[b], g[b], g[b], xp[b] if it else None, gp[b] if it else None, -1e-3 * it)
+                err = np.linalg.norm(mv[b] - m) / np.linalg.norm(m)
+                assert err < 1e-10, (so, it, b, err)
+            xp, gp = x.copy(), g.copy()
+            x = x - mv
+            g = np.stack([g0[b] + H0[b] @ (x[b] - x0[b]) for b in range(B)])
