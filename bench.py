@@ -426,12 +426,188 @@ def run_b200(args, rank, world, local_rank):
         print(json.dumps(line))
 
 
+# ------------------------------------------------------------------- config 5 (non-default)
+def _cpu_worker_c5(idx_list):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import np_oracle as O
+    from multioptpy_b200 import synthetic
+    prepared = []
+    for gi in idx_list:
+        x0, H0, g0, rng = synthetic.structure(5, gi, 200, saddle=True)
+        o = O.RSPRFOOracle(method="rsprfo_bofill", saddle_order=1)
+        o.set_hessian(H0)
+        m = o.run(x0, g0, None, None, 0.0, None)
+        x1, g1 = synthetic.second_point(x0, H0, g0, m, rng)
+        prepared.append((o, x0, g0, x1, g1, m))
+    t0 = time.perf_counter()
+    for o, x0, g0, x1, g1, m in prepared:
+        o.run(x1, g1, x0, g0, -1e-3, m)
+    return time.perf_counter() - t0, len(prepared)
+
+
+def run_b200_c5(args, rank, world, local_rank):
+    """BASELINE configs[4]: P-RFO saddle search with Bofill update, N = 200 atoms (3N = 600), batch 256
+    sharded over the ranks (strong scaling).  Selected with --workload c5; the default line is configs[1]."""
+    import torch
+    from multioptpy_b200 import _lib, ops, synthetic
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    natoms, total = 200, 256
+    n = 3 * natoms
+    B = total // world
+    K, W = args.steps, args.warmup
+    f64 = torch.float64
+    nuniq = min(B, 16)      # distinct seeded structures, tiled over the shard (generation cost on the host)
+    xs, Hs_, gs, rngs = [], [], [], []
+    for b in range(nuniq):
+        x0, H0, g0, rng = synthetic.structure(5, rank * nuniq + b, natoms, saddle=True)
+        xs.append(x0); Hs_.append(H0); gs.append(g0); rngs.append(rng)
+    rep = (B + nuniq - 1) // nuniq
+    tile = lambda a: torch.from_numpy(np.stack(a)).repeat(rep, *([1] * (np.stack(a).ndim - 1)))[:B].contiguous().to(dev)
+    H_d0, x0_d, g0_d = tile(Hs_), tile(xs), tile(gs)
+    z = lambda *sh: torch.zeros(*sh, dtype=f64, device=dev)
+    def fresh_state():
+        st = dict(state=z(B, ops.PRFO_STATE), prev_grad=z(B, n), prev_move=z(B, n), ts_vec=z(B, n))
+        st["state"][:, 0] = 0.1
+        return st
+    st0 = fresh_state()
+    out0 = ops.rsprfo_step(H_d0.clone(), x0_d, g0_d, st0, method=23, saddle_order=1, Be=z(B))
+    mv0 = out0["move"].clone()
+    x1_d = x0_d - mv0
+    g1_d = g0_d + torch.einsum("bij,bj->bi", H_d0, x1_d - x0_d)
+    Be1 = z(B) - 1e-3
+    # parity spot check against the oracle (checker only)
+    from oracle import np_oracle as O
+    o = O.RSPRFOOracle(method="rsprfo_bofill", saddle_order=1); o.set_hessian(Hs_[0])
+    m0 = o.run(xs[0], gs[0], None, None, 0.0, None)
+    worst = float(np.linalg.norm(mv0[0].cpu().numpy() - m0) / np.linalg.norm(m0))
+    m1 = o.run(x1_d[0].cpu().numpy(), g1_d[0].cpu().numpy(), xs[0], gs[0], -1e-3, m0)
+    ncopy = 3
+    Hc = [H_d0.clone() for _ in range(ncopy)]
+    stc = [{k: v.clone() for k, v in st0.items()} for _ in range(ncopy)]
+    st_ref = {k: v.clone() for k, v in st0.items()}
+    out = None
+
+    def one_step(i):
+        nonlocal out
+        j = i % ncopy
+        Hc[j].copy_(H_d0)
+        for k in st_ref:
+            stc[j][k].copy_(st_ref[k])
+        out = ops.rsprfo_step(Hc[j], x1_d, g1_d, stc[j], method=23, saddle_order=1, x_prev=x0_d, Bg_prev=g0_d,
+                              pre_move=mv0, Be=Be1, out=out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        one_step(i)
+    worst = max(worst, float(np.linalg.norm(out["move"][0].cpu().numpy() - m1) / np.linalg.norm(m1)))
+    if not worst < 1e-10:
+        raise SystemExit(f"bench.py: parity check failed before timing ({worst:.3e})")
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        one_step(W + i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    # e2e: geometry / gradient from pinned host memory, step back to the host; Hessians stay resident
+    hx1, hg1 = x1_d.cpu().pin_memory(), g1_d.cpu().pin_memory()
+    h_mv = torch.empty(B, n, dtype=f64).pin_memory()
+    dx, dg = torch.empty_like(x1_d), torch.empty_like(g1_d)
+    def e2e(i):
+        nonlocal out
+        j = i % ncopy
+        Hc[j].copy_(H_d0)
+        for k in st_ref:
+            stc[j][k].copy_(st_ref[k])
+        dx.copy_(hx1, non_blocking=True); dg.copy_(hg1, non_blocking=True)
+        out = ops.rsprfo_step(Hc[j], dx, dg, stc[j], method=23, saddle_order=1, x_prev=x0_d, Bg_prev=g0_d,
+                              pre_move=mv0, Be=Be1, out=out)
+        h_mv.copy_(out["move"], non_blocking=True)
+        torch.cuda.synchronize()
+    e2e(0); barrier()
+    Ke = max(3, min(K, 5))
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e(i + 1)
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s], dtype=f64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    value = world * B * K / (ms * 1e-3)
+    line = None
+    if rank == 0:
+        lib = _lib.load()
+        probe = torch.empty(148 * 16 * 256, dtype=f64, device=dev)
+        best = 1e30
+        for _ in range(6):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.mop_bench_dfma(148 * 16, 4096, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            b_.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b_))
+        fp64_peak = 148 * 16 * 256 * 4096 * 64 * 2 / (best * 1e-3) / 1e12
+        WF = 9.0 * n ** 3 + 4.0 / 3.0 * n ** 3 + 40.0 * n * n     # SURVEY §8d, RSPRFO
+        step_tf = value / world * WF / 1e12
+        cores = os.cpu_count() or 1
+        sample = max(cores, 8)
+        import multiprocessing as mp
+        for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[k] = "1"          # before the workers import NumPy
+        chunks = [c for c in ([list(range(w, sample, cores)) for w in range(cores)]) if c]
+        with mp.get_context("spawn").Pool(len(chunks)) as pool:
+            res = pool.map(_cpu_worker_c5, chunks)
+        cpu_val = sum(k for _, k in res) / max(t for t, _ in res)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "configs[4]: P-RFO saddle search with Bofill update, N=200 atoms (3N=600), "
+                                       f"batch 256 sharded over {world} GPU(s), step 1 of 2 (update active)",
+                           "batch_per_gpu": B, "natoms": natoms, "n": n, "method": "rsprfo_bofill", "saddle_order": 1,
+                           "distinct_structures_per_gpu": nuniq, "parity_vs_oracle": worst,
+                           "l2": "inputs larger than L2 (Hessian batch 737 MB / world, fresh copy every step)"},
+                "clocks": clocks,
+                "e2e": {"value": world * B * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * B * n * 8,
+                        "d2h_bytes_per_step": B * n * 8, "note": "Hessian batch resident on the device"},
+                "gpu_launches": 16 * K,
+                "roofline": {"bound": "fp64", "kernel": "whole P-RFO step (dominant: k_lg_tridiag2 cluster tridiagonalisation)",
+                             "achieved": step_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": step_tf / fp64_peak,
+                             "traffic": None, "algorithmic_flops_per_structure": WF,
+                             "peak_source": "in-run DFMA probe (mop_bench_dfma)"},
+                "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": len(chunks), "kind": "port",
+                                 "sample": f"{sample} structures, step-1 calls of oracle RSPRFOOracle timed, one process "
+                                           "per core, 1 BLAS thread each"}}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 (default): BASELINE configs[1], the headline line; c5: configs[4], P-RFO at 3N = 600")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -441,6 +617,9 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload == "c5":
+        run_b200_c5(args, rank, world, local_rank)
+        return
     run_b200(args, rank, world, local_rank)
 
 
