@@ -229,7 +229,7 @@ __device__ __forceinline__ void lg_update_symv(double* __restrict__ base, size_t
                                                const double* __restrict__ vn, double* __restrict__ rpub,
                                                double (&acc)[RL], int abl = 0) {
   // loads in flight per lane: RL * UNR doubles; the whole row set of a column in one to three round trips
-  constexpr int UNR = (RL <= 3) ? 8 : ((RL == 4) ? 6 : ((RL == 5) ? 5 : ((RL == 6) ? 4 : 3)));
+  constexpr int UNR = (RL <= 3) ? 8 : ((RL == 4) ? 6 : ((RL == 5) ? 5 : ((RL == 6) ? 4 : ((RL <= 8) ? 3 : 2))));
 #pragma unroll
   for (int q = 0; q < RL; ++q) acc[q] = 0.0;
   const int jlo = k + 1;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
     if constexpr (RLV <= R) lg_step3<RLV>(cluster, CL, A, n, k, first, W, lane, v, wv, vnew, rpub, pnext, a.ablate);   \
     break;
       switch (rl) {
-        LG_CASE(1) LG_CASE(2) LG_CASE(3) LG_CASE(4) LG_CASE(5) LG_CASE(6) LG_CASE(7) LG_CASE(8)
+        LG_CASE(1) LG_CASE(2) LG_CASE(3) LG_CASE(4) LG_CASE(5) LG_CASE(6) LG_CASE(7) LG_CASE(8) LG_CASE(9) LG_CASE(10)
         default: break;
       }
 #undef LG_CASE
@@ -928,7 +928,11 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     int CL = g_lg_cluster;
     const bool legacy = CL < 0;  // diagnostics: the first-generation kernel (negative cluster size)
     if (legacy) CL = -CL;
-    if (CL != 1 && CL != 2 && CL != 4 && CL != 8) CL = 8;
+    if (CL != 1 && CL != 2 && CL != 4 && CL != 8) {
+      // small batches: one wave of smaller clusters beats two waves of 8 (rows per warp <= 10)
+      CL = 8;
+      if (B * 8 > 148 && B * 4 <= 148 && (n + 4 * 16 - 1) / (4 * 16) <= 10) CL = 4;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CL));
     cfg.stream = stream;
@@ -942,7 +946,7 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     constexpr int T2 = 512;
     const int W = CL * (T2 / 32);
     const int R = (n + W - 1) / W;
-    if (legacy || R > 8) {
+    if (legacy || R > 10) {
       const size_t smem = sizeof(double) * 3 * (size_t)np;
       MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cfg.blockDim = dim3(mop::LG_TRI_THREADS);
@@ -963,7 +967,8 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
       else if (R == 4) LG_LAUNCH2(4);
       else if (R == 5) LG_LAUNCH2(5);
       else if (R == 6) LG_LAUNCH2(6);
-      else LG_LAUNCH2(8);
+      else if (R <= 8) LG_LAUNCH2(8);
+      else LG_LAUNCH2(10);
 #undef LG_LAUNCH2
     }
   }
