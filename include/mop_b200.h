@@ -337,6 +337,9 @@ int mop_debug_latency(double* out, void* stream);
 /* diagnostics: out[0..2] = cycles per bare barrier / reduce-publish-barrier-broadcast round /
  * the same plus a dependent sqrt and two reciprocals, for one CTA of `threads` threads. */
 int mop_debug_large_cluster(int cluster_ctas); /* tuning: CTAs per matrix of MOP_EIGH_LARGE (1, 2, 4, 8; 0 = auto) */
+int mop_debug_tri_packed(int on);       /* tuning: packed two-CTA-per-SM tridiagonalisation in the fused RS-I-RFO path (default 1) */
+int mop_debug_packed_timing(void* buf);   /* diagnostics: [B][16] int64 phase cycles of the packed kernel */
+int mop_debug_packed_threads(int threads); /* tuning: CTA size of the packed kernel (128, 256, 512) */
 int mop_debug_large_ablate(int mask); /* diagnostics: bit0 no trailing stores, bit1 no trailing loads (results invalid) */
 int mop_debug_large_timing(void* buf); /* diagnostics: [B][4] int64 phase cycles of the MOP_EIGH_LARGE reduction */
 int mop_debug_barrier_latency(int threads, double* out, void* stream);

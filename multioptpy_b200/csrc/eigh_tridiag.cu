@@ -56,6 +56,12 @@ struct TriArgs {
   double tmin, tmax;
   long long* dbg;    // optional [B][8] phase clocks (diagnostics)
   int ablate;        // diagnostics only: bit0 skip symv loop, bit1 skip update loop (results invalid)
+  // prefactored mode: T, tau, Q^T gp and the reflector rows (in Vh) come from k_tridiag_packed
+  const double* pf_d;
+  const double* pf_e;
+  const double* pf_tau;
+  const double* pf_gq;
+  const int* pf_flag;
 };
 
 template <int THREADS>
@@ -110,8 +116,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
 
   // ---- load.  Fused mode: the projection kernel writes a bit-symmetric matrix, read it
   // row-wise (coalesced); eigh mode symmetrises arbitrary input. -------------------------
+  const bool prefactored = a.pf_d != nullptr;
   double pn = 0.0;
-  if (a.fused) {
+  if (prefactored) {
+    for (int i = tid; i < n; i += THREADS) {
+      d[i] = a.pf_d[(size_t)b * n + i];
+      e[i] = a.pf_e[(size_t)b * n + i];
+      tau[i] = a.pf_tau[(size_t)b * n + i];
+      gq[i] = a.pf_gq[(size_t)b * n + i];
+    }
+  } else if (a.fused) {
     for (int idx = tid; idx < n * n; idx += THREADS) {
       const int i = idx / n, j = idx - i * n;
       const double v = Ain[idx];
@@ -126,10 +140,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
       pn = fma(v, v, pn);
     }
   }
-  if (a.fused)
+  if (a.fused && !prefactored)
     for (int i = tid; i < n; i += THREADS) gq[i] = a.gp[(size_t)b * n + i];
   if (tid == 0) s_fallback = 0;
-  const double fro = sqrt(block_sum(pn, s_red));
+  double fro = sqrt(block_sum(pn, s_red));
+  if (prefactored) {
+    const int fl = a.pf_flag[b];
+    fro = fl == 2 ? NAN : (fl == 1 ? 0.0 : 1.0);
+  }
   const bool finite_in = isfinite(fro);
   bool identity = !finite_in;   // non-finite input: rsirfo.py:365-369 identity fallback
   const bool trivial = identity || fro == 0.0;
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   // Thread (jc, q) owns the two columns jA = k+1+jc, jB = jA + cols2 and the rows
   // i = k+1+q, +G, ... ; block reductions are done by the warps that hold the q == 0
   // threads only (<= 3 warps), everyone else just adds their published partials.
-  if (!trivial && n > 2) {
+  if (!trivial && n > 2 && !prefactored) {
     double* rb = s_rbuf;  // [2][8] partials: (value, warp)
     int par = 0;
     double xn2;
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
       for (int i = 0; i < 5; ++i) a.dbg[(size_t)b * 16 + 8 + (tid == 0 ? 0 : 5) + i] = seg[i];
 #undef SEG
   }
-  if (!trivial) {
+  if (!trivial && !prefactored) {
     if (tid == 0) {
       if (n >= 2) {
         d[n - 2] = S[(n - 2) * lds + (n - 2)];
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_eigh_tridiag(TriArgs a) {
   TRI_MARK();  // 1: tridiagonalisation (+ Q^T gp)
 
   // spill the reflector rows (needed after S is recycled)
-  if (!trivial)
+  if (!trivial && !prefactored)
     for (int idx = tid; idx < n * n; idx += THREADS) {
       const int i = idx / n, j = idx - i * n;
       if (j > i) Vh[idx] = S[i * lds + j];
@@ -848,7 +866,18 @@ static size_t tri_smem_bytes(int n) {
 }
 
 int mop_tridiag_supported(int n) { return n >= 1 && n <= mop::TRI_MAX_N && tri_smem_bytes(n) <= 227 * 1024; }
-size_t mop_tridiag_workspace_bytes(int B, int n) { return 2 * sizeof(double) * (size_t)B * n * n; }
+// Vh | Dm | d, e, tau, gq | flag  (the last five feed the prefactored mode)
+size_t mop_tridiag_workspace_bytes(int B, int n) {
+  return 2 * sizeof(double) * (size_t)B * n * n + 4 * sizeof(double) * (size_t)B * n + sizeof(int) * (size_t)B + 64;
+}
+int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
+                              double* tau, double* gq, int* flag, cudaStream_t stream);
+static int g_tri_packed = 1;
+// tuning: 1 (default) = packed two-CTA-per-SM tridiagonalisation feeding the fused kernel, 0 = single kernel
+extern "C" int mop_debug_tri_packed(int on) {
+  g_tri_packed = on;
+  return MOP_OK;
+}
 
 template <int T>
 static int launch_tri(int B, const mop::TriArgs& a, size_t smem, cudaStream_t stream) {
@@ -928,5 +957,20 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
   a.tmax = tmax;
   a.dbg = g_tri_dbg;
   a.ablate = g_tri_ablate;
+  if (g_tri_packed && n > 2) {
+    double* pf = (double*)work + 2 * (size_t)B * n * n;
+    double* pd = pf;
+    double* pe = pf + (size_t)B * n;
+    double* pt = pf + 2 * (size_t)B * n;
+    double* pg = pf + 3 * (size_t)B * n;
+    int* pflag = (int*)(pf + 4 * (size_t)B * n);
+    int rc = mop_launch_tridiag_packed(B, n, Hp, gp, a.Vh, pd, pe, pt, pg, pflag, stream);
+    if (rc != MOP_OK) return rc;
+    a.pf_d = pd;
+    a.pf_e = pe;
+    a.pf_tau = pt;
+    a.pf_gq = pg;
+    a.pf_flag = pflag;
+  }
   return launch_tri_any(B, a, stream);
 }

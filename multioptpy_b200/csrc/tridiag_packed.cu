@@ -1,0 +1,272 @@
+// Householder tridiagonalisation on PACKED lower-triangular storage (n <= 160).
+//
+// The full-storage shared-memory kernel (eigh_tridiag.cu) needs 8 n^2 bytes, i.e. one CTA per SM at
+// n = 150, and its column step is latency bound (four barriers, two block reductions and the
+// Householder scalar chain per column: issue slots are ~60 % idle).  Here the matrix is kept as the
+// packed lower triangle, 4 n (n+1) bytes = 90.6 KB at n = 150, so TWO CTAs (two structures) share an
+// SM and fill each other's stalls.  LAPACK dsytd2 (lower) conventions; the reflectors, T and Q^T g are
+// handed to k_eigh_tridiag (prefactored mode) through global memory (L2).
+//
+// Column step k, m = n-k-1 trailing rows, S = THREADS / m_pad threads per index:
+//   symv   thread (i, s): every S-th term of  p_i = sum_{j<=i} L(i,j) v_j + sum_{r>i} L(r,i) v_r
+//          (row part contiguous in the packed row, column part conflict-free across threads),
+//          partial sums combined by shuffles inside the S-group - no shared-memory reduction;
+//   update thread t owns the row pair (k+1+t, n-1-t): every thread touches m+1 elements.
+#include "common.cuh"
+
+namespace mop {
+
+struct PkArgs {
+  int n;
+  const double* A;   // [B][n][n] symmetric input (projected Hessian)
+  const double* gp;  // [B][n] or null
+  double* Vh;        // [B][n][n] reflector k in row k, columns k+2.. (unit entry implicit)
+  double* dd;        // [B][n]
+  double* ee;        // [B][n]
+  double* tau;       // [B][n]
+  double* gq;        // [B][n] Q^T gp
+  int* flag;         // [B] 0 normal, 1 zero matrix, 2 non-finite input
+  long long* dbg;    // optional [B][8] phase cycles
+};
+
+__device__ __forceinline__ int pk(int i, int j) { return ((i * (i + 1)) >> 1) + j; }  // j <= i; n <= 160: fits int
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
+  extern __shared__ double sm[];
+  const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int np = (n + 3) & ~3;
+  double* L = sm;                                  // n (n+1) / 2
+  double* v = L + (((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3);  // np
+  double* w = v + np;                              // np
+  double* gq = w + np;                             // np
+  __shared__ double s_rb[2 * 32 * 2];  // every reduction is a block_sum_k<2>: the two parity buffers stay disjoint
+  int parity = 0;
+  const double* Ain = a.A + (size_t)b * n * n;
+  double* Vh = a.Vh + (size_t)b * n * n;
+
+  double pn[2] = {0.0, 0.0};
+  for (int idx = tid; idx < n * n; idx += THREADS) {
+    const int i = idx / n, j = idx - i * n;
+    const double x = Ain[idx];
+    if (j <= i) L[pk(i, j)] = x;
+    pn[0] = fma(x, x, pn[0]);
+  }
+  for (int i = tid; i < n; i += THREADS) gq[i] = a.gp ? a.gp[(size_t)b * n + i] : 0.0;
+  block_sum_k<2>(pn, s_rb, parity);
+  const double fro = sqrt(pn[0]);
+  const bool nonfinite = !isfinite(fro), trivial = nonfinite || fro == 0.0;
+  if (tid == 0) a.flag[b] = nonfinite ? 2 : (fro == 0.0 ? 1 : 0);
+  if (trivial || n <= 2) {
+    for (int i = tid; i < n; i += THREADS) {
+      a.dd[(size_t)b * n + i] = trivial ? 0.0 : L[pk(i, i)];
+      a.ee[(size_t)b * n + i] = (!trivial && i + 1 < n) ? L[pk(i + 1, i)] : 0.0;
+      a.tau[(size_t)b * n + i] = 0.0;
+      a.gq[(size_t)b * n + i] = gq[i];
+    }
+    return;
+  }
+  // norm^2 of column 0 below the sub-diagonal
+  double xn[2] = {0.0, 0.0};
+  for (int i = 2 + tid; i < n; i += THREADS) xn[0] = fma(L[pk(i, 0)], L[pk(i, 0)], xn[0]);
+  block_sum_k<2>(xn, s_rb, parity);
+  double xn2 = xn[0];
+
+  long long seg[6] = {0, 0, 0, 0, 0, 0}, ts = clock64();
+#define PSEG(i)                             \
+  do {                                      \
+    if (a.dbg) {                            \
+      const long long tn_ = clock64();      \
+      seg[i] += tn_ - ts;                   \
+      ts = tn_;                             \
+    }                                       \
+  } while (0)
+  for (int k = 0; k < n - 2; ++k) {
+    const int m = n - k - 1;  // trailing order; indices k+1 .. n-1
+    const double alpha = L[pk(k + 1, k)];
+    double beta = alpha, tk = 0.0, scal = 0.0;
+    if (xn2 > 0.0) {
+      beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+      tk = (beta - alpha) * fast_rcp(beta);
+      scal = fast_rcp(alpha - beta);
+    }
+    // v (unit entry explicit in shared memory), reflector row to global
+    for (int i = k + 1 + tid; i < n; i += THREADS) {
+      const double vi = (i == k + 1) ? 1.0 : L[pk(i, k)] * scal;
+      v[i] = vi;
+      if (i > k + 1) Vh[(size_t)k * n + i] = vi;
+    }
+    if (tid == 0) {
+      a.dd[(size_t)b * n + k] = L[pk(k, k)];
+      a.ee[(size_t)b * n + k] = beta;
+      a.tau[(size_t)b * n + k] = tk;
+    }
+    __syncthreads();  // (A) v complete
+    PSEG(0);
+    double red[2] = {0.0, 0.0};
+    double pi = 0.0;
+    // S threads per index, S a power of two <= 32 (a group never straddles a warp)
+    int S = 1;
+    while (S < 32 && 2 * S * m <= THREADS) S <<= 1;
+    const int t_idx = tid / S, s = tid - t_idx * S;
+    const bool act = t_idx < m;
+    const int i = k + 1 + t_idx;
+    if (tk != 0.0) {
+      if (act) {
+        // term q of index i: q < i-k -> L(i, k+1+q) v_{k+1+q};  else -> L(r, i) v_r, r = i+1+(q-(i-k))
+        const int nrow = i - k;  // row-part terms (columns k+1 .. i)
+        double a0 = 0.0, a1 = 0.0;
+        const double* Li = L + pk(i, k + 1);
+        const double* vq = v + k + 1;
+        double a2 = 0.0, a3 = 0.0;
+        int q = s;
+        for (; q + 3 * S < nrow; q += 4 * S) {  // four independent loads in flight
+          const double l0 = Li[q], l1 = Li[q + S], l2 = Li[q + 2 * S], l3 = Li[q + 3 * S];
+          const double u0 = vq[q], u1 = vq[q + S], u2 = vq[q + 2 * S], u3 = vq[q + 3 * S];
+          a0 = fma(l0, u0, a0);
+          a1 = fma(l1, u1, a1);
+          a2 = fma(l2, u2, a2);
+          a3 = fma(l3, u3, a3);
+        }
+        for (; q < nrow; q += S) a0 = fma(Li[q], vq[q], a0);
+        // column part: q continues at r = i + 1 + (q - nrow); pk(r + S, i) - pk(r, i) = r S + S (S + 1) / 2
+        int r = i + 1 + (q - nrow);
+        int off = pk(r, i);
+        const int inc0 = (S * (S + 1)) >> 1;
+        for (; r + 3 * S < n; r += 4 * S) {
+          const int o1 = off + r * S + inc0;
+          const int o2 = o1 + (r + S) * S + inc0;
+          const int o3 = o2 + (r + 2 * S) * S + inc0;
+          const double l0 = L[off], l1 = L[o1], l2 = L[o2], l3 = L[o3];
+          const double u0 = v[r], u1 = v[r + S], u2 = v[r + 2 * S], u3 = v[r + 3 * S];
+          a0 = fma(l0, u0, a0);
+          a1 = fma(l1, u1, a1);
+          a2 = fma(l2, u2, a2);
+          a3 = fma(l3, u3, a3);
+          off = o3 + (r + 3 * S) * S + inc0;
+        }
+        for (; r < n; r += S) {
+          a0 = fma(L[off], v[r], a0);
+          off += r * S + inc0;
+        }
+        a0 += a2;
+        a1 += a3;
+        pi = a0 + a1;
+      }
+      PSEG(1);
+      for (int o = S >> 1; o > 0; o >>= 1) pi += __shfl_xor_sync(MOP_FULL_MASK, pi, o);
+      pi *= tk;
+      if (act && s == 0) {
+        const double vi = v[i];
+        red[0] = pi * vi;
+        red[1] = vi * gq[i];
+      }
+      block_sum_k<2>(red, s_rb, parity);  // (C)
+      PSEG(2);
+      const double alpha2 = -0.5 * tk * red[0];
+      if (act && s == 0) {
+        const double vi = v[i];
+        w[i] = fma(alpha2, vi, pi);
+        gq[i] = fma(-tk * red[1], vi, gq[i]);
+      }
+      __syncthreads();  // (D) w complete
+      PSEG(3);
+      // rank-2 update of the lower triangle, row pairs (k+1+t, n-1-t): m+1 elements per pair
+      double nx[2] = {0.0, 0.0};
+      {
+        int S2 = 1;
+        const int npair = (m + 1) >> 1;
+        while (S2 < 32 && 2 * S2 * npair <= THREADS) S2 <<= 1;
+        const int t2 = tid / S2, s2 = tid - t2 * S2;
+        if (t2 < npair) {
+          const int rows[2] = {k + 1 + t2, n - 1 - t2};
+          const int nr = (rows[0] == rows[1]) ? 1 : 2;
+          for (int h = 0; h < nr; ++h) {
+            const int r = rows[h];
+            const double vr = v[r], wr = w[r];
+            double* Lr = L + pk(r, k + 1);
+            const int len = r - k;  // columns k+1 .. r
+            const double* wj = w + k + 1;
+            const double* vj = v + k + 1;
+            int c = s2;
+            if (c == 0) {  // first column of the trailing block: the next Householder column
+              const double x = Lr[0] - fma(vr, wj[0], wr * vj[0]);
+              Lr[0] = x;
+              if (r >= k + 3) nx[0] = fma(x, x, nx[0]);
+              c += S2;
+            }
+            for (; c + 3 * S2 < len; c += 4 * S2) {  // loads first: the compiler cannot prove Lr, w, v disjoint
+              const double l0 = Lr[c], l1 = Lr[c + S2], l2 = Lr[c + 2 * S2], l3 = Lr[c + 3 * S2];
+              const double w0 = wj[c], w1 = wj[c + S2], w2 = wj[c + 2 * S2], w3 = wj[c + 3 * S2];
+              const double u0 = vj[c], u1 = vj[c + S2], u2 = vj[c + 2 * S2], u3 = vj[c + 3 * S2];
+              Lr[c] = l0 - fma(vr, w0, wr * u0);
+              Lr[c + S2] = l1 - fma(vr, w1, wr * u1);
+              Lr[c + 2 * S2] = l2 - fma(vr, w2, wr * u2);
+              Lr[c + 3 * S2] = l3 - fma(vr, w3, wr * u3);
+            }
+            for (; c < len; c += S2) Lr[c] = Lr[c] - fma(vr, wj[c], wr * vj[c]);
+          }
+        }
+      }
+      PSEG(4);
+      block_sum_k<2>(nx, s_rb, parity);  // (E) also publishes the updated triangle
+      PSEG(5);
+      xn2 = nx[0];
+    } else {
+      double nx[2] = {0.0, 0.0};
+      for (int r = k + 3 + tid; r < n; r += THREADS) nx[0] = fma(L[pk(r, k + 1)], L[pk(r, k + 1)], nx[0]);
+      block_sum_k<2>(nx, s_rb, parity);
+      xn2 = nx[0];
+    }
+  }
+  if (tid == 0) {
+    a.dd[(size_t)b * n + n - 2] = L[pk(n - 2, n - 2)];
+    a.ee[(size_t)b * n + n - 2] = L[pk(n - 1, n - 2)];
+    a.tau[(size_t)b * n + n - 2] = 0.0;
+    a.dd[(size_t)b * n + n - 1] = L[pk(n - 1, n - 1)];
+    a.ee[(size_t)b * n + n - 1] = 0.0;
+    a.tau[(size_t)b * n + n - 1] = 0.0;
+  }
+  for (int i2 = tid; i2 < n; i2 += THREADS) a.gq[(size_t)b * n + i2] = gq[i2];
+  if (a.dbg && (tid == 0 || tid == 96))
+    for (int q = 0; q < 6; ++q) a.dbg[(size_t)b * 16 + (tid == 0 ? 0 : 8) + q] = seg[q];
+  (void)lane;
+}
+
+}  // namespace mop
+
+size_t mop_tridiag_packed_smem(int n) {
+  const int np = (n + 3) & ~3;
+  return sizeof(double) * ((((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3) + 3 * (size_t)np);
+}
+
+static int g_pk_threads = 256;
+static long long* g_pk_dbg = nullptr;
+extern "C" int mop_debug_packed_timing(void* buf) {
+  g_pk_dbg = (long long*)buf;
+  return MOP_OK;
+}
+extern "C" int mop_debug_packed_threads(int t) {
+  g_pk_threads = t;
+  return MOP_OK;
+}
+
+// d, e, tau, gq: [B][n]; Vh: [B][n][n]; flag: [B]
+int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
+                              double* tau, double* gq, int* flag, cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  mop::PkArgs a{n, A, gp, Vh, dd, ee, tau, gq, flag, g_pk_dbg};
+  const size_t smem = mop_tridiag_packed_smem(n);
+  if (g_pk_threads == 320) {
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_packed<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mop::k_tridiag_packed<320><<<B, 320, smem, stream>>>(a);
+  } else if (g_pk_threads == 512) {
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_packed<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mop::k_tridiag_packed<512><<<B, 512, smem, stream>>>(a);
+  } else {
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_packed<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mop::k_tridiag_packed<256><<<B, 256, smem, stream>>>(a);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
