@@ -108,7 +108,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
     // S threads per index, S a power of two <= 32 (a group never straddles a warp)
     int S = 1;
     while (S < 32 && 2 * S * m <= THREADS) S <<= 1;
-    const int t_idx = tid / S, s = tid - t_idx * S;
+    // lane -> (index, part) with the PART major inside the warp: a half-warp (one LDS.64 wavefront)
+    // then holds consecutive indices of one part, and rows i, i+1, ... of the packed triangle start
+    // T(i) = i (i+1) / 2 apart, which is a permutation of the 16 double-word banks
+    const int per = 32 / S;
+    const int t_idx = (tid >> 5) * per + (lane % per), s = lane / per;
     const bool act = t_idx < m;
     const int i = k + 1 + t_idx;
     if (tk != 0.0) {
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
         pi = a0 + a1;
       }
       PSEG(1);
-      for (int o = S >> 1; o > 0; o >>= 1) pi += __shfl_xor_sync(MOP_FULL_MASK, pi, o);
+      for (int o = per; o < 32; o <<= 1) pi += __shfl_xor_sync(MOP_FULL_MASK, pi, o);
       pi *= tk;
       if (act && s == 0) {
         const double vi = v[i];
@@ -177,7 +181,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
         int S2 = 1;
         const int npair = (m + 1) >> 1;
         while (S2 < 32 && 2 * S2 * npair <= THREADS) S2 <<= 1;
-        const int t2 = tid / S2, s2 = tid - t2 * S2;
+        const int per2 = 32 / S2;
+        const int t2 = (tid >> 5) * per2 + (lane % per2), s2 = lane / per2;
         if (t2 < npair) {
           const int rows[2] = {k + 1 + t2, n - 1 - t2};
           const int nr = (rows[0] == rows[1]) ? 1 : 2;
@@ -230,7 +235,6 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
   for (int i2 = tid; i2 < n; i2 += THREADS) a.gq[(size_t)b * n + i2] = gq[i2];
   if (a.dbg && (tid == 0 || tid == 96))
     for (int q = 0; q < 6; ++q) a.dbg[(size_t)b * 16 + (tid == 0 ? 0 : 8) + q] = seg[q];
-  (void)lane;
 }
 
 }  // namespace mop
