@@ -81,8 +81,10 @@ _WORK: dict = {}
 
 
 def workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (caller-owned memory for the C ABI)."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer per (device, stream): the library's kernels of one call run on the
+    caller's current stream, so calls issued on different streams must not share scratch."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
     buf = _WORK.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
