@@ -13,6 +13,11 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
                              const double* g, double* Hp_out, double* gp_out, int32_t* status,
                              cudaStream_t stream);
+size_t mop_hessian_update_scratch_bytes(int B, int n);
+int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guards, double* H, const double* s,
+                                    const double* y, const double* x, const double* xp, const double* g,
+                                    const double* gp, const double* state, int state_stride, double* delta_out,
+                                    int32_t* status, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t mop_jacobi_workspace_bytes(int B, int n);
 int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double* evecs,
                            int32_t* status, const int32_t* only_flagged, void* work,
@@ -224,8 +229,9 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   int rc;
   // (1) Hessian update with RAW gradients (rsirfo.py:308-309,1316-1372)
   if (x_prev && method != MOP_UPD_NONE) {
-    rc = mop_launch_hessian_update(B, n, method, 1, 1, H, nullptr, nullptr, x, x_prev, g, g_prev,
-                                   state, MOP_RSIRFO_STATE, nullptr, status, stream);
+    // scratch: the projected-Hessian buffer is not live yet
+    rc = mop_launch_hessian_update_split(B, n, method, 1, 1, H, nullptr, nullptr, x, x_prev, g, g_prev, state,
+                                         MOP_RSIRFO_STATE, nullptr, status, Hp, nn, stream);
     if (rc != MOP_OK) return rc;
   }
   // (2) TR/ROT projection of gradient and effective Hessian (rsirfo.py:337,349-358)

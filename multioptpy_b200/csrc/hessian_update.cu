@@ -184,6 +184,247 @@ k_hessian_update(int n, int method, int mode, int guards, double* __restrict__ H
   if (tid == 0 && status) status[b] = st | MOP_ST_UPDATED | s_flags;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-CTA path (used inside the fused optimizer steps, where scratch is available): the
+// one-CTA-per-structure kernel above is latency-bound (two dependent passes over one structure's
+// Hessian by 256 threads reach ~20 % of the HBM bandwidth) and leaves the GPU idle for small batches.
+//   k_upd_matvec   grid (ceil(n/32), B): u = H s (and H y for the flowchart), four rows per warp in flight
+//   k_upd_scalars  grid B, one warp's worth of arithmetic: guards, damping, scalars, coefficient matrix
+//   k_upd_apply    grid (tile pairs, B): H <- 1/2 (H + H^T) + delta for one 32 x 32 tile pair
+// Scratch per structure: s, y (damped), u, H y  (4 n doubles) + 24 doubles of coefficients / flags.
+constexpr int UPD_SCR_HDR = 24;
+__host__ __device__ inline size_t upd_scratch_doubles(int n) { return 4 * (size_t)n + UPD_SCR_HDR; }
+
+__device__ __forceinline__ bool upd_have_prev(const double* x_all, const double* xp_all, const double* gp_all,
+                                              const double* state, int state_stride, int b) {
+  if (x_all == nullptr) return true;
+  return (xp_all != nullptr) && (gp_all != nullptr) &&
+         (state == nullptr || state[(size_t)b * state_stride + MOP_RS_HAVE_PREV] != 0.0);
+}
+
+__global__ void __launch_bounds__(256)
+k_upd_matvec(int n, int method, const double* __restrict__ Hall, const double* __restrict__ s_all,
+             const double* __restrict__ y_all, const double* __restrict__ x_all, const double* __restrict__ xp_all,
+             const double* __restrict__ g_all, const double* __restrict__ gp_all, const double* __restrict__ state,
+             int state_stride, double* __restrict__ scratch) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (!upd_have_prev(x_all, xp_all, gp_all, state, state_stride, b)) return;
+  const int np = (n + 3) & ~3;
+  double* vs = sm;
+  double* vy = sm + np;
+  const bool flow = method == MOP_UPD_FLOWCHART;
+  for (int i = tid; i < n; i += 256) {
+    const size_t e = (size_t)b * n + i;
+    vs[i] = x_all ? x_all[e] - xp_all[e] : s_all[e];
+    if (flow) vy[i] = x_all ? g_all[e] - gp_all[e] : y_all[e];
+  }
+  __syncthreads();
+  const double* H = Hall + (size_t)b * n * n;
+  double* scr = scratch + (size_t)b * upd_scratch_doubles(n);
+  double* u = scr + UPD_SCR_HDR + 2 * (size_t)n;
+  double* hy = u + n;
+  const int r0 = blockIdx.x * 32 + w * 4;
+  double au[4] = {0, 0, 0, 0}, ah[4] = {0, 0, 0, 0};
+  for (int j = lane; j < n; j += 32) {
+    const double sj = vs[j];
+    const double yj = flow ? vy[j] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = r0 + q;
+      if (r < n) {
+        const double h = H[(size_t)r * n + j];
+        au[q] = fma(h, sj, au[q]);
+        if (flow) ah[q] = fma(h, yj, ah[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double a = warp_sum(au[q]);
+    const double hsum = flow ? warp_sum(ah[q]) : 0.0;
+    if (lane == 0 && r0 + q < n) {
+      u[r0 + q] = a;
+      if (flow) hy[r0 + q] = hsum;
+    }
+  }
+}
+
+// scratch header: [0..15] coefficient matrix, [16] flags, [17] apply (0 / 1)
+__global__ void __launch_bounds__(128)
+k_upd_scalars(int n, int method, int guards, const double* __restrict__ s_all, const double* __restrict__ y_all,
+              const double* __restrict__ x_all, const double* __restrict__ xp_all, const double* __restrict__ g_all,
+              const double* __restrict__ gp_all, const double* __restrict__ state, int state_stride,
+              double* __restrict__ scratch, int32_t* __restrict__ status) {
+  __shared__ double red[40];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* scr = scratch + (size_t)b * upd_scratch_doubles(n);
+  double* vs = scr + UPD_SCR_HDR;
+  double* vy = vs + n;
+  const double* vu = vy + n;
+  const double* hy = vu + n;
+  int st = status ? status[b] : 0;
+  st &= ~(MOP_ST_UPDATED | MOP_ST_UPD_SKIP_SMALL | MOP_ST_UPD_SKIP_CURV | MOP_ST_UPD_TERM_ZEROED | MOP_ST_NO_HISTORY);
+  if (!upd_have_prev(x_all, xp_all, gp_all, state, state_stride, b)) {
+    if (tid == 0) {
+      scr[17] = 0.0;
+      if (status) status[b] = st | MOP_ST_NO_HISTORY;
+    }
+    return;
+  }
+  double pss = 0, psy = 0, pyy = 0;
+  for (int i = tid; i < n; i += 128) {
+    const size_t e = (size_t)b * n + i;
+    const double s = x_all ? x_all[e] - xp_all[e] : s_all[e];
+    const double y = x_all ? g_all[e] - gp_all[e] : y_all[e];
+    vs[i] = s;
+    vy[i] = y;
+    pss = fma(s, s, pss);
+    psy = fma(s, y, psy);
+    pyy = fma(y, y, pyy);
+  }
+  const double ss = block_sum(pss, red);
+  double sy = block_sum(psy, red);
+  const double yy = block_sum(pyy, red);
+  if (guards) {
+    int skip = 0;
+    if (sqrt(ss) < 1e-10 || sqrt(yy) < 1e-10) skip = MOP_ST_UPD_SKIP_SMALL;
+    else if (guards == 1 && sy <= 0.0) skip = MOP_ST_UPD_SKIP_CURV;
+    if (skip) {
+      if (tid == 0) {
+        scr[17] = 0.0;
+        if (status) status[b] = st | skip;
+      }
+      return;
+    }
+  }
+  if (method_has_dd(method)) {
+    bool active = true;
+    if (method == MOP_UPD_BLOCK_BFGS_DD && !(sqrt(ss) > 1e-8)) active = false;
+    if (active) {
+      const double th = dd_theta(ss, sy, method_dd_thr(method));
+      if (th != 1.0) {
+        double p = 0;
+        for (int i = tid; i < n; i += 128) {
+          const double yt = th * vy[i] + (1.0 - th) * vs[i];
+          vy[i] = yt;
+          p = fma(vs[i], yt, p);
+        }
+        sy = block_sum(p, red);
+      }
+    }
+  }
+  int m = method;
+  if (method == MOP_UPD_FLOWCHART) {
+    double pzz = 0, pzs = 0;
+    for (int i = tid; i < n; i += 128) {
+      const double z = vy[i] - hy[i];
+      pzz = fma(z, z, pzz);
+      pzs = fma(z, vs[i], pzs);
+    }
+    const double zz = block_sum(pzz, red);
+    const double zs = block_sum(pzs, red);
+    m = flowchart_select(ss, yy, sy, zz, zs);
+  }
+  double psu = 0, prs = 0, prr = 0;
+  for (int i = tid; i < n; i += 128) {
+    const double r = vy[i] - vu[i];
+    psu = fma(vs[i], vu[i], psu);
+    prs = fma(r, vs[i], prs);
+    prr = fma(r, r, prr);
+  }
+  UpdScalars q;
+  q.ss = ss;
+  q.sy = sy;
+  q.su = block_sum(psu, red);
+  q.rs = block_sum(prs, red);
+  q.rr = block_sum(prr, red);
+  if (tid == 0) {
+    UpdCoef coef;
+    update_coefficients(m, q, coef);
+    for (int a = 0; a < 4; ++a)
+      for (int c = 0; c < 4; ++c) scr[4 * a + c] = coef.c[a][c];
+    scr[16] = (double)coef.flags;
+    scr[17] = 1.0;
+    if (status) status[b] = st | MOP_ST_UPDATED | coef.flags;
+  }
+}
+
+// CTA (I, b) walks the tile pairs (I, J >= I) of one structure; the tiles of pair J+1 are loaded into
+// registers while pair J is computed from shared memory.
+__global__ void __launch_bounds__(UPD_THREADS)
+k_upd_apply(int n, int T, int mode, double* __restrict__ Hall, const double* __restrict__ scratch,
+            double* __restrict__ delta_all) {
+  __shared__ double tA[TILE * (TILE + 1)], tB[TILE * (TILE + 1)];
+  __shared__ double vi_[4][TILE], vj_[4][TILE];
+  __shared__ UpdCoef coef;
+  const int b = blockIdx.y, tid = threadIdx.x, I = blockIdx.x;
+  const double* scr = scratch + (size_t)b * upd_scratch_doubles(n);
+  if (scr[17] == 0.0) return;
+  const int i0 = I * TILE;
+  const double* vs = scr + UPD_SCR_HDR;
+  auto vec = [&](int a, int gidx) -> double {  // a: s, y, u, r = y - u
+    if (gidx >= n) return 0.0;
+    return a < 3 ? vs[(size_t)a * n + gidx] : vs[(size_t)n + gidx] - vs[2 * (size_t)n + gidx];
+  };
+  if (tid < 16) coef.c[tid >> 2][tid & 3] = scr[tid];
+  if (tid < 4 * TILE) vi_[tid / TILE][tid % TILE] = vec(tid / TILE, i0 + tid % TILE);
+  double* H = Hall + (size_t)b * n * n;
+  double* D = (mode == 0) ? delta_all + (size_t)b * n * n : nullptr;
+  constexpr int EPT = TILE * TILE / UPD_THREADS;  // elements per thread and tile
+  double ra[EPT], rb[EPT];
+  auto load = [&](int J) {
+    const int j0 = J * TILE;
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int e = tid + u * UPD_THREADS, r = e >> 5, c = e & 31;
+      const int gi = i0 + r, gj = j0 + c, hi = j0 + r, hj = i0 + c;
+      ra[u] = (gi < n && gj < n) ? H[(size_t)gi * n + gj] : 0.0;
+      rb[u] = (hi < n && hj < n) ? H[(size_t)hi * n + hj] : 0.0;
+    }
+  };
+  if (mode == 1) load(I);
+  for (int J = I; J < T; ++J) {
+    const int j0 = J * TILE;
+    __syncthreads();  // previous pair's reads of the tiles / vj_ are done
+    if (mode == 1) {
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int e = tid + u * UPD_THREADS, r = e >> 5, c = e & 31;
+        tA[r * (TILE + 1) + c] = ra[u];
+        tB[r * (TILE + 1) + c] = rb[u];
+      }
+    }
+    if (tid < 4 * TILE) vj_[tid / TILE][tid % TILE] = vec(tid / TILE, j0 + tid % TILE);
+    __syncthreads();
+    if (mode == 1 && J + 1 < T) load(J + 1);
+    for (int e = tid; e < TILE * TILE; e += UPD_THREADS) {
+      const int r = e >> 5, c = e & 31;
+      {
+        const int gi = i0 + r, gj = j0 + c;
+        if (gi < n && gj < n) {
+          const double vi[4] = {vi_[0][r], vi_[1][r], vi_[2][r], vi_[3][r]};
+          const double vj[4] = {vj_[0][c], vj_[1][c], vj_[2][c], vj_[3][c]};
+          const double d = 0.5 * (coef_delta(coef, vi, vj) + coef_delta(coef, vj, vi));
+          if (mode == 1) H[(size_t)gi * n + gj] = 0.5 * (tA[r * (TILE + 1) + c] + tB[c * (TILE + 1) + r]) + d;
+          else D[(size_t)gi * n + gj] = d;
+        }
+      }
+      if (J != I) {
+        const int gi = j0 + r, gj = i0 + c;
+        if (gi < n && gj < n) {
+          const double vi[4] = {vj_[0][r], vj_[1][r], vj_[2][r], vj_[3][r]};
+          const double vj[4] = {vi_[0][c], vi_[1][c], vi_[2][c], vi_[3][c]};
+          const double d = 0.5 * (coef_delta(coef, vi, vj) + coef_delta(coef, vj, vi));
+          if (mode == 1) H[(size_t)gi * n + gj] = 0.5 * (tB[r * (TILE + 1) + c] + tA[c * (TILE + 1) + r]) + d;
+          else D[(size_t)gi * n + gj] = d;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace mop
 
 static size_t upd_smem_bytes(int n) {
@@ -228,4 +469,43 @@ extern "C" int mop_hessian_update(int B, int n, int method, int mode, int rsirfo
   return mop_launch_hessian_update(B, n, method, mode, rsirfo_guards, H, s, y, nullptr, nullptr,
                                    nullptr, nullptr, nullptr, 0, delta_out, status,
                                    (cudaStream_t)stream);
+}
+
+size_t mop_hessian_update_scratch_bytes(int B, int n) { return sizeof(double) * (size_t)B * mop::upd_scratch_doubles(n); }
+
+// Same contract as mop_launch_hessian_update, three multi-CTA kernels, `scratch` from the caller.
+int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guards, double* H, const double* s,
+                                    const double* y, const double* x, const double* xp, const double* g,
+                                    const double* gp, const double* state, int state_stride, double* delta_out,
+                                    int32_t* status, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+  if (method == MOP_UPD_PCFD_BOFILL) {
+    mop_set_error("pcfd_bofill (O(n^4) null-space perturbation) is not implemented on the device");
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (method < 0 || method > MOP_UPD_MSP) {
+    mop_set_error("unknown Hessian update method id %d", method);
+    return MOP_ERR_INVALID;
+  }
+  if (method == MOP_UPD_NONE || B == 0) return MOP_OK;
+  if (!scratch || scratch_bytes < mop_hessian_update_scratch_bytes(B, n)) {
+    mop_set_error("hessian update: scratch too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  const int np = (n + 3) & ~3;
+  double* scr = (double*)scratch;
+  {
+    dim3 grid((n + 31) / 32, B);
+    mop::k_upd_matvec<<<grid, 256, sizeof(double) * 2 * (size_t)np, stream>>>(n, method, H, s, y, x, xp, g, gp, state,
+                                                                            state_stride, scr);
+    MOP_CHECK_CUDA(cudaGetLastError());
+  }
+  mop::k_upd_scalars<<<B, 128, 0, stream>>>(n, method, guards, s, y, x, xp, g, gp, state, state_stride, scr, status);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  {
+    const int T = (n + mop::TILE - 1) / mop::TILE;
+    dim3 grid(T, B);
+    mop::k_upd_apply<<<grid, mop::UPD_THREADS, 0, stream>>>(n, T, mode, H, scr, delta_out);
+    MOP_CHECK_CUDA(cudaGetLastError());
+  }
+  return MOP_OK;
 }

@@ -433,6 +433,10 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
                              const double* g, double* Hp_out, double* gp_out, int32_t* status,
                              cudaStream_t stream);
+int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guards, double* H, const double* s,
+                                    const double* y, const double* x, const double* xp, const double* g,
+                                    const double* gp, const double* state, int state_stride, double* delta_out,
+                                    int32_t* status, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 extern "C" size_t mop_eigh_workspace_bytes(int B, int n, int algo);
 extern "C" int mop_eigh(int B, int n, int algo, const double* A, double* evals, double* evecs,
                         int32_t* status, void* work, size_t work_bytes, void* stream);
@@ -502,8 +506,9 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
     MOP_CHECK_CUDA(cudaGetLastError());
   }
   if (x_prev && method != MOP_UPD_NONE) {  // biased gradients, small-change skip only (rsprfo.py:1203-1213)
-    rc = mop_launch_hessian_update(B, n, method, 1, 2, H, nullptr, nullptr, x, x_prev, Bg, Bg_prev, state,
-                                   MOP_PRFO_STATE, nullptr, status, stream);
+    // scratch: the eigenvector buffer is not live yet
+    rc = mop_launch_hessian_update_split(B, n, method, 1, 2, H, nullptr, nullptr, x, x_prev, Bg, Bg_prev, state,
+                                         MOP_PRFO_STATE, nullptr, status, evecs, nn, stream);
     if (rc != MOP_OK) return rc;
   }
   {
