@@ -13,6 +13,10 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
                              const double* g, double* Hp_out, double* gp_out, int32_t* status,
                              cudaStream_t stream);
+size_t mop_project_scratch_bytes(int B, int n);
+int mop_launch_project_trrot_split(int B, int n, const double* H, const double* Hbias, const double* x,
+                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, void* scratch,
+                                   size_t scratch_bytes, cudaStream_t stream);
 size_t mop_hessian_update_scratch_bytes(int B, int n);
 int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guards, double* H, const double* s,
                                     const double* y, const double* x, const double* xp, const double* g,
@@ -235,7 +239,9 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
     if (rc != MOP_OK) return rc;
   }
   // (2) TR/ROT projection of gradient and effective Hessian (rsirfo.py:337,349-358)
-  rc = mop_launch_project_trrot(B, n, H, Hbias, x, Bg, Hp, gp, status, stream);
+  // small batches: the multi-CTA projection fills the GPU; large ones: one CTA per structure is as fast
+  rc = B <= 2 * 148 ? mop_launch_project_trrot_split(B, n, H, Hbias, x, Bg, Hp, gp, status, evecs, nn, stream)
+                    : mop_launch_project_trrot(B, n, H, Hbias, x, Bg, Hp, gp, status, stream);
   if (rc != MOP_OK) return rc;
   if (pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG)
     return mop_rsirfo_spectral_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,

@@ -433,6 +433,10 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
                              const double* g, double* Hp_out, double* gp_out, int32_t* status,
                              cudaStream_t stream);
+size_t mop_project_scratch_bytes(int B, int n);
+int mop_launch_project_trrot_split(int B, int n, const double* H, const double* Hbias, const double* x,
+                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, void* scratch,
+                                   size_t scratch_bytes, cudaStream_t stream);
 int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guards, double* H, const double* s,
                                     const double* y, const double* x, const double* xp, const double* g,
                                     const double* gp, const double* state, int state_stride, double* delta_out,
@@ -497,7 +501,9 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
   const bool factored = prfo_factored(n, eigh_algo);
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   // projected gradient (current geometry) and projected pre-update Hessian for the reduction ratio
-  int rc = mop_launch_project_trrot(B, n, H, Hbias, x, Bg, A, gp, status, stream);
+  // small batches: the multi-CTA projection fills the GPU; large ones: one CTA per structure is as fast
+  int rc = B <= 2 * 148 ? mop_launch_project_trrot_split(B, n, H, Hbias, x, Bg, A, gp, status, evecs, nn, stream)
+                        : mop_launch_project_trrot(B, n, H, Hbias, x, Bg, A, gp, status, stream);
   if (rc != MOP_OK) return rc;
   {
     const size_t smem = sizeof(double) * (size_t)n;

@@ -213,6 +213,229 @@ k_project_trrot(int n, const double* __restrict__ Hall, const double* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-CTA path (inside the fused optimizer steps, scratch from the caller): same arithmetic, spread
+// over row / tile blocks so that small batches fill the GPU and the three passes over one structure's
+// Hessian are not serialised inside one CTA.
+//   k_prj_basis  grid B            T, rank, projected gradient
+//   k_prj_w      grid (n/32, B)    W = 1/2 (M0 T + M0^T T) for a block of 32 indices (row + column pass)
+//   k_prj_y      grid B            M = T^T W, Y = W - 1/2 T sym(M)
+//   k_prj_out    grid (tile rows, B)  Hp = S - Y T^T - T Y^T, tile pairs (I, J >= I), register prefetch
+// Scratch per structure: T [6][np] | W -> Y [6][np] | header (rank) 8 doubles.
+__host__ __device__ inline size_t prj_scratch_doubles(int n) { return 12 * (size_t)((n + 3) & ~3) + 8; }
+
+__global__ void __launch_bounds__(PRJ_THREADS)
+k_prj_basis(int n, const double* __restrict__ x_all, const double* __restrict__ g_all, double* __restrict__ gp_all,
+            double* __restrict__ scratch, int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int np = (n + 3) & ~3;
+  double* T = sm;
+  double* raw = T + 6 * np;
+  double* red = raw + 6 * np;
+  double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  const int k = build_trrot_basis(n, x_all + (size_t)b * n, T, np, raw, red);
+  if (tid == 0) {
+    scr[12 * np] = (double)k;
+    if (status) {
+      int st = status[b] & ~MOP_ST_TRROT_RANKDEF;
+      if (k < 6) st |= MOP_ST_TRROT_RANKDEF;
+      status[b] = st;
+    }
+  }
+  for (int i = tid; i < 6 * np; i += PRJ_THREADS) scr[i] = (i / np < k) ? T[i] : 0.0;
+  if (g_all && gp_all) {
+    const double* g = g_all + (size_t)b * n;
+    double cf[6];
+    for (int j = 0; j < k; ++j) {
+      double p = 0.0;
+      for (int i = tid; i < n; i += PRJ_THREADS) p = fma(T[j * np + i], g[i], p);
+      cf[j] = block_sum(p, red);
+    }
+    for (int i = tid; i < n; i += PRJ_THREADS) {
+      double part = 0.0;
+      for (int j = 0; j < k; ++j) part = fma(T[j * np + i], cf[j], part);
+      gp_all[(size_t)b * n + i] = g[i] - part;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PRJ_THREADS)
+k_prj_w(int n, const double* __restrict__ Hall, const double* __restrict__ Hb_all, double* __restrict__ scratch) {
+  extern __shared__ double sm[];  // T [6][np] | colacc [8][6][32]
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int nw = PRJ_THREADS >> 5;
+  const int np = (n + 3) & ~3;
+  double* T = sm;
+  double* cacc = T + 6 * np;
+  double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  double* W = scr + 6 * np;
+  for (int i = tid; i < 6 * np; i += PRJ_THREADS) T[i] = scr[i];
+  __syncthreads();
+  const double* H = Hall + (size_t)b * n * n;
+  const double* Hb = Hb_all ? Hb_all + (size_t)b * n * n : nullptr;
+  const int i0 = blockIdx.x * 32;
+  // column pass: lane owns column i0 + lane, warp w the rows j = w, w + 8, ...
+  double ca[6] = {0, 0, 0, 0, 0, 0};
+  const int col = i0 + lane;
+  if (col < n) {
+    for (int j = w; j < n; j += nw) {
+      double a = H[(size_t)j * n + col];
+      if (Hb) a += Hb[(size_t)j * n + col];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) ca[v] = fma(a, T[v * np + j], ca[v]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 6; ++v) cacc[(w * 6 + v) * 32 + lane] = ca[v];
+  // row pass: warp w owns rows i0 + 4 w .. + 3
+  double ra[4][6];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int v = 0; v < 6; ++v) ra[q][v] = 0.0;
+  const int r0 = i0 + 4 * w;
+  for (int j = lane; j < n; j += 32) {
+    double t[6];
+#pragma unroll
+    for (int v = 0; v < 6; ++v) t[v] = T[v * np + j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = r0 + q;
+      if (r < n) {
+        double a = H[(size_t)r * n + j];
+        if (Hb) a += Hb[(size_t)r * n + j];
+#pragma unroll
+        for (int v = 0; v < 6; ++v) ra[q][v] = fma(a, t[v], ra[q][v]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = r0 + q;
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+      const double rsum = warp_sum(ra[q][v]);
+      if (lane == 0 && r < n) {
+        double csum = 0.0;
+        for (int ww = 0; ww < nw; ++ww) csum += cacc[(ww * 6 + v) * 32 + (r - i0)];
+        W[v * np + r] = 0.5 * rsum + 0.5 * csum;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PRJ_THREADS)
+k_prj_y(int n, double* __restrict__ scratch) {
+  __shared__ double M[36];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = PRJ_THREADS >> 5;
+  const int np = (n + 3) & ~3;
+  double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  const double* T = scr;
+  double* W = scr + 6 * np;
+  const int k = (int)scr[12 * np];
+  for (int e = w; e < k * k; e += nw) {
+    const int a = e / k, c = e - a * k;
+    double p = 0.0;
+    for (int i = lane; i < n; i += 32) p = fma(T[a * np + i], W[c * np + i], p);
+    p = warp_sum(p);
+    if (lane == 0) M[a * 6 + c] = p;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += PRJ_THREADS) {
+    double tv[6];
+    for (int a = 0; a < k; ++a) tv[a] = T[a * np + i];
+    for (int c = 0; c < k; ++c) {
+      double corr = 0.0;
+      for (int a = 0; a < k; ++a) corr = fma(tv[a], 0.5 * (M[a * 6 + c] + M[c * 6 + a]), corr);
+      W[c * np + i] -= 0.5 * corr;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PRJ_THREADS)
+k_prj_out(int n, int TT, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
+          const double* __restrict__ scratch, double* __restrict__ Hp_all) {
+  __shared__ double tA[PT * (PT + 1)], tB[PT * (PT + 1)];
+  __shared__ double ti[12][PT], tj[12][PT];  // rows 0-5: T, 6-11: Y, for the I and J index blocks
+  const int b = blockIdx.y, tid = threadIdx.x, I = blockIdx.x;
+  const int np = (n + 3) & ~3;
+  const double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  const int k = (int)scr[12 * np];
+  const double* H = Hall + (size_t)b * n * n;
+  const double* Hb = Hb_all ? Hb_all + (size_t)b * n * n : nullptr;
+  double* Hp = Hp_all + (size_t)b * n * n;
+  const int i0 = I * PT;
+  for (int e = tid; e < 12 * PT; e += PRJ_THREADS) {
+    const int a = e / PT, r = e - a * PT;
+    ti[a][r] = (i0 + r < n) ? scr[(size_t)a * np + i0 + r] : 0.0;
+  }
+  constexpr int EPT = PT * PT / PRJ_THREADS;
+  double ra[EPT], rb[EPT];
+  auto load = [&](int J) {
+    const int j0 = J * PT;
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int e = tid + u * PRJ_THREADS, r = e >> 5, c = e & 31;
+      int gi = i0 + r, gj = j0 + c;
+      double a = 0.0;
+      if (gi < n && gj < n) {
+        a = H[(size_t)gi * n + gj];
+        if (Hb) a += Hb[(size_t)gi * n + gj];
+      }
+      ra[u] = a;
+      gi = j0 + r;
+      gj = i0 + c;
+      a = 0.0;
+      if (gi < n && gj < n) {
+        a = H[(size_t)gi * n + gj];
+        if (Hb) a += Hb[(size_t)gi * n + gj];
+      }
+      rb[u] = a;
+    }
+  };
+  load(I);
+  for (int J = I; J < TT; ++J) {
+    const int j0 = J * PT;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int e = tid + u * PRJ_THREADS, r = e >> 5, c = e & 31;
+      tA[r * (PT + 1) + c] = ra[u];
+      tB[r * (PT + 1) + c] = rb[u];
+    }
+    for (int e = tid; e < 12 * PT; e += PRJ_THREADS) {
+      const int a = e / PT, r = e - a * PT;
+      tj[a][r] = (j0 + r < n) ? scr[(size_t)a * np + j0 + r] : 0.0;
+    }
+    __syncthreads();
+    if (J + 1 < TT) load(J + 1);
+    for (int e = tid; e < PT * PT; e += PRJ_THREADS) {
+      const int r = e >> 5, c = e & 31;
+      {
+        const int gi = i0 + r, gj = j0 + c;
+        if (gi < n && gj < n) {
+          double v = 0.5 * (tA[r * (PT + 1) + c] + tB[c * (PT + 1) + r]);
+          for (int a = 0; a < k; ++a)
+            v -= __dadd_rn(__dmul_rn(ti[6 + a][r], tj[a][c]), __dmul_rn(ti[a][r], tj[6 + a][c]));  // bit-symmetric
+          Hp[(size_t)gi * n + gj] = v;
+        }
+      }
+      if (J != I) {
+        const int gi = j0 + r, gj = i0 + c;
+        if (gi < n && gj < n) {
+          double v = 0.5 * (tB[r * (PT + 1) + c] + tA[c * (PT + 1) + r]);
+          for (int a = 0; a < k; ++a)
+            v -= __dadd_rn(__dmul_rn(tj[6 + a][r], ti[a][c]), __dmul_rn(tj[a][r], ti[6 + a][c]));  // bit-symmetric
+          Hp[(size_t)gi * n + gj] = v;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace mop
 
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
@@ -242,4 +465,44 @@ extern "C" int mop_project_trrot(int B, int n, const double* H, const double* Hb
   MOP_REQUIRE(!Hp_out || H, "mop_project_trrot: H required with Hp_out");
   return mop_launch_project_trrot(B, n, H, Hbias, x, g, Hp_out, gp_out, status,
                                   (cudaStream_t)stream);
+}
+
+size_t mop_project_scratch_bytes(int B, int n) { return sizeof(double) * (size_t)B * mop::prj_scratch_doubles(n); }
+
+// Same contract as mop_launch_project_trrot, four multi-CTA kernels, `scratch` from the caller.
+int mop_launch_project_trrot_split(int B, int n, const double* H, const double* Hbias, const double* x,
+                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, void* scratch,
+                                   size_t scratch_bytes, cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  const int np = (n + 3) & ~3;
+  if (!scratch || scratch_bytes < mop_project_scratch_bytes(B, n)) {
+    mop_set_error("projection: scratch too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  const size_t smem0 = sizeof(double) * (12 * (size_t)np + 40);
+  if (smem0 > 200 * 1024) {
+    mop_set_error("n = %d too large for the projection kernel", n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  double* scr = (double*)scratch;
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_prj_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+  mop::k_prj_basis<<<B, mop::PRJ_THREADS, smem0, stream>>>(n, x, g, gp_out, scr, status);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  if (!Hp_out) return MOP_OK;
+  {
+    const size_t smem = sizeof(double) * (6 * (size_t)np + 8 * 6 * 32);
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_prj_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n + 31) / 32, B);
+    mop::k_prj_w<<<grid, mop::PRJ_THREADS, smem, stream>>>(n, H, Hbias, scr);
+    MOP_CHECK_CUDA(cudaGetLastError());
+  }
+  mop::k_prj_y<<<B, mop::PRJ_THREADS, 0, stream>>>(n, scr);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  {
+    const int TT = (n + mop::PT - 1) / mop::PT;
+    dim3 grid(TT, B);
+    mop::k_prj_out<<<grid, mop::PRJ_THREADS, 0, stream>>>(n, TT, H, Hbias, scr, Hp_out);
+    MOP_CHECK_CUDA(cudaGetLastError());
+  }
+  return MOP_OK;
 }
