@@ -641,6 +641,9 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
     __syncthreads();
     LG_EMARK();
     // ---- CGS2 inside clusters, one warp per cluster ----
+    // The chain's vectors are columns of S (stride n between consecutive elements): they are copied
+    // once into rows of the dead pivot buffer Dm (contiguous), orthogonalised there with coalesced
+    // accesses, and copied back.
     for (int c0 = wid; c0 < n; c0 += NW) {
       if (cl_s[c0] != c0) continue;
       int cend = c0 + 1;
@@ -648,38 +651,46 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
       if (cend - c0 < 2) continue;
       const int s = blk_s[c0], t = blk_e[c0];
       double* dw = dots + wid * 64;
+      double* R = Dm + (size_t)c0 * lds;  // rows c0 .. cend-1 of Dm belong to this chain
+      for (int p = c0; p < cend; ++p)
+        for (int k = s + lane; k < t; k += 32) R[(size_t)(p - c0) * lds + k] = S[k * lds + p];
+      __syncwarp();
       for (int c = c0 + 1; c < cend; ++c) {
+        double* rc = R + (size_t)(c - c0) * lds;
         double nfirst = 1.0;
         for (int rep = 0; rep < 2; ++rep) {
           for (int p0 = c0; p0 < c; p0 += 64) {
             const int pe = min(c, p0 + 64);
             for (int p = p0; p < pe; ++p) {
+              const double* rp = R + (size_t)(p - c0) * lds;
               double dt = 0.0;
-              for (int k = s + lane; k < t; k += 32) dt = fma(S[k * lds + p], S[k * lds + c], dt);
+              for (int k = s + lane; k < t; k += 32) dt = fma(rp[k], rc[k], dt);
               dt = warp_sum(dt);
               if (lane == 0) dw[p - p0] = dt;
             }
             __syncwarp();
             for (int k = s + lane; k < t; k += 32) {
-              double zc = S[k * lds + c];
-              for (int p = p0; p < pe; ++p) zc = fma(-dw[p - p0], S[k * lds + p], zc);
-              S[k * lds + c] = zc;
+              double zc = rc[k];
+              for (int p = p0; p < pe; ++p) zc = fma(-dw[p - p0], R[(size_t)(p - c0) * lds + k], zc);
+              rc[k] = zc;
             }
             __syncwarp();
           }
           double nn = 0.0;
-          for (int k = s + lane; k < t; k += 32) nn = fma(S[k * lds + c], S[k * lds + c], nn);
+          for (int k = s + lane; k < t; k += 32) nn = fma(rc[k], rc[k], nn);
           nn = sqrt(warp_sum(nn));
           if (rep == 0) nfirst = nn;
           if (!(nn > 1e-2)) {
             if (lane == 0) s_fallback = 1;
           }
           const double sc = nn > 0.0 ? 1.0 / nn : 0.0;
-          for (int k = s + lane; k < t; k += 32) S[k * lds + c] *= sc;
+          for (int k = s + lane; k < t; k += 32) rc[k] *= sc;
           __syncwarp();
           if (rep == 0 && nfirst > 0.7) break;
         }
       }
+      for (int p = c0 + 1; p < cend; ++p)
+        for (int k = s + lane; k < t; k += 32) S[k * lds + p] = R[(size_t)(p - c0) * lds + k];
     }
     __syncthreads();
   } else {
