@@ -337,6 +337,7 @@ int mop_debug_latency(double* out, void* stream);
 /* diagnostics: out[0..2] = cycles per bare barrier / reduce-publish-barrier-broadcast round /
  * the same plus a dependent sqrt and two reciprocals, for one CTA of `threads` threads. */
 int mop_debug_large_cluster(int cluster_ctas); /* tuning: CTAs per matrix of MOP_EIGH_LARGE (1, 2, 4, 8; 0 = auto) */
+int mop_debug_eigh_small_pipeline(int on); /* tuning: mop_eigh at n <= 158 through packed tridiagonalisation + eigh_large stages (default 1) */
 int mop_debug_tri_packed(int on);       /* tuning: packed two-CTA-per-SM tridiagonalisation in the fused RS-I-RFO path (default 1) */
 int mop_debug_packed_timing(void* buf);   /* diagnostics: [B][16] int64 phase cycles of the packed kernel */
 int mop_debug_packed_threads(int threads); /* tuning: CTA size of the packed kernel (128, 256, 512) */

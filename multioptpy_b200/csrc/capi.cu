@@ -69,6 +69,12 @@ extern "C" const char* mop_last_error(void) { return g_err; }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static int g_eigh_small_pipeline = 1;
+extern "C" int mop_debug_eigh_small_pipeline(int on) {
+  g_eigh_small_pipeline = on;
+  return MOP_OK;
+}
+
 static int pick_algo(int algo, int n) {
   if (algo == MOP_EIGH_AUTO)
     return mop_tridiag_supported(n) ? MOP_EIGH_TRIDIAG : (mop_large_supported(n) ? MOP_EIGH_LARGE : MOP_EIGH_JACOBI);
@@ -78,7 +84,10 @@ static int pick_algo(int algo, int n) {
 static size_t eigh_work_bytes(int B, int n, int algo) {
   algo = pick_algo(algo, n);
   size_t jac = align256(mop_jacobi_workspace_bytes(B, n));  // also the fallback of the fast path
-  if (algo == MOP_EIGH_TRIDIAG) return jac + align256(mop_tridiag_workspace_bytes(B, n));
+  if (algo == MOP_EIGH_TRIDIAG) {
+    const size_t a = align256(mop_tridiag_workspace_bytes(B, n)), b = align256(mop_large_workspace_bytes(B, n));
+    return jac + (a > b ? a : b);
+  }
   if (algo == MOP_EIGH_LARGE) return jac + align256(mop_large_workspace_bytes(B, n));
   return jac;
 }
@@ -108,8 +117,12 @@ static int run_eigh(int B, int n, int algo, const double* A, double* evals, doub
       mop_set_error("eigh: the tridiagonal path needs a status array (fallback flags)");
       return MOP_ERR_INVALID;
     }
-    int rc = mop_launch_eigh_tridiag(B, n, A, evals, evecs, status, (char*)work + jac,
-                                     work_bytes - jac, stream);
+    // packed tridiagonalisation + global-memory spectrum + register back-transform (eigh_large.cu) is
+    // 3-4x faster than the single shared-memory kernel when V itself is wanted; mop_debug_tri_packed(0)
+    // selects the latter
+    int rc = g_eigh_small_pipeline
+                 ? mop_launch_eigh_large(B, n, A, evals, evecs, status, (char*)work + jac, work_bytes - jac, stream)
+                 : mop_launch_eigh_tridiag(B, n, A, evals, evecs, status, (char*)work + jac, work_bytes - jac, stream);
     if (rc != MOP_OK) return rc;
     // robust fallback for structures the fast path flagged (no host sync: CTAs of
     // unflagged structures exit immediately)

@@ -719,7 +719,7 @@ template <int NPL>
 __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a) {
   constexpr int NW = LG_BT_THREADS / 32;
   constexpr int CH = 4;  // reflectors staged per barrier
-  extern __shared__ double sm[];  // [2][CH][np]
+  extern __shared__ double sm[];  // [2][CH][np] | tau [np]
   const int n = a.n, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int np = (n + 3) & ~3;
   const int i = blockIdx.x * NW + wid;  // vector (column of Z)
@@ -734,21 +734,38 @@ __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a)
     const int j = lane + 32 * q;
     z[q] = (live && j < n) ? S[(size_t)j * n + i] : 0.0;
   }
-  // reflectors n-3 .. 0 in chunks of CH (descending)
+  // reflectors n-3 .. 0 in chunks of CH (descending); the next chunk travels from global memory to
+  // registers while the current one is applied from shared memory
   const int last = n - 3;
+  constexpr int PFV = (CH * LG_MAX_N + LG_BT_THREADS - 1) / LG_BT_THREADS;  // values per thread and chunk
+  double pf[PFV];
+  auto prefetch = [&](int kc) {
+#pragma unroll
+    for (int t = 0; t < PFV; ++t) {
+      const int idx = tid + t * LG_BT_THREADS;  // (u, j)
+      const int u = idx / n, j = idx - u * n;
+      const int k = kc - u;
+      pf[t] = (u < CH && k >= 0 && j >= k + 1) ? Vh[(size_t)k * n + j] : 0.0;
+    }
+  };
+  if (last >= 0) prefetch(last);
+  double* tau_s = sm + 2 * (size_t)CH * np;  // a global load per reflector would sit on the critical path
+  for (int j = tid; j < n; j += LG_BT_THREADS) tau_s[j] = tau[j];
   int buf = 0;
   for (int kc = last; kc >= 0; kc -= CH) {
     double* vb = sm + (size_t)buf * CH * np;
-    for (int u = 0; u < CH; ++u) {
-      const int k = kc - u;
-      if (k < 0) break;
-      for (int j = tid; j < n; j += LG_BT_THREADS) vb[u * np + j] = (j >= k + 1) ? Vh[(size_t)k * n + j] : 0.0;
+#pragma unroll
+    for (int t = 0; t < PFV; ++t) {
+      const int idx = tid + t * LG_BT_THREADS;
+      const int u = idx / n, j = idx - u * n;
+      if (u < CH) vb[u * np + j] = pf[t];
     }
     __syncthreads();
+    if (kc - CH >= 0) prefetch(kc - CH);
     for (int u = 0; u < CH; ++u) {
       const int k = kc - u;
       if (k < 0) break;
-      const double tk = tau[k];
+      const double tk = tau_s[k];
       if (tk == 0.0) continue;
       const double* vk = vb + u * np;
       const int q0 = (k + 1) >> 5;
@@ -889,13 +906,16 @@ size_t mop_large_workspace_bytes(int B, int n) {
 template <int NPL>
 static int lg_launch_bt(int B, const mop::LgArgs& a, cudaStream_t stream) {
   const int np = (a.n + 3) & ~3;
-  const size_t smem = sizeof(double) * 2 * 4 * (size_t)np;
+  const size_t smem = sizeof(double) * (2 * 4 + 1) * (size_t)np;
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_backtransform<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((a.n + (mop::LG_BT_THREADS / 32) - 1) / (mop::LG_BT_THREADS / 32), B);
   mop::k_lg_backtransform<NPL><<<grid, mop::LG_BT_THREADS, smem, stream>>>(a);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
+
+int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
+                              double* tau, double* gq, int* flag, cudaStream_t stream);
 
 static void lg_carve(int B, int n, void* work, mop::LgArgs& a) {
   const size_t nn = lg_al(sizeof(double) * (size_t)B * n * n), nv = lg_al(sizeof(double) * (size_t)B * n);
@@ -935,7 +955,14 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     MOP_CHECK_CUDA(cudaGetLastError());
   }
   const int np = (n + 3) & ~3;
-  {
+  if (n <= 160 && g_lg_cluster == 0) {
+    // the matrix fits one SM: the packed shared-memory tridiagonalisation (two structures per SM) replaces
+    // the cluster kernel; same outputs (reflector rows with explicit unit entries, d, e, tau)
+    double* gq_dummy = a.pbuf;
+    int* flag = (int*)(a.pbuf + (size_t)B * n);
+    int rc = mop_launch_tridiag_packed(B, n, a.A, nullptr, a.Vh, a.dd, a.ee, a.tau, gq_dummy, flag, stream);
+    if (rc != MOP_OK) return rc;
+  } else {
     int CL = g_lg_cluster;
     const bool legacy = CL < 0;  // diagnostics: the first-generation kernel (negative cluster size)
     if (legacy) CL = -CL;

@@ -459,7 +459,7 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 // large systems: the step is taken in the basis of the tridiagonal matrix (eigh_large.cu, part 4)
 static bool prfo_factored(int n, int eigh_algo) {
   if (eigh_algo == MOP_EIGH_LARGE) return mop_large_supported(n) != 0;
-  return eigh_algo == MOP_EIGH_AUTO && !mop_tridiag_supported(n) && mop_large_supported(n);
+  return eigh_algo == MOP_EIGH_AUTO && mop_large_supported(n);  // small n: packed front end (eigh_large.cu)
 }
 
 // workspace: Hp/A | evecs | evals | gp | 4 rotated vectors | eigh work

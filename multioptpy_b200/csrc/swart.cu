@@ -33,12 +33,16 @@ __device__ __forceinline__ double swart_screen(const double* xyz, const double* 
   return exp(1.0 - d / cs);
 }
 
-// H[rows of atom a][cols of atom c] += h * u u'^T for all atom pairs of a term with nat atoms
+// upper triangle of H += h * u u^T over the atoms of one term (the kernel mirrors it at the end: the
+// accumulation is atomic-throughput bound, the symmetric half would cost 1.8x the atomics)
 __device__ __forceinline__ void add_outer(double* H, int n, const int* at, int nat, const double* u, double h) {
   for (int p = 0; p < 3 * nat; ++p) {
     const int gp = 3 * at[p / 3] + p % 3;
     const double hp = h * u[p];
-    for (int q = 0; q < 3 * nat; ++q) atomicAdd(&H[(size_t)gp * n + 3 * at[q / 3] + q % 3], hp * u[q]);
+    for (int q = 0; q < 3 * nat; ++q) {
+      const int gq = 3 * at[q / 3] + q % 3;
+      if (gq >= gp) atomicAdd(&H[(size_t)gp * n + gq], hp * u[q]);
+    }
   }
 }
 
@@ -204,8 +208,11 @@ k_swart(int N, int in_smem, const double* __restrict__ xyz_all, const double* __
     __syncthreads();
   }
   if (tid == 0 && status) status[b] = s_bad;
-  if (in_smem)
-    for (int e = tid; e < n * n; e += SW_THREADS) Hg[e] = Hs[e];
+  // mirror the accumulated upper triangle and write out
+  for (int e = tid; e < n * n; e += SW_THREADS) {
+    const int r = e / n, c = e - r * n;
+    Hg[e] = (c >= r) ? H[e] : H[(size_t)c * n + r];
+  }
 }
 
 }  // namespace mop

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
   if (tid == 0) a.flag[b] = nonfinite ? 2 : (fro == 0.0 ? 1 : 0);
   if (trivial || n <= 2) {
     for (int i = tid; i < n; i += THREADS) {
-      a.dd[(size_t)b * n + i] = trivial ? 0.0 : L[pk(i, i)];
+      a.dd[(size_t)b * n + i] = nonfinite ? NAN : (trivial ? 0.0 : L[pk(i, i)]);
       a.ee[(size_t)b * n + i] = (!trivial && i + 1 < n) ? L[pk(i + 1, i)] : 0.0;
       a.tau[(size_t)b * n + i] = 0.0;
       a.gq[(size_t)b * n + i] = gq[i];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
     for (int i = k + 1 + tid; i < n; i += THREADS) {
       const double vi = (i == k + 1) ? 1.0 : L[pk(i, k)] * scal;
       v[i] = vi;
-      if (i > k + 1) Vh[(size_t)k * n + i] = vi;
+      Vh[(size_t)k * n + i] = vi;  // unit entry written too (the large-n consumers read it, the fused kernel ignores it)
     }
     if (tid == 0) {
       a.dd[(size_t)b * n + k] = L[pk(k, k)];
