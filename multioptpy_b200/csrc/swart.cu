@@ -215,6 +215,229 @@ k_swart(int N, int in_smem, const double* __restrict__ xyz_all, const double* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Gather formulation (natoms <= 100): no atomics.  Every 3 x 3 atom-pair block of the raw Hessian is
+// owned by one thread (off-diagonal blocks) or one warp (diagonal blocks), which sums the stretch term
+// and every bend term that touches both atoms, re-evaluating the bend's Wilson vectors where needed
+// (a bend (i, j, k) feeds six blocks, so it is evaluated six times: ~1e7 flops per structure at
+// N = 50 against ~6e5 FP64 shared-memory atomics, which cost ~30 cycles each in the scatter kernel).
+struct SwartBend {
+  int nvec;        // 1 or 2 Wilson vectors
+  double hb;       // force constant
+  double U[2][9];  // (i, j, k) components
+};
+
+// bend (i, j, k), i < k, centre j; l1 = |x_i - x_j|, l2 = |x_k - x_j|, ss = s_ij s_jk (swart.py:226-315)
+__device__ __forceinline__ void swart_bend_eval(const double* xyz, int i, int j, int k, double l1, double l2, double ss,
+                                                SwartBend& o) {
+  const SwartConst C;
+  // reciprocals once (FP64 division is ~20 instructions): differs from the reference's divisions by
+  // an ulp, far below the 1e-10 parity bar
+  const double il1 = 1.0 / l1, il2 = 1.0 / l2;
+  double v1[3], v2[3], n1[3], n2[3];
+  for (int c = 0; c < 3; ++c) {
+    v1[c] = xyz[3 * i + c] - xyz[3 * j + c];
+    v2[c] = xyz[3 * k + c] - xyz[3 * j + c];
+    n1[c] = v1[c] * il1;
+    n2[c] = v2[c] * il2;
+  }
+  double cs = n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2];
+  cs = fmin(fmax(cs, -1.0), 1.0);
+  const double s2 = fmax(1e-12, 1.0 - cs * cs);
+  const double sn = sqrt(s2);
+  const double iden = 1.0 / fmax(sn, 1e-6);
+  const double f1 = il1 * iden, f2 = il2 * iden;
+  double bn[9];
+  for (int c = 0; c < 3; ++c) {
+    bn[c] = (cs * n1[c] - n2[c]) * f1;
+    bn[6 + c] = (cs * n2[c] - n1[c]) * f2;
+    bn[3 + c] = -(bn[c] + bn[6 + c]);
+  }
+  const double w = C.f + (1.0 - C.f) * sn;
+  o.hb = 0.075 * (ss * ss) * (w * w);
+  o.nvec = 1;
+  const double th1 = cs > 1.0 - C.tolth ? 1.0 - cs : 1.0 + cs;
+  if (!(th1 < C.tolth)) {
+    for (int c = 0; c < 9; ++c) o.U[0][c] = bn[c];
+    return;
+  }
+  const double q = th1 / C.tolth;
+  const double sl = (1.0 - q * q) * (1.0 - q * q);
+  if (!(cs > 1.0 - C.tolth)) {
+    for (int c = 0; c < 9; ++c) o.U[0][c] = (1.0 - sl) * bn[c];
+    return;
+  }
+  double vn[3];
+  cross3(v1, v2, vn);
+  double nvn = norm3(vn);
+  if (nvn < 1e-12) {
+    const double sc1 = v1[0] / (l1 * l1);
+    double cand[3] = {1.0 - sc1 * v1[0], -sc1 * v1[1], -sc1 * v1[2]};
+    double cn = norm3(cand);
+    if (!(cn >= 1e-12)) {
+      const double sc2 = v1[1] / (l1 * l1);
+      cand[0] = -sc2 * v1[0]; cand[1] = 1.0 - sc2 * v1[1]; cand[2] = -sc2 * v1[2];
+      cn = fmax(norm3(cand), 1e-12);
+    }
+    vn[0] = cand[0]; vn[1] = cand[1]; vn[2] = cand[2];
+    nvn = cn;
+  }
+  nvn = fmax(nvn, 1e-12);
+  double vd[3], vn2[3];
+  for (int c = 0; c < 3; ++c) {
+    vn[c] /= nvn;
+    vd[c] = v1[c] - v2[c];
+  }
+  cross3(vd, vn, vn2);
+  const double n2n = fmax(norm3(vn2), 1e-12);
+  o.nvec = 2;
+  for (int c = 0; c < 3; ++c) {
+    const double t = vn2[c] / n2n;
+    o.U[0][c] = vn[c] * il1;
+    o.U[0][6 + c] = vn[c] * il2;
+    o.U[0][3 + c] = -o.U[0][c] - o.U[0][6 + c];
+    const double l0 = t * il1, l6 = t * il2;
+    o.U[1][c] = sl * l0 + (1.0 - sl) * bn[c];
+    o.U[1][6 + c] = sl * l6 + (1.0 - sl) * bn[6 + c];
+    o.U[1][3 + c] = sl * (-l0 - l6) + (1.0 - sl) * bn[3 + c];
+  }
+}
+
+// blk += hb sum_v U_v[sa .. sa+2] U_v[sb .. sb+2]^T
+__device__ __forceinline__ void swart_acc(double* blk, const SwartBend& o, int sa, int sb) {
+  for (int v = 0; v < o.nvec; ++v)
+    for (int p = 0; p < 3; ++p) {
+      const double hp = o.hb * o.U[v][sa + p];
+      for (int q = 0; q < 3; ++q) blk[3 * p + q] = fma(hp, o.U[v][sb + q], blk[3 * p + q]);
+    }
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+k_swart_gather(int N, const double* __restrict__ xyz_all, const double* __restrict__ rad_all, int rad_stride,
+               double* __restrict__ H_all, int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  const SwartConst C;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = 3 * N;
+  double* xyz = sm;          // 3N
+  double* rad = xyz + 3 * N; // N
+  double* D = rad + N;       // N x N distances (clamped)
+  double* Sc = D + N * N;    // N x N screening, 0 on the diagonal
+  __shared__ int s_bad;
+  double* H = H_all + (size_t)b * n * n;
+  for (int i = tid; i < 3 * N; i += SW_THREADS) xyz[i] = xyz_all[(size_t)b * 3 * N + i];
+  for (int i = tid; i < N; i += SW_THREADS) rad[i] = rad_all[(size_t)b * rad_stride + i];
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  for (int e = tid; e < N * N; e += SW_THREADS) {
+    const int i = e / N, j = e - i * N;
+    if (i > j) continue;
+    double d = 1.0, s = 0.0;
+    if (i != j) s = swart_screen(xyz, rad, i, j, &d);
+    D[i * N + j] = d; D[j * N + i] = d;
+    Sc[i * N + j] = s; Sc[j * N + i] = s;
+  }
+  __syncthreads();
+  // a bend (i, j, k) exists iff both ends are neighbours of the centre and the product screen passes
+  auto pass = [&](int j, int i, int k, double* ss) -> bool {
+    const double si = Sc[j * N + i], sk = Sc[j * N + k];
+    if (!(si >= C.eps2 && sk >= C.eps2)) return false;
+    *ss = si * sk;
+    return *ss >= C.eps1 && D[i * N + j] > 1e-8 && D[k * N + j] > 1e-8;
+  };
+  for (int round = 0; round < 2; ++round) {
+    const bool bends = round == 0;
+    // ---- off-diagonal blocks (a < b): one thread each ----
+    for (int e = tid; e < N * N; e += SW_THREADS) {
+      const int a = e / N, bb = e - a * N;
+      if (a >= bb) continue;
+      double blk[9];
+      {
+        const double d = D[a * N + bb], s = Sc[a * N + bb], h = -0.35 * (s * s * s);
+        double ev[3];
+        for (int c = 0; c < 3; ++c) ev[c] = (xyz[3 * a + c] - xyz[3 * bb + c]) / d;
+        for (int p = 0; p < 3; ++p)
+          for (int q = 0; q < 3; ++q) blk[3 * p + q] = h * ev[p] * ev[q];
+      }
+      if (bends) {
+        SwartBend o;
+        double ss;
+        for (int c = 0; c < N; ++c) {
+          if (c == a || c == bb) continue;
+          if (pass(c, a, bb, &ss)) {  // centre c, ends a < b
+            swart_bend_eval(xyz, a, c, bb, D[a * N + c], D[bb * N + c], ss, o);
+            swart_acc(blk, o, 0, 6);
+          }
+          {  // centre a, ends b and c
+            const int i = bb < c ? bb : c, k = bb < c ? c : bb;
+            if (pass(a, i, k, &ss)) {
+              swart_bend_eval(xyz, i, a, k, D[i * N + a], D[k * N + a], ss, o);
+              swart_acc(blk, o, 3, bb == i ? 0 : 6);
+            }
+          }
+          {  // centre b, ends a and c
+            const int i = a < c ? a : c, k = a < c ? c : a;
+            if (pass(bb, i, k, &ss)) {
+              swart_bend_eval(xyz, i, bb, k, D[i * N + bb], D[k * N + bb], ss, o);
+              swart_acc(blk, o, a == i ? 0 : 6, 3);
+            }
+          }
+        }
+      }
+      int bad = 0;
+      for (int p = 0; p < 3; ++p)
+        for (int q = 0; q < 3; ++q) {
+          const double x = blk[3 * p + q];
+          bad |= !isfinite(x);
+          H[(size_t)(3 * a + p) * n + 3 * bb + q] = x;
+          H[(size_t)(3 * bb + q) * n + 3 * a + p] = x;
+        }
+      if (bad) s_bad = 1;
+    }
+    // ---- diagonal blocks: one warp each, lanes split the third-atom loop ----
+    for (int a = wid; a < N; a += SW_WARPS) {
+      double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = lane; c < N; c += 32) {
+        if (c == a) continue;
+        const double d = D[a * N + c], s = Sc[a * N + c], h = 0.35 * (s * s * s);
+        double ev[3];
+        for (int p = 0; p < 3; ++p) ev[p] = (xyz[3 * a + p] - xyz[3 * c + p]) / d;
+        for (int p = 0; p < 3; ++p)
+          for (int q = 0; q < 3; ++q) blk[3 * p + q] = fma(h * ev[p], ev[q], blk[3 * p + q]);
+        if (!bends) continue;
+        SwartBend o;
+        double ss;
+        for (int c2 = 0; c2 < N; ++c2) {
+          if (c2 == a || c2 == c) continue;
+          if (c2 > c && pass(a, c, c2, &ss)) {  // centre a, ends c < c2
+            swart_bend_eval(xyz, c, a, c2, D[c * N + a], D[c2 * N + a], ss, o);
+            swart_acc(blk, o, 3, 3);
+          }
+          {  // centre c, ends a and c2
+            const int i = a < c2 ? a : c2, k = a < c2 ? c2 : a;
+            if (pass(c, i, k, &ss)) {
+              swart_bend_eval(xyz, i, c, k, D[i * N + c], D[k * N + c], ss, o);
+              const int sa = a == i ? 0 : 6;
+              swart_acc(blk, o, sa, sa);
+            }
+          }
+        }
+      }
+      int bad = 0;
+      for (int p = 0; p < 9; ++p) {
+        blk[p] = warp_sum(blk[p]);
+        bad |= !isfinite(blk[p]);
+      }
+      if (lane < 9) H[(size_t)(3 * a + lane / 3) * n + 3 * a + lane % 3] = blk[lane];
+      if (bad && lane == 0) s_bad = 1;
+    }
+    __syncthreads();
+    if (!s_bad || !bends) break;  // non-finite: redo with the stretch terms only (swart.py:340-350)
+  }
+  if (tid == 0 && status) status[b] = s_bad;
+}
+
 }  // namespace mop
 
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
@@ -249,6 +472,13 @@ extern "C" int mop_swart_hessian(int B, int natoms, const double* xyz, const dou
     Hraw = (double*)work;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (natoms <= 100) {  // gather kernel: no atomics
+    const size_t smem = sizeof(double) * (4 * (size_t)natoms + 2 * (size_t)natoms * natoms);
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_swart_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mop::k_swart_gather<<<B, mop::SW_THREADS, smem, stream>>>(natoms, xyz, radii, radii_stride, Hraw, status);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, stream);
+  }
   bool in_smem = swart_smem(natoms, true) <= 220 * 1024;
   const size_t smem = swart_smem(natoms, in_smem);
   if (smem > 220 * 1024) {

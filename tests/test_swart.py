@@ -50,13 +50,13 @@ def test_gpu_swart_vs_golden(golden_dir):
 
 @pytest.mark.gpu
 def test_gpu_swart_batched_and_large(golden_dir):
-    """Tensor mode over a batch of distinct geometries, and the global-memory accumulation path
-    (n > 156) against the oracle."""
+    """Tensor mode over a batch of distinct geometries (gather kernel, natoms <= 100) and the
+    scatter kernel with global-memory accumulation (natoms > 100) against the oracle."""
     import torch
     from multioptpy_b200 import synthetic
     from multioptpy_b200.ModelHessian.approx_hessian import ApproxHessian
     from multioptpy_b200.ModelHessian.swart import swart_radii
-    for natoms, B in ((24, 5), (60, 2)):
+    for natoms, B in ((24, 5), (60, 2), (104, 1)):
         elems = synthetic.elements(natoms)
         xs = np.stack([synthetic.grid_geometry(natoms, np.random.default_rng(90 + b), spacing=2.6, jitter=0.25) for b in range(B)])
         H = ApproxHessian(device="cuda:0").main(torch.from_numpy(xs).cuda(), elems, None, "swart").cpu().numpy()
