@@ -13,7 +13,7 @@
 
 namespace mop {
 
-constexpr int MH_THREADS = 512;
+constexpr int MH_THREADS = 256;
 constexpr double PI_D = 3.141592653589793;
 
 struct ICRec {      // one internal coordinate
@@ -103,7 +103,7 @@ __device__ __forceinline__ double sin_sq_angle(const double* xa, const double* x
 
 // ---------------------------------------------------------------------------------------
 // kind 0: connectivity tables only; kind 1: Fischer (ModelHessian/fischer.py)
-__global__ void __launch_bounds__(MH_THREADS, 1)
+__global__ void __launch_bounds__(MH_THREADS, 4)
 k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const double* __restrict__ rad_all,
                 int rad_stride, double factor, int capB, int capA, int capD, int* __restrict__ bonds_all,
                 int* __restrict__ angles_all, int* __restrict__ dihs_all, int* __restrict__ counts_all,
@@ -241,7 +241,7 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
 // decomposed parity check).
 // atom parameters prm[a][6] = {cov radius, period index 0/1/2, mass, UFF distance, UFF well
 // depth, UFF effective charge}.
-__global__ void __launch_bounds__(MH_THREADS, 1)
+__global__ void __launch_bounds__(MH_THREADS, 4)
 k_lindh(int N, const double* __restrict__ xyz_all, const double* __restrict__ prm_all, int prm_stride,
         int capB, int capA, int capD, int* __restrict__ bonds_all, int* __restrict__ angles_all,
         int* __restrict__ dihs_all, int* __restrict__ counts_all, double* __restrict__ fc_all,
@@ -293,25 +293,27 @@ k_lindh(int N, const double* __restrict__ xyz_all, const double* __restrict__ pr
     fc[t] = f;
   }
   __syncthreads();
-  // accumulate into the pair diagonal in table order (one thread: deterministic, as the reference)
-  if (tid == 0) {
+  // accumulate into the pair diagonal: one thread per internal coordinate, FP64 shared-memory atomics
+  // (a single thread walking the tables in global memory cost ~1e6 cycles per structure; the summation
+  // order differs from the reference's by rounding only)
+  {
     auto pidx = [N](int i, int j) { if (i > j) { const int t = i; i = j; j = t; } return i * N - i * (i + 1) / 2 + (j - i - 1); };
-    for (int t = 0; t < nrec; ++t) {
+    for (int t = tid; t < nrec; t += MH_THREADS) {
       const double f = fc[t];
       if (t < T.nb) {
         const int i = T.bonds[2 * t], j = T.bonds[2 * t + 1];
         const int lo = i < j ? i : j, hi = i < j ? j : i;
         const double m1 = prm[6 * lo + 2], m2 = prm[6 * hi + 2];
-        kd[pidx(i, j)] += f / ((m1 * m2) / (m1 + m2));
+        atomicAdd(&kd[pidx(i, j)], f / ((m1 * m2) / (m1 + m2)));
       } else if (t < T.nb + T.na) {
         const int* a = T.angles + 3 * (t - T.nb);
-        kd[pidx(a[0], a[1])] += f;
-        kd[pidx(a[1], a[2])] += f;
+        atomicAdd(&kd[pidx(a[0], a[1])], f);
+        atomicAdd(&kd[pidx(a[1], a[2])], f);
       } else {
         const int* a = T.dihs + 4 * (t - T.nb - T.na);
-        kd[pidx(a[0], a[1])] += f;
-        kd[pidx(a[1], a[2])] += f;
-        kd[pidx(a[2], a[3])] += f;
+        atomicAdd(&kd[pidx(a[0], a[1])], f);
+        atomicAdd(&kd[pidx(a[1], a[2])], f);
+        atomicAdd(&kd[pidx(a[2], a[3])], f);
       }
     }
   }
