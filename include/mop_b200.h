@@ -114,10 +114,13 @@ const char* mop_last_error(void);
  * mode 1: H <- 1/2 ((H + delta) + (H + delta)^T) in place, as
  *         RSIRFO.update_hessian does (Optimizer/rsirfo.py:1361-1372), with its
  *         skip rules (:1326,:1333) when rsirfo_guards != 0.
- * s, y: [B][n] displacement and gradient difference. */
+ * s, y: [B][n] displacement and gradient difference.
+ * work (optional, mop_hessian_update_workspace_bytes): with it the update runs as three multi-CTA kernels
+ * (row-block H s, per-structure coefficients, tile-row apply); with work = NULL as one CTA per structure. */
+size_t mop_hessian_update_workspace_bytes(int B, int n);
 int mop_hessian_update(int B, int n, int method, int mode, int rsirfo_guards, double* H,
                        const double* s, const double* y, double* delta_out, int32_t* status,
-                       void* stream);
+                       void* work, size_t work_bytes, void* stream);
 
 /* ---- (2a) TR/ROT projection ---------------------------------------------
  * Replaces Calculationtools.project_out_hess_tr_and_rot_for_coord

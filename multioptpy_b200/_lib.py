@@ -27,7 +27,8 @@ _sz = C.c_size_t
 SIGNATURES = {
     "mop_version": (_i, []),
     "mop_last_error": (C.c_char_p, []),
-    "mop_hessian_update": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "mop_hessian_update_workspace_bytes": (_sz, [_i, _i]),
+    "mop_hessian_update": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mop_project_trrot": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mop_eigh_workspace_bytes": (_sz, [_i, _i, _i]),
     "mop_eigh": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),

@@ -352,13 +352,16 @@ k_upd_scalars(int n, int method, int guards, const double* __restrict__ s_all, c
 }
 
 // CTA (I, b) walks the tile pairs (I, J >= I) of one structure; the tiles of pair J+1 are loaded into
-// registers while pair J is computed from shared memory.
+// registers while pair J is computed from shared memory.  With Cs = 1/2 (C + C^T) the symmetrised update of
+// element (i, j) is v_i^T Cs v_j = sum_a v_i[a] t_j[a], t_j = Cs v_j staged once per column (4 FMAs per
+// element); every value is computed once and its mirror image written from shared memory, so the result is
+// exactly symmetric and both global writes are coalesced.
 __global__ void __launch_bounds__(UPD_THREADS)
 k_upd_apply(int n, int T, int mode, double* __restrict__ Hall, const double* __restrict__ scratch,
             double* __restrict__ delta_all) {
   __shared__ double tA[TILE * (TILE + 1)], tB[TILE * (TILE + 1)];
-  __shared__ double vi_[4][TILE], vj_[4][TILE];
-  __shared__ UpdCoef coef;
+  __shared__ double vi_[4][TILE], tj_[4][TILE];
+  __shared__ double cs[4][4];
   const int b = blockIdx.y, tid = threadIdx.x, I = blockIdx.x;
   const double* scr = scratch + (size_t)b * upd_scratch_doubles(n);
   if (scr[17] == 0.0) return;
@@ -368,10 +371,11 @@ k_upd_apply(int n, int T, int mode, double* __restrict__ Hall, const double* __r
     if (gidx >= n) return 0.0;
     return a < 3 ? vs[(size_t)a * n + gidx] : vs[(size_t)n + gidx] - vs[2 * (size_t)n + gidx];
   };
-  if (tid < 16) coef.c[tid >> 2][tid & 3] = scr[tid];
+  if (tid < 16) cs[tid >> 2][tid & 3] = 0.5 * (scr[tid] + scr[4 * (tid & 3) + (tid >> 2)]);
   if (tid < 4 * TILE) vi_[tid / TILE][tid % TILE] = vec(tid / TILE, i0 + tid % TILE);
   double* H = Hall + (size_t)b * n * n;
   double* D = (mode == 0) ? delta_all + (size_t)b * n * n : nullptr;
+  double* O = mode == 1 ? H : D;
   constexpr int EPT = TILE * TILE / UPD_THREADS;  // elements per thread and tile
   double ra[EPT], rb[EPT];
   auto load = [&](int J) {
@@ -387,39 +391,47 @@ k_upd_apply(int n, int T, int mode, double* __restrict__ Hall, const double* __r
   if (mode == 1) load(I);
   for (int J = I; J < T; ++J) {
     const int j0 = J * TILE;
-    __syncthreads();  // previous pair's reads of the tiles / vj_ are done
-    if (mode == 1) {
+    __syncthreads();  // previous pair is done with the tiles and t_j
 #pragma unroll
-      for (int u = 0; u < EPT; ++u) {
-        const int e = tid + u * UPD_THREADS, r = e >> 5, c = e & 31;
-        tA[r * (TILE + 1) + c] = ra[u];
-        tB[r * (TILE + 1) + c] = rb[u];
+    for (int u = 0; u < EPT; ++u) {
+      const int e = tid + u * UPD_THREADS, r = e >> 5, c = e & 31;
+      tA[r * (TILE + 1) + c] = mode == 1 ? ra[u] : 0.0;
+      tB[r * (TILE + 1) + c] = mode == 1 ? rb[u] : 0.0;
+    }
+    if (tid < TILE) {  // t_j = Cs v_j for column j0 + tid
+      double vj[4];
+      for (int a2 = 0; a2 < 4; ++a2) vj[a2] = vec(a2, j0 + tid);
+      for (int a2 = 0; a2 < 4; ++a2) {
+        double t = 0.0;
+        for (int b2 = 0; b2 < 4; ++b2) t = fma(cs[a2][b2], vj[b2], t);
+        tj_[a2][tid] = t;
       }
     }
-    if (tid < 4 * TILE) vj_[tid / TILE][tid % TILE] = vec(tid / TILE, j0 + tid % TILE);
     __syncthreads();
     if (mode == 1 && J + 1 < T) load(J + 1);
-    for (int e = tid; e < TILE * TILE; e += UPD_THREADS) {
-      const int r = e >> 5, c = e & 31;
+    // value of element (i0 + r, j0 + c), kept in tA[r][c]; the diagonal tile computes r <= c only
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int e = tid + u * UPD_THREADS, r = e >> 5, c = e & 31;
+      if (J == I && r > c) continue;
+      double d = 0.0;
+#pragma unroll
+      for (int a2 = 0; a2 < 4; ++a2) d = fma(vi_[a2][r], tj_[a2][c], d);
+      const double val = 0.5 * (tA[r * (TILE + 1) + c] + tB[c * (TILE + 1) + r]) + d;
+      tA[r * (TILE + 1) + c] = val;
+      if (J == I) tA[c * (TILE + 1) + r] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int e = tid + u * UPD_THREADS, r = e >> 5, c = e & 31;
       {
         const int gi = i0 + r, gj = j0 + c;
-        if (gi < n && gj < n) {
-          const double vi[4] = {vi_[0][r], vi_[1][r], vi_[2][r], vi_[3][r]};
-          const double vj[4] = {vj_[0][c], vj_[1][c], vj_[2][c], vj_[3][c]};
-          const double d = 0.5 * (coef_delta(coef, vi, vj) + coef_delta(coef, vj, vi));
-          if (mode == 1) H[(size_t)gi * n + gj] = 0.5 * (tA[r * (TILE + 1) + c] + tB[c * (TILE + 1) + r]) + d;
-          else D[(size_t)gi * n + gj] = d;
-        }
+        if (gi < n && gj < n) O[(size_t)gi * n + gj] = tA[r * (TILE + 1) + c];
       }
-      if (J != I) {
+      if (J != I) {  // mirror image, row j0 + r
         const int gi = j0 + r, gj = i0 + c;
-        if (gi < n && gj < n) {
-          const double vi[4] = {vj_[0][r], vj_[1][r], vj_[2][r], vj_[3][r]};
-          const double vj[4] = {vi_[0][c], vi_[1][c], vi_[2][c], vi_[3][c]};
-          const double d = 0.5 * (coef_delta(coef, vi, vj) + coef_delta(coef, vj, vi));
-          if (mode == 1) H[(size_t)gi * n + gj] = 0.5 * (tB[r * (TILE + 1) + c] + tA[c * (TILE + 1) + r]) + d;
-          else D[(size_t)gi * n + gj] = d;
-        }
+        if (gi < n && gj < n) O[(size_t)gi * n + gj] = tA[c * (TILE + 1) + r];
       }
     }
   }
@@ -459,18 +471,6 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
   return MOP_OK;
 }
 
-extern "C" int mop_hessian_update(int B, int n, int method, int mode, int rsirfo_guards, double* H,
-                                  const double* s, const double* y, double* delta_out,
-                                  int32_t* status, void* stream) {
-  MOP_REQUIRE(B >= 0 && n > 0, "mop_hessian_update: B >= 0 and n > 0 required");
-  MOP_REQUIRE(H && s && y, "mop_hessian_update: H, s, y must be device pointers");
-  MOP_REQUIRE(mode == 0 || mode == 1, "mop_hessian_update: mode must be 0 (delta) or 1 (in place)");
-  MOP_REQUIRE(mode == 1 || delta_out, "mop_hessian_update: delta_out required in mode 0");
-  return mop_launch_hessian_update(B, n, method, mode, rsirfo_guards, H, s, y, nullptr, nullptr,
-                                   nullptr, nullptr, nullptr, 0, delta_out, status,
-                                   (cudaStream_t)stream);
-}
-
 size_t mop_hessian_update_scratch_bytes(int B, int n) { return sizeof(double) * (size_t)B * mop::upd_scratch_doubles(n); }
 
 // Same contract as mop_launch_hessian_update, three multi-CTA kernels, `scratch` from the caller.
@@ -508,4 +508,24 @@ int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guar
     MOP_CHECK_CUDA(cudaGetLastError());
   }
   return MOP_OK;
+}
+
+extern "C" size_t mop_hessian_update_workspace_bytes(int B, int n) {
+  return (B <= 0 || n <= 0) ? 0 : mop_hessian_update_scratch_bytes(B, n);
+}
+
+extern "C" int mop_hessian_update(int B, int n, int method, int mode, int rsirfo_guards, double* H,
+                                  const double* s, const double* y, double* delta_out,
+                                  int32_t* status, void* work, size_t work_bytes, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0, "mop_hessian_update: B >= 0 and n > 0 required");
+  MOP_REQUIRE(H && s && y, "mop_hessian_update: H, s, y must be device pointers");
+  MOP_REQUIRE(mode == 0 || mode == 1, "mop_hessian_update: mode must be 0 (delta) or 1 (in place)");
+  MOP_REQUIRE(mode == 1 || delta_out, "mop_hessian_update: delta_out required in mode 0");
+  if (work)
+    return mop_launch_hessian_update_split(B, n, method, mode, rsirfo_guards, H, s, y, nullptr, nullptr, nullptr,
+                                           nullptr, nullptr, 0, delta_out, status, work, work_bytes,
+                                           (cudaStream_t)stream);
+  return mop_launch_hessian_update(B, n, method, mode, rsirfo_guards, H, s, y, nullptr, nullptr,
+                                   nullptr, nullptr, nullptr, 0, delta_out, status,
+                                   (cudaStream_t)stream);
 }

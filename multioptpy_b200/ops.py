@@ -94,7 +94,7 @@ def workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
 
 # ---- (1) Hessian update --------------------------------------------------------
 def hessian_update(H, s, y, method: int, *, inplace: bool = False, rsirfo_guards: bool = False,
-                   status=None):
+                   status=None, multi_cta: bool = True):
     """delta_hess of one quasi-Newton update for each structure of the batch, or the
     in-place symmetrised update (RSIRFO.update_hessian) when ``inplace``."""
     lib = _lib.load()
@@ -104,9 +104,11 @@ def hessian_update(H, s, y, method: int, *, inplace: bool = False, rsirfo_guards
         status = torch.zeros(B, dtype=torch.int32, device=H.device)
     _chk(status, "status", (B,), torch.int32)
     delta = None if inplace else torch.empty_like(H)
+    nbytes = lib.mop_hessian_update_workspace_bytes(B, n) if multi_cta else 0
+    work = workspace(H.device, nbytes) if nbytes else None
     with torch.cuda.device(H.device):
         rc = lib.mop_hessian_update(B, n, int(method), 1 if inplace else 0, int(rsirfo_guards),
-                                    _ptr(H), _ptr(s), _ptr(y), _ptr(delta), _ptr(status),
+                                    _ptr(H), _ptr(s), _ptr(y), _ptr(delta), _ptr(status), _ptr(work), nbytes,
                                     _stream(H.device))
     _lib.check(rc, "mop_hessian_update")
     return (H if inplace else delta), status

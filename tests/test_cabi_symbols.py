@@ -31,7 +31,7 @@ def test_version_and_error_string():
     lib = _lib.load()
     assert lib.mop_version() == 100
     # argument validation happens on the host before any CUDA call
-    rc = lib.mop_hessian_update(1, 0, 15, 0, 0, None, None, None, None, None, None)
+    rc = lib.mop_hessian_update(1, 0, 15, 0, 0, None, None, None, None, None, None, 0, None)
     assert rc == -1
     assert b"n > 0" in lib.mop_last_error()
 

@@ -34,6 +34,8 @@ def test_update_deltas_vs_reference_golden(golden_dir):
         sel = np.where(z["method"] == mid)[0]
         H, s, y, ref = z["H"][sel], z["s"][sel], z["y"][sel], z["delta"][sel]
         d, st = ops.hessian_update(T(H), T(s), T(y), int(mid))
+        d1, st1 = ops.hessian_update(T(H), T(s), T(y), int(mid), multi_cta=False)   # single-kernel path
+        assert torch.equal(st, st1) and float((d - d1).abs().max()) <= 1e-12 * max(float(d1.abs().max()), 1e-300)
         d = d.cpu().numpy()
         for i in range(len(sel)):
             scale = max(np.linalg.norm(ref[i]), 1e-3 * np.linalg.norm(H[i]))
@@ -52,7 +54,12 @@ def test_update_inplace_vs_oracle(n, method):
     y[1] = -y[1]            # negative curvature -> skipped
     s[2] *= 1e-12           # tiny step -> skipped
     Hd = T(H)
+    Hd1 = T(H)
+    _, st1 = ops.hessian_update(Hd1, T(s), T(y), method, inplace=True, rsirfo_guards=True, multi_cta=False)
     _, st = ops.hessian_update(Hd, T(s), T(y), method, inplace=True, rsirfo_guards=True)
+    assert torch.equal(st, st1)
+    assert float((Hd - Hd1).abs().max()) <= 1e-12 * float(Hd1.abs().max())
+    assert torch.equal(Hd, Hd.transpose(1, 2))
     got, st = Hd.cpu().numpy(), st.cpu().numpy()
     for b in range(B):
         exp, upd = O.rsirfo_update_hessian(H[b], s[b], y[b], np.zeros(n), np.zeros(n), method)
