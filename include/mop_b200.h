@@ -213,6 +213,19 @@ int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radi
                         double* H_out, int32_t* counts_out, int32_t* status, void* work,
                         size_t work_bytes, void* stream);
 
+/* ---- step post-processing (either side of the optimizer step) -----------------------------
+ * mop_kabsch replaces Calculationtools.kabsch_algorithm (Utils/calc_tools.py:412-425): P, Q [B][natoms][3];
+ * P_aligned = P centred and rotated onto Q, Q_centred (optional) = Q minus its centroid (the reference
+ * mutates both arguments in place).  status[b] = 1 for collinear structures (rotation undefined, identity used).
+ * mop_check_convergence replaces ConvergenceChecker.check_convergence (optimization.py:1244-1289) without
+ * the optimizer-instance override: grad, disp [B][n]; out (optional) [B][8] = {converged, max displacement
+ * threshold, rms displacement threshold, max |g|, rms g, max |d|, rms d, 0}; converged (optional) [B]. */
+int mop_kabsch(int B, int natoms, const double* P, const double* Q, double* P_aligned, double* Q_centred,
+               int32_t* status, void* stream);
+int mop_check_convergence(int B, int n, const double* grad, const double* disp, double max_force_thr,
+                          double rms_force_thr, double max_disp_thr, double rms_disp_thr, double* out,
+                          int32_t* converged, void* stream);
+
 /* ---- redundant internal coordinates ------------------------------------------------------
  * Replaces Coordinate/redundant_coordinate.py: RedundantInternalCoordinates.B_matrix (:15-43),
  * RICgrad2cartgrad (:47-50), RIChess2carthess (:63-146), partial_stretch_B_matirx /

@@ -557,3 +557,30 @@ def ric_pb_cart_grad(pB, int_grad):
         _lib.check(lib.mop_ric_pb_cart_grad(B, n, m, _ptr(pB), _ptr(int_grad), _ptr(out), _stream(pB.device)),
                    "mop_ric_pb_cart_grad")
     return out
+
+
+# ------------------------------------------------------------------ step post-processing
+def kabsch(P, Q):
+    """Calculationtools.kabsch_algorithm for a batch: P, Q (B, N, 3) -> (P aligned, Q centred, status)."""
+    lib = _lib.load()
+    B, N, _ = P.shape
+    _chk(P, "P", (B, N, 3)); _chk(Q, "Q", (B, N, 3))
+    Pa, Qc = torch.empty_like(P), torch.empty_like(Q)
+    status = torch.zeros(B, dtype=torch.int32, device=P.device)
+    with torch.cuda.device(P.device):
+        _lib.check(lib.mop_kabsch(B, N, _ptr(P), _ptr(Q), _ptr(Pa), _ptr(Qc), _ptr(status), _stream(P.device)), "mop_kabsch")
+    return Pa, Qc, status
+
+
+def check_convergence(grad, disp, max_force_thr, rms_force_thr, max_disp_thr, rms_disp_thr):
+    """ConvergenceChecker.check_convergence for a batch: grad, disp (B, n) -> (converged int32 (B,), out (B, 8))."""
+    lib = _lib.load()
+    B, n = grad.shape
+    _chk(grad, "grad", (B, n)); _chk(disp, "disp", (B, n))
+    out = torch.empty(B, 8, dtype=torch.float64, device=grad.device)
+    conv = torch.empty(B, dtype=torch.int32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        rc = lib.mop_check_convergence(B, n, _ptr(grad), _ptr(disp), float(max_force_thr), float(rms_force_thr),
+                                       float(max_disp_thr), float(rms_disp_thr), _ptr(out), _ptr(conv), _stream(grad.device))
+    _lib.check(rc, "mop_check_convergence")
+    return conv, out

@@ -622,6 +622,61 @@ def gen_ric():
     np.savez_compressed(os.path.join(GOLD, "ric.npz"), **blob)
 
 
+def gen_post():
+    """Kabsch alignment and the convergence test (Utils/calc_tools.py:412-425, optimization.py:1244-1289)."""
+    import types
+    ct = ref_shim.ref("Utils.calc_tools")
+    # optimization.py pulls plotting / engine packages that are absent offline: stub whatever is missing
+    from unittest.mock import MagicMock
+    for _ in range(60):
+        try:
+            opt = ref_shim.ref("optimization")
+            break
+        except ModuleNotFoundError as exc:
+            parts = exc.name.split(".")
+            for k in range(1, len(parts) + 1):
+                sys.modules.setdefault(".".join(parts[:k]), MagicMock())
+    rng = np.random.default_rng(9090)
+    blob = {}
+    Ps, Qs, Pa, Qa = [], [], [], []
+    for case in range(12):
+        N = [5, 11, 24, 30][case % 4]
+        Q = synthetic.grid_geometry(N, rng)
+        th = rng.normal(size=3); th /= np.linalg.norm(th); ang = rng.uniform(0.2, 3.0)
+        K = np.array([[0, -th[2], th[1]], [th[2], 0, -th[0]], [-th[1], th[0], 0]])
+        R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        P = (R @ Q.T).T + rng.normal(0, 0.05, Q.shape) + rng.normal(0, 1.0, 3)
+        if case % 5 == 4:
+            P = P * np.array([1.0, 1.0, -1.0])        # mirror image: exercises the det < 0 branch
+        P0, Q0 = P.copy(), Q.copy()
+        with quiet():
+            Pr, Qr = ct.Calculationtools().kabsch_algorithm(P, Q)
+        pad = lambda a: np.pad(a, ((0, 30 - len(a)), (0, 0)))
+        Ps.append(pad(P0)); Qs.append(pad(Q0)); Pa.append(pad(np.asarray(Pr))); Qa.append(pad(np.asarray(Qr)))
+    blob["kabsch/natoms"] = np.array([[5, 11, 24, 30][c % 4] for c in range(12)], np.int32)
+    blob["kabsch/P"] = np.array(Ps); blob["kabsch/Q"] = np.array(Qs)
+    blob["kabsch/P_aligned"] = np.array(Pa); blob["kabsch/Q_centred"] = np.array(Qa)
+    # convergence test: gradients / displacements around the thresholds
+    chk = opt.ConvergenceChecker.__new__(opt.ConvergenceChecker)
+    rows = []
+    for case in range(40):
+        thr = dict(MAX_FORCE_THRESHOLD=3e-4, RMS_FORCE_THRESHOLD=2e-4, MAX_DISPLACEMENT_THRESHOLD=1.5e-3,
+                   RMS_DISPLACEMENT_THRESHOLD=1.0e-3)
+        chk.config = types.SimpleNamespace(**thr)
+        n = 36
+        g = rng.normal(0, 10 ** rng.uniform(-5.5, -3.0), n); d = rng.normal(0, 10 ** rng.uniform(-4.5, -2.5), n)
+        g[rng.integers(0, n, 5)] = 0.0; d[rng.integers(0, n, 5)] = 1e-11        # entries the rms filter drops
+        state = types.SimpleNamespace(effective_gradient=g.reshape(-1, 3))
+        ok, mdt, rdt = chk.check_convergence(state, d.reshape(-1, 3), [])
+        rows.append((g, d, ok, mdt, rdt))
+    blob["conv/grad"] = np.array([r[0] for r in rows]); blob["conv/disp"] = np.array([r[1] for r in rows])
+    blob["conv/ok"] = np.array([r[2] for r in rows], np.int32)
+    blob["conv/max_disp_thr"] = np.array([r[3] for r in rows]); blob["conv/rms_disp_thr"] = np.array([r[4] for r in rows])
+    blob["conv/thresholds"] = np.array([3e-4, 2e-4, 1.5e-3, 1.0e-3])
+    print("post: kabsch cases", len(Ps), "convergence cases", len(rows), "converged", int(blob["conv/ok"].sum()))
+    np.savez_compressed(os.path.join(GOLD, "post.npz"), **blob)
+
+
 RSPRFO_CASES = [
     # (name, method, saddle_order, natoms, nsteps, bias, seed)
     ("prfo_bofill_ts_n36", "rsprfo_bofill", 1, 12, 6, False, 1),
@@ -687,7 +742,7 @@ def gen_rsprfo():
     np.savez_compressed(os.path.join(GOLD, "rsprfo_traces.npz"), **blob)
 
 
-SETS = {"ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+SETS = {"post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo}
 
 if __name__ == "__main__":

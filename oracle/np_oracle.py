@@ -1580,3 +1580,38 @@ def ric_int_grad(pB, cart_grad):
 def ric_cart_grad(pB, int_grad):
     """calc_cart_grad_from_pBmat (:437-439)."""
     return np.asarray(pB, float).T @ np.asarray(int_grad, float).reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Step post-processing either side of the path (SURVEY §8f rank 3)
+# ---------------------------------------------------------------------------------------------
+def kabsch(P, Q):
+    """Calculationtools.kabsch_algorithm (Utils/calc_tools.py:412-425): returns (P rotated onto Q and
+    centred, Q centred); the reference mutates both arguments in place."""
+    P = np.array(P, float); Q = np.array(Q, float)
+    P -= P.mean(axis=0); Q -= Q.mean(axis=0)
+    U, S, Vt = np.linalg.svd(P.T @ Q)
+    R = Vt.T @ U.T
+    if np.linalg.det(R) < 0:
+        Vt[-1, :] *= -1
+        R = Vt.T @ U.T
+    return (R @ P.T).T, Q
+
+
+def rms_safely(v, threshold=1e-10):
+    """calculate_rms_safely (optimization.py:1244-1250)."""
+    v = np.asarray(v, float).ravel()
+    f = v[np.abs(v) > threshold]
+    return float(np.sqrt((f ** 2).mean())) if f.size else 0.0
+
+
+def check_convergence(grad, disp, max_force_thr, rms_force_thr, max_disp_thr, rms_disp_thr):
+    """ConvergenceChecker.check_convergence (optimization.py:1252-1289) without the optimizer-instance
+    override: (converged, max_displacement_threshold, rms_displacement_threshold, the four measures)."""
+    g = np.asarray(grad, float); d = np.asarray(disp, float)
+    mf, rf = float(np.abs(g).max()), rms_safely(g)
+    md, rd = float(np.abs(d).max()), rms_safely(d)
+    mdt = max(max_disp_thr, max_disp_thr + max(0.0, max_force_thr - mf))
+    rdt = max(rms_disp_thr, rms_disp_thr + max(0.0, rms_force_thr - rf))
+    ok = mf < max_force_thr and rf < rms_force_thr and md < mdt and rd < rdt
+    return bool(ok), mdt, rdt, (mf, rf, md, rd)
