@@ -306,14 +306,24 @@ int mop_afir(int B, int natoms, const double* xyz, int n1, const int32_t* frag1,
  *                 force [nloc][n] = -(g + projection), tau [nloc][n] = projection (get_tau).
  * mop_neb_ayala   replaces calculate_gamma (pathopt_bneb_force.py:161-222) and the rank-1
  *                 update H += gamma t t^T of RFOOptimizer (Optimizer/rfo_neb.py:43-73).
- * mop_neb_limit_tr replaces _limit_step_size (rfo_neb.py:76-83) and TR_NEB.TR_calc
- *                 (Optimizer/trust_radius_neb.py:17-98); delta [nloc][n] in place. */
+ * mop_neb_limit_tr replaces _limit_step_size (rfo_neb.py:76-83; only when apply_step_limit != 0) and
+ *                 TR_NEB.TR_calc (Optimizer/trust_radius_neb.py:17-98); delta [nloc][n] in place. */
 int mop_bneb_force(int nimg, int first, int nloc, int n, const double* x_halo, const double* E_halo,
                    const double* g, double* force, double* tau, void* stream);
 int mop_neb_ayala(int nimg, int first, int nloc, int n, const double* x_halo, const double* E_halo,
                   const double* g_halo, const double* tau, double* H, double* gamma_out, void* stream);
 int mop_neb_limit_tr(int nimg, int first, int nloc, int n, int fix_init_edge, int fix_end_edge,
-                     const double* x_halo, const double* g, double* delta, void* stream);
+                     int apply_step_limit, const double* x_halo, const double* g, double* delta, void* stream);
+/* FIRE optimizer of the NEB driver (Optimizer/fire_neb.py:38-92).  mop_neb_fire_blend: per-atom velocity / force
+ * blend vneb_out [nloc][natoms][3] and the power sum v_prev . F accumulated into the device scalar power_accum
+ * (zeroed by the caller, all-reduced over ranks when the chain is sharded; prev_velocity = NULL on the first
+ * iteration).  The (dt, a, n_reset) schedule is scalar host logic (host mirror FIREOptimizer).
+ * mop_neb_fire_advance: velocity_out = (reset ? 0 : vneb) + dt F, delta_out = dt (velocity_out + prev_velocity)
+ * or dt velocity_out; mop_neb_limit_tr(apply_step_limit = 0) then applies TR_calc. */
+int mop_neb_fire_blend(int nloc, int natoms, double a, const double* force, const double* velocity,
+                       const double* prev_velocity, double* vneb_out, double* power_accum, void* stream);
+int mop_neb_fire_advance(int nloc, int n, double dt, int reset, const double* vneb, const double* force,
+                         const double* prev_velocity, double* velocity_out, double* delta_out, void* stream);
 
 /* ---- caller side: composite outer trust radius -----------------------------------
  * Replaces TrustRadius.update_trust_radii (Optimizer/trust_radius.py:120-206) as called

@@ -60,7 +60,9 @@ SIGNATURES = {
     "mop_afir": (_i, [_i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "mop_bneb_force": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_neb_ayala": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
-    "mop_neb_limit_tr": (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mop_neb_limit_tr": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mop_neb_fire_blend": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p]),
+    "mop_neb_fire_advance": (_i, [_i, _i, _d, _i, _p, _p, _p, _p, _p, _p]),
     "mop_outer_trust_radius": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _p]),
     "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "mop_bench_dfma": (_i, [_i, _i, _p, _p]),

@@ -189,7 +189,7 @@ k_neb_ayala(int nimg, int first, int n, const double* __restrict__ xh, const dou
 }
 
 __global__ void __launch_bounds__(NEB_THREADS)
-k_neb_limit_tr(int nimg, int first, int n, int fix_init, int fix_end, const double* __restrict__ xh,
+k_neb_limit_tr(int nimg, int first, int n, int fix_init, int fix_end, int step_limit, const double* __restrict__ xh,
                const double* __restrict__ g_all, double* __restrict__ delta_all) {
   __shared__ double scratch[40];
   const int l = blockIdx.x, i = first + l, tid = threadIdx.x;
@@ -200,7 +200,7 @@ k_neb_limit_tr(int nimg, int first, int n, int fix_init, int fix_end, const doub
   double nrm = sqrt(block_sum(p, scratch));
   // _limit_step_size (rfo_neb.py:76-83)
   double scale = 1.0;
-  if (nrm > 1e-8) scale = fmin(endpoint ? 0.2 : 0.1, nrm) / nrm;
+  if (step_limit && nrm > 1e-8) scale = fmin(endpoint ? 0.2 : 0.1, nrm) / nrm;
   nrm *= scale;
   if (endpoint) {  // TR_calc ends (:18-27, :85-93)
     double f = scale;
@@ -249,6 +249,45 @@ k_neb_limit_tr(int nimg, int first, int n, int fix_init, int fix_end, const doub
   for (int k = tid; k < n; k += NEB_THREADS) d[k] *= f;
 }
 
+
+// ---- FIRE optimizer of the NEB driver (Optimizer/fire_neb.py:38-92) -----------------------------
+// blend: per atom  v <- (1 - a) v + a |v| / |F| F  (kept when |F| <= 1e-10), and the power
+// P = sum v_prev . F accumulated into one device scalar (the caller all-reduces it over ranks);
+// advance: v_new = (reset ? 0 : v_blend) + dt F,  delta = dt (v_new + v_prev) or dt v_new.
+__global__ void __launch_bounds__(256) k_neb_fire_blend(int natoms_total, double a, const double* __restrict__ F,
+                                                        const double* __restrict__ V, const double* __restrict__ Vp,
+                                                        double* __restrict__ Vneb, double* __restrict__ power) {
+  __shared__ double scratch[40];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double p = 0.0;
+  if (i < natoms_total) {
+    const double fx = F[3 * i], fy = F[3 * i + 1], fz = F[3 * i + 2];
+    const double vx = V[3 * i], vy = V[3 * i + 1], vz = V[3 * i + 2];
+    const double fn = sqrt(fx * fx + fy * fy + fz * fz), vn = sqrt(vx * vx + vy * vy + vz * vz);
+    double ox = vx, oy = vy, oz = vz;
+    if (fn > 1e-10) {
+      const double r = a * (vn / fn);
+      ox = (1.0 - a) * vx + r * fx;
+      oy = (1.0 - a) * vy + r * fy;
+      oz = (1.0 - a) * vz + r * fz;
+    }
+    Vneb[3 * i] = ox; Vneb[3 * i + 1] = oy; Vneb[3 * i + 2] = oz;
+    if (Vp) p = Vp[3 * i] * fx + Vp[3 * i + 1] * fy + Vp[3 * i + 2] * fz;
+  }
+  p = block_sum(p, scratch);
+  if (threadIdx.x == 0 && power && Vp) atomicAdd(power, p);
+}
+
+__global__ void __launch_bounds__(256) k_neb_fire_advance(size_t total, double dt, int reset, const double* __restrict__ Vneb,
+                                                          const double* __restrict__ F, const double* __restrict__ Vp,
+                                                          double* __restrict__ Vnew, double* __restrict__ delta) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const double v = (reset ? 0.0 * Vneb[e] : Vneb[e]) + dt * F[e];
+    Vnew[e] = v;
+    delta[e] = Vp ? dt * (v + Vp[e]) : dt * v;
+  }
+}
+
 }  // namespace mop
 
 extern "C" int mop_bneb_force(int nimg, int first, int nloc, int n, const double* x_halo,
@@ -280,13 +319,38 @@ extern "C" int mop_neb_ayala(int nimg, int first, int nloc, int n, const double*
 }
 
 extern "C" int mop_neb_limit_tr(int nimg, int first, int nloc, int n, int fix_init_edge, int fix_end_edge,
-                                const double* x_halo, const double* g, double* delta, void* stream) {
+                                int apply_step_limit, const double* x_halo, const double* g, double* delta,
+                                void* stream) {
   MOP_REQUIRE(nimg >= 2 && nloc >= 0 && first >= 0 && first + nloc <= nimg && n > 0,
               "mop_neb_limit_tr: bad image range or n");
   MOP_REQUIRE(x_halo && g && delta, "mop_neb_limit_tr: null pointer");
   if (nloc == 0) return MOP_OK;
   mop::k_neb_limit_tr<<<nloc, mop::NEB_THREADS, 0, (cudaStream_t)stream>>>(nimg, first, n, fix_init_edge,
-                                                                         fix_end_edge, x_halo, g, delta);
+                                                                         fix_end_edge, apply_step_limit, x_halo, g,
+                                                                         delta);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+extern "C" int mop_neb_fire_blend(int nloc, int natoms, double a, const double* force, const double* velocity,
+                                  const double* prev_velocity, double* vneb_out, double* power_accum, void* stream) {
+  MOP_REQUIRE(nloc >= 0 && natoms > 0 && force && velocity && vneb_out, "mop_neb_fire_blend: bad arguments");
+  if (nloc == 0) return MOP_OK;
+  const int tot = nloc * natoms;
+  mop::k_neb_fire_blend<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tot, a, force, velocity, prev_velocity,
+                                                                           vneb_out, power_accum);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+extern "C" int mop_neb_fire_advance(int nloc, int n, double dt, int reset, const double* vneb, const double* force,
+                                    const double* prev_velocity, double* velocity_out, double* delta_out, void* stream) {
+  MOP_REQUIRE(nloc >= 0 && n > 0 && vneb && force && velocity_out && delta_out, "mop_neb_fire_advance: bad arguments");
+  if (nloc == 0) return MOP_OK;
+  const size_t tot = (size_t)nloc * n;
+  const int grid = (int)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184);
+  mop::k_neb_fire_advance<<<grid, 256, 0, (cudaStream_t)stream>>>(tot, dt, reset, vneb, force, prev_velocity,
+                                                                 velocity_out, delta_out);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }

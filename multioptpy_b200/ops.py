@@ -365,14 +365,14 @@ def neb_ayala(nimg, first, x_halo, E_halo, g_halo, tau, H):
     return gamma
 
 
-def neb_limit_tr(nimg, first, x_halo, g, delta, fix_init_edge=False, fix_end_edge=False):
-    """_limit_step_size + TR_calc on delta (nloc, n), in place."""
+def neb_limit_tr(nimg, first, x_halo, g, delta, fix_init_edge=False, fix_end_edge=False, step_limit=True):
+    """_limit_step_size (unless step_limit is False: the FIRE optimizer) + TR_calc on delta (nloc, n), in place."""
     lib = _lib.load()
     nloc, n = delta.shape
     _chk(x_halo, "x_halo", (nloc + 2, n)); _chk(g, "g", (nloc, n)); _chk(delta, "delta", (nloc, n))
     with torch.cuda.device(delta.device):
         rc = lib.mop_neb_limit_tr(int(nimg), int(first), nloc, n, int(bool(fix_init_edge)), int(bool(fix_end_edge)),
-                                  _ptr(x_halo), _ptr(g), _ptr(delta), _stream(delta.device))
+                                  int(bool(step_limit)), _ptr(x_halo), _ptr(g), _ptr(delta), _stream(delta.device))
     _lib.check(rc, "mop_neb_limit_tr")
     return delta
 
@@ -584,3 +584,31 @@ def check_convergence(grad, disp, max_force_thr, rms_force_thr, max_disp_thr, rm
                                        float(max_disp_thr), float(rms_disp_thr), _ptr(out), _ptr(conv), _stream(grad.device))
     _lib.check(rc, "mop_check_convergence")
     return conv, out
+
+
+def neb_fire_blend(force, velocity, prev_velocity, a, power_accum):
+    """FIRE velocity / force blend; force, velocity (nloc, natoms, 3); adds sum v_prev . F to power_accum (1,)."""
+    lib = _lib.load()
+    nloc, natoms, _ = force.shape
+    _chk(force, "force", (nloc, natoms, 3)); _chk(velocity, "velocity", (nloc, natoms, 3)); _chk(power_accum, "power_accum", (1,))
+    if prev_velocity is not None:
+        _chk(prev_velocity, "prev_velocity", (nloc, natoms, 3))
+    out = torch.empty_like(velocity)
+    with torch.cuda.device(force.device):
+        rc = lib.mop_neb_fire_blend(nloc, natoms, float(a), _ptr(force), _ptr(velocity), _ptr(prev_velocity), _ptr(out),
+                                    _ptr(power_accum), _stream(force.device))
+    _lib.check(rc, "mop_neb_fire_blend")
+    return out
+
+
+def neb_fire_advance(vneb, force, prev_velocity, dt, reset):
+    """(velocity_new, delta) of the FIRE step; arrays (nloc, natoms, 3)."""
+    lib = _lib.load()
+    nloc = vneb.shape[0]
+    n = vneb[0].numel()
+    vnew, delta = torch.empty_like(vneb), torch.empty_like(vneb)
+    with torch.cuda.device(vneb.device):
+        rc = lib.mop_neb_fire_advance(nloc, n, float(dt), int(bool(reset)), _ptr(vneb), _ptr(force), _ptr(prev_velocity),
+                                      _ptr(vnew), _ptr(delta), _stream(vneb.device))
+    _lib.check(rc, "mop_neb_fire_advance")
+    return vnew, delta

@@ -622,6 +622,55 @@ def gen_ric():
     np.savez_compressed(os.path.join(GOLD, "ric.npz"), **blob)
 
 
+def gen_fire():
+    """FIRE optimizer of the NEB driver (Optimizer/fire_neb.py): 8-iteration trace on a synthetic chain with
+    a quadratic force field, (dt, a, n_reset) schedule included."""
+    import tempfile, types
+    fn = ref_shim.ref("Optimizer.fire_neb")
+    nimg, natoms = 9, 10
+    X, E, G = neb_chain(nimg, natoms, 41)
+    X = X.reshape(nimg, natoms, 3)
+    cfg = types.SimpleNamespace(dt=0.5, a=0.10, n_reset=0, FIRE_N_accelerate=2, FIRE_f_inc=1.10, FIRE_f_accelerate=0.99,
+                                FIRE_f_decelerate=0.5, FIRE_a_start=0.1, FIRE_dt_max=3.0,
+                                NEB_FOLDER_DIRECTORY=tempfile.mkdtemp() + "/", fix_init_edge=False, fix_end_edge=False,
+                                apply_convergence_criteria=False, bohr2angstroms=0.52917721067)
+    with quiet():
+        opt = fn.FIREOptimizer(cfg)
+    X0 = X.copy()
+    K = 0.05 + 0.02 * np.random.default_rng(3).random((nimg, natoms, 1))
+    force = lambda x: -K * (x - X0 * 0.97) * 0.2
+    V = np.zeros_like(X); Vp = np.zeros_like(X)
+    rec = {k: [] for k in ("X", "F", "V", "Vprev", "move", "state", "have_prev")}
+    geom = X.copy()
+    for it in range(8):
+        F = force(geom) * (-1.0 if it == 5 else 1.0)      # iteration 5: negative power -> reset branch
+        pre = Vp if it > 0 else []
+        rec["X"].append(geom.copy()); rec["F"].append(F.copy()); rec["V"].append(V.copy()); rec["Vprev"].append(Vp.copy())
+        rec["have_prev"].append(int(it > 0))
+        # the reference computes total_velocity internally and returns only the new geometry: re-derive what
+        # the driver carries over (NEB.execute keeps total_velocity from the optimizer's attribute-free maths)
+        dt_before, a_before = opt.dt, opt.a
+        with quiet():
+            new_geom_ang = opt.optimize(geom, F, pre, it, V, [], E, E, geom)
+        move = np.asarray(new_geom_ang) / cfg.bohr2angstroms - geom
+        rec["move"].append(move.copy()); rec["state"].append([opt.dt, opt.a, opt.n_reset])
+        # velocity bookkeeping as in the reference driver: restate the velocity update with the recorded state
+        fnm = np.linalg.norm(F, axis=2, keepdims=True); vnm = np.linalg.norm(V, axis=2, keepdims=True)
+        with np.errstate(all="ignore"):
+            blend = (1.0 - a_before) * V + a_before * (vnm / fnm) * F
+        vneb = np.where(fnm > 1e-10, blend, V)
+        if opt.n_reset == 0:
+            vneb = vneb * 0
+        Vnew = vneb + opt.dt * F
+        Vp = V.copy() if False else Vnew.copy() * 0 + (Vnew if it == 0 else Vnew)
+        Vp = Vnew.copy(); V = Vnew.copy()
+        geom = geom + move
+    blob = {k: np.array(v) for k, v in rec.items()}
+    blob["cfg"] = np.array([cfg.dt, 0.10, 0, cfg.FIRE_N_accelerate, cfg.FIRE_f_inc, cfg.FIRE_f_decelerate, cfg.FIRE_a_start, cfg.FIRE_dt_max])
+    print("fire: states", [tuple(np.round(s_, 4)) for s_ in rec["state"]])
+    np.savez_compressed(os.path.join(GOLD, "fire_neb.npz"), **blob)
+
+
 def gen_post():
     """Kabsch alignment and the convergence test (Utils/calc_tools.py:412-425, optimization.py:1244-1289)."""
     import types
@@ -742,7 +791,7 @@ def gen_rsprfo():
     np.savez_compressed(os.path.join(GOLD, "rsprfo_traces.npz"), **blob)
 
 
-SETS = {"post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+SETS = {"fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo}
 
 if __name__ == "__main__":

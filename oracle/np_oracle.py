@@ -1035,16 +1035,16 @@ def ayala_gamma(qp, qc, qn, Ep, Ec, En, gp, gc, gn, tangent):
         return 0.0
 
 
-def neb_limit_tr(X, G, delta):
-    """_limit_step_size (Optimizer/rfo_neb.py:76-83) + TR_NEB.TR_calc
-    (Optimizer/trust_radius_neb.py:17-98), free end images."""
+def neb_limit_tr(X, G, delta, step_limit=True):
+    """_limit_step_size (Optimizer/rfo_neb.py:76-83; skipped with step_limit=False, as the FIRE
+    optimizer does) + TR_NEB.TR_calc (Optimizer/trust_radius_neb.py:17-98), free end images."""
     nimg = X.shape[0]
     out = np.zeros_like(delta)
     for i in range(nimg):
         d = delta[i].copy()
         end = i == 0 or i == nimg - 1
         nrm = np.linalg.norm(d)
-        if nrm > 1e-8:
+        if step_limit and nrm > 1e-8:
             d = d / nrm * min(0.2 if end else 0.1, nrm)
         nrm = np.linalg.norm(d)
         if end:
@@ -1615,3 +1615,37 @@ def check_convergence(grad, disp, max_force_thr, rms_force_thr, max_disp_thr, rm
     rdt = max(rms_disp_thr, rms_disp_thr + max(0.0, rms_force_thr - rf))
     ok = mf < max_force_thr and rf < rms_force_thr and md < mdt and rd < rdt
     return bool(ok), mdt, rdt, (mf, rf, md, rd)
+
+
+class FIRENEBOracle:
+    """FIREOptimizer.optimize (Optimizer/fire_neb.py:38-92) up to the move vector: per-atom velocity /
+    force blend, the global power test P = sum v_prev . F, the (dt, a, n_reset) schedule (note that `a` is
+    multiplied by FIRE_f_inc, :65), velocity Verlet-like update, TR_calc.  Arrays are (nimg, natoms, 3)."""
+
+    def __init__(self, dt=0.5, a=0.10, n_reset=0, N_accelerate=5, f_inc=1.10, f_decelerate=0.5, a_start=0.1, dt_max=3.0):
+        self.dt, self.a, self.n_reset = dt, a, n_reset
+        self.N_acc, self.f_inc, self.f_dec, self.a_start, self.dt_max = N_accelerate, f_inc, f_decelerate, a_start, dt_max
+
+    def step(self, X, F, V, V_prev, optimize_num):
+        X = np.asarray(X, float); F = np.asarray(F, float); V = np.asarray(V, float)
+        have_prev = V_prev is not None and len(V_prev) > 1
+        fn = np.linalg.norm(F, axis=2, keepdims=True); vn = np.linalg.norm(V, axis=2, keepdims=True)
+        with np.errstate(all="ignore"):
+            blend = (1.0 - self.a) * V + self.a * (vn / fn) * F
+        vneb = np.where(fn > 1e-10, blend, V)
+        P = float(np.sum(np.asarray(V_prev, float) * F)) if (optimize_num != 0 and have_prev) else 0.0
+        if optimize_num > 0 and P > 0 and have_prev:
+            if self.n_reset > self.N_acc:
+                self.dt = min(self.dt * self.f_inc, self.dt_max)
+                self.a *= self.f_inc
+            self.n_reset += 1
+        else:
+            vneb = vneb * 0
+            self.a = self.a_start
+            self.dt *= self.f_dec
+            self.n_reset = 0
+        Vnew = vneb + self.dt * F
+        delta = self.dt * (Vnew + np.asarray(V_prev, float)) if (optimize_num != 0 and have_prev) else self.dt * Vnew
+        nimg = X.shape[0]
+        move = neb_limit_tr(X.reshape(nimg, -1), F.reshape(nimg, -1), delta.reshape(nimg, -1), step_limit=False)
+        return Vnew, delta, move.reshape(X.shape), P

@@ -101,3 +101,40 @@ def test_halo_exchange_gloo(world):
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res)
     assert sorted(f for _, _, f, _ in res)[0] == 0 and sum(nl for _, _, _, nl in res) == 11
+
+
+# ------------------------------------------------------------------ FIRE optimizer of the NEB driver
+def _fire_oracle(z):
+    c = z["cfg"]
+    return O.FIRENEBOracle(dt=c[0], a=c[1], n_reset=int(c[2]), N_accelerate=int(c[3]), f_inc=c[4], f_decelerate=c[5],
+                           a_start=c[6], dt_max=c[7])
+
+
+def test_oracle_fire_vs_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "fire_neb.npz"))
+    o = _fire_oracle(z)
+    for it in range(len(z["X"])):
+        _, _, mv, _ = o.step(z["X"][it], z["F"][it], z["V"][it], z["Vprev"][it] if z["have_prev"][it] else None, it)
+        ref = z["move"][it]          # recovered from the reference's Angstrom output: a few 1e-11 of round trip
+        assert np.abs(mv - ref).max() <= 2e-10 * np.abs(ref).max(), it
+        assert (o.dt, o.a, o.n_reset) == tuple(z["state"][it]), it
+
+
+@pytest.mark.gpu
+def test_gpu_fire_vs_golden(golden_dir):
+    import types
+    from multioptpy_b200.Optimizer.fire_neb import FIREOptimizer
+    z = np.load(os.path.join(golden_dir, "fire_neb.npz"))
+    c = z["cfg"]
+    cfg = types.SimpleNamespace(dt=c[0], a=c[1], n_reset=int(c[2]), FIRE_N_accelerate=int(c[3]), FIRE_f_inc=c[4],
+                                FIRE_f_accelerate=0.99, FIRE_f_decelerate=c[5], FIRE_a_start=c[6], FIRE_dt_max=c[7])
+    opt = FIREOptimizer(cfg, device="cuda:0")
+    o = _fire_oracle(z)
+    for it in range(len(z["X"])):
+        pre = z["Vprev"][it] if z["have_prev"][it] else []
+        new_ang = opt.optimize(z["X"][it], z["F"][it], pre, it, z["V"][it])
+        mv = new_ang / 0.52917721067 - z["X"][it]
+        Vn, _, mo, _ = o.step(z["X"][it], z["F"][it], z["V"][it], z["Vprev"][it] if z["have_prev"][it] else None, it)
+        assert np.abs(mv - mo).max() <= 1e-9 * np.abs(mo).max(), it       # Angstrom round trip of the return value
+        assert np.abs(opt.total_velocity - Vn).max() <= 1e-12 * max(np.abs(Vn).max(), 1e-300), it
+        assert (opt.dt, opt.a, opt.n_reset) == (o.dt, o.a, o.n_reset) == tuple(z["state"][it]), it
