@@ -213,6 +213,17 @@ int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radi
                         double* H_out, int32_t* counts_out, int32_t* status, void* work,
                         size_t work_bytes, void* stream);
 
+/* ---- restraint bias potentials --------------------------------------------------------------
+ * Replaces calc_energy + torch.func.jacrev / hessian (Potential/potential.py:127-137) for StructKeepPotential
+ * (kind 1), StructKeepPotentialv2 (kind 2; Potential/keep_potential.py) and StructKeepAnglePotential (kind 3;
+ * Potential/keep_angle_potential.py:7-229).  terms: device array of nterm records of mop_bias_term_bytes()
+ * bytes each: int32 kind, n1, n2, atoms[64] (0-based; kind 1: atoms i, j with n1 = n2 = 1; kind 2: the two
+ * fragments back to back; kind 3: atoms i, j, k with n1 = 3), then double k (spring constant) and p (distance
+ * in Angstrom, or angle in degrees).  E [B], grad [B][n], hess [B][n][n] are ADDED to (any may be NULL). */
+size_t mop_bias_term_bytes(void);
+int mop_bias_terms(int B, int natoms, int nterm, const void* terms, const double* xyz, double* E, double* grad,
+                   double* hess, void* stream);
+
 /* ---- step post-processing (either side of the optimizer step) -----------------------------
  * mop_kabsch replaces Calculationtools.kabsch_algorithm (Utils/calc_tools.py:412-425): P, Q [B][natoms][3];
  * P_aligned = P centred and rotated onto Q, Q_centred (optional) = Q minus its centroid (the reference

@@ -1,6 +1,6 @@
-"""Drop-in for the AFIR part of ``multioptpy.Potential.potential.BiasPotentialCalculation``
-(Potential/potential.py:53-202): sums the bias energy / gradient / Hessian of every AFIR term
-of ``force_data`` (the only bias potential the north-star path names; other potentials raise).
+"""Drop-in for ``multioptpy.Potential.potential.BiasPotentialCalculation`` (Potential/potential.py:53-202)
+restricted to the potentials built on the device: sums the bias energy / gradient / Hessian of every AFIR
+term and of the keep (distance, fragment distance, angle) restraints of ``force_data``; other potentials raise.
 The reference's side effects (.npy / .log files, :144,191-192) are not reproduced."""
 from __future__ import annotations
 
@@ -8,9 +8,10 @@ import numpy as np
 import torch
 
 from .._lib import MopError
+from .. import ops
 from .AFIR_potential import AFIRPotential
 
-_OTHER_KEYS = ["linear_mechano_force", "linear_mechano_force_v2", "flux_pot_const", "keep_pot_v2_spring_const",
+_OTHER_KEYS = ["linear_mechano_force", "linear_mechano_force_v2", "flux_pot_const",
                "keep_angle_v2_spring_const", "keep_dihedral_angle_v2_spring_const", "repulsive_potential_well_scale",
                "gaussian_potential_target", "nano_reactor_potential", "asymmetric_ellipsoidal_repulsive_potential_eps"]
 
@@ -52,4 +53,27 @@ class BiasPotentialCalculation:
             B_e += float(E.item())
             bias_grad = bias_grad + gr.cpu().numpy()
             bias_hess = bias_hess + H.cpu().numpy()
+        # restraints (potential.py:640-672,742-752): one launch for all terms
+        terms = []
+        for i, k in enumerate(force_data.get("keep_pot_spring_const", [])):
+            if k != 0.0:
+                a, b = force_data["keep_pot_atom_pairs"][i]
+                terms.append((ops.BIAS_KEEP, [a - 1], [b - 1], float(k), float(force_data["keep_pot_distance"][i])))
+        for i, k in enumerate(force_data.get("keep_pot_v2_spring_const", [])):
+            if 0.0 not in k:
+                terms.append((ops.BIAS_KEEP_V2, [a - 1 for a in force_data["keep_pot_v2_fragm1"][i]],
+                              [a - 1 for a in force_data["keep_pot_v2_fragm2"][i]], float(k[0]),
+                              float(force_data["keep_pot_v2_distance"][i][0])))
+        if N > 2:
+            for i, k in enumerate(force_data.get("keep_angle_spring_const", [])):
+                if k != 0.0:
+                    terms.append((ops.BIAS_KEEP_ANGLE, [a - 1 for a in force_data["keep_angle_atom_pairs"][i]], [],
+                                  float(k), float(force_data["keep_angle_angle"][i])))
+        if terms:
+            dev = torch.device(self.device)
+            xyz = torch.as_tensor(np.ascontiguousarray(geom)).reshape(1, N, 3).to(dev)
+            E, gr, H = ops.bias_terms(xyz, ops.pack_bias_terms(terms, dev), len(terms))
+            B_e += float(E[0].item())
+            bias_grad = bias_grad + gr[0].cpu().numpy().reshape(N, 3)
+            bias_hess = bias_hess + H[0].cpu().numpy()
         return bias_grad, B_e + e, g + bias_grad, bias_hess

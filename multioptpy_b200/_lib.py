@@ -42,6 +42,8 @@ SIGNATURES = {
     "mop_connectivity": (_i, [_i, _i, _p, _p, _i, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_fischer_workspace_bytes": (_sz, [_i, _i]),
     "mop_fischer_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mop_bias_term_bytes": (_sz, []),
+    "mop_bias_terms": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_kabsch": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_check_convergence": (_i, [_i, _i, _p, _p, _d, _d, _d, _d, _p, _p, _p]),
     "mop_ric_bmatrix": (_i, [_i, _i, _p, _p, _p]),

@@ -1,0 +1,126 @@
+// Restraint bias potentials: energy, gradient and Hessian of
+//   kind 1  StructKeepPotential     (Potential/keep_potential.py:5-61)   E = 1/2 k (|x_i - x_j| - r0)^2
+//   kind 2  StructKeepPotentialv2   (keep_potential.py:64-116)           same between two fragment centroids
+//   kind 3  StructKeepAnglePotential (keep_angle_potential.py:7-229)     E = 1/2 k (theta - theta0)^2 with the
+//           reference's fifth-order expansions of acos^2 within 1e-3 rad of 0 and pi and its three
+//           theta0 branches
+// The reference differentiates calc_energy with torch.func.jacrev / hessian on the CPU
+// (Potential/potential.py:127-137); here thread (term, coordinate pair) evaluates the same expression once in
+// hyper-dual arithmetic.  Results are ADDED to E, grad, hess (the aggregator sums all bias terms).
+#include "hyperdual.cuh"
+
+namespace mop {
+
+constexpr int BIAS_MAXA = 64;  // atoms per term (both fragments together)
+
+struct BiasTerm {
+  int kind;
+  int n1, n2;             // atoms in fragment 1 / 2 (kind 1: 1, 1; kind 3: atoms i, j, k in `atoms`, n1 = 3)
+  int atoms[BIAS_MAXA];   // 0-based
+  double k, p;            // spring constant; r0 in Angstrom (kinds 1, 2) or theta0 in degrees (kind 3)
+};
+
+__device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) {
+  // coordinate index c = 3 * (position in t.atoms) + component; seeds on ca, cb
+  auto X = [&](int pos, int comp) -> HD {
+    const int c = 3 * pos + comp;
+    return HD{xyz[3 * t.atoms[pos] + comp], c == ca ? 1.0 : 0.0, c == cb ? 1.0 : 0.0, 0.0};
+  };
+  const double BOHR2ANG = 0.52917721067;
+  if (t.kind == 1 || t.kind == 2) {
+    HD v[3];
+    for (int c = 0; c < 3; ++c) {
+      HD s1 = hd_const(0.0), s2 = hd_const(0.0);
+      for (int a = 0; a < t.n1; ++a) s1 = s1 + X(a, c);
+      for (int a = 0; a < t.n2; ++a) s2 = s2 + X(t.n1 + a, c);
+      v[c] = (1.0 / t.n1) * s1 - (1.0 / t.n2) * s2;
+    }
+    const HD d = hd_clamp_min(hd_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12);
+    const HD diff = d - hd_const(t.p / BOHR2ANG);
+    return (0.5 * t.k) * (diff * diff);
+  }
+  // kind 3
+  const double PI = 3.141592653589793;
+  const double theta0 = t.p * (PI / 180.0);
+  HD v1[3], v2[3];
+  for (int c = 0; c < 3; ++c) {
+    v1[c] = X(0, c) - X(1, c);
+    v2[c] = X(2, c) - X(1, c);
+  }
+  const HD n1 = hd_sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+  const HD n2 = hd_sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+  const HD n12 = hd_clamp_min(n1 * n2, 1e-12);
+  HD u = (v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2]) / n12;
+  u = hd_clamp(u, -1.0, 1.0);
+  const double ucp = cos(1e-3), ucn = cos(PI - 1e-3);
+  auto taylor = [](HD delta) -> HD {  // (acos(1 - delta))^2, Horner as the reference
+    HD term = hd_const(128.0 / 1575.0);
+    term = hd_const(4.0 / 35.0) + delta * term;
+    term = hd_const(8.0 / 45.0) + delta * term;
+    term = hd_const(1.0 / 3.0) + delta * term;
+    term = hd_const(2.0) + delta * term;
+    return delta * term;
+  };
+  const bool near0 = u.f > ucp, nearpi = u.f < ucn;
+  HD theta_minus;  // theta - theta0 (or its stand-in), energy = 1/2 k (.)^2
+  if (fabs(theta0) < 1e-8) {                 // branch A
+    if (near0) return (0.5 * t.k) * taylor(hd_const(1.0) - u);
+    if (nearpi) {
+      const HD th = hd_const(PI) - hd_sqrt(hd_clamp_min(taylor(hd_const(1.0) + u), 1e-30));
+      return (0.5 * t.k) * (th * th);
+    }
+    const HD th = hd_acos(hd_clamp(u, ucn, ucp));
+    return (0.5 * t.k) * (th * th);
+  }
+  if (fabs(theta0 - PI) < 1e-8) {            // branch B
+    if (nearpi) return (0.5 * t.k) * taylor(hd_const(1.0) + u);
+    if (near0) theta_minus = hd_sqrt(hd_clamp_min(taylor(hd_const(1.0) - u), 1e-30)) - hd_const(PI);
+    else theta_minus = hd_acos(hd_clamp(u, ucn, ucp)) - hd_const(PI);
+    return (0.5 * t.k) * (theta_minus * theta_minus);
+  }
+  if (near0) theta_minus = hd_sqrt(hd_clamp_min(taylor(hd_const(1.0) - u), 1e-30)) - hd_const(theta0);
+  else if (nearpi) theta_minus = (hd_const(PI) - hd_sqrt(hd_clamp_min(taylor(hd_const(1.0) + u), 1e-30))) - hd_const(theta0);
+  else theta_minus = hd_acos(u) - hd_const(theta0);
+  return (0.5 * t.k) * (theta_minus * theta_minus);
+}
+
+__global__ void __launch_bounds__(128) k_bias_terms(int N, const BiasTerm* __restrict__ terms, const double* __restrict__ xyz_all,
+                                                    double* __restrict__ E_all, double* __restrict__ g_all,
+                                                    double* __restrict__ H_all) {
+  __shared__ BiasTerm t;
+  const int b = blockIdx.y, n = 3 * N;
+  if (threadIdx.x == 0) t = terms[blockIdx.x];
+  __syncthreads();
+  const int m = t.kind == 3 ? 3 : t.n1 + t.n2, nc = 3 * m;
+  const double* xyz = xyz_all + (size_t)b * n;
+  for (int w = threadIdx.x; w < nc * nc; w += blockDim.x) {
+    const int ca = w / nc, cb = w - ca * nc;
+    if (cb < ca) continue;
+    const HD e = bias_energy(t, xyz, ca, cb);
+    const int ga = 3 * t.atoms[ca / 3] + ca % 3, gb = 3 * t.atoms[cb / 3] + cb % 3;
+    if (H_all) {
+      atomicAdd(&H_all[(size_t)b * n * n + (size_t)ga * n + gb], e.ab);
+      if (ca != cb) atomicAdd(&H_all[(size_t)b * n * n + (size_t)gb * n + ga], e.ab);
+    }
+    if (ca == cb) {
+      if (g_all) atomicAdd(&g_all[(size_t)b * n + ga], e.a);
+      if (ca == 0 && E_all) atomicAdd(&E_all[b], e.f);
+    }
+  }
+}
+
+}  // namespace mop
+
+// terms: device array of nterm records {int32 kind, n1, n2, atoms[64]; double k, p} (264 + 16 bytes, see
+// mop_bias_term_bytes); E [B], grad [B][3 natoms], hess [B][3 natoms][3 natoms] are accumulated into.
+extern "C" size_t mop_bias_term_bytes(void) { return sizeof(mop::BiasTerm); }
+
+extern "C" int mop_bias_terms(int B, int natoms, int nterm, const void* terms, const double* xyz, double* E, double* grad,
+                              double* hess, void* stream) {
+  MOP_REQUIRE(B >= 0 && natoms > 0 && nterm >= 0 && xyz && (nterm == 0 || terms), "mop_bias_terms: bad arguments");
+  if (B == 0 || nterm == 0) return MOP_OK;
+  dim3 grid(nterm, B);
+  mop::k_bias_terms<<<grid, 128, 0, (cudaStream_t)stream>>>(natoms, (const mop::BiasTerm*)terms, xyz, E, grad, hess);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}

@@ -10,6 +10,7 @@
 //                       SVD of the symmetric G = pB^T pB is its eigendecomposition (batched eigensolver)
 // All kernels are HBM-bound streaming / gather kernels; one CTA (or warp) per structure, row or term.
 #include "common.cuh"
+#include "hyperdual.cuh"
 
 namespace mop {
 
@@ -253,33 +254,6 @@ __global__ void __launch_bounds__(256) k_ric_bthb(int N, int diag, const double*
 }
 
 // ---- K matrix: hyper-dual second derivatives --------------------------------------------------------
-struct HD {
-  double f, a, b, ab;
-};
-__device__ __forceinline__ HD hd_const(double x) { return HD{x, 0.0, 0.0, 0.0}; }
-__device__ __forceinline__ HD operator+(HD x, HD y) { return HD{x.f + y.f, x.a + y.a, x.b + y.b, x.ab + y.ab}; }
-__device__ __forceinline__ HD operator-(HD x, HD y) { return HD{x.f - y.f, x.a - y.a, x.b - y.b, x.ab - y.ab}; }
-__device__ __forceinline__ HD operator*(HD x, HD y) {
-  return HD{x.f * y.f, x.a * y.f + x.f * y.a, x.b * y.f + x.f * y.b, x.ab * y.f + x.a * y.b + x.b * y.a + x.f * y.ab};
-}
-__device__ __forceinline__ HD hd_unary(HD x, double g, double g1, double g2) {
-  return HD{g, g1 * x.a, g1 * x.b, g1 * x.ab + g2 * x.a * x.b};
-}
-__device__ __forceinline__ HD hd_recip(HD x) { const double r = 1.0 / x.f; return hd_unary(x, r, -r * r, 2.0 * r * r * r); }
-__device__ __forceinline__ HD operator/(HD x, HD y) { return x * hd_recip(y); }
-__device__ __forceinline__ HD hd_sqrt(HD x) { const double s = sqrt(x.f); return hd_unary(x, s, 0.5 / s, -0.25 / (s * x.f)); }
-__device__ __forceinline__ HD hd_acos(HD x) {
-  const double om = 1.0 - x.f * x.f, s = sqrt(om);
-  return hd_unary(x, acos(x.f), -1.0 / s, -x.f / (s * om));
-}
-__device__ __forceinline__ HD hd_abs(HD x) { return x.f < 0.0 ? HD{-x.f, -x.a, -x.b, -x.ab} : x; }
-__device__ __forceinline__ HD hd_dot(const HD* u, const HD* v) { return u[0] * v[0] + u[1] * v[1] + u[2] * v[2]; }
-__device__ __forceinline__ void hd_cross(const HD* u, const HD* v, HD* c) {
-  c[0] = u[1] * v[2] - u[2] * v[1];
-  c[1] = u[2] * v[0] - u[0] * v[2];
-  c[2] = u[0] * v[1] - u[1] * v[0];
-}
-
 // TorchDerivatives.distance / angle / dihedral_angle (:442-477) on m atoms
 __device__ HD ric_coordinate(const HD (*c)[3], int m) {
   if (m == 2) {

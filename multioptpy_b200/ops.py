@@ -612,3 +612,45 @@ def neb_fire_advance(vneb, force, prev_velocity, dt, reset):
                                       _ptr(vnew), _ptr(delta), _stream(vneb.device))
     _lib.check(rc, "mop_neb_fire_advance")
     return vnew, delta
+
+
+# ------------------------------------------------------------------ restraint bias potentials
+BIAS_KEEP, BIAS_KEEP_V2, BIAS_KEEP_ANGLE = 1, 2, 3
+BIAS_MAXA = 64
+
+
+def pack_bias_terms(terms, device):
+    """terms: list of (kind, frag1 (0-based atoms), frag2, k, p) -> uint8 device tensor for bias_terms."""
+    import numpy as _np
+    lib = _lib.load()
+    rec = int(lib.mop_bias_term_bytes())
+    dt = _np.dtype([("kind", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("atoms", "<i4", (BIAS_MAXA,)), ("pad", "<i4"), ("k", "<f8"), ("p", "<f8")])
+    if dt.itemsize != rec:
+        raise MopError(f"bias term layout mismatch ({dt.itemsize} != {rec})")
+    buf = _np.zeros(len(terms), dtype=dt)
+    for i, (kind, f1, f2, k, p) in enumerate(terms):
+        at = list(f1) + list(f2)
+        if len(at) > BIAS_MAXA:
+            raise MopError("bias term: more than 64 atoms")
+        buf[i]["kind"], buf[i]["n1"], buf[i]["n2"] = kind, len(f1), len(f2)
+        buf[i]["atoms"][: len(at)] = at
+        buf[i]["k"], buf[i]["p"] = k, p
+    return torch.from_numpy(buf.view(_np.uint8).reshape(-1).copy()).to(device)
+
+
+def bias_terms(xyz, packed, nterm, E=None, grad=None, hess=None):
+    """Add E / gradient / Hessian of the packed restraint terms to E (B,), grad (B, 3N), hess (B, 3N, 3N)."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    dev = xyz.device
+    if E is None:
+        E = torch.zeros(B, dtype=torch.float64, device=dev)
+    if grad is None:
+        grad = torch.zeros(B, 3 * N, dtype=torch.float64, device=dev)
+    if hess is None:
+        hess = torch.zeros(B, 3 * N, 3 * N, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mop_bias_terms(B, N, int(nterm), _ptr(packed), _ptr(xyz), _ptr(E), _ptr(grad), _ptr(hess), _stream(dev))
+    _lib.check(rc, "mop_bias_terms")
+    return E, grad, hess

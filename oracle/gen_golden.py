@@ -622,6 +622,47 @@ def gen_ric():
     np.savez_compressed(os.path.join(GOLD, "ric.npz"), **blob)
 
 
+def gen_keep():
+    """Restraint bias potentials (Potential/keep_potential.py, keep_angle_potential.py): E, gradient and
+    Hessian by torch.func as the aggregator computes them (Potential/potential.py:127-137)."""
+    import torch
+    kp = ref_shim.ref("Potential.keep_potential")
+    ka = ref_shim.ref("Potential.keep_angle_potential")
+    elems, xyz = read_xyz(os.path.join(ref_shim.REF_ROOT, "test/aldol_rxn.xyz"))
+    N = len(elems)
+    lin = xyz.copy(); lin[1] = lin[0] + np.array([2.0, 0, 0]); lin[2] = lin[0] + np.array([4.3, 1e-5, 0])     # i=0? see cases
+    cases = [
+        ("keep_1_5", 1, [0], [4], 0.4, 1.6, xyz),
+        ("keep_3_11", 1, [2], [10], 1.2, 3.1, xyz),
+        ("keepv2", 2, [0, 1, 2, 3], [4, 5, 6, 7, 8], 0.7, 2.5, xyz),
+        ("angle_gen", 3, [1, 0, 2], [], 0.3, 109.5, xyz),
+        ("angle_to_180", 3, [5, 4, 9], [], 0.2, 180.0, xyz),
+        ("angle_to_0", 3, [5, 4, 9], [], 0.2, 0.0, xyz),
+        ("angle_near_pi", 3, [1, 0, 2], [], 0.5, 120.0, lin),      # atoms 1-0-2 almost linear: Taylor branch at pi
+        ("angle_near_pi_180", 3, [1, 0, 2], [], 0.5, 180.0, lin),
+    ]
+    lin[1] = lin[0] + np.array([-2.0, 0, 0]); lin[2] = lin[0] + np.array([2.3, 4e-4, 0])
+    blob = {"names": np.array([c[0] for c in cases])}
+    for name, kind, f1, f2, k, p, geom in cases:
+        g = torch.tensor(geom, dtype=torch.float64)
+        par = torch.tensor([k, p], dtype=torch.float64)
+        if kind == 1:
+            pot = kp.StructKeepPotential(keep_pot_spring_const=k, keep_pot_distance=p, keep_pot_atom_pairs=[f1[0] + 1, f2[0] + 1])
+        elif kind == 2:
+            pot = kp.StructKeepPotentialv2(keep_pot_v2_spring_const=k, keep_pot_v2_distance=p,
+                                           keep_pot_v2_fragm1=[a + 1 for a in f1], keep_pot_v2_fragm2=[a + 1 for a in f2])
+        else:
+            pot = ka.StructKeepAnglePotential(keep_angle_atom_pairs=[a + 1 for a in f1], keep_angle_spring_const=k, keep_angle_angle=p)
+        E = float(pot.calc_energy(g, par))
+        gr = torch.func.jacrev(pot.calc_energy, argnums=0)(g, par).numpy()
+        H = torch.func.hessian(pot.calc_energy, argnums=0)(g, par).reshape(3 * N, 3 * N).numpy()
+        blob[f"{name}/xyz"] = geom; blob[f"{name}/kind"] = np.int32(kind)
+        blob[f"{name}/f1"] = np.array(f1, np.int32); blob[f"{name}/f2"] = np.array(f2, np.int32)
+        blob[f"{name}/kp"] = np.array([k, p]); blob[f"{name}/E"] = E; blob[f"{name}/g"] = gr; blob[f"{name}/H"] = H
+        print("keep case", name, "E", E, "|g|", np.linalg.norm(gr), "|H|", np.linalg.norm(H))
+    np.savez_compressed(os.path.join(GOLD, "keep.npz"), **blob)
+
+
 def gen_fire():
     """FIRE optimizer of the NEB driver (Optimizer/fire_neb.py): 8-iteration trace on a synthetic chain with
     a quadratic force field, (dt, a, n_reset) schedule included."""
@@ -791,7 +832,7 @@ def gen_rsprfo():
     np.savez_compressed(os.path.join(GOLD, "rsprfo_traces.npz"), **blob)
 
 
-SETS = {"fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+SETS = {"keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo}
 
 if __name__ == "__main__":

@@ -1649,3 +1649,64 @@ class FIRENEBOracle:
         nimg = X.shape[0]
         move = neb_limit_tr(X.reshape(nimg, -1), F.reshape(nimg, -1), delta.reshape(nimg, -1), step_limit=False)
         return Vnew, delta, move.reshape(X.shape), P
+
+
+# ---------------------------------------------------------------------------------------------
+# Restraint bias potentials: Potential/keep_potential.py, keep_angle_potential.py
+# ---------------------------------------------------------------------------------------------
+def _keep_energy_torch(geom, kind, f1, f2, k, p):
+    """calc_energy of StructKeepPotential (kind 1), StructKeepPotentialv2 (kind 2), StructKeepAnglePotential
+    (kind 3) restated on a torch tensor (atoms 0-based; p = distance in Angstrom or angle in degrees)."""
+    import math
+    import torch
+    if kind in (1, 2):
+        v = geom[list(f1)].mean(dim=0) - geom[list(f2)].mean(dim=0)
+        d = torch.clamp(torch.sqrt(torch.sum(v ** 2)), min=1e-12)
+        return 0.5 * k * (d - p / BOHR2ANG) ** 2
+    i, j, kk = f1
+    theta0 = math.radians(p) if False else p * (math.pi / 180.0)
+    v1, v2 = geom[i] - geom[j], geom[kk] - geom[j]
+    u = torch.dot(v1, v2) / torch.clamp(torch.linalg.norm(v1) * torch.linalg.norm(v2), min=1e-12)
+    u = torch.clamp(u, -1.0, 1.0)
+    ucp, ucn = math.cos(1e-3), math.cos(math.pi - 1e-3)
+    C = [128.0 / 1575.0, 4.0 / 35.0, 8.0 / 45.0, 1.0 / 3.0, 2.0]
+
+    def taylor(delta):
+        t = C[0]
+        for c in C[1:]:
+            t = c + delta * t
+        return delta * t
+    near0, nearpi = bool(u > ucp), bool(u < ucn)
+    if abs(theta0) < 1e-8:
+        if near0:
+            return 0.5 * k * taylor(1.0 - u)
+        if nearpi:
+            return 0.5 * k * (math.pi - torch.sqrt(torch.clamp(taylor(1.0 + u), min=1e-30))) ** 2
+        return 0.5 * k * torch.acos(torch.clamp(u, ucn, ucp)) ** 2
+    if abs(theta0 - math.pi) < 1e-8:
+        if nearpi:
+            return 0.5 * k * taylor(1.0 + u)
+        if near0:
+            return 0.5 * k * (torch.sqrt(torch.clamp(taylor(1.0 - u), min=1e-30)) - math.pi) ** 2
+        return 0.5 * k * (torch.acos(torch.clamp(u, ucn, ucp)) - math.pi) ** 2
+    if near0:
+        th = torch.sqrt(torch.clamp(taylor(1.0 - u), min=1e-30))
+    elif nearpi:
+        th = math.pi - torch.sqrt(torch.clamp(taylor(1.0 + u), min=1e-30))
+    else:
+        th = torch.acos(u)
+    return 0.5 * k * (th - theta0) ** 2
+
+
+BOHR2ANG = 0.52917721067
+
+
+def keep_egh(coord, kind, f1, f2, k, p):
+    """(E, grad (N,3), hess (3N,3N)) by torch.func, as Potential/potential.py:127-137 does."""
+    import torch
+    geom = torch.tensor(np.asarray(coord, float), dtype=torch.float64)
+    f = lambda x: _keep_energy_torch(x, kind, f1, f2, k, p)
+    E = f(geom)
+    g = torch.func.jacrev(f)(geom)
+    H = torch.func.hessian(f)(geom).reshape(geom.numel(), geom.numel())
+    return float(E), g.numpy(), H.numpy()
