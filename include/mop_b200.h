@@ -378,6 +378,7 @@ int mop_debug_eigh_small_pipeline(int on); /* tuning: mop_eigh at n <= 158 throu
 int mop_debug_tri_packed(int on);       /* tuning: packed two-CTA-per-SM tridiagonalisation in the fused RS-I-RFO path (default 1) */
 int mop_debug_packed_timing(void* buf);   /* diagnostics: [B][16] int64 phase cycles of the packed kernel */
 int mop_debug_packed_threads(int threads); /* tuning: CTA size of the packed kernel (128, 256, 512) */
+int mop_debug_large_pair(int mode);     /* tuning: two matrices per cluster in lock-step: 0 auto, 1 always, -1 never */
 int mop_debug_large_ablate(int mask); /* diagnostics: bit0 no trailing stores, bit1 no trailing loads (results invalid) */
 int mop_debug_large_timing(void* buf); /* diagnostics: [B][4] int64 phase cycles of the MOP_EIGH_LARGE reduction */
 int mop_debug_barrier_latency(int threads, double* out, void* stream);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mop_debug_latency": (_i, [_p, _p]),
     "mop_debug_barrier_latency": (_i, [_i, _p, _p]),
     "mop_debug_large_cluster": (_i, [_i]),
+    "mop_debug_large_pair": (_i, [_i]),
     "mop_debug_tri_packed": (_i, [_i]),
     "mop_debug_eigh_small_pipeline": (_i, [_i]),
     "mop_debug_packed_threads": (_i, [_i]),

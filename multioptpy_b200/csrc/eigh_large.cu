@@ -414,6 +414,153 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
     for (int q = 0; q < 4; ++q) a.dbg[(size_t)b * 4 + q] = tacc[q];
 }
 
+// Two matrices per cluster in lock-step: the per-column fixed costs (pivot-row pull, two block
+// reductions, the Householder scalar chain, the cluster barrier and its wait for the slowest warp)
+// are paid once per PAIR of columns, and the two independent update + symv passes give every warp
+// twice the loads in flight between barriers.  blockIdx.x / CL = pair index; matrices 2 pair and
+// 2 pair + 1 (the second may not exist: its arithmetic is skipped, the barriers are not).
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2x(LgArgs a, int B) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+  const int pair = blockIdx.x / CL;
+  const int n = a.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = THREADS / 32;
+  const int np = (n + 3) & ~3;
+  extern __shared__ double sm[];
+  // per matrix m: vb [2][np] | pb [2][np] | rowb [2][np] | rcur [np] | wv [np]  = 8 np doubles
+  double* base[2] = {sm, sm + 8 * (size_t)np};
+  __shared__ double s_rb[2 * 32 * 2];
+  int parity = 0;
+  const int bm[2] = {2 * pair, 2 * pair + 1};
+  const bool act[2] = {true, bm[1] < B};
+  double* A[2];
+  double* Vh[2];
+  for (int m = 0; m < 2; ++m) {
+    const int b = act[m] ? bm[m] : bm[0];
+    A[m] = a.A + (size_t)b * n * n;
+    Vh[m] = a.Vh + (size_t)b * n * n;
+  }
+  const int W = CL * NW, gw = wid * CL + cr;
+  double tau_prev[2] = {0.0, 0.0};
+  int cur = 0;
+
+  for (int m = 0; m < 2; ++m) {
+    double* vb = base[m];
+    double* rowb = vb + 4 * np;
+    double* wv = vb + 7 * np;
+    if (gw == 0 && act[m])
+      for (int j = lane; j < n; j += 32) rowb[j] = A[m][j];
+    for (int j = tid; j < np; j += THREADS) {
+      vb[j] = 0.0;
+      wv[j] = 0.0;
+    }
+  }
+  cluster.sync();
+
+  for (int k = 0; k < n; ++k) {
+    const bool pend = k > 0;
+    // (1) pull the pivot rows, p . v
+    double part[2] = {0.0, 0.0};
+    for (int m = 0; m < 2; ++m) {
+      if (!act[m]) continue;
+      double* vb = base[m];
+      const double* v = vb + cur * np;
+      const double* p = vb + 2 * np + (k & 1) * np;
+      double* rcur = vb + 6 * np;
+      const double* rrow = cluster.map_shared_rank(vb + 4 * np + (k & 1) * np, k % CL);
+      for (int j = k + tid; j < n; j += THREADS) {
+        rcur[j] = rrow[j];
+        if (pend) part[m] = fma(p[j], v[j], part[m]);
+      }
+    }
+    block_sum_k<2>(part, s_rb, parity);
+    // (2) w, row k through the pending reflector, its norm
+    double x2[2] = {0.0, 0.0}, cc[2];
+    for (int m = 0; m < 2; ++m) {
+      cc[m] = 0.5 * tau_prev[m] * tau_prev[m] * part[m];
+      if (!act[m]) continue;
+      double* vb = base[m];
+      const double* v = vb + cur * np;
+      const double* p = vb + 2 * np + (k & 1) * np;
+      double* rcur = vb + 6 * np;
+      double* wv = vb + 7 * np;
+      if (pend) {
+        const double vk = v[k], wk = fma(tau_prev[m], p[k], -cc[m] * vk);
+        for (int j = k + tid; j < n; j += THREADS) {
+          const double vj = v[j];
+          const double wj = fma(tau_prev[m], p[j], -cc[m] * vj);
+          wv[j] = wj;
+          const double r = rcur[j] - fma(vk, wj, wk * vj);
+          rcur[j] = r;
+          if (j >= k + 2) x2[m] = fma(r, r, x2[m]);
+        }
+      } else {
+        for (int j = k + 2 + tid; j < n; j += THREADS) x2[m] = fma(rcur[j], rcur[j], x2[m]);
+      }
+    }
+    block_sum_k<2>(x2, s_rb, parity);
+    double tau[2] = {0.0, 0.0};
+    for (int m = 0; m < 2; ++m) {
+      if (!act[m]) continue;
+      double* vb = base[m];
+      double* vnew = vb + (cur ^ 1) * np;
+      const double* rcur = vb + 6 * np;
+      const double dk = rcur[k];
+      const double alpha = (k + 1 < n) ? rcur[k + 1] : 0.0;
+      double ek = alpha, scl = 0.0;
+      if (k <= n - 3 && x2[m] > 0.0) {
+        const double beta = -copysign(sqrt(fma(alpha, alpha, x2[m])), alpha);
+        tau[m] = (beta - alpha) / beta;
+        scl = 1.0 / (alpha - beta);
+        ek = beta;
+      }
+      if (cr == 0 && tid == 0) {
+        a.dd[(size_t)bm[m] * n + k] = dk;
+        a.ee[(size_t)bm[m] * n + k] = (k + 1 < n) ? ek : 0.0;
+        a.tau[(size_t)bm[m] * n + k] = tau[m];
+      }
+      if (k < n - 1)
+        for (int j = k + 1 + tid; j < n; j += THREADS) {
+          const double vj = (j == k + 1) ? 1.0 : rcur[j] * scl;
+          vnew[j] = vj;
+          if (cr == 0) Vh[m][(size_t)k * n + j] = vj;
+        }
+    }
+    if (k == n - 1) break;
+    __syncthreads();
+    // (3) own live rows (>= k+1) of both matrices: pending rank-2 update fused with A v'
+    {
+      const int q0 = (k + 1 > gw) ? (k + 1 - gw + W - 1) / W : 0;
+      const int first = gw + q0 * W;
+      const int rl = first < n ? (n - 1 - first) / W + 1 : 0;
+      for (int m = 0; m < 2; ++m) {
+        if (!act[m]) continue;
+        double* vb = base[m];
+        const double* v = vb + cur * np;
+        const double* vnew = vb + (cur ^ 1) * np;
+        const double* wv = vb + 7 * np;
+        double* rpub = vb + 4 * np + ((k + 1) & 1) * np;
+        double* pnext = vb + 2 * np + ((k + 1) & 1) * np;
+#define LG_CASE(RLV)                                                                                                    \
+  case RLV:                                                                                                             \
+    if constexpr (RLV <= R) lg_step3<RLV>(cluster, CL, A[m], n, k, first, W, lane, v, wv, vnew, rpub, pnext, a.ablate); \
+    break;
+        switch (rl) {
+          LG_CASE(1) LG_CASE(2) LG_CASE(3) LG_CASE(4) LG_CASE(5) LG_CASE(6) LG_CASE(7) LG_CASE(8) LG_CASE(9) LG_CASE(10)
+          default: break;
+        }
+#undef LG_CASE
+      }
+    }
+    cur ^= 1;
+    tau_prev[0] = tau[0];
+    tau_prev[1] = tau[1];
+    cluster.sync();
+  }
+  cluster.sync();  // nobody leaves while its shared memory may still be read
+}
+
 // ---- 2. eigenpairs of T, one CTA per matrix ---------------------------------------------------
 __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
   constexpr int THREADS = LG_EIG_THREADS;
@@ -879,6 +1026,11 @@ __global__ void k_lg_clear_tau_flagged(int n, const int32_t* __restrict__ status
 // ------------------------------------------------------------------------------------------------
 static size_t lg_al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int g_lg_cluster = 0;
+static int g_lg_pair = 0;   // 0 auto, 1 always, -1 never
+extern "C" int mop_debug_large_pair(int mode) {
+  g_lg_pair = mode;
+  return MOP_OK;
+}
 extern "C" int mop_debug_large_cluster(int cl) {
   g_lg_cluster = cl;
   return MOP_OK;
@@ -991,9 +1143,28 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
       cfg.dynamicSmemBytes = smem;
       MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag, a));
     } else {
-      const size_t smem = sizeof(double) * 8 * (size_t)np;
+      // two matrices per cluster in lock-step when the batch still fills the GPU with pairs
+      const bool paired = g_lg_pair >= 0 && (g_lg_pair == 1 || B >= 2 * (148 / CL));
+      const size_t smem = sizeof(double) * (paired ? 16 : 8) * (size_t)np;
       cfg.blockDim = dim3(T2);
       cfg.dynamicSmemBytes = smem;
+      if (paired) {
+        cfg.gridDim = dim3((unsigned)(((B + 1) / 2) * CL));
+#define LG_LAUNCH2X(RR)                                                                                          \
+  do {                                                                                                           \
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag2x<RR, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                             \
+    MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag2x<RR, T2>, a, B));                                  \
+  } while (0)
+        if (R <= 2) LG_LAUNCH2X(2);
+        else if (R == 3) LG_LAUNCH2X(3);
+        else if (R == 4) LG_LAUNCH2X(4);
+        else if (R == 5) LG_LAUNCH2X(5);
+        else if (R == 6) LG_LAUNCH2X(6);
+        else if (R <= 8) LG_LAUNCH2X(8);
+        else LG_LAUNCH2X(10);
+#undef LG_LAUNCH2X
+      } else {
 #define LG_LAUNCH2(RR)                                                                                          \
   do {                                                                                                          \
     MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag2<RR, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1008,6 +1179,7 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
       else if (R <= 8) LG_LAUNCH2(8);
       else LG_LAUNCH2(10);
 #undef LG_LAUNCH2
+      }
     }
   }
   {
