@@ -561,6 +561,105 @@ __global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2x(LgArgs a, int B) {
   cluster.sync();  // nobody leaves while its shared memory may still be read
 }
 
+// ---- inverse iteration for a cluster vector that cancelled (LAPACK dstein's method) -----------------
+// Twisted-factorisation vectors of (numerically) multiple eigenvalues are nearly parallel, so
+// orthogonalising them against each other leaves rounding noise.  Such a vector is rebuilt by inverse
+// iteration on the unreduced block [s, t): random start, (T - lam I)^{-1} by Gaussian elimination with
+// partial pivoting (dgttrf / dgtts2 recurrences, tiny pivots replaced), re-orthogonalisation against the
+// cluster vectors found so far after every solve.  One warp; lane 0 runs the O(m) recurrences in shared
+// memory.  fix: 6 arrays of np doubles (x | dl | dd | du | du2 | piv).  prev: rows [0, nprev) of R
+// (stride lds) are the finished cluster vectors.  Result in fix[0 .. m).
+__device__ void lg_inverse_iteration(const double* d, const double* e, int s, int t, double lam, const double* R, size_t lds,
+                                     int nprev, double* fix, int np, int lane, unsigned seed) {
+  const int m = t - s;
+  double* x = fix;
+  double* dl = fix + np;
+  double* dd = fix + 2 * np;
+  double* du = fix + 3 * np;
+  double* du2 = fix + 4 * np;
+  double* pv = fix + 5 * np;
+  const double tiny = TRI_EPS;  // T is scaled to unit norm
+  for (int i = lane; i < m; i += 32) {
+    unsigned h = (seed + 0x9e3779b9u * (unsigned)(i + 1));
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    x[i] = (double)(h & 0xffffffu) / 8388608.0 - 1.0;
+  }
+  __syncwarp();
+  if (lane == 0) {  // factorise T - lam I
+    for (int i = 0; i < m; ++i) {
+      dd[i] = d[s + i] - lam;
+      if (i < m - 1) {
+        du[i] = e[s + i];
+        dl[i] = e[s + i];
+      }
+      du2[i] = 0.0;
+      pv[i] = 0.0;
+    }
+    for (int i = 0; i < m - 1; ++i) {
+      if (fabs(dd[i]) >= fabs(dl[i])) {
+        if (fabs(dd[i]) < tiny) dd[i] = dd[i] < 0.0 ? -tiny : tiny;
+        const double f = dl[i] / dd[i];
+        dl[i] = f;
+        dd[i + 1] -= f * du[i];
+      } else {
+        const double f = dd[i] / dl[i];
+        dd[i] = dl[i];
+        dl[i] = f;
+        const double tmp = du[i];
+        du[i] = dd[i + 1];
+        dd[i + 1] = tmp - f * dd[i + 1];
+        if (i < m - 2) {
+          du2[i] = du[i + 1];
+          du[i + 1] = -f * du[i + 1];
+        }
+        pv[i] = 1.0;
+      }
+    }
+    if (fabs(dd[m - 1]) < tiny) dd[m - 1] = dd[m - 1] < 0.0 ? -tiny : tiny;
+  }
+  __syncwarp();
+  for (int it = 0; it < 4; ++it) {
+    // orthogonalise against the finished cluster vectors (twice), normalise
+    for (int rep = 0; rep < 2; ++rep)
+      for (int p = 0; p < nprev; ++p) {
+        const double* rp = R + (size_t)p * lds + s;
+        double dt = 0.0;
+        for (int i = lane; i < m; i += 32) dt = fma(rp[i], x[i], dt);
+        dt = warp_sum(dt);
+        for (int i = lane; i < m; i += 32) x[i] = fma(-dt, rp[i], x[i]);
+        __syncwarp();
+      }
+    double nn = 0.0;
+    for (int i = lane; i < m; i += 32) nn = fma(x[i], x[i], nn);
+    nn = sqrt(warp_sum(nn));
+    const double sc = nn > 0.0 ? 1.0 / nn : 0.0;
+    for (int i = lane; i < m; i += 32) x[i] *= sc;
+    __syncwarp();
+    if (it == 3) break;
+    if (lane == 0) {  // x <- (T - lam I)^{-1} x
+      for (int i = 0; i < m - 1; ++i) {
+        if (pv[i] == 0.0) {
+          x[i + 1] -= dl[i] * x[i];
+        } else {
+          const double tmp = x[i];
+          x[i] = x[i + 1];
+          x[i + 1] = tmp - dl[i] * x[i];
+        }
+      }
+      x[m - 1] /= dd[m - 1];
+      if (m > 1) x[m - 2] = (x[m - 2] - du[m - 2] * x[m - 1]) / dd[m - 2];
+      for (int i = m - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / dd[i];
+      double mx = 0.0;  // keep the iterate finite
+      for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(x[i]));
+      if (mx > 0.0 && isfinite(mx)) {
+        const double r = 1.0 / mx;
+        for (int i = 0; i < m; ++i) x[i] *= r;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---- 2. eigenpairs of T, one CTA per matrix ---------------------------------------------------
 __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
   constexpr int THREADS = LG_EIG_THREADS;
@@ -578,16 +677,20 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
   int* blk_e = blk_s + np;
   int* cl_s = blk_e + np;
   int* twist = cl_s + np;
-  int* cnts = twist + np;        // P * np
+  int* cnts = twist + np;        // P * np (P <= 3)
+  double* fixb = (double*)(cnts + 3 * np + (np & 1));  // 6 np: inverse-iteration scratch, one user at a time
   __shared__ double s_red[40];
   __shared__ double s_tnorm;
-  __shared__ int s_fallback;
+  __shared__ int s_fallback, s_fixlock;
   double* S = a.Z + (size_t)b * n * n;
   double* Dm = a.Dm + (size_t)b * n * n;
   const size_t lds = n;
   int st_in = a.status ? a.status[b] : 0;
   st_in &= ~(MOP_ST_EIG_FALLBACK | MOP_ST_EIG_NOCONV);
-  if (tid == 0) s_fallback = 0;
+  if (tid == 0) {
+    s_fallback = 0;
+    s_fixlock = 0;
+  }
   long long tq = clock64();
   int tslot = 0;
 #define LG_EMARK()                                                                    \
@@ -828,7 +931,27 @@ __global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
           nn = sqrt(warp_sum(nn));
           if (rep == 0) nfirst = nn;
           if (!(nn > 1e-2)) {
-            if (lane == 0) s_fallback = 1;
+            // the vector lies (numerically) in the span of its cluster: rebuild it by inverse iteration
+            if (lane == 0)
+              while (atomicCAS(&s_fixlock, 0, 1) != 0) {
+              }
+            __syncwarp();
+            __threadfence_block();
+            lg_inverse_iteration(d, e, s, t, lam[c], R, lds, c - c0, fixb, np, lane, (unsigned)(b * 7919 + c));
+            double chk = 0.0;
+            for (int k = s + lane; k < t; k += 32) {
+              const double xv = fixb[k - s];
+              rc[k] = xv;
+              chk = fma(xv, xv, chk);
+            }
+            chk = warp_sum(chk);
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) {
+              if (!(chk > 0.5) || !isfinite(chk)) s_fallback = 1;  // not even inverse iteration produced a vector
+              atomicExch(&s_fixlock, 0);
+            }
+            break;  // orthonormal against the cluster by construction
           }
           const double sc = nn > 0.0 ? 1.0 / nn : 0.0;
           for (int k = s + lane; k < t; k += 32) rc[k] *= sc;
@@ -1184,8 +1307,9 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
   }
   {
     const int P = (3 * n <= mop::LG_EIG_THREADS) ? 3 : ((2 * n <= mop::LG_EIG_THREADS) ? 2 : 1);
-    const size_t smem = sizeof(double) * (6 * (size_t)np + (mop::LG_EIG_THREADS / 32) * 64) +
-                        sizeof(int) * (4 + P) * (size_t)np;
+    (void)P;
+    const size_t smem = sizeof(double) * (12 * (size_t)np + (mop::LG_EIG_THREADS / 32) * 64 + 2) +
+                        sizeof(int) * 7 * (size_t)np;
     MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mop::k_lg_trieig<<<B, mop::LG_EIG_THREADS, smem, stream>>>(a);
     MOP_CHECK_CUDA(cudaGetLastError());
