@@ -264,36 +264,53 @@ def run_b200(args, rank, world, local_rank):
     value = world * B * K / (ms * 1e-3)
 
     # ---- e2e: host buffers -> C ABI -> host buffers, copies inside the timed region ----
-    nchunk = int(os.environ.get("MOP_BENCH_E2E_CHUNKS", "4"))
-    nstream = int(os.environ.get("MOP_BENCH_E2E_STREAMS", "4"))
-    cb = B // nchunk
+    # chunk sizes: whole waves of the packed tridiagonalisation (2 CTAs x 148 SMs = 296 structures), the
+    # short chunk first so that compute starts early (MOP_BENCH_E2E_SPLIT overrides, comma separated)
+    split_env = os.environ.get("MOP_BENCH_E2E_SPLIT", "")
+    if split_env:
+        sizes = [int(v) for v in split_env.split(",")]
+    else:
+        sizes = [B % 296] * (1 if B % 296 else 0) + [296] * (B // 296)
+    assert sum(sizes) == B and all(v > 0 for v in sizes)
+    bounds = np.concatenate([[0], np.cumsum(sizes)])
+    nchunk = len(sizes)
+    nstream = min(nchunk, int(os.environ.get("MOP_BENCH_E2E_STREAMS", "4")))
+    cb = max(sizes)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     hH, hx1, hg1, hx0, hg0 = pin(H0), pin(x1), pin(g1), pin(x0), pin(g0)
     hBe = pin(np.full(B, -1e-3)); hst = state1.cpu().pin_memory()
     h_move = torch.empty(B, n, dtype=f64).pin_memory()
     h_Hout = torch.empty(B, n, n, dtype=f64).pin_memory()
     h_stat = torch.empty(B, dtype=torch.int32).pin_memory()
-    streams = [torch.cuda.Stream(dev) for _ in range(nstream)]
+    # earlier chunks get the higher stream priority: their CTAs are scheduled first, so the chunks finish
+    # (and their results go back over PCIe) one after the other instead of all together at the end
+    prio = os.environ.get("MOP_BENCH_E2E_PRIO", "1") == "1"
+    streams = [torch.cuda.Stream(dev, priority=(-min(5, nstream - 1 - i) if prio else 0)) for i in range(nstream)]
     dbuf = [dict(H=torch.empty(cb, n, n, dtype=f64, device=dev), x1=torch.empty(cb, n, dtype=f64, device=dev),
                  g1=torch.empty(cb, n, dtype=f64, device=dev), x0=torch.empty(cb, n, dtype=f64, device=dev),
                  g0=torch.empty(cb, n, dtype=f64, device=dev), Be=torch.empty(cb, dtype=f64, device=dev),
-                 st=torch.empty(cb, ops.RSIRFO_STATE, dtype=f64, device=dev), out=None) for _ in range(nstream)]
+                 st=torch.empty(cb, ops.RSIRFO_STATE, dtype=f64, device=dev), outs={}) for _ in range(nstream)]
     h2d = (hH.numel() + hx1.numel() * 4 + hBe.numel() + hst.numel()) * 8
     d2h = (h_move.numel() + h_Hout.numel()) * 8 + h_stat.numel() * 4
 
     def e2e_step():
         for c in range(nchunk):
-            s = streams[c % nstream]; d = dbuf[c % nstream]; sl = slice(c * cb, (c + 1) * cb)
+            s = streams[c % nstream]; d = dbuf[c % nstream]
+            lo, hi = int(bounds[c]), int(bounds[c + 1]); m = hi - lo; sl = slice(lo, hi)
             with torch.cuda.stream(s):
-                d["H"].copy_(hH[sl], non_blocking=True); d["x1"].copy_(hx1[sl], non_blocking=True)
-                d["g1"].copy_(hg1[sl], non_blocking=True); d["x0"].copy_(hx0[sl], non_blocking=True)
-                d["g0"].copy_(hg0[sl], non_blocking=True); d["Be"].copy_(hBe[sl], non_blocking=True)
-                d["st"].copy_(hst[sl], non_blocking=True)
-                d["out"] = ops.rsirfo_step(d["H"], d["x1"], d["g1"], d["g1"], d["st"], method=method_id,
-                                           x_prev=d["x0"], g_prev=d["g0"], Be=d["Be"], out=d["out"])
-                h_move[sl].copy_(d["out"]["move"], non_blocking=True)
-                h_Hout[sl].copy_(d["H"], non_blocking=True)
-                h_stat[sl].copy_(d["out"]["status"], non_blocking=True)
+                dH, dx1, dg1, dx0, dg0 = d["H"][:m], d["x1"][:m], d["g1"][:m], d["x0"][:m], d["g0"][:m]
+                dBe, dst = d["Be"][:m], d["st"][:m]
+                # vectors first: they ride behind the previous chunk's Hessian copy instead of delaying this chunk
+                dx1.copy_(hx1[sl], non_blocking=True); dg1.copy_(hg1[sl], non_blocking=True)
+                dx0.copy_(hx0[sl], non_blocking=True); dg0.copy_(hg0[sl], non_blocking=True)
+                dBe.copy_(hBe[sl], non_blocking=True); dst.copy_(hst[sl], non_blocking=True)
+                dH.copy_(hH[sl], non_blocking=True)
+                o = ops.rsirfo_step(dH, dx1, dg1, dg1, dst, method=method_id, x_prev=dx0, g_prev=dg0, Be=dBe,
+                                    out=d["outs"].get(m))
+                d["outs"][m] = o
+                h_move[sl].copy_(o["move"], non_blocking=True)
+                h_Hout[sl].copy_(dH, non_blocking=True)
+                h_stat[sl].copy_(o["status"], non_blocking=True)
         for s in streams:
             s.synchronize()
 
@@ -407,14 +424,14 @@ def run_b200(args, rank, world, local_rank):
             "config": workload_config(B, {"eigh": "auto", "parity_vs_oracle": worst}),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": f"pinned host buffers incl. the Hessian batch both ways, {nchunk} chunks on {nstream} streams",
+                    "note": f"pinned host buffers incl. the Hessian batch both ways, chunks of {sizes} structures on {nstream} streams",
                     "matches_resident_path": e2e_ok, "max_rel_diff_vs_resident": e2e_diff},
             "e2e_hessian_resident": {"value": e2e_res_val, "unit": UNIT,
                                      "h2d_bytes_per_step": 2 * B * n * 8, "d2h_bytes_per_step": B * n * 8},
             "gpu_launches": 8 * K,   # update (3 kernels), projection, packed tridiagonalisation, spectrum + step, 2 fallback kernels
             "roofline": {"bound": "fp64",
-                         "kernel": "k_tridiag_packed<256> + k_eigh_tridiag<512> (prefactored): tridiagonalisation, spectrum "
-                                   "and RFO step in the eigenbasis, timed together (dominant pair of the step)",
+                         "kernel": "k_tridiag_packed<256> + k_spectrum_step: tridiagonalisation, then spectrum, eigenvectors "
+                                   "of T and the RFO step in the eigenbasis, timed together (dominant pair of the step)",
                          "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": eig_tflops / fp64_peak, "traffic": traffic,
                          "traffic_source": "profiles/r1_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write)",

@@ -23,6 +23,9 @@ int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guar
                                     const double* gp, const double* state, int state_stride, double* delta_out,
                                     int32_t* status, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t mop_jacobi_workspace_bytes(int B, int n);
+int mop_launch_eigh_jacobi_ext(int B, int n, const double* A, double* evals, double* evecs,
+                               int32_t* status, const int32_t* only_flagged, void* work,
+                               size_t work_bytes, double* awork_ext, cudaStream_t stream);
 int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double* evecs,
                            int32_t* status, const int32_t* only_flagged, void* work,
                            size_t work_bytes, cudaStream_t stream);
@@ -46,7 +49,7 @@ int mop_launch_rfo_step(int B, int n, int saddle_order, int neb_mode, double tmi
 int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
                             const double* Hp, const double* gp, const double* Bg, const double* Be,
                             double* state, double* move, double* evals_out, double* pred,
-                            int32_t* status, void* work, size_t work_bytes, cudaStream_t stream);
+                            int32_t* status, void* work, size_t work_bytes, double* zbuf, cudaStream_t stream);
 
 extern "C" size_t mop_rsirfo_spectral_workspace_bytes(int B, int n);
 extern "C" int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_mode, double trust_min,
@@ -189,9 +192,11 @@ extern "C" int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_
   // CTAs of unflagged structures exit immediately).
   int rc = mop_launch_rsirfo_fused(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,
                                    state, move_out, eigvals_out, pred_out, status, twork,
-                                   work_bytes - (nn + nv + jac), stream);
+                                   work_bytes - (nn + nv + jac), evecs /* free until the fallback runs */, stream);
   if (rc != MOP_OK) return rc;
-  rc = mop_launch_eigh_jacobi(B, n, Hp, evals, evecs, status, status, jwork, jac, stream);
+  // the working matrices of the flagged structures go to the (now dead) reflector / pivot slabs, not to
+  // shared memory: the launch is almost always empty and must not wait for whole SMs
+  rc = mop_launch_eigh_jacobi_ext(B, n, Hp, evals, evecs, status, status, jwork, jac, (double*)twork, stream);
   if (rc != MOP_OK) return rc;
   return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, gp, Bg,
                              Be, state, move_out, eigvals_out, pred_out, status, 1, stream);

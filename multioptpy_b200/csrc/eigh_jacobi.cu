@@ -174,9 +174,13 @@ size_t mop_jacobi_workspace_bytes(int B, int n) {
   return bytes;
 }
 
-int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double* evecs,
-                           int32_t* status, const int32_t* only_flagged, void* work,
-                           size_t work_bytes, cudaStream_t stream) {
+// awork_ext (optional, >= B * m * (m | 1) doubles with m = n rounded up to even): keep the working matrix
+// there instead of in shared memory.  The fallback launches that follow the fast eigensolvers pass it:
+// with 180 KB of shared memory per CTA the (almost always empty) launch could not share an SM with the
+// kernels of other streams and stalled its stream until whole SMs drained.
+int mop_launch_eigh_jacobi_ext(int B, int n, const double* A, double* evals, double* evecs,
+                               int32_t* status, const int32_t* only_flagged, void* work,
+                               size_t work_bytes, double* awork_ext, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   if (work_bytes < mop_jacobi_workspace_bytes(B, n) || !work) {
     mop_set_error("eigh (jacobi): workspace too small (%zu < %zu)", work_bytes,
@@ -184,15 +188,21 @@ int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double*
     return MOP_ERR_WORKSPACE;
   }
   const int m = (n + 1) & ~1, half = m >> 1, lda = m | 1;
-  const int use_smem = n <= mop_jacobi_smem_max_n();
+  const int use_smem = n <= mop_jacobi_smem_max_n() && !awork_ext;
   size_t smem = sizeof(double) * (40 + 2 * (size_t)half) + sizeof(int) * (2 * (size_t)half + m);
   if (use_smem) smem += sizeof(double) * (size_t)m * lda;
   double* Vwork = (double*)work;
-  double* Awork = use_smem ? nullptr : Vwork + (size_t)B * n * n;
+  double* Awork = use_smem ? nullptr : (awork_ext ? awork_ext : Vwork + (size_t)B * n * n);
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_eigh_jacobi,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mop::k_eigh_jacobi<<<B, mop::JAC_THREADS, smem, stream>>>(n, use_smem, A, Awork, Vwork, evals,
                                                            evecs, status, only_flagged);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
+}
+
+int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double* evecs,
+                           int32_t* status, const int32_t* only_flagged, void* work,
+                           size_t work_bytes, cudaStream_t stream) {
+  return mop_launch_eigh_jacobi_ext(B, n, A, evals, evecs, status, only_flagged, work, work_bytes, nullptr, stream);
 }

@@ -872,6 +872,19 @@ size_t mop_tridiag_workspace_bytes(int B, int n) {
 }
 int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
                               double* tau, double* gq, int* flag, cudaStream_t stream);
+int mop_spectrum_step_supported(int n);
+int mop_launch_spectrum_step(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
+                             const double* Vh, double* Z, double* Dm, const double* pd, const double* pe,
+                             const double* ptau, const double* pgq, const int* pflag, const double* Bg,
+                             const double* Be, double* state, double* move, double* evals_out, double* pred,
+                             int32_t* status, cudaStream_t stream);
+static int g_tri_spectrum = 1;
+// tuning: 1 (default) = k_spectrum_step (Z in global memory, 7 CTAs per SM) after the packed
+// tridiagonalisation, 0 = k_eigh_tridiag in prefactored mode (Z in shared memory, 1 CTA per SM)
+extern "C" int mop_debug_tri_spectrum(int on) {
+  g_tri_spectrum = on;
+  return MOP_OK;
+}
 static int g_tri_packed = 1;
 // tuning: 1 (default) = packed two-CTA-per-SM tridiagonalisation feeding the fused kernel, 0 = single kernel
 extern "C" int mop_debug_tri_packed(int on) {
@@ -926,7 +939,7 @@ int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double
 int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
                             const double* Hp, const double* gp, const double* Bg, const double* Be,
                             double* state, double* move, double* evals_out, double* pred,
-                            int32_t* status, void* work, size_t work_bytes, cudaStream_t stream) {
+                            int32_t* status, void* work, size_t work_bytes, double* zbuf, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   if (!mop_tridiag_supported(n)) {
     mop_set_error("fused RS-I-RFO kernel: n = %d not supported (max %d)", n, mop::TRI_MAX_N);
@@ -966,6 +979,11 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
     int* pflag = (int*)(pf + 4 * (size_t)B * n);
     int rc = mop_launch_tridiag_packed(B, n, Hp, gp, a.Vh, pd, pe, pt, pg, pflag, stream);
     if (rc != MOP_OK) return rc;
+    // spectrum + step with Z in global memory, seven structures per SM (spectrum_step.cu); zbuf is a
+    // [B][n][n] slab the caller does not need until this launch has finished
+    if (zbuf && g_tri_spectrum && mop_spectrum_step_supported(n))
+      return mop_launch_spectrum_step(B, n, saddle_order, neb_mode, tmin, tmax, a.Vh, zbuf, a.Dm, pd, pe, pt, pg,
+                                      pflag, Bg, Be, state, move, evals_out, pred, status, stream);
     a.pf_d = pd;
     a.pf_e = pe;
     a.pf_tau = pt;

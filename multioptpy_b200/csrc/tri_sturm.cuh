@@ -53,4 +53,50 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
   return cnt;
 }
 
+// The same count, also returning the last term of the sequence, p_n(x) = det(T - x I) up to the
+// positive scale 2^pexp, as (pval, pexp): the characteristic polynomial value that drives the
+// superlinear root-finder of k_spectrum_step.  sign(pval) == (-1)^count by construction.
+__device__ __forceinline__ int sturm_eval(const double* __restrict__ d, const double* __restrict__ e2,
+                                          int s, int t, double x, double* pval, int* pexp) {
+  double pm1 = 1.0;
+  double p = d[s] - x;
+  int cnt = (unsigned)__double2hiint(p) >> 31;
+  int esum = 0;
+  int k = s + 1;
+  for (; k + 3 < t; k += 4) {
+    const double a0 = d[k] - x, a1 = d[k + 1] - x, a2 = d[k + 2] - x, a3 = d[k + 3] - x;
+    const double b0 = e2[k - 1], b1 = e2[k], b2 = e2[k + 1], b3 = e2[k + 2];
+    const double p0 = fma(a0, p, -(b0 * pm1));
+    const double p1 = fma(a1, p0, -(b1 * p));
+    const double p2 = fma(a2, p1, -(b2 * p0));
+    const double p3 = fma(a3, p2, -(b3 * p1));
+    const int h = __double2hiint(p), h0 = __double2hiint(p0), h1 = __double2hiint(p1),
+              h2 = __double2hiint(p2), h3 = __double2hiint(p3);
+    cnt += ((unsigned)(h ^ h0) >> 31) + ((unsigned)(h0 ^ h1) >> 31) + ((unsigned)(h1 ^ h2) >> 31) +
+           ((unsigned)(h2 ^ h3) >> 31);
+    pm1 = p2;
+    p = p3;
+    const unsigned ex = ((unsigned)h3 >> 20) & 0x7ffu;
+    if (ex - 523u > 1000u) {
+      const double a = fmax(fabs(p), fabs(pm1));
+      if (a > 0.0 && a < INFINITY) {
+        const int ea = (__double2hiint(a) >> 20) & 0x7ff;
+        const double sc = __hiloint2double((2046 - ea) << 20, 0);   // 2^(1023 - ea)
+        p *= sc;
+        pm1 *= sc;
+        esum += ea - 1023;
+      }
+    }
+  }
+  for (; k < t; ++k) {
+    const double pn = fma(d[k] - x, p, -(e2[k - 1] * pm1));
+    cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31;
+    pm1 = p;
+    p = pn;
+  }
+  *pval = p;
+  *pexp = esum;
+  return cnt;
+}
+
 }  // namespace mop

@@ -50,3 +50,18 @@ for i, nm in enumerate(names):
 print("  total median", np.median(d[:, :8].sum(1)))
 print("phase-1 segments warp0   [top..A, A..B(symv), B..C(reduce), C..E-arrive(update), E wait]:", [int(np.median(d[:, 8 + i])) for i in range(5)])
 print("phase-1 segments warp15  [top..A, A..B(symv), B..C(reduce), C..E-arrive(update), E wait]:", [int(np.median(d[:, 13 + i])) for i in range(3)])
+
+# k_spectrum_step phases (default path)
+dbg2 = torch.zeros(B, 16, dtype=torch.int64, device=dev)
+lib.mop_debug_spectrum_timing(dbg2.data_ptr())
+Hx = H.clone(); stx = st.clone()
+out = ops.rsirfo_step(Hx, x1d, g1d, g1d, stx, method=m, x_prev=x0d, g_prev=g0d, Be=zero - 1e-3)
+torch.cuda.synchronize()
+lib.mop_debug_spectrum_timing(None)
+d2 = dbg2.cpu().numpy().astype(float)
+names2 = ["load/scale/split", "eigenvalues", "twisted", "cluster CGS2", "gamma + rfo core", "Z c", "Q y"]
+print("k_spectrum_step phase cycles (median / max over CTAs):")
+for i, nm in enumerate(names2):
+    print(f"  {nm:20s} {np.median(d2[:, i]):12.0f}  max {d2[:, i].max():12.0f}")
+print("  total median", np.median(d2[:, :7].sum(1)))
+print("status:", bits(out["status"].cpu().numpy()))

@@ -1,0 +1,13 @@
+#!/bin/bash
+# e2e chunk-size sweep of bench.py (diagnostics)
+run() {
+  MOP_BENCH_E2E_SPLIT=$1 MOP_BENCH_E2E_STREAMS=$2 MOP_BENCH_E2E_PRIO=$3 python bench.py --steps 5 --warmup 3 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('split $1 streams $2 prio $3: value %.4g e2e %.4g ok %s resident %.4g' % (d['value'], d['e2e']['value'], d['e2e']['matches_resident_path'], d['e2e_hessian_resident']['value']))"
+}
+run 256,256,256,256 4 0
+run 256,256,256,256 4 1
+run 256,256,256,128,128 5 1
+run 136,296,296,296 4 1
+run 296,296,296,136 4 1
+run 128,256,256,256,128 5 1
