@@ -188,6 +188,8 @@ def run_b200(args, rank, world, local_rank):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     lib = _lib.load()
+    if os.environ.get("MOP_STREAM_CHUNK"):      # tuning aid: update + projection chunk size
+        lib.mop_debug_stream_chunk(int(os.environ["MOP_STREAM_CHUNK"]))
     B, n = BATCH, 3 * NATOMS
     K, W = args.steps, args.warmup
     f64 = torch.float64

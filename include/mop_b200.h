@@ -376,6 +376,7 @@ int mop_debug_latency(double* out, void* stream);
 int mop_debug_large_cluster(int cluster_ctas); /* tuning: CTAs per matrix of MOP_EIGH_LARGE (1, 2, 4, 8; 0 = auto) */
 int mop_debug_eigh_small_pipeline(int on); /* tuning: mop_eigh at n <= 158 through packed tridiagonalisation + eigh_large stages (default 1) */
 int mop_debug_tri_packed(int on);       /* tuning: packed two-CTA-per-SM tridiagonalisation in the fused RS-I-RFO path (default 1) */
+int mop_debug_stream_chunk(int structures); /* tuning: structures per update + projection chunk of mop_rsirfo_step (default 0 = whole batch) */
 int mop_debug_tri_spectrum(int on);     /* tuning: k_spectrum_step (Z in global memory, 7 structures per SM) after the packed kernel (default 1) */
 int mop_debug_spectrum_timing(void* buf); /* diagnostics: [B][16] int64 phase cycles of k_spectrum_step */
 int mop_debug_packed_timing(void* buf);   /* diagnostics: [B][16] int64 phase cycles of the packed kernel */

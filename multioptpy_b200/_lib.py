@@ -79,6 +79,7 @@ SIGNATURES = {
     "mop_debug_large_pair": (_i, [_i]),
     "mop_debug_tri_packed": (_i, [_i]),
     "mop_debug_tri_spectrum": (_i, [_i]),
+    "mop_debug_stream_chunk": (_i, [_i]),
     "mop_debug_spectrum_timing": (_i, [_p]),
     "mop_debug_eigh_small_pipeline": (_i, [_i]),
     "mop_debug_packed_threads": (_i, [_i]),

@@ -72,6 +72,12 @@ extern "C" const char* mop_last_error(void) { return g_err; }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static int g_stream_chunk = 0;
+// tuning: structures per update + projection chunk of mop_rsirfo_step (0, the default = the whole batch at once)
+extern "C" int mop_debug_stream_chunk(int structures) {
+  g_stream_chunk = structures;
+  return MOP_OK;
+}
 static int g_eigh_small_pipeline = 1;
 extern "C" int mop_debug_eigh_small_pipeline(int on) {
   g_eigh_small_pipeline = on;
@@ -248,19 +254,38 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   const size_t ebytes = rest_bytes - (nn + 3 * nv);
 
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
-  int rc;
-  // (1) Hessian update with RAW gradients (rsirfo.py:308-309,1316-1372)
-  if (x_prev && method != MOP_UPD_NONE) {
-    // scratch: the projected-Hessian buffer is not live yet
-    rc = mop_launch_hessian_update_split(B, n, method, 1, 1, H, nullptr, nullptr, x, x_prev, g, g_prev, state,
-                                         MOP_RSIRFO_STATE, nullptr, status, Hp, nn, stream);
+  int rc = MOP_OK;
+  // (1) Hessian update with RAW gradients (rsirfo.py:308-309,1316-1372) and (2) TR/ROT projection of gradient
+  // and effective Hessian (rsirfo.py:337,349-358).  Small batches take the multi-CTA projection (it fills the
+  // GPU), large ones one CTA per structure (as fast, fewer launches).  mop_debug_stream_chunk(c) runs the pair
+  // chunk by chunk so that a chunk stays in L2 between its passes - measured SLOWER on B200 at n = 150 (the
+  // short launches are latency bound: 4.97 ms per step at c = 256 against 4.44 ms), hence off by default.
+  const size_t n2 = (size_t)n * n;
+  const bool chunked = g_stream_chunk > 0 && g_stream_chunk < B;
+  const bool split_ok = nn >= mop_project_scratch_bytes(B, n) && nn >= mop_hessian_update_scratch_bytes(B, n) &&
+                        (chunked || B <= 2 * 148);
+  const int CH = (split_ok && chunked) ? g_stream_chunk : B;
+  for (int b0 = 0; b0 < B; b0 += CH) {
+    const int bc = B - b0 < CH ? B - b0 : CH;
+    double* Hc = H + b0 * n2;
+    const double* Hbc = Hbias ? Hbias + b0 * n2 : nullptr;
+    const size_t chunk_bytes = sizeof(double) * bc * n2;
+    if (x_prev && method != MOP_UPD_NONE) {
+      // scratch: the projected-Hessian buffer of this chunk is not live yet
+      rc = mop_launch_hessian_update_split(bc, n, method, 1, 1, Hc, nullptr, nullptr, x + (size_t)b0 * n,
+                                           x_prev + (size_t)b0 * n, g + (size_t)b0 * n, g_prev + (size_t)b0 * n,
+                                           state + (size_t)b0 * MOP_RSIRFO_STATE, MOP_RSIRFO_STATE, nullptr,
+                                           status + b0, split_ok ? (void*)(Hp + b0 * n2) : (void*)Hp,
+                                           split_ok ? chunk_bytes : nn, stream);
+      if (rc != MOP_OK) return rc;
+    }
+    rc = split_ok ? mop_launch_project_trrot_split(bc, n, Hc, Hbc, x + (size_t)b0 * n, Bg + (size_t)b0 * n,
+                                                   Hp + b0 * n2, gp + (size_t)b0 * n, status + b0, evecs + b0 * n2,
+                                                   chunk_bytes, stream)
+                  : mop_launch_project_trrot(bc, n, Hc, Hbc, x + (size_t)b0 * n, Bg + (size_t)b0 * n, Hp + b0 * n2,
+                                             gp + (size_t)b0 * n, status + b0, stream);
     if (rc != MOP_OK) return rc;
   }
-  // (2) TR/ROT projection of gradient and effective Hessian (rsirfo.py:337,349-358)
-  // small batches: the multi-CTA projection fills the GPU; large ones: one CTA per structure is as fast
-  rc = B <= 2 * 148 ? mop_launch_project_trrot_split(B, n, H, Hbias, x, Bg, Hp, gp, status, evecs, nn, stream)
-                    : mop_launch_project_trrot(B, n, H, Hbias, x, Bg, Hp, gp, status, stream);
-  if (rc != MOP_OK) return rc;
   if (pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG)
     return mop_rsirfo_spectral_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Hp, gp, Bg, Be,
                                     state, move_out, eigvals_out, pred_out, status, rest, rest_bytes,

@@ -226,15 +226,15 @@ k_project_trrot(int n, const double* __restrict__ Hall, const double* __restrict
 __host__ __device__ inline size_t prj_scratch_doubles(int n) { return 12 * (size_t)((n + 3) & ~3) + 8; }
 
 __global__ void __launch_bounds__(PRJ_THREADS)
-k_prj_basis(int n, const double* __restrict__ x_all, const double* __restrict__ g_all, double* __restrict__ gp_all,
-            double* __restrict__ scratch, int32_t* __restrict__ status) {
+k_prj_basis(int n, size_t sstride, const double* __restrict__ x_all, const double* __restrict__ g_all,
+            double* __restrict__ gp_all, double* __restrict__ scratch, int32_t* __restrict__ status) {
   extern __shared__ double sm[];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int np = (n + 3) & ~3;
   double* T = sm;
   double* raw = T + 6 * np;
   double* red = raw + 6 * np;
-  double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  double* scr = scratch + (size_t)b * sstride;
   const int k = build_trrot_basis(n, x_all + (size_t)b * n, T, np, raw, red);
   if (tid == 0) {
     scr[12 * np] = (double)k;
@@ -262,14 +262,15 @@ k_prj_basis(int n, const double* __restrict__ x_all, const double* __restrict__ 
 }
 
 __global__ void __launch_bounds__(PRJ_THREADS)
-k_prj_w(int n, const double* __restrict__ Hall, const double* __restrict__ Hb_all, double* __restrict__ scratch) {
+k_prj_w(int n, size_t sstride, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
+        double* __restrict__ scratch) {
   extern __shared__ double sm[];  // T [6][np] | colacc [8][6][32]
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   constexpr int nw = PRJ_THREADS >> 5;
   const int np = (n + 3) & ~3;
   double* T = sm;
   double* cacc = T + 6 * np;
-  double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  double* scr = scratch + (size_t)b * sstride;
   double* W = scr + 6 * np;
   for (int i = tid; i < 6 * np; i += PRJ_THREADS) T[i] = scr[i];
   __syncthreads();
@@ -327,15 +328,104 @@ k_prj_w(int n, const double* __restrict__ Hall, const double* __restrict__ Hb_al
   }
 }
 
+// One-read W pass: CTA (slab, b) streams the 32 rows of its slab ONCE.  Element a = M0[r][j] adds a T[j] to
+// the row sums of r (complete inside the CTA) and a T[r] to the column sums of j (partial: this slab only);
+// the partials go to scratch [slab][6][np] and k_prj_y adds them in slab order (deterministic).
+// shared: T [6][np] | cpart [8 warps][6][np]
 __global__ void __launch_bounds__(PRJ_THREADS)
-k_prj_y(int n, double* __restrict__ scratch) {
+k_prj_w1(int n, size_t sstride, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
+         double* __restrict__ scratch) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int nw = PRJ_THREADS >> 5;
+  const int np = (n + 3) & ~3;
+  double* T = sm;
+  double* cpart = T + 6 * np;
+  double* scr = scratch + (size_t)b * sstride;
+  double* W = scr + 6 * np;
+  double* Wc = scr + 12 * np + 8 + (size_t)blockIdx.x * 6 * np;
+  for (int i = tid; i < 6 * np; i += PRJ_THREADS) T[i] = scr[i];
+  __syncthreads();
+  const double* H = Hall + (size_t)b * n * n;
+  const double* Hb = Hb_all ? Hb_all + (size_t)b * n * n : nullptr;
+  const int i0 = blockIdx.x * 32, r0 = i0 + 4 * w;
+  double tr[4][6], ra[4][6];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+      tr[q][v] = (r0 + q < n) ? T[v * np + r0 + q] : 0.0;
+      ra[q][v] = 0.0;
+    }
+  for (int j0 = 0; j0 < n; j0 += 64) {  // two column chunks per pass: eight loads in flight per lane
+    double a[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0 + 32 * h + lane;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q;
+        double x = 0.0;
+        if (r < n && j < n) {
+          x = H[(size_t)r * n + j];
+          if (Hb) x += Hb[(size_t)r * n + j];
+        }
+        a[h][q] = x;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0 + 32 * h + lane;
+      if (j < n) {
+#pragma unroll
+        for (int v = 0; v < 6; ++v) {
+          const double t = T[v * np + j];
+          double c = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ra[q][v] = fma(a[h][q], t, ra[q][v]);
+            c = fma(a[h][q], tr[q][v], c);
+          }
+          cpart[(size_t)(w * 6 + v) * np + j] = c;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+      const double rsum = warp_sum(ra[q][v]);
+      if (lane == 0 && r0 + q < n) W[v * np + r0 + q] = rsum;
+    }
+  __syncthreads();
+  for (int e = tid; e < 6 * np; e += PRJ_THREADS) {
+    const int v = e / np, j = e - v * np;
+    double csum = 0.0;
+    if (j < n)
+      for (int ww = 0; ww < nw; ++ww) csum += cpart[(size_t)(ww * 6 + v) * np + j];
+    Wc[e] = csum;
+  }
+}
+
+__global__ void __launch_bounds__(PRJ_THREADS)
+k_prj_y(int n, size_t sstride, int nslab, double* __restrict__ scratch) {
   __shared__ double M[36];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = PRJ_THREADS >> 5;
   const int np = (n + 3) & ~3;
-  double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  double* scr = scratch + (size_t)b * sstride;
   const double* T = scr;
   double* W = scr + 6 * np;
   const int k = (int)scr[12 * np];
+  if (nslab > 0) {  // one-read W pass: W = 1/2 (row sums + column partials of every row slab, fixed order)
+    const double* Wc = scr + 12 * np + 8;
+    for (int e = tid; e < 6 * np; e += PRJ_THREADS) {
+      double csum = 0.0;
+      for (int sl = 0; sl < nslab; ++sl) csum += Wc[(size_t)sl * 6 * np + e];
+      W[e] = 0.5 * W[e] + 0.5 * csum;
+    }
+    __syncthreads();
+  }
   for (int e = w; e < k * k; e += nw) {
     const int a = e / k, c = e - a * k;
     double p = 0.0;
@@ -356,13 +446,13 @@ k_prj_y(int n, double* __restrict__ scratch) {
 }
 
 __global__ void __launch_bounds__(PRJ_THREADS)
-k_prj_out(int n, int TT, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
+k_prj_out(int n, size_t sstride, int TT, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
           const double* __restrict__ scratch, double* __restrict__ Hp_all) {
   __shared__ double tA[PT * (PT + 1)], tB[PT * (PT + 1)];
   __shared__ double ti[12][PT], tj[12][PT];  // rows 0-5: T, 6-11: Y, for the I and J index blocks
   const int b = blockIdx.y, tid = threadIdx.x, I = blockIdx.x;
   const int np = (n + 3) & ~3;
-  const double* scr = scratch + (size_t)b * prj_scratch_doubles(n);
+  const double* scr = scratch + (size_t)b * sstride;
   const int k = (int)scr[12 * np];
   const double* H = Hall + (size_t)b * n * n;
   const double* Hb = Hb_all ? Hb_all + (size_t)b * n * n : nullptr;
@@ -467,7 +557,17 @@ extern "C" int mop_project_trrot(int B, int n, const double* H, const double* Hb
                                   (cudaStream_t)stream);
 }
 
-size_t mop_project_scratch_bytes(int B, int n) { return sizeof(double) * (size_t)B * mop::prj_scratch_doubles(n); }
+// scratch layouts: two-read W pass 12 np + 8 doubles per structure; one-read W pass adds [nslab][6][np]
+static size_t prj_stride(int n, int one_read) {
+  const size_t np = (size_t)((n + 3) & ~3);
+  return mop::prj_scratch_doubles(n) + (one_read ? (size_t)((n + 31) / 32) * 6 * np : 0);
+}
+static size_t prj_w1_smem(int n) { return sizeof(double) * (size_t)((n + 3) & ~3) * (6 + 8 * 6); }
+size_t mop_project_scratch_bytes(int B, int n) { return sizeof(double) * (size_t)B * prj_stride(n, 0); }
+// preferred scratch: enough for the one-read W pass (the launcher falls back to two reads with less)
+size_t mop_project_scratch_bytes_pref(int B, int n) {
+  return sizeof(double) * (size_t)B * prj_stride(n, prj_w1_smem(n) <= 100 * 1024);
+}
 
 // Same contract as mop_launch_project_trrot, four multi-CTA kernels, `scratch` from the caller.
 int mop_launch_project_trrot_split(int B, int n, const double* H, const double* Hbias, const double* x,
@@ -484,24 +584,31 @@ int mop_launch_project_trrot_split(int B, int n, const double* H, const double* 
     mop_set_error("n = %d too large for the projection kernel", n);
     return MOP_ERR_UNSUPPORTED;
   }
+  const int nslab = (n + 31) / 32;
+  const int one_read = prj_w1_smem(n) <= 100 * 1024 && scratch_bytes >= sizeof(double) * (size_t)B * prj_stride(n, 1);
+  const size_t sstride = prj_stride(n, one_read);
   double* scr = (double*)scratch;
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_prj_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-  mop::k_prj_basis<<<B, mop::PRJ_THREADS, smem0, stream>>>(n, x, g, gp_out, scr, status);
+  mop::k_prj_basis<<<B, mop::PRJ_THREADS, smem0, stream>>>(n, sstride, x, g, gp_out, scr, status);
   MOP_CHECK_CUDA(cudaGetLastError());
   if (!Hp_out) return MOP_OK;
-  {
+  dim3 grid(nslab, B);
+  if (one_read) {
+    const size_t smem = prj_w1_smem(n);
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_prj_w1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mop::k_prj_w1<<<grid, mop::PRJ_THREADS, smem, stream>>>(n, sstride, H, Hbias, scr);
+  } else {
     const size_t smem = sizeof(double) * (6 * (size_t)np + 8 * 6 * 32);
     MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_prj_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((n + 31) / 32, B);
-    mop::k_prj_w<<<grid, mop::PRJ_THREADS, smem, stream>>>(n, H, Hbias, scr);
-    MOP_CHECK_CUDA(cudaGetLastError());
+    mop::k_prj_w<<<grid, mop::PRJ_THREADS, smem, stream>>>(n, sstride, H, Hbias, scr);
   }
-  mop::k_prj_y<<<B, mop::PRJ_THREADS, 0, stream>>>(n, scr);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  mop::k_prj_y<<<B, mop::PRJ_THREADS, 0, stream>>>(n, sstride, one_read ? nslab : 0, scr);
   MOP_CHECK_CUDA(cudaGetLastError());
   {
     const int TT = (n + mop::PT - 1) / mop::PT;
-    dim3 grid(TT, B);
-    mop::k_prj_out<<<grid, mop::PRJ_THREADS, 0, stream>>>(n, TT, H, Hbias, scr, Hp_out);
+    dim3 grid2(TT, B);
+    mop::k_prj_out<<<grid2, mop::PRJ_THREADS, 0, stream>>>(n, sstride, TT, H, Hbias, scr, Hp_out);
     MOP_CHECK_CUDA(cudaGetLastError());
   }
   return MOP_OK;

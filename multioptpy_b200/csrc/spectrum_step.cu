@@ -53,12 +53,18 @@ struct SpArgs {
   long long* dbg;     // optional [B][16] phase clocks (diagnostics)
 };
 
-__host__ __device__ inline size_t sp_x_doubles(int n) {
+// Shared-memory plan (doubles; np = n rounded up to 4):
+//   tau | lam | gq | zsc | e2     5 np   live to the end (e2 is recycled as the coefficients of y = Z c)
+//   Y:  d | e | de (2 np) | X     T itself, dead once the eigenvectors exist; X = grid-phase scratch (4 np)
+// and from the cluster phase on the whole of Y is recycled: CGS2 pair buffers + dots, then lam_s | gam_s |
+// RfoArrays, then the reflector ring.  Seven CTAs stay under the 164 KB carve-out (92 KB of L1 left for the
+// local-memory spills and the strided cluster accesses).
+__host__ __device__ inline size_t sp_y_doubles(int n) {
   const size_t np = (size_t)((n + 3) & ~3);
-  size_t x = 2 * np + rfo_core_smem_bytes(n) / sizeof(double) + 8;  // lam_s, gam_s, RfoArrays
-  if (x < 3 * np) x = 3 * np;                                        // grid values, counts, exponents
-  if (x < (size_t)SP_NW * (2 * np + 64)) x = (size_t)SP_NW * (2 * np + 64);  // CGS2 pair buffers + dots
-  return (x + 1) & ~(size_t)1;
+  size_t y = 2 * np + rfo_core_smem_bytes(n) / sizeof(double) + 8;           // lam_s, gam_s, RfoArrays; ring 12 np
+  if (y < 8 * np) y = 8 * np;                                                 // d, e, de + grid-phase scratch
+  if (y < (size_t)SP_NW * (2 * np + 64)) y = (size_t)SP_NW * (2 * np + 64);   // CGS2 pair buffers + dots
+  return (y + 1) & ~(size_t)1;
 }
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
@@ -72,22 +78,24 @@ __device__ __forceinline__ double* gq_dots(double* X, int np, int wid) { return 
 __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
   constexpr int THREADS = SP_THREADS;
   constexpr int NW = SP_NW;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int np = (n + 3) & ~3;
-  double* d = sm;              // np
-  double* e = d + np;          // np   e[k] couples k, k+1
-  double* e2 = e + np;         // np   later: c_i * zsc_i (column coefficients of y = Z c)
-  double* tau = e2 + np;       // np
+  double* tau = sm;            // np
   double* lam = tau + np;      // np   eigenvalue of thread-row i (scaled)
   double* gq = lam + np;       // np   Q^T gp, later y
   double* zsc = gq + np;       // np   normalisation factor of column i of Z
-  double* X = zsc + np;        // phase scratch (aliased)
-  int* blk_s = (int*)(X + sp_x_doubles(n));
-  int* blk_e = blk_s + np;
-  int* cl_s = blk_e + np;
-  int* rank = cl_s + np;
-  int* inv = rank + np;
+  double* e2 = zsc + np;       // np   later: c_i * zsc_i (column coefficients of y = Z c)
+  double* Y = e2 + np;         // recycled region (see sp_y_doubles)
+  double* d = Y;               // np
+  double* e = d + np;          // np   e[k] couples k, k+1
+  double2* de = (double2*)(e + np);  // np pairs (d_k, e_{k-1}^2): the Sturm table (16-byte aligned: np % 4 == 0)
+  double* X = e + 3 * np;      // grid-phase scratch, 4 np
+  unsigned char* blk_s = (unsigned char*)(Y + sp_y_doubles(n));  // index tables: n <= 160 fits a byte
+  unsigned char* blk_e = blk_s + np;
+  unsigned char* cl_s = blk_e + np;
+  unsigned char* rank = cl_s + np;
+  unsigned char* inv = rank + np;
   __shared__ double s_red[40];
   __shared__ double s_tnorm;
   __shared__ int s_fallback;
@@ -150,6 +158,7 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
       e2[tid] = enew * enew;
     }
     __syncthreads();
+    if (tid < n) de[tid] = make_double2(d[tid], tid > 0 ? e2[tid - 1] : 0.0);
     // block of row i: [blk_s, blk_e); every thread scans outwards from its own row
     if (tid < n) {
       int s = tid, t = tid;
@@ -171,22 +180,32 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
     int* gexp = gcnt + np;                // binary exponents of gpv
     double gl = INFINITY, gu = -INFINITY;
     int bs = 0, bt = 0;
+    // Gershgorin interval of every block: the block's first row scans it once, the others read the result
+    double* gbl = X;            // [np] lower bound, stored at the block start
+    double* gbu = X + 3 * np;   // [np] upper bound (X holds at least 4 np doubles)
+    if (tid < n && blk_s[tid] == tid) {
+      const int s0 = tid, t0 = blk_e[tid];
+      double a = INFINITY, c = -INFINITY;
+      for (int r = s0; r < t0; ++r) {
+        const double rad = (r > s0 ? fabs(e[r - 1]) : 0.0) + (r < t0 - 1 ? fabs(e[r]) : 0.0);
+        a = fmin(a, d[r] - rad);
+        c = fmax(c, d[r] + rad);
+      }
+      const double pad = 4.0 * TRI_EPS * n * fmax(fabs(a), fabs(c)) + 1e-300;
+      gbl[tid] = a - pad;
+      gbu[tid] = c + pad;
+    }
+    __syncthreads();
     if (tid < n) {
       bs = blk_s[tid];
       bt = blk_e[tid];
-      for (int r = bs; r < bt; ++r) {
-        const double rad = (r > bs ? fabs(e[r - 1]) : 0.0) + (r < bt - 1 ? fabs(e[r]) : 0.0);
-        gl = fmin(gl, d[r] - rad);
-        gu = fmax(gu, d[r] + rad);
-      }
-      const double pad = 4.0 * TRI_EPS * n * fmax(fabs(gl), fabs(gu)) + 1e-300;
-      gl -= pad;
-      gu += pad;
+      gl = gbl[bs];
+      gu = gbu[bs];
       const int m = bt - bs, j = tid - bs;
       const double x = gl + (gu - gl) * ((double)(j + 1) / (double)(m + 1));
       double pv;
       int pe;
-      gcnt[tid] = sturm_eval(d, e2, bs, bt, x, &pv, &pe);
+      gcnt[tid] = sturm_eval(de, bs, bt, x, &pv, &pe);
       gpv[tid] = pv;
       gexp[tid] = pe;
     }
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
         if (!(x > l && x < h)) break;
         double pv;
         int pe;
-        const int c = sturm_eval(d, e2, bs, bt, x, &pv, &pe);
+        const int c = sturm_eval(de, bs, bt, x, &pv, &pe);
         if (c >= want) {
           h = x;
           ph = pv;
@@ -370,7 +389,7 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
       const int cs = cend - c0;
       if (cs < 2) continue;
       const int s = blk_s[c0], t = blk_e[c0], m = t - s;
-      double* buf = (cs == 2) ? X + (size_t)wid * 2 * np : Dm + (size_t)c0 * n;  // buf[col * m + row]
+      double* buf = (cs == 2) ? Y + (size_t)wid * 2 * np : Dm + (size_t)c0 * n;  // buf[col * m + row]
       for (int i0 = 0; i0 < cs * m; i0 += 32 * 8) {
         double zz[8];
 #pragma unroll
@@ -401,13 +420,13 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
             double dt = 0.0;
             for (int k = lane; k < m; k += 32) dt = fma(zp[k], zc_[k], dt);
             dt = warp_sum(dt);
-            if (lane == 0) gq_dots(X, np, wid)[p & 63] = dt;
+            if (lane == 0) gq_dots(Y, np, wid)[p & 63] = dt;
             if ((p & 63) == 63 || p == c - 1) {
               __syncwarp();
               const int p0 = p & ~63;
               for (int k = lane; k < m; k += 32) {
                 double zv = zc_[k];
-                for (int pp = p0; pp <= p; ++pp) zv = fma(-gq_dots(X, np, wid)[pp - p0], buf[(size_t)pp * m + k], zv);
+                for (int pp = p0; pp <= p; ++pp) zv = fma(-gq_dots(Y, np, wid)[pp - p0], buf[(size_t)pp * m + k], zv);
                 zc_[k] = zv;
               }
               __syncwarp();
@@ -464,9 +483,9 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
   double* evals = a.evals ? a.evals + (size_t)b * n : nullptr;
 
   // ---- gamma = Z^T (Q^T gp), step in the eigenbasis ----------------------------------------------
-  double* lam_s = X;
-  double* gam_s = X + np;
-  RfoArrays R = rfo_carve(X + 2 * np, n);
+  double* lam_s = Y;
+  double* gam_s = Y + np;
+  RfoArrays R = rfo_carve(Y + 2 * np, n);
   double pg = 0.0;
   for (int i = tid; i < n; i += THREADS) {
     const double g = a.Bg[(size_t)b * n + i];
@@ -540,7 +559,7 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
   if (wid == 0) {
     if (!trivial) {
       constexpr int NS = 6;
-      double* ring = X;  // [NS][2][np]
+      double* ring = Y;  // [NS][2][np]
       const int nround = (n - 3 >= 1) ? (n - 3 + 1) / 2 : 0;  // rounds r = 0.. handle k = n-3-2r >= 1
       auto issue = [&](int r) {
         if (r < nround) {
@@ -650,7 +669,7 @@ int mop_launch_spectrum_step(int B, int n, int saddle_order, int neb_mode, doubl
   a.tmax = tmax;
   a.dbg = g_sp_dbg;
   const int np = (n + 3) & ~3;
-  const size_t smem = sizeof(double) * (7 * (size_t)np + mop::sp_x_doubles(n)) + sizeof(int) * 5 * (size_t)np;
+  const size_t smem = sizeof(double) * (5 * (size_t)np + mop::sp_y_doubles(n)) + 5 * (size_t)np;
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_spectrum_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mop::k_spectrum_step<<<B, mop::SP_THREADS, smem, stream>>>(a);
   MOP_CHECK_CUDA(cudaGetLastError());

@@ -9,6 +9,7 @@ B = int(os.environ.get("DIAG_B", "1024")); dev = torch.device("cuda:0")
 x0, H0, g0, rngs = bench.make_inputs(B, 0)
 T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 lib = _lib.load()
+lib.mop_debug_stream_chunk(int(os.environ.get("CHUNK", "256")))
 lib.mop_debug_tri_packed(int(os.environ.get("PACKED", "1"))); lib.mop_debug_packed_threads(int(os.environ.get("PKT", "256")))
 H = T(H0); st = ops.new_rsirfo_state(B, 0.5, dev)
 zero = torch.zeros(B, dtype=torch.float64, device=dev)
