@@ -29,15 +29,31 @@ struct PkArgs {
   long long* dbg;    // optional [B][8] phase cycles
 };
 
-__device__ __forceinline__ int pk(int i, int j) { return ((i * (i + 1)) >> 1) + j; }  // j <= i; n <= 160: fits int
+// Padded packed lower triangle: row i (i + 1 entries) is allotted 16 ceil(i / 16) + 1 doubles, so consecutive
+// rows start one double-word bank apart (mod 16): the sixteen lanes of a shared-memory wavefront that read the
+// same column of sixteen consecutive rows - the access pattern of the symv row part, the rank-2 update and the
+// Householder column - hit sixteen different banks.  (The plain triangle T(i) = i (i + 1) / 2 is a permutation
+// of the banks only for some i: ncu counted 39 % excess wavefronts.)  10 % more shared memory: 99.8 KB at
+// n = 150, still two CTAs per SM.
+__device__ __host__ __forceinline__ int pk_row(int i) {  // start of row i; i = 0 falls out of the formula (q = -1)
+  const int q = (i - 1) >> 4, rem = (i - 1) & 15;
+  return i + 16 * (q + 1) * (8 * q + rem);
+}
+__device__ __forceinline__ int pk_len(int r) { return ((r + 15) & ~15) + 1; }  // pk_row(r + 1) - pk_row(r)
+__device__ __forceinline__ int pk(int i, int j) { return pk_row(i) + j; }  // j <= i; n <= 160: fits int
+// smallest power of two S <= 32 with 2 S m > threads, as log2 (the thread-per-index split of the column step)
+__device__ __forceinline__ int split_log2(int threads, int m) {
+  const int lg = 32 - __clz(threads / (2 * m));
+  return lg < 5 ? lg : 5;
+}
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
   extern __shared__ double sm[];
   const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int np = (n + 3) & ~3;
-  double* L = sm;                                  // n (n+1) / 2
-  double* v = L + (((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3);  // np
+  double* L = sm;                                  // pk_row(n) doubles
+  double* v = L + (((size_t)pk_row(n) + 3) & ~(size_t)3);  // np
   double* w = v + np;                              // np
   double* gq = w + np;                             // np
   __shared__ double s_rb[2 * 32 * 2];  // every reduction is a block_sum_k<2>: the two parity buffers stay disjoint
@@ -105,24 +121,22 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
     PSEG(0);
     double red[2] = {0.0, 0.0};
     double pi = 0.0;
-    // S threads per index, S a power of two <= 32 (a group never straddles a warp)
-    int S = 1;
-    while (S < 32 && 2 * S * m <= THREADS) S <<= 1;
-    // lane -> (index, part) with the PART major inside the warp: a half-warp (one LDS.64 wavefront)
-    // then holds consecutive indices of one part, and rows i, i+1, ... of the packed triangle start
-    // T(i) = i (i+1) / 2 apart, which is a permutation of the 16 double-word banks
-    const int per = 32 / S;
-    const int t_idx = (tid >> 5) * per + (lane % per), s = lane / per;
+    // S threads per index, S a power of two <= 32 (a group never straddles a warp).  Lanes are PART major: a
+    // half-warp (one LDS.64 wavefront) holds W = min(32 / S, 16) consecutive indices; for S <= 2 (m > 64,
+    // where the time goes) these are sixteen consecutive indices of ONE part, and with the padded rows every
+    // wavefront below is conflict free.  Part s takes the terms s, s + S, ... (balanced to one term).
+    const int lgS = split_log2(THREADS, m), S = 1 << lgS;
+    const int per = 32 >> lgS, lgW = (5 - lgS) < 4 ? (5 - lgS) : 4, W = 1 << lgW;
+    const int t_idx = (tid >> 5) * per + (lane & (per - 1)), s = lane >> (5 - lgS);
     const bool act = t_idx < m;
     const int i = k + 1 + t_idx;
     if (tk != 0.0) {
       if (act) {
-        // term q of index i: q < i-k -> L(i, k+1+q) v_{k+1+q};  else -> L(r, i) v_r, r = i+1+(q-(i-k))
-        const int nrow = i - k;  // row-part terms (columns k+1 .. i)
-        double a0 = 0.0, a1 = 0.0;
-        const double* Li = L + pk(i, k + 1);
+        // row part: terms q = 0 .. i-k-1 -> L(i, k+1+q) v_{k+1+q}
+        const int nrow = i - k;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const double* Li = L + pk_row(i) + k + 1;
         const double* vq = v + k + 1;
-        double a2 = 0.0, a3 = 0.0;
         int q = s;
         for (; q + 3 * S < nrow; q += 4 * S) {  // four independent loads in flight
           const double l0 = Li[q], l1 = Li[q + S], l2 = Li[q + 2 * S], l3 = Li[q + 3 * S];
@@ -133,32 +147,44 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
           a3 = fma(l3, u3, a3);
         }
         for (; q < nrow; q += S) a0 = fma(Li[q], vq[q], a0);
-        // column part: q continues at r = i + 1 + (q - nrow); pk(r + S, i) - pk(r, i) = r S + S (S + 1) / 2
-        int r = i + 1 + (q - nrow);
-        int off = pk(r, i);
-        const int inc0 = (S * (S + 1)) >> 1;
-        for (; r + 3 * S < n; r += 4 * S) {
-          const int o1 = off + r * S + inc0;
-          const int o2 = o1 + (r + S) * S + inc0;
-          const int o3 = o2 + (r + 2 * S) * S + inc0;
-          const double l0 = L[off], l1 = L[o1], l2 = L[o2], l3 = L[o3];
-          const double u0 = v[r], u1 = v[r + S], u2 = v[r + 2 * S], u3 = v[r + 3 * S];
-          a0 = fma(l0, u0, a0);
-          a1 = fma(l1, u1, a1);
-          a2 = fma(l2, u2, a2);
-          a3 = fma(l3, u3, a3);
-          off = o3 + (r + 3 * S) * S + inc0;
-        }
-        for (; r < n; r += S) {
-          a0 = fma(L[off], v[r], a0);
-          off += r * S + inc0;
+        // column part: rows r > i -> L(r, i) v_r.  The W indices of a group walk the SAME rows (from the
+        // group's first index + 1, the rows up to the own index masked out): L(r, i .. i+W-1) is contiguous
+        // and v_r a broadcast.
+        int r = i - (lane & (W - 1)) + 1 + s;
+        if (S == 1) {  // m > 128: consecutive rows, the offset advances by the row allotment
+          int off = pk_row(r) + i;
+          for (; r + 3 < n; r += 4) {
+            const int o1 = off + pk_len(r), o2 = o1 + pk_len(r + 1), o3 = o2 + pk_len(r + 2);
+            const double l0 = L[off], l1 = L[o1], l2 = L[o2], l3 = L[o3];
+            const double u0 = v[r], u1 = v[r + 1], u2 = v[r + 2], u3 = v[r + 3];
+            a0 = fma(r > i ? l0 : 0.0, u0, a0);
+            a1 = fma(r + 1 > i ? l1 : 0.0, u1, a1);
+            a2 = fma(r + 2 > i ? l2 : 0.0, u2, a2);
+            a3 = fma(r + 3 > i ? l3 : 0.0, u3, a3);
+            off = o3 + pk_len(r + 3);
+          }
+          for (; r < n; ++r) {
+            a0 = fma(r > i ? L[off] : 0.0, v[r], a0);
+            off += pk_len(r);
+          }
+        } else {
+          for (; r + 3 * S < n; r += 4 * S) {
+            const double l0 = L[pk_row(r) + i], l1 = L[pk_row(r + S) + i], l2 = L[pk_row(r + 2 * S) + i],
+                         l3 = L[pk_row(r + 3 * S) + i];
+            const double u0 = v[r], u1 = v[r + S], u2 = v[r + 2 * S], u3 = v[r + 3 * S];
+            a0 = fma(r > i ? l0 : 0.0, u0, a0);
+            a1 = fma(r + S > i ? l1 : 0.0, u1, a1);
+            a2 = fma(r + 2 * S > i ? l2 : 0.0, u2, a2);
+            a3 = fma(r + 3 * S > i ? l3 : 0.0, u3, a3);
+          }
+          for (; r < n; r += S) a0 = fma(r > i ? L[pk_row(r) + i] : 0.0, v[r], a0);
         }
         a0 += a2;
         a1 += a3;
         pi = a0 + a1;
       }
       PSEG(1);
-      for (int o = per; o < 32; o <<= 1) pi += __shfl_xor_sync(MOP_FULL_MASK, pi, o);
+      for (int o = per; o < 32; o <<= 1) pi += __shfl_xor_sync(MOP_FULL_MASK, pi, o);  // the S parts of an index
       pi *= tk;
       if (act && s == 0) {
         const double vi = v[i];
@@ -178,18 +204,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
       // rank-2 update of the lower triangle, row pairs (k+1+t, n-1-t): m+1 elements per pair
       double nx[2] = {0.0, 0.0};
       {
-        int S2 = 1;
         const int npair = (m + 1) >> 1;
-        while (S2 < 32 && 2 * S2 * npair <= THREADS) S2 <<= 1;
-        const int per2 = 32 / S2;
-        const int t2 = (tid >> 5) * per2 + (lane % per2), s2 = lane / per2;
+        const int lgS2 = split_log2(THREADS, npair), S2 = 1 << lgS2;
+        const int per2 = 32 >> lgS2;
+        const int t2 = (tid >> 5) * per2 + (lane & (per2 - 1)), s2 = lane >> (5 - lgS2);
         if (t2 < npair) {
           const int rows[2] = {k + 1 + t2, n - 1 - t2};
           const int nr = (rows[0] == rows[1]) ? 1 : 2;
           for (int h = 0; h < nr; ++h) {
             const int r = rows[h];
             const double vr = v[r], wr = w[r];
-            double* Lr = L + pk(r, k + 1);
+            double* Lr = L + pk_row(r) + k + 1;
             const int len = r - k;  // columns k+1 .. r
             const double* wj = w + k + 1;
             const double* vj = v + k + 1;
@@ -241,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
 
 size_t mop_tridiag_packed_smem(int n) {
   const int np = (n + 3) & ~3;
-  return sizeof(double) * ((((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3) + 3 * (size_t)np);
+  return sizeof(double) * ((((size_t)mop::pk_row(n) + 3) & ~(size_t)3) + 3 * (size_t)np);
 }
 
 static int g_pk_threads = 256;
