@@ -84,6 +84,7 @@ SIGNATURES = {
     "mop_debug_eigh_small_pipeline": (_i, [_i]),
     "mop_debug_packed_threads": (_i, [_i]),
     "mop_debug_packed_timing": (_i, [_p]),
+    "mop_debug_packed_rowwarp": (_i, [_i]),
     "mop_debug_large_timing": (_i, [_p]),
     "mop_debug_large_ablate": (_i, [_i]),
 }
