@@ -514,6 +514,222 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rw(PkArgs a) {
 #undef RSEG
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused variant (default): the rank-2 update of reflector k-1 and the symv of reflector k in ONE pass over
+// the triangle.  The symv needs v_k, which needs the norm of the updated column k - but the symv is linear:
+// with u = the raw updated column k (rows > k) and v_k = s u + (1 - s alpha) e_{k+1}  (s = 1 / (alpha - beta)),
+//     A' v_k = s (A' u) + (1 - s alpha) A'(:, k+1),
+// so the pass accumulates q = A' u while it writes A' = A - v w^T - w v^T, and the scalars join afterwards.
+// Per column: (a) u and its norm, O(m)  (E)  (b) the fused pass  (P)  (c) q -> p -> w, v  (C)(D): four
+// barriers and one read + one write of every element (k_tridiag_rw: five barriers, two reads + one write).
+// Row blocks of FOUR consecutive rows per warp (register budget: v, w, u and the column sums of 5 column
+// chunks per lane plus four rows in flight), otherwise the mapping of k_tridiag_rw.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) k_tridiag_rwf(PkArgs a) {
+  constexpr int NW = THREADS / 32;
+  constexpr int MAXU = 5;  // n <= 160 columns over 32 lanes
+  extern __shared__ double sm[];
+  const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int np = (n + 3) & ~3;
+  double* L = sm;                                                 // n (n + 1) / 2
+  double* v = L + (((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3);   // np   reflector being applied
+  double* w = v + np;                                             // np
+  double* gq = w + np;                                            // np
+  double* uu = gq + np;                                           // np   raw next column
+  double* prow = uu + np;                                         // np   row sums of the symv
+  double* part = prow + np;                                       // NW * np  column sums per warp
+  __shared__ double s_rb[2 * 32 * 2];
+  __shared__ double s_alpha;
+  int parity = 0;
+  const double* Ain = a.A + (size_t)b * n * n;
+  double* Vh = a.Vh + (size_t)b * n * n;
+
+  double pn[2] = {0.0, 0.0};
+  for (int idx = tid; idx < n * n; idx += THREADS) {
+    const int i = idx / n, j = idx - i * n;
+    const double x = Ain[idx];
+    if (j <= i) L[pk0(i, j)] = x;
+    pn[0] = fma(x, x, pn[0]);
+  }
+  for (int i = tid; i < n; i += THREADS) {
+    gq[i] = a.gp ? a.gp[(size_t)b * n + i] : 0.0;
+    v[i] = 0.0;  // "reflector -1": nothing to apply in the first pass
+    w[i] = 0.0;
+  }
+  block_sum_k<2>(pn, s_rb, parity);
+  const double fro = sqrt(pn[0]);
+  const bool nonfinite = !isfinite(fro), trivial = nonfinite || fro == 0.0;
+  if (tid == 0) a.flag[b] = nonfinite ? 2 : (fro == 0.0 ? 1 : 0);
+  if (trivial || n <= 2) {
+    for (int i = tid; i < n; i += THREADS) {
+      a.dd[(size_t)b * n + i] = nonfinite ? NAN : (trivial ? 0.0 : L[pk0(i, i)]);
+      a.ee[(size_t)b * n + i] = (!trivial && i + 1 < n) ? L[pk0(i + 1, i)] : 0.0;
+      a.tau[(size_t)b * n + i] = 0.0;
+      a.gq[(size_t)b * n + i] = gq[i];
+    }
+    return;
+  }
+
+  long long seg[6] = {0, 0, 0, 0, 0, 0}, ts = clock64();
+#define FSEG(i)                             \
+  do {                                      \
+    if (a.dbg) {                            \
+      const long long tn_ = clock64();      \
+      seg[i] += tn_ - ts;                   \
+      ts = tn_;                             \
+    }                                       \
+  } while (0)
+  for (int k = 0; k < n - 2; ++k) {  // reflector k is defined, reflector k-1 (v, w) applied; trailing rows >= k
+    const int m = n - k;             // order of the block the pass updates (rows / columns k .. n-1)
+    // ---- (a) raw updated column k: u_i = L(i, k) - v_i w_k - w_i v_k, thread per row -------------------
+    double xs[2] = {0.0, 0.0};
+    {
+      const int i = k + tid;
+      if (i < n) {
+        const double ui = L[pk0(i, k)] - fma(v[i], w[k], w[i] * v[k]);
+        uu[i] = i > k ? ui : 0.0;  // index k takes no part in the next symv
+        if (i == k) a.dd[(size_t)b * n + k] = ui;
+        if (i == k + 1) s_alpha = ui;
+        if (i >= k + 2) xs[0] = ui * ui;
+      }
+    }
+    block_sum_k<2>(xs, s_rb, parity);  // (E) u, alpha published
+    const double xn2 = xs[0], alpha = s_alpha;
+    double beta = alpha, tk = 0.0, scal = 0.0;
+    if (xn2 > 0.0) {
+      beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+      tk = (beta - alpha) * fast_rcp(beta);
+      scal = fast_rcp(alpha - beta);
+    }
+    if (tid == 0) {
+      a.ee[(size_t)b * n + k] = beta;
+      a.tau[(size_t)b * n + k] = tk;
+    }
+    FSEG(0);
+    // ---- (b) fused pass: warp = four consecutive rows, lane = column ---------------------------------
+    double vreg[MAXU], wreg[MAXU], ureg[MAXU], cacc[MAXU];
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int c = k + lane + 32 * u;
+      const bool in = c < n;
+      vreg[u] = in ? v[c] : 0.0;
+      wreg[u] = in ? w[c] : 0.0;
+      ureg[u] = in ? uu[c] : 0.0;
+      cacc[u] = 0.0;
+    }
+    const int nblk = (m + 3) >> 2;
+    for (int pb = 0; pb * NW < nblk; ++pb) {
+      const int blk = nblk - 1 - (pb * NW + ((pb & 1) ? NW - 1 - wid : wid));  // longest blocks first, serpentine
+      if (blk < 0) continue;  // warp-uniform
+      const int rb = k + 4 * blk;
+      const int nu = ((min(rb + 3, n - 1) - k) >> 5) + 1;  // chunks of the longest row of the block
+      double vr[4], wr[4], ur[4], rs[4];
+      int ro[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = rb + j;
+        const bool in = r < n;
+        vr[j] = in ? v[r] : 0.0;
+        wr[j] = in ? w[r] : 0.0;
+        ur[j] = in ? uu[r] : 0.0;
+        rs[j] = 0.0;
+        ro[j] = pk0(in ? r : n - 1, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < MAXU; ++u) {
+        if (u < nu) {  // warp-uniform
+          const int c = k + lane + 32 * u;
+          double x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = (c <= rb + j && rb + j < n) ? L[ro[j] + c] : 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool in = c <= rb + j && rb + j < n;
+            x[j] -= fma(vr[j], wreg[u], wr[j] * vreg[u]);
+            if (in) L[ro[j] + c] = x[j];
+            const double xm = in ? x[j] : 0.0;
+            // the diagonal element also lands in the column accumulator; (c) takes it out again
+            rs[j] = fma(xm, ureg[u], rs[j]);
+            cacc[u] = fma(xm, ur[j], cacc[u]);
+          }
+        }
+      }
+      // transposing butterfly: 4 row sums over 32 lanes in 6 shuffles
+      const bool h16 = lane & 16, h8 = lane & 8;
+      double t2[2], t1;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double send = h16 ? rs[j] : rs[j + 2];
+        const double keep = h16 ? rs[j + 2] : rs[j];
+        t2[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 16);
+      }
+      {
+        const double send = h8 ? t2[0] : t2[1];
+        const double keep = h8 ? t2[1] : t2[0];
+        t1 = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 8);
+      }
+      t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 4);
+      t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 2);
+      t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 1);
+      if ((lane & 7) == 0) {  // lanes with bit 4 set hold rows 2-3, bit 3 adds 1
+        const int i = rb + (h16 ? 2 : 0) + (h8 ? 1 : 0);
+        if (i < n) prow[i] = t1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int c = k + lane + 32 * u;
+      if (c < n) part[wid * np + c] = cacc[u];
+    }
+    __syncthreads();  // (P) updated triangle, row sums and column partials complete
+    FSEG(1);
+    // ---- (c) q = A' u  ->  p = t (s q + (1 - s alpha) A'(:, k+1)),  v = s u + (1 - s alpha) e_{k+1} ----
+    double red[2] = {0.0, 0.0};
+    double pi = 0.0, vi = 0.0;
+    const int i = k + 1 + tid;
+    if (i < n) {
+      const double ui = uu[i];
+      double q = fma(-L[pk0(i, i)], ui, prow[i]);  // the diagonal term was counted in both sums
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) q += part[ww * np + i];
+      vi = (i == k + 1) ? 1.0 : ui * scal;
+      pi = tk * fma(scal, q, (1.0 - scal * alpha) * L[pk0(i, k + 1)]);
+      red[0] = pi * vi;
+      red[1] = vi * gq[i];
+    }
+    block_sum_k<2>(red, s_rb, parity);  // (C)
+    FSEG(2);
+    const double alpha2 = -0.5 * tk * red[0];
+    if (i < n) {
+      v[i] = vi;
+      w[i] = fma(alpha2, vi, pi);
+      gq[i] = fma(-tk * red[1], vi, gq[i]);
+      Vh[(size_t)k * n + i] = vi;
+    }
+    if (tid == 0) {  // index k leaves the trailing block
+      v[k] = 0.0;
+      w[k] = 0.0;
+    }
+    __syncthreads();  // (D) v, w of reflector k complete
+    FSEG(3);
+  }
+  // reflector n-3 is still to be applied to the last 2 x 2 block
+  if (tid == 0) {
+    const int i0 = n - 2, i1 = n - 1;
+    a.dd[(size_t)b * n + i0] = L[pk0(i0, i0)] - 2.0 * v[i0] * w[i0];
+    a.ee[(size_t)b * n + i0] = L[pk0(i1, i0)] - fma(v[i1], w[i0], w[i1] * v[i0]);
+    a.tau[(size_t)b * n + i0] = 0.0;
+    a.dd[(size_t)b * n + i1] = L[pk0(i1, i1)] - 2.0 * v[i1] * w[i1];
+    a.ee[(size_t)b * n + i1] = 0.0;
+    a.tau[(size_t)b * n + i1] = 0.0;
+  }
+  for (int i2 = tid; i2 < n; i2 += THREADS) a.gq[(size_t)b * n + i2] = gq[i2];
+  if (a.dbg && (tid == 0 || tid == 96))
+    for (int q = 0; q < 6; ++q) a.dbg[(size_t)b * 16 + (tid == 0 ? 0 : 8) + q] = seg[q];
+#undef FSEG
+}
+
 }  // namespace mop
 
 size_t mop_tridiag_packed_smem(int n) {
@@ -523,10 +739,11 @@ size_t mop_tridiag_packed_smem(int n) {
 
 size_t mop_tridiag_rw_smem(int n) {
   const int np = (n + 3) & ~3;
-  return sizeof(double) * ((((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3) + (4 + 8) * (size_t)np);
+  return sizeof(double) * ((((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3) + (5 + 8) * (size_t)np);
 }
-static int g_pk_rowwarp = 1;
-// tuning: 1 (default) = k_tridiag_rw (warp per row, lanes over columns), 0 = k_tridiag_packed (thread groups per index)
+static int g_pk_rowwarp = 2;
+// tuning: 2 (default) = k_tridiag_rwf (update + symv fused), 1 = k_tridiag_rw (warp per row, lanes over columns),
+// 0 = k_tridiag_packed (thread groups per index)
 extern "C" int mop_debug_packed_rowwarp(int on) {
   g_pk_rowwarp = on;
   return MOP_OK;
@@ -547,6 +764,13 @@ int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, d
                               double* tau, double* gq, int* flag, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   mop::PkArgs a{n, A, gp, Vh, dd, ee, tau, gq, flag, g_pk_dbg};
+  if (g_pk_rowwarp == 2) {
+    const size_t smem_rw = mop_tridiag_rw_smem(n);
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_rwf<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rw));
+    mop::k_tridiag_rwf<256><<<B, 256, smem_rw, stream>>>(a);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    return MOP_OK;
+  }
   if (g_pk_rowwarp) {
     const size_t smem_rw = mop_tridiag_rw_smem(n);
     MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_rw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rw));
