@@ -525,6 +525,43 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rw(PkArgs a) {
 // barriers and one read + one write of every element (k_tridiag_rw: five barriers, two reads + one write).
 // Row blocks of FOUR consecutive rows per warp (register budget: v, w, u and the column sums of 5 column
 // chunks per lane plus four rows in flight), otherwise the mapping of k_tridiag_rw.
+// Block-wide sums of EIGHT values for 8-warp CTAs, one barrier (double-buffered like block_sum_k): a
+// transposing butterfly leaves value j with the lanes whose bits 4..2 spell j (9 shuffles instead of 40), the
+// eight per-warp partials of each value are combined by every warp and handed to all lanes.
+__device__ __forceinline__ void block_sum8(double (&r)[8], double* buf, int& parity, int lane, int wid) {
+  double* bq = buf + (parity & 1) * 64;
+  parity ^= 1;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  double t4[4], t2[2], t1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double send = h16 ? r[j] : r[j + 4];
+    const double keep = h16 ? r[j + 4] : r[j];
+    t4[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double send = h8 ? t4[j] : t4[j + 2];
+    const double keep = h8 ? t4[j + 2] : t4[j];
+    t2[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 8);
+  }
+  {
+    const double send = h4 ? t2[0] : t2[1];
+    const double keep = h4 ? t2[1] : t2[0];
+    t1 = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 4);
+  }
+  t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 2);
+  t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 1);
+  const int j = lane >> 2;  // value index held by this lane: (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0)
+  if ((lane & 3) == 0) bq[j * 8 + wid] = t1;
+  __syncthreads();
+  double t = bq[j * 8 + (lane & 3)] + bq[j * 8 + (lane & 3) + 4];  // warps sub and sub + 4 of value j
+  t += __shfl_xor_sync(MOP_FULL_MASK, t, 1);
+  t += __shfl_xor_sync(MOP_FULL_MASK, t, 2);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) r[q] = __shfl_sync(MOP_FULL_MASK, t, 4 * q);
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rwf(PkArgs a) {
   constexpr int NW = THREADS / 32;
@@ -540,7 +577,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rwf(PkArgs a) {
   double* prow = uu + np;                                         // np   row sums of the symv
   double* part = prow + np;                                       // NW * np  column sums per warp
   __shared__ double s_rb[2 * 32 * 2];
-  __shared__ double s_alpha;
+  __shared__ double s_r8[2 * 8 * 8];
   int parity = 0;
   const double* Ain = a.A + (size_t)b * n * n;
   double* Vh = a.Vh + (size_t)b * n * n;
@@ -571,6 +608,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rwf(PkArgs a) {
     return;
   }
 
+  // raw column 0 and d_0; "reflector -1" is zero
+  for (int i = tid; i < n; i += THREADS) uu[i] = i > 0 ? L[pk0(i, 0)] : 0.0;
+  if (tid == 0) a.dd[(size_t)b * n] = L[0];
+  __syncthreads();
+
   long long seg[6] = {0, 0, 0, 0, 0, 0}, ts = clock64();
 #define FSEG(i)                             \
   do {                                      \
@@ -580,33 +622,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rwf(PkArgs a) {
       ts = tn_;                             \
     }                                       \
   } while (0)
-  for (int k = 0; k < n - 2; ++k) {  // reflector k is defined, reflector k-1 (v, w) applied; trailing rows >= k
-    const int m = n - k;             // order of the block the pass updates (rows / columns k .. n-1)
-    // ---- (a) raw updated column k: u_i = L(i, k) - v_i w_k - w_i v_k, thread per row -------------------
-    double xs[2] = {0.0, 0.0};
-    {
-      const int i = k + tid;
-      if (i < n) {
-        const double ui = L[pk0(i, k)] - fma(v[i], w[k], w[i] * v[k]);
-        uu[i] = i > k ? ui : 0.0;  // index k takes no part in the next symv
-        if (i == k) a.dd[(size_t)b * n + k] = ui;
-        if (i == k + 1) s_alpha = ui;
-        if (i >= k + 2) xs[0] = ui * ui;
-      }
-    }
-    block_sum_k<2>(xs, s_rb, parity);  // (E) u, alpha published
-    const double xn2 = xs[0], alpha = s_alpha;
-    double beta = alpha, tk = 0.0, scal = 0.0;
-    if (xn2 > 0.0) {
-      beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
-      tk = (beta - alpha) * fast_rcp(beta);
-      scal = fast_rcp(alpha - beta);
-    }
-    if (tid == 0) {
-      a.ee[(size_t)b * n + k] = beta;
-      a.tau[(size_t)b * n + k] = tk;
-    }
-    FSEG(0);
+  // Invariant at the top of iteration k: v, w = reflector k-1 (not yet applied to L), uu = the raw updated
+  // column k (rows > k; uu[k] = 0), d_k written.
+  for (int k = 0; k < n - 2; ++k) {
+    const int m = n - k;  // order of the block the pass updates (rows / columns k .. n-1)
     // ---- (b) fused pass: warp = four consecutive rows, lane = column ---------------------------------
     double vreg[MAXU], wreg[MAXU], ureg[MAXU], cacc[MAXU];
 #pragma unroll
@@ -684,41 +703,71 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rwf(PkArgs a) {
     }
     __syncthreads();  // (P) updated triangle, row sums and column partials complete
     FSEG(1);
-    // ---- (c) q = A' u  ->  p = t (s q + (1 - s alpha) A'(:, k+1)),  v = s u + (1 - s alpha) e_{k+1} ----
-    double red[2] = {0.0, 0.0};
-    double pi = 0.0, vi = 0.0;
+    // ---- (c) q = A' u; every scalar of the step from ONE block reduction -------------------------------
+    //   S1 = sum q_i u_i, S2 = sum c_i u_i, S3 = sum u_i gq_i, S4 = sum u_i^2 over i >= k+2 (c = A'(:, k+1)),
+    //   and q, c, gq at i = k+1.  Then beta, t, s;  p = t (s q + (1 - s alpha) c),  v = s u (v_{k+1} = 1),
+    //   p.v = t [(s q0 + ca c0) + s (s S1 + ca S2)],  v.gq = gq0 + s S3,  w = p - t/2 (p.v) v,
+    //   and the raw NEXT column  u'_i = c_i - v_i w_{k+1} - w_i  comes from the same registers.
     const int i = k + 1 + tid;
+    const double alpha = uu[k + 1];
+    double ui = 0.0, qi = 0.0, ci = 0.0, gi = 0.0;
+    double rd[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (i < n) {
-      const double ui = uu[i];
-      double q = fma(-L[pk0(i, i)], ui, prow[i]);  // the diagonal term was counted in both sums
+      ui = uu[i];
+      qi = fma(-L[pk0(i, i)], ui, prow[i]);  // the diagonal term was counted in both sums
 #pragma unroll
-      for (int ww = 0; ww < NW; ++ww) q += part[ww * np + i];
-      vi = (i == k + 1) ? 1.0 : ui * scal;
-      pi = tk * fma(scal, q, (1.0 - scal * alpha) * L[pk0(i, k + 1)]);
-      red[0] = pi * vi;
-      red[1] = vi * gq[i];
+      for (int ww = 0; ww < NW; ++ww) qi += part[ww * np + i];
+      ci = L[pk0(i, k + 1)];
+      gi = gq[i];
+      if (tid == 0) {
+        rd[4] = qi;
+        rd[5] = ci;
+        rd[6] = gi;
+      } else {
+        rd[0] = qi * ui;
+        rd[1] = ci * ui;
+        rd[2] = ui * gi;
+        rd[3] = ui * ui;
+      }
     }
-    block_sum_k<2>(red, s_rb, parity);  // (C)
+    block_sum8(rd, s_r8, parity, lane, wid);  // (C)
     FSEG(2);
-    const double alpha2 = -0.5 * tk * red[0];
+    const double xn2 = rd[3];
+    double beta = alpha, tk = 0.0, scal = 0.0;
+    if (xn2 > 0.0) {
+      beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+      tk = (beta - alpha) * fast_rcp(beta);
+      scal = fast_rcp(alpha - beta);
+    }
+    const double ca = 1.0 - scal * alpha;
+    const double p0 = tk * fma(scal, rd[4], ca * rd[5]);
+    const double pv = p0 + tk * scal * fma(scal, rd[0], ca * rd[1]);
+    const double vg = fma(scal, rd[2], rd[6]);
+    const double alpha2 = -0.5 * tk * pv;
+    const double w0 = p0 + alpha2;  // w_{k+1}
     if (i < n) {
+      const double vi = (tid == 0) ? 1.0 : ui * scal;
+      const double pi = tk * fma(scal, qi, ca * ci);
+      const double wi = fma(alpha2, vi, pi);
+      const double un = ci - fma(vi, w0, wi);  // raw column k+1 after reflector k
       v[i] = vi;
-      w[i] = fma(alpha2, vi, pi);
-      gq[i] = fma(-tk * red[1], vi, gq[i]);
+      w[i] = wi;
+      gq[i] = fma(-tk * vg, vi, gi);
+      uu[i] = tid == 0 ? 0.0 : un;
       Vh[(size_t)k * n + i] = vi;
+      if (tid == 0) {
+        a.ee[(size_t)b * n + k] = beta;
+        a.tau[(size_t)b * n + k] = tk;
+        a.dd[(size_t)b * n + k + 1] = un;
+      }
     }
-    if (tid == 0) {  // index k leaves the trailing block
-      v[k] = 0.0;
-      w[k] = 0.0;
-    }
-    __syncthreads();  // (D) v, w of reflector k complete
+    __syncthreads();  // (D) v, w of reflector k and the raw column k+1 complete
     FSEG(3);
   }
-  // reflector n-3 is still to be applied to the last 2 x 2 block
+  // reflector n-3 is still to be applied to the last diagonal element; e_{n-2} is the raw column n-2
   if (tid == 0) {
     const int i0 = n - 2, i1 = n - 1;
-    a.dd[(size_t)b * n + i0] = L[pk0(i0, i0)] - 2.0 * v[i0] * w[i0];
-    a.ee[(size_t)b * n + i0] = L[pk0(i1, i0)] - fma(v[i1], w[i0], w[i1] * v[i0]);
+    a.ee[(size_t)b * n + i0] = uu[i1];
     a.tau[(size_t)b * n + i0] = 0.0;
     a.dd[(size_t)b * n + i1] = L[pk0(i1, i1)] - 2.0 * v[i1] * w[i1];
     a.ee[(size_t)b * n + i1] = 0.0;
