@@ -379,7 +379,7 @@ int mop_debug_tri_packed(int on);       /* tuning: packed two-CTA-per-SM tridiag
 int mop_debug_stream_chunk(int structures); /* tuning: structures per update + projection chunk of mop_rsirfo_step (default 0 = whole batch) */
 int mop_debug_tri_spectrum(int on);     /* tuning: k_spectrum_step (Z in global memory, 7 structures per SM) after the packed kernel (default 1) */
 int mop_debug_spectrum_timing(void* buf); /* diagnostics: [B][16] int64 phase cycles of k_spectrum_step */
-int mop_debug_packed_rowwarp(int on);   /* tuning: warp-per-row packed tridiagonalisation k_tridiag_rw (default 1) or the thread-group kernel (0) */
+int mop_debug_packed_rowwarp(int on);   /* tuning: fused warp-per-row packed tridiagonalisation k_tridiag_rwf (default 1) or the thread-group kernel k_tridiag_packed (0) */
 int mop_debug_packed_timing(void* buf);   /* diagnostics: [B][16] int64 phase cycles of the packed kernel */
 int mop_debug_packed_threads(int threads); /* tuning: CTA size of the packed kernel (128, 256, 512) */
 int mop_debug_large_pair(int mode);     /* tuning: two matrices per cluster in lock-step: 0 auto, 1 always, -1 never */

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------
-// Row-per-warp variant (default).  ncu on k_tridiag_packed: the shared-memory pipe is ~70 % busy and every
+// Row-per-warp mapping (k_tridiag_rwf below).  ncu on k_tridiag_packed: the shared-memory pipe is ~70 % busy and every
 // element of the triangle is read twice by the symv (row part + column gather) with one more load of v or
 // w per FMA.  Here a WARP owns a row and its LANES the columns, for the symv and for the rank-2 update:
 //   symv    x = L(i, c) is read once, contiguously; it feeds the row sum (x v_c, v_c in a register, one
@@ -273,247 +273,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_packed(PkArgs a) {
 //           combined across the eight warps through shared memory;
 //   update  L(r, c) -= v_r w_c + w_r v_c with v_c, w_c in registers: one load and one store per element.
 // Plain triangle T(i) = i (i + 1) / 2 (row accesses are contiguous, no padding needed); shared memory:
-// L | v | w | gq | prow | part[8][np] = 105 KB at n = 150, two CTAs per SM.
+// L | v | w | gq | u | prow | part[8][np] = 106 KB at n = 150, two CTAs per SM.
 __device__ __forceinline__ int pk0(int i, int j) { return ((i * (i + 1)) >> 1) + j; }
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 2) k_tridiag_rw(PkArgs a) {
-  constexpr int NW = THREADS / 32;
-  constexpr int MAXU = 5;  // n <= 160 columns over 32 lanes
-  extern __shared__ double sm[];
-  const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int np = (n + 3) & ~3;
-  double* L = sm;                                                 // n (n + 1) / 2
-  double* v = L + (((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3);   // np
-  double* w = v + np;                                             // np
-  double* gq = w + np;                                            // np
-  double* prow = gq + np;                                         // np   row sums of the symv
-  double* part = prow + np;                                       // NW * np  column sums per warp
-  __shared__ double s_rb[2 * 32 * 2];
-  int parity = 0;
-  const double* Ain = a.A + (size_t)b * n * n;
-  double* Vh = a.Vh + (size_t)b * n * n;
-
-  double pn[2] = {0.0, 0.0};
-  for (int idx = tid; idx < n * n; idx += THREADS) {
-    const int i = idx / n, j = idx - i * n;
-    const double x = Ain[idx];
-    if (j <= i) L[pk0(i, j)] = x;
-    pn[0] = fma(x, x, pn[0]);
-  }
-  for (int i = tid; i < n; i += THREADS) gq[i] = a.gp ? a.gp[(size_t)b * n + i] : 0.0;
-  block_sum_k<2>(pn, s_rb, parity);
-  const double fro = sqrt(pn[0]);
-  const bool nonfinite = !isfinite(fro), trivial = nonfinite || fro == 0.0;
-  if (tid == 0) a.flag[b] = nonfinite ? 2 : (fro == 0.0 ? 1 : 0);
-  if (trivial || n <= 2) {
-    for (int i = tid; i < n; i += THREADS) {
-      a.dd[(size_t)b * n + i] = nonfinite ? NAN : (trivial ? 0.0 : L[pk0(i, i)]);
-      a.ee[(size_t)b * n + i] = (!trivial && i + 1 < n) ? L[pk0(i + 1, i)] : 0.0;
-      a.tau[(size_t)b * n + i] = 0.0;
-      a.gq[(size_t)b * n + i] = gq[i];
-    }
-    return;
-  }
-  double xn[2] = {0.0, 0.0};
-  for (int i = 2 + tid; i < n; i += THREADS) xn[0] = fma(L[pk0(i, 0)], L[pk0(i, 0)], xn[0]);
-  block_sum_k<2>(xn, s_rb, parity);
-  double xn2 = xn[0];
-
-  long long seg[6] = {0, 0, 0, 0, 0, 0}, ts = clock64();
-#define RSEG(i)                             \
-  do {                                      \
-    if (a.dbg) {                            \
-      const long long tn_ = clock64();      \
-      seg[i] += tn_ - ts;                   \
-      ts = tn_;                             \
-    }                                       \
-  } while (0)
-  for (int k = 0; k < n - 2; ++k) {
-    const int m = n - k - 1, c0 = k + 1;  // trailing order; indices c0 .. n-1
-    const double alpha = L[pk0(k + 1, k)];
-    double beta = alpha, tk = 0.0, scal = 0.0;
-    if (xn2 > 0.0) {
-      beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
-      tk = (beta - alpha) * fast_rcp(beta);
-      scal = fast_rcp(alpha - beta);
-    }
-    for (int i = c0 + tid; i < n; i += THREADS) {
-      const double vi = (i == c0) ? 1.0 : L[pk0(i, k)] * scal;
-      v[i] = vi;
-      Vh[(size_t)k * n + i] = vi;
-    }
-    if (tid == 0) {
-      a.dd[(size_t)b * n + k] = L[pk0(k, k)];
-      a.ee[(size_t)b * n + k] = beta;
-      a.tau[(size_t)b * n + k] = tk;
-    }
-    __syncthreads();  // (A) v complete
-    RSEG(0);
-    if (tk != 0.0) {
-      // ---- symv: warp = row, lane = column ---------------------------------------------------------
-      double vreg[MAXU], cacc[MAXU];
-#pragma unroll
-      for (int u = 0; u < MAXU; ++u) {
-        const int c = c0 + lane + 32 * u;
-        vreg[u] = c < n ? v[c] : 0.0;
-        cacc[u] = 0.0;
-      }
-      // Row blocks of eight CONSECUTIVE rows, dealt to the warps longest first in serpentine order (balances
-      // the row lengths to about one chunk); the eight rows of a block need the same number of 32-column chunks, so one warp-uniform
-      // test per chunk guards a branch-free body of eight independent loads and sixteen FMAs.
-      const int nblk = (m + 7) >> 3;
-      for (int pb = 0; pb * NW < nblk; ++pb) {
-        const int blk = nblk - 1 - (pb * NW + ((pb & 1) ? NW - 1 - wid : wid));  // longest blocks first
-        if (blk < 0) continue;  // warp-uniform
-        const int ib = c0 + 8 * blk;
-        const int nu = ((min(ib + 7, n - 1) - c0) >> 5) + 1;  // chunks of the longest row of the block
-        double rs[8], vi[8];
-        int ro[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = ib + j;
-          rs[j] = 0.0;
-          vi[j] = i < n ? v[i] : 0.0;
-          ro[j] = pk0(i < n ? i : n - 1, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < MAXU; ++u) {
-          if (u < nu) {  // warp-uniform
-            const int c = c0 + lane + 32 * u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              // rows beyond n-1 and columns beyond the diagonal are masked; the diagonal element also lands
-              // in the column accumulator, the finalisation takes it out again
-              const double x = (c <= ib + j && ib + j < n) ? L[ro[j] + c] : 0.0;
-              rs[j] = fma(x, vreg[u], rs[j]);
-              cacc[u] = fma(x, vi[j], cacc[u]);
-            }
-          }
-        }
-        // transposing butterfly: 8 row sums over 32 lanes in 9 shuffles
-        double t4[4], t2[2], t1;
-        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double send = h16 ? rs[j] : rs[j + 4];
-          const double keep = h16 ? rs[j + 4] : rs[j];
-          t4[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 16);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const double send = h8 ? t4[j] : t4[j + 2];
-          const double keep = h8 ? t4[j + 2] : t4[j];
-          t2[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 8);
-        }
-        {
-          const double send = h4 ? t2[0] : t2[1];
-          const double keep = h4 ? t2[1] : t2[0];
-          t1 = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 4);
-        }
-        t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 2);
-        t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 1);
-        // lanes with bit 4 set hold rows 4-7, bit 3 adds 2, bit 2 adds 1
-        if ((lane & 3) == 0) {
-          const int i = ib + (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
-          if (i < n) prow[i] = t1;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < MAXU; ++u) {
-        const int c = c0 + lane + 32 * u;
-        if (c < n) part[wid * np + c] = cacc[u];
-      }
-      __syncthreads();  // (P) row sums and column partials complete
-      RSEG(1);
-      double red[2] = {0.0, 0.0};
-      double pi = 0.0, vi = 0.0;
-      const int i = c0 + tid;
-      if (tid < m) {
-        vi = v[i];
-        double sum = fma(-L[pk0(i, i)], vi, prow[i]);  // the diagonal term was counted in both sums
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww) sum += part[ww * np + i];
-        pi = tk * sum;
-        red[0] = pi * vi;
-        red[1] = vi * gq[i];
-      }
-      block_sum_k<2>(red, s_rb, parity);  // (C)
-      RSEG(2);
-      const double alpha2 = -0.5 * tk * red[0];
-      if (tid < m) {
-        w[i] = fma(alpha2, vi, pi);
-        gq[i] = fma(-tk * red[1], vi, gq[i]);
-      }
-      __syncthreads();  // (D) w complete
-      RSEG(3);
-      // ---- rank-2 update: warp = row, lane = column; v_c, w_c in registers ------------------------------
-      double wreg[MAXU];
-#pragma unroll
-      for (int u = 0; u < MAXU; ++u) {
-        const int c = c0 + lane + 32 * u;
-        wreg[u] = c < n ? w[c] : 0.0;
-      }
-      double nx[2] = {0.0, 0.0};
-      for (int pb = 0; pb * NW < nblk; ++pb) {  // the same row blocks as the symv
-        const int blk = nblk - 1 - (pb * NW + ((pb & 1) ? NW - 1 - wid : wid));  // longest blocks first
-        if (blk < 0) continue;  // warp-uniform
-        const int rb = c0 + 8 * blk;
-        const int nu = ((min(rb + 7, n - 1) - c0) >> 5) + 1;
-        double vr[8], wr[8];
-        int ro[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = rb + j;
-          vr[j] = r < n ? v[r] : 0.0;
-          wr[j] = r < n ? w[r] : 0.0;
-          ro[j] = pk0(r < n ? r : n - 1, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < MAXU; ++u) {
-          if (u < nu) {  // warp-uniform
-            const int c = c0 + lane + 32 * u;
-            double x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = (c <= rb + j && rb + j < n) ? L[ro[j] + c] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              x[j] -= fma(vr[j], wreg[u], wr[j] * vreg[u]);
-              if (c <= rb + j && rb + j < n) L[ro[j] + c] = x[j];
-            }
-            if (u == 0 && lane == 0) {  // column c0: the next Householder column, rows >= k + 3
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (rb + j >= k + 3 && rb + j < n) nx[0] = fma(x[j], x[j], nx[0]);
-            }
-          }
-        }
-      }
-      RSEG(4);
-      block_sum_k<2>(nx, s_rb, parity);  // (E) also publishes the updated triangle
-      RSEG(5);
-      xn2 = nx[0];
-    } else {
-      double nx[2] = {0.0, 0.0};
-      for (int r = k + 3 + tid; r < n; r += THREADS) nx[0] = fma(L[pk0(r, k + 1)], L[pk0(r, k + 1)], nx[0]);
-      block_sum_k<2>(nx, s_rb, parity);
-      xn2 = nx[0];
-    }
-  }
-  if (tid == 0) {
-    a.dd[(size_t)b * n + n - 2] = L[pk0(n - 2, n - 2)];
-    a.ee[(size_t)b * n + n - 2] = L[pk0(n - 1, n - 2)];
-    a.tau[(size_t)b * n + n - 2] = 0.0;
-    a.dd[(size_t)b * n + n - 1] = L[pk0(n - 1, n - 1)];
-    a.ee[(size_t)b * n + n - 1] = 0.0;
-    a.tau[(size_t)b * n + n - 1] = 0.0;
-  }
-  for (int i2 = tid; i2 < n; i2 += THREADS) a.gq[(size_t)b * n + i2] = gq[i2];
-  if (a.dbg && (tid == 0 || tid == 96))
-    for (int q = 0; q < 6; ++q) a.dbg[(size_t)b * 16 + (tid == 0 ? 0 : 8) + q] = seg[q];
-#undef RSEG
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // Fused variant (default): the rank-2 update of reflector k-1 and the symv of reflector k in ONE pass over
@@ -521,10 +282,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rw(PkArgs a) {
 // with u = the raw updated column k (rows > k) and v_k = s u + (1 - s alpha) e_{k+1}  (s = 1 / (alpha - beta)),
 //     A' v_k = s (A' u) + (1 - s alpha) A'(:, k+1),
 // so the pass accumulates q = A' u while it writes A' = A - v w^T - w v^T, and the scalars join afterwards.
-// Per column: (a) u and its norm, O(m)  (E)  (b) the fused pass  (P)  (c) q -> p -> w, v  (C)(D): four
-// barriers and one read + one write of every element (k_tridiag_rw: five barriers, two reads + one write).
+// Per column: (b) the fused pass  (P)  (c) q, the sums S1..S4 and three scalars through ONE block reduction
+// (C), then beta, t, s, p, w, v AND the raw next column u' from the values already in registers  (D): three
+// barriers and one read + one write of every element (separate passes: five barriers, two reads + one write).
 // Row blocks of FOUR consecutive rows per warp (register budget: v, w, u and the column sums of 5 column
-// chunks per lane plus four rows in flight), otherwise the mapping of k_tridiag_rw.
+// chunks per lane plus four rows in flight), dealt longest first in serpentine order.
+//
 // Block-wide sums of EIGHT values for 8-warp CTAs, one barrier (double-buffered like block_sum_k): a
 // transposing butterfly leaves value j with the lanes whose bits 4..2 spell j (9 shuffles instead of 40), the
 // eight per-warp partials of each value are combined by every warp and handed to all lanes.
@@ -790,9 +553,9 @@ size_t mop_tridiag_rw_smem(int n) {
   const int np = (n + 3) & ~3;
   return sizeof(double) * ((((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3) + (5 + 8) * (size_t)np);
 }
-static int g_pk_rowwarp = 2;
-// tuning: 2 (default) = k_tridiag_rwf (update + symv fused), 1 = k_tridiag_rw (warp per row, lanes over columns),
-// 0 = k_tridiag_packed (thread groups per index)
+static int g_pk_rowwarp = 1;
+// tuning: 1 (default) = k_tridiag_rwf (warp per row block, lanes over columns, update + symv fused),
+// 0 = k_tridiag_packed (thread groups per index, separate symv and update passes)
 extern "C" int mop_debug_packed_rowwarp(int on) {
   g_pk_rowwarp = on;
   return MOP_OK;
@@ -813,17 +576,10 @@ int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, d
                               double* tau, double* gq, int* flag, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   mop::PkArgs a{n, A, gp, Vh, dd, ee, tau, gq, flag, g_pk_dbg};
-  if (g_pk_rowwarp == 2) {
+  if (g_pk_rowwarp) {
     const size_t smem_rw = mop_tridiag_rw_smem(n);
     MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_rwf<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rw));
     mop::k_tridiag_rwf<256><<<B, 256, smem_rw, stream>>>(a);
-    MOP_CHECK_CUDA(cudaGetLastError());
-    return MOP_OK;
-  }
-  if (g_pk_rowwarp) {
-    const size_t smem_rw = mop_tridiag_rw_smem(n);
-    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_rw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rw));
-    mop::k_tridiag_rw<256><<<B, 256, smem_rw, stream>>>(a);
     MOP_CHECK_CUDA(cudaGetLastError());
     return MOP_OK;
   }
