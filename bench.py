@@ -412,7 +412,7 @@ def run_b200(args, rank, world, local_rank):
         cpu_val, used = cpu_baseline(sample, cores)
         traffic = None          # DRAM bytes of the dominant kernel pair per launch, from the committed ncu capture
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
             if tr.get("batch") == B and tr.get("n") == n:
                 traffic = tr["dominant_pair_bytes_per_launch"]
         except Exception:
@@ -436,7 +436,7 @@ def run_b200(args, rank, world, local_rank):
                                    "of T and the RFO step in the eigenbasis, timed together (dominant pair of the step)",
                          "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": eig_tflops / fp64_peak, "traffic": traffic,
-                         "traffic_source": "profiles/r1_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write)",
+                         "traffic_source": "profiles/r1b_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write)",
                          "algorithmic_flops_per_launch": B * WF, "kernel_ms": eig_ms,
                          "executed_flops_per_launch_estimate": executed_flops,
                          "executed_tflops_estimate": executed_flops / (eig_ms * 1e-3) / 1e12,

@@ -411,39 +411,70 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
         }
       }
       __syncwarp();
+      // Column c lives in registers (rows lane + 32 u); the dots against the finished columns are taken four
+      // at a time (twenty independent loads in flight instead of one dependent round trip per column - the
+      // low end of a dense spectrum can chain 10 - 15 eigenvalues into one cluster).
+      constexpr int MAXJ = (SP_MAX_N + 31) / 32;
+      double* dts = gq_dots(Y, np, wid);
       for (int c = 1; c < cs; ++c) {
         double* zc_ = buf + (size_t)c * m;
+        double zr[MAXJ];
+#pragma unroll
+        for (int u = 0; u < MAXJ; ++u) zr[u] = (lane + 32 * u < m) ? zc_[lane + 32 * u] : 0.0;
         double nfirst = 1.0;
         for (int rep = 0; rep < 2; ++rep) {
-          for (int p = 0; p < c; ++p) {  // classical Gram-Schmidt: all dots from the same vector
-            const double* zp = buf + (size_t)p * m;
-            double dt = 0.0;
-            for (int k = lane; k < m; k += 32) dt = fma(zp[k], zc_[k], dt);
-            dt = warp_sum(dt);
-            if (lane == 0) gq_dots(Y, np, wid)[p & 63] = dt;
-            if ((p & 63) == 63 || p == c - 1) {
-              __syncwarp();
-              const int p0 = p & ~63;
-              for (int k = lane; k < m; k += 32) {
-                double zv = zc_[k];
-                for (int pp = p0; pp <= p; ++pp) zv = fma(-gq_dots(Y, np, wid)[pp - p0], buf[(size_t)pp * m + k], zv);
-                zc_[k] = zv;
+          for (int p0 = 0; p0 < c; p0 += 64) {  // classical Gram-Schmidt: all dots of a batch from the same vector
+            const int pe = min(c, p0 + 64);
+            for (int p = p0; p < pe; p += 4) {
+              double d4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (p + q < pe) {  // warp-uniform
+                  const double* zp = buf + (size_t)(p + q) * m;
+#pragma unroll
+                  for (int u = 0; u < MAXJ; ++u)
+                    if (lane + 32 * u < m) d4[q] = fma(zp[lane + 32 * u], zr[u], d4[q]);
+                }
               }
-              __syncwarp();
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d4[q] += __shfl_xor_sync(MOP_FULL_MASK, d4[q], o);
+              }
+              if (lane < 4 && p + lane < pe) dts[p + lane - p0] = lane == 0 ? d4[0] : (lane == 1 ? d4[1] : (lane == 2 ? d4[2] : d4[3]));
             }
+            __syncwarp();
+            for (int p = p0; p < pe; p += 4) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (p + q < pe) {  // warp-uniform
+                  const double* zp = buf + (size_t)(p + q) * m;
+                  const double dq = dts[p + q - p0];
+#pragma unroll
+                  for (int u = 0; u < MAXJ; ++u)
+                    if (lane + 32 * u < m) zr[u] = fma(-dq, zp[lane + 32 * u], zr[u]);
+                }
+              }
+            }
+            __syncwarp();
           }
           double nn = 0.0;
-          for (int k = lane; k < m; k += 32) nn = fma(zc_[k], zc_[k], nn);
+#pragma unroll
+          for (int u = 0; u < MAXJ; ++u) nn = fma(zr[u], zr[u], nn);
           nn = sqrt(warp_sum(nn));
           if (rep == 0) nfirst = nn;
           if (!(nn > 1e-2)) {
             if (lane == 0) s_fallback = 1;  // vector (nearly) inside the span of its cluster
           }
           const double sc = nn > 0.0 ? 1.0 / nn : 0.0;
-          for (int k = lane; k < m; k += 32) zc_[k] *= sc;
-          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < MAXJ; ++u) zr[u] *= sc;
           if (rep == 0 && nfirst > 0.7) break;  // "twice is enough" only when needed
         }
+#pragma unroll
+        for (int u = 0; u < MAXJ; ++u)
+          if (lane + 32 * u < m) zc_[lane + 32 * u] = zr[u];
+        __syncwarp();
       }
       for (int c = 1; c < cs; ++c) {
         for (int k = lane; k < m; k += 32) Z[(size_t)(s + k) * n + c0 + c] = buf[(size_t)c * m + k];
