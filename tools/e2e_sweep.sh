@@ -5,9 +5,8 @@ run() {
 import json,sys
 d=json.loads(sys.stdin.read()); print('split $1 streams $2 prio $3: value %.4g e2e %.4g ok %s resident %.4g' % (d['value'], d['e2e']['value'], d['e2e']['matches_resident_path'], d['e2e_hessian_resident']['value']))"
 }
-run 256,256,256,256 4 0
-run 256,256,256,256 4 1
-run 256,256,256,128,128 5 1
 run 136,296,296,296 4 1
-run 296,296,296,136 4 1
-run 128,256,256,256,128 5 1
+run 256,256,256,256 4 1
+run 128,128,128,128,128,128,128,128 8 1
+run 64,192,256,256,192,64 6 1
+run 148,148,148,148,148,148,136 7 1
