@@ -418,22 +418,36 @@ __global__ void __launch_bounds__(THREADS, 2) k_tridiag_rwf(PkArgs a) {
         rs[j] = 0.0;
         ro[j] = pk0(in ? r : n - 1, 0);
       }
+      const bool full4 = rb + 3 < n;  // warp-uniform: all four rows exist
 #pragma unroll
       for (int u = 0; u < MAXU; ++u) {
         if (u < nu) {  // warp-uniform
           const int c = k + lane + 32 * u;
           double x[4];
+          if (full4 && k + 32 * u + 31 <= rb) {
+            // interior chunk: every lane's column lies at or below the diagonal of all four rows - no masks
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = (c <= rb + j && rb + j < n) ? L[ro[j] + c] : 0.0;
+            for (int j = 0; j < 4; ++j) x[j] = L[ro[j] + c];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool in = c <= rb + j && rb + j < n;
-            x[j] -= fma(vr[j], wreg[u], wr[j] * vreg[u]);
-            if (in) L[ro[j] + c] = x[j];
-            const double xm = in ? x[j] : 0.0;
-            // the diagonal element also lands in the column accumulator; (c) takes it out again
-            rs[j] = fma(xm, ureg[u], rs[j]);
-            cacc[u] = fma(xm, ur[j], cacc[u]);
+            for (int j = 0; j < 4; ++j) {
+              x[j] -= fma(vr[j], wreg[u], wr[j] * vreg[u]);
+              L[ro[j] + c] = x[j];
+              rs[j] = fma(x[j], ureg[u], rs[j]);
+              cacc[u] = fma(x[j], ur[j], cacc[u]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = (c <= rb + j && rb + j < n) ? L[ro[j] + c] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool in = c <= rb + j && rb + j < n;
+              x[j] -= fma(vr[j], wreg[u], wr[j] * vreg[u]);
+              if (in) L[ro[j] + c] = x[j];
+              const double xm = in ? x[j] : 0.0;
+              // the diagonal element also lands in the column accumulator; (c) takes it out again
+              rs[j] = fma(xm, ureg[u], rs[j]);
+              cacc[u] = fma(xm, ur[j], cacc[u]);
+            }
           }
         }
       }
