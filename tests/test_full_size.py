@@ -60,3 +60,52 @@ def test_c2_batch_properties_and_sample_parity():
         assert np.linalg.norm(mv[b] - m) / np.linalg.norm(m) < 1e-10, b
         ref = o.last["eigvals"]
         assert np.abs(lam[b] - ref).max() <= 1e-10 * np.abs(ref).max(), b
+
+
+@pytest.mark.parametrize("case", ["diag", "n9", "n15_saddle"])
+def test_fused_path_edge_cases_vs_oracle(case):
+    """Shapes and spectra the big batches never produce: an already diagonal Hessian (every Householder
+    reflector is the identity: tau = 0 columns), three atoms (n = 9, fewer columns than one warp) and a first-order
+    saddle at n = 15.  1e-10 relative on the step.  (Two atoms are a documented deviation: the reference's reduced
+    QR and the Gram-Schmidt basis differ for rank-deficient TR/ROT sets)"""
+    rng = np.random.default_rng(7)
+    natoms, saddle = {"diag": (4, 0), "n9": (3, 0), "n15_saddle": (5, 1)}[case]
+    n = 3 * natoms
+    B = 5
+    xs, Hs, gs = [], [], []
+    for b in range(B):
+        x = synthetic.grid_geometry(natoms, rng).reshape(-1)
+        H = np.diag(np.linspace(0.2, 2.0, n) * (1.0 + 0.1 * b)) if case == "diag" else synthetic.spd_hessian(n, rng)
+        if saddle:
+            w, V = np.linalg.eigh(O.project_hessian_trrot(H, x))
+            H = H - (w[6] + 0.05) * np.outer(V[:, 6], V[:, 6])     # lowest non-null mode -> -0.05
+        xs.append(x); Hs.append(H); gs.append(rng.standard_normal(n) * 1e-2)
+    x0, H0, g0 = np.stack(xs), np.stack(Hs), np.stack(gs)
+    st = ops.new_rsirfo_state(B, 0.1 if saddle else 0.5, DEV)
+    out = ops.rsirfo_step(T(H0), T(x0), T(g0), T(g0), st, method=ops.resolve_update_method("rsirfo_bfgs"),
+                          saddle_order=saddle, Be=torch.zeros(B, dtype=torch.float64, device=DEV),
+                          trust_max=0.1 if saddle else 0.5)
+    mv = out["move"].cpu().numpy()
+    for b in range(B):
+        o = O.RSIRFOOracle(method="rsirfo_bfgs", saddle_order=saddle)
+        o.set_hessian(H0[b].copy()); o.set_bias_hessian(None)
+        m = o.run(x0[b], g0[b], g0[b], None, None, 0.0)
+        assert np.linalg.norm(mv[b] - m) / np.linalg.norm(m) < 1e-10, (case, b)
+
+
+@pytest.mark.parametrize("n", [4, 5, 7, 156, 157])
+def test_eigh_small_pipeline_sizes(n):
+    """mop_eigh through the packed tridiagonalisation at the sizes around its limits (n = 157 is the largest the
+    shared-memory path takes; 4 .. 7 have fewer rows than one row block per warp)."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((4, n, n)); A = 0.5 * (A + A.transpose(0, 2, 1))
+    A[1] = np.diag(np.arange(n, dtype=float))
+    evals, evecs, st = ops.eigh(T(A), "tridiag")
+    evals, evecs = evals.cpu().numpy(), evecs.cpu().numpy()
+    for b in range(4):
+        ref = np.linalg.eigvalsh(A[b])
+        scale = np.abs(ref).max()
+        assert np.abs(evals[b] - ref).max() <= 1e-13 * scale * max(1, n / 10)
+        Vb = evecs[b].T
+        assert np.abs(Vb.T @ Vb - np.eye(n)).max() < 1e-12
+        assert np.abs(A[b] @ Vb - Vb * evals[b]).max() < 1e-12 * scale * n

@@ -2,6 +2,7 @@
 # Round evidence on one B200 (run under gpurun): GPU tests, the bench line, the ncu launch list of the bench
 # command, one ncu --set full capture of the dominant kernels, and the config-5 bench line.
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c 'import __graft_entry__ as g; g.smoke(); print("smoke ok")' 2>&1 | tail -1
 python bench.py > gpurun_out/r1b_bench_c2_1gpu.json 2> gpurun_out/r1b_bench_err.log
 tail -c 300 gpurun_out/r1b_bench_c2_1gpu.json
 python bench.py --steps 2 --warmup 1 > gpurun_out/plain_bench.log 2>&1 &&
