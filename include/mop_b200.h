@@ -215,11 +215,13 @@ int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radi
 
 /* ---- restraint bias potentials --------------------------------------------------------------
  * Replaces calc_energy + torch.func.jacrev / hessian (Potential/potential.py:127-137) for StructKeepPotential
- * (kind 1), StructKeepPotentialv2 (kind 2; Potential/keep_potential.py) and StructKeepAnglePotential (kind 3;
- * Potential/keep_angle_potential.py:7-229).  terms: device array of nterm records of mop_bias_term_bytes()
+ * (kind 1), StructKeepPotentialv2 (kind 2; Potential/keep_potential.py), StructKeepAnglePotential (kind 3;
+ * Potential/keep_angle_potential.py:7-229) and StructKeepDihedralAnglePotential (kind 4;
+ * Potential/keep_dihedral_angle_potential.py:6-154).  terms: device array of nterm records of mop_bias_term_bytes()
  * bytes each: int32 kind, n1, n2, atoms[64] (0-based; kind 1: atoms i, j with n1 = n2 = 1; kind 2: the two
- * fragments back to back; kind 3: atoms i, j, k with n1 = 3), then double k (spring constant) and p (distance
- * in Angstrom, or angle in degrees).  E [B], grad [B][n], hess [B][n][n] are ADDED to (any may be NULL). */
+ * fragments back to back; kind 3: atoms i, j, k with n1 = 3; kind 4: atoms i, j, k, l with n1 = 4), then double
+ * k (spring constant) and p (distance in Angstrom; angle in degrees for kind 3; phi0 in RADIANS for kind 4 - the
+ * reference converts it in float32 or float64 depending on the caller, the host reproduces that).  E [B], grad [B][n], hess [B][n][n] are ADDED to (any may be NULL). */
 size_t mop_bias_term_bytes(void);
 int mop_bias_terms(int B, int natoms, int nterm, const void* terms, const double* xyz, double* E, double* grad,
                    double* hess, void* stream);

@@ -1,5 +1,6 @@
-"""Drop-ins for ``multioptpy.Potential.keep_potential.StructKeepPotential`` / ``StructKeepPotentialv2`` and
-``multioptpy.Potential.keep_angle_potential.StructKeepAnglePotential`` on the CUDA restraint kernel
+"""Drop-ins for ``multioptpy.Potential.keep_potential.StructKeepPotential`` / ``StructKeepPotentialv2``,
+``multioptpy.Potential.keep_angle_potential.StructKeepAnglePotential`` and
+``multioptpy.Potential.keep_dihedral_angle_potential.StructKeepDihedralAnglePotential`` on the CUDA restraint kernel
 (csrc/bias.cu).  ``calc_energy`` keeps the reference signature; ``calc_energy_grad_hess`` returns what the
 aggregator obtains from ``torch.func.jacrev`` / ``hessian`` (Potential/potential.py:127-137)."""
 from __future__ import annotations
@@ -60,3 +61,21 @@ class StructKeepAnglePotential(_Restraint):
     def _term(self, params):
         k, th = _pair(params, self.config, "keep_angle_spring_const", "keep_angle_angle")
         return (ops.BIAS_KEEP_ANGLE, [a - 1 for a in self.config["keep_angle_atom_pairs"]], [], k, th)
+
+
+def dihedral_phi0(params, config):
+    """(k, phi0 in radians) exactly as keep_dihedral_angle_potential.py:76-91 obtains them: without parameters
+    the configured angle becomes a float32 tensor before ``torch.deg2rad``; with parameters a tensor entry keeps
+    its own dtype (the aggregator passes float64) and a Python number becomes float32."""
+    if len(params) == 0:
+        return float(config["keep_dihedral_angle_spring_const"]), float(torch.deg2rad(torch.tensor(config["keep_dihedral_angle_angle"])))
+    deg = params[1]
+    if not isinstance(deg, torch.Tensor):
+        deg = torch.tensor(deg)
+    return float(params[0]), float(torch.deg2rad(deg.detach()))
+
+
+class StructKeepDihedralAnglePotential(_Restraint):
+    def _term(self, params):
+        k, phi0 = dihedral_phi0(params, self.config)
+        return (ops.BIAS_KEEP_DIHEDRAL, [a - 1 for a in self.config["keep_dihedral_angle_atom_pairs"]], [], k, phi0)

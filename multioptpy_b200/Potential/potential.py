@@ -69,6 +69,12 @@ class BiasPotentialCalculation:
                 if k != 0.0:
                     terms.append((ops.BIAS_KEEP_ANGLE, [a - 1 for a in force_data["keep_angle_atom_pairs"][i]], [],
                                   float(k), float(force_data["keep_angle_angle"][i])))
+        if N > 3:                                        # potential.py:779-789 (parameters go in as float64)
+            for i, k in enumerate(force_data.get("keep_dihedral_angle_spring_const", [])):
+                if k != 0.0:
+                    phi0 = float(torch.deg2rad(torch.tensor(float(force_data["keep_dihedral_angle_angle"][i]), dtype=torch.float64)))
+                    terms.append((ops.BIAS_KEEP_DIHEDRAL, [a - 1 for a in force_data["keep_dihedral_angle_atom_pairs"][i]],
+                                  [], float(k), phi0))
         if terms:
             dev = torch.device(self.device)
             xyz = torch.as_tensor(np.ascontiguousarray(geom)).reshape(1, N, 3).to(dev)

@@ -4,6 +4,9 @@
 //   kind 3  StructKeepAnglePotential (keep_angle_potential.py:7-229)     E = 1/2 k (theta - theta0)^2 with the
 //           reference's fifth-order expansions of acos^2 within 1e-3 rad of 0 and pi and its three
 //           theta0 branches
+//   kind 4  StructKeepDihedralAnglePotential (keep_dihedral_angle_potential.py:6-154)  E = 1/2 k wrap(phi - phi0)^2
+//           S(|n1|^2) S(|n2|^2) with the smoothstep collinearity switch; phi0 arrives in RADIANS (the reference
+//           converts degrees in float32 or float64 depending on the caller - the host mirror reproduces that)
 // The reference differentiates calc_energy with torch.func.jacrev / hessian on the CPU
 // (Potential/potential.py:127-137); here thread (term, coordinate pair) evaluates the same expression once in
 // hyper-dual arithmetic.  Results are ADDED to E, grad, hess (the aggregator sums all bias terms).
@@ -15,9 +18,9 @@ constexpr int BIAS_MAXA = 64;  // atoms per term (both fragments together)
 
 struct BiasTerm {
   int kind;
-  int n1, n2;             // atoms in fragment 1 / 2 (kind 1: 1, 1; kind 3: atoms i, j, k in `atoms`, n1 = 3)
+  int n1, n2;             // atoms in fragment 1 / 2 (kind 1: 1, 1; kind 3 / 4: atoms i, j, k (, l) in `atoms`, n1 = 3 / 4)
   int atoms[BIAS_MAXA];   // 0-based
-  double k, p;            // spring constant; r0 in Angstrom (kinds 1, 2) or theta0 in degrees (kind 3)
+  double k, p;            // spring constant; r0 in Angstrom (kinds 1, 2), theta0 in degrees (kind 3), phi0 in radians (kind 4)
 };
 
 __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) {
@@ -39,8 +42,38 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     const HD diff = d - hd_const(t.p / BOHR2ANG);
     return (0.5 * t.k) * (diff * diff);
   }
-  // kind 3
   const double PI = 3.141592653589793;
+  if (t.kind == 4) {
+    HD b1[3], b2[3], b3[3], n1[3], n2[3], m1[3];
+    for (int c = 0; c < 3; ++c) {
+      b1[c] = X(1, c) - X(0, c);
+      b2[c] = X(2, c) - X(1, c);
+      b3[c] = X(3, c) - X(2, c);
+    }
+    hd_cross(b1, b2, n1);
+    hd_cross(b2, b3, n2);
+    const HD n1sq = hd_dot(n1, n1), n2sq = hd_dot(n2, n2);
+    auto sw = [](HD val) -> HD {  // smoothstep on [1e-10, 1e-8]
+      HD tt = hd_clamp((1.0 / (1e-8 - 1e-10)) * (val - hd_const(1e-10)), 0.0, 1.0);
+      return tt * tt * (hd_const(3.0) - 2.0 * tt);
+    };
+    const HD s1 = sw(n1sq), s2 = sw(n2sq);
+    const HD in1 = hd_recip(hd_clamp_min(hd_sqrt(n1sq), 1e-12)), in2 = hd_recip(hd_clamp_min(hd_sqrt(n2sq), 1e-12));
+    const HD ib2 = hd_recip(hd_clamp_min(hd_sqrt(hd_dot(b2, b2)), 1e-12));
+    HD n1h[3], n2h[3], b2h[3];
+    for (int c = 0; c < 3; ++c) {
+      n1h[c] = n1[c] * in1;
+      n2h[c] = n2[c] * in2;
+      b2h[c] = b2[c] * ib2;
+    }
+    const HD x = hd_dot(n1h, n2h);
+    hd_cross(n1h, n2h, m1);
+    const HD y = hd_dot(m1, b2h);
+    HD diff = hd_atan2(y, x) - hd_const(t.p);
+    diff = diff - hd_const(2.0 * PI * rint(diff.f / (2.0 * PI)));  // wrap to [-pi, pi]; torch.round = half to even
+    return ((0.5 * t.k) * (diff * diff)) * s1 * s2;
+  }
+  // kind 3
   const double theta0 = t.p * (PI / 180.0);
   HD v1[3], v2[3];
   for (int c = 0; c < 3; ++c) {
@@ -91,7 +124,7 @@ __global__ void __launch_bounds__(128) k_bias_terms(int N, const BiasTerm* __res
   const int b = blockIdx.y, n = 3 * N;
   if (threadIdx.x == 0) t = terms[blockIdx.x];
   __syncthreads();
-  const int m = t.kind == 3 ? 3 : t.n1 + t.n2, nc = 3 * m;
+  const int m = t.kind == 3 ? 3 : (t.kind == 4 ? 4 : t.n1 + t.n2), nc = 3 * m;
   const double* xyz = xyz_all + (size_t)b * n;
   for (int w = threadIdx.x; w < nc * nc; w += blockDim.x) {
     const int ca = w / nc, cb = w - ca * nc;

@@ -26,6 +26,14 @@ __device__ __forceinline__ HD hd_acos(HD x) {
   const double om = 1.0 - x.f * x.f, s = sqrt(om);
   return hd_unary(x, acos(x.f), -1.0 / s, -x.f / (s * om));
 }
+// atan2(y, x): f_y = x / r2, f_x = -y / r2, f_yy = -2 x y / r2^2 = -f_xx, f_xy = (y^2 - x^2) / r2^2
+__device__ __forceinline__ HD hd_atan2(HD y, HD x) {
+  const double r2 = x.f * x.f + y.f * y.f, ir2 = 1.0 / r2;
+  const double fy = x.f * ir2, fx = -y.f * ir2;
+  const double fyy = -2.0 * x.f * y.f * ir2 * ir2, fxy = (y.f * y.f - x.f * x.f) * ir2 * ir2;
+  return HD{atan2(y.f, x.f), fy * y.a + fx * x.a, fy * y.b + fx * x.b,
+            fy * y.ab + fx * x.ab + fyy * (y.a * y.b - x.a * x.b) + fxy * (y.a * x.b + x.a * y.b)};
+}
 __device__ __forceinline__ HD hd_abs(HD x) { return x.f < 0.0 ? HD{-x.f, -x.a, -x.b, -x.ab} : x; }
 __device__ __forceinline__ HD hd_dot(const HD* u, const HD* v) { return u[0] * v[0] + u[1] * v[1] + u[2] * v[2]; }
 __device__ __forceinline__ void hd_cross(const HD* u, const HD* v, HD* c) {

@@ -615,7 +615,7 @@ def neb_fire_advance(vneb, force, prev_velocity, dt, reset):
 
 
 # ------------------------------------------------------------------ restraint bias potentials
-BIAS_KEEP, BIAS_KEEP_V2, BIAS_KEEP_ANGLE = 1, 2, 3
+BIAS_KEEP, BIAS_KEEP_V2, BIAS_KEEP_ANGLE, BIAS_KEEP_DIHEDRAL = 1, 2, 3, 4   # kind 4: p = phi0 in RADIANS
 BIAS_MAXA = 64
 
 

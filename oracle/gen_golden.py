@@ -628,6 +628,7 @@ def gen_keep():
     import torch
     kp = ref_shim.ref("Potential.keep_potential")
     ka = ref_shim.ref("Potential.keep_angle_potential")
+    kd = ref_shim.ref("Potential.keep_dihedral_angle_potential")
     elems, xyz = read_xyz(os.path.join(ref_shim.REF_ROOT, "test/aldol_rxn.xyz"))
     N = len(elems)
     lin = xyz.copy(); lin[1] = lin[0] + np.array([2.0, 0, 0]); lin[2] = lin[0] + np.array([4.3, 1e-5, 0])     # i=0? see cases
@@ -640,6 +641,12 @@ def gen_keep():
         ("angle_to_0", 3, [5, 4, 9], [], 0.2, 0.0, xyz),
         ("angle_near_pi", 3, [1, 0, 2], [], 0.5, 120.0, lin),      # atoms 1-0-2 almost linear: Taylor branch at pi
         ("angle_near_pi_180", 3, [1, 0, 2], [], 0.5, 180.0, lin),
+        # dihedrals (kind 4): p in degrees here; the blob stores the radians the reference derived from it.
+        # "_cfg" cases call calc_energy without parameters (configured angle -> float32 deg2rad)
+        ("dihedral_gen", 4, [1, 0, 4, 5], [], 0.3, 60.0, xyz),
+        ("dihedral_wrap", 4, [6, 4, 5, 7], [], 0.25, 175.0, xyz),
+        ("dihedral_neg", 4, [2, 0, 4, 9], [], 0.4, -123.4, xyz),
+        ("dihedral_cfg", 4, [1, 0, 4, 5], [], 0.3, 60.1, xyz),
     ]
     lin[1] = lin[0] + np.array([-2.0, 0, 0]); lin[2] = lin[0] + np.array([2.3, 4e-4, 0])
     blob = {"names": np.array([c[0] for c in cases])}
@@ -651,8 +658,16 @@ def gen_keep():
         elif kind == 2:
             pot = kp.StructKeepPotentialv2(keep_pot_v2_spring_const=k, keep_pot_v2_distance=p,
                                            keep_pot_v2_fragm1=[a + 1 for a in f1], keep_pot_v2_fragm2=[a + 1 for a in f2])
-        else:
+        elif kind == 3:
             pot = ka.StructKeepAnglePotential(keep_angle_atom_pairs=[a + 1 for a in f1], keep_angle_spring_const=k, keep_angle_angle=p)
+        else:
+            pot = kd.StructKeepDihedralAnglePotential(keep_dihedral_angle_atom_pairs=[a + 1 for a in f1],
+                                                      keep_dihedral_angle_spring_const=k, keep_dihedral_angle_angle=p)
+            if name.endswith("_cfg"):
+                par = []                                                      # configured angle: float32 deg2rad
+                blob[f"{name}/phi0"] = float(torch.deg2rad(torch.tensor(p)))
+            else:
+                blob[f"{name}/phi0"] = float(torch.deg2rad(par[1]))           # float64, as the aggregator passes it
         E = float(pot.calc_energy(g, par))
         gr = torch.func.jacrev(pot.calc_energy, argnums=0)(g, par).numpy()
         H = torch.func.hessian(pot.calc_energy, argnums=0)(g, par).reshape(3 * N, 3 * N).numpy()

@@ -1656,9 +1656,27 @@ class FIRENEBOracle:
 # ---------------------------------------------------------------------------------------------
 def _keep_energy_torch(geom, kind, f1, f2, k, p):
     """calc_energy of StructKeepPotential (kind 1), StructKeepPotentialv2 (kind 2), StructKeepAnglePotential
-    (kind 3) restated on a torch tensor (atoms 0-based; p = distance in Angstrom or angle in degrees)."""
+    (kind 3), StructKeepDihedralAnglePotential (kind 4; keep_dihedral_angle_potential.py:62-154) restated on a
+    torch tensor (atoms 0-based; p = distance in Angstrom, angle in degrees, or - kind 4 - phi0 in RADIANS as
+    the reference's float32 / float64 deg2rad left it)."""
     import math
     import torch
+    if kind == 4:
+        i1, i2, i3, i4 = f1
+        b1, b2, b3 = geom[i2] - geom[i1], geom[i3] - geom[i2], geom[i4] - geom[i3]
+        n1, n2 = torch.linalg.cross(b1, b2), torch.linalg.cross(b2, b3)
+        n1sq, n2sq = torch.sum(n1 ** 2), torch.sum(n2 ** 2)
+
+        def switch(val):
+            t = torch.clamp((val - 1e-10) / (1e-8 - 1e-10), 0.0, 1.0)
+            return t * t * (3.0 - 2.0 * t)
+        n1h = n1 / torch.clamp(torch.sqrt(n1sq), min=1e-12)
+        n2h = n2 / torch.clamp(torch.sqrt(n2sq), min=1e-12)
+        b2h = b2 / torch.clamp(torch.linalg.norm(b2), min=1e-12)
+        phi = torch.atan2(torch.sum(torch.linalg.cross(n1h, n2h) * b2h), torch.sum(n1h * n2h))
+        diff = phi - p
+        diff = diff - 2.0 * math.pi * torch.round(diff / (2.0 * math.pi))
+        return 0.5 * k * diff ** 2 * switch(n1sq) * switch(n2sq)
     if kind in (1, 2):
         v = geom[list(f1)].mean(dim=0) - geom[list(f2)].mean(dim=0)
         d = torch.clamp(torch.sqrt(torch.sum(v ** 2)), min=1e-12)

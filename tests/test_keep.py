@@ -23,6 +23,8 @@ def test_oracle_keep_vs_reference(golden_dir):
     z, names = _z(golden_dir)
     for name in names:
         k, p = z[f"{name}/kp"]
+        if int(z[f"{name}/kind"]) == 4:
+            p = float(z[f"{name}/phi0"])      # radians, float32- or float64-derived as the reference call did
         E, g, H = O.keep_egh(z[f"{name}/xyz"], int(z[f"{name}/kind"]), list(z[f"{name}/f1"]), list(z[f"{name}/f2"]), k, p)
         assert abs(E - float(z[f"{name}/E"])) <= 1e-14 * max(abs(E), 1e-300), name
         assert rel(g, z[f"{name}/g"]) < 1e-13 and rel(H, z[f"{name}/H"]) < 1e-13, name
@@ -30,7 +32,9 @@ def test_oracle_keep_vs_reference(golden_dir):
 
 @pytest.mark.gpu
 def test_gpu_keep_vs_golden(golden_dir):
-    from multioptpy_b200.Potential.keep_potential import StructKeepAnglePotential, StructKeepPotential, StructKeepPotentialv2
+    from multioptpy_b200.Potential.keep_potential import (StructKeepAnglePotential, StructKeepDihedralAnglePotential,
+                                                           StructKeepPotential, StructKeepPotentialv2)
+    import torch
     z, names = _z(golden_dir)
     for name in names:
         kind = int(z[f"{name}/kind"]); k, p = z[f"{name}/kp"]
@@ -40,8 +44,20 @@ def test_gpu_keep_vs_golden(golden_dir):
         elif kind == 2:
             pot = StructKeepPotentialv2(device="cuda:0", keep_pot_v2_spring_const=k, keep_pot_v2_distance=p,
                                         keep_pot_v2_fragm1=f1, keep_pot_v2_fragm2=f2)
-        else:
+        elif kind == 3:
             pot = StructKeepAnglePotential(device="cuda:0", keep_angle_atom_pairs=f1, keep_angle_spring_const=k, keep_angle_angle=p)
+        else:
+            pot = StructKeepDihedralAnglePotential(device="cuda:0", keep_dihedral_angle_atom_pairs=f1,
+                                                   keep_dihedral_angle_spring_const=float(k), keep_dihedral_angle_angle=float(p))   # Python floats, as the
+            # reference is configured: torch.tensor(float) is float32, torch.tensor(np.float64) would not be
+        if kind == 4:   # parameters as the reference call that made the golden: none (configured, float32) or float64 tensor
+            params = [] if name.endswith("_cfg") else torch.tensor([k, p], dtype=torch.float64)
+            E, g, H = pot.calc_energy_grad_hess(z[f"{name}/xyz"], params)
+            Eref = float(z[f"{name}/E"])
+            assert abs(float(E[0]) - Eref) <= RTOL * max(abs(Eref), 1e-12), name
+            assert rel(g[0].cpu().numpy(), z[f"{name}/g"].ravel()) < RTOL, name
+            assert rel(H[0].cpu().numpy(), z[f"{name}/H"]) < RTOL, name
+            continue
         E, g, H = pot.calc_energy_grad_hess(z[f"{name}/xyz"], [k, p])
         Eref = float(z[f"{name}/E"])
         assert abs(float(E[0]) - Eref) <= RTOL * max(abs(Eref), 1e-12), name
@@ -77,7 +93,8 @@ def test_gpu_keep_batched_vs_oracle():
     from multioptpy_b200 import ops, synthetic
     B, N = 6, 12
     xs = np.stack([synthetic.grid_geometry(N, np.random.default_rng(70 + b)) for b in range(B)])
-    terms = [(ops.BIAS_KEEP, [0], [5], 0.3, 1.8), (ops.BIAS_KEEP_V2, [1, 2, 3], [7, 8], 0.9, 2.2), (ops.BIAS_KEEP_ANGLE, [4, 6, 9], [], 0.25, 100.0)]
+    terms = [(ops.BIAS_KEEP, [0], [5], 0.3, 1.8), (ops.BIAS_KEEP_V2, [1, 2, 3], [7, 8], 0.9, 2.2), (ops.BIAS_KEEP_ANGLE, [4, 6, 9], [], 0.25, 100.0),
+             (ops.BIAS_KEEP_DIHEDRAL, [2, 5, 8, 11], [], 0.35, 1.1), (ops.BIAS_KEEP_DIHEDRAL, [0, 3, 7, 10], [], 0.2, -2.9)]
     E, g, H = ops.bias_terms(torch.from_numpy(xs).cuda(), ops.pack_bias_terms(terms, torch.device("cuda:0")), len(terms))
     for b in range(B):
         Er, gr, Hr = 0.0, np.zeros((N, 3)), np.zeros((3 * N, 3 * N))
