@@ -238,12 +238,17 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
       }
       double wa = INFINITY, wb = INFINITY;
       int side = 0;
+      const double dead_s = 1e-7 / s_tnorm;  // in units of ||T||
       for (int round = 0; round < 200; ++round) {
         const double width = h - l;
         // relative 2 eps plus the absolute floor eps ||T|| / 2 (dstebz: abstol = eps ||T||): below it the
         // computed p_n is rounding noise and the tridiagonal itself carries errors of that size
         const double tolw = 2.0 * TRI_EPS * fmax(fabs(l), fabs(h)) + 0.5 * TRI_EPS;
         if (!(width > tolw)) break;
+        // modes the RFO step discards (the whole bracket inside |lambda| < 1e-7, rsirfo.py:30 filters < 1e-6) -
+        // in practice the six TR/ROT null modes, one unresolvable cluster at 1e-17 ||T|| - need no more than
+        // 1e-13 ||T||: their vectors are never used and 1e-13 is far below every threshold applied to eigenvalues
+        if (width < 1e-13 && h < dead_s && l > -dead_s) break;
         const bool force = width > 0.5 * wa;
         wa = wb;
         wb = width;
