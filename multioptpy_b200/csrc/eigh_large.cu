@@ -661,8 +661,10 @@ __device__ void lg_inverse_iteration(const double* d, const double* e, int s, in
 }
 
 // ---- 2. eigenpairs of T, one CTA per matrix ---------------------------------------------------
-__global__ void __launch_bounds__(LG_EIG_THREADS, 1) k_lg_trieig(LgArgs a) {
-  constexpr int THREADS = LG_EIG_THREADS;
+// THREADS = 1024 for large n (three-way multisection, forward and backward sweeps on separate threads); 256 for
+// n <= 160, where a few hundred threads are all the phases can use and four CTAs per SM overlap their chains
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 1)) k_lg_trieig(LgArgs a) {
   constexpr int NW = THREADS / 32;
   extern __shared__ double sm[];
   const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1306,12 +1308,15 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     }
   }
   {
-    const int P = (3 * n <= mop::LG_EIG_THREADS) ? 3 : ((2 * n <= mop::LG_EIG_THREADS) ? 2 : 1);
-    (void)P;
-    const size_t smem = sizeof(double) * (12 * (size_t)np + (mop::LG_EIG_THREADS / 32) * 64 + 2) +
-                        sizeof(int) * 7 * (size_t)np;
-    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mop::k_lg_trieig<<<B, mop::LG_EIG_THREADS, smem, stream>>>(a);
+    const int thr = n <= 160 ? 256 : mop::LG_EIG_THREADS;
+    const size_t smem = sizeof(double) * (12 * (size_t)np + (thr / 32) * 64 + 2) + sizeof(int) * 7 * (size_t)np;
+    if (thr == 256) {
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mop::k_lg_trieig<256><<<B, 256, smem, stream>>>(a);
+    } else {
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig<mop::LG_EIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mop::k_lg_trieig<mop::LG_EIG_THREADS><<<B, mop::LG_EIG_THREADS, smem, stream>>>(a);
+    }
     MOP_CHECK_CUDA(cudaGetLastError());
   }
   return MOP_OK;
