@@ -661,10 +661,11 @@ __device__ void lg_inverse_iteration(const double* d, const double* e, int s, in
 }
 
 // ---- 2. eigenpairs of T, one CTA per matrix ---------------------------------------------------
-// THREADS = 1024 for large n (three-way multisection, forward and backward sweeps on separate threads); 256 for
-// n <= 160, where a few hundred threads are all the phases can use and four CTAs per SM overlap their chains
+// THREADS = 1024 for large n (three-way multisection, forward and backward sweeps on separate threads); 160 for
+// n <= 160, where one thread per eigenpair is all the phases can use and seven CTAs per SM overlap their chains
+// (P-RFO at n = 150, 1024 structures: 2.2 ms at 1024 threads, 1.3 ms at 256 x 4 CTAs, 1.1 ms at 160 x 7)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 1)) k_lg_trieig(LgArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 160 ? 7 : (THREADS <= 256 ? 4 : 1))) k_lg_trieig(LgArgs a) {
   constexpr int NW = THREADS / 32;
   extern __shared__ double sm[];
   const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1308,11 +1309,11 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     }
   }
   {
-    const int thr = n <= 160 ? 256 : mop::LG_EIG_THREADS;
+    const int thr = n <= 160 ? 160 : mop::LG_EIG_THREADS;
     const size_t smem = sizeof(double) * (12 * (size_t)np + (thr / 32) * 64 + 2) + sizeof(int) * 7 * (size_t)np;
-    if (thr == 256) {
-      MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mop::k_lg_trieig<256><<<B, 256, smem, stream>>>(a);
+    if (thr == 160) {
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mop::k_lg_trieig<160><<<B, 160, smem, stream>>>(a);
     } else {
       MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_trieig<mop::LG_EIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       mop::k_lg_trieig<mop::LG_EIG_THREADS><<<B, mop::LG_EIG_THREADS, smem, stream>>>(a);
