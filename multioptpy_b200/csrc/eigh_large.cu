@@ -1010,15 +1010,20 @@ __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a)
   // reflectors n-3 .. 0 in chunks of CH (descending); the next chunk travels from global memory to
   // registers while the current one is applied from shared memory
   const int last = n - 3;
-  constexpr int PFV = (CH * LG_MAX_N + LG_BT_THREADS - 1) / LG_BT_THREADS;  // values per thread and chunk
-  double pf[PFV];
+  // staging map: reflector u of the chunk, element j = tid (+ THREADS for n > THREADS) - no index division, and at
+  // small n only the first n threads load (the flat (u, j) = idx / n map spent ~1 k instructions per thread and
+  // chunk on divisions and masked slots: 7.0 ms of the 10.4 ms of mop_eigh at n = 150)
+  constexpr int JT = (LG_MAX_N + LG_BT_THREADS - 1) / LG_BT_THREADS;  // elements per thread and reflector
+  double pf[CH][JT];
   auto prefetch = [&](int kc) {
 #pragma unroll
-    for (int t = 0; t < PFV; ++t) {
-      const int idx = tid + t * LG_BT_THREADS;  // (u, j)
-      const int u = idx / n, j = idx - u * n;
+    for (int u = 0; u < CH; ++u) {
       const int k = kc - u;
-      pf[t] = (u < CH && k >= 0 && j >= k + 1) ? Vh[(size_t)k * n + j] : 0.0;
+#pragma unroll
+      for (int t = 0; t < JT; ++t) {
+        const int j = tid + t * LG_BT_THREADS;
+        pf[u][t] = (k >= 0 && j < n && j >= k + 1) ? Vh[(size_t)k * n + j] : 0.0;
+      }
     }
   };
   if (last >= 0) prefetch(last);
@@ -1028,11 +1033,12 @@ __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a)
   for (int kc = last; kc >= 0; kc -= CH) {
     double* vb = sm + (size_t)buf * CH * np;
 #pragma unroll
-    for (int t = 0; t < PFV; ++t) {
-      const int idx = tid + t * LG_BT_THREADS;
-      const int u = idx / n, j = idx - u * n;
-      if (u < CH) vb[u * np + j] = pf[t];
-    }
+    for (int u = 0; u < CH; ++u)
+#pragma unroll
+      for (int t = 0; t < JT; ++t) {
+        const int j = tid + t * LG_BT_THREADS;
+        if (j < n) vb[u * np + j] = pf[u][t];
+      }
     __syncthreads();
     if (kc - CH >= 0) prefetch(kc - CH);
     for (int u = 0; u < CH; ++u) {
