@@ -992,7 +992,10 @@ template <int NPL>
 __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a) {
   constexpr int NW = LG_BT_THREADS / 32;
   constexpr int CH = 4;  // reflectors staged per barrier
-  extern __shared__ double sm[];  // [2][CH][np] | tau [np]
+  constexpr int RS = 32 * NPL;    // staged reflector row: zero beyond n and up to the unit entry, so the dot and
+                                  // the update below need no masks (ncu: 132 instructions per reflector and warp
+                                  // with them, half of the kernel)
+  extern __shared__ double sm[];  // [2][CH][RS] | tau [np]
   const int n = a.n, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int np = (n + 3) & ~3;
   const int i = blockIdx.x * NW + wid;  // vector (column of Z)
@@ -1027,17 +1030,19 @@ __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a)
     }
   };
   if (last >= 0) prefetch(last);
-  double* tau_s = sm + 2 * (size_t)CH * np;  // a global load per reflector would sit on the critical path
+  double* tau_s = sm + 2 * (size_t)CH * RS;  // a global load per reflector would sit on the critical path
   for (int j = tid; j < n; j += LG_BT_THREADS) tau_s[j] = tau[j];
+  for (int j = tid; j < 2 * CH * RS; j += LG_BT_THREADS) sm[j] = 0.0;  // the slots j >= n stay zero
+  __syncthreads();
   int buf = 0;
   for (int kc = last; kc >= 0; kc -= CH) {
-    double* vb = sm + (size_t)buf * CH * np;
+    double* vb = sm + (size_t)buf * CH * RS;
 #pragma unroll
     for (int u = 0; u < CH; ++u)
 #pragma unroll
       for (int t = 0; t < JT; ++t) {
         const int j = tid + t * LG_BT_THREADS;
-        if (j < n) vb[u * np + j] = pf[u][t];
+        if (j < n) vb[u * RS + j] = pf[u][t];
       }
     __syncthreads();
     if (kc - CH >= 0) prefetch(kc - CH);
@@ -1046,16 +1051,18 @@ __global__ void __launch_bounds__(LG_BT_THREADS, 1) k_lg_backtransform(LgArgs a)
       if (k < 0) break;
       const double tk = tau_s[k];
       if (tk == 0.0) continue;
-      const double* vk = vb + u * np;
-      const int q0 = (k + 1) >> 5;
-      double dot = 0.0;
+      const double* vk = vb + u * RS + lane;
+      double vq[NPL], d0 = 0.0, d1 = 0.0;
 #pragma unroll
-      for (int q = 0; q < NPL; ++q)
-        if (q >= q0) dot = fma(lane + 32 * q < n ? vk[lane + 32 * q] : 0.0, z[q], dot);
-      dot = warp_sum(dot) * tk;
+      for (int q = 0; q < NPL; ++q) vq[q] = vk[32 * q];
 #pragma unroll
-      for (int q = 0; q < NPL; ++q)
-        if (q >= q0) z[q] = fma(-dot, lane + 32 * q < n ? vk[lane + 32 * q] : 0.0, z[q]);
+      for (int q = 0; q < NPL; q += 2) {
+        d0 = fma(vq[q], z[q], d0);
+        if (q + 1 < NPL) d1 = fma(vq[q + 1], z[q + 1], d1);
+      }
+      const double dot = warp_sum(d0 + d1) * tk;
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) z[q] = fma(-dot, vq[q], z[q]);
     }
     buf ^= 1;
   }
@@ -1190,7 +1197,7 @@ size_t mop_large_workspace_bytes(int B, int n) {
 template <int NPL>
 static int lg_launch_bt(int B, const mop::LgArgs& a, cudaStream_t stream) {
   const int np = (a.n + 3) & ~3;
-  const size_t smem = sizeof(double) * (2 * 4 + 1) * (size_t)np;
+  const size_t smem = sizeof(double) * (2 * 4 * (size_t)(32 * NPL) + (size_t)np);
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_backtransform<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((a.n + (mop::LG_BT_THREADS / 32) - 1) / (mop::LG_BT_THREADS / 32), B);
   mop::k_lg_backtransform<NPL><<<grid, mop::LG_BT_THREADS, smem, stream>>>(a);
@@ -1339,6 +1346,7 @@ int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* 
   if (rc != MOP_OK) return rc;
   a.evecs = evecs;
   const int npl = (n + 31) / 32;
+  if (npl <= 5) return lg_launch_bt<5>(B, a, stream);
   if (npl <= 8) return lg_launch_bt<8>(B, a, stream);
   if (npl <= 12) return lg_launch_bt<12>(B, a, stream);
   if (npl <= 16) return lg_launch_bt<16>(B, a, stream);
