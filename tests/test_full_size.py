@@ -109,3 +109,34 @@ def test_eigh_small_pipeline_sizes(n):
         Vb = evecs[b].T
         assert np.abs(Vb.T @ Vb - np.eye(n)).max() < 1e-12
         assert np.abs(A[b] @ Vb - Vb * evals[b]).max() < 1e-12 * scale * n
+
+
+def test_rsirfo_step_cuda_graph_replay():
+    """The library allocates nothing and never synchronises, so one optimizer step can be captured into a CUDA
+    graph and replayed: the replay on fresh inputs must reproduce the eager result bit for bit."""
+    B, natoms = 64, 30
+    n = 3 * natoms
+    x0, H0, g0, _ = synthetic.batch(1003, B, natoms)
+    method = ops.resolve_update_method("rsirfo_bfgs")
+    zero = torch.zeros(B, dtype=torch.float64, device=DEV)
+    # eager reference
+    He, ste = T(H0), ops.new_rsirfo_state(B, 0.5, DEV)
+    ref = ops.rsirfo_step(He, T(x0), T(g0), T(g0), ste, method=method, Be=zero)
+    ref_mv, ref_st = ref["move"].clone(), ste.clone()
+    # static buffers, warm-up on the capture stream, capture, replay on the real inputs
+    Hs, xs, gs = T(H0 * 1.01), T(x0), T(g0 * 0.5)
+    sts = ops.new_rsirfo_state(B, 0.5, DEV)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        out = ops.rsirfo_step(Hs, xs, gs, gs, sts, method=method, Be=zero)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=side):
+        out = ops.rsirfo_step(Hs, xs, gs, gs, sts, method=method, Be=zero, out=out)
+    Hs.copy_(T(H0)); gs.copy_(T(g0)); sts.copy_(ops.new_rsirfo_state(B, 0.5, DEV))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["move"], ref_mv)
+    assert torch.equal(sts, ref_st)
