@@ -83,6 +83,8 @@ enum {
 #define MOP_ST_EIG_NOCONV (1 << 11)     /* eigensolver hit its sweep / iteration limit    */
 #define MOP_ST_EIG_FALLBACK (1 << 12)   /* robust Jacobi fallback produced the spectrum   */
 #define MOP_ST_NO_HISTORY (1 << 13)     /* first call: no previous point, update skipped  */
+#define MOP_ST_UPD_REJECTED (1 << 14)   /* P-RFO: updated spectrum > 1e6, update reverted (rsprfo.py:1247) */
+#define MOP_ST_LINDH_NO_K (1 << 15)     /* Lindh: non-zero gradient but no internal gradient, K term omitted */
 
 /* eigensolver selection */
 #define MOP_EIGH_AUTO 0
@@ -167,7 +169,9 @@ int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode, in
  * Per-structure state: state [B][MOP_PRFO_STATE] doubles (column 0 = trust radius, initialise
  * to 0.1 for saddle searches / 0.5 for minimisations, rest 0), prev_grad / prev_move / ts_vec
  * [B][n] scratch owned by the caller across calls.  pre_move, x_prev, Bg_prev, Hbias may be NULL.
- * Not reproduced: the rejection of an update whose eigenvalues exceed 1e6 (rsprfo.py:1242-1250). */
+ * An update whose spectrum exceeds 1e6 is reverted bit-exactly (rsprfo.py:1242-1250; MOP_ST_UPD_REJECTED): the
+ * Frobenius norm decides almost every structure (||H||_F <= 1e6 accepts, ||H||_F > 1e6 sqrt(n) rejects), the
+ * band between them goes through the Jacobi eigensolver. */
 #define MOP_PRFO_STATE 8
 size_t mop_rsprfo_workspace_bytes(int B, int n, int eigh_algo);
 int mop_rsprfo_step(int B, int n, int method, int saddle_order, int eigh_algo, double trust_min,

@@ -9,8 +9,12 @@ indexes it by a bond/angle/dihedral counter although its rows are atom pairs —
 coordinates changes it by O(1), so that gradient has no reproducible value.  ``main``
 therefore adds ``K`` only when the caller supplies the internal gradient (``int_grad=``, e.g. the
 reference's own ``cartgrad2RICgrad`` output); without it ``main`` equals the reference for a zero
-gradient."""
+gradient.  When a NON-ZERO ``cart_gradient`` arrives without ``int_grad`` the omission is reported: a
+``UserWarning`` and ``ops.ST_LINDH_NO_K`` in ``last_status`` (one int32 per structure, OR-ed with the
+kernel's table-overflow bit 1)."""
 from __future__ import annotations
+
+import warnings
 
 import numpy as np
 import torch
@@ -37,6 +41,20 @@ class LindhApproxHessian:
     def __init__(self, device="cuda"):
         self.force_const_list = [0.45, 0.15, 0.005]
         self.device = torch.device(device)
+        self.last_status = None
+
+    def _k_omitted(self, cart_gradient):
+        if cart_gradient is None:
+            return False
+        if isinstance(cart_gradient, torch.Tensor):
+            nz = bool((cart_gradient != 0).any().item())
+        else:
+            nz = bool(np.any(np.asarray(cart_gradient, dtype=np.float64) != 0.0))
+        if nz:
+            warnings.warn("LindhApproxHessian(B200): non-zero cart_gradient without int_grad - the reference's K term "
+                          "(second derivatives times an internal gradient from a singular solve, SURVEY H2) is "
+                          "omitted; pass int_grad= to add it", UserWarning, stacklevel=3)
+        return nz
 
     def guess_lindh_diagonal(self, coord, element_list):
         """Diagonal of guess_lindh_hessian (lindh.py:79-143): force constant per atom pair."""
@@ -48,10 +66,14 @@ class LindhApproxHessian:
         prm = lindh_atom_params(element_list)
         if int_grad is not None:
             return self._main_with_int_grad(coord, element_list, prm, int_grad)
+        no_k = ops.ST_LINDH_NO_K if self._k_omitted(cart_gradient) else 0
         if isinstance(coord, torch.Tensor):
-            return ops.lindh_hessian(coord, prm)[0]
+            H, _, _, status = ops.lindh_hessian(coord, prm)
+            self.last_status = status | no_k       # bit 0: table capacity exceeded (caller's to check, no host sync here)
+            return H
         xyz = torch.as_tensor(np.ascontiguousarray(np.asarray(coord, dtype=np.float64)).reshape(1, -1, 3)).to(self.device)
         H, _, _, status = ops.lindh_hessian(xyz, prm)
+        self.last_status = status | no_k
         if int(status[0].item()) != 0:
             raise ops.MopError("Lindh model Hessian: connectivity table capacity exceeded")
         return H[0].cpu().numpy()

@@ -114,6 +114,7 @@ class RSIRFO:
     def _ensure_state(self, B):
         if self.Initialization or self._state is None or self._state.shape[0] != B:
             self._state = ops.new_rsirfo_state(B, self.trust_radius, self.device)
+            self._out = None     # result buffers belong to the batch shape of the state
             self.predicted_energy_changes = []
             self.actual_energy_changes = []
             self.prev_geometry = None
@@ -144,6 +145,8 @@ class RSIRFO:
             x_prev, g_prev = x_prev.squeeze(-1), g_prev.squeeze(-1)
         if not isinstance(Be, torch.Tensor):
             Be = torch.full((B,), float(Be), dtype=torch.float64, device=x.device)
+        if self._out is not None and tuple(self._out["move"].shape) != (B, n):
+            self._out = None
         self._out = ops.rsirfo_step(
             self.hessian, x, Bg, g, self._state, method=self._method_id,
             saddle_order=self.saddle_order, neb_mode=self.NEB_mode, Hbias=self.bias_hessian,

@@ -79,6 +79,7 @@ class EnhancedRSPRFO:
             z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
             self._st = dict(state=z(B, ops.PRFO_STATE), prev_grad=z(B, n), prev_move=z(B, n), ts_vec=z(B, n))
             self._st["state"][:, 0] = self.trust_radius_initial
+            self._out = None     # result buffers belong to the batch shape of the state
             self.trust_radius = self.trust_radius_initial
             self.predicted_energy_changes = []
             self.iter = 0
@@ -111,6 +112,8 @@ class EnhancedRSPRFO:
             have = lambda a: a is not None and len(a) > 0
             Be = torch.tensor([float(B_e)], dtype=torch.float64, device=dev)
         first = self._ensure(B, n, dev)
+        if tensor_mode and self._out is not None and tuple(self._out["move"].shape) != (B, n):
+            self._out = None
         hist = (not first) and have(pre_B_g) and have(pre_geom)
         self._out = ops.rsprfo_step(
             H, x, Bg, self._st, method=self._method_id, saddle_order=self.saddle_order, Hbias=Hb,

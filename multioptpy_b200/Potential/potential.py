@@ -1,6 +1,7 @@
 """Drop-in for ``multioptpy.Potential.potential.BiasPotentialCalculation`` (Potential/potential.py:53-202)
 restricted to the potentials built on the device: sums the bias energy / gradient / Hessian of every AFIR
-term and of the keep (distance, fragment distance, angle) restraints of ``force_data``; other potentials raise.
+term and of the keep (distance, fragment distance, angle, dihedral) restraints of ``force_data``; every other
+potential the reference would activate raises ``MopError`` (``active_keys`` walks the reference's key list).
 The reference's side effects (.npy / .log files, :144,191-192) are not reproduced."""
 from __future__ import annotations
 
@@ -11,9 +12,44 @@ from .._lib import MopError
 from .. import ops
 from .AFIR_potential import AFIRPotential
 
-_OTHER_KEYS = ["linear_mechano_force", "linear_mechano_force_v2", "flux_pot_const",
-               "keep_angle_v2_spring_const", "keep_dihedral_angle_v2_spring_const", "repulsive_potential_well_scale",
-               "gaussian_potential_target", "nano_reactor_potential", "asymmetric_ellipsoidal_repulsive_potential_eps"]
+# Every activation key of the reference aggregator (potential.py:228-300,434-900) with the reference's OWN activation
+# test: "nz" = an entry != 0.0, "all" = an entry (a list) without a 0.0 in it, "len" = a non-empty list.  Keys handled
+# on the device are in _HANDLED; any other ACTIVE key raises instead of being silently dropped.
+_ACTIVATION = {
+    "AFIR_gamma": "all", "keep_pot_spring_const": "nz", "keep_pot_v2_spring_const": "all",
+    "keep_angle_spring_const": "nz", "keep_dihedral_angle_spring_const": "nz",
+    "anharmonic_keep_pot_spring_const": "nz", "well_pot_wall_energy": "nz", "wall_well_pot_wall_energy": "nz",
+    "void_point_well_pot_wall_energy": "nz", "around_well_pot_wall_energy": "nz",
+    "keep_angle_v2_spring_const": "all", "keep_out_of_plain_angle_spring_const": "nz",
+    "keep_dihedral_angle_v2_spring_const": "all", "keep_dihedral_angle_cos_potential_const": "all",
+    "keep_out_of_plain_angle_v2_spring_const": "all", "void_point_pot_spring_const": "nz",
+    "linear_mechano_force": "nz", "linear_mechano_force_v2": "nz", "flux_pot_const": "len",
+    "value_range_upper_const": "nz", "universal_pot_const": "nz", "repulsive_potential_v2_well_scale": "nz",
+    "repulsive_potential_well_scale": "nz", "repulsive_potential_gaussian_LJ_well_depth": "nz",
+    "repulsive_potential_gaussian_gau_well_depth": "nz", "cone_potential_well_value": "nz",
+    "spacer_model_potential_well_depth": "nz", "gaussian_potential_target": "len", "nano_reactor_potential": "len",
+    "asymmetric_ellipsoidal_repulsive_potential_eps": "len", "asymmetric_ellipsoidal_repulsive_potential_v2_eps": "len",
+}
+_HANDLED = {"AFIR_gamma", "keep_pot_spring_const", "keep_pot_v2_spring_const", "keep_angle_spring_const",
+            "keep_dihedral_angle_spring_const"}
+
+
+def active_keys(force_data):
+    """Activation keys of ``force_data`` that the reference aggregator would turn into a potential term."""
+    out = []
+    for key, rule in _ACTIVATION.items():
+        val = force_data.get(key, [])
+        if val is None or len(val) == 0:
+            continue
+        if rule == "len":
+            on = True
+        elif rule == "nz":
+            on = any(v != 0.0 for v in val)
+        else:
+            on = any(0.0 not in list(np.atleast_1d(np.asarray(v, dtype=object))) for v in val)
+        if on:
+            out.append(key)
+    return out
 
 
 def gradually_change_param(param_1, param_2, iter):
@@ -34,9 +70,10 @@ class BiasPotentialCalculation:
 
     def main(self, e, g, geom_num_list, element_list, force_data, pre_B_g="", iter="", initial_geom_num_list=""):
         """-> (bias_grad (N,3), B_e, B_g (N,3), bias_hessian (3N,3N)), potential.py:202."""
-        for key in _OTHER_KEYS:
-            if len(force_data.get(key, [])) > 0 and any(np.ravel(np.asarray(force_data[key], dtype=object)) != 0):
-                raise MopError(f"bias potential '{key}' is outside the B200 hot-path scope (AFIR only)")
+        for key in active_keys(force_data):
+            if key not in _HANDLED:
+                raise MopError(f"bias potential '{key}' is active but not built on the device "
+                               f"(handled: {sorted(_HANDLED)}); refusing to drop it silently")
         geom = np.asarray(geom_num_list, dtype=np.float64)
         N = geom.shape[0]
         bias_grad = np.zeros_like(geom)

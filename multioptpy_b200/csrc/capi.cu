@@ -11,12 +11,12 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
                               const double* g, const double* gp, const double* state, int state_stride,
                               double* delta_out, int32_t* status, cudaStream_t stream);
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
-                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
                              cudaStream_t stream);
 size_t mop_project_scratch_bytes(int B, int n);
 int mop_launch_project_trrot_split(int B, int n, const double* H, const double* Hbias, const double* x,
-                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, void* scratch,
-                                   size_t scratch_bytes, cudaStream_t stream);
+                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
+                                   void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t mop_hessian_update_scratch_bytes(int B, int n);
 int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guards, double* H, const double* s,
                                     const double* y, const double* x, const double* xp, const double* g,
@@ -272,18 +272,25 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
     const size_t chunk_bytes = sizeof(double) * bc * n2;
     if (x_prev && method != MOP_UPD_NONE) {
       // scratch: the projected-Hessian buffer of this chunk is not live yet
-      rc = mop_launch_hessian_update_split(bc, n, method, 1, 1, Hc, nullptr, nullptr, x + (size_t)b0 * n,
+      // (tiny n: the multi-CTA scratch, B (4 n + 24) doubles, does not fit the Hp slab - one CTA per structure)
+      const size_t upd_scr = split_ok ? chunk_bytes : nn;
+      rc = upd_scr >= mop_hessian_update_scratch_bytes(bc, n)
+               ? mop_launch_hessian_update_split(bc, n, method, 1, 1, Hc, nullptr, nullptr, x + (size_t)b0 * n,
+                                                 x_prev + (size_t)b0 * n, g + (size_t)b0 * n, g_prev + (size_t)b0 * n,
+                                                 state + (size_t)b0 * MOP_RSIRFO_STATE, MOP_RSIRFO_STATE, nullptr,
+                                                 status + b0, split_ok ? (void*)(Hp + b0 * n2) : (void*)Hp, upd_scr,
+                                                 stream)
+               : mop_launch_hessian_update(bc, n, method, 1, 1, Hc, nullptr, nullptr, x + (size_t)b0 * n,
                                            x_prev + (size_t)b0 * n, g + (size_t)b0 * n, g_prev + (size_t)b0 * n,
                                            state + (size_t)b0 * MOP_RSIRFO_STATE, MOP_RSIRFO_STATE, nullptr,
-                                           status + b0, split_ok ? (void*)(Hp + b0 * n2) : (void*)Hp,
-                                           split_ok ? chunk_bytes : nn, stream);
+                                           status + b0, stream);
       if (rc != MOP_OK) return rc;
     }
     rc = split_ok ? mop_launch_project_trrot_split(bc, n, Hc, Hbc, x + (size_t)b0 * n, Bg + (size_t)b0 * n,
-                                                   Hp + b0 * n2, gp + (size_t)b0 * n, status + b0, evecs + b0 * n2,
+                                                   Hp + b0 * n2, gp + (size_t)b0 * n, status + b0, 0, evecs + b0 * n2,
                                                    chunk_bytes, stream)
                   : mop_launch_project_trrot(bc, n, Hc, Hbc, x + (size_t)b0 * n, Bg + (size_t)b0 * n, Hp + b0 * n2,
-                                             gp + (size_t)b0 * n, status + b0, stream);
+                                             gp + (size_t)b0 * n, status + b0, 0, stream);
     if (rc != MOP_OK) return rc;
   }
   if (pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG)

@@ -372,7 +372,7 @@ k_lindh(int N, const double* __restrict__ xyz_all, const double* __restrict__ pr
 
 // forward declaration (project.cu)
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
-                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
                              cudaStream_t stream);
 
 static size_t mh_smem(int N) {
@@ -456,7 +456,7 @@ extern "C" int mop_fischer_hessian(int B, int natoms, const double* xyz, const d
   if (counts_out)
     MOP_CHECK_CUDA(cudaMemcpyAsync(counts_out, counts, sizeof(int32_t) * 3 * (size_t)B,
                                    cudaMemcpyDeviceToDevice, stream));
-  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, stream);
+  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, 0, stream);
 }
 
 
@@ -515,5 +515,5 @@ extern "C" int mop_lindh_hessian(int B, int natoms, const double* xyz, const dou
   if (counts_out)
     MOP_CHECK_CUDA(cudaMemcpyAsync(counts_out, counts, sizeof(int32_t) * 3 * (size_t)B,
                                    cudaMemcpyDeviceToDevice, stream));
-  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, stream);
+  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, 0, stream);
 }

@@ -130,6 +130,50 @@ k_prfo_prev(int n, const double* __restrict__ Hp_all, const double* __restrict__
   st[MOP_PS_TRUST] = trust;
 }
 
+// Update rejection of EnhancedRSPRFO.update_hessian (rsprfo.py:1239-1250): the reference computes eigvalsh of the
+// updated Hessian and keeps the OLD Hessian when max |lambda| > 1e6.  ||H||_2 <= ||H||_F <= sqrt(n) ||H||_2, so the
+// Frobenius norm settles every structure outside the band 1e6 < ||H||_F <= 1e6 sqrt(n); structures inside it are
+// flagged for the Jacobi eigensolver (flag = MOP_ST_EIG_FALLBACK, the bit its only_flagged filter tests).  A
+// non-finite Hessian is accepted, as in the reference (eigvalsh returns NaN, and NaN > 1e6 is false).
+__global__ void __launch_bounds__(512) k_prfo_guard(int n, const double* __restrict__ H, const int32_t* __restrict__ status,
+                                                    int32_t* __restrict__ flag) {
+  __shared__ double scratch[40];
+  const size_t b = blockIdx.x, nn = (size_t)n * n;
+  if (!(status[b] & MOP_ST_UPDATED)) {  // block-uniform
+    if (threadIdx.x == 0) flag[b] = 0;
+    return;
+  }
+  double acc = 0.0;
+  for (size_t e = threadIdx.x; e < nn; e += blockDim.x) {
+    const double x = H[b * nn + e];
+    acc = fma(x, x, acc);
+  }
+  const double fro = sqrt(block_sum(acc, scratch));
+  if (threadIdx.x == 0) {
+    int f = 0;
+    if (isfinite(fro) && fro > 1e6) f = (fro > 1e6 * sqrt((double)n)) ? 2 : MOP_ST_EIG_FALLBACK;
+    flag[b] = f;
+  }
+}
+
+// flag 2: reject; flag MOP_ST_EIG_FALLBACK: reject when the Jacobi spectrum of the updated Hessian exceeds 1e6
+__global__ void k_prfo_revert(int n, double* __restrict__ H, const double* __restrict__ Hold,
+                              const int32_t* __restrict__ flag, const double* __restrict__ evals,
+                              int32_t* __restrict__ status) {
+  const size_t b = blockIdx.y, nn = (size_t)n * n;
+  const int f = flag[b];
+  if (f == 0) return;
+  if (f != 2) {
+    double mx = 0.0;
+    for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(evals[b * n + i]));  // NaN-free by construction (fmax drops NaN)
+    if (!(mx > 1e6)) return;
+  }
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x)
+    H[b * nn + e] = Hold[b * nn + e];
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    status[b] = (status[b] & ~(MOP_ST_UPDATED | MOP_ST_UPD_TERM_ZEROED)) | MOP_ST_UPD_REJECTED;
+}
+
 __global__ void k_sum_sym(int n, const double* __restrict__ H, const double* __restrict__ Hb,
                           double* __restrict__ out) {
   const size_t b = blockIdx.y;
@@ -431,12 +475,13 @@ int mop_launch_hessian_update(int B, int n, int method, int mode, int guards, do
                               const double* g, const double* gp, const double* state, int state_stride,
                               double* delta_out, int32_t* status, cudaStream_t stream);
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
-                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
                              cudaStream_t stream);
 size_t mop_project_scratch_bytes(int B, int n);
+size_t mop_hessian_update_scratch_bytes(int B, int n);
 int mop_launch_project_trrot_split(int B, int n, const double* H, const double* Hbias, const double* x,
-                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, void* scratch,
-                                   size_t scratch_bytes, cudaStream_t stream);
+                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
+                                   void* scratch, size_t scratch_bytes, cudaStream_t stream);
 int mop_launch_hessian_update_split(int B, int n, int method, int mode, int guards, double* H, const double* s,
                                     const double* y, const double* x, const double* xp, const double* g,
                                     const double* gp, const double* state, int state_stride, double* delta_out,
@@ -502,8 +547,8 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   // projected gradient (current geometry) and projected pre-update Hessian for the reduction ratio
   // small batches: the multi-CTA projection fills the GPU; large ones: one CTA per structure is as fast
-  int rc = B <= 2 * 148 ? mop_launch_project_trrot_split(B, n, H, Hbias, x, Bg, A, gp, status, evecs, nn, stream)
-                        : mop_launch_project_trrot(B, n, H, Hbias, x, Bg, A, gp, status, stream);
+  int rc = B <= 2 * 148 ? mop_launch_project_trrot_split(B, n, H, Hbias, x, Bg, A, gp, status, 1, evecs, nn, stream)
+                        : mop_launch_project_trrot(B, n, H, Hbias, x, Bg, A, gp, status, 1, stream);
   if (rc != MOP_OK) return rc;
   {
     const size_t smem = sizeof(double) * (size_t)n;
@@ -512,10 +557,25 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
     MOP_CHECK_CUDA(cudaGetLastError());
   }
   if (x_prev && method != MOP_UPD_NONE) {  // biased gradients, small-change skip only (rsprfo.py:1203-1213)
+    // the pre-update Hessian is kept in A (dead since k_prfo_prev) until the rejection test has passed
+    MOP_CHECK_CUDA(cudaMemcpyAsync(A, H, sizeof(double) * (size_t)B * n * n, cudaMemcpyDeviceToDevice, stream));
     // scratch: the eigenvector buffer is not live yet
-    rc = mop_launch_hessian_update_split(B, n, method, 1, 2, H, nullptr, nullptr, x, x_prev, Bg, Bg_prev, state,
-                                         MOP_PRFO_STATE, nullptr, status, evecs, nn, stream);
+    rc = nn >= mop_hessian_update_scratch_bytes(B, n)
+             ? mop_launch_hessian_update_split(B, n, method, 1, 2, H, nullptr, nullptr, x, x_prev, Bg, Bg_prev, state,
+                                               MOP_PRFO_STATE, nullptr, status, evecs, nn, stream)
+             : mop_launch_hessian_update(B, n, method, 1, 2, H, nullptr, nullptr, x, x_prev, Bg, Bg_prev, state,
+                                         MOP_PRFO_STATE, nullptr, status, stream);
     if (rc != MOP_OK) return rc;
+    // rsprfo.py:1239-1250: revert an update whose spectrum exceeds 1e6
+    int32_t* rflag = (int32_t*)Xg;  // [B] ints; the rotated-vector slots are not live yet
+    mop::k_prfo_guard<<<B, 512, 0, stream>>>(n, H, status, rflag);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    const size_t jac = al256(mop_jacobi_workspace_bytes(B, n));
+    rc = mop_launch_eigh_jacobi(B, n, H, evals, evecs, nullptr, rflag, ework, jac, stream);  // almost always empty
+    if (rc != MOP_OK) return rc;
+    dim3 rgrid(32, B);
+    mop::k_prfo_revert<<<rgrid, 256, 0, stream>>>(n, H, A, rflag, evals, status);
+    MOP_CHECK_CUDA(cudaGetLastError());
   }
   {
     dim3 grid(148, B);

@@ -7,8 +7,11 @@
 // which is O(n^2) and streams the matrix twice (W pass + output pass).
 // T (n x k, k <= 6) is the reference's CLASSICAL Gram-Schmidt basis (drop 1e-10).
 // The gradient projection g - Q Q^T g (Optimizer/rsirfo.py:128-190, reduced QR)
-// spans the same space when the six vectors are independent; for rank-deficient
-// sets (linear molecules) the GS basis is used and MOP_ST_TRROT_RANKDEF is set.
+// spans the same space when the six vectors are independent.  For rank-deficient
+// sets (two atoms, linear molecules; MOP_ST_TRROT_RANKDEF) the reference's Q keeps
+// SIX orthonormal columns - Householder QR never drops one, the column of the
+// dependent vector is whatever the earlier reflectors make of a unit vector - so
+// the kernel replays LAPACK's dgeqr2 + dorg2r there (project_grad_qr below).
 #include "common.cuh"
 
 namespace mop {
@@ -67,8 +70,86 @@ __device__ int build_trrot_basis(int n, const double* __restrict__ x, double* T,
   return k;
 }
 
+// Gradient projection for RANK-DEFICIENT TR/ROT sets, as the reference computes it: numpy.linalg.qr(A, 'reduced') of
+// the 3N x 6 matrix of raw vectors is LAPACK dgeqrf (unblocked dgeqr2 for six columns) + dorgqr (dorg2r), i.e.
+// K = min(3N, 6) Householder reflectors and ALWAYS K orthonormal columns.  A dependent column leaves a zero (or
+// rounding-noise) residual: tau = 0 for an exact zero, and Q's column is the image of a unit vector under the earlier
+// reflectors - not in the TR/ROT span.  rule 0 = RSIRFO._project_grad_tr_rot (rsirfo.py:172-188): every column is
+// projected out (for two atoms Q is 6 x 6 orthogonal and the projected gradient is rounding noise); rule 1 =
+// EnhancedRSPRFO._project_grad_tr_rot (rsprfo.py:244-285): fewer than three atoms -> gradient returned as is, columns
+// with |R_jj| <= 1e-10 dropped.  A [6][np] holds the raw vectors and is destroyed.  Whole CTA; scratch >= 40 doubles.
+__device__ void project_grad_qr(int n, double* A, int np, const double* __restrict__ g, double* __restrict__ gp,
+                                int rule, double* scratch) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (rule == 1 && n < 9) {
+    for (int i = tid; i < n; i += nt) gp[i] = g[i];
+    return;
+  }
+  const int K = n < 6 ? n : 6;
+  double tau[6], rdiag[6];
+  for (int j = 0; j < K; ++j) {  // dgeqr2: dlarfg on column j, then H_j applied to the columns to its right
+    double* aj = A + (size_t)j * np;
+    double p = 0.0;
+    for (int i = j + 1 + tid; i < n; i += nt) p = fma(aj[i], aj[i], p);
+    const double xnorm = sqrt(block_sum(p, scratch));
+    const double alpha = aj[j];
+    __syncthreads();
+    double t = 0.0, beta = alpha;
+    if (xnorm != 0.0) {
+      beta = -copysign(hypot(alpha, xnorm), alpha);
+      t = (beta - alpha) / beta;
+      const double sc = 1.0 / (alpha - beta);
+      for (int i = j + 1 + tid; i < n; i += nt) aj[i] *= sc;
+    }
+    tau[j] = t;
+    rdiag[j] = beta;
+    __syncthreads();
+    if (t != 0.0)
+      for (int c = j + 1; c < 6; ++c) {
+        double* ac = A + (size_t)c * np;
+        double q = 0.0;
+        for (int i = j + 1 + tid; i < n; i += nt) q = fma(aj[i], ac[i], q);
+        const double wc = t * (block_sum(q, scratch) + ac[j]);
+        for (int i = j + 1 + tid; i < n; i += nt) ac[i] = fma(-wc, aj[i], ac[i]);
+        __syncthreads();
+        if (tid == 0) ac[j] -= wc;
+        __syncthreads();
+      }
+  }
+  for (int j = K - 1; j >= 0; --j) {  // dorg2r: Q = H_0 ... H_{K-1} (first K columns), built from the last reflector back
+    double* aj = A + (size_t)j * np;
+    const double t = tau[j];
+    if (t != 0.0)
+      for (int c = j + 1; c < K; ++c) {
+        double* qc = A + (size_t)c * np;
+        double q = 0.0;
+        for (int i = j + 1 + tid; i < n; i += nt) q = fma(aj[i], qc[i], q);
+        const double wc = t * (block_sum(q, scratch) + qc[j]);
+        for (int i = j + 1 + tid; i < n; i += nt) qc[i] = fma(-wc, aj[i], qc[i]);
+        __syncthreads();
+        if (tid == 0) qc[j] -= wc;
+        __syncthreads();
+      }
+    for (int i = tid; i < n; i += nt) aj[i] = (i > j) ? -t * aj[i] : (i == j ? 1.0 - t : 0.0);
+    __syncthreads();
+  }
+  double cf[6];
+  for (int j = 0; j < K; ++j) {
+    double q = 0.0;
+    for (int i = tid; i < n; i += nt) q = fma(A[(size_t)j * np + i], g[i], q);
+    cf[j] = block_sum(q, scratch);
+    if (rule == 1 && !(fabs(rdiag[j]) > 1e-10)) cf[j] = 0.0;
+  }
+  for (int i = tid; i < n; i += nt) {
+    double part = 0.0;
+    for (int j = 0; j < K; ++j) part = fma(A[(size_t)j * np + i], cf[j], part);
+    gp[i] = g[i] - part;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(PRJ_THREADS)
-k_project_trrot(int n, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
+k_project_trrot(int n, int grad_rule, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
                 const double* __restrict__ x_all, const double* __restrict__ g_all,
                 double* __restrict__ Hp_all, double* __restrict__ gp_all,
                 int32_t* __restrict__ status) {
@@ -95,16 +176,20 @@ k_project_trrot(int n, const double* __restrict__ Hall, const double* __restrict
   // ---- gradient: gp = g - T (T^T g) -----------------------------------------
   if (g_all && gp_all) {
     const double* g = g_all + (size_t)b * n;
-    double cf[6];
-    for (int j = 0; j < k; ++j) {
-      double p = 0.0;
-      for (int i = tid; i < n; i += PRJ_THREADS) p = fma(T[j * np + i], g[i], p);
-      cf[j] = block_sum(p, scratch);
-    }
-    for (int i = tid; i < n; i += PRJ_THREADS) {
-      double part = 0.0;
-      for (int j = 0; j < k; ++j) part = fma(T[j * np + i], cf[j], part);
-      gp_all[(size_t)b * n + i] = g[i] - part;
+    if (k < 6) {  // block-uniform: the reference's Householder Q differs from the Gram-Schmidt span here
+      project_grad_qr(n, raw, np, g, gp_all + (size_t)b * n, grad_rule, scratch);
+    } else {
+      double cf[6];
+      for (int j = 0; j < k; ++j) {
+        double p = 0.0;
+        for (int i = tid; i < n; i += PRJ_THREADS) p = fma(T[j * np + i], g[i], p);
+        cf[j] = block_sum(p, scratch);
+      }
+      for (int i = tid; i < n; i += PRJ_THREADS) {
+        double part = 0.0;
+        for (int j = 0; j < k; ++j) part = fma(T[j * np + i], cf[j], part);
+        gp_all[(size_t)b * n + i] = g[i] - part;
+      }
     }
   }
   if (!Hp_all) return;
@@ -226,7 +311,7 @@ k_project_trrot(int n, const double* __restrict__ Hall, const double* __restrict
 __host__ __device__ inline size_t prj_scratch_doubles(int n) { return 12 * (size_t)((n + 3) & ~3) + 8; }
 
 __global__ void __launch_bounds__(PRJ_THREADS)
-k_prj_basis(int n, size_t sstride, const double* __restrict__ x_all, const double* __restrict__ g_all,
+k_prj_basis(int n, int grad_rule, size_t sstride, const double* __restrict__ x_all, const double* __restrict__ g_all,
             double* __restrict__ gp_all, double* __restrict__ scratch, int32_t* __restrict__ status) {
   extern __shared__ double sm[];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -247,6 +332,11 @@ k_prj_basis(int n, size_t sstride, const double* __restrict__ x_all, const doubl
   for (int i = tid; i < 6 * np; i += PRJ_THREADS) scr[i] = (i / np < k) ? T[i] : 0.0;
   if (g_all && gp_all) {
     const double* g = g_all + (size_t)b * n;
+    if (k < 6) {
+      __syncthreads();
+      project_grad_qr(n, raw, np, g, gp_all + (size_t)b * n, grad_rule, red);
+      return;
+    }
     double cf[6];
     for (int j = 0; j < k; ++j) {
       double p = 0.0;
@@ -528,8 +618,9 @@ k_prj_out(int n, size_t sstride, int TT, const double* __restrict__ Hall, const 
 
 }  // namespace mop
 
+// grad_rule: 0 = RSIRFO's gradient projection, 1 = EnhancedRSPRFO's (they differ for rank-deficient TR/ROT sets only)
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
-                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
                              cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   const int np = (n + 3) & ~3;
@@ -540,7 +631,7 @@ int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias,
   }
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_project_trrot,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mop::k_project_trrot<<<B, mop::PRJ_THREADS, smem, stream>>>(n, H, Hbias, x, g, Hp_out, gp_out,
+  mop::k_project_trrot<<<B, mop::PRJ_THREADS, smem, stream>>>(n, grad_rule, H, Hbias, x, g, Hp_out, gp_out,
                                                             status);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
@@ -553,7 +644,7 @@ extern "C" int mop_project_trrot(int B, int n, const double* H, const double* Hb
   MOP_REQUIRE(x, "mop_project_trrot: x must be a device pointer");
   MOP_REQUIRE((H && Hp_out) || (g && gp_out), "mop_project_trrot: nothing to project");
   MOP_REQUIRE(!Hp_out || H, "mop_project_trrot: H required with Hp_out");
-  return mop_launch_project_trrot(B, n, H, Hbias, x, g, Hp_out, gp_out, status,
+  return mop_launch_project_trrot(B, n, H, Hbias, x, g, Hp_out, gp_out, status, 0,
                                   (cudaStream_t)stream);
 }
 
@@ -571,8 +662,8 @@ size_t mop_project_scratch_bytes_pref(int B, int n) {
 
 // Same contract as mop_launch_project_trrot, four multi-CTA kernels, `scratch` from the caller.
 int mop_launch_project_trrot_split(int B, int n, const double* H, const double* Hbias, const double* x,
-                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, void* scratch,
-                                   size_t scratch_bytes, cudaStream_t stream) {
+                                   const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
+                                   void* scratch, size_t scratch_bytes, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   const int np = (n + 3) & ~3;
   if (!scratch || scratch_bytes < mop_project_scratch_bytes(B, n)) {
@@ -589,7 +680,7 @@ int mop_launch_project_trrot_split(int B, int n, const double* H, const double* 
   const size_t sstride = prj_stride(n, one_read);
   double* scr = (double*)scratch;
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_prj_basis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-  mop::k_prj_basis<<<B, mop::PRJ_THREADS, smem0, stream>>>(n, sstride, x, g, gp_out, scr, status);
+  mop::k_prj_basis<<<B, mop::PRJ_THREADS, smem0, stream>>>(n, grad_rule, sstride, x, g, gp_out, scr, status);
   MOP_CHECK_CUDA(cudaGetLastError());
   if (!Hp_out) return MOP_OK;
   dim3 grid(nslab, B);

@@ -441,7 +441,7 @@ k_swart_gather(int N, const double* __restrict__ xyz_all, const double* __restri
 }  // namespace mop
 
 int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x,
-                             const double* g, double* Hp_out, double* gp_out, int32_t* status,
+                             const double* g, double* Hp_out, double* gp_out, int32_t* status, int grad_rule,
                              cudaStream_t stream);
 
 static size_t swart_smem(int N, bool in_smem) {
@@ -477,7 +477,7 @@ extern "C" int mop_swart_hessian(int B, int natoms, const double* xyz, const dou
     MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_swart_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mop::k_swart_gather<<<B, mop::SW_THREADS, smem, stream>>>(natoms, xyz, radii, radii_stride, Hraw, status);
     MOP_CHECK_CUDA(cudaGetLastError());
-    return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, stream);
+    return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, 0, stream);
   }
   bool in_smem = swart_smem(natoms, true) <= 220 * 1024;
   const size_t smem = swart_smem(natoms, in_smem);
@@ -488,5 +488,5 @@ extern "C" int mop_swart_hessian(int B, int natoms, const double* xyz, const dou
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_swart, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mop::k_swart<<<B, mop::SW_THREADS, smem, stream>>>(natoms, in_smem ? 1 : 0, xyz, radii, radii_stride, Hraw, status);
   MOP_CHECK_CUDA(cudaGetLastError());
-  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, stream);
+  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, 0, stream);
 }

@@ -43,6 +43,8 @@ ST_BRENT_BRACKET = 1 << 10
 ST_EIG_NOCONV = 1 << 11
 ST_EIG_FALLBACK = 1 << 12
 ST_NO_HISTORY = 1 << 13
+ST_UPD_REJECTED = 1 << 14
+ST_LINDH_NO_K = 1 << 15
 
 
 def resolve_update_method(name: str) -> int:
@@ -71,6 +73,13 @@ def _chk(t: torch.Tensor, name: str, shape=None, dtype=torch.float64) -> torch.T
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def _chk_out(out, B, n):
+    """A caller-supplied result dict is written by the kernels with B * n (move, eigvals) / B (pred, status)
+    elements: validate every entry so a stale dict from a smaller batch can never be overrun."""
+    _chk(out["move"], "out['move']", (B, n)); _chk(out["eigvals"], "out['eigvals']", (B, n))
+    _chk(out["pred"], "out['pred']", (B,)); _chk(out["status"], "out['status']", (B,), torch.int32)
 
 
 def _stream(dev) -> int:
@@ -103,7 +112,7 @@ def hessian_update(H, s, y, method: int, *, inplace: bool = False, rsirfo_guards
     if status is None:
         status = torch.zeros(B, dtype=torch.int32, device=H.device)
     _chk(status, "status", (B,), torch.int32)
-    delta = None if inplace else torch.empty_like(H)
+    delta = None if inplace else torch.zeros_like(H)   # skipped structures (RSIRFO guards) leave their delta at zero
     nbytes = lib.mop_hessian_update_workspace_bytes(B, n) if multi_cta else 0
     work = workspace(H.device, nbytes) if nbytes else None
     with torch.cuda.device(H.device):
@@ -191,6 +200,8 @@ def rsirfo_step(H, x, Bg, g, state, *, method: int, saddle_order: int = 0, neb_m
             "pred": torch.empty(B, dtype=torch.float64, device=dev),
             "status": torch.empty(B, dtype=torch.int32, device=dev),
         }
+    else:
+        _chk_out(out, B, n)
     nbytes = lib.mop_rsirfo_workspace_bytes(B, n, algo_id)
     work = workspace(dev, nbytes)
     with torch.cuda.device(dev):
@@ -220,6 +231,8 @@ def rsirfo_spectral_step(Hp, gp, Bg, state, *, saddle_order: int = 0, neb_mode: 
             "pred": torch.empty(B, dtype=torch.float64, device=dev),
             "status": torch.zeros(B, dtype=torch.int32, device=dev),
         }
+    else:
+        _chk_out(out, B, n)
     nbytes = lib.mop_rsirfo_spectral_workspace_bytes(B, n)
     work = workspace(dev, nbytes)
     with torch.cuda.device(dev):
@@ -425,6 +438,8 @@ def rsprfo_step(H, x, Bg, st, *, method: int, saddle_order: int = 1, Hbias=None,
                "eigvals": torch.empty(B, n, dtype=torch.float64, device=dev),
                "pred": torch.empty(B, dtype=torch.float64, device=dev),
                "status": torch.empty(B, dtype=torch.int32, device=dev)}
+    else:
+        _chk_out(out, B, n)
     nbytes = lib.mop_rsprfo_workspace_bytes(B, n, algo_id)
     work = workspace(dev, nbytes)
     with torch.cuda.device(dev):

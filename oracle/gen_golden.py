@@ -244,6 +244,80 @@ def gen_projection():
     print("projection: 4 cases")
 
 
+RANKDEF_GEOMS = {
+    # rank-deficient TR/ROT sets.  "exact": the dependent raw vector is exactly zero (axis-aligned), so the reference's
+    # Householder Q is reproducible; "noise": the dependent column is rounding noise in the reference itself.
+    "diatomic_z": (np.array([[0.0, 0.0, -1.1], [0.0, 0.0, 1.1]]), "exact"),
+    "diatomic_x": (np.array([[-0.9, 0.0, 0.0], [1.3, 0.0, 0.0]]), "exact"),
+    "diatomic_general": (np.array([[0.3, -0.2, 0.5], [1.1, 0.9, -0.7]]), "noise"),
+    "linear3_z": (np.array([[0.0, 0.0, -2.2], [0.0, 0.0, 0.1], [0.0, 0.0, 2.3]]), "exact"),
+    "linear3_x": (np.array([[-2.2, 0.0, 0.0], [0.1, 0.0, 0.0], [2.3, 0.0, 0.0]]), "exact"),
+    "linear4_y": (np.array([[0.0, -3.1, 0.0], [0.0, -1.0, 0.0], [0.0, 1.2, 0.0], [0.0, 3.4, 0.0]]), "exact"),
+    "linear3_general": (np.array([[-1.0, -1.0, -1.0], [0.1, 0.1, 0.1], [1.3, 1.3, 1.3]]), "noise"),
+}
+
+
+def gen_rankdef():
+    """Gradient / Hessian projection and full RSIRFO / EnhancedRSPRFO steps on two-atom and linear geometries
+    (rsirfo.py:128-190 reduced QR keeps six columns; rsprfo.py:244-285 drops |R_jj| <= 1e-10 columns and skips
+    fewer than three atoms; calc_tools.py:249-316 Gram-Schmidt with drop)."""
+    rs = ref_shim.ref("Optimizer.rsirfo")
+    rp = ref_shim.ref("Optimizer.rsprfo")
+    ct = ref_shim.ref("Utils.calc_tools")
+    blob = {"names": np.array(list(RANKDEF_GEOMS)), "kind": np.array([v[1] for v in RANKDEF_GEOMS.values()])}
+    for si, (name, (xyz, kind)) in enumerate(RANKDEF_GEOMS.items()):
+        rng = np.random.default_rng(7700 + si)
+        natoms = xyz.shape[0]; n = 3 * natoms
+        x = xyz.reshape(-1)
+        H = synthetic.spd_hessian(n, rng)
+        g = rng.normal(0.0, 1e-2, size=n)
+        with quiet():
+            o1 = rs.RSIRFO(method="rsirfo_bfgs", saddle_order=0)
+            o2 = rp.EnhancedRSPRFO(method="rsprfo_bofill", saddle_order=1, element_list=["C"] * natoms)
+            gp1 = o1._project_grad_tr_rot(g.copy(), x.reshape(-1, 1).copy())
+            gp2 = o2._project_grad_tr_rot(g.copy(), x.reshape(-1, 1).copy())
+            Hp = ct.Calculationtools().project_out_hess_tr_and_rot_for_coord(
+                H.copy(), x.reshape(-1, 3).copy(), x.reshape(-1, 3).copy(), False)
+            # two full steps of each optimizer (the second with an update) on a quadratic surface
+            col = lambda a: np.asarray(a, float).reshape(-1, 1).copy()
+            o1.set_hessian(H.copy()); o1.set_bias_hessian(np.zeros((n, n)))
+            mv1a = np.asarray(o1.run(col(x), col(g), [], [], 0.0, 0.0, [], col(x), col(g), []), float).ravel()
+            x1 = x - mv1a; g1 = g + H @ (x1 - x) * 1.05
+            mv1b = np.asarray(o1.run(col(x1), col(g1), col(g), col(x), -1e-3, 0.0, col(mv1a), col(x), col(g1), col(g)), float).ravel()
+            Hn = synthetic.spd_hessian(n, rng, neg_lowest=True)
+            o2.set_hessian(Hn.copy()); o2.set_bias_hessian(np.zeros((n, n)))
+            mv2a = np.asarray(o2.run(col(x), col(g), [], [], 0.0, 0.0, [], col(x), col(g), []), float).ravel()
+        blob.update({f"{name}/x": x, f"{name}/H": H, f"{name}/g": g, f"{name}/gp_rsirfo": gp1, f"{name}/gp_rsprfo": gp2,
+                     f"{name}/Hp": Hp, f"{name}/move_rsirfo0": mv1a, f"{name}/x1": x1, f"{name}/g1": g1,
+                     f"{name}/move_rsirfo1": mv1b, f"{name}/H_rsirfo1": np.array(o1.hessian, float),
+                     f"{name}/Hn": Hn, f"{name}/move_rsprfo0": mv2a})
+        print("rankdef", name, kind, "|gp1|", np.linalg.norm(gp1), "|gp2|", np.linalg.norm(gp2))
+    np.savez_compressed(os.path.join(GOLD, "rankdef.npz"), **blob)
+
+
+def gen_potkeys():
+    """Activation keys of BiasPotentialCalculation (Potential/potential.py): every force_data key the reference tests
+    before it builds a potential term, with the form of the test."""
+    import json, re
+    src = open(os.path.join(ref_shim.REF_ROOT, "multioptpy", "Potential", "potential.py")).read().splitlines()
+    keys = {}
+    for ln, line in enumerate(src, 1):
+        t = line.strip()
+        if not t.startswith("if "):
+            continue
+        for m in re.finditer(r'force_data\["([A-Za-z0-9_]+)"\]', t):
+            k = m.group(1)
+            if re.search(r'not 0\.0 in force_data\["%s"\]' % k, t):
+                keys.setdefault(k, ["all", ln])
+            elif re.search(r'force_data\["%s"\]\[i\] != 0\.0' % k, t):
+                keys.setdefault(k, ["nz", ln])
+            elif re.search(r'len\(force_data\["%s"\]\) > 0' % k, t):
+                keys.setdefault(k, ["len", ln])
+    with open(os.path.join(GOLD, "potential_keys.json"), "w") as f:
+        json.dump(keys, f, indent=1, sort_keys=True)
+    print("potkeys:", len(keys), "activation keys")
+
+
 def read_xyz(path):
     """Minimal xyz reader (Angstrom) -> (elements, coords in Bohr)."""
     lines = [l.split() for l in open(path).read().strip().splitlines()]
@@ -847,8 +921,78 @@ def gen_rsprfo():
     np.savez_compressed(os.path.join(GOLD, "rsprfo_traces.npz"), **blob)
 
 
+RSPRFO_REJECT_CASES = [
+    # (name, method, saddle_order, natoms, nsteps, spike_step, big_modes, seed)
+    # spike_step: the gradient fed at that step makes s.y tiny and ||y|| ~ 1, so the BFGS term y y^T / (s.y) pushes the
+    # updated spectrum beyond 1e6 -> EnhancedRSPRFO.update_hessian reverts (rsprfo.py:1242-1250)
+    ("prfo_reject_bfgs_n30", "rsprfo_bfgs", 1, 10, 5, 2, 0, 11),
+    ("prfo_reject_sr1_n24", "rsprfo_sr1", 1, 8, 5, 3, 0, 12),
+    # big_modes: six modes at 6e5 -> ||H||_F = 1.47e6 > 1e6 but max |lambda| = 6e5: accepted (only the exact spectrum decides)
+    ("prfo_bigmodes_accept_n30", "rsprfo_bofill", 1, 10, 4, -1, 6, 13),
+]
+
+
+def run_rsprfo_reject_case(case):
+    name, method, so, natoms, nsteps, spike, big, seed = case
+    rp = ref_shim.ref("Optimizer.rsprfo")
+    rng = np.random.default_rng(616100 + seed)
+    n = 3 * natoms
+    x0 = synthetic.grid_geometry(natoms, rng).reshape(-1)
+    H0 = synthetic.spd_hessian(n, rng, neg_lowest=so > 0)
+    if big:
+        Q, _ = np.linalg.qr(rng.standard_normal((n, big)))
+        H0 = H0 + 6e5 * (Q @ Q.T); H0 = 0.5 * (H0 + H0.T)
+    E = rng.standard_normal((n, n))
+    Ht = H0 + 0.05 * (E + E.T) / np.sqrt(n)
+    g0 = rng.normal(0.0, 1e-2, size=n)
+    Hb = np.zeros((n, n))
+    pes = QuadraticPES(x0, g0, Ht, Hb, rng)
+    with quiet():
+        opt = rp.EnhancedRSPRFO(method=method, saddle_order=so, element_list=["C"] * natoms,
+                                trust_radius_max=0.3, trust_radius_min=0.01)
+        opt.set_hessian(H0.copy()); opt.set_bias_hessian(Hb.copy())
+    rec = {k: [] for k in ("x", "Bg", "Be", "move", "H_after", "trust", "pred")}
+    x = x0.copy(); x_prev = Bg_prev = mv_prev = None
+    col = lambda a: a.reshape(-1, 1).copy()
+    for k in range(nsteps):
+        e, g = pes.raw(x)
+        if k == spike:
+            s = x - x_prev
+            u = rng.standard_normal(n); u -= (u @ s) / (s @ s) * s; u /= np.linalg.norm(u)
+            base = np.asarray(opt.hessian, float) @ s if "sr1" in method else 0.0    # SR1: (y - H s).s = 1e-8 instead
+            g = Bg_prev + base + u + 1e-8 * s / (s @ s)   # s.y = 1e-8, ||y|| ~ 1
+        Be, Bg = e, g
+        with quiet():
+            if x_prev is None:
+                mv = opt.run(col(x), col(Bg), [], [], Be, 0.0, [], col(x0), col(g), [])
+            else:
+                mv = opt.run(col(x), col(Bg), col(Bg_prev), col(x_prev), Be, 0.0, col(mv_prev), col(x0), col(g), [])
+        mv = np.asarray(mv, float).ravel()
+        rec["x"].append(x.copy()); rec["Bg"].append(Bg.copy()); rec["Be"].append(Be); rec["move"].append(mv)
+        rec["H_after"].append(np.array(opt.hessian, float)); rec["trust"].append(float(opt.trust_radius))
+        rec["pred"].append(float(opt.predicted_energy_changes[-1]))
+        x_prev, Bg_prev, mv_prev = x.copy(), Bg.copy(), mv.copy()
+        x = x - mv
+    if spike >= 0:   # the spike step must have left the Hessian untouched
+        assert np.array_equal(rec["H_after"][spike], rec["H_after"][spike - 1]), name
+    out = {f"{name}/{k}": np.array(v) for k, v in rec.items()}
+    out[f"{name}/H0"] = H0; out[f"{name}/Hb"] = Hb
+    out[f"{name}/meta"] = np.array([so, natoms, nsteps, spike], np.int64)
+    out[f"{name}/method"] = np.array(method)
+    return out
+
+
+def gen_rsprfo_reject():
+    blob = {}
+    for case in RSPRFO_REJECT_CASES:
+        blob.update(run_rsprfo_reject_case(case))
+        print("rsprfo reject case", case[0])
+    blob["names"] = np.array([c[0] for c in RSPRFO_REJECT_CASES])
+    np.savez_compressed(os.path.join(GOLD, "rsprfo_reject.npz"), **blob)
+
+
 SETS = {"keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
-        "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo}
+        "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo, "rsprfo_reject": gen_rsprfo_reject, "rankdef": gen_rankdef, "potkeys": gen_potkeys}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

@@ -102,3 +102,22 @@ def test_gpu_keep_batched_vs_oracle():
             e1, g1, h1 = O.keep_egh(xs[b], kind, f1, f2, k, p)
             Er += e1; gr += g1; Hr += h1
         assert abs(float(E[b]) - Er) <= RTOL * abs(Er) and rel(g[b].cpu().numpy(), gr.ravel()) < RTOL and rel(H[b].cpu().numpy(), Hr) < RTOL, b
+
+
+def test_every_reference_activation_key_is_handled_or_raises(golden_dir):
+    """a force_data key the reference would turn into a potential must never be dropped silently.
+    tests/golden/potential_keys.json lists every activation test of the reference aggregator
+    (Potential/potential.py, generated by oracle/gen_golden.py potkeys)."""
+    import json
+    from multioptpy_b200.Potential import potential as P
+    keys = json.load(open(os.path.join(golden_dir, "potential_keys.json")))
+    assert set(keys) <= set(P._ACTIVATION)
+    for key, (rule, _line) in keys.items():
+        assert P._ACTIVATION[key] == rule, key
+        fd = {key: [[1.0, 2.0]] if rule == "all" else [1.0]}
+        assert P.active_keys(fd) == [key]
+        off = {key: [[0.0, 2.0]] if rule == "all" else ([0.0] if rule == "nz" else [])}
+        assert P.active_keys(off) == []
+        if key not in P._HANDLED:
+            with pytest.raises(P.MopError):
+                P.BiasPotentialCalculation("").main(0.0, np.zeros((3, 3)), np.zeros((3, 3)), ["H"] * 3, fd)

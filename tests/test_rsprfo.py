@@ -15,8 +15,8 @@ def rel(a, b):
     return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
 
 
-def _load(golden_dir):
-    z = np.load(os.path.join(golden_dir, "rsprfo_traces.npz"))
+def _load(golden_dir, fname="rsprfo_traces.npz"):
+    z = np.load(os.path.join(golden_dir, fname))
     return z, [str(s) for s in z["names"]]
 
 
@@ -99,3 +99,68 @@ def test_gpu_rsprfo_batched_vs_oracle():
         xp, gp, mp = x.copy(), g.copy(), mv.copy()
         x = x - mv
         g = np.stack([g0[b] + H0[b] @ (x[b] - x0[b]) for b in range(B)])
+
+
+# ---- update rejection (rsprfo.py:1242-1250): an update whose spectrum exceeds 1e6 is reverted ----------------
+def _reject_rtol(name):
+    # the "bigmodes" Hessian carries six modes at 6e5 beside modes at 1e-3..1 (||H||_F = 1.47e6 > 1e6 > max |lambda|,
+    # so only the exact spectrum can accept it): eps * cond = 1e-16 * 6e8 bounds what ANY eigensolver reproduces of the
+    # step components along the soft modes; two LAPACK drivers differ by 4e-10 on it
+    return 5e-9 if "bigmodes" in name else RTOL
+
+
+def _oracle_trace(z, name):
+    so, natoms, nsteps, spike = [int(v) for v in z[f"{name}/meta"]]
+    opt = O.RSPRFOOracle(method=str(z[f"{name}/method"]), saddle_order=so, trust_radius_max=0.3)
+    opt.set_hessian(z[f"{name}/H0"]); opt.set_bias_hessian(z[f"{name}/Hb"])
+    X, BG, BE = z[f"{name}/x"], z[f"{name}/Bg"], z[f"{name}/Be"]
+    mv_prev = None
+    rtol = _reject_rtol(name)
+    for k in range(nsteps):
+        H_before = opt.hessian.copy()
+        mv = opt.run(X[k], BG[k], X[k - 1] if k else None, BG[k - 1] if k else None, float(BE[k]), mv_prev)
+        assert rel(mv, z[f"{name}/move"][k]) < rtol, (name, k)
+        assert rel(opt.hessian, z[f"{name}/H_after"][k]) < RTOL, (name, k)
+        assert abs(opt.trust - z[f"{name}/trust"][k]) < 1e-13, (name, k)
+        if k == spike:
+            assert np.array_equal(opt.hessian, H_before)
+        mv_prev = mv
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_oracle_rsprfo_reject_trace(golden_dir, idx):
+    z, names = _load(golden_dir, "rsprfo_reject.npz")
+    _oracle_trace(z, names[idx])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(3))
+def test_gpu_rsprfo_reject_trace(golden_dir, idx):
+    from multioptpy_b200.Optimizer.rsprfo import EnhancedRSPRFO
+    from multioptpy_b200 import ops as _lib
+    z, names = _load(golden_dir, "rsprfo_reject.npz")
+    name = names[idx]
+    so, natoms, nsteps, spike = [int(v) for v in z[f"{name}/meta"]]
+    opt = EnhancedRSPRFO(method=str(z[f"{name}/method"]), saddle_order=so, element_list=["C"] * natoms,
+                         trust_radius_max=0.3, trust_radius_min=0.01, device="cuda:0", display_flag=False)
+    opt.set_hessian(z[f"{name}/H0"]); opt.set_bias_hessian(z[f"{name}/Hb"])
+    X, BG, BE = z[f"{name}/x"], z[f"{name}/Bg"], z[f"{name}/Be"]
+    col = lambda a: a.reshape(-1, 1).copy()
+    mv_prev = None
+    for k in range(nsteps):
+        H_before = np.array(opt.hessian, copy=True)
+        if k == 0:
+            mv = opt.run(col(X[k]), col(BG[k]), [], [], float(BE[k]), 0.0, [], col(X[0]), col(BG[k]), [])
+        else:
+            mv = opt.run(col(X[k]), col(BG[k]), col(BG[k - 1]), col(X[k - 1]), float(BE[k]), 0.0, col(mv_prev),
+                         col(X[0]), col(BG[k]), [])
+        assert rel(mv.ravel(), z[f"{name}/move"][k]) < _reject_rtol(name), (name, k)
+        assert rel(opt.hessian, z[f"{name}/H_after"][k]) < RTOL, (name, k)
+        assert abs(opt.trust_radius - z[f"{name}/trust"][k]) < 1e-13, (name, k)
+        st = int(opt.last_status[0])
+        if k == spike:       # reverted bit-exactly, reported in the status word
+            assert np.array_equal(opt.hessian, H_before), name
+            assert st & _lib.ST_UPD_REJECTED and not st & _lib.ST_UPDATED
+        elif k > 0:
+            assert st & _lib.ST_UPDATED and not st & _lib.ST_UPD_REJECTED
+        mv_prev = mv.ravel().copy()
