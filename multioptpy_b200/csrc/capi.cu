@@ -262,7 +262,8 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   // short launches are latency bound: 4.97 ms per step at c = 256 against 4.44 ms), hence off by default.
   const size_t n2 = (size_t)n * n;
   const bool chunked = g_stream_chunk > 0 && g_stream_chunk < B;
-  const bool split_ok = nn >= mop_project_scratch_bytes(B, n) && nn >= mop_hessian_update_scratch_bytes(B, n) &&
+  const size_t slab = sizeof(double) * (size_t)B * n2;  // what a [B][n][n] slab really holds (nn is rounded up)
+  const bool split_ok = slab >= mop_project_scratch_bytes(B, n) && slab >= mop_hessian_update_scratch_bytes(B, n) &&
                         (chunked || B <= 2 * 148);
   const int CH = (split_ok && chunked) ? g_stream_chunk : B;
   for (int b0 = 0; b0 < B; b0 += CH) {

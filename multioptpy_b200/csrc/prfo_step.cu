@@ -461,7 +461,8 @@ k_prfo_step(int n, int so, double tmin, double tmax, const double* __restrict__ 
     if (pred_all) pred_all[b] = pred;
     if (status) {
       const int keep = status[b] & (MOP_ST_UPDATED | MOP_ST_UPD_SKIP_SMALL | MOP_ST_UPD_TERM_ZEROED |
-                                    MOP_ST_NO_HISTORY | MOP_ST_TRROT_RANKDEF | MOP_ST_EIG_NOCONV | MOP_ST_EIG_FALLBACK);
+                                    MOP_ST_NO_HISTORY | MOP_ST_TRROT_RANKDEF | MOP_ST_EIG_NOCONV | MOP_ST_EIG_FALLBACK |
+                                    MOP_ST_UPD_REJECTED);
       status[b] = keep | flags;
     }
   }
@@ -547,8 +548,9 @@ extern "C" int mop_rsprfo_step(int B, int n, int method, int saddle_order, int e
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   // projected gradient (current geometry) and projected pre-update Hessian for the reduction ratio
   // small batches: the multi-CTA projection fills the GPU; large ones: one CTA per structure is as fast
-  int rc = B <= 2 * 148 ? mop_launch_project_trrot_split(B, n, H, Hbias, x, Bg, A, gp, status, 1, evecs, nn, stream)
-                        : mop_launch_project_trrot(B, n, H, Hbias, x, Bg, A, gp, status, 1, stream);
+  const bool prj_split = B <= 2 * 148 && nn >= mop_project_scratch_bytes(B, n);  // (tiny n: scratch exceeds the slab)
+  int rc = prj_split ? mop_launch_project_trrot_split(B, n, H, Hbias, x, Bg, A, gp, status, 1, evecs, nn, stream)
+                     : mop_launch_project_trrot(B, n, H, Hbias, x, Bg, A, gp, status, 1, stream);
   if (rc != MOP_OK) return rc;
   {
     const size_t smem = sizeof(double) * (size_t)n;

@@ -91,7 +91,7 @@ def test_gpu_rankdef_projection(golden_dir):
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     for name, kind in zip(names, kinds):
         x, g, H = z[f"{name}/x"], z[f"{name}/g"], z[f"{name}/H"]
-        Hp, gp, st = ops.project_trrot(T(H[None]), T(x[None]), T(g[None]))
+        Hp, gp, st = ops.project_trrot(T(H[None]), T(x[None]), g=T(g[None]))
         assert int(st[0]) & ops.ST_TRROT_RANKDEF, name
         _check_gp_rsirfo(name, kind, g, x, gp[0].cpu().numpy(), z[f"{name}/gp_rsirfo"])
         assert rel(Hp[0].cpu().numpy(), z[f"{name}/Hp"]) < RTOL, name
@@ -121,3 +121,63 @@ def test_gpu_rankdef_steps(golden_dir):
                    col(z[f"{name}/g1"]), col(g)).ravel()
         assert _move_ok(name, kind, m1, z[f"{name}/move_rsirfo1"], n), name
         assert rel(np.asarray(o.hessian), z[f"{name}/H_rsirfo1"]) < RTOL, name
+
+
+@pytest.mark.gpu
+def test_gpu_batched_diatomics_two_steps():
+    """n = 6 with B >= 3 used to fail on the first step with history (update scratch larger than the
+    n x n slab).  Five diatomics, two RS-I-RFO steps: the update is deterministic (Hessian vs oracle 1e-10), the step
+    itself is the noise-driven hard case (direction along the bond, see _move_ok)."""
+    import torch
+    from multioptpy_b200.Optimizer.rsirfo import RSIRFO
+    rng = np.random.default_rng(42)
+    B, n = 5, 6
+    x0 = np.stack([np.concatenate([c, c + d]) for c, d in zip(rng.normal(size=(B, 3)), rng.normal(size=(B, 3)) + 1.5)])
+    H0 = np.stack([(lambda A: A @ A.T / n + 0.3 * np.eye(n))(rng.standard_normal((n, n))) for _ in range(B)])
+    g0 = rng.normal(0, 1e-2, size=(B, n))
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    opt = RSIRFO(method="rsirfo_bofill", saddle_order=0, device="cuda:0")
+    Hd = T(H0); opt.set_hessian(Hd); opt.set_bias_hessian(None)
+    z = torch.zeros(B, dtype=torch.float64, device="cuda")
+    mv0 = opt.run(T(x0), T(g0), B_e=z, g=T(g0)).cpu().numpy().copy()
+    x1 = x0 - 0.01 * rng.standard_normal((B, n))
+    g1 = g0 + np.einsum("bij,bj->bi", H0, x1 - x0) * 1.1
+    mv1 = opt.run(T(x1), T(g1), pre_geom=T(x0), B_e=z - 1e-3, g=T(g1), pre_g=T(g0)).cpu().numpy()
+    st = opt.last_status.cpu().numpy()
+    assert np.all(st & ops_ST("ST_UPDATED")) and np.all(st & ops_ST("ST_TRROT_RANKDEF"))
+    for b in range(B):
+        o = O.RSIRFOOracle(method="rsirfo_bofill", saddle_order=0)
+        o.set_hessian(H0[b].copy()); o.set_bias_hessian(None)
+        m0 = o.run(x0[b], g0[b], g0[b], None, None, 0.0)
+        m1 = o.run(x1[b], g1[b], g1[b], x0[b], g0[b], -1e-3)
+        assert _move_ok("diatomic", "exact", mv0[b], m0, n) and _move_ok("diatomic", "exact", mv1[b], m1, n), b
+        assert rel(Hd[b].cpu().numpy(), o.hessian) < RTOL, b
+
+
+def ops_ST(name):
+    from multioptpy_b200 import ops
+    return getattr(ops, name)
+
+
+@pytest.mark.gpu
+def test_gpu_result_buffers_follow_the_batch_shape():
+    """a cached result dict from a smaller batch must never be handed to a larger launch."""
+    import torch
+    from multioptpy_b200 import ops, synthetic
+    from multioptpy_b200.Optimizer.rsirfo import RSIRFO
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    opt = RSIRFO(method="rsirfo_bfgs", saddle_order=0, device="cuda:0")
+    for B, natoms in ((2, 5), (6, 9), (3, 4)):
+        x0, H0, g0, _ = synthetic.batch(9, B, natoms)
+        opt.set_hessian(T(H0)); opt.set_bias_hessian(None)
+        mv = opt.run(T(x0), T(g0), B_e=torch.zeros(B, dtype=torch.float64, device="cuda"), g=T(g0))
+        assert tuple(mv.shape) == (B, 3 * natoms)
+        o = O.RSIRFOOracle(method="rsirfo_bfgs", saddle_order=0)
+        o.set_hessian(H0[-1].copy()); o.set_bias_hessian(None)
+        assert rel(mv[-1].cpu().numpy(), o.run(x0[-1], g0[-1], g0[-1], None, None, 0.0)) < RTOL
+    st = ops.new_rsirfo_state(4, 0.5, torch.device("cuda:0"))
+    x0, H0, g0, _ = synthetic.batch(9, 4, 5)
+    small = {"move": torch.empty(2, 15, dtype=torch.float64, device="cuda"), "eigvals": torch.empty(2, 15, dtype=torch.float64, device="cuda"),
+             "pred": torch.empty(2, dtype=torch.float64, device="cuda"), "status": torch.empty(2, dtype=torch.int32, device="cuda")}
+    with pytest.raises(ops.MopError):
+        ops.rsirfo_step(T(H0), T(x0), T(g0), T(g0), st, method=15, out=small)
