@@ -567,6 +567,14 @@ size_t mop_tridiag_rw_smem(int n) {
   const int np = (n + 3) & ~3;
   return sizeof(double) * ((((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3) + (5 + 8) * (size_t)np);
 }
+int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
+                           double* tau, double* gq, int* flag, cudaStream_t stream);
+static int g_pk_blocked = 1;
+// tuning: 1 (default) = k_tridiag_blk (tridiag_blocked.cu: dlatrd panels, thread-per-row symv, DMMA trailing updates)
+extern "C" int mop_debug_packed_blocked(int on) {
+  g_pk_blocked = on;
+  return MOP_OK;
+}
 static int g_pk_rowwarp = 1;
 // tuning: 1 (default) = k_tridiag_rwf (warp per row block, lanes over columns, update + symv fused),
 // 0 = k_tridiag_packed (thread groups per index, separate symv and update passes)
@@ -589,6 +597,7 @@ extern "C" int mop_debug_packed_threads(int t) {
 int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
                               double* tau, double* gq, int* flag, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
+  if (g_pk_blocked) return mop_launch_tridiag_blk(B, n, A, gp, Vh, dd, ee, tau, gq, flag, stream);
   mop::PkArgs a{n, A, gp, Vh, dd, ee, tau, gq, flag, g_pk_dbg};
   if (g_pk_rowwarp) {
     const size_t smem_rw = mop_tridiag_rw_smem(n);
