@@ -392,6 +392,7 @@ int mop_debug_large_pair(int mode);     /* tuning: two matrices per cluster in l
 int mop_debug_large_ablate(int mask); /* diagnostics: bit0 no trailing stores, bit1 no trailing loads (results invalid) */
 int mop_debug_large_timing(void* buf); /* diagnostics: [B][4] int64 phase cycles of the MOP_EIGH_LARGE reduction */
 int mop_debug_barrier_latency(int threads, double* out, void* stream);
+int mop_debug_front_fused(int on);      /* tuning: update + projection fused into the tridiagonalisation kernel (default 1) */
 int mop_debug_packed_blocked(int on);    /* tuning: blocked DMMA tridiagonalisation k_tridiag_blk (default 1) */
 
 #ifdef __cplusplus

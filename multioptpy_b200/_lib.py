@@ -88,6 +88,7 @@ SIGNATURES = {
     "mop_debug_large_timing": (_i, [_p]),
     "mop_debug_large_ablate": (_i, [_i]),
     "mop_debug_packed_blocked": (_i, [_i]),
+    "mop_debug_front_fused": (_i, [_i]),
 }
 
 _lib = None

@@ -51,6 +51,20 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
                             double* state, double* move, double* evals_out, double* pred,
                             int32_t* status, void* work, size_t work_bytes, double* zbuf, cudaStream_t stream);
 
+int mop_launch_project_trrot_flagged(int B, int n, const double* H, const double* Hbias, const double* x,
+                                     double* Hp_out, const int32_t* flags, cudaStream_t stream);
+int mop_launch_front_tridiag_blk(int B, int n, int method, int guards, int grad_rule, double* H, const double* Hbias,
+                                 const double* x, const double* xp, const double* g, const double* gprev,
+                                 const double* Bg, const double* state, int state_stride, double* gp_out,
+                                 int32_t* status, double* Vh, double* dd, double* ee, double* tau, double* gq, int* flag,
+                                 cudaStream_t stream);
+int mop_spectrum_step_supported(int n);
+int mop_launch_spectrum_step(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
+                             const double* Vh, double* Z, double* Dm, const double* pd, const double* pe,
+                             const double* ptau, const double* pgq, const int* pflag, const double* Bg,
+                             const double* Be, double* state, double* move, double* evals_out, double* pred,
+                             int32_t* status, cudaStream_t stream);
+
 extern "C" size_t mop_rsirfo_spectral_workspace_bytes(int B, int n);
 extern "C" int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_mode, double trust_min,
                                         double trust_max, const double* Hp, const double* gp,
@@ -76,6 +90,12 @@ static int g_stream_chunk = 0;
 // tuning: structures per update + projection chunk of mop_rsirfo_step (0, the default = the whole batch at once)
 extern "C" int mop_debug_stream_chunk(int structures) {
   g_stream_chunk = structures;
+  return MOP_OK;
+}
+static int g_front_fused = 1;
+// tuning: 1 (default) = update + projection fused into the tridiagonalisation kernel (n <= 160)
+extern "C" int mop_debug_front_fused(int on) {
+  g_front_fused = on;
   return MOP_OK;
 }
 static int g_eigh_small_pipeline = 1;
@@ -255,6 +275,37 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
 
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   int rc = MOP_OK;
+  if (g_front_fused && pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG && mop_spectrum_step_supported(n)) {
+    // n <= 160: ONE kernel reads H, applies the update (raw gradients, rsirfo.py:308-309,1316-1372), writes H back,
+    // projects gradient and effective Hessian (rsirfo.py:337,349-358) and tridiagonalises on the triangle in shared
+    // memory - the projected Hessian never exists in HBM; the spectrum kernel finishes the step.
+    const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
+    double* zbuf = (double*)rest;                    // evecs slab of the spectral layout
+    double* evals2 = (double*)(rest + nn);
+    void* jwork = rest + nn + nv;
+    double* twork = (double*)(rest + nn + nv + jac);
+    const size_t bnn = (size_t)B * n * n, bn = (size_t)B * n;
+    double* Vh = twork;
+    double* Dm = twork + bnn;
+    double* pd = twork + 2 * bnn;
+    double* pe = pd + bn;
+    double* pt = pd + 2 * bn;
+    double* pg = pd + 3 * bn;
+    int* pflag = (int*)(pd + 4 * bn);
+    rc = mop_launch_front_tridiag_blk(B, n, x_prev ? method : MOP_UPD_NONE, 1, 0, H, Hbias, x, x_prev, g, g_prev, Bg,
+                                      state, MOP_RSIRFO_STATE, gp, status, Vh, pd, pe, pt, pg, pflag, stream);
+    if (rc != MOP_OK) return rc;
+    rc = mop_launch_spectrum_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Vh, zbuf, Dm, pd, pe, pt, pg, pflag,
+                                  Bg, Be, state, move_out, eigvals_out, pred_out, status, stream);
+    if (rc != MOP_OK) return rc;
+    // robust path for the structures the spectrum kernel flagged (almost always none: empty launches, no host sync)
+    rc = mop_launch_project_trrot_flagged(B, n, H, Hbias, x, Hp, status, stream);
+    if (rc != MOP_OK) return rc;
+    rc = mop_launch_eigh_jacobi_ext(B, n, Hp, evals2, zbuf, status, status, jwork, jac, twork, stream);
+    if (rc != MOP_OK) return rc;
+    return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals2, zbuf, gp, Bg, Be, state,
+                               move_out, eigvals_out, pred_out, status, 1, stream);
+  }
   // (1) Hessian update with RAW gradients (rsirfo.py:308-309,1316-1372) and (2) TR/ROT projection of gradient
   // and effective Hessian (rsirfo.py:337,349-358).  Small batches take the multi-CTA projection (it fills the
   // GPU), large ones one CTA per structure (as fast, fewer launches).  mop_debug_stream_chunk(c) runs the pair

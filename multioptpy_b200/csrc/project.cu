@@ -23,9 +23,10 @@ __global__ void __launch_bounds__(PRJ_THREADS)
 k_project_trrot(int n, int grad_rule, const double* __restrict__ Hall, const double* __restrict__ Hb_all,
                 const double* __restrict__ x_all, const double* __restrict__ g_all,
                 double* __restrict__ Hp_all, double* __restrict__ gp_all,
-                int32_t* __restrict__ status) {
+                int32_t* __restrict__ status, const int32_t* __restrict__ only_flagged) {
   extern __shared__ double sm[];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = PRJ_THREADS >> 5;
+  if (only_flagged && !(only_flagged[b] & MOP_ST_EIG_FALLBACK)) return;  // fallback re-projection of flagged structures
   const int np = (n + 3) & ~3;
   double* T = sm;                 // 6 x np
   double* raw = T + 6 * np;       // 6 x np   (later reused as W -> Y)
@@ -503,7 +504,26 @@ int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias,
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_project_trrot,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mop::k_project_trrot<<<B, mop::PRJ_THREADS, smem, stream>>>(n, grad_rule, H, Hbias, x, g, Hp_out, gp_out,
-                                                            status);
+                                                            status, nullptr);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+// The same projection for the structures whose status carries MOP_ST_EIG_FALLBACK only (the others exit at once):
+// the fused front end never writes the projected Hessian, the robust eigensolver path needs it.
+int mop_launch_project_trrot_flagged(int B, int n, const double* H, const double* Hbias, const double* x,
+                                     double* Hp_out, const int32_t* flags, cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  const int np = (n + 3) & ~3;
+  const size_t smem = sizeof(double) * (12 * (size_t)np + 40 + 36 + 2 * mop::PT * (mop::PT + 1));
+  if (smem > 200 * 1024) {
+    mop_set_error("n = %d too large for the projection kernel", n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_project_trrot,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_project_trrot<<<B, mop::PRJ_THREADS, smem, stream>>>(n, 0, H, Hbias, x, nullptr, Hp_out, nullptr, nullptr,
+                                                            flags);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }

@@ -24,7 +24,8 @@
 //
 // Outputs are those of mop_launch_tridiag_packed (LAPACK dsytd2 conventions): d, e, tau, the reflector rows Vh
 // and Q^T g.  Replaces the reduction stage of numpy.linalg.eigh at Optimizer/rsirfo.py:606,626,652.
-#include "common.cuh"
+#include "trrot.cuh"
+#include "update_coef.cuh"
 
 namespace mop {
 
@@ -39,6 +40,25 @@ struct PkArgs {
   double* gq;        // [B][n] Q^T gp
   int* flag;         // [B] 0 normal, 1 zero matrix, 2 non-finite input
   long long* dbg;    // optional [B][16] phase cycles
+};
+
+// Fused front end (FUSED kernels): the Hessian update, its write-back and the TR/ROT projection run on the triangle in
+// shared memory before the reduction starts, so H is read once and written once and the projected Hessian never
+// exists in HBM (RSIRFO.run steps 1-2: Optimizer/rsirfo.py:308-358, update_hessian :1316-1372,
+// Utils/calc_tools.py:249-316).
+struct FrontArgs {
+  double* H;             // [B][n][n] in / out (written only when the update is applied)
+  const double* Hbias;   // [B][n][n] or null
+  const double* x;       // [B][n]
+  const double* xp;      // [B][n] previous geometry or null
+  const double* g;       // [B][n] gradient of the update (raw for RSIRFO)
+  const double* gprev;   // [B][n] or null
+  const double* Bg;      // [B][n] gradient to project
+  const double* state;   // [B][state_stride] or null (MOP_RS_HAVE_PREV)
+  int state_stride;
+  int method, guards, grad_rule;
+  double* gp_out;        // [B][n] projected gradient
+  int32_t* status;       // [B]
 };
 
 constexpr int TB_NB = 6;   // reflectors per panel: 4 scalars + 2 * NB panel products = the 16 slots of one reduction
@@ -206,6 +226,364 @@ __device__ __forceinline__ void symv_diag32(const double* __restrict__ L, const 
   }
 }
 
+
+// One half-pass over a row-major n x n matrix in global memory: rows are dealt to the warps four at a time (twenty
+// loads in flight per lane), LOWER = the row segments j <= i, otherwise j > i.  Element (i, j) adds w x to the packed
+// triangle at (max, min) (w = 1/2 off the diagonal, so two half-passes leave sym(M) there; INIT stores instead of
+// adding) and x v_j to the row sums acc0 / acc1 (M s and M y of the update), which go to out0 / out1.
+template <int NW, bool LOWER, bool INIT, int NVEC>
+__device__ __forceinline__ void front_half_pass(const double* __restrict__ M, int n, double* L, const double* v0,
+                                                const double* v1, double* out0, double* out1, int lane, int wid) {
+  for (int i0 = 4 * wid; i0 < n; i0 += 4 * NW) {
+    double x[4][5];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int j = lane + 32 * q;
+        const bool in = i < n && j < n && (LOWER ? j <= i : j > i);
+        x[r][q] = in ? M[(size_t)i * n + j] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int j = lane + 32 * q;
+        const bool in = i < n && j < n && (LOWER ? j <= i : j > i);
+        if (in) {
+          const double w = (j == i) ? x[r][q] : 0.5 * x[r][q];
+          double* dst = LOWER ? L + tri0(i) + j : L + tri0(j) + i;
+          if (INIT) *dst = w;
+          else *dst += w;
+          if (NVEC > 0) a0 = fma(x[r][q], v0[j], a0);
+          if (NVEC > 1) a1 = fma(x[r][q], v1[j], a1);
+        }
+      }
+      if (NVEC > 0) {
+        a0 = warp_sum(a0);
+        if (NVEC > 1) a1 = warp_sum(a1);
+        if (lane == 0 && i < n) {
+          if (LOWER) {
+            out0[i] = a0;
+            if (NVEC > 1) out1[i] = a1;
+          } else {
+            out0[i] += a0;
+            if (NVEC > 1) out1[i] += a1;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Rank-2k update of the whole triangle with the projection vectors, Hp = S - Y T^T - T Y^T, as C + (-P) Q^T with
+// P = [Y | T], Q = [T | Y] (K = 12; vectors k .. 5 are zero): the same 8 x 8 DMMA tiles as the trailing updates.
+// T, Y: [6][np].
+template <int NW>
+__device__ __forceinline__ void project_update_dmma(double* L, const double* T, const double* Y, int n, int np,
+                                                    int lane, int wid) {
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = (n + 7) >> 3;
+  for (int I = mt - 1 - wid; I >= 0; I -= NW) {
+    const int ri = 8 * I + g;
+    const int ric = ri < n ? ri : n - 1;
+    const int Tr = tri0(ric);
+    double a[3];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+      const int c = 4 * ks + t;
+      const double pa = c < 6 ? Y[c * np + ric] : T[(c - 6) * np + ric];
+      a[ks] = ri < n ? -pa : 0.0;
+    }
+    for (int J0 = 0; J0 <= I; J0 += 4) {
+      double bq[4][3], c0[4], c1[4];
+      bool in0[4], in1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int J = J0 + u;
+        const int rj = 8 * J + g;
+        const bool jin = J <= I && rj < n;
+        const int rjc = jin ? rj : n - 1;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+          const int c = 4 * ks + t;
+          const double qb = c < 6 ? T[c * np + rjc] : Y[(c - 6) * np + rjc];
+          bq[u][ks] = jin ? qb : 0.0;
+        }
+        const int cj = 8 * J + 2 * t;
+        in0[u] = J <= I && ri < n && cj <= ri;
+        in1[u] = J <= I && ri < n && cj + 1 <= ri;
+        c0[u] = in0[u] ? L[Tr + cj] : 0.0;
+        c1[u] = in1[u] ? L[Tr + cj + 1] : 0.0;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (J0 + u <= I) dmma884(c0[u], c1[u], a[ks], bq[u][ks], c0[u], c1[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cj = 8 * (J0 + u) + 2 * t;
+        if (in0[u]) L[Tr + cj] = c0[u];
+        if (in1[u]) L[Tr + cj + 1] = c1[u];
+      }
+    }
+  }
+}
+
+// The fused front end.  On return L holds the projected effective Hessian sym(P^T (H' + Hbias) P) (H' = the updated
+// Hessian, already written back), *gp_mine the projected gradient entry of row tid.  `fr` is the region behind the
+// triangle (free until the reduction starts; left dirty).  Whole CTA.
+template <int NW>
+__device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L, double* fr, double* gp_mine) {
+  constexpr int THREADS = 32 * NW;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t nn = (size_t)n * n;
+  double* H = f.H + (size_t)b * nn;
+  double* vs = fr;            // s
+  double* vy = vs + np;       // y (after damping)
+  double* vu = vy + np;       // u = H s
+  double* vr = vu + np;       // r = y - u
+  double* hy = vr + np;       // H y (flowchart)         -- later Tm rows 0 .. 3 live in hy .. hy + 4 np
+  double* scratch = fr + 12 * np;  // 48 doubles
+  __shared__ UpdCoef coef;
+  int st = f.status ? f.status[b] : 0;
+  st &= ~(MOP_ST_UPDATED | MOP_ST_UPD_SKIP_SMALL | MOP_ST_UPD_SKIP_CURV | MOP_ST_UPD_TERM_ZEROED | MOP_ST_NO_HISTORY |
+          MOP_ST_TRROT_RANKDEF);
+
+  // ---- s, y, guards, damping (RSIRFO.update_hessian, rsirfo.py:1316-1340) ----------------------------------------
+  const bool asked = f.method != MOP_UPD_NONE && f.xp != nullptr && f.gprev != nullptr;
+  const bool have_prev = asked && (f.state == nullptr || f.state[(size_t)b * f.state_stride + MOP_RS_HAVE_PREV] != 0.0);
+  bool upd = have_prev;
+  int m = f.method;
+  double ss = 0.0, sy = 0.0, yy = 0.0;
+  if (!have_prev) {
+    if (asked) st |= MOP_ST_NO_HISTORY;
+  } else {
+    for (int i = tid; i < n; i += THREADS) {
+      vs[i] = f.x[(size_t)b * n + i] - f.xp[(size_t)b * n + i];
+      vy[i] = f.g[(size_t)b * n + i] - f.gprev[(size_t)b * n + i];
+    }
+    __syncthreads();
+    double pss = 0, psy = 0, pyy = 0;
+    for (int i = tid; i < n; i += THREADS) {
+      pss = fma(vs[i], vs[i], pss);
+      psy = fma(vs[i], vy[i], psy);
+      pyy = fma(vy[i], vy[i], pyy);
+    }
+    ss = block_sum(pss, scratch);
+    sy = block_sum(psy, scratch);
+    yy = block_sum(pyy, scratch);
+    if (f.guards) {
+      int skip = 0;
+      if (sqrt(ss) < 1e-10 || sqrt(yy) < 1e-10) skip = MOP_ST_UPD_SKIP_SMALL;
+      else if (f.guards == 1 && sy <= 0.0) skip = MOP_ST_UPD_SKIP_CURV;
+      if (skip) {
+        st |= skip;
+        upd = false;
+      }
+    }
+    if (upd && method_has_dd(m)) {
+      bool active = true;
+      if (m == MOP_UPD_BLOCK_BFGS_DD && !(sqrt(ss) > 1e-8)) active = false;
+      if (active) {
+        const double th = dd_theta(ss, sy, method_dd_thr(m));
+        if (th != 1.0) {
+          for (int i = tid; i < n; i += THREADS) vy[i] = th * vy[i] + (1.0 - th) * vs[i];
+          __syncthreads();
+          double p = 0;
+          for (int i = tid; i < n; i += THREADS) p = fma(vs[i], vy[i], p);
+          sy = block_sum(p, scratch);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- one read of H: sym(H) into the triangle, u = H s (and H y) from the same loads ----------------------------
+  if (upd) {
+    if (m == MOP_UPD_FLOWCHART) {
+      front_half_pass<NW, true, true, 2>(H, n, L, vs, vy, vu, hy, lane, wid);
+      __syncthreads();
+      front_half_pass<NW, false, false, 2>(H, n, L, vs, vy, vu, hy, lane, wid);
+    } else {
+      front_half_pass<NW, true, true, 1>(H, n, L, vs, vy, vu, hy, lane, wid);
+      __syncthreads();
+      front_half_pass<NW, false, false, 1>(H, n, L, vs, vy, vu, hy, lane, wid);
+    }
+  } else {
+    front_half_pass<NW, true, true, 0>(H, n, L, vs, vy, vu, hy, lane, wid);
+    __syncthreads();
+    front_half_pass<NW, false, false, 0>(H, n, L, vs, vy, vu, hy, lane, wid);
+  }
+  __syncthreads();
+
+  if (upd) {
+    // ---- scalars, coefficient matrix (hessian_update.py / block_hessian_update.py through update_coef.cuh) -------
+    if (m == MOP_UPD_FLOWCHART) {
+      double pzz = 0, pzs = 0;
+      for (int i = tid; i < n; i += THREADS) {
+        const double z = vy[i] - hy[i];
+        pzz = fma(z, z, pzz);
+        pzs = fma(z, vs[i], pzs);
+      }
+      const double zz = block_sum(pzz, scratch);
+      const double zs = block_sum(pzs, scratch);
+      m = flowchart_select(ss, yy, sy, zz, zs);
+    }
+    double psu = 0, prs = 0, prr = 0;
+    for (int i = tid; i < n; i += THREADS) {
+      const double r = vy[i] - vu[i];
+      vr[i] = r;
+      psu = fma(vs[i], vu[i], psu);
+      prs = fma(r, vs[i], prs);
+      prr = fma(r, r, prr);
+    }
+    UpdScalars q;
+    q.ss = ss;
+    q.sy = sy;
+    q.su = block_sum(psu, scratch);
+    q.rs = block_sum(prs, scratch);
+    q.rr = block_sum(prr, scratch);
+    if (tid == 0) update_coefficients(m, q, coef);
+    __syncthreads();
+    st |= MOP_ST_UPDATED | coef.flags;
+    // Tm[a][j] = sum_b C[a][b] v_b[j]: delta_ij = sum_a v_a[i] Tm[a][j]  (the fma order of coef_delta)
+    double* Tm = hy;  // 4 np (H y is dead)
+    for (int j = tid; j < n; j += THREADS) {
+      const double vj[4] = {vs[j], vy[j], vu[j], vr[j]};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t = fma(coef.c[a][c], vj[c], t);
+        Tm[a * np + j] = t;
+      }
+    }
+    __syncthreads();
+    // ---- H' = sym(H) + 1/2 (delta + delta^T) on the triangle: thread per row ------------------------------------
+    if (tid < n) {
+      const int i = tid;
+      const double vi[4] = {vs[i], vy[i], vu[i], vr[i]};
+      const double ti[4] = {Tm[i], Tm[np + i], Tm[2 * np + i], Tm[3 * np + i]};
+      double* Li = L + tri0(i);
+      for (int j = 0; j <= i; ++j) {
+        double d0 = 0.0, d1 = 0.0;
+        const double vj[4] = {vs[j], vy[j], vu[j], vr[j]};
+        const double tj[4] = {Tm[j], Tm[np + j], Tm[2 * np + j], Tm[3 * np + j]};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          d0 = fma(vi[a], tj[a], d0);
+          d1 = fma(vj[a], ti[a], d1);
+        }
+        Li[j] += 0.5 * (d0 + d1);
+      }
+    }
+    __syncthreads();
+    // ---- write H' back (the only write of the Hessian): full rows from the triangle ----------------------------
+    for (int i = wid; i < n; i += NW) {
+      double* row = H + (size_t)i * n;
+      for (int j = lane; j < n; j += 32) row[j] = (j <= i) ? L[tri0(i) + j] : L[tri0(j) + i];
+    }
+  }
+  // ---- effective Hessian: + sym(Hbias) (rsirfo.py:349-353) -----------------------------------------------------------
+  if (f.Hbias) {
+    const double* Hb = f.Hbias + (size_t)b * nn;
+    __syncthreads();
+    front_half_pass<NW, true, false, 0>(Hb, n, L, vs, vy, vu, hy, lane, wid);
+    __syncthreads();
+    front_half_pass<NW, false, false, 0>(Hb, n, L, vs, vy, vu, hy, lane, wid);
+  }
+  __syncthreads();
+
+  // ---- TR/ROT basis (classical Gram-Schmidt with drop, calc_tools.py:250-259), projected gradient -----------------
+  double* T = fr;             // [6][np]
+  double* Y = fr + 6 * np;    // [6][np]: raw vectors, then W = S T, then Y
+  const int k = build_trrot_basis(n, f.x + (size_t)b * n, T, np, Y, scratch);
+  if (k < 6) st |= MOP_ST_TRROT_RANKDEF;
+  {
+    const double* g = f.Bg + (size_t)b * n;
+    double* gpo = f.gp_out + (size_t)b * n;
+    if (k < 6) {  // block-uniform: the reference's Householder Q differs from the Gram-Schmidt span here
+      project_grad_qr(n, Y, np, g, gpo, f.grad_rule, scratch);
+      __syncthreads();
+      *gp_mine = tid < n ? gpo[tid] : 0.0;
+    } else {
+      double cf[6];
+      for (int j = 0; j < 6; ++j) {
+        double p = 0.0;
+        for (int i = tid; i < n; i += THREADS) p = fma(T[j * np + i], g[i], p);
+        cf[j] = block_sum(p, scratch);
+      }
+      double mine = 0.0;
+      for (int i = tid; i < n; i += THREADS) {
+        double part = 0.0;
+        for (int j = 0; j < 6; ++j) part = fma(T[j * np + i], cf[j], part);
+        const double v = g[i] - part;
+        gpo[i] = v;
+        if (i == tid) mine = v;
+      }
+      *gp_mine = mine;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 6 * np; e += THREADS) {
+    if (e / np >= k) T[e] = 0.0;  // unused basis slots (rejected candidates leave their residual there)
+    Y[e] = 0.0;
+  }
+  __syncthreads();
+  // ---- W = S T: thread per row on the triangle (row part + column part), six vectors at once -------------------------
+  if (tid < n) {
+    const int i = tid;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double* Li = L + tri0(i);
+    for (int j = 0; j <= i; ++j) {
+      const double x = Li[j];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) acc[v] = fma(x, T[v * np + j], acc[v]);
+    }
+    const double* p = L + tri0(i + 1) + i;
+    for (int r = i + 1; r < n; ++r) {
+      const double x = p[0];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) acc[v] = fma(x, T[v * np + r], acc[v]);
+      p += r + 1;
+    }
+#pragma unroll
+    for (int v = 0; v < 6; ++v)
+      if (v < k) Y[v * np + i] = acc[v];
+  }
+  __syncthreads();
+  // M = T^T W (k x k), Y = W - 1/2 T sym(M)
+  double* M = scratch;  // 36
+  for (int e = wid; e < k * k; e += NW) {
+    const int a = e / k, c = e - a * k;
+    double p = 0.0;
+    for (int i = lane; i < n; i += 32) p = fma(T[a * np + i], Y[c * np + i], p);
+    p = warp_sum(p);
+    if (lane == 0) M[a * 6 + c] = p;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += THREADS) {
+    double tv[6];
+    for (int a = 0; a < k; ++a) tv[a] = T[a * np + i];
+    for (int c = 0; c < k; ++c) {
+      double corr = 0.0;
+      for (int a = 0; a < k; ++a) corr = fma(tv[a], 0.5 * (M[a * 6 + c] + M[c * 6 + a]), corr);
+      Y[c * np + i] -= 0.5 * corr;
+    }
+  }
+  __syncthreads();
+  // ---- Hp = S - Y T^T - T Y^T: rank-12 update on the tensor cores ---------------------------------------------------
+  project_update_dmma<NW>(L, T, Y, n, np, lane, wid);
+  if (tid == 0 && f.status) f.status[b] = st;
+  __syncthreads();
+}
+
 template <int NW>
 struct TbMinBlocks {
   static constexpr int value = NW >= 5 ? 2 : (NW == 4 ? 3 : (NW == 3 ? 5 : (NW == 2 ? 8 : 16)));
@@ -215,11 +593,14 @@ struct TbMinBlocks {
 __host__ __device__ inline size_t tb_smem_doubles(int n, int nw) {
   const size_t np = (size_t)((n + 3) & ~3);
   const size_t nl = ((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1;
-  return nl + (size_t)n * TB_WS + (32 * (size_t)nw + 16) + 2 * np + 2 * 16 * (size_t)nw + 16 * (size_t)nw + 4 + 64;
+  size_t fr = (size_t)n * TB_WS + (32 * (size_t)nw + 16) + 2 * np + 2 * 16 * (size_t)nw + 16 * (size_t)nw + 4 + 64;
+  const size_t front = 12 * np + 48;  // fused front end: T | Y (or s, y, u, r, H y, coefficient rows) + reduction scratch
+  if (fr < front) fr = front;
+  return nl + fr;
 }
 
-template <int NW, bool DBG>
-__global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk(PkArgs a) {
+template <int NW, bool DBG, bool FUSED>
+__global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk(PkArgs a, FrontArgs f) {
   constexpr int THREADS = 32 * NW;
   constexpr int NB = TB_NB, WS = TB_WS;
   constexpr int NU = 32 * NW + 16;  // uu is zero outside (k, n): the symv loops run in whole batches of eight
@@ -237,24 +618,32 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
   double* pub = tot + 16 * NW;      // [4]  z_{k+1}, c_{k+1}
   double* s_rb = pub + 4;           // [64] block_sum_k<2> scratch
   int parity = 0, parity2 = 0;
-  const double* Ain = a.A + (size_t)b * n * n;
+  const double* Ain = FUSED ? nullptr : a.A + (size_t)b * n * n;
   double* Vh = a.Vh + (size_t)b * n * n;
 
-  // everything behind the triangle starts finite (the batched symv multiplies a few words of it by zero)
-  for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
-  // ---- load the lower triangle (row segments, coalesced), Frobenius norm of it for the trivial cases ----
   double pn[2] = {0.0, 0.0};
-  for (int i = wid; i < n; i += NW) {
-    const double* row = Ain + (size_t)i * n;
-    double* Lr = L + tri0(i);
-    for (int j = lane; j <= i; j += 32) {
-      const double x = row[j];
-      Lr[j] = x;
-      pn[0] = fma(x, x, pn[0]);
+  double gp_mine = 0.0;
+  if (FUSED) {
+    // update + write-back + projection on the triangle (one read and one write of H, no projected Hessian in HBM)
+    fused_front<NW>(f, n, np, b, L, Wp, &gp_mine);
+    for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
+    for (int e = tid; e < n * (n + 1) / 2; e += THREADS) pn[0] = fma(L[e], L[e], pn[0]);
+  } else {
+    // everything behind the triangle starts finite (the batched symv multiplies a few words of it by zero)
+    for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
+    // ---- load the lower triangle (row segments, coalesced), Frobenius norm of it for the trivial cases ----
+    for (int i = wid; i < n; i += NW) {
+      const double* row = Ain + (size_t)i * n;
+      double* Lr = L + tri0(i);
+      for (int j = lane; j <= i; j += 32) {
+        const double x = row[j];
+        Lr[j] = x;
+        pn[0] = fma(x, x, pn[0]);
+      }
     }
   }
   __syncthreads();
-  for (int i = tid; i < n; i += THREADS) gq[i] = a.gp ? a.gp[(size_t)b * n + i] : 0.0;
+  for (int i = tid; i < n; i += THREADS) gq[i] = FUSED ? (i == tid ? gp_mine : 0.0) : (a.gp ? a.gp[(size_t)b * n + i] : 0.0);
   block_sum_k<2>(pn, s_rb, parity2);
   const double fro = sqrt(pn[0]);
   const bool nonfinite = !isfinite(fro), trivial = nonfinite || fro == 0.0;
@@ -504,13 +893,25 @@ extern "C" int mop_priv_tridiag_blk_timing(void* buf) {
 
 int mop_tridiag_blk_supported(int n) { return n >= 1 && n <= 160; }
 
-template <int NW, bool DBG>
-static int launch_blk(int B, const mop::PkArgs& a, cudaStream_t stream) {
+template <int NW, bool DBG, bool FUSED>
+static int launch_blk(int B, const mop::PkArgs& a, const mop::FrontArgs& f, cudaStream_t stream) {
   const size_t smem = sizeof(double) * mop::tb_smem_doubles(a.n, NW);
-  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_blk<NW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mop::k_tridiag_blk<NW, DBG><<<B, 32 * NW, smem, stream>>>(a);
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_tridiag_blk<NW, DBG, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  mop::k_tridiag_blk<NW, DBG, FUSED><<<B, 32 * NW, smem, stream>>>(a, f);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
+}
+
+template <bool FUSED>
+static int dispatch_blk(int B, const mop::PkArgs& a, const mop::FrontArgs& f, cudaStream_t stream) {
+  switch ((a.n + 31) / 32) {
+    case 1: return launch_blk<1, false, FUSED>(B, a, f, stream);
+    case 2: return launch_blk<2, false, FUSED>(B, a, f, stream);
+    case 3: return launch_blk<3, false, FUSED>(B, a, f, stream);
+    case 4: return launch_blk<4, false, FUSED>(B, a, f, stream);
+    default: return (a.dbg && !FUSED) ? launch_blk<5, true, false>(B, a, f, stream) : launch_blk<5, false, FUSED>(B, a, f, stream);
+  }
 }
 
 // d, e, tau, gq: [B][n]; Vh: [B][n][n]; flag: [B]
@@ -522,12 +923,23 @@ int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, doub
     return MOP_ERR_UNSUPPORTED;
   }
   mop::PkArgs a{n, A, gp, Vh, dd, ee, tau, gq, flag, g_tb_dbg};
-  const int nw = (n + 31) / 32;
-  switch (nw) {
-    case 1: return launch_blk<1, false>(B, a, stream);
-    case 2: return launch_blk<2, false>(B, a, stream);
-    case 3: return launch_blk<3, false>(B, a, stream);
-    case 4: return launch_blk<4, false>(B, a, stream);
-    default: return a.dbg ? launch_blk<5, true>(B, a, stream) : launch_blk<5, false>(B, a, stream);
+  mop::FrontArgs f{};
+  return dispatch_blk<false>(B, a, f, stream);
+}
+
+// Steps 1-3a of RSIRFO.run in one kernel: Hessian update (method, guards as mop_launch_hessian_update with mode 1),
+// write-back of H, TR/ROT projection of gradient (-> gp_out) and effective Hessian, tridiagonalisation of the latter.
+int mop_launch_front_tridiag_blk(int B, int n, int method, int guards, int grad_rule, double* H, const double* Hbias,
+                                 const double* x, const double* xp, const double* g, const double* gprev,
+                                 const double* Bg, const double* state, int state_stride, double* gp_out,
+                                 int32_t* status, double* Vh, double* dd, double* ee, double* tau, double* gq, int* flag,
+                                 cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  if (!mop_tridiag_blk_supported(n) || n < 3) {
+    mop_set_error("fused update + projection + tridiagonalisation: n = %d not supported (3 .. 160)", n);
+    return MOP_ERR_UNSUPPORTED;
   }
+  mop::PkArgs a{n, nullptr, nullptr, Vh, dd, ee, tau, gq, flag, nullptr};
+  mop::FrontArgs f{H, Hbias, x, xp, g, gprev, Bg, state, state_stride, method, guards, grad_rule, gp_out, status};
+  return dispatch_blk<true>(B, a, f, stream);
 }

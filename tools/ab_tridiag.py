@@ -22,8 +22,8 @@ for b in range(B):
     x1[b], g1[b] = synthetic.second_point(x0[b], H0[b], g0[b], mv0[b], rngs[b])
 x0d, g0d, x1d, g1d = T(x0), T(g0), T(x1), T(g1)
 ref = None
-for blocked in (0, 1):
-    lib.mop_debug_packed_blocked(blocked)
+for blocked, fused in ((0, 0), (1, 0), (1, 1)):
+    lib.mop_debug_packed_blocked(blocked); lib.mop_debug_front_fused(fused)
     Hs = [H.clone() for _ in range(4)]; sts = [st.clone() for _ in range(4)]
     o = None
     for i in range(2):
@@ -41,15 +41,15 @@ for blocked in (0, 1):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 8
     fb = int((o["status"] & ops.ST_EIG_FALLBACK).ne(0).sum())
-    print(f"blocked={blocked}: {ms:.3f} ms/step = {B / ms * 1e3:.0f} steps/s; max rel diff vs rwf {err:.2e}; fallbacks {fb}", flush=True)
+    print(f"blocked={blocked} fused={fused}: {ms:.3f} ms/step = {B / ms * 1e3:.0f} steps/s; max rel diff vs rwf {err:.2e}; fallbacks {fb}", flush=True)
 # phase clocks of the blocked kernel
-lib.mop_debug_packed_blocked(1)
+lib.mop_debug_packed_blocked(1); lib.mop_debug_front_fused(0)
 dbg = torch.zeros(B, 16, dtype=torch.int64, device=dev)
 lib.mop_priv_tridiag_blk_timing(dbg.data_ptr())
 Hs = H.clone(); s2 = st.clone()
 ops.rsirfo_step(Hs, x1d, g1d, g1d, s2, method=m, x_prev=x0d, g_prev=g0d, Be=zero - 1e-3)
 torch.cuda.synchronize()
-lib.mop_priv_tridiag_blk_timing(None)
+lib.mop_priv_tridiag_blk_timing(None); lib.mop_debug_front_fused(1)
 d = dbg.cpu().numpy().astype(float)
 names = ["(a) panel rows + c", "(b) symv", "(c) reduction", "(d) scalars/w/v", "trailing DMMA"]
 tot = d[:, :5].sum(1).mean()
