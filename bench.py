@@ -10,6 +10,13 @@ two-step sequence (history present, Hessian update active, s.y > 0), SURVEY §8d
 One bench "step" = one pass of the hot path over the whole batch; `value` counts
 structure-steps per second over all ranks (weak scaling: per-GPU batch fixed).
 
+`e2e` goes through the C ABI with HOST buffers every step: the Hessian batch travels as packed lower triangles
+(mop_rsirfo_step_packed, 92.6 MB instead of 184 MB per 1024 structures), geometry / gradients / state beside it, the
+move vectors and status words come back; the updated Hessians stay on the device (RSIRFO keeps its Hessian between
+run() calls; get_hessian() unpacks on demand) and are read back ONCE after the timed loop for the check.
+`per_config` carries the other named shapes of BASELINE.json (configs[2] NEB 64 x 30, configs[3] 8192 x N=24 / N=8,
+configs[4] 256 x 3N=600), each with value, parity_vs_oracle and roofline (bench_configs.py); --no-per-config skips them.
+
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -228,7 +235,9 @@ def run_b200(args, rank, world, local_rank):
         raise SystemExit(f"bench.py: parity check failed before timing ({worst:.3e})")
 
     # ---- rotating pristine copies (each timed step sees an un-updated Hessian batch) ----
-    ncopy = max(2, min(K + W, 24))
+    ncopy = max(2, K + W)     # every step of the run sees a pristine (not yet updated) Hessian batch
+    if ncopy * B * n * n * 8 > 60e9:
+        raise SystemExit(f"bench.py: {K} + {W} pristine Hessian copies do not fit; use fewer steps")
     Hs = [H_d0.clone() for _ in range(ncopy)]
     sts = [state1.clone() for _ in range(ncopy)]
     method_id = ops.resolve_update_method(METHOD)
@@ -279,28 +288,32 @@ def run_b200(args, rank, world, local_rank):
     nstream = min(nchunk, int(os.environ.get("MOP_BENCH_E2E_STREAMS", "4")))
     cb = max(sizes)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    hH, hx1, hg1, hx0, hg0 = pin(H0), pin(x1), pin(g1), pin(x0), pin(g0)
+    ntri = n * (n + 1) // 2
+    il = np.tril_indices(n)
+    hH = pin(H0[:, il[0], il[1]])                    # packed lower triangles, row i at i (i + 1) / 2
+    hx1, hg1, hx0, hg0 = pin(x1), pin(g1), pin(x0), pin(g0)
     hBe = pin(np.full(B, -1e-3)); hst = state1.cpu().pin_memory()
     h_move = torch.empty(B, n, dtype=f64).pin_memory()
-    h_Hout = torch.empty(B, n, n, dtype=f64).pin_memory()
     h_stat = torch.empty(B, dtype=torch.int32).pin_memory()
     # earlier chunks get the higher stream priority: their CTAs are scheduled first, so the chunks finish
     # (and their results go back over PCIe) one after the other instead of all together at the end
     prio = os.environ.get("MOP_BENCH_E2E_PRIO", "1") == "1"
     streams = [torch.cuda.Stream(dev, priority=(-min(5, nstream - 1 - i) if prio else 0)) for i in range(nstream)]
-    dbuf = [dict(H=torch.empty(cb, n, n, dtype=f64, device=dev), x1=torch.empty(cb, n, dtype=f64, device=dev),
+    # device-side Hessian storage of the e2e path: one packed slab per chunk (stays resident after the step)
+    dHp = torch.empty(B, ntri, dtype=f64, device=dev)
+    dbuf = [dict(x1=torch.empty(cb, n, dtype=f64, device=dev),
                  g1=torch.empty(cb, n, dtype=f64, device=dev), x0=torch.empty(cb, n, dtype=f64, device=dev),
                  g0=torch.empty(cb, n, dtype=f64, device=dev), Be=torch.empty(cb, dtype=f64, device=dev),
                  st=torch.empty(cb, ops.RSIRFO_STATE, dtype=f64, device=dev), outs={}) for _ in range(nstream)]
     h2d = (hH.numel() + hx1.numel() * 4 + hBe.numel() + hst.numel()) * 8
-    d2h = (h_move.numel() + h_Hout.numel()) * 8 + h_stat.numel() * 4
+    d2h = h_move.numel() * 8 + h_stat.numel() * 4
 
     def e2e_step():
         for c in range(nchunk):
             s = streams[c % nstream]; d = dbuf[c % nstream]
             lo, hi = int(bounds[c]), int(bounds[c + 1]); m = hi - lo; sl = slice(lo, hi)
             with torch.cuda.stream(s):
-                dH, dx1, dg1, dx0, dg0 = d["H"][:m], d["x1"][:m], d["g1"][:m], d["x0"][:m], d["g0"][:m]
+                dH, dx1, dg1, dx0, dg0 = dHp[sl], d["x1"][:m], d["g1"][:m], d["x0"][:m], d["g0"][:m]
                 dBe, dst = d["Be"][:m], d["st"][:m]
                 # vectors first: they ride behind the previous chunk's Hessian copy instead of delaying this chunk
                 dx1.copy_(hx1[sl], non_blocking=True); dg1.copy_(hg1[sl], non_blocking=True)
@@ -308,10 +321,9 @@ def run_b200(args, rank, world, local_rank):
                 dBe.copy_(hBe[sl], non_blocking=True); dst.copy_(hst[sl], non_blocking=True)
                 dH.copy_(hH[sl], non_blocking=True)
                 o = ops.rsirfo_step(dH, dx1, dg1, dg1, dst, method=method_id, x_prev=dx0, g_prev=dg0, Be=dBe,
-                                    out=d["outs"].get(m))
+                                    out=d["outs"].get(m), packed=True)
                 d["outs"][m] = o
                 h_move[sl].copy_(o["move"], non_blocking=True)
-                h_Hout[sl].copy_(dH, non_blocking=True)
                 h_stat[sl].copy_(o["status"], non_blocking=True)
         for s in streams:
             s.synchronize()
@@ -333,7 +345,11 @@ def run_b200(args, rank, world, local_rank):
     # the host-buffer path must reproduce the device-resident result of the timed steps
     ref_mv = out["move"].cpu().numpy()
     e2e_diff = float(np.max(np.linalg.norm(h_move.numpy() - ref_mv, axis=1) / np.linalg.norm(ref_mv, axis=1)))
-    e2e_ok = bool(np.isfinite(h_move.numpy()).all() and e2e_diff < 1e-12)
+    # lazy read-back of the updated Hessians (once, outside the timed loop): must equal the resident path's
+    H_e2e = ops.unpack_lower(dHp, n)
+    H_res = Hs[(W + K - 1) % ncopy]
+    e2e_hdiff = float(((H_e2e - H_res).flatten(1).norm(dim=1) / H_res.flatten(1).norm(dim=1)).max())
+    e2e_ok = bool(np.isfinite(h_move.numpy()).all() and e2e_diff < 1e-12 and e2e_hdiff < 1e-12)
 
     # ---- e2e with the Hessian batch resident on the device (steady-state drop-in) -------
     d_x1, d_g1 = torch.empty_like(x1_d), torch.empty_like(g1_d)
@@ -408,11 +424,11 @@ def run_b200(args, rank, world, local_rank):
         hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
         cores = os.cpu_count() or 1
-        sample = min(B, max(64, cores * 4))
+        sample = min(B, max(64, cores * 8))      # >= 8 structures per process: the 64-structure sample was noisy
         cpu_val, used = cpu_baseline(sample, cores)
         traffic = None          # DRAM bytes of the dominant kernel pair per launch, from the committed ncu capture
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             if tr.get("batch") == B and tr.get("n") == n:
                 traffic = tr["dominant_pair_bytes_per_launch"]
         except Exception:
@@ -423,20 +439,24 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(B, {"eigh": "auto", "parity_vs_oracle": worst}),
+            "config": workload_config(B),
+            "parity_vs_oracle": worst, "eigh": "auto",
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": f"pinned host buffers incl. the Hessian batch both ways, chunks of {sizes} structures on {nstream} streams",
-                    "matches_resident_path": e2e_ok, "max_rel_diff_vs_resident": e2e_diff},
+                    "note": f"pinned host buffers through mop_rsirfo_step_packed: Hessian batch in as packed lower triangles "
+                            f"every step, moves + status out; updated Hessians stay on the device (read back once after "
+                            f"the loop for the check); chunks of {sizes} structures on {nstream} streams",
+                    "matches_resident_path": e2e_ok, "max_rel_diff_vs_resident": e2e_diff,
+                    "hessian_max_rel_diff_vs_resident": e2e_hdiff},
             "e2e_hessian_resident": {"value": e2e_res_val, "unit": UNIT,
                                      "h2d_bytes_per_step": 2 * B * n * 8, "d2h_bytes_per_step": B * n * 8},
-            "gpu_launches": 8 * K,   # update (3 kernels), projection, packed tridiagonalisation, spectrum + step, 2 fallback kernels
+            "gpu_launches": 5 * K,   # fused update + projection + tridiagonalisation, spectrum + step, 3 (empty) fallback launches
             "roofline": {"bound": "fp64",
-                         "kernel": "k_tridiag_packed<256> + k_spectrum_step: tridiagonalisation, then spectrum, eigenvectors "
-                                   "of T and the RFO step in the eigenbasis, timed together (dominant pair of the step)",
+                         "kernel": "k_tridiag_blk<5> + k_spectrum_step: blocked DMMA tridiagonalisation, then spectrum, "
+                                   "eigenvectors of T and the RFO step in the eigenbasis, timed together (dominant pair)",
                          "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": eig_tflops / fp64_peak, "traffic": traffic,
-                         "traffic_source": "profiles/r1b_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write)",
+                         "traffic_source": "profiles/r2_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write)",
                          "algorithmic_flops_per_launch": B * WF, "kernel_ms": eig_ms,
                          "executed_flops_per_launch_estimate": executed_flops,
                          "executed_tflops_estimate": executed_flops / (eig_ms * 1e-3) / 1e12,
@@ -448,13 +468,38 @@ def run_b200(args, rank, world, local_rank):
                              "traffic": None, "kernel_ms": upd_ms, "peak_source": hbm_src},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": used, "kind": "port",
                              "sample": f"{sample} structures of the same batch, step-1 calls timed, one process per "
-                                       f"core, 1 BLAS thread each (oracle/np_oracle.py)"},
+                                       f"core, 1 BLAS thread each (oracle/np_oracle.py)",
+                             "port_vs_reference": port_factor()},
         }
+    if not args.no_per_config:
+        import bench_configs as bc
+        recs = {}
+        fpk = fp64_peak if rank == 0 else None
+        for key, fn in (("configs[2]", lambda: bc.c3_record(dev, rank, world, dist)),
+                        ("configs[3] N=24", lambda: bc.c4_record(dev, rank, world, dist, 24)),
+                        ("configs[3] N=8", lambda: bc.c4_record(dev, rank, world, dist, 8)),
+                        ("configs[4]", lambda: bc.c5_record(dev, rank, world, dist, fp64_peak=fpk))):
+            if key == "configs[2]" and 64 % world:
+                continue
+            r = fn()
+            if rank == 0:
+                recs[key] = r
+        if line is not None:
+            line["per_config"] = recs
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def port_factor():
+    """Speed of the oracle port relative to the UNMODIFIED reference on the same inputs, measured where /root/reference
+    exists by tools/port_vs_reference.py (committed result: profiles/port_vs_reference.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "port_vs_reference.json")))
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------- config 5 (non-default)
@@ -637,6 +682,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-per-config", action="store_true",
+                    help="skip the per_config records (configs[2], [3], [4]) of the default line")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2 (default): BASELINE configs[1], the headline line; c5: configs[4], P-RFO at 3N = 600")
     args = ap.parse_args()

@@ -84,6 +84,7 @@ enum {
 #define MOP_ST_EIG_FALLBACK (1 << 12)   /* robust Jacobi fallback produced the spectrum   */
 #define MOP_ST_NO_HISTORY (1 << 13)     /* first call: no previous point, update skipped  */
 #define MOP_ST_UPD_REJECTED (1 << 14)   /* P-RFO: updated spectrum > 1e6, update reverted (rsprfo.py:1247) */
+#define MOP_ST_ALPHA_UNSTABLE (1 << 16) /* alpha loop did not end on its rounding-free exits: the secular root is ill-conditioned, the reference's own step is summation-order dependent (rfo_secular.cuh) */
 #define MOP_ST_LINDH_NO_K (1 << 15)     /* Lindh: non-zero gradient but no internal gradient, K term omitted */
 
 /* eigensolver selection */
@@ -158,6 +159,25 @@ int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode, in
                     const double* g_prev, const double* Be, double* state, double* move_out,
                     double* eigvals_out, double* pred_out, int32_t* status, void* work,
                     size_t work_bytes, void* stream);
+
+/* The same step with the Hessians in PACKED lower-triangular storage, [B][n (n + 1) / 2] with row i at
+ * i (i + 1) / 2 (they are symmetric: RSIRFO symmetrises after every update, rsirfo.py:1372): half the bytes in HBM
+ * and over PCIe.  3 <= n <= 160 (the shared-memory path); workspace = mop_rsirfo_workspace_bytes(B, n,
+ * MOP_EIGH_TRIDIAG).  mop_pack_lower / mop_unpack_lower convert between the layouts on the device. */
+int mop_rsirfo_step_packed(int B, int n, int method, int saddle_order, int neb_mode, double trust_min,
+                           double trust_max, double* H_packed, const double* Hbias_packed, const double* x,
+                           const double* Bg, const double* g, const double* x_prev, const double* g_prev,
+                           const double* Be, double* state, double* move_out, double* eigvals_out, double* pred_out,
+                           int32_t* status, void* work, size_t work_bytes, void* stream);
+/* The same step for a batch whose structures use DIFFERENT update methods, method_per [B] int32 on the device
+ * (a NEB chain: rsirfo_block_fsb at the ends, rsirfo_block_bofill inside, Optimizer/rfo_neb.py:116-121). */
+int mop_rsirfo_step_mixed(int B, int n, const int32_t* method_per, int saddle_order, int neb_mode, double trust_min,
+                          double trust_max, double* H, const double* Hbias, const double* x, const double* Bg,
+                          const double* g, const double* x_prev, const double* g_prev, const double* Be, double* state,
+                          double* move_out, double* eigvals_out, double* pred_out, int32_t* status, void* work,
+                          size_t work_bytes, void* stream);
+int mop_pack_lower(int B, int n, const double* H, double* packed, void* stream);
+int mop_unpack_lower(int B, int n, const double* packed, double* H, void* stream);
 
 /* ---- (2e) one RS-P-RFO step ----------------------------------------------------
  * Replaces EnhancedRSPRFO.run (Optimizer/rsprfo.py:713-886): reduction ratio of the previous

@@ -70,6 +70,7 @@ class RSIRFO:
         self.last_status = None
         self._state = None     # (B, 16) device tensor
         self._out = None
+        self._packed = False
         self._method_id = ops.resolve_update_method(self.hessian_update_method)
 
     # ---- reference API ------------------------------------------------------------
@@ -82,11 +83,22 @@ class RSIRFO:
 
     def set_hessian(self, hessian):
         self.hessian = hessian
+        self._packed = False
+
+    def set_hessian_packed(self, packed):
+        """Tensor mode: keep the (symmetric) Hessian batch as packed lower triangles (B, n (n + 1) / 2) - half the
+        bytes in HBM and over PCIe (n <= 160).  ``get_hessian()`` unpacks on demand."""
+        self.hessian = packed
+        self._packed = True
 
     def set_bias_hessian(self, bias_hessian):
         self.bias_hessian = bias_hessian
 
     def get_hessian(self):
+        if getattr(self, "_packed", False) and self.hessian is not None:
+            np_ = self.hessian.shape[1]
+            n = int(round((np.sqrt(8.0 * np_ + 1.0) - 1.0) / 2.0))
+            return ops.unpack_lower(self.hessian, n)
         return self.hessian
 
     def get_bias_hessian(self):
@@ -152,7 +164,7 @@ class RSIRFO:
             saddle_order=self.saddle_order, neb_mode=self.NEB_mode, Hbias=self.bias_hessian,
             x_prev=x_prev if have_hist else None, g_prev=g_prev if have_hist else None, Be=Be,
             trust_min=self.trust_radius_min, trust_max=self.trust_radius_max,
-            eigh_algo=self.eigh_algo, out=self._out)
+            eigh_algo=self.eigh_algo, out=self._out, packed=getattr(self, "_packed", False))
         self.last_status = self._out["status"]
         self.prev_geometry, self.prev_gradient, self.prev_energy = x, Bg, Be
         self.iteration += 1

@@ -35,6 +35,12 @@ SIGNATURES = {
     "mop_rsirfo_workspace_bytes": (_sz, [_i, _i, _i]),
     "mop_rsirfo_step": (_i, [_i, _i, _i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                              _p, _p, _p, _p, _sz, _p]),
+    "mop_rsirfo_step_packed": (_i, [_i, _i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                    _p, _sz, _p]),
+    "mop_rsirfo_step_mixed": (_i, [_i, _i, _p, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                   _p, _sz, _p]),
+    "mop_pack_lower": (_i, [_i, _i, _p, _p, _p]),
+    "mop_unpack_lower": (_i, [_i, _i, _p, _p, _p]),
     "mop_rsprfo_workspace_bytes": (_sz, [_i, _i, _i]),
     "mop_rsprfo_step": (_i, [_i, _i, _i, _i, _i, _d, _d] + [_p] * 16 + [_sz, _p]),
     "mop_rsirfo_spectral_workspace_bytes": (_sz, [_i, _i]),

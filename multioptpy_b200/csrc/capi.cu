@@ -53,7 +53,8 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
 
 int mop_launch_project_trrot_flagged(int B, int n, const double* H, const double* Hbias, const double* x,
                                      double* Hp_out, const int32_t* flags, cudaStream_t stream);
-int mop_launch_front_tridiag_blk(int B, int n, int method, int guards, int grad_rule, double* H, const double* Hbias,
+int mop_launch_front_tridiag_blk(int B, int n, int method, const int32_t* method_per, int guards, int grad_rule,
+                                 int packed, double* H, const double* Hbias,
                                  const double* x, const double* xp, const double* g, const double* gprev,
                                  const double* Bg, const double* state, int state_stride, double* gp_out,
                                  int32_t* status, double* Vh, double* dd, double* ee, double* tau, double* gq, int* flag,
@@ -92,6 +93,45 @@ extern "C" int mop_debug_stream_chunk(int structures) {
   g_stream_chunk = structures;
   return MOP_OK;
 }
+namespace mop {
+// Packed lower triangle <-> full symmetric matrix (row i of the triangle at i (i + 1) / 2).  only_flagged: structures
+// without MOP_ST_EIG_FALLBACK in flags[b] are skipped (the robust path of the packed step).
+__global__ void k_unpack_lower(int n, const double* __restrict__ P, double* __restrict__ H,
+                               const int32_t* __restrict__ only_flagged) {
+  const size_t b = blockIdx.y, nn = (size_t)n * n, nt = (size_t)n * (n + 1) / 2;
+  if (only_flagged && !(only_flagged[b] & MOP_ST_EIG_FALLBACK)) return;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    const int hi = i > j ? i : j, lo = i > j ? j : i;
+    H[b * nn + e] = P[b * nt + ((size_t)hi * (hi + 1) >> 1) + lo];
+  }
+}
+__global__ void k_pack_lower(int n, const double* __restrict__ H, double* __restrict__ P) {
+  const size_t b = blockIdx.y, nn = (size_t)n * n, nt = (size_t)n * (n + 1) / 2;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    if (j <= i) P[b * nt + ((size_t)i * (i + 1) >> 1) + j] = H[b * nn + e];
+  }
+}
+}  // namespace mop
+
+extern "C" int mop_pack_lower(int B, int n, const double* H, double* packed, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0 && H && packed, "mop_pack_lower: bad arguments");
+  if (B == 0) return MOP_OK;
+  dim3 grid(64, B);
+  mop::k_pack_lower<<<grid, 256, 0, (cudaStream_t)stream>>>(n, H, packed);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+extern "C" int mop_unpack_lower(int B, int n, const double* packed, double* H, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0 && H && packed, "mop_unpack_lower: bad arguments");
+  if (B == 0) return MOP_OK;
+  dim3 grid(64, B);
+  mop::k_unpack_lower<<<grid, 256, 0, (cudaStream_t)stream>>>(n, packed, H, nullptr);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
 static int g_front_fused = 1;
 // tuning: 1 (default) = update + projection fused into the tridiagonalisation kernel (n <= 160)
 extern "C" int mop_debug_front_fused(int on) {
@@ -228,6 +268,57 @@ extern "C" int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_
                              Be, state, move_out, eigvals_out, pred_out, status, 1, stream);
 }
 
+// n <= 160: ONE kernel reads H, applies the update (raw gradients, rsirfo.py:308-309,1316-1372), writes H back,
+// projects gradient and effective Hessian (rsirfo.py:337,349-358) and tridiagonalises on the triangle in shared
+// memory - the projected Hessian never exists in HBM; the spectrum kernel finishes the step.  packed: H / Hbias are
+// packed lower triangles.  Hp, gp, rest: the workspace carve of mop_rsirfo_step (status already zeroed).
+static int rsirfo_step_fused(int B, int n, int method, const int32_t* method_per, int saddle_order, int neb_mode, double trust_min,
+                             double trust_max, int packed, double* H, const double* Hbias, const double* x,
+                             const double* Bg, const double* g, const double* x_prev, const double* g_prev,
+                             const double* Be, double* state, double* move_out, double* eigvals_out, double* pred_out,
+                             int32_t* status, double* Hp, double* gp, char* rest, cudaStream_t stream) {
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
+  double* zbuf = (double*)rest;                    // evecs slab of the spectral layout
+  double* evals2 = (double*)(rest + nn);
+  void* jwork = rest + nn + nv;
+  double* twork = (double*)(rest + nn + nv + jac);
+  const size_t bnn = (size_t)B * n * n, bn = (size_t)B * n;
+  double* Vh = twork;
+  double* Dm = twork + bnn;
+  double* pd = twork + 2 * bnn;
+  double* pe = pd + bn;
+  double* pt = pd + 2 * bn;
+  double* pg = pd + 3 * bn;
+  int* pflag = (int*)(pd + 4 * bn);
+  int rc = mop_launch_front_tridiag_blk(B, n, x_prev ? method : MOP_UPD_NONE, x_prev ? method_per : nullptr, 1, 0, packed, H, Hbias, x, x_prev, g,
+                                        g_prev, Bg, state, MOP_RSIRFO_STATE, gp, status, Vh, pd, pe, pt, pg, pflag,
+                                        stream);
+  if (rc != MOP_OK) return rc;
+  rc = mop_launch_spectrum_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Vh, zbuf, Dm, pd, pe, pt, pg, pflag,
+                                Bg, Be, state, move_out, eigvals_out, pred_out, status, stream);
+  if (rc != MOP_OK) return rc;
+  // robust path for the structures the spectrum kernel flagged (almost always none: empty launches, no host sync)
+  const double* Hfull = H;
+  const double* Hbfull = Hbias;
+  if (packed) {  // the flagged structures' Hessians as full squares, in slabs that are dead by now
+    dim3 grid(32, B);
+    mop::k_unpack_lower<<<grid, 256, 0, stream>>>(n, H, Dm, status);
+    if (Hbias) mop::k_unpack_lower<<<grid, 256, 0, stream>>>(n, Hbias, Vh, status);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    Hfull = Dm;
+    Hbfull = Hbias ? Vh : nullptr;
+  }
+  rc = mop_launch_project_trrot_flagged(B, n, Hfull, Hbfull, x, Hp, status, stream);
+  if (rc != MOP_OK) return rc;
+  // (packed: the Jacobi working matrices must not alias the unpacked inputs - they go to the eigenvector slab's twin)
+  rc = mop_launch_eigh_jacobi_ext(B, n, Hp, evals2, zbuf, status, status, jwork, jac, packed ? nullptr : twork, stream);
+  if (rc != MOP_OK) return rc;
+  return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals2, zbuf, gp, Bg, Be, state,
+                             move_out, eigvals_out, pred_out, status, 1, stream);
+}
+
 // workspace of mop_rsirfo_step: Hp | evecs | evals | gp | eigh work
 extern "C" size_t mop_rsirfo_workspace_bytes(int B, int n, int algo) {
   if (B <= 0 || n <= 0) return 0;
@@ -275,37 +366,9 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
 
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   int rc = MOP_OK;
-  if (g_front_fused && pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG && mop_spectrum_step_supported(n)) {
-    // n <= 160: ONE kernel reads H, applies the update (raw gradients, rsirfo.py:308-309,1316-1372), writes H back,
-    // projects gradient and effective Hessian (rsirfo.py:337,349-358) and tridiagonalises on the triangle in shared
-    // memory - the projected Hessian never exists in HBM; the spectrum kernel finishes the step.
-    const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
-    double* zbuf = (double*)rest;                    // evecs slab of the spectral layout
-    double* evals2 = (double*)(rest + nn);
-    void* jwork = rest + nn + nv;
-    double* twork = (double*)(rest + nn + nv + jac);
-    const size_t bnn = (size_t)B * n * n, bn = (size_t)B * n;
-    double* Vh = twork;
-    double* Dm = twork + bnn;
-    double* pd = twork + 2 * bnn;
-    double* pe = pd + bn;
-    double* pt = pd + 2 * bn;
-    double* pg = pd + 3 * bn;
-    int* pflag = (int*)(pd + 4 * bn);
-    rc = mop_launch_front_tridiag_blk(B, n, x_prev ? method : MOP_UPD_NONE, 1, 0, H, Hbias, x, x_prev, g, g_prev, Bg,
-                                      state, MOP_RSIRFO_STATE, gp, status, Vh, pd, pe, pt, pg, pflag, stream);
-    if (rc != MOP_OK) return rc;
-    rc = mop_launch_spectrum_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Vh, zbuf, Dm, pd, pe, pt, pg, pflag,
-                                  Bg, Be, state, move_out, eigvals_out, pred_out, status, stream);
-    if (rc != MOP_OK) return rc;
-    // robust path for the structures the spectrum kernel flagged (almost always none: empty launches, no host sync)
-    rc = mop_launch_project_trrot_flagged(B, n, H, Hbias, x, Hp, status, stream);
-    if (rc != MOP_OK) return rc;
-    rc = mop_launch_eigh_jacobi_ext(B, n, Hp, evals2, zbuf, status, status, jwork, jac, twork, stream);
-    if (rc != MOP_OK) return rc;
-    return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals2, zbuf, gp, Bg, Be, state,
-                               move_out, eigvals_out, pred_out, status, 1, stream);
-  }
+  if (g_front_fused && pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG && mop_spectrum_step_supported(n))
+    return rsirfo_step_fused(B, n, method, nullptr, saddle_order, neb_mode, trust_min, trust_max, 0, H, Hbias, x, Bg, g, x_prev,
+                             g_prev, Be, state, move_out, eigvals_out, pred_out, status, Hp, gp, rest, stream);
   // (1) Hessian update with RAW gradients (rsirfo.py:308-309,1316-1372) and (2) TR/ROT projection of gradient
   // and effective Hessian (rsirfo.py:337,349-358).  Small batches take the multi-CTA projection (it fills the
   // GPU), large ones one CTA per structure (as fast, fewer launches).  mop_debug_stream_chunk(c) runs the pair
@@ -375,4 +438,70 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
   // (4) image function, secular solve, step, bookkeeping (rsirfo.py:365-490)
   return mop_launch_rfo_step(B, n, saddle_order, neb_mode, trust_min, trust_max, evals, evecs, gp,
                              Bg, Be, state, move_out, eigvals_out, pred_out, status, 0, stream);
+}
+
+// RSIRFO.run with the Hessians in PACKED lower-triangular storage, [B][n (n + 1) / 2] (row i at i (i + 1) / 2): half
+// the bytes in HBM and over PCIe; otherwise mop_rsirfo_step.  n <= 160 (the fused shared-memory path) only.
+extern "C" int mop_rsirfo_step_packed(int B, int n, int method, int saddle_order, int neb_mode, double trust_min,
+                                      double trust_max, double* H_packed, const double* Hbias_packed, const double* x,
+                                      const double* Bg, const double* g, const double* x_prev, const double* g_prev,
+                                      const double* Be, double* state, double* move_out, double* eigvals_out,
+                                      double* pred_out, int32_t* status, void* work, size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && n > 0 && n % 3 == 0, "mop_rsirfo_step_packed: n must be a positive multiple of 3");
+  MOP_REQUIRE(H_packed && x && Bg && g && state && move_out && status && work,
+              "mop_rsirfo_step_packed: H, x, Bg, g, state, move_out, status, work must be device pointers");
+  MOP_REQUIRE(saddle_order >= 0 && saddle_order < n, "mop_rsirfo_step_packed: bad saddle_order");
+  MOP_REQUIRE((x_prev == nullptr) == (g_prev == nullptr),
+              "mop_rsirfo_step_packed: x_prev and g_prev must both be given or both be NULL");
+  if (B == 0) return MOP_OK;
+  if (!mop_spectrum_step_supported(n) || !mop_tridiag_supported(n)) {
+    mop_set_error("mop_rsirfo_step_packed: n = %d is outside the shared-memory path (3 .. 160)", n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (work_bytes < mop_rsirfo_workspace_bytes(B, n, MOP_EIGH_TRIDIAG)) {
+    mop_set_error("mop_rsirfo_step_packed: workspace too small (%zu < %zu bytes)", work_bytes,
+                  mop_rsirfo_workspace_bytes(B, n, MOP_EIGH_TRIDIAG));
+    return MOP_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  char* w = (char*)work;
+  MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
+  return rsirfo_step_fused(B, n, method, nullptr, saddle_order, neb_mode, trust_min, trust_max, 1, H_packed, Hbias_packed, x, Bg,
+                           g, x_prev, g_prev, Be, state, move_out, eigvals_out, pred_out, status, (double*)w,
+                           (double*)(w + nn), w + nn + nv, stream);
+}
+
+// RSIRFO.run for a batch whose structures use DIFFERENT update methods (method_per [B], device): a NEB chain runs
+// rsirfo_block_fsb at its ends and rsirfo_block_bofill inside (Optimizer/rfo_neb.py:116-121) - one launch instead of
+// one per group.  Full-square Hessians; 3 <= n <= 160; workspace = mop_rsirfo_workspace_bytes(B, n, MOP_EIGH_TRIDIAG).
+extern "C" int mop_rsirfo_step_mixed(int B, int n, const int32_t* method_per, int saddle_order, int neb_mode,
+                                     double trust_min, double trust_max, double* H, const double* Hbias, const double* x,
+                                     const double* Bg, const double* g, const double* x_prev, const double* g_prev,
+                                     const double* Be, double* state, double* move_out, double* eigvals_out,
+                                     double* pred_out, int32_t* status, void* work, size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && n > 0 && n % 3 == 0, "mop_rsirfo_step_mixed: n must be a positive multiple of 3");
+  MOP_REQUIRE(method_per && H && x && Bg && g && state && move_out && status && work,
+              "mop_rsirfo_step_mixed: method_per, H, x, Bg, g, state, move_out, status, work must be device pointers");
+  MOP_REQUIRE(saddle_order >= 0 && saddle_order < n, "mop_rsirfo_step_mixed: bad saddle_order");
+  MOP_REQUIRE((x_prev == nullptr) == (g_prev == nullptr),
+              "mop_rsirfo_step_mixed: x_prev and g_prev must both be given or both be NULL");
+  if (B == 0) return MOP_OK;
+  if (!mop_spectrum_step_supported(n) || !mop_tridiag_supported(n)) {
+    mop_set_error("mop_rsirfo_step_mixed: n = %d is outside the shared-memory path (3 .. 160)", n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (work_bytes < mop_rsirfo_workspace_bytes(B, n, MOP_EIGH_TRIDIAG)) {
+    mop_set_error("mop_rsirfo_step_mixed: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  char* w = (char*)work;
+  MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
+  return rsirfo_step_fused(B, n, MOP_UPD_FLOWCHART, method_per, saddle_order, neb_mode, trust_min, trust_max, 0, H, Hbias,
+                           x, Bg, g, x_prev, g_prev, Be, state, move_out, eigvals_out, pred_out, status, (double*)w,
+                           (double*)(w + nn), w + nn + nv, stream);
 }

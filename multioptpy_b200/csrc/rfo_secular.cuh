@@ -138,6 +138,15 @@ __device__ __forceinline__ double step_derivative(const RfoWork& w, double alpha
 
 // compute_rsprfo_step, rsirfo.py:986-1248.  Leaves the returned step in w.step.
 // `best` is scratch [k].  Returns status bits to OR in.
+//
+// The step does not depend on alpha analytically (solve_rfo scales eigenvalues and gradient alike): the
+// norms the loop sees differ by rounding only and every exit test (converged at once, alpha clipped to a bound, three
+// equal norms) is decided with a wide margin - the replay is exact.  The exception: a secular root within ~1e-6 |pole|
+// of its pole.  The loose stopping rule of the root finder (rsirfo.py:1437-1503) then lets the step norm jump between
+// bisection histories by far more than the loop's 1e-6 test, and the micro-cycle the reference stops on is decided by
+// last-bit differences of its BLAS / numpy sums (machine dependent).  The replay is still carried out, but a loop
+// whose norms spread by more than 1e-7, or that converges / runs out after the first cycle, reports
+// MOP_ST_ALPHA_UNSTABLE: the step is not reproducible to 1e-10, in the reference itself.
 __device__ __forceinline__ int alpha_search(const RfoWork& w, double trust, double* best, int lane) {
   const double alpha0 = 1.0, alpha_max = 1000.0, alpha_step_max = 10.0, step_tol = 1e-3;
   const int max_micro = 40;
@@ -158,9 +167,13 @@ __device__ __forceinline__ int alpha_search(const RfoWork& w, double trust, doub
   double best_diff = INFINITY;
   bool has_left = false, has_right = false;
   double a_left = 0.0, a_right = 0.0;
+  double nmin = INFINITY, nmax = 0.0;
   for (int it = 0; it < max_micro; ++it) {
     const double mu = solve_rfo(w, alpha, lane, nullptr);
     const double nrm = sqrt(warp_norm2(w.step, w.k, lane));
+    nmin = fmin(nmin, nrm);
+    nmax = fmax(nmax, nrm);
+    const int spread = (nmax - nmin > 1e-7) ? MOP_ST_ALPHA_UNSTABLE : 0;
     const double diff = fabs(nrm - trust);
     if (diff < best_diff) {
       for (int i = lane; i < w.k; i += 32) best[i] = w.step[i];
@@ -175,7 +188,7 @@ __device__ __forceinline__ int alpha_search(const RfoWork& w, double trust, doub
       a_right = alpha;
       has_right = true;
     }
-    if (fabs(obj) < 1e-8 || diff < step_tol) return flags;
+    if (fabs(obj) < 1e-8 || diff < step_tol) return it == 0 ? flags : (flags | MOP_ST_ALPHA_UNSTABLE);  // crossed the tolerance by rounding
     // history (fixed-size array in the reference; max_micro entries always fit)
     const double prev0 = hist0, prev1 = hist1;
     hist0 = hist1;
@@ -193,9 +206,10 @@ __device__ __forceinline__ int alpha_search(const RfoWork& w, double trust, doub
       if (has_left && has_right) a_new = fmax(fmin(a_new, a_right * 0.99), a_left * 1.01);
     }
     alpha = fmin(fmax(a_new, 1e-6), alpha_max);
-    if (alpha == alpha_max || alpha == 1e-6) return flags;
-    if (nhist >= 3 && fabs(hist1 - hist0) < 1e-6 && fabs(prev1 - prev0) < 1e-6) return flags;
+    if (alpha == alpha_max || alpha == 1e-6) return flags | spread;
+    if (nhist >= 3 && fabs(hist1 - hist0) < 1e-6 && fabs(prev1 - prev0) < 1e-6) return flags | spread;
   }
+  flags |= MOP_ST_ALPHA_UNSTABLE;
   // micro-cycles exhausted (rsirfo.py:1213-1246)
   if (have_best) {
     const double bn = sqrt(warp_norm2(best, w.k, lane));

@@ -57,6 +57,8 @@ struct FrontArgs {
   const double* state;   // [B][state_stride] or null (MOP_RS_HAVE_PREV)
   int state_stride;
   int method, guards, grad_rule;
+  const int32_t* method_per;  // [B] per-structure update method (overrides `method`) or null: NEB chains mix FSB / Bofill
+  int packed;            // != 0: H and Hbias are packed lower triangles [B][n (n + 1) / 2] (row i at i (i + 1) / 2)
   double* gp_out;        // [B][n] projected gradient
   int32_t* status;       // [B]
 };
@@ -343,7 +345,7 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
   constexpr int THREADS = 32 * NW;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const size_t nn = (size_t)n * n;
-  double* H = f.H + (size_t)b * nn;
+  double* H = f.H + (size_t)b * nn;   // (full-square layout; the packed layout is addressed where it is used)
   double* vs = fr;            // s
   double* vy = vs + np;       // y (after damping)
   double* vu = vy + np;       // u = H s
@@ -356,10 +358,11 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
           MOP_ST_TRROT_RANKDEF);
 
   // ---- s, y, guards, damping (RSIRFO.update_hessian, rsirfo.py:1316-1340) ----------------------------------------
-  const bool asked = f.method != MOP_UPD_NONE && f.xp != nullptr && f.gprev != nullptr;
+  const int method_b = f.method_per ? f.method_per[b] : f.method;
+  const bool asked = method_b != MOP_UPD_NONE && f.xp != nullptr && f.gprev != nullptr;
   const bool have_prev = asked && (f.state == nullptr || f.state[(size_t)b * f.state_stride + MOP_RS_HAVE_PREV] != 0.0);
   bool upd = have_prev;
-  int m = f.method;
+  int m = method_b;
   double ss = 0.0, sy = 0.0, yy = 0.0;
   if (!have_prev) {
     if (asked) st |= MOP_ST_NO_HISTORY;
@@ -405,7 +408,34 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
   __syncthreads();
 
   // ---- one read of H: sym(H) into the triangle, u = H s (and H y) from the same loads ----------------------------
-  if (upd) {
+  const int ntri = (n * (n + 1)) >> 1;
+  if (f.packed) {
+    // packed lower triangle in HBM = the shared-memory layout: a straight coalesced copy, then u = H s as a
+    // thread-per-row symv on the triangle
+    const double* Hpk = f.H + (size_t)b * ntri;
+    for (int e = tid; e < ntri; e += THREADS) L[e] = Hpk[e];
+    __syncthreads();
+    if (upd && tid < n) {
+      const int i = tid;
+      const bool two = m == MOP_UPD_FLOWCHART;
+      double a0 = 0.0, a1 = 0.0;
+      const double* Li = L + tri0(i);
+      for (int j = 0; j <= i; ++j) {
+        const double x = Li[j];
+        a0 = fma(x, vs[j], a0);
+        if (two) a1 = fma(x, vy[j], a1);
+      }
+      const double* p = L + tri0(i + 1) + i;
+      for (int r = i + 1; r < n; ++r) {
+        const double x = p[0];
+        a0 = fma(x, vs[r], a0);
+        if (two) a1 = fma(x, vy[r], a1);
+        p += r + 1;
+      }
+      vu[i] = a0;
+      if (two) hy[i] = a1;
+    }
+  } else if (upd) {
     if (m == MOP_UPD_FLOWCHART) {
       front_half_pass<NW, true, true, 2>(H, n, L, vs, vy, vu, hy, lane, wid);
       __syncthreads();
@@ -484,14 +514,23 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
       }
     }
     __syncthreads();
-    // ---- write H' back (the only write of the Hessian): full rows from the triangle ----------------------------
-    for (int i = wid; i < n; i += NW) {
-      double* row = H + (size_t)i * n;
-      for (int j = lane; j < n; j += 32) row[j] = (j <= i) ? L[tri0(i) + j] : L[tri0(j) + i];
+    // ---- write H' back (the only write of the Hessian): full rows from the triangle, or the triangle itself ------
+    if (f.packed) {
+      double* Hpk = f.H + (size_t)b * ntri;
+      for (int e = tid; e < ntri; e += THREADS) Hpk[e] = L[e];
+    } else {
+      for (int i = wid; i < n; i += NW) {
+        double* row = H + (size_t)i * n;
+        for (int j = lane; j < n; j += 32) row[j] = (j <= i) ? L[tri0(i) + j] : L[tri0(j) + i];
+      }
     }
   }
   // ---- effective Hessian: + sym(Hbias) (rsirfo.py:349-353) -----------------------------------------------------------
-  if (f.Hbias) {
+  if (f.Hbias && f.packed) {
+    const double* Hb = f.Hbias + (size_t)b * ntri;
+    __syncthreads();
+    for (int e = tid; e < ntri; e += THREADS) L[e] += Hb[e];
+  } else if (f.Hbias) {
     const double* Hb = f.Hbias + (size_t)b * nn;
     __syncthreads();
     front_half_pass<NW, true, false, 0>(Hb, n, L, vs, vy, vu, hy, lane, wid);
@@ -929,7 +968,9 @@ int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, doub
 
 // Steps 1-3a of RSIRFO.run in one kernel: Hessian update (method, guards as mop_launch_hessian_update with mode 1),
 // write-back of H, TR/ROT projection of gradient (-> gp_out) and effective Hessian, tridiagonalisation of the latter.
-int mop_launch_front_tridiag_blk(int B, int n, int method, int guards, int grad_rule, double* H, const double* Hbias,
+// packed != 0: H and Hbias are packed lower triangles [B][n (n + 1) / 2].
+int mop_launch_front_tridiag_blk(int B, int n, int method, const int32_t* method_per, int guards, int grad_rule,
+                                 int packed, double* H, const double* Hbias,
                                  const double* x, const double* xp, const double* g, const double* gprev,
                                  const double* Bg, const double* state, int state_stride, double* gp_out,
                                  int32_t* status, double* Vh, double* dd, double* ee, double* tau, double* gq, int* flag,
@@ -940,6 +981,6 @@ int mop_launch_front_tridiag_blk(int B, int n, int method, int guards, int grad_
     return MOP_ERR_UNSUPPORTED;
   }
   mop::PkArgs a{n, nullptr, nullptr, Vh, dd, ee, tau, gq, flag, nullptr};
-  mop::FrontArgs f{H, Hbias, x, xp, g, gprev, Bg, state, state_stride, method, guards, grad_rule, gp_out, status};
+  mop::FrontArgs f{H, Hbias, x, xp, g, gprev, Bg, state, state_stride, method, guards, grad_rule, method_per, packed, gp_out, status};
   return dispatch_blk<true>(B, a, f, stream);
 }

@@ -40,6 +40,7 @@ ST_STEP_NAN_SD = 1 << 7
 ST_HARD_CASE = 1 << 8
 ST_TRROT_RANKDEF = 1 << 9
 ST_BRENT_BRACKET = 1 << 10
+ST_ALPHA_UNSTABLE = 1 << 16
 ST_EIG_NOCONV = 1 << 11
 ST_EIG_FALLBACK = 1 << 12
 ST_NO_HISTORY = 1 << 13
@@ -174,18 +175,42 @@ def new_rsirfo_state(B: int, trust0: float, device) -> torch.Tensor:
     return st
 
 
+def pack_lower(H):
+    """(B, n, n) symmetric -> (B, n (n + 1) / 2) packed lower triangle (row i at i (i + 1) / 2), on the device."""
+    lib = _lib.load()
+    B, n, _ = H.shape
+    _chk(H, "H", (B, n, n))
+    P = torch.empty(B, n * (n + 1) // 2, dtype=torch.float64, device=H.device)
+    with torch.cuda.device(H.device):
+        _lib.check(lib.mop_pack_lower(B, n, _ptr(H), _ptr(P), _stream(H.device)), "mop_pack_lower")
+    return P
+
+
+def unpack_lower(P, n: int):
+    """(B, n (n + 1) / 2) packed lower triangle -> (B, n, n) full symmetric matrix, on the device."""
+    lib = _lib.load()
+    B = P.shape[0]
+    _chk(P, "P", (B, n * (n + 1) // 2))
+    H = torch.empty(B, n, n, dtype=torch.float64, device=P.device)
+    with torch.cuda.device(P.device):
+        _lib.check(lib.mop_unpack_lower(B, n, _ptr(P), _ptr(H), _stream(P.device)), "mop_unpack_lower")
+    return H
+
+
 def rsirfo_step(H, x, Bg, g, state, *, method: int, saddle_order: int = 0, neb_mode: bool = False,
                 Hbias=None, x_prev=None, g_prev=None, Be=None, trust_min: float = 0.01,
-                trust_max: float = 0.5, eigh_algo="auto", out=None):
+                trust_max: float = 0.5, eigh_algo="auto", out=None, packed: bool = False):
     """One RSIRFO.run for every structure of the batch.  H is updated in place.
+    ``packed``: H (and Hbias) are packed lower triangles (B, n (n + 1) / 2) - half the bytes; n <= 160.
     Returns dict(move, eigvals, pred, status)."""
     lib = _lib.load()
     B, n = x.shape
     dev = x.device
-    _chk(H, "H", (B, n, n)); _chk(x, "x", (B, n)); _chk(Bg, "Bg", (B, n)); _chk(g, "g", (B, n))
+    hshape = (B, n * (n + 1) // 2) if packed else (B, n, n)
+    _chk(H, "H", hshape); _chk(x, "x", (B, n)); _chk(Bg, "Bg", (B, n)); _chk(g, "g", (B, n))
     _chk(state, "state", (B, RSIRFO_STATE))
     if Hbias is not None:
-        _chk(Hbias, "Hbias", (B, n, n))
+        _chk(Hbias, "Hbias", hshape)
     if (x_prev is None) != (g_prev is None):
         raise MopError("x_prev and g_prev must be given together")
     if x_prev is not None:
@@ -202,6 +227,31 @@ def rsirfo_step(H, x, Bg, g, state, *, method: int, saddle_order: int = 0, neb_m
         }
     else:
         _chk_out(out, B, n)
+    if isinstance(method, torch.Tensor):   # per-structure update methods (NEB chains): one launch for the batch
+        if packed:
+            raise MopError("rsirfo_step: per-structure methods and packed storage are not combined")
+        _chk(method, "method", (B,), torch.int32)
+        nbytes = lib.mop_rsirfo_workspace_bytes(B, n, EIGH_TRIDIAG)
+        work = workspace(dev, nbytes)
+        with torch.cuda.device(dev):
+            rc = lib.mop_rsirfo_step_mixed(B, n, _ptr(method), int(saddle_order), int(bool(neb_mode)),
+                                           float(trust_min), float(trust_max), _ptr(H), _ptr(Hbias), _ptr(x),
+                                           _ptr(Bg), _ptr(g), _ptr(x_prev), _ptr(g_prev), _ptr(Be), _ptr(state),
+                                           _ptr(out["move"]), _ptr(out["eigvals"]), _ptr(out["pred"]),
+                                           _ptr(out["status"]), _ptr(work), nbytes, _stream(dev))
+        _lib.check(rc, "mop_rsirfo_step_mixed")
+        return out
+    if packed:
+        nbytes = lib.mop_rsirfo_workspace_bytes(B, n, EIGH_TRIDIAG)
+        work = workspace(dev, nbytes)
+        with torch.cuda.device(dev):
+            rc = lib.mop_rsirfo_step_packed(B, n, int(method), int(saddle_order), int(bool(neb_mode)),
+                                            float(trust_min), float(trust_max), _ptr(H), _ptr(Hbias), _ptr(x),
+                                            _ptr(Bg), _ptr(g), _ptr(x_prev), _ptr(g_prev), _ptr(Be), _ptr(state),
+                                            _ptr(out["move"]), _ptr(out["eigvals"]), _ptr(out["pred"]),
+                                            _ptr(out["status"]), _ptr(work), nbytes, _stream(dev))
+        _lib.check(rc, "mop_rsirfo_step_packed")
+        return out
     nbytes = lib.mop_rsirfo_workspace_bytes(B, n, algo_id)
     work = workspace(dev, nbytes)
     with torch.cuda.device(dev):

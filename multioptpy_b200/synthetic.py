@@ -64,3 +64,56 @@ def batch(config: int, B: int, natoms: int, saddle: bool = False):
         x0, H, g0, rng = structure(config, b, natoms, saddle)
         xs.append(x0); Hs.append(H); gs.append(g0); rngs.append(rng)
     return np.stack(xs), np.stack(Hs), np.stack(gs), rngs
+
+
+# ---- config 3 (NEB 64 x 30) and config 4 (conformer / AFIR batch 8192 x N) shapes, SURVEY §8d ----------------------
+def neb_chain(nimg: int, natoms: int, seed: int = 3000):
+    """A NEB chain: linear interpolation between two jittered end points + N(0, 0.05^2), energies from a 1-D
+    double well along the path (uphill, downhill and extremum branches of the tangent rule all occur), seeded
+    gradients and per-image Hessians.  -> X (nimg, n), E (nimg,), G (nimg, n), H (nimg, n, n)."""
+    rng = np.random.default_rng(seed)
+    n = 3 * natoms
+    xa = grid_geometry(natoms, rng).reshape(-1)
+    xb = xa + rng.normal(0.0, 0.3, n)
+    t = np.linspace(0.0, 1.0, nimg)
+    X = xa[None, :] + (xb - xa)[None, :] * t[:, None] + rng.normal(0.0, 0.05, (nimg, n))
+    E = 0.05 * (16.0 * t ** 2 * (1.0 - t) ** 2 - 0.3 * t) - 0.02 * np.sin(6.0 * np.pi * t)   # two wells, ripples
+    G = rng.normal(0.0, 1e-2, (nimg, n))
+    H = np.stack([spd_hessian(n, np.random.default_rng(seed + 40 + i)) for i in range(nimg)])
+    return X, E, G, H
+
+
+def neb_next(X, G, H, delta, rng):
+    """The chain after one NEB move (x - delta, as the caller applies it) with gradients of the local quadratic
+    models plus noise: gives the second iteration its quasi-Newton history."""
+    X1 = X - delta
+    G1 = G + np.einsum("bij,bj->bi", H, X1 - X) + rng.normal(0.0, 1e-4, X.shape)
+    return X1, G1
+
+
+def s8_crown(rng: np.random.Generator, jitter: float) -> np.ndarray:
+    """One S8 crown ring in Bohr (S-S 2.06 A, S-S-S 108 deg: ring radius 2.357 A, puckering +-0.497 A), randomly
+    rotated about its axis, plus Gaussian jitter (A)."""
+    R, h = 2.357, 0.9946
+    phi = rng.uniform(0.0, 2.0 * np.pi) + np.arange(8) * (np.pi / 4.0)
+    p = np.stack([R * np.cos(phi), R * np.sin(phi), 0.5 * h * (-1.0) ** np.arange(8)], axis=1)
+    return (p + rng.normal(0.0, jitter, size=(8, 3))) / 0.52917721067
+
+
+def conformer_batch(B: int, natoms: int, seed: int = 4000, jitter: float = 0.05):
+    """Config 4: B S8-like conformers - natoms / 8 crown rings stacked 4 A apart along z with a random lateral offset,
+    every atom jittered (the model Hessian of the reference then has a handful of mildly negative modes, as for a real
+    distorted ring; a cubic grid of sulfur atoms puts the LJ terms of lindh.py:118-130 at -8 Hartree / Bohr^2) - with raw
+    gradients.  -> xyz (B, natoms, 3) in Bohr, g (B, 3 natoms)."""
+    assert natoms % 8 == 0
+    xyz = np.empty((B, natoms, 3)); g = np.empty((B, 3 * natoms))
+    for b in range(B):
+        rng = np.random.default_rng(seed + b)
+        rings = []
+        for r in range(natoms // 8):
+            ring = s8_crown(rng, jitter)
+            ring += np.array([rng.normal(0.0, 0.3), rng.normal(0.0, 0.3), 4.0 * r]) / 0.52917721067
+            rings.append(ring)
+        xyz[b] = np.concatenate(rings)
+        g[b] = rng.normal(0.0, 1e-2, 3 * natoms)
+    return xyz, g

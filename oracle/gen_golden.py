@@ -318,6 +318,52 @@ def gen_potkeys():
     print("potkeys:", len(keys), "activation keys")
 
 
+def gen_neb_full():
+    """The UNMODIFIED reference RFOOptimizer.optimize (Optimizer/rfo_neb.py:104-208) driven for three NEB iterations:
+    BNEB force, per-image RS-I-RFO with Ayala update, TR_calc, FIRE move, RFO / FIRE combine -> new geometry."""
+    import tempfile, types
+    bn = ref_shim.ref("MEP.pathopt_bneb_force")
+    rn = ref_shim.ref("Optimizer.rfo_neb")
+    nimg, natoms = 9, 10
+    n = 3 * natoms
+    tmp = tempfile.mkdtemp() + "/"
+    cfg = types.SimpleNamespace(NEB_FOLDER_DIRECTORY=tmp, fix_init_edge=False, fix_end_edge=False,
+                                apply_convergence_criteria=False, element_list=synthetic.elements(natoms),
+                                bohr2angstroms=0.52917721067, dt=0.5, a=0.10, n_reset=0, FIRE_N_accelerate=5,
+                                FIRE_f_inc=1.10, FIRE_f_accelerate=0.99, FIRE_f_decelerate=0.5, FIRE_a_start=0.1,
+                                FIRE_dt_max=3.0)
+    rngH = np.random.default_rng(78)
+    H_init = np.stack([synthetic.spd_hessian(n, rngH) for _ in range(nimg)])
+    for i in range(nimg):
+        np.save(os.path.join(tmp, f"tmp_hessian_{i}.npy"), H_init[i])
+    opt = rn.RFOOptimizer(cfg)
+    calc = bn.CaluculationBNEB()
+    X, E, G = neb_chain(nimg, natoms, 41)
+    rec = {k: [] for k in ("X", "E", "G", "V", "Vprev", "new_geom_ang")}
+    V = np.zeros((nimg, natoms, 3)); Vprev = np.zeros((nimg, natoms, 3))
+    prevX = prevG = None
+    rngv = np.random.default_rng(5)
+    for it in range(3):
+        geoms = X.reshape(nimg, natoms, 3).copy(); grads = G.reshape(nimg, natoms, 3).copy()
+        with quiet():
+            new_ang = opt.optimize(geoms, grads, None if prevX is None else prevX.reshape(nimg, natoms, 3),
+                                   None if prevG is None else prevG.reshape(nimg, natoms, 3), it, E.copy(), E.copy(),
+                                   Vprev.copy(), V.copy(), None, None, calc)
+        rec["X"].append(X.copy()); rec["E"].append(E.copy()); rec["G"].append(G.copy())
+        rec["V"].append(V.copy()); rec["Vprev"].append(Vprev.copy()); rec["new_geom_ang"].append(np.asarray(new_ang, float))
+        prevX, prevG = X.copy(), G.copy()
+        Xn, En, Gn = neb_chain(nimg, natoms, 42 + it)
+        X = (np.asarray(new_ang, float) / cfg.bohr2angstroms).reshape(nimg, n)
+        E = En; G = G + 0.3 * (Gn - G)
+        Vprev = V.copy(); V = rngv.normal(0.0, 0.02, (nimg, natoms, 3))
+    blob = {k: np.array(v) for k, v in rec.items()}
+    blob["H_init"] = H_init
+    blob["H_final"] = np.stack([np.load(os.path.join(tmp, f"tmp_hessian_{i}.npy")) for i in range(nimg)])
+    blob["meta"] = np.array([nimg, natoms], np.int64)
+    np.savez_compressed(os.path.join(GOLD, "neb_full.npz"), **blob)
+    print("neb_full: |dx| per iteration", [float(np.abs(rec["new_geom_ang"][i] / cfg.bohr2angstroms - rec["X"][i].reshape(nimg, natoms, 3)).max()) for i in range(3)])
+
+
 def read_xyz(path):
     """Minimal xyz reader (Angstrom) -> (elements, coords in Bohr)."""
     lines = [l.split() for l in open(path).read().strip().splitlines()]
@@ -992,7 +1038,7 @@ def gen_rsprfo_reject():
 
 
 SETS = {"keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
-        "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo, "rsprfo_reject": gen_rsprfo_reject, "rankdef": gen_rankdef, "potkeys": gen_potkeys}
+        "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo, "rsprfo_reject": gen_rsprfo_reject, "rankdef": gen_rankdef, "potkeys": gen_potkeys, "neb_full": gen_neb_full}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

@@ -1651,6 +1651,21 @@ class FIRENEBOracle:
         return Vnew, delta, move.reshape(X.shape), P
 
 
+def neb_optimize_step(orc, X, E, G, V, V_prev, optimize_num, ratio=0.5, fire_cfg=None):
+    """RFOOptimizer.optimize (Optimizer/rfo_neb.py:104-208) from the pieces above: RFO move vectors (orc: a
+    NEBRFOOracle carrying the Hessians), a FRESH FIREOptimizer per call (rfo_neb.py:185) driven with the projected
+    NEB force, and the combine of :196-203 - ends take -rfo, the interior (1 - r) fire - r rfo.
+    X (nimg, n), V / V_prev (nimg, natoms, 3).  Returns the new geometry in Bohr, (nimg, n)."""
+    nimg, n = X.shape
+    F, T, gam, delta, rfo = orc.step(X, E, G)
+    fire = FIRENEBOracle(**(fire_cfg or {}))
+    _, _, fmove, _ = fire.step(X.reshape(nimg, -1, 3), F.reshape(nimg, -1, 3), V, V_prev, optimize_num)
+    fmove = fmove.reshape(nimg, n)
+    move = (1.0 - ratio) * fmove - ratio * rfo
+    move[0] = -rfo[0]; move[-1] = -rfo[-1]
+    return X + move
+
+
 # ---------------------------------------------------------------------------------------------
 # Restraint bias potentials (SURVEY §8f rank 2): Potential/keep_potential.py, keep_angle_potential.py
 # ---------------------------------------------------------------------------------------------

@@ -287,3 +287,46 @@ def test_bias_potential_aggregator_aldol(golden_dir):
     assert abs(Be - 3.794394592266868e-01) < 1e-10
     assert abs(np.linalg.norm(Bg) - 3.827240360969133e-02) < 1e-11
     assert abs(np.linalg.norm(Hb) - 7.463054721281174e-03) < 1e-12
+
+
+# ------------------------------------------------------------------ packed lower-triangular storage
+@pytest.mark.gpu
+@pytest.mark.parametrize("natoms,method,bias", [(11, "rsirfo_bofill", False), (30, "rsirfo_block_fsb", True),
+                                                (50, "rsirfo_bfgs", False), (8, "rsirfo_flowchart", True)])
+def test_rsirfo_packed_storage_vs_oracle(natoms, method, bias):
+    """mop_rsirfo_step_packed (Hessians as packed lower triangles, n (n + 1) / 2 doubles per structure): two steps
+    vs the oracle (1e-10), the updated triangle vs the oracle's Hessian, pack / unpack round trip bit-exact."""
+    import torch
+    from multioptpy_b200 import ops, synthetic
+    from multioptpy_b200.Optimizer.rsirfo import RSIRFO
+    B = 6
+    n = 3 * natoms
+    x0, H0, g0, rngs = synthetic.batch(77, B, natoms)
+    rng = np.random.default_rng(5)
+    Hb = np.zeros_like(H0)
+    if bias:
+        for b in range(B):
+            M = rng.standard_normal((n, 3)); Hb[b] = 0.02 * (M @ M.T)
+    dev = "cuda:0"
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    P = ops.pack_lower(T(H0))
+    assert torch.equal(ops.unpack_lower(P, n), T(H0))
+    opt = RSIRFO(method=method, saddle_order=0, device=dev)
+    opt.set_hessian_packed(P); opt.set_bias_hessian(ops.pack_lower(T(Hb)) if bias else None)
+    z = torch.zeros(B, dtype=torch.float64, device=dev)
+    mv0 = opt.run(T(x0), T(g0), B_e=z, g=T(g0)).cpu().numpy().copy()
+    x1 = np.empty_like(x0); g1 = np.empty_like(g0); oracles = []
+    for b in range(B):
+        o = O.RSIRFOOracle(method=method, saddle_order=0)
+        o.set_hessian(H0[b].copy()); o.set_bias_hessian(Hb[b].copy() if bias else None)
+        m = o.run(x0[b], g0[b], g0[b], None, None, 0.0)
+        assert rel(mv0[b], m) < RTOL, b
+        x1[b], g1[b] = synthetic.second_point(x0[b], H0[b], g0[b], m, rngs[b])
+        oracles.append(o)
+    mv1 = opt.run(T(x1), T(g1), pre_geom=T(x0), B_e=z - 1e-3, g=T(g1), pre_g=T(g0)).cpu().numpy()
+    Hfull = opt.get_hessian().cpu().numpy()
+    for b, o in enumerate(oracles):
+        m = o.run(x1[b], g1[b], g1[b], x0[b], g0[b], -1e-3)
+        assert rel(mv1[b], m) < RTOL, b
+        assert rel(Hfull[b], o.hessian) < RTOL, b
+        assert np.array_equal(Hfull[b], Hfull[b].T)

@@ -138,3 +138,38 @@ def test_gpu_fire_vs_golden(golden_dir):
         assert np.abs(mv - mo).max() <= 1e-9 * np.abs(mo).max(), it       # Angstrom round trip of the return value
         assert np.abs(opt.total_velocity - Vn).max() <= 1e-12 * max(np.abs(Vn).max(), 1e-300), it
         assert (opt.dt, opt.a, opt.n_reset) == (o.dt, o.a, o.n_reset) == tuple(z["state"][it]), it
+
+
+# ------------------------------------------- the whole RFOOptimizer.optimize incl. the RFO / FIRE combine (rfo_neb.py:186-206)
+def test_oracle_full_neb_optimize_vs_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "neb_full.npz"))
+    nimg, natoms = [int(v) for v in z["meta"]]
+    orc = O.NEBRFOOracle(z["H_init"])
+    for it in range(z["X"].shape[0]):
+        new = O.neb_optimize_step(orc, z["X"][it], z["E"][it], z["G"][it], z["V"][it], z["Vprev"][it], it)
+        ref = z["new_geom_ang"][it].reshape(nimg, -1) / 0.52917721067
+        assert np.abs(new - ref).max() <= 1e-10 * np.abs(ref).max(), it
+    assert rel(np.stack(orc.H), z["H_final"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_full_neb_optimize_vs_reference(golden_dir):
+    import types
+    from multioptpy_b200.Optimizer.rfo_neb import RFOOptimizer
+    from multioptpy_b200.Optimizer.fire_neb import FIREOptimizer
+    z = np.load(os.path.join(golden_dir, "neb_full.npz"))
+    nimg, natoms = [int(v) for v in z["meta"]]
+    dev = "cuda:0"
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cfg = types.SimpleNamespace(dt=0.5, a=0.10, n_reset=0, FIRE_N_accelerate=5, FIRE_f_inc=1.10, FIRE_f_accelerate=0.99,
+                                FIRE_f_decelerate=0.5, FIRE_a_start=0.1, FIRE_dt_max=3.0)
+    opt = RFOOptimizer(nimg, natoms, device=dev)
+    opt.set_hessians(T(z["H_init"]))
+    for it in range(z["X"].shape[0]):
+        fire = FIREOptimizer(cfg, device=dev)          # the reference builds a fresh one per call (rfo_neb.py:185)
+        x = T(z["X"][it])
+        move, _ = opt.optimize_step(x, T(z["E"][it]), T(z["G"][it]), fire, T(z["V"][it]), T(z["Vprev"][it]), it)
+        new = (x + move).cpu().numpy()
+        ref = z["new_geom_ang"][it].reshape(nimg, -1) / 0.52917721067
+        assert np.abs(new - ref).max() <= 1e-10 * np.abs(ref).max(), it
+    assert rel(opt.hessian.cpu().numpy(), z["H_final"]) < 1e-9
