@@ -408,6 +408,7 @@ int mop_debug_spectrum_timing(void* buf); /* diagnostics: [B][16] int64 phase cy
 int mop_debug_packed_rowwarp(int on);   /* tuning: fused warp-per-row packed tridiagonalisation k_tridiag_rwf (default 1) or the thread-group kernel k_tridiag_packed (0) */
 int mop_debug_packed_timing(void* buf);   /* diagnostics: [B][16] int64 phase cycles of the packed kernel */
 int mop_debug_packed_threads(int threads); /* tuning: CTA size of the packed kernel (128, 256, 512) */
+int mop_debug_large_blocked(int on);   /* tuning: blocked dlatrd + DMMA cluster tridiagonalisation for n > 160 (default 1) */
 int mop_debug_large_pair(int mode);     /* tuning: two matrices per cluster in lock-step: 0 auto, 1 always, -1 never */
 int mop_debug_large_ablate(int mask); /* diagnostics: bit0 no trailing stores, bit1 no trailing loads (results invalid) */
 int mop_debug_large_timing(void* buf); /* diagnostics: [B][4] int64 phase cycles of the MOP_EIGH_LARGE reduction */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mop_debug_barrier_latency": (_i, [_i, _p, _p]),
     "mop_debug_large_cluster": (_i, [_i]),
     "mop_debug_large_pair": (_i, [_i]),
+    "mop_debug_large_blocked": (_i, [_i]),
     "mop_debug_tri_packed": (_i, [_i]),
     "mop_debug_tri_spectrum": (_i, [_i]),
     "mop_debug_stream_chunk": (_i, [_i]),

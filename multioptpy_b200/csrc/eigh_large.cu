@@ -1165,6 +1165,15 @@ __global__ void k_lg_clear_tau_flagged(int n, const int32_t* __restrict__ status
 // ------------------------------------------------------------------------------------------------
 static size_t lg_al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int g_lg_cluster = 0;
+static int g_lg_blocked = 1;
+// tuning: 1 (default) = blocked dlatrd + DMMA cluster tridiagonalisation (tridiag_cluster.cu), 0 = the unblocked
+// fused update + symv kernels of this file
+extern "C" int mop_debug_large_blocked(int on) {
+  g_lg_blocked = on;
+  return MOP_OK;
+}
+int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, double* ee, double* tau,
+                               int cluster_ctas, cudaStream_t stream);
 static int g_lg_pair = 0;   // 0 auto, 1 always, -1 never
 extern "C" int mop_debug_large_pair(int mode) {
   g_lg_pair = mode;
@@ -1252,6 +1261,9 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     double* gq_dummy = a.pbuf;
     int* flag = (int*)(a.pbuf + (size_t)B * n);
     int rc = mop_launch_tridiag_packed(B, n, a.A, nullptr, a.Vh, a.dd, a.ee, a.tau, gq_dummy, flag, stream);
+    if (rc != MOP_OK) return rc;
+  } else if (g_lg_blocked && g_lg_cluster >= 0) {
+    int rc = mop_launch_tridiag_cluster(B, n, a.A, a.Vh, a.dd, a.ee, a.tau, g_lg_cluster, stream);
     if (rc != MOP_OK) return rc;
   } else {
     int CL = g_lg_cluster;

@@ -87,12 +87,14 @@ __device__ __forceinline__ RfoArrays rfo_carve(double* base, int n) {
 // lam/gam: [n] in shared memory (lam may be modified by the level-shift emulation).
 // identity: the spectrum was non-finite and has been replaced by (1, gp) by the caller.
 // Returns status flags; writes R.coef (indexed like lam), *pred_out, state.
+// MAXJ > 0 (n <= 32 MAXJ): the register-resident secular solver (rfo_secular.cuh), bracket probes on warps 1 and 2.
+template <int MAXJ = 0>
 static __device__ int rfo_core(int n, int saddle_order, int neb_mode, double tmin, double tmax,
                         double* lam, const double* gam, bool identity, double gnorm_raw, double Be,
                         double* st, const RfoArrays& R, double* pred_out) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
   __shared__ int s_k, s_flags;
-  __shared__ double s_trust;
+  __shared__ double s_trust, s_probe[2];
   int flags = 0;
 
   // level shift emulation (rsirfo.py:602-631): eigh(H + 1e-5 I) - 1e-5
@@ -191,8 +193,48 @@ static __device__ int rfo_core(int n, int saddle_order, int neb_mode, double tmi
   const int kk = s_k;
   const double trust = s_trust;
 
-  // RS step in the eigenbasis: warp 0 (rsirfo.py:924-985)
-  if (wid == 0) {
+  // RS step in the eigenbasis (rsirfo.py:924-985)
+  if (MAXJ > 0) {
+    const int nw = nt >> 5;
+    RfoTerms<(MAXJ > 0 ? MAXJ : 1)> w;
+    w.lam = R.lamk;
+    w.gam = R.gamk;
+    w.k = kk;
+    double stepr[(MAXJ > 0 ? MAXJ : 1)];
+    double mu0 = 0.0, n0 = 0.0;
+    bool hard = false;
+    if (wid == 0) {
+      double n2;
+      mu0 = solve_rfo_r(w, 1.0, lane, &hard, stepr, &n2);
+      n0 = sqrt(n2);
+      if (lane == 0) s_flags = (!(n0 <= trust) ? MOP_ST_ALPHA_SEARCH : 0) | (hard ? MOP_ST_HARD_CASE : 0);
+    }
+    __syncthreads();
+    const int sf0 = s_flags;
+    __syncthreads();
+    if (sf0 & MOP_ST_ALPHA_SEARCH) {  // block-uniform
+      // probes of the Brent bracket on the warps that would idle (warp 0 itself when the CTA has no others)
+      const int w_lo = nw > 1 ? 1 : 0, w_hi = nw > 2 ? 2 : w_lo;
+      int f = 0;
+      if (wid == 0) f = alpha_newton_r(w, trust, mu0, n0, stepr, R.w3, lane);
+      if (wid == w_lo) {
+        const double o = alpha_probe_r<(MAXJ > 0 ? MAXJ : 1)>(R.lamk, R.gamk, kk, 1e-6, trust, lane);
+        if (lane == 0) s_probe[0] = o;
+      }
+      if (wid == w_hi) {
+        const double o = alpha_probe_r<(MAXJ > 0 ? MAXJ : 1)>(R.lamk, R.gamk, kk, 1000.0, trust, lane);
+        if (lane == 0) s_probe[1] = o;
+      }
+      if (wid == 0 && lane == 0) s_flags |= f;
+      __syncthreads();
+      if (tid == 0 && s_probe[0] * s_probe[1] < 0.0) s_flags |= MOP_ST_BRENT_BRACKET;  // Brent branch not replayed
+    }
+    if (wid == 0) {
+#pragma unroll
+      for (int u = 0; u < (MAXJ > 0 ? MAXJ : 1); ++u)
+        if (lane + 32 * u < kk) R.stepk[lane + 32 * u] = stepr[u];
+    }
+  } else if (wid == 0) {
     RfoWork w{R.lamk, R.gamk, R.w1, R.w2, R.stepk, kk};
     bool hard = false;
     int f = 0;

@@ -27,9 +27,14 @@
 
 namespace mop {
 
-constexpr int SP_THREADS = 160;
 constexpr int SP_MAX_N = 160;
-constexpr int SP_NW = SP_THREADS / 32;
+// The CTA has one thread per row / eigenvalue, rounded up to whole warps (NW = ceil(n / 32) <= 5), and as many CTAs
+// share an SM as 64 registers per thread allow (58 at NW = 5): small structures (config 4: n = 72, n = 24) are
+// latency chains just like the large ones, only more of them fit.
+template <int NW>
+struct SpMinBlocks {
+  static constexpr int value = NW >= 5 ? 7 : (NW == 4 ? 8 : (NW == 3 ? 10 : (NW == 2 ? 16 : 32)));
+};
 
 struct SpArgs {
   int n;
@@ -59,7 +64,7 @@ struct SpArgs {
 // and from the cluster phase on the whole of Y is recycled: CGS2 pair buffers + dots, then lam_s | gam_s |
 // RfoArrays, then the reflector ring.  Seven CTAs stay under the 164 KB carve-out (92 KB of L1 left for the
 // local-memory spills and the strided cluster accesses).
-__host__ __device__ inline size_t sp_y_doubles(int n) {
+__host__ __device__ inline size_t sp_y_doubles(int n, int SP_NW) {
   const size_t np = (size_t)((n + 3) & ~3);
   size_t y = 2 * np + rfo_core_smem_bytes(n) / sizeof(double) + 8;           // lam_s, gam_s, RfoArrays; ring 12 np
   if (y < 8 * np) y = 8 * np;                                                 // d, e, de + grid-phase scratch
@@ -73,11 +78,11 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 
 // per-warp slot for the CGS2 dot products: behind the five 2-column pair buffers in X
-__device__ __forceinline__ double* gq_dots(double* X, int np, int wid) { return X + (size_t)SP_NW * 2 * np + wid * 64; }
+__device__ __forceinline__ double* gq_dots(double* X, int np, int wid, int nw) { return X + (size_t)nw * 2 * np + wid * 64; }
 
-__global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
-  constexpr int THREADS = SP_THREADS;
-  constexpr int NW = SP_NW;
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, SpMinBlocks<NW>::value) k_spectrum_step(SpArgs a) {
+  constexpr int THREADS = 32 * NW;
   extern __shared__ __align__(16) double sm[];
   const int n = a.n, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int np = (n + 3) & ~3;
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
   double* e = d + np;          // np   e[k] couples k, k+1
   double2* de = (double2*)(e + np);  // np pairs (d_k, e_{k-1}^2): the Sturm table (16-byte aligned: np % 4 == 0)
   double* X = e + 3 * np;      // grid-phase scratch, 4 np
-  unsigned char* blk_s = (unsigned char*)(Y + sp_y_doubles(n));  // index tables: n <= 160 fits a byte
+  unsigned char* blk_s = (unsigned char*)(Y + sp_y_doubles(n, NW));  // index tables: n <= 160 fits a byte
   unsigned char* blk_e = blk_s + np;
   unsigned char* cl_s = blk_e + np;
   unsigned char* rank = cl_s + np;
@@ -419,8 +424,8 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
       // Column c lives in registers (rows lane + 32 u); the dots against the finished columns are taken four
       // at a time (twenty independent loads in flight instead of one dependent round trip per column - the
       // low end of a dense spectrum can chain 10 - 15 eigenvalues into one cluster).
-      constexpr int MAXJ = (SP_MAX_N + 31) / 32;
-      double* dts = gq_dots(Y, np, wid);
+      constexpr int MAXJ = NW;
+      double* dts = gq_dots(Y, np, wid, NW);
       for (int c = 1; c < cs; ++c) {
         double* zc_ = buf + (size_t)c * m;
         double zr[MAXJ];
@@ -551,7 +556,7 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
   if (evals && tid < n) evals[tid] = lam_s[tid];
   double* stp = a.state + (size_t)b * MOP_RSIRFO_STATE;
   int flags = identity ? MOP_ST_EIG_NONFINITE : 0;
-  flags |= rfo_core(n, a.saddle_order, a.neb_mode, a.tmin, a.tmax, lam_s, gam_s, identity, gnorm_raw,
+  flags |= rfo_core<NW>(n, a.saddle_order, a.neb_mode, a.tmin, a.tmax, lam_s, gam_s, identity, gnorm_raw,
                     a.Be ? a.Be[b] : 0.0, stp, R, a.pred ? a.pred + b : nullptr);
   SP_MARK();  // 4: gamma + eigenbasis RFO
 
@@ -561,7 +566,7 @@ __global__ void __launch_bounds__(SP_THREADS, 7) k_spectrum_step(SpArgs a) {
   __syncthreads();
   double* y = gq;
   {
-    constexpr int MAXJ = (SP_MAX_N + 31) / 32;
+    constexpr int MAXJ = NW;
     double cc[MAXJ];
 #pragma unroll
     for (int u = 0; u < MAXJ; ++u) cc[u] = (lane + 32 * u < n) ? cz[lane + 32 * u] : 0.0;
@@ -672,6 +677,16 @@ extern "C" int mop_debug_spectrum_timing(void* buf) {
   return MOP_OK;
 }
 
+template <int NW>
+static int launch_spectrum(int B, const mop::SpArgs& a, cudaStream_t stream) {
+  const int np = (a.n + 3) & ~3;
+  const size_t smem = sizeof(double) * (5 * (size_t)np + mop::sp_y_doubles(a.n, NW)) + 5 * (size_t)np;
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_spectrum_step<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_spectrum_step<NW><<<B, 32 * NW, smem, stream>>>(a);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
 int mop_spectrum_step_supported(int n) { return n >= 3 && n <= mop::SP_MAX_N; }
 
 // T, tau, Q^T gp, flag and the reflector rows Vh come from mop_launch_tridiag_packed; Z and Dm are
@@ -704,10 +719,11 @@ int mop_launch_spectrum_step(int B, int n, int saddle_order, int neb_mode, doubl
   a.tmin = tmin;
   a.tmax = tmax;
   a.dbg = g_sp_dbg;
-  const int np = (n + 3) & ~3;
-  const size_t smem = sizeof(double) * (5 * (size_t)np + mop::sp_y_doubles(n)) + 5 * (size_t)np;
-  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_spectrum_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mop::k_spectrum_step<<<B, mop::SP_THREADS, smem, stream>>>(a);
-  MOP_CHECK_CUDA(cudaGetLastError());
-  return MOP_OK;
+  switch ((n + 31) / 32) {
+    case 1: return launch_spectrum<1>(B, a, stream);
+    case 2: return launch_spectrum<2>(B, a, stream);
+    case 3: return launch_spectrum<3>(B, a, stream);
+    case 4: return launch_spectrum<4>(B, a, stream);
+    default: return launch_spectrum<5>(B, a, stream);
+  }
 }

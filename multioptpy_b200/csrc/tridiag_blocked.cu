@@ -24,6 +24,7 @@
 //
 // Outputs are those of mop_launch_tridiag_packed (LAPACK dsytd2 conventions): d, e, tau, the reflector rows Vh
 // and Q^T g.  Replaces the reduction stage of numpy.linalg.eigh at Optimizer/rsirfo.py:606,626,652.
+#include "dmma.cuh"
 #include "trrot.cuh"
 #include "update_coef.cuh"
 
@@ -67,77 +68,6 @@ constexpr int TB_NB = 6;   // reflectors per panel: 4 scalars + 2 * NB panel pro
 constexpr int TB_WS = 10;  // doubles per row of the W panel: 80-byte rows, eight 128-bit row reads hit 32 banks once
 
 __device__ __forceinline__ int tri0(int i) { return (i * (i + 1)) >> 1; }
-
-// D = A B + C on the FP64 tensor cores: A 8 x 4 (row), B 4 x 8 (col), C / D 8 x 8.  Lane (g = lane / 4,
-// t = lane % 4) holds A(g, t), B(t, g) and C(g, 2 t), C(g, 2 t + 1).
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
-               : "=d"(d0), "=d"(d1)
-               : "d"(a), "d"(b), "d"(c0), "d"(c1));
-}
-
-// Block-wide sums of SIXTEEN values, one barrier.  A transposing butterfly (16 + 8 + 4 + 2 + 2 shuffles instead
-// of 16 x 10) leaves slot j with lanes 2 j, 2 j + 1; the per-warp partials of every slot are summed by every
-// warp in fixed order (deterministic) and handed to all lanes through the warp's own row of `tot`.
-// red: [2][16][NW] (double-buffered by `parity`, so one barrier per call is enough), tot: [NW][16].
-template <int NW>
-__device__ __forceinline__ void block_sum16(double (&r)[16], double* red, double* tot, int& parity, int lane,
-                                            int wid, bool contributes) {
-  double* bq = red + (parity & 1) * (16 * NW);
-  parity ^= 1;
-  if (contributes) {  // warp-uniform
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-    double t8[8], t4[4], t2[2], t1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double send = h16 ? r[j] : r[j + 8];
-      const double keep = h16 ? r[j + 8] : r[j];
-      t8[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double send = h8 ? t8[j] : t8[j + 4];
-      const double keep = h8 ? t8[j + 4] : t8[j];
-      t4[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 8);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const double send = h4 ? t4[j] : t4[j + 2];
-      const double keep = h4 ? t4[j + 2] : t4[j];
-      t2[j] = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 4);
-    }
-    {
-      const double send = h2 ? t2[0] : t2[1];
-      const double keep = h2 ? t2[1] : t2[0];
-      t1 = keep + __shfl_xor_sync(MOP_FULL_MASK, send, 2);
-    }
-    t1 += __shfl_xor_sync(MOP_FULL_MASK, t1, 1);
-    const int slot = lane >> 1;  // (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0)
-    if ((lane & 1) == 0) bq[slot * NW + wid] = t1;
-  } else if (lane < 16) {
-    bq[lane * NW + wid] = 0.0;
-  }
-  __syncthreads();
-  if (!contributes) return;  // a warp without live rows needs no totals
-  double* tw = tot + wid * 16;
-  if (lane < 16) {
-    double t[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) t[w] = bq[lane * NW + w];
-    double acc = t[0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) acc += t[w];
-    tw[lane] = acc;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 16; q += 2) {
-    const double2 v = *reinterpret_cast<const double2*>(tw + q);
-    r[q] = v.x;
-    r[q + 1] = v.y;
-  }
-  __syncwarp();
-}
 
 // Rank-2NB update of the trailing triangle with one finished panel, A(i, j) -= sum_l V(i, l) W(j, l) + W(i, l) V(j, l)
 // for i >= j >= kn, as C + (-P) Q^T with P = [V | W], Q = [W | V] (K = 12): 8 x 8 tiles, three DMMAs each.
@@ -632,7 +562,7 @@ struct TbMinBlocks {
 __host__ __device__ inline size_t tb_smem_doubles(int n, int nw) {
   const size_t np = (size_t)((n + 3) & ~3);
   const size_t nl = ((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1;
-  size_t fr = (size_t)n * TB_WS + (32 * (size_t)nw + 16) + 2 * np + 2 * 16 * (size_t)nw + 16 * (size_t)nw + 4 + 64;
+  size_t fr = (size_t)n * TB_WS + (32 * (size_t)nw + 16) + 2 * np + (size_t)red16_doubles(nw) + 16 * (size_t)nw + 4 + 64;
   const size_t front = 12 * np + 48;  // fused front end: T | Y (or s, y, u, r, H y, coefficient rows) + reduction scratch
   if (fr < front) fr = front;
   return nl + fr;
@@ -653,7 +583,7 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
   double* zrow = uu + NU;           // [np] row-part sums of the symv (permuted lane map)
   double* gq = zrow + np;           // [np] Q^T g
   double* red = gq + np;            // [2][16][NW]
-  double* tot = red + 2 * 16 * NW;  // [NW][16]
+  double* tot = red + red16_doubles(NW);  // [NW][16]
   double* pub = tot + 16 * NW;      // [4]  z_{k+1}, c_{k+1}
   double* s_rb = pub + 4;           // [64] block_sum_k<2> scratch
   int parity = 0, parity2 = 0;
