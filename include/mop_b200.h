@@ -237,6 +237,37 @@ int mop_fischer_hessian(int B, int natoms, const double* xyz, const double* radi
                         double* H_out, int32_t* counts_out, int32_t* status, void* work,
                         size_t work_bytes, void* stream);
 
+/* ---- (3b') Fischer + D3 model Hessian, old variant -----------------------------------------
+ * Replaces FischerD3ApproxHessianOld.main (ModelHessian/fischerd3old.py:355-381), i.e.
+ * ApproxHessian().main(coord, element_list, cart_gradient, "fischerd3old") - what a bare `-modelhess` selects
+ * (interface.py:184-191): the Fischer terms with the linear-angle skips (:195-210) and the sin^2-damped torsion force
+ * constants (:258-300), plus the reference's simplified D3(BJ) pair blocks (:85-128) for every pair that is not bonded
+ * at 1.3 x the covalent radii (:322-352), symmetrisation, TR/ROT projection.
+ * atom_params [B or 1][natoms][4] = {covalent radius (Bohr), D2 C6 (hartree bohr^6), D3 r4r2, D2 vdW radius (Bohr)}
+ * (param_stride 0: one set for the batch); s6, s8, a1, a2: Parameters/d3.py (PBE0: 1.0, 0.7875, 0.4289, 4.4407).
+ * Workspace: mop_fischer_workspace_bytes. */
+int mop_fischer_d3old_hessian(int B, int natoms, const double* xyz, const double* atom_params, int param_stride,
+                              double s6, double s8, double a1, double a2, double* H_out, int32_t* counts_out,
+                              int32_t* status, void* work, size_t work_bytes, void* stream);
+
+/* FischerD3ApproxHessian.main (ModelHessian/fischerd3.py:186-304; `fischerd3`, the AutoTS default, test/config.json):
+ * as above with the table connectivity (factor 1.1) for the torsion bond count and the non-bonded mask, cut-offs 0.1 /
+ * 1e-3, and C6 scaled per atom by clip(1 - 0.05 (CN - CN_ref), 0.75, 1.25) with the fractional coordination number of
+ * :47-62.  atom_params [B or 1][natoms][5] = {..., reference coordination number}. */
+int mop_fischer_d3_hessian(int B, int natoms, const double* xyz, const double* atom_params, int param_stride,
+                           double s6, double s8, double a1, double a2, double* H_out, int32_t* counts_out,
+                           int32_t* status, void* work, size_t work_bytes, void* stream);
+
+/* ---- model Hessian modifiers (ModelHessian/approx_hessian.py:95-110) ---------------------------------------------
+ * "ts": TransitionStateHessian.create_ts_hessian (ModelHessian/tshess.py:14-40) - unless an eigenvalue < -1e-8 exists,
+ * reflect through the lowest mode with |lambda| >= 1e-8: out = sym((1 - 2 v v^T) H).  "clip": eigenvalue smoothing
+ * (approx_hessian.py:103-126): out = V diag(s(lambda)) V^T, s(x) = sign(x) (2 - |x|^-0.1) for |x| >= 1.
+ * evals [B][n], evecs [B][n][n] (rows = eigenvectors): the output of mop_eigh on the same Hessians.  out must not
+ * alias the inputs; modified (optional) [B] = 1 where the reflection was applied. */
+int mop_hessian_ts_modify(int B, int n, const double* H, const double* evals, const double* evecs, double* out,
+                          int32_t* modified, void* stream);
+int mop_hessian_clip_eigvals(int B, int n, const double* evals, const double* evecs, double* out, void* stream);
+
 /* ---- restraint bias potentials --------------------------------------------------------------
  * Replaces calc_energy + torch.func.jacrev / hessian (Potential/potential.py:127-137) for StructKeepPotential
  * (kind 1), StructKeepPotentialv2 (kind 2; Potential/keep_potential.py), StructKeepAnglePotential (kind 3;

@@ -48,6 +48,10 @@ SIGNATURES = {
     "mop_connectivity": (_i, [_i, _i, _p, _p, _i, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_fischer_workspace_bytes": (_sz, [_i, _i]),
     "mop_fischer_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mop_fischer_d3old_hessian": (_i, [_i, _i, _p, _p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _sz, _p]),
+    "mop_hessian_ts_modify": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
+    "mop_hessian_clip_eigvals": (_i, [_i, _i, _p, _p, _p, _p]),
+    "mop_fischer_d3_hessian": (_i, [_i, _i, _p, _p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _sz, _p]),
     "mop_bias_term_bytes": (_sz, []),
     "mop_bias_terms": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_kabsch": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),

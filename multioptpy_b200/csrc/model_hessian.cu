@@ -102,12 +102,47 @@ __device__ __forceinline__ double sin_sq_angle(const double* xa, const double* x
 }
 
 // ---------------------------------------------------------------------------------------
-// kind 0: connectivity tables only; kind 1: Fischer (ModelHessian/fischer.py)
+// D3(BJ) pair block of FischerD3ApproxHessianOld.d3_hessian_contribution (fischerd3old.py:85-128):
+// h_proj u u^T + h_perp (1 - u u^T) with the reference's "simplified" second derivative.  pi / pj: {cov radius, C6, r4r2,
+// vdW radius} of the two atoms; d3c = (s6, s8, a1, a2).
+__device__ __forceinline__ void d3_pair_block(const double* xi, const double* xj, const double* pi, const double* pj,
+                                              const double d3c[4], double blk[9]) {
+  const double dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+  const double r = np_dist(xi, xj);
+  const double c6 = sqrt(pi[1] * pj[1]);
+  const double c8 = 3.0 * c6 * sqrt(pi[2] * pj[2]);
+  const double r0 = pi[3] + pj[3];
+  const double s6 = d3c[0], s8 = d3c[1], a1 = d3c[2], a2 = d3c[3];
+  const double r2 = r * r, r4 = r2 * r2, r5 = r4 * r, r6 = r4 * r2, r7 = r6 * r, r8 = r4 * r4, r9 = r8 * r;
+  const double q6 = a1 * r0 + a2, q8 = a1 * r0 + (a2 + 2.0);
+  const double q62 = q6 * q6, q82 = q8 * q8, q84 = q82 * q82;
+  const double d6 = r6 + q62 * q62 * q62, d8 = r8 + q84 * q84;
+  const double f6 = r6 / d6, f8 = r8 / d8;
+  const double df6 = 6.0 * r5 / d6 - 6.0 * (r6 * r6) / (d6 * d6);
+  const double df8 = 8.0 * r7 / d8 - 8.0 * (r8 * r8) / (d8 * d8);
+  const double g6 = -s6 * c6 * ((-6.0 / r7) * f6 + (1.0 / r6) * df6);
+  const double g8 = -s8 * c8 * ((-8.0 / r9) * f8 + (1.0 / r8) * df8);
+  const double hpar = s6 * c6 / r8 * (42.0 * f6 - r * df6) + s8 * c8 / (r8 * r2) * (72.0 * f8 - r * df8);
+  const double hperp = (g6 + g8) / r;
+  const double u[3] = {dx / r, dy / r, dz / r};
+  for (int p = 0; p < 3; ++p)
+    for (int m = 0; m < 3; ++m) {
+      const double P = u[p] * u[m];
+      blk[3 * p + m] = hpar * P + hperp * ((p == m ? 1.0 : 0.0) - P);
+    }
+}
+
+// kind 0: connectivity tables only; kind 1: Fischer (ModelHessian/fischer.py); kind 2: Fischer + D3, old variant
+// (ModelHessian/fischerd3old.py: linear-angle skips, sin^2-damped torsions, D3(BJ) blocks for the non-bonded pairs;
+// rad_all then holds FOUR doubles per atom: covalent radius, D2 C6, D3 r4r2, D2 vdW radius); kind 3: Fischer + "dynamic"
+// D3 (ModelHessian/fischerd3.py: C6 scaled by the fractional coordination number against a reference valence, the
+// 1.1-factor connectivity for the torsion bond count and the non-bonded mask; FIVE doubles per atom, + reference CN)
 __global__ void __launch_bounds__(MH_THREADS, 4)
 k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const double* __restrict__ rad_all,
                 int rad_stride, double factor, int capB, int capA, int capD, int* __restrict__ bonds_all,
                 int* __restrict__ angles_all, int* __restrict__ dihs_all, int* __restrict__ counts_all,
-                ICRec* __restrict__ rec_all, double* __restrict__ H_all, int32_t* __restrict__ status) {
+                ICRec* __restrict__ rec_all, double* __restrict__ H_all, int32_t* __restrict__ status, double s6,
+                double s8, double a1, double a2) {
   extern __shared__ double sm[];
   const int b = blockIdx.x, tid = threadIdx.x;
   double* xyz = sm;              // 3N
@@ -117,7 +152,9 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
   int* nb13 = wtot + 36;         // N : neighbour count with the 1.3 factor (Fischer bond_sum)
   unsigned char* bm = (unsigned char*)(nb13 + N + (N & 1));  // N*N
   for (int i = tid; i < 3 * N; i += MH_THREADS) xyz[i] = xyz_all[(size_t)b * 3 * N + i];
-  for (int i = tid; i < N; i += MH_THREADS) rad[i] = rad_all[(size_t)b * rad_stride + i];
+  const int pw = kind == 2 ? 4 : (kind == 3 ? 5 : 1);  // doubles per atom in rad_all
+  const double* prm4 = rad_all + (size_t)b * rad_stride * pw;
+  for (int i = tid; i < N; i += MH_THREADS) rad[i] = prm4[(size_t)i * pw];
   __syncthreads();
   bond_matrix(N, xyz, rad, factor, bm);
   ConnTables T;
@@ -138,9 +175,24 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
   ICRec* rec = rec_all + (size_t)b * (capB + capA + capD);
   const int nrec = T.nb + T.na + T.nd;
   // bond_sum uses a SECOND connectivity with factor 1.3 (fischer.py:17,63)
+  double* cscale = (double*)(bm + (((size_t)N * N + 7) & ~(size_t)7));  // kind 3: [N] CN scaling of C6
   for (int i = tid; i < N; i += MH_THREADS) {
     int c = 0;
+    double cn = 0.0;
     for (int j = 0; j < N; ++j) {
+      if (kind == 3) {
+        // calc_coordination_numbers (fischerd3.py:47-62): 1 / (1 + exp(clip(-16 (4/3 r / rcov - 1), -100, 100))),
+        // the diagonal (r = inf) included, which adds 1 / (1 + e^-100) to every atom
+        double term = -100.0;
+        if (j != i) {
+          const double d = np_dist(xyz + 3 * i, xyz + 3 * j);
+          term = -16.0 * ((4.0 / 3.0) * (d / __dadd_rn(rad[i], rad[j])) - 1.0);
+          term = fmin(fmax(term, -100.0), 100.0);
+        }
+        cn += 1.0 / (1.0 + exp(term));
+        if (j != i) c += bm[i * N + j];   // neighbor_counts = bond_mat.sum(axis=1) (fischerd3.py:138)
+        continue;
+      }
       if (j == i) continue;
       const int lo = i < j ? i : j, hi = i < j ? j : i;  // dist = ||coord[lo] - coord[hi]||
       const double d = np_dist(xyz + 3 * lo, xyz + 3 * hi);
@@ -148,6 +200,7 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
       c += d <= __dmul_rn(cs, 1.3);
     }
     nb13[i] = c;
+    if (kind == 3) cscale[i] = fmin(fmax(1.0 - 0.05 * (cn - prm4[(size_t)i * 5 + 4]), 0.75), 1.25);
   }
   __syncthreads();
   for (int t = tid; t < nrec; t += MH_THREADS) {
@@ -160,7 +213,7 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
       r.atom[0] = i; r.atom[1] = j;
       const double rij = np_dist(xyz + 3 * i, xyz + 3 * j);
       const double rcov = __dadd_rn(rad[i], rad[j]);
-      r.k = 0.3601 * exp(-1.944 * (rij - rcov));
+      r.k = (kind == 3 && rij < 0.1) ? 0.0 : 0.3601 * exp(-1.944 * (rij - rcov));
       stretch2(xyz + 3 * i, xyz + 3 * j, r.b, r.b + 3);
     } else if (t < T.nb + T.na) {  // fischer_angle (:100-131)
       const int* a = T.angles + 3 * (t - T.nb);
@@ -171,14 +224,41 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
       const double val = cij * cjk;
       r.k = fabs(val) < 1e-10 ? 0.0
                               : 0.089 + 0.11 / pow(val, -0.42) * exp(-0.44 * (rij + rjk - cij - cjk));
-      bend2(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k, r.b, nullptr, nullptr);
+      bool skip = false;
+      if (kind >= 2) {  // fischerd3old.py:195-210, fischerd3.py:104-117: overlapping atoms and (anti)parallel arms are skipped
+        const double* xi = xyz + 3 * i; const double* xj = xyz + 3 * j; const double* xk = xyz + 3 * k;
+        const double dt = (xi[0] - xj[0]) * (xk[0] - xj[0]) + (xi[1] - xj[1]) * (xk[1] - xj[1]) +
+                          (xi[2] - xj[2]) * (xk[2] - xj[2]);
+        skip = rij < 0.1 || rjk < 0.1 || fabs(dt / (rij * rjk)) > 0.9999;
+      }
+      if (skip) r.k = 0.0;
+      else bend2(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k, r.b, nullptr, nullptr);
     } else {  // fischer_dihedral (:133-210)
       const int* a = T.dihs + 4 * (t - T.nb - T.na);
       const int i = a[0], j = a[1], k = a[2], l = a[3];
       r.atom[0] = i; r.atom[1] = j; r.atom[2] = k; r.atom[3] = l;
-      const double s1 = sin_sq_angle(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k);
-      const double s2 = sin_sq_angle(xyz + 3 * j, xyz + 3 * k, xyz + 3 * l);
-      if (!(s1 < 1.0e-3 || s2 < 1.0e-3)) {
+      double s1, s2, damp = 1.0;
+      bool ok;
+      if (kind >= 2) {  // fischerd3old.py:258-300 (cut-offs 1e-8 / 1e-4), fischerd3.py:143-163 (0.1 / 1e-3)
+        const double* xi = xyz + 3 * i; const double* xj = xyz + 3 * j; const double* xk = xyz + 3 * k; const double* xl = xyz + 3 * l;
+        const double nji = np_dist(xi, xj), njk = np_dist(xk, xj), nkl = np_dist(xl, xk);
+        const double nmin = kind == 3 ? 0.1 : 1e-8, smin = kind == 3 ? 1e-3 : 1e-4;
+        ok = !(nji < nmin || njk < nmin || nkl < nmin);
+        if (ok) {
+          const double d1 = (xi[0] - xj[0]) * (xk[0] - xj[0]) + (xi[1] - xj[1]) * (xk[1] - xj[1]) + (xi[2] - xj[2]) * (xk[2] - xj[2]);
+          const double d2 = -((xk[0] - xj[0]) * (xl[0] - xk[0]) + (xk[1] - xj[1]) * (xl[1] - xk[1]) + (xk[2] - xj[2]) * (xl[2] - xk[2]));
+          const double c1 = d1 / (nji * njk), c2 = d2 / (njk * nkl);
+          s1 = 1.0 - fmin(c1 * c1, 1.0);
+          s2 = 1.0 - fmin(c2 * c2, 1.0);
+          ok = !(s1 < smin || s2 < smin);
+          damp = s1 * s2;
+        }
+      } else {
+        s1 = sin_sq_angle(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k);
+        s2 = sin_sq_angle(xyz + 3 * j, xyz + 3 * k, xyz + 3 * l);
+        ok = !(s1 < 1.0e-3 || s2 < 1.0e-3);
+      }
+      if (ok) {
         const double rjk = np_dist(xyz + 3 * j, xyz + 3 * k);
         const double cjk = __dadd_rn(rad[j], rad[k]);
         const int bond_sum = nb13[j] + nb13[k] - 2;
@@ -186,6 +266,7 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
         r.k = fabs(val) < 1e-10
                   ? 0.0
                   : 0.0015 + 14.0 * pow((double)max(bond_sum, 0), 0.57) / pow(val, 4.0) * exp(-2.85 * (rjk - cjk));
+        r.k *= damp;
         torsion2(xyz + 3 * i, xyz + 3 * j, xyz + 3 * k, xyz + 3 * l, r.b);
       }
     }
@@ -212,10 +293,39 @@ k_model_hessian(int kind, int N, const double* __restrict__ xyz_all, const doubl
       if (pa < 0 || pc < 0) continue;
       const double k = r->k;
       if (k == 0.0) continue;  // skipped dihedral (reference `continue`s before accumulating)
+      if (kind >= 2) {  // force_const * np.outer(b_m, b_n) (fischerd3old.py:168-229)
 #pragma unroll
-      for (int p = 0; p < 3; ++p)
+        for (int p = 0; p < 3; ++p)
 #pragma unroll
-        for (int m = 0; m < 3; ++m) acc[3 * p + m] += k * r->b[3 * pa + p] * r->b[3 * pc + m];
+          for (int m = 0; m < 3; ++m) acc[3 * p + m] += k * (r->b[3 * pa + p] * r->b[3 * pc + m]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int m = 0; m < 3; ++m) acc[3 * p + m] += k * r->b[3 * pa + p] * r->b[3 * pc + m];
+      }
+    }
+    if (kind >= 2) {  // d3_dispersion_hessian (fischerd3old.py:322-352): non-bonded (factor 1.3) pairs, r >= 0.1;
+                      // fischerd3.py:205-214: not bonded in the table connectivity, r > 0.1, C6 scaled by the CN factors
+      const double d3c[4] = {s6, s8, a1, a2};
+      for (int o = (a == c ? 0 : c); o < (a == c ? N : c + 1); ++o) {
+        if (o == a) continue;
+        const int hi = a > o ? a : o, lo = a > o ? o : a;  // the reference's pair (i > j)
+        const double d = np_dist(xyz + 3 * hi, xyz + 3 * lo);
+        double ph[4], pl[4];
+        if (kind == 2) {
+          if (d <= __dmul_rn(__dadd_rn(rad[hi], rad[lo]), 1.3) || d < 0.1) continue;
+          for (int q = 0; q < 4; ++q) { ph[q] = prm4[4 * (size_t)hi + q]; pl[q] = prm4[4 * (size_t)lo + q]; }
+        } else {
+          if (bm[hi * N + lo] || !(d > 0.1)) continue;
+          for (int q = 0; q < 4; ++q) { ph[q] = prm4[5 * (size_t)hi + q]; pl[q] = prm4[5 * (size_t)lo + q]; }
+          ph[1] *= cscale[hi];
+          pl[1] *= cscale[lo];
+        }
+        double blk[9];
+        d3_pair_block(xyz + 3 * hi, xyz + 3 * lo, ph, pl, d3c, blk);
+        for (int q = 0; q < 9; ++q) acc[q] += (a == c) ? blk[q] : -blk[q];
+      }
     }
     // upper triangle is authoritative: cart_hess[i, j] = cart_hess[j, i] for j < i (fischer.py:229-231)
     for (int p = 0; p < 3; ++p)
@@ -376,7 +486,7 @@ int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias,
                              cudaStream_t stream);
 
 static size_t mh_smem(int N) {
-  return sizeof(double) * (4 * (size_t)N) + sizeof(int) * (40 + (size_t)N + 1) + (size_t)N * N + 16;
+  return sizeof(double) * (5 * (size_t)N + 2) + sizeof(int) * (40 + (size_t)N + 1) + (size_t)N * N + 16;
 }
 
 extern "C" int mop_connectivity(int B, int natoms, const double* xyz, const double* radii,
@@ -396,7 +506,7 @@ extern "C" int mop_connectivity(int B, int natoms, const double* xyz, const doub
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_model_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mop::k_model_hessian<<<B, mop::MH_THREADS, smem, (cudaStream_t)stream>>>(
       0, natoms, xyz, radii, radii_stride, factor, capB, capA, capD, bonds, angles, dihedrals, counts,
-      nullptr, nullptr, status);
+      nullptr, nullptr, status, 0.0, 0.0, 0.0, 0.0);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
@@ -451,7 +561,7 @@ extern "C" int mop_fischer_hessian(int B, int natoms, const double* xyz, const d
   MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_model_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mop::k_model_hessian<<<B, mop::MH_THREADS, smem, stream>>>(1, natoms, xyz, radii, radii_stride, 1.1, cb, ca,
                                                            cd, bonds, angles, dihs, counts, rec, Hraw,
-                                                           status);
+                                                           status, 0.0, 0.0, 0.0, 0.0);
   MOP_CHECK_CUDA(cudaGetLastError());
   if (counts_out)
     MOP_CHECK_CUDA(cudaMemcpyAsync(counts_out, counts, sizeof(int32_t) * 3 * (size_t)B,
@@ -459,6 +569,64 @@ extern "C" int mop_fischer_hessian(int B, int natoms, const double* xyz, const d
   return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, 0, stream);
 }
 
+
+// FischerD3ApproxHessianOld.main (ModelHessian/fischerd3old.py:355-381): H_out [B][3N][3N], TR/ROT projected.
+// atom_params [B or 1][natoms][4] = {covalent radius (Bohr), D2 C6 (hartree bohr^6), D3 r4r2, D2 vdW radius (Bohr)};
+// d3 = (s6, s8, a1, a2).  Workspace: mop_fischer_workspace_bytes.
+static int fischer_d3_common(int kind, int B, int natoms, const double* xyz, const double* atom_params,
+                             int param_stride, double s6, double s8, double a1, double a2, double* H_out,
+                             int32_t* counts_out, int32_t* status, void* work, size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && natoms > 0, "mop_fischer_d3old_hessian: B >= 0 and natoms > 0 required");
+  MOP_REQUIRE(xyz && atom_params && H_out && work, "mop_fischer_d3old_hessian: xyz, atom_params, H_out, work required");
+  MOP_REQUIRE(param_stride == 0 || param_stride == natoms, "mop_fischer_d3old_hessian: param_stride must be 0 or natoms");
+  if (B == 0) return MOP_OK;
+  if (work_bytes < mop_fischer_workspace_bytes(B, natoms)) {
+    mop_set_error("mop_fischer_d3old_hessian: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int cb, ca, cd;
+  fischer_caps(natoms, &cb, &ca, &cd);
+  char* w = (char*)work;
+  int32_t* bonds = (int32_t*)w;
+  int32_t* angles = bonds + (size_t)B * 2 * cb;
+  int32_t* dihs = angles + (size_t)B * 3 * ca;
+  int32_t* counts = dihs + (size_t)B * 4 * cd;
+  size_t off = ((size_t)B * (2 * cb + 3 * ca + 4 * cd + 4) * sizeof(int32_t) + 255) & ~(size_t)255;
+  mop::ICRec* rec = (mop::ICRec*)(w + off);
+  off += ((size_t)B * (cb + ca + cd) * sizeof(mop::ICRec) + 255) & ~(size_t)255;
+  double* Hraw = (double*)(w + off);
+  const size_t smem = mh_smem(natoms);
+  if (smem > 200 * 1024) {
+    mop_set_error("mop_fischer_d3old_hessian: natoms = %d too large", natoms);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_model_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_model_hessian<<<B, mop::MH_THREADS, smem, stream>>>(kind, natoms, xyz, atom_params, param_stride, 1.1, cb, ca, cd,
+                                                           bonds, angles, dihs, counts, rec, Hraw, status, s6, s8, a1, a2);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  if (counts_out)
+    MOP_CHECK_CUDA(cudaMemcpyAsync(counts_out, counts, sizeof(int32_t) * 3 * (size_t)B, cudaMemcpyDeviceToDevice, stream));
+  return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int mop_fischer_d3old_hessian(int B, int natoms, const double* xyz, const double* atom_params,
+                                         int param_stride, double s6, double s8, double a1, double a2, double* H_out,
+                                         int32_t* counts_out, int32_t* status, void* work, size_t work_bytes,
+                                         void* stream_) {
+  return fischer_d3_common(2, B, natoms, xyz, atom_params, param_stride, s6, s8, a1, a2, H_out, counts_out, status, work,
+                           work_bytes, stream_);
+}
+
+// FischerD3ApproxHessian.main (ModelHessian/fischerd3.py:186-304, the variant the AutoTS configurations select):
+// atom_params [B or 1][natoms][5] = {covalent radius, D2 C6, D3 r4r2, D2 vdW radius, reference coordination number}.
+extern "C" int mop_fischer_d3_hessian(int B, int natoms, const double* xyz, const double* atom_params,
+                                      int param_stride, double s6, double s8, double a1, double a2, double* H_out,
+                                      int32_t* counts_out, int32_t* status, void* work, size_t work_bytes,
+                                      void* stream_) {
+  return fischer_d3_common(3, B, natoms, xyz, atom_params, param_stride, s6, s8, a1, a2, H_out, counts_out, status, work,
+                           work_bytes, stream_);
+}
 
 static size_t lindh_smem(int N) {
   const size_t M = (size_t)N * (N - 1) / 2;

@@ -1,0 +1,125 @@
+// Eigenvalue-based modifiers of a model Hessian (ModelHessian/approx_hessian.py:95-110), applied after the base model:
+//   "ts"   TransitionStateHessian.create_ts_hessian (ModelHessian/tshess.py:14-40): reflect the Hessian through the
+//          lowest non-zero mode, sym((1 - 2 v v^T) H), unless a negative eigenvalue exists already;
+//   "clip" eigenvalue smoothing (approx_hessian.py:103-126): V diag(smooth(lambda)) V^T with
+//          smooth(x) = sign(x) (2 - |x|^-0.1) for |x| >= 1.
+// Both take the eigendecomposition from mop_eigh (rows of `evecs` = eigenvectors, ascending).  One CTA per structure.
+#include "common.cuh"
+
+namespace mop {
+
+__global__ void __launch_bounds__(256) k_ts_modify(int n, const double* __restrict__ H_all,
+                                                   const double* __restrict__ evals_all,
+                                                   const double* __restrict__ evecs_all, double* __restrict__ out_all,
+                                                   int32_t* __restrict__ modified) {
+  extern __shared__ double sm[];
+  double* v = sm;      // [n] target eigenvector
+  double* u = v + n;   // [n] H^T v
+  __shared__ int s_neg, s_count;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  const double* H = H_all + (size_t)b * n * n;
+  const double* ev = evals_all + (size_t)b * n;
+  double* out = out_all + (size_t)b * n * n;
+  if (tid == 0) {
+    int neg = 0, count = 0;
+    for (int i = 0; i < n; ++i) neg |= ev[i] < -1e-8;          // tshess.py:19
+    for (int i = 0; i < n; ++i) {                               // :23-28: leading (numerically) zero modes
+      if (fabs(ev[i]) < 1e-8) ++count;
+      else break;
+    }
+    s_neg = neg;
+    s_count = count;
+  }
+  __syncthreads();
+  const bool keep = s_neg || s_count >= n;  // (all modes zero: the reference indexes out of range; left unchanged here)
+  if (tid == 0 && modified) modified[b] = keep ? 0 : 1;
+  if (keep) {
+    for (size_t e = tid; e < (size_t)n * n; e += blockDim.x) out[e] = H[e];
+    return;
+  }
+  const double* vec = evecs_all + ((size_t)b * n + s_count) * n;
+  for (int i = tid; i < n; i += blockDim.x) {
+    v[i] = vec[i];
+    u[i] = 0.0;
+  }
+  __syncthreads();
+  // u_j = sum_k v_k H_kj: warps over row blocks, lanes over columns (coalesced); per-warp partials combined through atomics
+  // would not be deterministic - every thread owns columns instead
+  for (int j = tid; j < n; j += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc = fma(v[k], H[(size_t)k * n + j], acc);
+    u[j] = acc;
+  }
+  __syncthreads();
+  (void)lane; (void)w; (void)nw;
+  // ts = 1/2 (M + M^T), M = H - 2 v u^T  (tshess.py:33-38)
+  for (size_t e = tid; e < (size_t)n * n; e += blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    const double mij = H[e] - 2.0 * v[i] * u[j];
+    const double mji = H[(size_t)j * n + i] - 2.0 * v[j] * u[i];
+    out[e] = 0.5 * (mij + mji);
+  }
+}
+
+__device__ __forceinline__ double smooth_eigval(double x) {  // approx_hessian.py:119-126, alpha = 0.1
+  const double a = fabs(x);
+  if (a >= 1.0) return sgn(x) * (2.0 - 1.0 / pow(a, 0.1));
+  return x;
+}
+
+// out = V diag(smooth(lambda)) V^T; evecs rows = eigenvectors.  32 x 32 output tiles, k-loop through shared memory.
+__global__ void __launch_bounds__(256) k_clip_recompose(int n, const double* __restrict__ evals_all,
+                                                        const double* __restrict__ evecs_all,
+                                                        double* __restrict__ out_all) {
+  __shared__ double A[32][33], Bt[32][33], lam[32];
+  const int b = blockIdx.z, ti = blockIdx.y * 32, tj = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const double* V = evecs_all + (size_t)b * n * n;
+  const double* ev = evals_all + (size_t)b * n;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    for (int r = ty; r < 32; r += 8) {  // A[k][i] = V[k0 + k][ti + i], Bt[k][j] = V[k0 + k][tj + j]
+      const int k = k0 + r;
+      A[r][tx] = (k < n && ti + tx < n) ? V[(size_t)k * n + ti + tx] : 0.0;
+      Bt[r][tx] = (k < n && tj + tx < n) ? V[(size_t)k * n + tj + tx] : 0.0;
+    }
+    if (threadIdx.x < 32) lam[threadIdx.x] = k0 + threadIdx.x < n ? smooth_eigval(ev[k0 + threadIdx.x]) : 0.0;
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const double bj = Bt[k][tx] * lam[k];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(A[k][ty + 8 * q], bj, acc[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = ti + ty + 8 * q, j = tj + tx;
+    if (i < n && j < n) out_all[(size_t)b * n * n + (size_t)i * n + j] = acc[q];
+  }
+}
+
+}  // namespace mop
+
+// TransitionStateHessian.create_ts_hessian for a batch: H, out [B][n][n] (out may not alias H), evals [B][n] and evecs
+// [B][n][n] from mop_eigh(H); modified (optional) [B]: 1 where the reflection was applied.
+extern "C" int mop_hessian_ts_modify(int B, int n, const double* H, const double* evals, const double* evecs, double* out,
+                                     int32_t* modified, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0 && H && evals && evecs && out && out != H, "mop_hessian_ts_modify: bad arguments");
+  if (B == 0) return MOP_OK;
+  mop::k_ts_modify<<<B, 256, sizeof(double) * 2 * n, (cudaStream_t)stream>>>(n, H, evals, evecs, out, modified);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+// The "clip" modifier: out = V diag(smooth(lambda)) V^T from mop_eigh's (evals, evecs).
+extern "C" int mop_hessian_clip_eigvals(int B, int n, const double* evals, const double* evecs, double* out,
+                                        void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0 && evals && evecs && out && out != evecs, "mop_hessian_clip_eigvals: bad arguments");
+  if (B == 0) return MOP_OK;
+  dim3 grid((n + 31) / 32, (n + 31) / 32, B);
+  mop::k_clip_recompose<<<grid, 256, 0, (cudaStream_t)stream>>>(n, evals, evecs, out);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}

@@ -7,6 +7,7 @@ linear algebra.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -360,6 +361,63 @@ def fischer_hessian(xyz, radii):
                                      _ptr(work), nbytes, _stream(xyz.device))
     _lib.check(rc, "mop_fischer_hessian")
     return H, counts, status
+
+
+def fischer_d3old_hessian(xyz, atom_params, d3=None, dynamic=False):
+    """FischerD3ApproxHessianOld.main (dynamic=True: FischerD3ApproxHessian.main) for every structure: (B, 3N, 3N)
+    projected model Hessians.  atom_params (N, 4) or (B, N, 4): covalent radius, D2 C6, D3 r4r2, D2 vdW radius
+    (ModelHessian.fischerd3old.d3_atom_params; dynamic: 5 columns, + the reference coordination number);
+    d3 = (s6, s8, a1, a2), default: the reference's PBE0 values."""
+    from .Parameters import tables
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3))
+    if not isinstance(atom_params, torch.Tensor):
+        atom_params = torch.from_numpy(np.ascontiguousarray(np.asarray(atom_params, dtype=np.float64))).to(xyz.device)
+    npar = 5 if dynamic else 4
+    if atom_params.dim() == 2:
+        _chk(atom_params, "atom_params", (N, npar)); stride = 0
+    else:
+        _chk(atom_params, "atom_params", (B, N, npar)); stride = N
+    s6, s8, a1, a2 = d3 if d3 is not None else (tables.D3_S6, tables.D3_S8, tables.D3_A1, tables.D3_A2)
+    H = torch.empty(B, 3 * N, 3 * N, dtype=torch.float64, device=xyz.device)
+    counts = torch.zeros(B, 3, dtype=torch.int32, device=xyz.device)
+    status = torch.zeros(B, dtype=torch.int32, device=xyz.device)
+    nbytes = lib.mop_fischer_workspace_bytes(B, N)
+    work = workspace(xyz.device, nbytes)
+    with torch.cuda.device(xyz.device):
+        fn = lib.mop_fischer_d3_hessian if dynamic else lib.mop_fischer_d3old_hessian
+        rc = fn(B, N, _ptr(xyz), _ptr(atom_params), stride, float(s6), float(s8), float(a1), float(a2), _ptr(H),
+                _ptr(counts), _ptr(status), _ptr(work), nbytes, _stream(xyz.device))
+    _lib.check(rc, "mop_fischer_d3old_hessian")
+    return H, counts, status
+
+
+def hessian_ts_modify(H):
+    """TransitionStateHessian.create_ts_hessian (ModelHessian/tshess.py) for a batch -> (H_ts, modified [B])."""
+    lib = _lib.load()
+    B, n, _ = H.shape
+    _chk(H, "H", (B, n, n))
+    evals, evecs, st = eigh(H)
+    out = torch.empty_like(H)
+    mod = torch.zeros(B, dtype=torch.int32, device=H.device)
+    with torch.cuda.device(H.device):
+        rc = lib.mop_hessian_ts_modify(B, n, _ptr(H), _ptr(evals), _ptr(evecs), _ptr(out), _ptr(mod), _stream(H.device))
+    _lib.check(rc, "mop_hessian_ts_modify")
+    return out, mod
+
+
+def hessian_clip_eigvals(H):
+    """The "clip" modifier of ApproxHessian.main (approx_hessian.py:103-126): V diag(smooth(lambda)) V^T."""
+    lib = _lib.load()
+    B, n, _ = H.shape
+    _chk(H, "H", (B, n, n))
+    evals, evecs, st = eigh(H)
+    out = torch.empty_like(H)
+    with torch.cuda.device(H.device):
+        rc = lib.mop_hessian_clip_eigvals(B, n, _ptr(evals), _ptr(evecs), _ptr(out), _stream(H.device))
+    _lib.check(rc, "mop_hessian_clip_eigvals")
+    return out
 
 
 def afir(xyz, frag1, frag2, radii_f32, gamma, want_grad: bool = True, want_hess: bool = True):

@@ -1037,7 +1037,34 @@ def gen_rsprfo_reject():
     np.savez_compressed(os.path.join(GOLD, "rsprfo_reject.npz"), **blob)
 
 
-SETS = {"keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+MODELHESS_EXTRA = {   # exactly linear and near-linear molecules: the skip / damping branches of the D3 variants
+    "co2": (["O", "C", "O"], np.array([[-2.2, 0.0, 0.0], [0.0, 0.0, 0.0], [2.2, 0.0, 0.0]])),
+    "hcch": (["H", "C", "C", "H"], np.array([[-3.15, 0.0, 0.0], [-1.14, 0.0, 0.0], [1.14, 0.0, 0.0], [3.15, 0.0, 0.0]])),
+    "hccf_bent": (["H", "C", "C", "F"], np.array([[-3.15, 0.03, 0.0], [-1.14, 0.0, 0.0], [1.14, 0.0, 0.01], [3.5, -0.02, 0.0]])),
+    "h2o2": (["O", "O", "H", "H"], np.array([[1.6, 0.0, -4.0], [1.6, 0.46, -2.64], [2.43, 0.05, -2.32], [0.79, -0.52, -4.02]]) / 0.52917721067),
+}
+MODELHESS_TYPES = ["fischerd3old", "fischerd3", "fischerts", "fischerclip", "fischerd3oldtsclip", "fischerd3clip"]
+
+
+def gen_modelhess_d3():
+    """fischerd3old / fischerd3 and the ts / clip modifiers through the reference's own dispatcher
+    (ApproxHessian.main, ModelHessian/approx_hessian.py:30-112)."""
+    ah = ref_shim.ref("ModelHessian.approx_hessian")
+    cases = [(n, *producer_geometry(n, p)) for n, p in PRODUCER_CASES] + [(n, e, x) for n, (e, x) in MODELHESS_EXTRA.items()]
+    blob = {"names": np.array([c[0] for c in cases]), "types": np.array(MODELHESS_TYPES)}
+    for name, elems, xyz in cases:
+        N = len(elems)
+        blob[f"{name}/elements"] = np.array(elems)
+        blob[f"{name}/xyz"] = np.asarray(xyz, float)
+        for t in MODELHESS_TYPES:
+            with quiet():
+                H = ah.ApproxHessian().main(np.asarray(xyz, float).copy(), list(elems), np.zeros((N, 3)), t)
+            blob[f"{name}/{t}"] = np.asarray(H, float)
+        print("modelhess_d3 case", name, N, "atoms")
+    np.savez_compressed(os.path.join(GOLD, "modelhess_d3.npz"), **blob)
+
+
+SETS = {"modelhess_d3": gen_modelhess_d3, "keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo, "rsprfo_reject": gen_rsprfo_reject, "rankdef": gen_rankdef, "potkeys": gen_potkeys, "neb_full": gen_neb_full}
 
 if __name__ == "__main__":

@@ -919,6 +919,198 @@ def fischer_hessian(coord, radii):
     return project_hessian_trrot(H, coord.reshape(-1))
 
 
+def d3_pair_block(r_vec, r, c6i, c6j, r4r2i, r4r2j, r0, s6, s8, a1, a2):
+    """FischerD3ApproxHessianOld.d3_hessian_contribution, ModelHessian/fischerd3old.py:85-128: the 3 x 3 block
+    h_proj P + h_perp (1 - P) of one non-bonded pair (BJ damping; the 'simplified' second derivative of the
+    reference, not the analytic one)."""
+    c6 = math.sqrt(c6i * c6j)
+    c8 = 3.0 * c6 * math.sqrt(r4r2i * r4r2j)
+    d6 = r ** 6 + (a1 * r0 + a2) ** 6
+    d8 = r ** 8 + (a1 * r0 + (a2 + 2.0)) ** 8
+    f6 = r ** 6 / d6
+    f8 = r ** 8 / d8
+    df6 = 6 * r ** 5 / d6 - 6 * r ** 12 / d6 ** 2
+    df8 = 8 * r ** 7 / d8 - 8 * r ** 16 / d8 ** 2
+    g6 = -s6 * c6 * ((-6.0 / r ** 7) * f6 + (1.0 / r ** 6) * df6)
+    g8 = -s8 * c8 * ((-8.0 / r ** 9) * f8 + (1.0 / r ** 8) * df8)
+    u = r_vec / r
+    P = np.outer(u, u)
+    h_proj = s6 * c6 / r ** 8 * (42.0 * f6 - r * df6) + s8 * c8 / r ** 10 * (72.0 * f8 - r * df8)
+    h_perp = (g6 + g8) / r
+    return h_proj * P + h_perp * (np.eye(3) - P)
+
+
+def fischerd3old_hessian(coord, prm, d3=(1.0, 0.7875, 0.4289, 4.4407)):
+    """FischerD3ApproxHessianOld.main, ModelHessian/fischerd3old.py:355-381 - the model Hessian a bare `-modelhess`
+    selects (interface.py:184-191).  prm (N, 4): covalent radius, D2 C6 (hartree bohr^6), D3 r4r2, D2 vdW radius
+    (Bohr); d3 = (s6, s8, a1, a2), PBE0 defaults of Parameters/d3.py."""
+    coord = np.asarray(coord, float)
+    prm = np.asarray(prm, float)
+    radii = prm[:, 0]
+    N = len(coord)
+    H = np.zeros((3 * N, 3 * N))
+    bonds, angles, dihs = connectivity_tables(coord, radii, 1.1)
+    dist = np.linalg.norm(coord[:, None, :] - coord[None, :, :], axis=-1)
+    bm13 = dist <= (radii[:, None] + radii[None, :]) * 1.3             # get_bond_connectivity (:131-150)
+    np.fill_diagonal(bm13, False)
+
+    def add(atoms, k, b):
+        for a in range(len(atoms)):
+            for c in range(len(atoms)):
+                H[3 * atoms[a]:3 * atoms[a] + 3, 3 * atoms[c]:3 * atoms[c] + 3] += k * np.outer(b[a], b[c])
+
+    for i, j in bonds:                                                    # fischer_bond (:153-183)
+        r = np.linalg.norm(coord[i] - coord[j])
+        k = 0.3601 * math.exp(-1.944 * (r - (radii[i] + radii[j])))
+        add([i, j], k, w_stretch(coord[i], coord[j])[1])
+    for i, j, k_ in angles:                                               # fischer_angle (:186-233)
+        v1 = coord[i] - coord[j]; v2 = coord[k_] - coord[j]
+        r1 = np.linalg.norm(v1); r2 = np.linalg.norm(v2)
+        if r1 < 0.1 or r2 < 0.1:
+            continue
+        if abs(np.dot(v1, v2) / (r1 * r2)) > 0.9999:
+            continue
+        c1 = radii[i] + radii[j]; c2 = radii[j] + radii[k_]
+        val = c1 * c2
+        k = 0.0 if abs(val) < 1e-10 else 0.089 + 0.11 / val ** (-0.42) * math.exp(-0.44 * (r1 + r2 - c1 - c2))
+        add([i, j, k_], k, w_bend(coord[i], coord[j], coord[k_])[1])
+    for i, j, k_, l in dihs:                                              # fischer_dihedral (:236-319)
+        vji = coord[i] - coord[j]; vjk = coord[k_] - coord[j]; vkl = coord[l] - coord[k_]
+        r = np.linalg.norm(vjk); rc = radii[j] + radii[k_]
+        bond_sum = int(bm13[j].sum() + bm13[k_].sum() - 2)
+        val = r * rc
+        k = 0.0 if abs(val) < 1e-10 else 0.0015 + 14.0 * max(bond_sum, 0) ** 0.57 / val ** 4.0 * math.exp(-2.85 * (r - rc))
+        nji = np.linalg.norm(vji)
+        if nji < 1e-8 or r < 1e-8:
+            continue
+        c1 = np.dot(vji, vjk) / (nji * r)
+        nkl = np.linalg.norm(vkl)
+        if nkl < 1e-8:
+            continue
+        c2 = np.dot(-vjk, vkl) / (r * nkl)
+        s1 = 1.0 - min(c1 ** 2, 1.0); s2 = 1.0 - min(c2 ** 2, 1.0)
+        if s1 < 1e-4 or s2 < 1e-4:
+            continue
+        add([i, j, k_, l], k * (s1 * s2), w_torsion(coord[i], coord[j], coord[k_], coord[l]))
+    s6, s8, a1, a2 = d3
+    for i in range(N):                                                    # d3_dispersion_hessian (:322-352)
+        for j in range(i):
+            if bm13[i, j]:
+                continue
+            rv = coord[i] - coord[j]
+            r = np.linalg.norm(rv)
+            if r < 0.1:
+                continue
+            blk = d3_pair_block(rv, r, prm[i, 1], prm[j, 1], prm[i, 2], prm[j, 2], prm[i, 3] + prm[j, 3], s6, s8, a1, a2)
+            H[3 * i:3 * i + 3, 3 * i:3 * i + 3] += blk
+            H[3 * j:3 * j + 3, 3 * j:3 * j + 3] += blk
+            H[3 * i:3 * i + 3, 3 * j:3 * j + 3] -= blk
+            H[3 * j:3 * j + 3, 3 * i:3 * i + 3] -= blk
+    H = (H + H.T) / 2.0
+    return project_hessian_trrot(H, coord.reshape(-1))
+
+
+def fischerd3_hessian(coord, prm, d3=(1.0, 0.7875, 0.4289, 4.4407)):
+    """FischerD3ApproxHessian.main, ModelHessian/fischerd3.py:186-304 (the finite-value fallbacks at :290-302 are not
+    restated: they only fire on NaN input).  prm (N, 5): covalent radius, D2 C6, D3 r4r2, D2 vdW radius, reference
+    coordination number."""
+    coord = np.asarray(coord, float)
+    prm = np.asarray(prm, float)
+    radii = prm[:, 0]
+    N = len(coord)
+    H = np.zeros((3 * N, 3 * N))
+    bm = bond_matrix(coord, radii, 1.1).astype(bool)
+    bonds, angles, dihs = connectivity_tables(coord, radii, 1.1)
+    dist = np.linalg.norm(coord[:, None, :] - coord[None, :, :], axis=-1)
+    rm = dist.copy(); np.fill_diagonal(rm, np.inf)                        # calc_coordination_numbers (:47-62)
+    with np.errstate(over="ignore"):
+        term = np.clip(-16.0 * ((4.0 / 3.0) * (rm / (radii[:, None] + radii[None, :])) - 1.0), -100, 100)
+    cn = np.sum(1.0 / (1.0 + np.exp(term)), axis=1)
+
+    def add(atoms, k, b):
+        for a in range(len(atoms)):
+            for c in range(len(atoms)):
+                H[3 * atoms[a]:3 * atoms[a] + 3, 3 * atoms[c]:3 * atoms[c] + 3] += k * np.outer(b[a], b[c])
+
+    for i, j in bonds:                                                    # fischer_bond (:83-100)
+        rv = coord[i] - coord[j]
+        r = np.linalg.norm(rv)
+        if r < 0.1:
+            continue
+        k = 0.3601 * math.exp(-1.944 * (r - (radii[i] + radii[j])))
+        u = rv / r
+        add([i, j], k, [u, -u])
+    for i, j, k_ in angles:                                               # fischer_angle (:102-135)
+        v1 = coord[i] - coord[j]; v2 = coord[k_] - coord[j]
+        r1 = np.linalg.norm(v1); r2 = np.linalg.norm(v2)
+        if r1 < 0.1 or r2 < 0.1:
+            continue
+        if abs(np.dot(v1, v2) / (r1 * r2)) > 0.9999:
+            continue
+        c1 = radii[i] + radii[j]; c2 = radii[j] + radii[k_]
+        val = c1 * c2
+        k = 0.0 if abs(val) < 1e-10 else 0.089 + 0.11 / val ** (-0.42) * math.exp(-0.44 * (r1 + r2 - c1 - c2))
+        add([i, j, k_], k, w_bend(coord[i], coord[j], coord[k_])[1])
+    ncount = bm.sum(axis=1)
+    for i, j, k_, l in dihs:                                              # fischer_dihedral (:137-184)
+        vji = coord[i] - coord[j]; vjk = coord[k_] - coord[j]; vkl = coord[l] - coord[k_]
+        nji, njk, nkl = np.linalg.norm(vji), np.linalg.norm(vjk), np.linalg.norm(vkl)
+        if min(nji, njk, nkl) < 0.1:
+            continue
+        c1 = np.dot(vji, vjk) / (nji * njk)
+        c2 = np.dot(-vjk, vkl) / (njk * nkl)
+        s1 = 1.0 - min(c1 ** 2, 1.0); s2 = 1.0 - min(c2 ** 2, 1.0)
+        if s1 < 1e-3 or s2 < 1e-3:
+            continue
+        bond_sum = int(ncount[j] + ncount[k_] - 2)
+        rc = radii[j] + radii[k_]
+        val = njk * rc
+        k = 0.0 if abs(val) < 1e-10 else 0.0015 + 14.0 * max(bond_sum, 0) ** 0.57 / val ** 4.0 * math.exp(-2.85 * (njk - rc))
+        b = w_torsion(coord[i], coord[j], coord[k_], coord[l])
+        if not np.all(np.isfinite(b)):
+            continue
+        add([i, j, k_, l], k * (s1 * s2), b)
+    s6, s8, a1, a2 = d3
+    scale = np.clip(1.0 - 0.05 * (cn - prm[:, 4]), 0.75, 1.25)            # dynamic C6 (:232-237)
+    for i in range(N):
+        for j in range(i):
+            if bm[i, j] or not dist[i, j] > 0.1:
+                continue
+            blk = d3_pair_block(coord[i] - coord[j], dist[i, j], prm[i, 1] * scale[i], prm[j, 1] * scale[j], prm[i, 2],
+                                prm[j, 2], prm[i, 3] + prm[j, 3], s6, s8, a1, a2)
+            H[3 * i:3 * i + 3, 3 * i:3 * i + 3] += blk
+            H[3 * j:3 * j + 3, 3 * j:3 * j + 3] += blk
+            H[3 * i:3 * i + 3, 3 * j:3 * j + 3] -= blk
+            H[3 * j:3 * j + 3, 3 * i:3 * i + 3] -= blk
+    H = (H + H.T) / 2.0
+    return project_hessian_trrot(H, coord.reshape(-1))
+
+
+def ts_hessian(H):
+    """TransitionStateHessian.create_ts_hessian, ModelHessian/tshess.py:14-40."""
+    lam, V = np.linalg.eigh(H)
+    if np.any(lam < -1e-8):
+        return H
+    count = 0
+    for x in lam:
+        if abs(x) < 1e-8:
+            count += 1
+        else:
+            break
+    v = V[:, count]
+    M = (np.eye(len(lam)) - 2.0 * np.outer(v, v)) @ H
+    return 0.5 * (M + M.T)
+
+
+def clip_hessian(H, alpha=0.1):
+    """The "clip" modifier, ModelHessian/approx_hessian.py:103-126."""
+    lam, V = np.linalg.eigh(H)
+    out = lam.astype(float, copy=True)
+    m = np.abs(lam) >= 1.0
+    out[m] = np.sign(lam[m]) * (2.0 - 1.0 / (np.abs(lam)[m] ** alpha))
+    return V @ (np.diag(out) @ V.T)
+
+
 # --------------------------------------------------------------------------
 # AFIR bias potential (Potential/AFIR_potential.py:18-55 + autograd, potential.py:130-135)
 # --------------------------------------------------------------------------
