@@ -1,6 +1,7 @@
 """Drop-in for ``multioptpy.Potential.potential.BiasPotentialCalculation`` (Potential/potential.py:53-202)
 restricted to the potentials built on the device: sums the bias energy / gradient / Hessian of every AFIR
-term and of the keep (distance, fragment distance, angle, dihedral) restraints of ``force_data``; every other
+term, of the keep (distance, fragment distance, angle, dihedral, out-of-plane angle, anharmonic) restraints, of the
+fragment well potential and of the LJ repulsive potential (scale / value units) of ``force_data``; every other
 potential the reference would activate raises ``MopError`` (``active_keys`` walks the reference's key list).
 The reference's side effects (.npy / .log files, :144,191-192) are not reproduced."""
 from __future__ import annotations
@@ -31,7 +32,30 @@ _ACTIVATION = {
     "asymmetric_ellipsoidal_repulsive_potential_eps": "len", "asymmetric_ellipsoidal_repulsive_potential_v2_eps": "len",
 }
 _HANDLED = {"AFIR_gamma", "keep_pot_spring_const", "keep_pot_v2_spring_const", "keep_angle_spring_const",
-            "keep_dihedral_angle_spring_const"}
+            "keep_dihedral_angle_spring_const", "anharmonic_keep_pot_spring_const", "well_pot_wall_energy",
+            "keep_out_of_plain_angle_spring_const", "repulsive_potential_well_scale"}
+
+
+def lj_pair_terms(element_list, fragm_1, fragm_2, well, dist, unit):
+    """LJRepulsivePotentialScale / Value (LJ_repulsive_potential.py:9-114) expanded into one term per atom pair of
+    the fragment product (torch.meshgrid(..., indexing='ij') order).  "scale": eps, sigma = sqrt(scale^2 p_i p_j) in the
+    reference's FLOAT32 arithmetic (its UFF tables go through torch.tensor(list of Python floats)); "value": kJ/mol and
+    Angstrom converted in float64."""
+    from ..Parameters import tables
+    terms = []
+    for a in fragm_1:
+        for b in fragm_2:
+            if unit == "scale":
+                ea, eb = element_list[a - 1], element_list[b - 1]
+                w = torch.sqrt(well ** 2 * torch.tensor([tables.UFF_VDW_WELL_DEPTH[ea]]) * torch.tensor([tables.UFF_VDW_WELL_DEPTH[eb]]))
+                d = torch.sqrt(dist ** 2 * torch.tensor([tables.UFF_VDW_DISTANCE[ea]]) * torch.tensor([tables.UFF_VDW_DISTANCE[eb]]))
+                eps, sig = float(w[0]), float(d[0])
+            elif unit == "value":
+                eps, sig = well / tables.HARTREE2KJMOL, dist / tables.BOHR2ANG
+            else:
+                raise MopError("repulsive_potential_unit must be 'scale' or 'value'")
+            terms.append((ops.BIAS_LJ_PAIR, [a - 1], [b - 1], eps, sig))
+    return terms
 
 
 def active_keys(force_data):
@@ -111,6 +135,31 @@ class BiasPotentialCalculation:
                 if k != 0.0:
                     phi0 = float(torch.deg2rad(torch.tensor(float(force_data["keep_dihedral_angle_angle"][i]), dtype=torch.float64)))
                     terms.append((ops.BIAS_KEEP_DIHEDRAL, [a - 1 for a in force_data["keep_dihedral_angle_atom_pairs"][i]],
+                                  [], float(k), phi0))
+        from ..Parameters import tables
+        for i, k in enumerate(force_data.get("anharmonic_keep_pot_spring_const", [])):      # potential.py:673-685
+            if k != 0.0:
+                depth = float(force_data["anharmonic_keep_pot_potential_well_depth"][i])
+                if depth != 0.0:                                   # (zero depth: the reference's energy is the constant 0)
+                    a, b = force_data["anharmonic_keep_pot_atom_pairs"][i]
+                    terms.append((ops.BIAS_ANHARMONIC_KEEP, [a - 1], [b - 1], float(k),
+                                  float(force_data["anharmonic_keep_pot_distance"][i]), [depth]))
+        for i, wv in enumerate(force_data.get("well_pot_wall_energy", [])):                  # potential.py:687-698
+            if wv != 0.0:
+                lim = [float(v) / tables.BOHR2ANG for v in force_data["well_pot_limit_dist"][i]]
+                terms.append((ops.BIAS_WELL, [a - 1 for a in force_data["well_pot_fragm_1"][i]],
+                              [a - 1 for a in force_data["well_pot_fragm_2"][i]], float(wv) / tables.HARTREE2KJMOL, 0.0, lim))
+        for i, wv in enumerate(force_data.get("repulsive_potential_well_scale", [])):        # potential.py:574-604
+            if wv != 0.0:
+                terms += lj_pair_terms(element_list, force_data["repulsive_potential_Fragm_1"][i],
+                                       force_data["repulsive_potential_Fragm_2"][i], float(wv),
+                                       float(force_data["repulsive_potential_dist_scale"][i]),
+                                       force_data["repulsive_potential_unit"][i])
+        if N > 3:                                                                            # potential.py:796-809
+            for i, k in enumerate(force_data.get("keep_out_of_plain_angle_spring_const", [])):
+                if k != 0.0:
+                    phi0 = float(torch.deg2rad(torch.tensor(float(force_data["keep_out_of_plain_angle_angle"][i]), dtype=torch.float64)))
+                    terms.append((ops.BIAS_KEEP_OOP, [a - 1 for a in force_data["keep_out_of_plain_angle_atom_pairs"][i]],
                                   [], float(k), phi0))
         if terms:
             dev = torch.device(self.device)

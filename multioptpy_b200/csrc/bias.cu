@@ -7,6 +7,15 @@
 //   kind 4  StructKeepDihedralAnglePotential (keep_dihedral_angle_potential.py:6-154)  E = 1/2 k wrap(phi - phi0)^2
 //           S(|n1|^2) S(|n2|^2) with the smoothstep collinearity switch; phi0 arrives in RADIANS (the reference
 //           converts degrees in float32 or float64 depending on the caller - the host mirror reproduces that)
+//   kind 5  one atom pair of LJRepulsivePotentialScale / Value (LJ_repulsive_potential.py:9-114)
+//           E = eps (-2 (sigma / r)^6 + (sigma / r)^12); the host expands the fragment product and derives eps, sigma
+//           (the "scale" unit in the reference's float32 arithmetic)
+//   kind 6  StructAnharmonicKeepPotential (anharmonic_keep_potential.py:14-27)  E = D (1 - exp(-sqrt(k / 2D) (r - r0)))^2
+//   kind 7  WellPotential (switching_potential.py:5-67)  flat-bottomed well between two fragment centroids with
+//           quintic switching walls: limits a < b < c < d
+//   kind 8  StructKeepOutofPlainAnglePotential (keep_outofplain_angle_potential.py:6-146)  E = 1/2 k (phi - phi0)^2,
+//           phi = atan2(a1 . n, sqrt(|a1|^2 - (a1 . n)^2)) the elevation of a1 over the plane (a2, a3); zero when the
+//           plane is undefined (|a2 x a3|^2 < 1e-8)
 // The reference differentiates calc_energy with torch.func.jacrev / hessian on the CPU
 // (Potential/potential.py:127-137); here thread (term, coordinate pair) evaluates the same expression once in
 // hyper-dual arithmetic.  Results are ADDED to E, grad, hess (the aggregator sums all bias terms).
@@ -21,7 +30,16 @@ struct BiasTerm {
   int n1, n2;             // atoms in fragment 1 / 2 (kind 1: 1, 1; kind 3 / 4: atoms i, j, k (, l) in `atoms`, n1 = 3 / 4)
   int atoms[BIAS_MAXA];   // 0-based
   double k, p;            // spring constant; r0 in Angstrom (kinds 1, 2), theta0 in degrees (kind 3), phi0 in radians (kind 4)
+  double q[4];            // kind 6: q[0] = well depth; kind 7: k = wall energy (Hartree), q = a, b, c, d (Bohr);
+                          // kind 5: k = eps (Hartree), p = sigma (Bohr); kind 8: p = phi0 in radians
 };
+
+__device__ __forceinline__ HD hd_exp(HD x) { const double e = exp(x.f); return hd_unary(x, e, e, e); }
+__device__ __forceinline__ HD hd_pow_int(HD x, int n) {
+  HD r = hd_const(1.0);
+  for (int i = 0; i < n; ++i) r = r * x;
+  return r;
+}
 
 __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) {
   // coordinate index c = 3 * (position in t.atoms) + component; seeds on ca, cb
@@ -40,6 +58,58 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     }
     const HD d = hd_clamp_min(hd_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12);
     const HD diff = d - hd_const(t.p / BOHR2ANG);
+    return (0.5 * t.k) * (diff * diff);
+  }
+  if (t.kind == 5 || t.kind == 6) {  // atom pair
+    HD v[3];
+    for (int c = 0; c < 3; ++c) v[c] = X(0, c) - X(1, c);
+    const HD r = hd_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (t.kind == 5) {
+      const HD x = hd_const(t.p) / r;
+      const HD x2 = x * x, x6 = x2 * x2 * x2;
+      return t.k * (x6 * x6 - 2.0 * x6);
+    }
+    const HD ex = hd_exp((-sqrt(t.k / (2.0 * t.q[0]))) * (r - hd_const(t.p / BOHR2ANG)));
+    const HD om = hd_const(1.0) - ex;
+    return t.q[0] * (om * om);
+  }
+  if (t.kind == 7) {
+    HD v[3];
+    for (int c = 0; c < 3; ++c) {
+      HD s1 = hd_const(0.0), s2 = hd_const(0.0);
+      for (int a = 0; a < t.n1; ++a) s1 = s1 + X(a, c);
+      for (int a = 0; a < t.n2; ++a) s2 = s2 + X(t.n1 + a, c);
+      v[c] = (1.0 / t.n1) * s1 - (1.0 / t.n2) * s2;
+    }
+    const HD r = hd_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double a = t.q[0], b = t.q[1], c = t.q[2], d = t.q[3];
+    const HD xs = (0.5 / (b - a)) * r + hd_const(1.0 - 0.5 * b / (b - a));
+    const HD xl = (0.5 / (c - d)) * r + hd_const(1.0 - 0.5 * c / (c - d));
+    auto wall = [](HD x) -> HD {  // 2 - 20 x^3 + 30 x^4 - 12 x^5
+      const HD x3 = x * x * x;
+      return hd_const(2.0) - 20.0 * x3 + 30.0 * (x3 * x) - 12.0 * (x3 * x * x);
+    };
+    if (r.f <= a) return t.k * (hd_const(2.875) - 3.75 * xs);
+    if (r.f <= b) return t.k * wall(xs);
+    if (r.f < c) return hd_const(0.0);
+    if (r.f < d) return t.k * wall(xl);
+    return t.k * (hd_const(2.875) - 3.75 * xl);
+  }
+  if (t.kind == 8) {
+    HD a1[3], a2[3], a3[3], nn[3];
+    for (int c = 0; c < 3; ++c) {
+      a1[c] = X(1, c) - X(0, c);
+      a2[c] = X(2, c) - X(0, c);
+      a3[c] = X(3, c) - X(0, c);
+    }
+    hd_cross(a2, a3, nn);
+    const HD nsq = hd_dot(nn, nn);
+    if (nsq.f < 1e-8) return hd_const(0.0);  // torch.where(is_undefined_plane, 0, .)
+    const HD inn = hd_recip(hd_clamp_min(hd_sqrt(nsq), 1e-12));
+    const HD h = hd_dot(a1, nn) * inn;
+    const HD a1sq = hd_dot(a1, a1);          // (|a1|)^2 of the reference: sqrt then square, same value to rounding
+    const HD rp = hd_sqrt(hd_clamp_min(a1sq - h * h, 0.0));
+    const HD diff = hd_atan2(h, rp) - hd_const(t.p);
     return (0.5 * t.k) * (diff * diff);
   }
   const double PI = 3.141592653589793;
@@ -124,7 +194,8 @@ __global__ void __launch_bounds__(128) k_bias_terms(int N, const BiasTerm* __res
   const int b = blockIdx.y, n = 3 * N;
   if (threadIdx.x == 0) t = terms[blockIdx.x];
   __syncthreads();
-  const int m = t.kind == 3 ? 3 : (t.kind == 4 ? 4 : t.n1 + t.n2), nc = 3 * m;
+  const int m = t.kind == 3 ? 3 : ((t.kind == 4 || t.kind == 8) ? 4 : ((t.kind == 5 || t.kind == 6) ? 2 : t.n1 + t.n2));
+  const int nc = 3 * m;
   const double* xyz = xyz_all + (size_t)b * n;
   for (int w = threadIdx.x; w < nc * nc; w += blockDim.x) {
     const int ca = w / nc, cb = w - ca * nc;

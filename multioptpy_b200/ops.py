@@ -739,19 +739,26 @@ def neb_fire_advance(vneb, force, prev_velocity, dt, reset):
 
 # ------------------------------------------------------------------ restraint bias potentials
 BIAS_KEEP, BIAS_KEEP_V2, BIAS_KEEP_ANGLE, BIAS_KEEP_DIHEDRAL = 1, 2, 3, 4   # kind 4: p = phi0 in RADIANS
+# kind 5: k = eps (Hartree), p = sigma (Bohr); kind 6: k, p = r0 (Angstrom), q[0] = well depth; kind 7: k = wall energy
+# (Hartree), q = the four limits (Bohr); kind 8: atoms centre, probe, plane 1, plane 2; p = phi0 in RADIANS
+BIAS_LJ_PAIR, BIAS_ANHARMONIC_KEEP, BIAS_WELL, BIAS_KEEP_OOP = 5, 6, 7, 8
 BIAS_MAXA = 64
 
 
 def pack_bias_terms(terms, device):
-    """terms: list of (kind, frag1 (0-based atoms), frag2, k, p) -> uint8 device tensor for bias_terms."""
+    """terms: list of (kind, frag1 (0-based atoms), frag2, k, p[, q (up to four extra parameters)]) -> uint8 device
+    tensor for bias_terms."""
     import numpy as _np
     lib = _lib.load()
     rec = int(lib.mop_bias_term_bytes())
-    dt = _np.dtype([("kind", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("atoms", "<i4", (BIAS_MAXA,)), ("pad", "<i4"), ("k", "<f8"), ("p", "<f8")])
+    dt = _np.dtype([("kind", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("atoms", "<i4", (BIAS_MAXA,)), ("pad", "<i4"), ("k", "<f8"), ("p", "<f8"), ("q", "<f8", (4,))])
     if dt.itemsize != rec:
         raise MopError(f"bias term layout mismatch ({dt.itemsize} != {rec})")
     buf = _np.zeros(len(terms), dtype=dt)
-    for i, (kind, f1, f2, k, p) in enumerate(terms):
+    for i, term in enumerate(terms):
+        kind, f1, f2, k, p = term[:5]
+        q = list(term[5]) if len(term) > 5 else []
+        buf[i]["q"][: len(q)] = q
         at = list(f1) + list(f2)
         if len(at) > BIAS_MAXA:
             raise MopError("bias term: more than 64 atoms")

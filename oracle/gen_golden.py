@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import contextlib
 import io
+import json
 import os
 import sys
 
@@ -798,6 +799,63 @@ def gen_keep():
     np.savez_compressed(os.path.join(GOLD, "keep.npz"), **blob)
 
 
+def gen_bias2():
+    """LJ repulsive (scale / value), anharmonic keep, fragment well and out-of-plane-angle potentials
+    (Potential/LJ_repulsive_potential.py, anharmonic_keep_potential.py, switching_potential.py,
+    keep_outofplain_angle_potential.py): E, gradient, Hessian by torch.func as the aggregator computes them."""
+    import torch
+    lj = ref_shim.ref("Potential.LJ_repulsive_potential")
+    an = ref_shim.ref("Potential.anharmonic_keep_potential")
+    sw = ref_shim.ref("Potential.switching_potential")
+    oop = ref_shim.ref("Potential.keep_outofplain_angle_potential")
+    elems, xyz = read_xyz(os.path.join(ref_shim.REF_ROOT, "test/aldol_rxn.xyz"))
+    N = len(elems)
+    cen = lambda f: xyz[[a - 1 for a in f]].mean(axis=0)
+    f1w, f2w = [1, 2, 3, 4], [5, 6, 7, 8, 9]
+    dw = np.linalg.norm(cen(f1w) - cen(f2w)) * 0.52917721067      # centroid distance in Angstrom
+    flat = xyz.copy(); flat[2] = flat[0] + 1.7 * (flat[1] - flat[0])          # atoms 1, 2, 3 collinear: undefined plane
+    cases = [
+        ("lj_scale", dict(cls="lj_scale", well=1.3, dist=0.9, f1=[1, 2, 3], f2=[5, 6, 10, 11]), xyz),
+        ("lj_value", dict(cls="lj_value", well=2.5, dist=3.2, f1=[1, 4], f2=[6, 7, 8]), xyz),
+        ("anharmonic", dict(cls="anh", k=0.35, depth=0.12, pair=[1, 5], dist=1.7), xyz),
+        ("anharmonic_far", dict(cls="anh", k=0.9, depth=0.05, pair=[3, 11], dist=2.4), xyz),
+        ("well_inside", dict(cls="well", wall=40.0, f1=f1w, f2=f2w, lim=[dw - 1.5, dw - 0.8, dw + 0.9, dw + 1.6]), xyz),
+        ("well_short_switch", dict(cls="well", wall=40.0, f1=f1w, f2=f2w, lim=[dw - 0.3, dw + 0.4, dw + 1.9, dw + 2.6]), xyz),
+        ("well_short_linear", dict(cls="well", wall=25.0, f1=f1w, f2=f2w, lim=[dw + 0.2, dw + 0.9, dw + 1.9, dw + 2.6]), xyz),
+        ("well_long_switch", dict(cls="well", wall=40.0, f1=f1w, f2=f2w, lim=[dw - 2.6, dw - 1.9, dw - 0.4, dw + 0.3]), xyz),
+        ("well_long_linear", dict(cls="well", wall=25.0, f1=f1w, f2=f2w, lim=[dw - 2.6, dw - 1.9, dw - 0.9, dw - 0.2]), xyz),
+        ("oop_gen", dict(cls="oop", k=0.3, atoms=[1, 2, 3, 5], angle=12.0), xyz),
+        ("oop_neg", dict(cls="oop", k=0.2, atoms=[5, 6, 7, 10], angle=-25.0), xyz),
+        ("oop_undefined", dict(cls="oop", k=0.3, atoms=[1, 5, 2, 3], angle=10.0), flat),
+    ]
+    blob = {"names": np.array([c[0] for c in cases]), "elements": np.array(elems)}
+    for name, cfg, geom in cases:
+        g = torch.tensor(geom, dtype=torch.float64)
+        par = []
+        if cfg["cls"] == "lj_scale":
+            pot = lj.LJRepulsivePotentialScale(repulsive_potential_well_scale=cfg["well"], repulsive_potential_dist_scale=cfg["dist"],
+                                               repulsive_potential_Fragm_1=cfg["f1"], repulsive_potential_Fragm_2=cfg["f2"], element_list=elems)
+        elif cfg["cls"] == "lj_value":
+            pot = lj.LJRepulsivePotentialValue(repulsive_potential_well_value=cfg["well"], repulsive_potential_dist_value=cfg["dist"],
+                                               repulsive_potential_Fragm_1=cfg["f1"], repulsive_potential_Fragm_2=cfg["f2"], element_list=elems)
+        elif cfg["cls"] == "anh":
+            pot = an.StructAnharmonicKeepPotential(anharmonic_keep_pot_spring_const=cfg["k"], anharmonic_keep_pot_potential_well_depth=cfg["depth"],
+                                                   anharmonic_keep_pot_atom_pairs=cfg["pair"], anharmonic_keep_pot_distance=cfg["dist"])
+        elif cfg["cls"] == "well":
+            pot = sw.WellPotential(well_pot_wall_energy=cfg["wall"], well_pot_fragm_1=cfg["f1"], well_pot_fragm_2=cfg["f2"], well_pot_limit_dist=cfg["lim"])
+        else:
+            pot = oop.StructKeepOutofPlainAnglePotential(keep_out_of_plain_angle_spring_const=cfg["k"],
+                                                         keep_out_of_plain_angle_atom_pairs=cfg["atoms"], keep_out_of_plain_angle_angle=cfg["angle"])
+            par = torch.tensor([cfg["k"], cfg["angle"]], dtype=torch.float64)     # as the aggregator passes it (potential.py:802)
+        E = float(pot.calc_energy(g, par))
+        gr = torch.func.jacrev(pot.calc_energy, argnums=0)(g, par).numpy()
+        H = torch.func.hessian(pot.calc_energy, argnums=0)(g, par).reshape(3 * N, 3 * N).numpy()
+        blob[f"{name}/xyz"] = geom; blob[f"{name}/E"] = E; blob[f"{name}/g"] = gr; blob[f"{name}/H"] = H
+        blob[f"{name}/cfg"] = np.array(json.dumps(cfg))
+        print("bias2 case", name, "E", E, "|g|", np.linalg.norm(gr), "|H|", np.linalg.norm(H))
+    np.savez_compressed(os.path.join(GOLD, "bias2.npz"), **blob)
+
+
 def gen_fire():
     """FIRE optimizer of the NEB driver (Optimizer/fire_neb.py): 8-iteration trace on a synthetic chain with
     a quadratic force field, (dt, a, n_reset) schedule included."""
@@ -1064,7 +1122,7 @@ def gen_modelhess_d3():
     np.savez_compressed(os.path.join(GOLD, "modelhess_d3.npz"), **blob)
 
 
-SETS = {"modelhess_d3": gen_modelhess_d3, "keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+SETS = {"bias2": gen_bias2, "modelhess_d3": gen_modelhess_d3, "keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo, "rsprfo_reject": gen_rsprfo_reject, "rankdef": gen_rankdef, "potkeys": gen_potkeys, "neb_full": gen_neb_full}
 
 if __name__ == "__main__":

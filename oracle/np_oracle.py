@@ -1926,6 +1926,62 @@ def _keep_energy_torch(geom, kind, f1, f2, k, p):
 BOHR2ANG = 0.52917721067
 
 
+def _bias2_energy_torch(geom, kind, f1, f2, k, p, q):
+    """calc_energy of one atom pair of LJRepulsivePotentialScale / Value (kind 5: k = eps, p = sigma, both already in
+    atomic units; LJ_repulsive_potential.py:42-62,97-114), StructAnharmonicKeepPotential (kind 6;
+    anharmonic_keep_potential.py:14-27), WellPotential (kind 7: k = wall energy in Hartree, q = limits in Bohr;
+    switching_potential.py:14-67) and StructKeepOutofPlainAnglePotential (kind 8: p = phi0 in radians;
+    keep_outofplain_angle_potential.py:33-146), restated on a torch tensor (atoms 0-based)."""
+    import math
+    import torch
+    if kind == 5:
+        r = torch.linalg.norm(geom[f1[0]] - geom[f2[0]])
+        return k * (-2 * (p / r) ** 6 + (p / r) ** 12)
+    if kind == 6:
+        r = torch.linalg.norm(geom[f1[0]] - geom[f2[0]])
+        return q[0] * (1.0 - torch.exp(-math.sqrt(k / (2 * q[0])) * (r - p / BOHR2ANG))) ** 2
+    if kind == 7:
+        r = torch.linalg.norm(geom[list(f1)].sum(dim=0) / len(f1) - geom[list(f2)].sum(dim=0) / len(f2))
+        a, b, c, d = q
+        xs = 0.5 / (b - a) * r + (1.0 - 0.5 * b / (b - a))
+        xl = 0.5 / (c - d) * r + (1.0 - 0.5 * c / (c - d))
+        if r <= a:
+            return k * (-3.75 * xs + 2.875)
+        if r <= b:
+            return k * (2.0 - 20.0 * xs ** 3 + 30.0 * xs ** 4 - 12.0 * xs ** 5)
+        if r < c:
+            return 0.0 * r
+        if r < d:
+            return k * (2.0 - 20.0 * xl ** 3 + 30.0 * xl ** 4 - 12.0 * xl ** 5)
+        return k * (-3.75 * xl + 2.875)
+    ci, i1, i2, i3 = f1
+    a1, a2, a3 = geom[i1] - geom[ci], geom[i2] - geom[ci], geom[i3] - geom[ci]
+    n = torch.linalg.cross(a2, a3)
+    nsq = torch.sum(n ** 2)
+    if nsq < 1e-8:
+        return 0.0 * nsq
+    nh = n / torch.clamp(torch.sqrt(nsq), min=1e-12)
+    h = torch.sum(a1 * nh)
+    rp = torch.sqrt(torch.clamp(torch.linalg.norm(a1) ** 2 - h ** 2, min=0.0))
+    return 0.5 * k * (torch.atan2(h, rp) - p) ** 2
+
+
+def bias2_egh(coord, terms):
+    """(E, grad (N,3), hess (3N,3N)) of a list of (kind, f1, f2, k, p, q) terms by torch.func."""
+    import torch
+    geom = torch.tensor(np.asarray(coord, float), dtype=torch.float64)
+
+    def f(x):
+        e = 0.0
+        for kind, f1, f2, k, p, q in terms:
+            e = e + _bias2_energy_torch(x, kind, f1, f2, k, p, q)
+        return e
+    E = f(geom)
+    g = torch.func.jacrev(f)(geom)
+    H = torch.func.hessian(f)(geom).reshape(geom.numel(), geom.numel())
+    return float(E), g.numpy(), H.numpy()
+
+
 def keep_egh(coord, kind, f1, f2, k, p):
     """(E, grad (N,3), hess (3N,3N)) by torch.func, as Potential/potential.py:127-137 does."""
     import torch

@@ -1,0 +1,118 @@
+"""LJ repulsive (scale / value), anharmonic keep, fragment well and out-of-plane-angle bias potentials (SURVEY 8f
+rank 2): the oracle and the CUDA path (k_bias_terms kinds 5-8, through the BiasPotentialCalculation drop-in) against
+goldens from the reference classes (oracle/gen_golden.py bias2)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import np_oracle as O  # noqa: E402
+
+RTOL = 1e-10
+B2A = 0.52917721067
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0))
+
+
+def load(golden_dir):
+    z = np.load(os.path.join(golden_dir, "bias2.npz"))
+    return z, [str(n) for n in z["names"]], [str(e) for e in z["elements"]]
+
+
+def force_data_for(cfg):
+    """The force_data entries that activate the case in the aggregator (Potential/potential.py:574-809)."""
+    c = cfg["cls"]
+    if c in ("lj_scale", "lj_value"):
+        return {"repulsive_potential_well_scale": [cfg["well"]], "repulsive_potential_dist_scale": [cfg["dist"]],
+                "repulsive_potential_Fragm_1": [cfg["f1"]], "repulsive_potential_Fragm_2": [cfg["f2"]],
+                "repulsive_potential_unit": ["scale" if c == "lj_scale" else "value"]}
+    if c == "anh":
+        return {"anharmonic_keep_pot_spring_const": [cfg["k"]], "anharmonic_keep_pot_potential_well_depth": [cfg["depth"]],
+                "anharmonic_keep_pot_atom_pairs": [cfg["pair"]], "anharmonic_keep_pot_distance": [cfg["dist"]]}
+    if c == "well":
+        return {"well_pot_wall_energy": [cfg["wall"]], "well_pot_fragm_1": [cfg["f1"]], "well_pot_fragm_2": [cfg["f2"]],
+                "well_pot_limit_dist": [cfg["lim"]]}
+    return {"keep_out_of_plain_angle_spring_const": [cfg["k"]], "keep_out_of_plain_angle_atom_pairs": [cfg["atoms"]],
+            "keep_out_of_plain_angle_angle": [cfg["angle"]]}
+
+
+def oracle_terms(cfg, elems):
+    """(kind, f1, f2, k, p, q) records of the oracle for one case - the host mirror's own term builder for LJ, so the
+    float32 parameter arithmetic of the reference is exercised on both sides."""
+    import torch
+    from multioptpy_b200.Potential.potential import lj_pair_terms
+    from multioptpy_b200.Parameters import tables
+    c = cfg["cls"]
+    if c in ("lj_scale", "lj_value"):
+        return [(5, f1, f2, k, p, []) for _, f1, f2, k, p in
+                lj_pair_terms(elems, cfg["f1"], cfg["f2"], cfg["well"], cfg["dist"], "scale" if c == "lj_scale" else "value")]
+    if c == "anh":
+        return [(6, [cfg["pair"][0] - 1], [cfg["pair"][1] - 1], cfg["k"], cfg["dist"], [cfg["depth"]])]
+    if c == "well":
+        return [(7, [a - 1 for a in cfg["f1"]], [a - 1 for a in cfg["f2"]], cfg["wall"] / tables.HARTREE2KJMOL, 0.0,
+                 [v / B2A for v in cfg["lim"]])]
+    phi0 = float(torch.deg2rad(torch.tensor(cfg["angle"], dtype=torch.float64)))
+    return [(8, [a - 1 for a in cfg["atoms"]], [], cfg["k"], phi0, [])]
+
+
+def test_oracle_matches_reference(golden_dir):
+    z, names, elems = load(golden_dir)
+    for name in names:
+        cfg = json.loads(str(z[f"{name}/cfg"]))
+        E, g, H = O.bias2_egh(z[f"{name}/xyz"], oracle_terms(cfg, elems))
+        assert abs(E - float(z[f"{name}/E"])) <= RTOL * max(abs(float(z[f"{name}/E"])), 1e-300), name
+        if np.linalg.norm(z[f"{name}/g"]) == 0.0:
+            assert np.all(g == 0.0) and np.all(H == 0.0), name
+        else:
+            assert rel(g, z[f"{name}/g"]) < RTOL and rel(H, z[f"{name}/H"]) < RTOL, name
+
+
+def test_every_well_region_is_covered(golden_dir):
+    z, names, _ = load(golden_dir)
+    wells = [n for n in names if n.startswith("well_")]
+    assert len(wells) == 5 and float(z["well_inside/E"]) == 0.0
+    assert all(float(z[f"{n}/E"]) > 0.0 for n in wells if n != "well_inside")
+
+
+@pytest.mark.gpu
+def test_cuda_aggregator_matches_reference(golden_dir):
+    from multioptpy_b200.Potential.potential import BiasPotentialCalculation
+    z, names, elems = load(golden_dir)
+    for name in names:
+        cfg = json.loads(str(z[f"{name}/cfg"]))
+        xyz = z[f"{name}/xyz"]
+        bpc = BiasPotentialCalculation(device="cuda:0")
+        bg, Be, Bg, bh = bpc.main(0.0, np.zeros_like(xyz), xyz, elems, force_data_for(cfg))
+        Eref = float(z[f"{name}/E"])
+        assert abs(Be - Eref) <= RTOL * max(abs(Eref), 1e-300), name
+        if np.linalg.norm(z[f"{name}/g"]) == 0.0:
+            assert np.all(bg == 0.0) and np.all(bh == 0.0), name
+        else:
+            assert rel(bg, z[f"{name}/g"]) < RTOL, name
+            assert rel(bh, z[f"{name}/H"]) < RTOL, name
+
+
+@pytest.mark.gpu
+def test_cuda_batched_terms_vs_oracle():
+    """Several term kinds in one launch over a jittered batch."""
+    import torch
+    from multioptpy_b200 import ops, synthetic
+    B, N = 6, 12
+    xyz = np.stack([synthetic.grid_geometry(N, np.random.default_rng(70 + b), spacing=2.7, jitter=0.3) for b in range(B)])
+    terms = [(5, [0], [7], 3e-4, 5.1, []), (5, [1], [9], 2e-4, 4.4, []), (6, [2], [3], 0.4, 1.5, [0.1]),
+             (7, [0, 1, 2], [8, 9, 10, 11], 0.01, 0.0, [1.0, 2.0, 3.0, 4.5]), (8, [4, 5, 6, 0], [], 0.25, 0.3, [])]
+    dev = "cuda:0"
+    xd = torch.from_numpy(xyz).to(dev)
+    packed = ops.pack_bias_terms([(k, f1, f2, kk, p, q) for k, f1, f2, kk, p, q in terms], dev)
+    E, g, H = ops.bias_terms(xd, packed, len(terms))
+    for b in range(B):
+        Eo, go, Ho = O.bias2_egh(xyz[b], terms)
+        assert abs(float(E[b]) - Eo) <= RTOL * abs(Eo)
+        assert rel(g[b].cpu().numpy().reshape(N, 3), go) < RTOL
+        assert rel(H[b].cpu().numpy(), Ho) < RTOL
