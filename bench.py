@@ -195,8 +195,6 @@ def run_b200(args, rank, world, local_rank):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     lib = _lib.load()
-    if os.environ.get("MOP_STREAM_CHUNK"):      # tuning aid: update + projection chunk size
-        lib.mop_debug_stream_chunk(int(os.environ["MOP_STREAM_CHUNK"]))
     B, n = BATCH, 3 * NATOMS
     K, W = args.steps, args.warmup
     f64 = torch.float64
@@ -378,12 +376,12 @@ def run_b200(args, rank, world, local_rank):
         probe = torch.empty(148 * 16 * 256, dtype=f64, device=dev)
         iters = 4096
         for _ in range(2):
-            _lib.check(lib.mop_bench_dfma(148 * 16, iters, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            _lib.check(lib.mop_priv_bench_dfma(148 * 16, iters, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
         best = 1e30
         for _ in range(5):
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            _lib.check(lib.mop_bench_dfma(148 * 16, iters, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            _lib.check(lib.mop_priv_bench_dfma(148 * 16, iters, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
             b_.record(); torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b_))
         fp64_peak = 148 * 16 * 256 * iters * 64 * 2 / (best * 1e-3) / 1e12   # TFLOP/s
@@ -460,7 +458,7 @@ def run_b200(args, rank, world, local_rank):
                          "algorithmic_flops_per_launch": B * WF, "kernel_ms": eig_ms,
                          "executed_flops_per_launch_estimate": executed_flops,
                          "executed_tflops_estimate": executed_flops / (eig_ms * 1e-3) / 1e12,
-                         "peak_source": "in-run DFMA probe (mop_bench_dfma); MEASURED_PEAKS.json has no FP64 figure",
+                         "peak_source": "in-run DFMA probe (mop_priv_bench_dfma); MEASURED_PEAKS.json has no FP64 figure",
                          "whole_step_algorithmic_tflops": step_tflops_alg,
                          "whole_step_frac": step_tflops_alg / fp64_peak},
             "roofline_hbm": {"bound": "hbm", "kernel": "Hessian update, multi-CTA path (k_upd_matvec + k_upd_scalars + k_upd_apply)",
@@ -635,7 +633,7 @@ def run_b200_c5(args, rank, world, local_rank):
         for _ in range(6):
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            _lib.check(lib.mop_bench_dfma(148 * 16, 4096, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            _lib.check(lib.mop_priv_bench_dfma(148 * 16, 4096, probe.data_ptr(), torch.cuda.current_stream().cuda_stream))
             b_.record(); torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b_))
         fp64_peak = 148 * 16 * 256 * 4096 * 64 * 2 / (best * 1e-3) / 1e12
@@ -665,7 +663,7 @@ def run_b200_c5(args, rank, world, local_rank):
                 "roofline": {"bound": "fp64", "kernel": "whole P-RFO step (dominant: k_lg_tridiag2 cluster tridiagonalisation)",
                              "achieved": step_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": step_tf / fp64_peak,
                              "traffic": None, "algorithmic_flops_per_structure": WF,
-                             "peak_source": "in-run DFMA probe (mop_bench_dfma)"},
+                             "peak_source": "in-run DFMA probe (mop_priv_bench_dfma)"},
                 "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": len(chunks), "kind": "port",
                                  "sample": f"{sample} structures, step-1 calls of oracle RSPRFOOracle timed, one process "
                                            "per core, 1 BLAS thread each"}}

@@ -268,6 +268,16 @@ int mop_hessian_ts_modify(int B, int n, const double* H, const double* evals, co
                           int32_t* modified, void* stream);
 int mop_hessian_clip_eigvals(int B, int n, const double* evals, const double* evecs, double* out, void* stream);
 
+/* ---- effective Hessian for fixed atoms ---------------------------------------------------------------------------
+ * Replaces HessianManager.calc_eff_hess_for_fix_atoms_and_set_hess (optimization.py:1325-1343,1358-1362):
+ * H -= H[:, f] pinv(H[f, f] + 1e-10 I) H[f, :] with f the 3 n_fix coordinates of force_data["fix_atoms"], applied by the
+ * caller to the bias Hessian and to the model Hessian.  mop_fix_atoms_gather writes the regularised blocks
+ * [B][m][m]; mop_eigh diagonalises them; mop_fix_atoms_schur forms the pseudo-inverse (numpy.linalg.pinv cut-off,
+ * 1e-15 max|lambda|) and updates H in place. */
+int mop_fix_atoms_gather(int B, int n, int m, const int32_t* fix_coords, const double* H, double* blocks, void* stream);
+int mop_fix_atoms_schur(int B, int n, int m, const int32_t* fix_coords, const double* evals, const double* evecs,
+                        double* H, void* stream);
+
 /* ---- restraint bias potentials --------------------------------------------------------------
  * Replaces calc_energy + torch.func.jacrev / hessian (Potential/potential.py:127-137) for StructKeepPotential
  * (kind 1), StructKeepPotentialv2 (kind 2; Potential/keep_potential.py), StructKeepAnglePotential (kind 3;
@@ -411,41 +421,8 @@ int mop_outer_trust_radius(int B, int n, const double* H, const double* Hbias, c
 int mop_clamp_and_move(int B, int n, const double* x, double* move, const double* trust_outer,
                        double* x_new_ang, void* stream);
 
-/* ---- measurement helpers (bench.py) -----------------------------------------
- * mop_bench_dfma: FP64 FMA peak probe; one launch = blocks*256*iters*64*2 FLOPs.
- * mop_bench_fill: write `count` doubles (L2 flush when the buffer exceeds L2). */
-int mop_bench_dfma(int blocks, int iters, double* out, void* stream);
-int mop_bench_fill(double* buf, size_t count, double value, void* stream);
-/* diagnostics: device buffer [B][8] int64 receiving per-phase SM clock counts of the
- * tridiagonal / fused kernel (NULL switches it off).  Not thread-safe; tools only. */
-int mop_debug_tri_timing(void* buf);
-/* diagnostics / tuning: force the CTA size (128/256/512/1024) of the tridiagonal kernels; 0 = auto. */
-int mop_debug_tri_threads(int threads);
-/* diagnostics: skip parts of the tridiagonalisation (timing ablations; results invalid). */
-int mop_debug_tri_ablate(int mask);
-/* diagnostics: out[i] = the kernels' division-free reciprocal of x[i] (accuracy test). */
-int mop_debug_fast_rcp(const double* x, double* out, size_t count, void* stream);
-/* diagnostics: out[0..7] = dependent-chain latencies in SM cycles of DFMA, DADD, DMUL,
- * shared load, 64-bit shuffle, fast reciprocal, sqrt(+add), divide (out: >= 9 doubles). */
-int mop_debug_latency(double* out, void* stream);
-/* diagnostics: out[0..2] = cycles per bare barrier / reduce-publish-barrier-broadcast round /
- * the same plus a dependent sqrt and two reciprocals, for one CTA of `threads` threads. */
-int mop_debug_large_cluster(int cluster_ctas); /* tuning: CTAs per matrix of MOP_EIGH_LARGE (1, 2, 4, 8; 0 = auto) */
-int mop_debug_eigh_small_pipeline(int on); /* tuning: mop_eigh at n <= 158 through packed tridiagonalisation + eigh_large stages (default 1) */
-int mop_debug_tri_packed(int on);       /* tuning: packed two-CTA-per-SM tridiagonalisation in the fused RS-I-RFO path (default 1) */
-int mop_debug_stream_chunk(int structures); /* tuning: structures per update + projection chunk of mop_rsirfo_step (default 0 = whole batch) */
-int mop_debug_tri_spectrum(int on);     /* tuning: k_spectrum_step (Z in global memory, 7 structures per SM) after the packed kernel (default 1) */
-int mop_debug_spectrum_timing(void* buf); /* diagnostics: [B][16] int64 phase cycles of k_spectrum_step */
-int mop_debug_packed_rowwarp(int on);   /* tuning: fused warp-per-row packed tridiagonalisation k_tridiag_rwf (default 1) or the thread-group kernel k_tridiag_packed (0) */
-int mop_debug_packed_timing(void* buf);   /* diagnostics: [B][16] int64 phase cycles of the packed kernel */
-int mop_debug_packed_threads(int threads); /* tuning: CTA size of the packed kernel (128, 256, 512) */
-int mop_debug_large_blocked(int on);   /* tuning: blocked dlatrd + DMMA cluster tridiagonalisation for n > 160 (default 1) */
-int mop_debug_large_pair(int mode);     /* tuning: two matrices per cluster in lock-step: 0 auto, 1 always, -1 never */
-int mop_debug_large_ablate(int mask); /* diagnostics: bit0 no trailing stores, bit1 no trailing loads (results invalid) */
-int mop_debug_large_timing(void* buf); /* diagnostics: [B][4] int64 phase cycles of the MOP_EIGH_LARGE reduction */
-int mop_debug_barrier_latency(int threads, double* out, void* stream);
-int mop_debug_front_fused(int on);      /* tuning: update + projection fused into the tridiagonalisation kernel (default 1) */
-int mop_debug_packed_blocked(int on);    /* tuning: blocked DMMA tridiagonalisation k_tridiag_blk (default 1) */
+/* Measurement probes and tuning / diagnostic hooks are NOT part of this interface: they are declared in
+ * multioptpy_b200/csrc/mop_private.h (mop_priv_*), used by bench.py and tools/ only. */
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mop_fischer_workspace_bytes": (_sz, [_i, _i]),
     "mop_fischer_hessian": (_i, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "mop_fischer_d3old_hessian": (_i, [_i, _i, _p, _p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _sz, _p]),
+    "mop_fix_atoms_gather": (_i, [_i, _i, _i, _p, _p, _p, _p]),
+    "mop_fix_atoms_schur": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
     "mop_hessian_ts_modify": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_hessian_clip_eigvals": (_i, [_i, _i, _p, _p, _p, _p]),
     "mop_fischer_d3_hessian": (_i, [_i, _i, _p, _p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _sz, _p]),
@@ -77,29 +79,21 @@ SIGNATURES = {
     "mop_neb_fire_advance": (_i, [_i, _i, _d, _i, _p, _p, _p, _p, _p, _p]),
     "mop_outer_trust_radius": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _p]),
     "mop_clamp_and_move": (_i, [_i, _i, _p, _p, _p, _p, _p]),
-    "mop_bench_dfma": (_i, [_i, _i, _p, _p]),
-    "mop_bench_fill": (_i, [_p, _sz, _d, _p]),
-    "mop_debug_tri_timing": (_i, [_p]),
-    "mop_debug_tri_threads": (_i, [_i]),
-    "mop_debug_tri_ablate": (_i, [_i]),
-    "mop_debug_fast_rcp": (_i, [_p, _p, _sz, _p]),
-    "mop_debug_latency": (_i, [_p, _p]),
-    "mop_debug_barrier_latency": (_i, [_i, _p, _p]),
-    "mop_debug_large_cluster": (_i, [_i]),
-    "mop_debug_large_pair": (_i, [_i]),
-    "mop_debug_large_blocked": (_i, [_i]),
-    "mop_debug_tri_packed": (_i, [_i]),
-    "mop_debug_tri_spectrum": (_i, [_i]),
-    "mop_debug_stream_chunk": (_i, [_i]),
-    "mop_debug_spectrum_timing": (_i, [_p]),
-    "mop_debug_eigh_small_pipeline": (_i, [_i]),
-    "mop_debug_packed_threads": (_i, [_i]),
-    "mop_debug_packed_timing": (_i, [_p]),
-    "mop_debug_packed_rowwarp": (_i, [_i]),
-    "mop_debug_large_timing": (_i, [_p]),
-    "mop_debug_large_ablate": (_i, [_i]),
-    "mop_debug_packed_blocked": (_i, [_i]),
-    "mop_debug_front_fused": (_i, [_i]),
+}
+
+# Private symbols (csrc/mop_private.h): measurement probes and tuning / diagnostic hooks used by bench.py and tools/.
+PRIVATE_SIGNATURES = {
+    "mop_priv_bench_dfma": (_i, [_i, _i, _p, _p]),
+    "mop_priv_bench_fill": (_i, [_p, _sz, _d, _p]),
+    "mop_priv_fast_rcp": (_i, [_p, _p, _sz, _p]),
+    "mop_priv_latency": (_i, [_p, _p]),
+    "mop_priv_barrier_latency": (_i, [_i, _p, _p]),
+    "mop_priv_spectrum_timing": (_i, [_p]),
+    "mop_priv_tridiag_blk_timing": (_i, [_p]),
+    "mop_priv_tridiag_cluster_timing": (_i, [_p]),
+    "mop_priv_large_cluster": (_i, [_i]),
+    "mop_priv_tridiag_cluster_sym": (_i, [_i]),
+    "mop_priv_tridiag_cluster_ablate": (_i, [_i]),
 }
 
 _lib = None
@@ -114,7 +108,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} not found: the CUDA library is required (no CPU fallback). "
             "Build it with `python -m multioptpy_b200.build`.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(PRIVATE_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args

@@ -131,24 +131,24 @@ __global__ void k_barrier_latency(double* out) {
 
 // Launches blocks x 256 threads, each doing iters * 64 dependent-chain-interleaved DFMAs.
 // FLOPs of one launch = blocks * 256 * iters * 64 * 2.
-extern "C" int mop_bench_dfma(int blocks, int iters, double* out, void* stream) {
-  MOP_REQUIRE(blocks > 0 && iters > 0 && out, "mop_bench_dfma: bad arguments");
+extern "C" int mop_priv_bench_dfma(int blocks, int iters, double* out, void* stream) {
+  MOP_REQUIRE(blocks > 0 && iters > 0 && out, "mop_priv_bench_dfma: bad arguments");
   mop::k_dfma_peak<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
 
 // Writes `count` doubles (use a buffer larger than the 126 MB L2 to flush it).
-extern "C" int mop_bench_fill(double* buf, size_t count, double value, void* stream) {
-  MOP_REQUIRE(buf && count > 0, "mop_bench_fill: bad arguments");
+extern "C" int mop_priv_bench_fill(double* buf, size_t count, double value, void* stream) {
+  MOP_REQUIRE(buf && count > 0, "mop_priv_bench_fill: bad arguments");
   mop::k_fill<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(buf, count, value);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
 
 // out[i] = fast_rcp(x[i]) (the division-free reciprocal used by the twisted factorisation)
-extern "C" int mop_debug_fast_rcp(const double* x, double* out, size_t count, void* stream) {
-  MOP_REQUIRE(x && out && count > 0, "mop_debug_fast_rcp: bad arguments");
+extern "C" int mop_priv_fast_rcp(const double* x, double* out, size_t count, void* stream) {
+  MOP_REQUIRE(x && out && count > 0, "mop_priv_fast_rcp: bad arguments");
   mop::k_fast_rcp<<<148, 256, 0, (cudaStream_t)stream>>>(x, out, count);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
@@ -156,15 +156,15 @@ extern "C" int mop_debug_fast_rcp(const double* x, double* out, size_t count, vo
 
 // out[0..7]: dependent-chain latency in cycles of DFMA, DADD, DMUL, LDS, SHFL.64, fast_rcp,
 // sqrt(+add), div (one warp, nothing else running)
-extern "C" int mop_debug_latency(double* out, void* stream) {
-  MOP_REQUIRE(out, "mop_debug_latency: bad arguments");
+extern "C" int mop_priv_latency(double* out, void* stream) {
+  MOP_REQUIRE(out, "mop_priv_latency: bad arguments");
   mop::k_latency<<<1, 32, 0, (cudaStream_t)stream>>>(out);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
 
-extern "C" int mop_debug_barrier_latency(int threads, double* out, void* stream) {
-  MOP_REQUIRE(out && threads >= 32 && threads <= 1024, "mop_debug_barrier_latency: bad arguments");
+extern "C" int mop_priv_barrier_latency(int threads, double* out, void* stream) {
+  MOP_REQUIRE(out && threads >= 32 && threads <= 1024, "mop_priv_barrier_latency: bad arguments");
   mop::k_barrier_latency<<<1, threads, 0, (cudaStream_t)stream>>>(out);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;

@@ -31,8 +31,6 @@ int mop_launch_eigh_jacobi(int B, int n, const double* A, double* evals, double*
                            size_t work_bytes, cudaStream_t stream);
 size_t mop_tridiag_workspace_bytes(int B, int n);
 int mop_tridiag_supported(int n);
-int mop_launch_eigh_tridiag(int B, int n, const double* A, double* evals, double* evecs,
-                            int32_t* status, void* work, size_t work_bytes, cudaStream_t stream);
 size_t mop_large_workspace_bytes(int B, int n);
 int mop_large_supported(int n);
 int mop_launch_eigh_large(int B, int n, const double* A, double* evals, double* evecs, int32_t* status,
@@ -87,12 +85,6 @@ extern "C" const char* mop_last_error(void) { return g_err; }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static int g_stream_chunk = 0;
-// tuning: structures per update + projection chunk of mop_rsirfo_step (0, the default = the whole batch at once)
-extern "C" int mop_debug_stream_chunk(int structures) {
-  g_stream_chunk = structures;
-  return MOP_OK;
-}
 namespace mop {
 // Packed lower triangle <-> full symmetric matrix (row i of the triangle at i (i + 1) / 2).  only_flagged: structures
 // without MOP_ST_EIG_FALLBACK in flags[b] are skipped (the robust path of the packed step).
@@ -129,18 +121,6 @@ extern "C" int mop_unpack_lower(int B, int n, const double* packed, double* H, v
   dim3 grid(64, B);
   mop::k_unpack_lower<<<grid, 256, 0, (cudaStream_t)stream>>>(n, packed, H, nullptr);
   MOP_CHECK_CUDA(cudaGetLastError());
-  return MOP_OK;
-}
-
-static int g_front_fused = 1;
-// tuning: 1 (default) = update + projection fused into the tridiagonalisation kernel (n <= 160)
-extern "C" int mop_debug_front_fused(int on) {
-  g_front_fused = on;
-  return MOP_OK;
-}
-static int g_eigh_small_pipeline = 1;
-extern "C" int mop_debug_eigh_small_pipeline(int on) {
-  g_eigh_small_pipeline = on;
   return MOP_OK;
 }
 
@@ -186,12 +166,8 @@ static int run_eigh(int B, int n, int algo, const double* A, double* evals, doub
       mop_set_error("eigh: the tridiagonal path needs a status array (fallback flags)");
       return MOP_ERR_INVALID;
     }
-    // packed tridiagonalisation + global-memory spectrum + register back-transform (eigh_large.cu) is
-    // 3-4x faster than the single shared-memory kernel when V itself is wanted; mop_debug_tri_packed(0)
-    // selects the latter
-    int rc = g_eigh_small_pipeline
-                 ? mop_launch_eigh_large(B, n, A, evals, evecs, status, (char*)work + jac, work_bytes - jac, stream)
-                 : mop_launch_eigh_tridiag(B, n, A, evals, evecs, status, (char*)work + jac, work_bytes - jac, stream);
+    // blocked shared-memory tridiagonalisation + global-memory spectrum + register back-transform (eigh_large.cu)
+    int rc = mop_launch_eigh_large(B, n, A, evals, evecs, status, (char*)work + jac, work_bytes - jac, stream);
     if (rc != MOP_OK) return rc;
     // robust fallback for structures the fast path flagged (no host sync: CTAs of
     // unflagged structures exit immediately)
@@ -366,20 +342,19 @@ extern "C" int mop_rsirfo_step(int B, int n, int method, int saddle_order, int n
 
   MOP_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, stream));
   int rc = MOP_OK;
-  if (g_front_fused && pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG && mop_spectrum_step_supported(n))
+  if (pick_algo(eigh_algo, n) == MOP_EIGH_TRIDIAG && mop_spectrum_step_supported(n))
     return rsirfo_step_fused(B, n, method, nullptr, saddle_order, neb_mode, trust_min, trust_max, 0, H, Hbias, x, Bg, g, x_prev,
                              g_prev, Be, state, move_out, eigvals_out, pred_out, status, Hp, gp, rest, stream);
   // (1) Hessian update with RAW gradients (rsirfo.py:308-309,1316-1372) and (2) TR/ROT projection of gradient
-  // and effective Hessian (rsirfo.py:337,349-358).  Small batches take the multi-CTA projection (it fills the
-  // GPU), large ones one CTA per structure (as fast, fewer launches).  mop_debug_stream_chunk(c) runs the pair
-  // chunk by chunk so that a chunk stays in L2 between its passes - measured SLOWER on B200 at n = 150 (the
-  // short launches are latency bound: 4.97 ms per step at c = 256 against 4.44 ms), hence off by default.
+  // and effective Hessian (rsirfo.py:337,349-358) for n > 160.  Small batches take the multi-CTA projection (it
+  // fills the GPU), large ones one CTA per structure (as fast, fewer launches).  (Running the pair chunk by chunk so
+  // that a chunk stays in L2 between its passes was measured SLOWER on B200: the short launches are latency bound.)
   const size_t n2 = (size_t)n * n;
-  const bool chunked = g_stream_chunk > 0 && g_stream_chunk < B;
+  const bool chunked = false;
   const size_t slab = sizeof(double) * (size_t)B * n2;  // what a [B][n][n] slab really holds (nn is rounded up)
   const bool split_ok = slab >= mop_project_scratch_bytes(B, n) && slab >= mop_hessian_update_scratch_bytes(B, n) &&
                         (chunked || B <= 2 * 148);
-  const int CH = (split_ok && chunked) ? g_stream_chunk : B;
+  const int CH = B;
   for (int b0 = 0; b0 < B; b0 += CH) {
     const int bc = B - b0 < CH ? B - b0 : CH;
     double* Hc = H + b0 * n2;

@@ -4,11 +4,8 @@
 // The matrix stays in global memory (a batch slice that is being reduced is L2-resident) and
 // one thread-block CLUSTER reduces one matrix, so that a single matrix is streamed by the
 // L2 ports of several SMs and the per-column synchronisation is a hardware cluster barrier:
-//   1. k_lg_tridiag: Householder tridiagonalisation A = Q T Q^T, one cluster barrier per
-//      column.  The rank-2 update of column k and the product A v for column k+1 are fused
-//      into one pass over the trailing rows (each element is read and written once per
-//      column: 16 bytes instead of 24), rows are dealt to the warps of the cluster in groups
-//      of four so that v, w and v' are read from shared memory once per four rows.
+//   1. k_lg_tridiag_blk (tridiag_cluster.cu): blocked Householder tridiagonalisation A = Q T Q^T (dlatrd panels,
+//      DMMA trailing updates); n <= 160: k_tridiag_blk (tridiag_blocked.cu), one CTA per matrix.
 //   2. k_lg_trieig: eigenvalues of T by bisection on the Sturm count, eigenvectors by twisted
 //      factorisation, CGS2 inside clusters - the algorithm of eigh_tridiag.cu with Z in
 //      global memory (column i = vector i).
@@ -28,10 +25,8 @@ namespace cg = cooperative_groups;
 namespace mop {
 
 constexpr int LG_MAX_N = 1024;
-constexpr int LG_TRI_THREADS = 1024;
 constexpr int LG_EIG_THREADS = 1024;
 constexpr int LG_BT_THREADS = 512;
-constexpr int LG_ROWS = 4;  // rows per warp in the fused update + symv
 // Re-orthogonalisation threshold on eigenvalue gaps relative to ||T||.  A twisted-factorisation
 // vector is accurate to about eps ||T|| / gap, so neighbours further apart than this are orthogonal
 // to ~1e-12 already; dstein's 1e-3 would chain most of a dense 600-eigenvalue spectrum.
@@ -70,495 +65,6 @@ __global__ void __launch_bounds__(256) k_lg_symcopy(int n, const double* __restr
     const int i = i0 + r, j = j0 + tx;
     if (i < n && j < n) Aout[off + (size_t)i * n + j] = 0.5 * (Ain[off + (size_t)i * n + j] + t[tx][r]);
   }
-}
-
-// ---- 1. tridiagonalisation, one cluster per matrix ---------------------------------------------
-__global__ void __launch_bounds__(LG_TRI_THREADS, 1) k_lg_tridiag(LgArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
-  const int b = blockIdx.x / CL;
-  const int n = a.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = LG_TRI_THREADS / 32;
-  const int np = (n + 3) & ~3;
-  extern __shared__ double sm[];
-  double* v = sm;        // pending reflector (indices k..n-1)
-  double* w = v + np;    // its w
-  double* vn = w + np;   // row k, then the new reflector
-  __shared__ double s_red[40];
-  double* A = a.A + (size_t)b * n * n;
-  double* Vh = a.Vh + (size_t)b * n * n;
-  double* pb0 = a.pbuf + (size_t)b * 2 * n;
-  double* pb1 = pb0 + n;
-  double tau_prev = 0.0;
-  const int W = CL * NW, gw = wid * CL + cr;
-
-  long long tacc[4] = {0, 0, 0, 0};
-  long long tp = clock64();
-#define LG_MARK(slot)                    \
-  do {                                   \
-    if (a.dbg) {                         \
-      const long long tnow = clock64();  \
-      tacc[slot] += tnow - tp;           \
-      tp = tnow;                         \
-    }                                    \
-  } while (0)
-  for (int k = 0; k < n; ++k) {
-    const bool pend = k > 0;
-    // (a) w = tau p - 1/2 tau^2 (p . v) v from the products the cluster wrote last column
-    if (pend) {
-      const double* p = (k & 1) ? pb1 : pb0;
-      double part = 0.0;
-      for (int j = k + tid; j < n; j += LG_TRI_THREADS) {
-        const double pj = p[j];
-        w[j] = pj;
-        part = fma(pj, v[j], part);
-      }
-      const double dot = block_sum(part, s_red);
-      const double c = 0.5 * tau_prev * tau_prev * dot;
-      for (int j = k + tid; j < n; j += LG_TRI_THREADS) w[j] = tau_prev * w[j] - c * v[j];
-      __syncthreads();
-    }
-    LG_MARK(0);
-    // (b) row k of the updated matrix, Householder vector for column k
-    const double* Ak = A + (size_t)k * n;
-    double x2 = 0.0;
-    {
-      const double vk = pend ? v[k] : 0.0, wk = pend ? w[k] : 0.0;
-      for (int j = k + tid; j < n; j += LG_TRI_THREADS) {
-        double r = Ak[j];
-        if (pend) r -= fma(vk, w[j], wk * v[j]);
-        vn[j] = r;
-        if (j >= k + 2) x2 = fma(r, r, x2);
-      }
-    }
-    x2 = block_sum(x2, s_red);
-    const double dk = vn[k];
-    const double alpha = (k + 1 < n) ? vn[k + 1] : 0.0;
-    double tau = 0.0, ek = alpha, scl = 0.0;
-    if (k <= n - 3 && x2 > 0.0) {
-      const double beta = -copysign(sqrt(fma(alpha, alpha, x2)), alpha);
-      tau = (beta - alpha) / beta;
-      scl = 1.0 / (alpha - beta);
-      ek = beta;
-    }
-    __syncthreads();
-    for (int j = k + 1 + tid; j < n; j += LG_TRI_THREADS) vn[j] = (j == k + 1) ? 1.0 : vn[j] * scl;
-    if (cr == 0 && tid == 0) {
-      a.dd[(size_t)b * n + k] = dk;
-      a.ee[(size_t)b * n + k] = (k + 1 < n) ? ek : 0.0;
-      a.tau[(size_t)b * n + k] = tau;
-    }
-    __syncthreads();
-    if (k == n - 1) break;
-    if (cr == 0)
-      for (int j = k + 1 + tid; j < n; j += LG_TRI_THREADS) Vh[(size_t)k * n + j] = vn[j];
-    LG_MARK(1);
-    // (c) own rows >= k+1: apply the pending rank-2 update, accumulate A v'
-    double* pw = ((k + 1) & 1) ? pb1 : pb0;
-    const int g0 = (k + 1) / LG_ROWS;
-    for (int g = g0 + gw; g * LG_ROWS < n; g += W) {
-      double acc[LG_ROWS], vi[LG_ROWS], wi[LG_ROWS];
-      double* Ar[LG_ROWS];
-      bool ok[LG_ROWS];
-#pragma unroll
-      for (int q = 0; q < LG_ROWS; ++q) {
-        const int r = g * LG_ROWS + q;
-        ok[q] = r >= k + 1 && r < n;
-        const int rc = ok[q] ? r : k + 1;
-        Ar[q] = A + (size_t)rc * n;
-        vi[q] = pend ? v[rc] : 0.0;
-        wi[q] = pend ? w[rc] : 0.0;
-        acc[q] = 0.0;
-      }
-      if (pend) {
-#pragma unroll 2
-        for (int j = k + 1 + lane; j < n; j += 32) {
-          const double vj = v[j], wj = w[j], vnj = vn[j];
-#pragma unroll
-          for (int q = 0; q < LG_ROWS; ++q) {
-            if (ok[q]) {
-              double x = Ar[q][j];
-              x = fma(-vi[q], wj, x);
-              x = fma(-wi[q], vj, x);
-              Ar[q][j] = x;
-              acc[q] = fma(x, vnj, acc[q]);
-            }
-          }
-        }
-      } else {
-#pragma unroll 2
-        for (int j = k + 1 + lane; j < n; j += 32) {
-          const double vnj = vn[j];
-#pragma unroll
-          for (int q = 0; q < LG_ROWS; ++q)
-            if (ok[q]) acc[q] = fma(Ar[q][j], vnj, acc[q]);
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < LG_ROWS; ++q) {
-        const double s = warp_sum(acc[q]);
-        if (ok[q] && lane == 0) pw[g * LG_ROWS + q] = s;
-      }
-    }
-    double* t = v;
-    v = vn;
-    vn = t;
-    tau_prev = tau;
-    LG_MARK(2);
-    cluster.sync();
-    LG_MARK(3);
-  }
-  if (a.dbg && tid == 0 && cr == 0)
-    for (int q = 0; q < 4; ++q) a.dbg[(size_t)b * 4 + q] = tacc[q];
-}
-
-
-// ---- 1'. tridiagonalisation, one cluster per matrix, rows owned by warps for the whole reduction ---
-// Every row of the matrix is owned by one warp of the cluster for the whole reduction, so no CTA ever
-// reads matrix elements another CTA wrote: the cluster exchanges only two n-vectors per column,
-// through distributed shared memory (A v' pushed into every CTA, the next pivot row pulled from its
-// owner), and the per-column critical path is three CTA barriers, one cluster barrier and the
-// L2 round trips of the fused update + symv, whose loads are issued UNR chunks deep.
-
-// RL live rows  first, first + rs, ...  of one warp (rs = row stride in elements), columns k+1 .. n-1:
-//   A[r][j] -= v_r w_j + w_r v_j ;  acc_r += A[r][j] vn_j ;  PUB: row `first` = k+1 is copied to rpub.
-template <int RL, bool PUB>
-__device__ __forceinline__ void lg_update_symv(double* __restrict__ base, size_t rs, int n, int k, int lane,
-                                               const double (&vi)[RL], const double (&wi)[RL],
-                                               const double* __restrict__ v, const double* __restrict__ wv,
-                                               const double* __restrict__ vn, double* __restrict__ rpub,
-                                               double (&acc)[RL], int abl = 0) {
-  // loads in flight per lane: RL * UNR doubles; the whole row set of a column in one to three round trips
-  constexpr int UNR = (RL <= 3) ? 8 : ((RL == 4) ? 6 : ((RL == 5) ? 5 : ((RL == 6) ? 4 : ((RL <= 8) ? 3 : 2))));
-#pragma unroll
-  for (int q = 0; q < RL; ++q) acc[q] = 0.0;
-  const int jlo = k + 1;
-  auto block = [&](int j0, auto nu_tag, auto pred_tag) {
-    constexpr int NU = decltype(nu_tag)::value;
-    constexpr bool PRED = decltype(pred_tag)::value;
-    double x[RL][NU];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      const int j = j0 + 32 * u + lane;
-      const bool inb = !PRED || (j >= jlo && j < n);
-#pragma unroll
-      for (int q = 0; q < RL; ++q) x[q][u] = (inb && !(abl & 2)) ? base[(size_t)q * rs + j] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      const int j = j0 + 32 * u + lane;
-      const bool inb = !PRED || (j >= jlo && j < n);
-      if (inb) {
-        const double vj = v[j], wj = wv[j], vnj = vn[j];
-#pragma unroll
-        for (int q = 0; q < RL; ++q) {
-          double xx = x[q][u];
-          xx = fma(-vi[q], wj, xx);
-          xx = fma(-wi[q], vj, xx);
-          if (!(abl & 1)) base[(size_t)q * rs + j] = xx;
-          if (PUB && q == 0) rpub[j] = xx;
-          acc[q] = fma(xx, vnj, acc[q]);
-        }
-      }
-    }
-  };
-  using one = std::integral_constant<int, 1>;
-  using many = std::integral_constant<int, UNR>;
-  (void)sizeof(one);
-  for (int j0 = jlo & ~31; j0 < n; j0 += 32 * UNR) block(j0, many{}, std::true_type{});
-#pragma unroll
-  for (int q = 0; q < RL; ++q) acc[q] = warp_sum(acc[q]);
-}
-
-// step (3) of one warp: RL live rows starting at `first`; pushes A v' for them into every CTA
-template <int RL>
-__device__ __forceinline__ void lg_step3(cg::cluster_group& cluster, int CL, double* A, int n, int k, int first, int W,
-                                         int lane, const double* v, const double* wv, const double* vn,
-                                         double* rpub, double* pnext, int abl) {
-  double acc[RL], vi[RL], wi[RL];
-#pragma unroll
-  for (int q = 0; q < RL; ++q) {
-    vi[q] = v[first + q * W];
-    wi[q] = wv[first + q * W];
-  }
-  double* base = A + (size_t)first * n;
-  const size_t rs = (size_t)W * n;
-  if (first == k + 1)
-    lg_update_symv<RL, true>(base, rs, n, k, lane, vi, wi, v, wv, vn, rpub, acc, abl);
-  else
-    lg_update_symv<RL, false>(base, rs, n, k, lane, vi, wi, v, wv, vn, rpub, acc, abl);
-  for (int idx = lane; idx < RL * CL; idx += 32) {
-    const int q = idx / CL, t = idx - q * CL;
-    double val = 0.0;
-#pragma unroll
-    for (int qq = 0; qq < RL; ++qq)
-      if (qq == q) val = acc[qq];
-    double* dst = cluster.map_shared_rank(pnext, t);
-    dst[first + q * W] = val;
-  }
-}
-
-// Warp gw = wid * CL + cr owns rows gw, gw + W, gw + 2 W, ... (W = CL * NW warps in the cluster, at
-// most R rows each): live rows stay evenly spread over all warps while the trailing matrix shrinks.
-template <int R, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2(LgArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
-  const int b = blockIdx.x / CL;
-  const int n = a.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = THREADS / 32;
-  const int np = (n + 3) & ~3;
-  extern __shared__ double sm[];
-  double* vb = sm;               // [2][np] reflectors
-  double* pb = vb + 2 * np;      // [2][np] A v (filled by every warp of the cluster)
-  double* rowb = pb + 2 * np;    // [2][np] pivot row published by its owner
-  double* rcur = rowb + 2 * np;  // [np] pivot row of this column
-  double* wv = rcur + np;        // [np] w of the pending reflector
-  __shared__ double s_rb[2 * 32];
-  int parity = 0;
-  double* A = a.A + (size_t)b * n * n;
-  double* Vh = a.Vh + (size_t)b * n * n;
-  const int W = CL * NW, gw = wid * CL + cr;
-  double tau_prev = 0.0;
-  int cur = 0;
-  long long tacc[4] = {0, 0, 0, 0};
-  long long tp = clock64();
-
-  if (gw == 0) {  // owner of row 0 publishes it
-    for (int j = lane; j < n; j += 32) rowb[j] = A[j];
-  }
-  for (int j = tid; j < np; j += THREADS) {  // column 0 has no pending reflector: v = w = 0
-    vb[j] = 0.0;
-    wv[j] = 0.0;
-  }
-  cluster.sync();
-
-  for (int k = 0; k < n; ++k) {
-    const bool pend = k > 0;
-    const double* v = vb + cur * np;
-    double* vnew = vb + (cur ^ 1) * np;
-    const double* p = pb + (k & 1) * np;
-    const double* rrow = cluster.map_shared_rank(rowb + (k & 1) * np, k % CL);
-    // (1) pull the pivot row, p . v
-    double part[1] = {0.0};
-    for (int j = k + tid; j < n; j += THREADS) {
-      rcur[j] = rrow[j];
-      if (pend) part[0] = fma(p[j], v[j], part[0]);
-    }
-    block_sum_k<1>(part, s_rb, parity);
-    const double c = 0.5 * tau_prev * tau_prev * part[0];
-    LG_MARK(0);
-    // (2) w, row k through the pending reflector, its norm
-    double x2[1] = {0.0};
-    if (pend) {
-      const double vk = v[k], wk = fma(tau_prev, p[k], -c * vk);
-      for (int j = k + tid; j < n; j += THREADS) {
-        const double vj = v[j];
-        const double wj = fma(tau_prev, p[j], -c * vj);
-        wv[j] = wj;
-        const double r = rcur[j] - fma(vk, wj, wk * vj);
-        rcur[j] = r;
-        if (j >= k + 2) x2[0] = fma(r, r, x2[0]);
-      }
-    } else {
-      for (int j = k + 2 + tid; j < n; j += THREADS) x2[0] = fma(rcur[j], rcur[j], x2[0]);
-    }
-    block_sum_k<1>(x2, s_rb, parity);
-    const double dk = rcur[k];
-    const double alpha = (k + 1 < n) ? rcur[k + 1] : 0.0;
-    double tau = 0.0, ek = alpha, scl = 0.0;
-    if (k <= n - 3 && x2[0] > 0.0) {
-      const double beta = -copysign(sqrt(fma(alpha, alpha, x2[0])), alpha);
-      tau = (beta - alpha) / beta;
-      scl = 1.0 / (alpha - beta);
-      ek = beta;
-    }
-    if (cr == 0 && tid == 0) {
-      a.dd[(size_t)b * n + k] = dk;
-      a.ee[(size_t)b * n + k] = (k + 1 < n) ? ek : 0.0;
-      a.tau[(size_t)b * n + k] = tau;
-    }
-    if (k == n - 1) break;
-    for (int j = k + 1 + tid; j < n; j += THREADS) {
-      const double vj = (j == k + 1) ? 1.0 : rcur[j] * scl;
-      vnew[j] = vj;
-      if (cr == 0) Vh[(size_t)k * n + j] = vj;
-    }
-    __syncthreads();
-    LG_MARK(1);
-    // (3) own live rows (>= k+1): pending rank-2 update fused with A v'
-    {
-      const int q0 = (k + 1 > gw) ? (k + 1 - gw + W - 1) / W : 0;
-      const int first = gw + q0 * W;
-      const int rl = first < n ? (n - 1 - first) / W + 1 : 0;
-      double* rpub = rowb + ((k + 1) & 1) * np;
-      double* pnext = pb + ((k + 1) & 1) * np;
-#define LG_CASE(RLV)                                                                                         \
-  case RLV:                                                                                                  \
-    if constexpr (RLV <= R) lg_step3<RLV>(cluster, CL, A, n, k, first, W, lane, v, wv, vnew, rpub, pnext, a.ablate);   \
-    break;
-      switch (rl) {
-        LG_CASE(1) LG_CASE(2) LG_CASE(3) LG_CASE(4) LG_CASE(5) LG_CASE(6) LG_CASE(7) LG_CASE(8) LG_CASE(9) LG_CASE(10)
-        default: break;
-      }
-#undef LG_CASE
-    }
-    cur ^= 1;
-    tau_prev = tau;
-    LG_MARK(2);
-    cluster.sync();
-    LG_MARK(3);
-  }
-  cluster.sync();  // nobody leaves while its shared memory may still be read
-  if (a.dbg && tid == 448 && cr == CL - 1)
-    for (int q = 0; q < 4; ++q) a.dbg[(size_t)b * 4 + q] = tacc[q];
-}
-
-// Two matrices per cluster in lock-step: the per-column fixed costs (pivot-row pull, two block
-// reductions, the Householder scalar chain, the cluster barrier and its wait for the slowest warp)
-// are paid once per PAIR of columns, and the two independent update + symv passes give every warp
-// twice the loads in flight between barriers.  blockIdx.x / CL = pair index; matrices 2 pair and
-// 2 pair + 1 (the second may not exist: its arithmetic is skipped, the barriers are not).
-template <int R, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) k_lg_tridiag2x(LgArgs a, int B) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
-  const int pair = blockIdx.x / CL;
-  const int n = a.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = THREADS / 32;
-  const int np = (n + 3) & ~3;
-  extern __shared__ double sm[];
-  // per matrix m: vb [2][np] | pb [2][np] | rowb [2][np] | rcur [np] | wv [np]  = 8 np doubles
-  double* base[2] = {sm, sm + 8 * (size_t)np};
-  __shared__ double s_rb[2 * 32 * 2];
-  int parity = 0;
-  const int bm[2] = {2 * pair, 2 * pair + 1};
-  const bool act[2] = {true, bm[1] < B};
-  double* A[2];
-  double* Vh[2];
-  for (int m = 0; m < 2; ++m) {
-    const int b = act[m] ? bm[m] : bm[0];
-    A[m] = a.A + (size_t)b * n * n;
-    Vh[m] = a.Vh + (size_t)b * n * n;
-  }
-  const int W = CL * NW, gw = wid * CL + cr;
-  double tau_prev[2] = {0.0, 0.0};
-  int cur = 0;
-
-  for (int m = 0; m < 2; ++m) {
-    double* vb = base[m];
-    double* rowb = vb + 4 * np;
-    double* wv = vb + 7 * np;
-    if (gw == 0 && act[m])
-      for (int j = lane; j < n; j += 32) rowb[j] = A[m][j];
-    for (int j = tid; j < np; j += THREADS) {
-      vb[j] = 0.0;
-      wv[j] = 0.0;
-    }
-  }
-  cluster.sync();
-
-  for (int k = 0; k < n; ++k) {
-    const bool pend = k > 0;
-    // (1) pull the pivot rows, p . v
-    double part[2] = {0.0, 0.0};
-    for (int m = 0; m < 2; ++m) {
-      if (!act[m]) continue;
-      double* vb = base[m];
-      const double* v = vb + cur * np;
-      const double* p = vb + 2 * np + (k & 1) * np;
-      double* rcur = vb + 6 * np;
-      const double* rrow = cluster.map_shared_rank(vb + 4 * np + (k & 1) * np, k % CL);
-      for (int j = k + tid; j < n; j += THREADS) {
-        rcur[j] = rrow[j];
-        if (pend) part[m] = fma(p[j], v[j], part[m]);
-      }
-    }
-    block_sum_k<2>(part, s_rb, parity);
-    // (2) w, row k through the pending reflector, its norm
-    double x2[2] = {0.0, 0.0}, cc[2];
-    for (int m = 0; m < 2; ++m) {
-      cc[m] = 0.5 * tau_prev[m] * tau_prev[m] * part[m];
-      if (!act[m]) continue;
-      double* vb = base[m];
-      const double* v = vb + cur * np;
-      const double* p = vb + 2 * np + (k & 1) * np;
-      double* rcur = vb + 6 * np;
-      double* wv = vb + 7 * np;
-      if (pend) {
-        const double vk = v[k], wk = fma(tau_prev[m], p[k], -cc[m] * vk);
-        for (int j = k + tid; j < n; j += THREADS) {
-          const double vj = v[j];
-          const double wj = fma(tau_prev[m], p[j], -cc[m] * vj);
-          wv[j] = wj;
-          const double r = rcur[j] - fma(vk, wj, wk * vj);
-          rcur[j] = r;
-          if (j >= k + 2) x2[m] = fma(r, r, x2[m]);
-        }
-      } else {
-        for (int j = k + 2 + tid; j < n; j += THREADS) x2[m] = fma(rcur[j], rcur[j], x2[m]);
-      }
-    }
-    block_sum_k<2>(x2, s_rb, parity);
-    double tau[2] = {0.0, 0.0};
-    for (int m = 0; m < 2; ++m) {
-      if (!act[m]) continue;
-      double* vb = base[m];
-      double* vnew = vb + (cur ^ 1) * np;
-      const double* rcur = vb + 6 * np;
-      const double dk = rcur[k];
-      const double alpha = (k + 1 < n) ? rcur[k + 1] : 0.0;
-      double ek = alpha, scl = 0.0;
-      if (k <= n - 3 && x2[m] > 0.0) {
-        const double beta = -copysign(sqrt(fma(alpha, alpha, x2[m])), alpha);
-        tau[m] = (beta - alpha) / beta;
-        scl = 1.0 / (alpha - beta);
-        ek = beta;
-      }
-      if (cr == 0 && tid == 0) {
-        a.dd[(size_t)bm[m] * n + k] = dk;
-        a.ee[(size_t)bm[m] * n + k] = (k + 1 < n) ? ek : 0.0;
-        a.tau[(size_t)bm[m] * n + k] = tau[m];
-      }
-      if (k < n - 1)
-        for (int j = k + 1 + tid; j < n; j += THREADS) {
-          const double vj = (j == k + 1) ? 1.0 : rcur[j] * scl;
-          vnew[j] = vj;
-          if (cr == 0) Vh[m][(size_t)k * n + j] = vj;
-        }
-    }
-    if (k == n - 1) break;
-    __syncthreads();
-    // (3) own live rows (>= k+1) of both matrices: pending rank-2 update fused with A v'
-    {
-      const int q0 = (k + 1 > gw) ? (k + 1 - gw + W - 1) / W : 0;
-      const int first = gw + q0 * W;
-      const int rl = first < n ? (n - 1 - first) / W + 1 : 0;
-      for (int m = 0; m < 2; ++m) {
-        if (!act[m]) continue;
-        double* vb = base[m];
-        const double* v = vb + cur * np;
-        const double* vnew = vb + (cur ^ 1) * np;
-        const double* wv = vb + 7 * np;
-        double* rpub = vb + 4 * np + ((k + 1) & 1) * np;
-        double* pnext = vb + 2 * np + ((k + 1) & 1) * np;
-#define LG_CASE(RLV)                                                                                                    \
-  case RLV:                                                                                                             \
-    if constexpr (RLV <= R) lg_step3<RLV>(cluster, CL, A[m], n, k, first, W, lane, v, wv, vnew, rpub, pnext, a.ablate); \
-    break;
-        switch (rl) {
-          LG_CASE(1) LG_CASE(2) LG_CASE(3) LG_CASE(4) LG_CASE(5) LG_CASE(6) LG_CASE(7) LG_CASE(8) LG_CASE(9) LG_CASE(10)
-          default: break;
-        }
-#undef LG_CASE
-      }
-    }
-    cur ^= 1;
-    tau_prev[0] = tau[0];
-    tau_prev[1] = tau[1];
-    cluster.sync();
-  }
-  cluster.sync();  // nobody leaves while its shared memory may still be read
 }
 
 // ---- inverse iteration for a cluster vector that cancelled (LAPACK dstein's method) -----------------
@@ -1165,36 +671,15 @@ __global__ void k_lg_clear_tau_flagged(int n, const int32_t* __restrict__ status
 // ------------------------------------------------------------------------------------------------
 static size_t lg_al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int g_lg_cluster = 0;
-static int g_lg_blocked = 1;
-// tuning: 1 (default) = blocked dlatrd + DMMA cluster tridiagonalisation (tridiag_cluster.cu), 0 = the unblocked
-// fused update + symv kernels of this file
-extern "C" int mop_debug_large_blocked(int on) {
-  g_lg_blocked = on;
+// tuning (csrc/mop_private.h): CTAs per matrix of the cluster tridiagonalisation (1, 2, 4, 8; 0 = by batch size)
+extern "C" int mop_priv_large_cluster(int cl) {
+  g_lg_cluster = cl;
   return MOP_OK;
 }
 int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, double* ee, double* tau,
                                int cluster_ctas, cudaStream_t stream);
-static int g_lg_pair = 0;   // 0 auto, 1 always, -1 never
-extern "C" int mop_debug_large_pair(int mode) {
-  g_lg_pair = mode;
-  return MOP_OK;
-}
-extern "C" int mop_debug_large_cluster(int cl) {
-  g_lg_cluster = cl;
-  return MOP_OK;
-}
-static long long* g_lg_dbg = nullptr;
-static int g_lg_ablate = 0;
-extern "C" int mop_debug_large_ablate(int mask) {
-  g_lg_ablate = mask;
-  return MOP_OK;
-}
-// diagnostics: device buffer [B][4] receiving the cycles one CTA of each cluster spent in the
-// column phases (w, Householder, update + symv, cluster barrier) of the next launches
-extern "C" int mop_debug_large_timing(void* buf) {
-  g_lg_dbg = (long long*)buf;
-  return MOP_OK;
-}
+int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
+                           double* tau, double* gq, int* flag, cudaStream_t stream);
 
 int mop_large_supported(int n) { return n >= 3 && n <= mop::LG_MAX_N; }
 
@@ -1213,9 +698,6 @@ static int lg_launch_bt(int B, const mop::LgArgs& a, cudaStream_t stream) {
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
-
-int mop_launch_tridiag_packed(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
-                              double* tau, double* gq, int* flag, cudaStream_t stream);
 
 static void lg_carve(int B, int n, void* work, mop::LgArgs& a) {
   const size_t nn = lg_al(sizeof(double) * (size_t)B * n * n), nv = lg_al(sizeof(double) * (size_t)B * n);
@@ -1247,8 +729,8 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
   a.evals = evals;
   a.evecs = nullptr;
   a.status = status;
-  a.dbg = g_lg_dbg;
-  a.ablate = g_lg_ablate;
+  a.dbg = nullptr;
+  a.ablate = 0;
   {
     dim3 grid((n + 31) / 32, (n + 31) / 32, B);
     mop::k_lg_symcopy<<<grid, 256, 0, stream>>>(n, A, a.A);
@@ -1256,82 +738,15 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
   }
   const int np = (n + 3) & ~3;
   if (n <= 160 && g_lg_cluster == 0) {
-    // the matrix fits one SM: the packed shared-memory tridiagonalisation (two structures per SM) replaces
-    // the cluster kernel; same outputs (reflector rows with explicit unit entries, d, e, tau)
+    // the matrix fits one SM: the blocked shared-memory tridiagonalisation (two structures per SM) replaces the
+    // cluster kernel; same outputs (reflector rows with explicit unit entries, d, e, tau)
     double* gq_dummy = a.pbuf;
     int* flag = (int*)(a.pbuf + (size_t)B * n);
-    int rc = mop_launch_tridiag_packed(B, n, a.A, nullptr, a.Vh, a.dd, a.ee, a.tau, gq_dummy, flag, stream);
-    if (rc != MOP_OK) return rc;
-  } else if (g_lg_blocked && g_lg_cluster >= 0) {
-    int rc = mop_launch_tridiag_cluster(B, n, a.A, a.Vh, a.dd, a.ee, a.tau, g_lg_cluster, stream);
+    int rc = mop_launch_tridiag_blk(B, n, a.A, nullptr, a.Vh, a.dd, a.ee, a.tau, gq_dummy, flag, stream);
     if (rc != MOP_OK) return rc;
   } else {
-    int CL = g_lg_cluster;
-    const bool legacy = CL < 0;  // diagnostics: the first-generation kernel (negative cluster size)
-    if (legacy) CL = -CL;
-    if (CL != 1 && CL != 2 && CL != 4 && CL != 8) {
-      // small batches: one wave of smaller clusters beats two waves of 8 (rows per warp <= 10)
-      CL = 8;
-      if (B * 8 > 148 && B * 4 <= 148 && (n + 4 * 16 - 1) / (4 * 16) <= 10) CL = 4;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B * CL));
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    constexpr int T2 = 512;
-    const int W = CL * (T2 / 32);
-    const int R = (n + W - 1) / W;
-    if (legacy || R > 10) {
-      const size_t smem = sizeof(double) * 3 * (size_t)np;
-      MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cfg.blockDim = dim3(mop::LG_TRI_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag, a));
-    } else {
-      // two matrices per cluster in lock-step when the batch still fills the GPU with pairs
-      const bool paired = g_lg_pair >= 0 && (g_lg_pair == 1 || B >= 2 * (148 / CL));
-      const size_t smem = sizeof(double) * (paired ? 16 : 8) * (size_t)np;
-      cfg.blockDim = dim3(T2);
-      cfg.dynamicSmemBytes = smem;
-      if (paired) {
-        cfg.gridDim = dim3((unsigned)(((B + 1) / 2) * CL));
-#define LG_LAUNCH2X(RR)                                                                                          \
-  do {                                                                                                           \
-    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag2x<RR, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)smem));                                                             \
-    MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag2x<RR, T2>, a, B));                                  \
-  } while (0)
-        if (R <= 2) LG_LAUNCH2X(2);
-        else if (R == 3) LG_LAUNCH2X(3);
-        else if (R == 4) LG_LAUNCH2X(4);
-        else if (R == 5) LG_LAUNCH2X(5);
-        else if (R == 6) LG_LAUNCH2X(6);
-        else if (R <= 8) LG_LAUNCH2X(8);
-        else LG_LAUNCH2X(10);
-#undef LG_LAUNCH2X
-      } else {
-#define LG_LAUNCH2(RR)                                                                                          \
-  do {                                                                                                          \
-    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_lg_tridiag2<RR, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)smem));                                                            \
-    MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mop::k_lg_tridiag2<RR, T2>, a));                                     \
-  } while (0)
-      if (R <= 2) LG_LAUNCH2(2);
-      else if (R == 3) LG_LAUNCH2(3);
-      else if (R == 4) LG_LAUNCH2(4);
-      else if (R == 5) LG_LAUNCH2(5);
-      else if (R == 6) LG_LAUNCH2(6);
-      else if (R <= 8) LG_LAUNCH2(8);
-      else LG_LAUNCH2(10);
-#undef LG_LAUNCH2
-      }
-    }
+    int rc = mop_launch_tridiag_cluster(B, n, a.A, a.Vh, a.dd, a.ee, a.tau, g_lg_cluster, stream);
+    if (rc != MOP_OK) return rc;
   }
   {
     const int thr = n <= 160 ? 160 : mop::LG_EIG_THREADS;

@@ -123,3 +123,89 @@ extern "C" int mop_hessian_clip_eigvals(int B, int n, const double* evals, const
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
+
+// ---- effective Hessian for fixed atoms (optimization.py:1325-1343,1358-1362) --------------------------------------------
+// H -= H[:, f] pinv(H[f, f] + 1e-10 I) H[f, :] for the coordinate set f of the fixed atoms (HessianManager.
+// calc_eff_hess_for_fix_atoms_and_set_hess applies it to the bias Hessian and to the model Hessian).  The pseudo-inverse
+// comes from the eigendecomposition of the small symmetric block (mop_eigh on the gathered blocks): numpy.linalg.pinv
+// drops singular values <= 1e-15 max|lambda|.
+namespace mop {
+
+__global__ void __launch_bounds__(256) k_gather_fix_block(int n, int m, const int* __restrict__ fix,
+                                                          const double* __restrict__ H_all, double* __restrict__ F_all) {
+  const int b = blockIdx.x;
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int p = e / m, q = e - p * m;
+    F_all[(size_t)b * m * m + e] = H_all[(size_t)b * n * n + (size_t)fix[p] * n + fix[q]] + (p == q ? 1e-10 : 0.0);
+  }
+}
+
+// evals / evecs (rows = eigenvectors) of the gathered blocks.  Shared memory: P [m][m] | W [m][n] | C [n][m].
+__global__ void __launch_bounds__(256) k_schur_fix(int n, int m, const int* __restrict__ fix,
+                                                   const double* __restrict__ evals_all,
+                                                   const double* __restrict__ evecs_all, double* __restrict__ H_all) {
+  extern __shared__ double sm[];
+  double* P = sm;
+  double* W = P + (size_t)m * m;
+  double* C = W + (size_t)m * n;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* H = H_all + (size_t)b * n * n;
+  const double* ev = evals_all + (size_t)b * m;
+  const double* V = evecs_all + (size_t)b * m * m;
+  double mx = 0.0;
+  for (int k = 0; k < m; ++k) mx = fmax(mx, fabs(ev[k]));
+  const double cut = 1e-15 * mx;
+  for (int e = tid; e < m * m; e += blockDim.x) {
+    const int p = e / m, q = e - p * m;
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k)
+      if (fabs(ev[k]) > cut) acc += V[(size_t)k * m + p] * V[(size_t)k * m + q] / ev[k];
+    P[e] = acc;
+  }
+  for (int e = tid; e < n * m; e += blockDim.x) {
+    const int i = e / m, a = e - i * m;
+    C[e] = H[(size_t)i * n + fix[a]];          // H[:, f]
+  }
+  __syncthreads();
+  for (int e = tid; e < m * n; e += blockDim.x) {  // W = P H[f, :]
+    const int a = e / n, j = e - a * n;
+    double acc = 0.0;
+    for (int c = 0; c < m; ++c) acc += P[a * m + c] * H[(size_t)fix[c] * n + j];
+    W[e] = acc;
+  }
+  __syncthreads();
+  for (size_t e = tid; e < (size_t)n * n; e += blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    double acc = 0.0;
+    for (int a = 0; a < m; ++a) acc += C[i * m + a] * W[a * n + j];
+    H[e] -= acc;
+  }
+}
+
+}  // namespace mop
+
+extern "C" int mop_fix_atoms_gather(int B, int n, int m, const int32_t* fix_coords, const double* H, double* blocks,
+                                    void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0 && m > 0 && m <= n && fix_coords && H && blocks, "mop_fix_atoms_gather: bad arguments");
+  if (B == 0) return MOP_OK;
+  mop::k_gather_fix_block<<<B, 256, 0, (cudaStream_t)stream>>>(n, m, fix_coords, H, blocks);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+// H [B][n][n] in place; fix_coords [m] device int32 (3 (a - 1) + c of every fixed atom); evals [B][m], evecs [B][m][m]:
+// mop_eigh of the blocks from mop_fix_atoms_gather.
+extern "C" int mop_fix_atoms_schur(int B, int n, int m, const int32_t* fix_coords, const double* evals,
+                                   const double* evecs, double* H, void* stream) {
+  MOP_REQUIRE(B >= 0 && n > 0 && m > 0 && m <= n && fix_coords && evals && evecs && H, "mop_fix_atoms_schur: bad arguments");
+  if (B == 0) return MOP_OK;
+  const size_t smem = sizeof(double) * ((size_t)m * m + 2 * (size_t)m * n);
+  if (smem > 200 * 1024) {
+    mop_set_error("mop_fix_atoms_schur: %d fixed coordinates of %d need %zu bytes of shared memory", m, n, smem);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_schur_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mop::k_schur_fix<<<B, 256, smem, (cudaStream_t)stream>>>(n, m, fix_coords, evals, evecs, H);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}

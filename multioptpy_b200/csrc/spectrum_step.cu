@@ -1,6 +1,6 @@
 // Spectrum + RS-I-RFO step of a tridiagonalised Hessian, SEVEN structures per SM (n <= 160).
 //
-// k_eigh_tridiag (eigh_tridiag.cu) keeps the eigenvectors Z of T in shared memory: one CTA per SM, and
+// The first-generation kernel kept the eigenvectors Z of T in shared memory: one CTA per SM, and
 // every phase after the tridiagonalisation is a long dependent chain run by a few hundred threads
 // (Sturm bisection 53 %, twisted factorisation 20 %, the one-warp secular solve and back-transform the
 // rest) - the SM idles.  Here Z lives in global memory (one [n][n] slab per structure, column i owned by
@@ -671,8 +671,8 @@ __global__ void __launch_bounds__(32 * NW, SpMinBlocks<NW>::value) k_spectrum_st
 }  // namespace mop
 
 static long long* g_sp_dbg = nullptr;
-// diagnostics: device buffer [B][16] receiving per-phase clock counts of the next launches
-extern "C" int mop_debug_spectrum_timing(void* buf) {
+// diagnostics (include/../csrc/mop_private.h): device buffer [B][16] receiving per-phase clock counts of the next launches
+extern "C" int mop_priv_spectrum_timing(void* buf) {
   g_sp_dbg = (long long*)buf;
   return MOP_OK;
 }
@@ -726,4 +726,42 @@ int mop_launch_spectrum_step(int B, int n, int saddle_order, int neb_mode, doubl
     case 4: return launch_spectrum<4>(B, a, stream);
     default: return launch_spectrum<5>(B, a, stream);
   }
+}
+
+// ---- the shared-memory spectral path, 3 <= n <= 160: blocked tridiagonalisation + spectrum / step ------------------
+int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
+                           double* tau, double* gq, int* flag, cudaStream_t stream);
+
+int mop_tridiag_supported(int n) { return n >= 3 && n <= mop::SP_MAX_N; }
+// Vh | Dm | d, e, tau, gq | flag
+size_t mop_tridiag_workspace_bytes(int B, int n) {
+  return 2 * sizeof(double) * (size_t)B * n * n + 4 * sizeof(double) * (size_t)B * n + sizeof(int) * (size_t)B + 64;
+}
+
+// RS-I-RFO step from an already projected Hessian (mop_rsirfo_spectral_step): k_tridiag_blk, then k_spectrum_step.
+// zbuf: a [B][n][n] slab for the eigenvectors of T.
+int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
+                            const double* Hp, const double* gp, const double* Bg, const double* Be,
+                            double* state, double* move, double* evals_out, double* pred,
+                            int32_t* status, void* work, size_t work_bytes, double* zbuf, cudaStream_t stream) {
+  if (B == 0) return MOP_OK;
+  if (!mop_tridiag_supported(n) || !zbuf) {
+    mop_set_error("spectral RS-I-RFO step: n = %d not supported (3 .. %d)", n, mop::SP_MAX_N);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (!work || work_bytes < mop_tridiag_workspace_bytes(B, n)) {
+    mop_set_error("spectral RS-I-RFO step: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  double* Vh = (double*)work;
+  double* Dm = Vh + (size_t)B * n * n;
+  double* pd = Vh + 2 * (size_t)B * n * n;
+  double* pe = pd + (size_t)B * n;
+  double* pt = pd + 2 * (size_t)B * n;
+  double* pg = pd + 3 * (size_t)B * n;
+  int* pflag = (int*)(pd + 4 * (size_t)B * n);
+  int rc = mop_launch_tridiag_blk(B, n, Hp, gp, Vh, pd, pe, pt, pg, pflag, stream);
+  if (rc != MOP_OK) return rc;
+  return mop_launch_spectrum_step(B, n, saddle_order, neb_mode, tmin, tmax, Vh, zbuf, Dm, pd, pe, pt, pg, pflag, Bg, Be,
+                                  state, move, evals_out, pred, status, stream);
 }

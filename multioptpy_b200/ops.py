@@ -393,6 +393,31 @@ def fischer_d3old_hessian(xyz, atom_params, d3=None, dynamic=False):
     return H, counts, status
 
 
+def fix_atoms_effective_hessian(H, fix_atoms):
+    """HessianManager.calc_eff_hess_for_fix_atoms_and_set_hess (optimization.py:1325-1343): in place
+    H -= H[:, f] pinv(H[f, f] + 1e-10 I) H[f, :], f = the coordinates of the 1-based atoms in fix_atoms."""
+    lib = _lib.load()
+    B, n, _ = H.shape
+    _chk(H, "H", (B, n, n))
+    fix = []
+    for a in fix_atoms:
+        fix.extend([3 * (a - 1), 3 * (a - 1) + 1, 3 * (a - 1) + 2])
+    m = len(fix)
+    if m == 0:
+        return H
+    if max(fix) >= n or min(fix) < 0:
+        raise MopError("fix_atoms: atom index out of range")
+    fd = torch.tensor(fix, dtype=torch.int32, device=H.device)
+    blocks = torch.empty(B, m, m, dtype=torch.float64, device=H.device)
+    with torch.cuda.device(H.device):
+        _lib.check(lib.mop_fix_atoms_gather(B, n, m, _ptr(fd), _ptr(H), _ptr(blocks), _stream(H.device)), "mop_fix_atoms_gather")
+    evals, evecs, st = eigh(blocks, "jacobi" if m <= 64 else "auto")
+    with torch.cuda.device(H.device):
+        _lib.check(lib.mop_fix_atoms_schur(B, n, m, _ptr(fd), _ptr(evals), _ptr(evecs), _ptr(H), _stream(H.device)),
+                   "mop_fix_atoms_schur")
+    return H
+
+
 def hessian_ts_modify(H):
     """TransitionStateHessian.create_ts_hessian (ModelHessian/tshess.py) for a batch -> (H_ts, modified [B])."""
     lib = _lib.load()

@@ -1086,6 +1086,16 @@ def fischerd3_hessian(coord, prm, d3=(1.0, 0.7875, 0.4289, 4.4407)):
     return project_hessian_trrot(H, coord.reshape(-1))
 
 
+def fix_atoms_effective_hessian(H, fix_atoms):
+    """HessianManager.calc_eff_hess_for_fix_atoms_and_set_hess, optimization.py:1325-1343 (one Hessian)."""
+    fix = []
+    for a in fix_atoms:
+        fix.extend([3 * (a - 1), 3 * (a - 1) + 1, 3 * (a - 1) + 2])
+    fix = np.array(fix, dtype="int64")
+    inv = np.linalg.pinv(H[np.ix_(fix, fix)] + np.eye(len(fix)) * 1e-10)
+    return H - np.dot(H[:, fix], np.dot(inv, H[fix, :]))
+
+
 def ts_hessian(H):
     """TransitionStateHessian.create_ts_hessian, ModelHessian/tshess.py:14-40."""
     lam, V = np.linalg.eigh(H)

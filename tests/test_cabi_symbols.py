@@ -8,8 +8,8 @@ from multioptpy_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "mop_b200.h")).read()
+def declared_symbols(path=("include", "mop_b200.h")):
+    text = open(os.path.join(ROOT, *path)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(mop_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,6 +25,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in mop_b200.h but not exported"
     # and the ctypes table covers the header exactly
     assert sorted(_lib.SIGNATURES) == names
+    # the public header carries no probe / tuning hooks; those live in the private header, equally complete
+    assert not [n for n in names if "debug" in n or "bench" in n or "priv" in n]
+    priv = declared_symbols(("multioptpy_b200", "csrc", "mop_private.h"))
+    assert sorted(_lib.PRIVATE_SIGNATURES) == priv
+    for name in priv:
+        assert hasattr(lib, name), f"{name} declared in mop_private.h but not exported"
 
 
 def test_version_and_error_string():

@@ -34,12 +34,12 @@ def test_eigh_large_vs_lapack(n, cl):
         A[2] = O.project_hessian_trrot(synthetic.spd_hessian(n, rng), x)
     A[3] = np.diag(np.linspace(-1.0, 2.0, n)) + 1e-3 * A[3]
     lib = _lib.load()
-    lib.mop_debug_large_cluster(cl)
+    lib.mop_priv_large_cluster(cl)
     try:
         evals, evecs, st = ops.eigh(torch.from_numpy(A).cuda(), "large")
         torch.cuda.synchronize()
     finally:
-        lib.mop_debug_large_cluster(0)
+        lib.mop_priv_large_cluster(0)
     st = st.cpu().numpy()
     assert not (st & ops.ST_EIG_NOCONV).any()
     _check(A, evals.cpu().numpy(), evecs.cpu().numpy())

@@ -173,3 +173,22 @@ def test_gpu_full_neb_optimize_vs_reference(golden_dir):
         ref = z["new_geom_ang"][it].reshape(nimg, -1) / 0.52917721067
         assert np.abs(new - ref).max() <= 1e-10 * np.abs(ref).max(), it
     assert rel(opt.hessian.cpu().numpy(), z["H_final"]) < 1e-9
+
+
+def test_neb_on_disk_formats_roundtrip(tmp_path):
+    """tmp_hessian_<i>.npy and the 12-decimal xyz samples of the reference (rfo_neb.py:18-25,175; fileio.py:441-446)."""
+    from multioptpy_b200 import fileio
+    rng = np.random.default_rng(3)
+    H = rng.standard_normal((3, 9, 9))
+    fileio.save_neb_hessians(str(tmp_path), H, first=2)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["tmp_hessian_2.npy", "tmp_hessian_3.npy", "tmp_hessian_4.npy"]
+    back = fileio.load_neb_hessians(str(tmp_path), nimg=6, natoms=3, first=1, nloc=5)
+    assert np.array_equal(back[1:4], H) and np.array_equal(back[0], np.eye(9)) and np.array_equal(back[4], np.eye(9))
+    G = rng.standard_normal((2, 3, 3)) * 3
+    paths = fileio.write_xyz_samples(str(tmp_path / "s"), "aldol", ["C", "H", "Cl"], G, (0, 1))
+    txt = open(paths[0]).read().splitlines()
+    assert txt[0] == "3" and txt[1] == "0 1"
+    x = G[0][2]
+    assert txt[4] == f"Cl   {x[0]:>17.12f}   {x[1]:>17.12f}   {x[2]:>17.12f}"      # the reference's f-string, verbatim layout
+    e, xyz, cm = fileio.read_xyz_sample(paths[1])
+    assert e == ["C", "H", "Cl"] and cm == (0, 1) and np.abs(xyz - G[1]).max() < 5e-13

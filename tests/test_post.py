@@ -76,3 +76,36 @@ def test_gpu_convergence_vs_golden(golden_dir):
         st = types.SimpleNamespace(effective_gradient=z["conv/grad"][c].reshape(-1, 3))
         ok, mdt, rdt = chk.check_convergence(st, z["conv/disp"][c].reshape(-1, 3), [])
         assert int(ok) == z["conv/ok"][c] and mdt == z["conv/max_disp_thr"][c]
+
+
+def test_fix_atoms_oracle_matches_reference_expression():
+    """The oracle restates optimization.py:1325-1343 verbatim; its defining properties: rows / columns of the fixed
+    coordinates vanish (to the 1e-10 regularisation) and the free block is the Schur complement."""
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((18, 18)); H = A @ A.T + np.eye(18)
+    He = O.fix_atoms_effective_hessian(H.copy(), [2, 5])
+    fix = [3, 4, 5, 12, 13, 14]
+    free = [i for i in range(18) if i not in fix]
+    assert np.abs(He[fix]).max() < 1e-8 and np.abs(He[:, fix]).max() < 1e-8
+    S = H[np.ix_(free, free)] - H[np.ix_(free, fix)] @ np.linalg.solve(H[np.ix_(fix, fix)], H[np.ix_(fix, free)])
+    assert np.abs(He[np.ix_(free, free)] - S).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_fix_atoms_effective_hessian_vs_oracle():
+    import torch
+    from multioptpy_b200 import ops
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(6)
+    B, n = 5, 33
+    Hs = []
+    for b in range(B):
+        A = rng.standard_normal((n, n)); Hs.append(A @ A.T / n + 0.1 * np.eye(n))
+    Hs[3][np.ix_(range(6, 9), range(n))] = 0.0; Hs[3][np.ix_(range(n), range(6, 9))] = 0.0    # a singular fixed block: pinv cut-off
+    H = np.stack(Hs)
+    Hd = torch.from_numpy(H.copy()).to("cuda:0")
+    ops.fix_atoms_effective_hessian(Hd, [3, 7, 10])
+    for b in range(B):
+        ref = O.fix_atoms_effective_hessian(H[b].copy(), [3, 7, 10])
+        assert np.linalg.norm(Hd[b].cpu().numpy() - ref) <= 1e-10 * np.linalg.norm(ref)

@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 HBM = float(peaks.get("hbm_gbs", 6650.0))
-FP64 = 36.7  # TFLOP/s, mop_bench_dfma (bench.py measures it in-run)
+FP64 = 36.7  # TFLOP/s, mop_priv_bench_dfma (bench.py measures it in-run)
 T = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev) if dt is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
 rows = []
 

@@ -60,11 +60,11 @@ elif which == "sp":   # phase cycles of k_spectrum_step on the C4 chain (iterati
     ch.step(H, r["x0"], ch.g, r["E_afir"], r["g_afir"], r["H_afir"], st0)
     Eb1, gb1, Hb1 = ch.afir(x1g)
     dbg = torch.zeros(B, 16, dtype=torch.int64, device=dev)
-    lib.mop_debug_spectrum_timing(dbg.data_ptr())
+    lib.mop_priv_spectrum_timing(dbg.data_ptr())
     H.copy_(r["H_model"]); st = st0.clone()
     o = ch.step(H, r["x1"], r["g1"], Eb1, gb1, Hb1, st, x_prev=r["x0"], g_prev=ch.g, dE=1e-3)
     torch.cuda.synchronize()
-    lib.mop_debug_spectrum_timing(0)
+    lib.mop_priv_spectrum_timing(0)
     d = dbg.cpu().numpy().astype(float)
     names = ["load/scale/split", "eigenvalues", "twisted vectors", "cluster CGS2", "gamma + rfo_core", "y = Z c", "Q y"]
     tot = d[:, :7].sum(1)

@@ -11,8 +11,8 @@ A = rng.standard_normal((B, n, n)); A = 0.5 * (A + A.transpose(0, 2, 1))
 At = torch.from_numpy(A).cuda()
 lib = _lib.load()
 raw = ctypes.CDLL(lib._name) if hasattr(lib, "_name") else lib
-for blocked, cl, sym in ((1, 8, 0), (1, 4, 1), (1, 4, 0), (1, 2, 1), (1, 2, 0), (0, 0, 0)):
-    lib.mop_debug_large_blocked(blocked); lib.mop_debug_large_cluster(cl); raw.mop_priv_tridiag_cluster_sym(sym)
+for blocked, cl, sym in ((1, 8, 0), (1, 4, 1), (1, 4, 0), (1, 2, 1), (1, 2, 0), (1, 1, 1)):
+    lib.mop_priv_large_cluster(cl); raw.mop_priv_tridiag_cluster_sym(sym)
     ops.eigh(At, "large"); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -22,7 +22,7 @@ for blocked, cl, sym in ((1, 8, 0), (1, 4, 1), (1, 4, 0), (1, 2, 1), (1, 2, 0), 
     ref = np.linalg.eigvalsh(A[:2])
     err = np.abs(ev[:2].cpu().numpy() - ref).max() / np.abs(ref).max()
     print(f"n={n} B={B} blocked={blocked} cluster={cl} sym={sym}: {e0.elapsed_time(e1)/2:.2f} ms per mop_eigh batch, eig err {err:.2e}, fallbacks {(st.cpu().numpy() & ops.ST_EIG_FALLBACK != 0).sum()}")
-lib.mop_debug_large_blocked(1); lib.mop_debug_large_cluster(int(os.environ.get("CL", "8")))
+lib.mop_priv_large_cluster(int(os.environ.get("CL", "8")))
 dbg = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
 f = raw.mop_priv_tridiag_cluster_timing; f.argtypes = [ctypes.c_void_p]; f.restype = ctypes.c_int
 raw.mop_priv_tridiag_cluster_sym(int(os.environ.get("SYM", "1")))

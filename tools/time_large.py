@@ -11,7 +11,7 @@ A = rng.standard_normal((B, n, n)); A = 0.5 * (A + A.transpose(0, 2, 1))
 At = torch.from_numpy(A).cuda()
 lib = _lib.load()
 for cl in (8, 4, 2, 1):
-    lib.mop_debug_large_cluster(cl)
+    lib.mop_priv_large_cluster(cl)
     ops.eigh(At, "large"); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -19,4 +19,4 @@ for cl in (8, 4, 2, 1):
         ev, V, st = ops.eigh(At, "large")
     e1.record(); torch.cuda.synchronize()
     print(f"n={n} B={B} cluster={cl}: {e0.elapsed_time(e1)/3:.2f} ms per batch, fallbacks {(st.cpu().numpy() & ops.ST_EIG_FALLBACK != 0).sum()}")
-lib.mop_debug_large_cluster(0)
+lib.mop_priv_large_cluster(0)
