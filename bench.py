@@ -386,21 +386,16 @@ def run_b200(args, rank, world, local_rank):
             best = min(best, a.elapsed_time(b_))
         fp64_peak = 148 * 16 * 256 * iters * 64 * 2 / (best * 1e-3) / 1e12   # TFLOP/s
 
-        Hp, gp_, _ = ops.project_trrot(H_d0, x1_d, g=g1_d)
         reps = max(3, min(K, 10))
-        sp_out = None
-        for j in range(2):
-            sp_out = ops.rsirfo_spectral_step(Hp, gp_, g1_d, sts[j % ncopy], Be=Be1, out=sp_out)
-        torch.cuda.synchronize()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for j in range(reps):
-            sp_out = ops.rsirfo_spectral_step(Hp, gp_, g1_d, sts[j % ncopy], Be=Be1, out=sp_out)
-        b_.record(); torch.cuda.synchronize()
-        eig_ms = a.elapsed_time(b_) / reps
-        WF = 9.0 * n ** 3                      # algorithmic flops of one eigh with vectors
+        # The dominant kernel pair IS the step: k_tridiag_blk<5, fused> (update + write-back + projection +
+        # tridiagonalisation) and k_spectrum_step (spectrum, eigenvectors of T, RFO step) are the only launches of
+        # the timed region that do work (the three fallback launches that follow are empty), so its duration is the
+        # device time of the timed loop itself, ms / K, and its algorithmic work W_F = 9 n^3 + 40 n^2 per structure
+        # (one eigendecomposition with vectors + the O(n^2) update / projection / step algebra).
+        eig_ms = ms / K
+        WF = 9.0 * n ** 3 + 40.0 * n * n
         eig_tflops = B * WF / (eig_ms * 1e-3) / 1e12
-        executed_flops = B * (4.0 / 3.0 * n ** 3 + 30.0 * n * n)   # Householder reduction + O(n^2) rest
+        executed_flops = B * (4.0 / 3.0 * n ** 3 + 60.0 * n * n)   # Householder reduction + the O(n^2) rest
         # streaming update kernel against the HBM roofline
         sd = (x1_d - x0_d).contiguous(); yd = (g1_d - g0_d).contiguous()
         Hu = H_d0.clone()
@@ -450,8 +445,10 @@ def run_b200(args, rank, world, local_rank):
                                      "h2d_bytes_per_step": 2 * B * n * 8, "d2h_bytes_per_step": B * n * 8},
             "gpu_launches": 5 * K,   # fused update + projection + tridiagonalisation, spectrum + step, 3 (empty) fallback launches
             "roofline": {"bound": "fp64",
-                         "kernel": "k_tridiag_blk<5> + k_spectrum_step: blocked DMMA tridiagonalisation, then spectrum, "
-                                   "eigenvectors of T and the RFO step in the eigenbasis, timed together (dominant pair)",
+                         "kernel": "k_tridiag_blk<5, fused> + k_spectrum_step = the timed step: Hessian update, write-back, "
+                                   "TR/ROT projection and blocked DMMA tridiagonalisation in one kernel, then spectrum, "
+                                   "eigenvectors of T and the RFO step in the eigenbasis (the other launches of the step are "
+                                   "empty fallbacks); duration = ms_per_step of the timed region",
                          "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": eig_tflops / fp64_peak, "traffic": traffic,
                          "traffic_source": "profiles/r2_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write)",

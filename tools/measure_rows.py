@@ -1,7 +1,7 @@
 """Per-row measurement of the hot-path kernels (SURVEY §8 a-rows) on one B200: device time per call
 (CUDA events, median of repeats, inputs resident and larger than L2 where the config is), algorithmic
 bytes / flops, fraction of the measured roofline, and the CPU oracle timed on one host core beside it.
-Writes gpurun_out/r1b_row_measurements.json (copied to profiles/) and prints a markdown table.  Not the bench line: bench.py is."""
+Writes gpurun_out/r2_row_measurements.json (copied to profiles/) and prints a markdown table.  Not the bench line: bench.py is."""
 import json, os, sys, time, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -165,7 +165,7 @@ cpu = cpu_s(lambda: O.bneb_force(X, E, G), reps=1)
 add("a19-a20", "mop_bneb_force + mop_neb_ayala + mop_neb_limit_tr (one NEB iteration's path kernels, 64 images)", nimg,
     gpu_ms(neb), None, None, cpu / nimg, "config 3 on one GPU; unit = image; cpu = oracle bneb_force only")
 
-json.dump({"hbm_peak_gbs": HBM, "fp64_peak_tflops": FP64, "rows": rows}, open(os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "profiles", "r1b_row_measurements.json"), "w"), indent=1)
+json.dump({"hbm_peak_gbs": HBM, "fp64_peak_tflops": FP64, "rows": rows}, open(os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "profiles", "r2_row_measurements.json"), "w"), indent=1)
 print("\n| row | kernel | units | ms | units/s | GB/s (frac of HBM) | TFLOP/s alg. (frac) | CPU units/s/core | note |")
 print("|---|---|---|---|---|---|---|---|---|")
 for r in rows:
