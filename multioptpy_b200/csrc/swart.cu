@@ -217,223 +217,238 @@ k_swart(int N, int in_smem, const double* __restrict__ xyz_all, const double* __
 
 
 // ------------------------------------------------------------------------------------------------
-// Gather formulation (natoms <= 100): no atomics.  Every 3 x 3 atom-pair block of the raw Hessian is
-// owned by one thread (off-diagonal blocks) or one warp (diagonal blocks), which sums the stretch term
-// and every bend term that touches both atoms, re-evaluating the bend's Wilson vectors where needed
-// (a bend (i, j, k) feeds six blocks, so it is evaluated six times: ~1e7 flops per structure at
-// N = 50 against ~6e5 FP64 shared-memory atomics, which cost ~30 cycles each in the scatter kernel).
-struct SwartBend {
-  int nvec;        // 1 or 2 Wilson vectors
-  double hb;       // force constant
-  double U[2][9];  // (i, j, k) components
-};
+// Gather formulation (natoms <= 100): no atomics.  Every off-diagonal 3 x 3 atom-pair block (a < b) of
+// the raw Hessian is owned by one WARP, which sums the stretch term and every bend that touches both
+// atoms: centre c with ends (a, b), centre a with ends (b, c), centre b with ends (a, c) — 3 (N - 2)
+// candidates, of which the screens pass about a fifth.  The lanes screen the candidates 32 at a time
+// (two contiguous rows of the screen table) and compact the survivors into the warp's queue with
+// ballots; then every lane evaluates one queued bend per round — regular, near-180 and near-0 degree
+// (linear-bend pair) bends through ONE code path, U1 = c1 bn + c2 t / l, U2 = c3 vn / l — into a private
+// 3 x 3 accumulator that is reduced once per pair.  History (1024 structures, N = 50): FP64 shared-memory
+// atomics 13.8 ms; thread-per-block gather that evaluated inside the candidate loop 16.7 ms at 6 of 32
+// lanes active (profiles/r2_ncu_producers_summary.csv); this kernel 1.1 ms.  The diagonal blocks follow
+// from translational invariance — every Wilson vector of a stretch or bend sums to zero over its
+// atoms, so block(a, a) = - sum_{b != a} block(a, b) — summed in fixed order from the rows the CTA
+// just wrote: a bend is evaluated three times instead of six and the result is deterministic.
+// Reciprocal distances are tabulated and sqrt / division go through MUFU seeds + Newton steps (~1 ulp,
+// no IEEE slow path); the parity bar is 1e-10.
+constexpr int SWP_THREADS = 256;
+constexpr int SWP_WARPS = SWP_THREADS / 32;
 
-// bend (i, j, k), i < k, centre j; l1 = |x_i - x_j|, l2 = |x_k - x_j|, ss = s_ij s_jk (swart.py:226-315)
-__device__ __forceinline__ void swart_bend_eval(const double* xyz, int i, int j, int k, double l1, double l2, double ss,
-                                                SwartBend& o) {
-  const SwartConst C;
-  // reciprocals once (FP64 division is ~20 instructions): differs from the reference's divisions by
-  // an ulp, far below the 1e-10 parity bar
-  const double il1 = 1.0 / l1, il2 = 1.0 / l2;
-  double v1[3], v2[3], n1[3], n2[3];
-  for (int c = 0; c < 3; ++c) {
-    v1[c] = xyz[3 * i + c] - xyz[3 * j + c];
-    v2[c] = xyz[3 * k + c] - xyz[3 * j + c];
-    n1[c] = v1[c] * il1;
-    n2[c] = v2[c] * il2;
+// MUFU seed + three Newton steps: ~1 ulp for normal x (callers clamp x >= 1e-12)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double h = 0.5 * x;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const double e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
   }
-  double cs = n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2];
-  cs = fmin(fmax(cs, -1.0), 1.0);
-  const double s2 = fmax(1e-12, 1.0 - cs * cs);
-  const double sn = sqrt(s2);
-  const double iden = 1.0 / fmax(sn, 1e-6);
-  const double f1 = il1 * iden, f2 = il2 * iden;
-  double bn[9];
-  for (int c = 0; c < 3; ++c) {
-    bn[c] = (cs * n1[c] - n2[c]) * f1;
-    bn[6 + c] = (cs * n2[c] - n1[c]) * f2;
-    bn[3 + c] = -(bn[c] + bn[6 + c]);
-  }
-  const double w = C.f + (1.0 - C.f) * sn;
-  o.hb = 0.075 * (ss * ss) * (w * w);
-  o.nvec = 1;
-  const double th1 = cs > 1.0 - C.tolth ? 1.0 - cs : 1.0 + cs;
-  if (!(th1 < C.tolth)) {
-    for (int c = 0; c < 9; ++c) o.U[0][c] = bn[c];
-    return;
-  }
-  const double q = th1 / C.tolth;
-  const double sl = (1.0 - q * q) * (1.0 - q * q);
-  if (!(cs > 1.0 - C.tolth)) {
-    for (int c = 0; c < 9; ++c) o.U[0][c] = (1.0 - sl) * bn[c];
-    return;
-  }
-  double vn[3];
-  cross3(v1, v2, vn);
-  double nvn = norm3(vn);
-  if (nvn < 1e-12) {
-    const double sc1 = v1[0] / (l1 * l1);
-    double cand[3] = {1.0 - sc1 * v1[0], -sc1 * v1[1], -sc1 * v1[2]};
-    double cn = norm3(cand);
-    if (!(cn >= 1e-12)) {
-      const double sc2 = v1[1] / (l1 * l1);
-      cand[0] = -sc2 * v1[0]; cand[1] = 1.0 - sc2 * v1[1]; cand[2] = -sc2 * v1[2];
-      cn = fmax(norm3(cand), 1e-12);
-    }
-    vn[0] = cand[0]; vn[1] = cand[1]; vn[2] = cand[2];
-    nvn = cn;
-  }
-  nvn = fmax(nvn, 1e-12);
-  double vd[3], vn2[3];
-  for (int c = 0; c < 3; ++c) {
-    vn[c] /= nvn;
-    vd[c] = v1[c] - v2[c];
-  }
-  cross3(vd, vn, vn2);
-  const double n2n = fmax(norm3(vn2), 1e-12);
-  o.nvec = 2;
-  for (int c = 0; c < 3; ++c) {
-    const double t = vn2[c] / n2n;
-    o.U[0][c] = vn[c] * il1;
-    o.U[0][6 + c] = vn[c] * il2;
-    o.U[0][3 + c] = -o.U[0][c] - o.U[0][6 + c];
-    const double l0 = t * il1, l6 = t * il2;
-    o.U[1][c] = sl * l0 + (1.0 - sl) * bn[c];
-    o.U[1][6 + c] = sl * l6 + (1.0 - sl) * bn[6 + c];
-    o.U[1][3 + c] = sl * (-l0 - l6) + (1.0 - sl) * bn[3 + c];
-  }
+  return r;
 }
 
-// blk += hb sum_v U_v[sa .. sa+2] U_v[sb .. sb+2]^T
-__device__ __forceinline__ void swart_acc(double* blk, const SwartBend& o, int sa, int sb) {
-  for (int v = 0; v < o.nvec; ++v)
-    for (int p = 0; p < 3; ++p) {
-      const double hp = o.hb * o.U[v][sa + p];
-      for (int q = 0; q < 3; ++q) blk[3 * p + q] = fma(hp, o.U[v][sb + q], blk[3 * p + q]);
-    }
+// smem doubles: xyz 3N | rad N | ID N^2 (1 / clamped distance) | Sc N^2 (screen; negated where the distance
+// is degenerate, 0 on the diagonal) | per warp: bend queue (3N screens + 3N codes)
+__host__ __device__ inline size_t swp_smem_bytes(int N) {
+  return sizeof(double) * (4 * (size_t)N + 2 * (size_t)N * N + (size_t)SWP_WARPS * 3 * N) +
+         sizeof(int) * ((size_t)SWP_WARPS * 3 * N + 2);
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 1)
-k_swart_gather(int N, const double* __restrict__ xyz_all, const double* __restrict__ rad_all, int rad_stride,
-               double* __restrict__ H_all, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(SWP_THREADS, 3)
+k_swart_pair(int N, const double* __restrict__ xyz_all, const double* __restrict__ rad_all, int rad_stride,
+             double* H_all, int32_t* __restrict__ status) {
   extern __shared__ double sm[];
   const SwartConst C;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = 3 * N;
-  double* xyz = sm;          // 3N
-  double* rad = xyz + 3 * N; // N
-  double* D = rad + N;       // N x N distances (clamped)
-  double* Sc = D + N * N;    // N x N screening, 0 on the diagonal
+  double* xyz = sm;           // 3N
+  double* rad = xyz + 3 * N;  // N
+  double* ID = rad + N;       // N x N
+  double* Sc = ID + N * N;    // N x N
+  double* qss = Sc + N * N + (size_t)wid * 3 * N;                               // this warp's queue: s_ij s_jk
+  int* qcode = (int*)(Sc + N * N + (size_t)SWP_WARPS * 3 * N) + (size_t)wid * 3 * N;  // (type << 8) | c
   __shared__ int s_bad;
   double* H = H_all + (size_t)b * n * n;
-  for (int i = tid; i < 3 * N; i += SW_THREADS) xyz[i] = xyz_all[(size_t)b * 3 * N + i];
-  for (int i = tid; i < N; i += SW_THREADS) rad[i] = rad_all[(size_t)b * rad_stride + i];
+  for (int i = tid; i < 3 * N; i += SWP_THREADS) xyz[i] = xyz_all[(size_t)b * 3 * N + i];
+  for (int i = tid; i < N; i += SWP_THREADS) rad[i] = rad_all[(size_t)b * rad_stride + i];
   if (tid == 0) s_bad = 0;
   __syncthreads();
-  for (int e = tid; e < N * N; e += SW_THREADS) {
-    const int i = e / N, j = e - i * N;
-    if (i > j) continue;
-    double d = 1.0, s = 0.0;
-    if (i != j) s = swart_screen(xyz, rad, i, j, &d);
-    D[i * N + j] = d; D[j * N + i] = d;
+  const int npair = N * (N - 1) / 2;
+  // pair t -> (a < bb): row a holds the pairs (a, a+1 .. N-1)
+  auto pair_of = [&](int t, int* pa, int* pb) {
+    int a = (int)((2.0 * N - 1.0 - sqrt((2.0 * N - 1.0) * (2.0 * N - 1.0) - 8.0 * t)) * 0.5);
+    while (a > 0 && a * (2 * N - a - 1) / 2 > t) --a;
+    while ((a + 1) * (2 * N - a - 2) / 2 <= t) ++a;
+    *pa = a;
+    *pb = a + 1 + (t - a * (2 * N - a - 1) / 2);
+  };
+  for (int t = tid; t < npair; t += SWP_THREADS) {
+    int i, j;
+    pair_of(t, &i, &j);
+    double d;
+    double s = swart_screen(xyz, rad, i, j, &d);
+    const double id = 1.0 / d;
+    if (!(d > 1e-8)) s = -s;  // bends skip degenerate distances (swart.py:226: l > 1e-8), stretches use |s|
+    ID[i * N + j] = id; ID[j * N + i] = id;
     Sc[i * N + j] = s; Sc[j * N + i] = s;
   }
+  for (int i = tid; i < N; i += SWP_THREADS) {
+    ID[i * N + i] = 1.0;
+    Sc[i * N + i] = 0.0;
+  }
   __syncthreads();
-  // a bend (i, j, k) exists iff both ends are neighbours of the centre and the product screen passes
-  auto pass = [&](int j, int i, int k, double* ss) -> bool {
-    const double si = Sc[j * N + i], sk = Sc[j * N + k];
-    if (!(si >= C.eps2 && sk >= C.eps2)) return false;
-    *ss = si * sk;
-    return *ss >= C.eps1 && D[i * N + j] > 1e-8 && D[k * N + j] > 1e-8;
-  };
   for (int round = 0; round < 2; ++round) {
     const bool bends = round == 0;
-    // ---- off-diagonal blocks (a < b): one thread each ----
-    for (int e = tid; e < N * N; e += SW_THREADS) {
-      const int a = e / N, bb = e - a * N;
-      if (a >= bb) continue;
-      double blk[9];
-      {
-        const double d = D[a * N + bb], s = Sc[a * N + bb], h = -0.35 * (s * s * s);
-        double ev[3];
-        for (int c = 0; c < 3; ++c) ev[c] = (xyz[3 * a + c] - xyz[3 * bb + c]) / d;
-        for (int p = 0; p < 3; ++p)
-          for (int q = 0; q < 3; ++q) blk[3 * p + q] = h * ev[p] * ev[q];
-      }
+    // ---- off-diagonal blocks: one warp per pair (a < bb), pairs dealt cyclically ----
+    for (int t = wid; t < npair; t += SWP_WARPS) {
+      int a, bb;
+      pair_of(t, &a, &bb);
+      const double* Sa = Sc + a * N;
+      const double* Sb = Sc + bb * N;
+      const double sab = Sa[bb];
+      int qn = 0;
       if (bends) {
-        SwartBend o;
-        double ss;
-        for (int c = 0; c < N; ++c) {
-          if (c == a || c == bb) continue;
-          if (pass(c, a, bb, &ss)) {  // centre c, ends a < b
-            swart_bend_eval(xyz, a, c, bb, D[a * N + c], D[bb * N + c], ss, o);
-            swart_acc(blk, o, 0, 6);
-          }
-          {  // centre a, ends b and c
-            const int i = bb < c ? bb : c, k = bb < c ? c : bb;
-            if (pass(a, i, k, &ss)) {
-              swart_bend_eval(xyz, i, a, k, D[i * N + a], D[k * N + a], ss, o);
-              swart_acc(blk, o, 3, bb == i ? 0 : 6);
-            }
-          }
-          {  // centre b, ends a and c
-            const int i = a < c ? a : c, k = a < c ? c : a;
-            if (pass(bb, i, k, &ss)) {
-              swart_bend_eval(xyz, i, bb, k, D[i * N + bb], D[k * N + bb], ss, o);
-              swart_acc(blk, o, a == i ? 0 : 6, 3);
-            }
-          }
+        // screen the 3 (N - 2) candidate bends, lanes over the third atom c:
+        //   type 0: centre c, ends (a, bb)   type 1: centre a, ends (bb, c)   type 2: centre bb, ends (a, c)
+        const bool ab_ok = sab >= C.eps2;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          const int c = c0 + lane;
+          const bool in = c < N && c != a && c != bb;
+          const double sa = in ? Sa[c] : 0.0, sb = in ? Sb[c] : 0.0;
+          const bool na = sa >= C.eps2, nb = sb >= C.eps2;
+          const double ss0 = sa * sb, ss1 = sab * sa, ss2 = sab * sb;
+          const bool p0 = na && nb && ss0 >= C.eps1;
+          const bool p1 = ab_ok && na && ss1 >= C.eps1;
+          const bool p2 = ab_ok && nb && ss2 >= C.eps1;
+          const unsigned lt = (1u << lane) - 1u;
+          unsigned m = __ballot_sync(MOP_FULL_MASK, p0);
+          if (p0) { const int q = qn + __popc(m & lt); qss[q] = ss0; qcode[q] = c; }
+          qn += __popc(m);
+          m = __ballot_sync(MOP_FULL_MASK, p1);
+          if (p1) { const int q = qn + __popc(m & lt); qss[q] = ss1; qcode[q] = 256 | c; }
+          qn += __popc(m);
+          m = __ballot_sync(MOP_FULL_MASK, p2);
+          if (p2) { const int q = qn + __popc(m & lt); qss[q] = ss2; qcode[q] = 512 | c; }
+          qn += __popc(m);
         }
+        __syncwarp();
       }
-      int bad = 0;
-      for (int p = 0; p < 3; ++p)
-        for (int q = 0; q < 3; ++q) {
-          const double x = blk[3 * p + q];
-          bad |= !isfinite(x);
-          H[(size_t)(3 * a + p) * n + 3 * bb + q] = x;
-          H[(size_t)(3 * bb + q) * n + 3 * a + p] = x;
-        }
-      if (bad) s_bad = 1;
-    }
-    // ---- diagonal blocks: one warp each, lanes split the third-atom loop ----
-    for (int a = wid; a < N; a += SW_WARPS) {
       double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int c = lane; c < N; c += 32) {
-        if (c == a) continue;
-        const double d = D[a * N + c], s = Sc[a * N + c], h = 0.35 * (s * s * s);
-        double ev[3];
-        for (int p = 0; p < 3; ++p) ev[p] = (xyz[3 * a + p] - xyz[3 * c + p]) / d;
-        for (int p = 0; p < 3; ++p)
-          for (int q = 0; q < 3; ++q) blk[3 * p + q] = fma(h * ev[p], ev[q], blk[3 * p + q]);
-        if (!bends) continue;
-        SwartBend o;
-        double ss;
-        for (int c2 = 0; c2 < N; ++c2) {
-          if (c2 == a || c2 == c) continue;
-          if (c2 > c && pass(a, c, c2, &ss)) {  // centre a, ends c < c2
-            swart_bend_eval(xyz, c, a, c2, D[c * N + a], D[c2 * N + a], ss, o);
-            swart_acc(blk, o, 3, 3);
-          }
-          {  // centre c, ends a and c2
-            const int i = a < c2 ? a : c2, k = a < c2 ? c2 : a;
-            if (pass(c, i, k, &ss)) {
-              swart_bend_eval(xyz, i, c, k, D[i * N + c], D[k * N + c], ss, o);
-              const int sa = a == i ? 0 : 6;
-              swart_acc(blk, o, sa, sa);
+      for (int q = lane; q < qn; q += 32) {
+        const int code = qcode[q], ty = code >> 8, c = code & 255;
+        const double ss = qss[q];
+        // centre j, ends (p, q2): the bend is symmetric in its ends, so the end that belongs to the block comes first
+        const int j = ty == 0 ? c : (ty == 1 ? a : bb);
+        const int p = ty == 1 ? bb : a;
+        const int q2 = ty == 0 ? bb : c;
+        const double il1 = ID[j * N + p], il2 = ID[j * N + q2];
+        double n1[3], n2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double xj = xyz[3 * j + k];
+          n1[k] = (xyz[3 * p + k] - xj) * il1;
+          n2[k] = (xyz[3 * q2 + k] - xj) * il2;
+        }
+        double cs = n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2];
+        cs = fmin(fmax(cs, -1.0), 1.0);
+        const double s2 = fmax(1e-12, 1.0 - cs * cs);
+        const double rs = fast_rsqrt(s2);
+        const double sn = s2 * rs;
+        const double iden = fmin(rs, 1e6);  // 1 / max(sn, 1e-6)
+        const double w = C.f + (1.0 - C.f) * sn;
+        const double hb = 0.075 * (ss * ss) * (w * w);
+        // Wilson vectors as  U1 = c1 bn + c2 t / l,  U2 = c3 vn / l  (swart.py:226-315):
+        //   regular bend: c1 = 1;  near 180 degrees: c1 = 1 - sl;  near 0 degrees (cos > 0.8): the linear-bend pair
+        //   c1 = 1 - sl, c2 = sl with t = unit((v1 - v2) x vn), c3 = 1 with vn = unit(v1 x v2)
+        double c1 = 1.0, c2 = 0.0, c3 = 0.0;
+        double tv[3] = {0.0, 0.0, 0.0}, vn[3] = {0.0, 0.0, 0.0};
+        const bool lin = cs > 1.0 - C.tolth;
+        const double th1 = lin ? 1.0 - cs : 1.0 + cs;
+        if (th1 < C.tolth) {
+          const double qq = th1 / C.tolth;
+          const double sl = (1.0 - qq * qq) * (1.0 - qq * qq);
+          c1 = 1.0 - sl;
+          if (lin) {
+            c2 = sl;
+            c3 = 1.0;
+            // v1 x v2 = l1 l2 (n1 x n2); only the direction enters unless it is degenerate (< 1e-12)
+            vn[0] = n1[1] * n2[2] - n1[2] * n2[1];
+            vn[1] = n1[2] * n2[0] - n1[0] * n2[2];
+            vn[2] = n1[0] * n2[1] - n1[1] * n2[0];
+            double nv2 = vn[0] * vn[0] + vn[1] * vn[1] + vn[2] * vn[2];
+            const double lim = 1e-12 * il1 * il2;
+            if (nv2 < lim * lim) {  // exactly collinear: perpendicular to the lower-index end (swart.py:150-165)
+              const double* nf = p < q2 ? n1 : n2;
+              vn[0] = 1.0 - nf[0] * nf[0]; vn[1] = -nf[0] * nf[1]; vn[2] = -nf[0] * nf[2];
+              nv2 = vn[0] * vn[0] + vn[1] * vn[1] + vn[2] * vn[2];
+              if (!(nv2 >= 1e-24)) {
+                vn[0] = -nf[1] * nf[0]; vn[1] = 1.0 - nf[1] * nf[1]; vn[2] = -nf[1] * nf[2];
+                nv2 = fmax(vn[0] * vn[0] + vn[1] * vn[1] + vn[2] * vn[2], 1e-24);
+              }
             }
+            const double rv = fast_rsqrt(nv2);
+            vn[0] *= rv; vn[1] *= rv; vn[2] *= rv;
+            // v1 - v2 is proportional to n1 il2 - n2 il1
+            const double vd[3] = {n1[0] * il2 - n2[0] * il1, n1[1] * il2 - n2[1] * il1, n1[2] * il2 - n2[2] * il1};
+            tv[0] = vd[1] * vn[2] - vd[2] * vn[1];
+            tv[1] = vd[2] * vn[0] - vd[0] * vn[2];
+            tv[2] = vd[0] * vn[1] - vd[1] * vn[0];
+            const double rt = fast_rsqrt(fmax(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2], 1e-300));
+            tv[0] *= rt; tv[1] *= rt; tv[2] *= rt;
           }
         }
+        const double f1 = c1 * il1 * iden, f2 = c1 * il2 * iden, g1 = c2 * il1, g2 = c2 * il2, h1 = c3 * il1, h2 = c3 * il2;
+        double ua[3], ub[3], wa[3], wb[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double up = fma(g1, tv[k], (cs * n1[k] - n2[k]) * f1);
+          const double uq = fma(g2, tv[k], (cs * n2[k] - n1[k]) * f2);
+          const double uj = -(up + uq);
+          ua[k] = ty == 1 ? uj : up;
+          ub[k] = ty == 0 ? uq : (ty == 1 ? up : uj);
+          const double wp = vn[k] * h1, wq = vn[k] * h2, wj = -(wp + wq);
+          wa[k] = ty == 1 ? wj : wp;
+          wb[k] = ty == 0 ? wq : (ty == 1 ? wp : wj);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double hp = hb * ua[k], hw = hb * wa[k];
+#pragma unroll
+          for (int m = 0; m < 3; ++m) blk[3 * k + m] = fma(hw, wb[m], fma(hp, ub[m], blk[3 * k + m]));
+        }
       }
-      int bad = 0;
-      for (int p = 0; p < 9; ++p) {
-        blk[p] = warp_sum(blk[p]);
-        bad |= !isfinite(blk[p]);
+      if (qn > 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) blk[k] = warp_sum(blk[k]);
       }
-      if (lane < 9) H[(size_t)(3 * a + lane / 3) * n + 3 * a + lane % 3] = blk[lane];
-      if (bad && lane == 0) s_bad = 1;
+      if (lane < 9) {
+        const int pp = lane / 3, qq = lane - 3 * pp;
+        const double sabs = fabs(sab), h = -0.35 * (sabs * sabs * sabs), id = ID[a * N + bb];
+        const double ep = (xyz[3 * a + pp] - xyz[3 * bb + pp]) * id, eq = (xyz[3 * a + qq] - xyz[3 * bb + qq]) * id;
+        double x = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          if (k == lane) x = blk[k];
+        x = fma(h * ep, eq, x);
+        if (!isfinite(x)) s_bad = 1;
+        H[(size_t)(3 * a + pp) * n + 3 * bb + qq] = x;
+        H[(size_t)(3 * bb + qq) * n + 3 * a + pp] = x;
+      }
+      __syncwarp();
     }
     __syncthreads();
     if (!s_bad || !bends) break;  // non-finite: redo with the stretch terms only (swart.py:340-350)
+    __syncthreads();
+  }
+  // diagonal blocks from translational invariance, fixed summation order
+  for (int e = tid; e < 3 * n; e += SWP_THREADS) {
+    const int r = e / 3, q = e - 3 * r, a = r / 3;
+    const double* row = H + (size_t)r * n + q;
+    double acc = 0.0;
+    for (int c = 0; c < N; ++c)
+      if (c != a) acc += row[3 * c];
+    H[(size_t)r * n + 3 * a + q] = -acc;
   }
   if (tid == 0 && status) status[b] = s_bad;
 }
@@ -473,9 +488,9 @@ extern "C" int mop_swart_hessian(int B, int natoms, const double* xyz, const dou
   }
   cudaStream_t stream = (cudaStream_t)stream_;
   if (natoms <= 100) {  // gather kernel: no atomics
-    const size_t smem = sizeof(double) * (4 * (size_t)natoms + 2 * (size_t)natoms * natoms);
-    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_swart_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mop::k_swart_gather<<<B, mop::SW_THREADS, smem, stream>>>(natoms, xyz, radii, radii_stride, Hraw, status);
+    const size_t smem = mop::swp_smem_bytes(natoms);
+    MOP_CHECK_CUDA(cudaFuncSetAttribute(mop::k_swart_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mop::k_swart_pair<<<B, mop::SWP_THREADS, smem, stream>>>(natoms, xyz, radii, radii_stride, Hraw, status);
     MOP_CHECK_CUDA(cudaGetLastError());
     return mop_launch_project_trrot(B, 3 * natoms, Hraw, nullptr, xyz, nullptr, H_out, nullptr, nullptr, 0, stream);
   }

@@ -31,4 +31,20 @@ terms = [(ops.BIAS_KEEP, [0], [5], 0.4, 2.1), (ops.BIAS_KEEP_ANGLE, [1, 0, 2], [
          (ops.BIAS_KEEP_DIHEDRAL, [1, 0, 4, 5], [], 0.3, 1.0), (ops.BIAS_WELL, [0, 1, 2], [8, 9, 10], 0.01, 0.0, [1.0, 2.0, 9.0, 10.0])]
 ops.bias_terms(x4d, ops.pack_bias_terms(terms, dev), len(terms))
 torch.cuda.synchronize()
+if os.environ.get("TIME"):   # CUDA-event medians per call (ms), host wrapper included
+    def ms(f, reps=7):
+        f(); torch.cuda.synchronize(); ts = []
+        for _ in range(reps):
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); f(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+    sr = T(np.array(swart_radii(elems))); fr = T(np.array(radii_array(elems))); dp = d3_atom_params(elems); lp = lindh_atom_params(el4)
+    gam = torch.full((B4,), 100.0, dtype=torch.float64, device=dev)
+    x24 = x4d[:1024].contiguous()
+    kd = torch.rand(1024, N4 * (N4 - 1) // 2, dtype=torch.float64, device=dev)
+    print(f"swart 1024xN50        {ms(lambda: ops.swart_hessian(xd, sr)):8.3f} ms")
+    print(f"fischer 1024xN50      {ms(lambda: ops.fischer_hessian(xd, fr)):8.3f} ms")
+    print(f"fischerd3old 1024xN50 {ms(lambda: ops.fischer_d3old_hessian(xd, dp)):8.3f} ms")
+    print(f"lindh 8192xN24        {ms(lambda: ops.lindh_hessian(x4d, lp)):8.3f} ms")
+    print(f"afir 8192xN24         {ms(lambda: ops.afir(x4d, f1, f2, rad, gam)):8.3f} ms")
 print("ok")

@@ -15,6 +15,18 @@ mv0 = out["move"].cpu().numpy()
 x1 = np.empty_like(x0); g1 = np.empty_like(g0)
 for b in range(B):
     x1[b], g1[b] = synthetic.second_point(x0[b], H0[b], g0[b], mv0[b], rngs[b])
+dbg = None
+if os.environ.get("SP_PHASES"):   # phase clocks of k_spectrum_step (cycles per structure)
+    from multioptpy_b200 import _lib
+    dbg = torch.zeros(B, 16, dtype=torch.int64, device=dev)
+    _lib.load().mop_priv_spectrum_timing(dbg.data_ptr())
 out = ops.rsirfo_step(H, T(x1), T(g1), T(g1), st, method=m, x_prev=T(x0), g_prev=T(g0), Be=zero - 1e-3)
 torch.cuda.synchronize()
+if dbg is not None:
+    _lib.load().mop_priv_spectrum_timing(0)
+    d = dbg.cpu().numpy().astype(float)
+    names = ["load/scale/split", "eigenvalues", "twisted vectors", "cluster CGS2", "gamma + rfo_core", "y = Z c", "Q y"]
+    print("mean cycles per structure", d[:, :7].sum(1).mean())
+    for q, nm in enumerate(names):
+        print(f"  {nm:20s} mean {d[:, q].mean():10.0f}  p50 {np.median(d[:, q]):10.0f}  max {d[:, q].max():10.0f}")
 print("ok", int(out["status"].sum().item()))
