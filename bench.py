@@ -272,59 +272,26 @@ def run_b200(args, rank, world, local_rank):
         ms = float(t.item())
     value = world * B * K / (ms * 1e-3)
 
-    # ---- e2e: host buffers -> C ABI -> host buffers, copies inside the timed region ----
-    # chunk sizes: whole waves of the packed tridiagonalisation (2 CTAs x 148 SMs = 296 structures), the
-    # short chunk first so that compute starts early (MOP_BENCH_E2E_SPLIT overrides, comma separated)
+    # ---- e2e: host buffers -> public host-buffer API (multioptpy_b200.host_pipeline.HostStepPipeline: chunked
+    # cudaMemcpyAsync + mop_rsirfo_step_packed_begin per chunk, mop_rsirfo_step_packed_finish once) -> host buffers;
+    # every copy is inside the timed region (MOP_BENCH_E2E_SPLIT / _STREAMS override the chunking)
+    from multioptpy_b200.host_pipeline import HostStepPipeline, pack_lower_host
     split_env = os.environ.get("MOP_BENCH_E2E_SPLIT", "")
-    if split_env:
-        sizes = [int(v) for v in split_env.split(",")]
-    else:
-        sizes = [B % 296] * (1 if B % 296 else 0) + [296] * (B // 296)
-    assert sum(sizes) == B and all(v > 0 for v in sizes)
-    bounds = np.concatenate([[0], np.cumsum(sizes)])
-    nchunk = len(sizes)
-    nstream = min(nchunk, int(os.environ.get("MOP_BENCH_E2E_STREAMS", "4")))
-    cb = max(sizes)
+    sizes = [int(v) for v in split_env.split(",")] if split_env else None
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    ntri = n * (n + 1) // 2
-    il = np.tril_indices(n)
-    hH = pin(H0[:, il[0], il[1]])                    # packed lower triangles, row i at i (i + 1) / 2
+    hH = pin(pack_lower_host(H0))                    # packed lower triangles, row i at i (i + 1) / 2
     hx1, hg1, hx0, hg0 = pin(x1), pin(g1), pin(x0), pin(g0)
     hBe = pin(np.full(B, -1e-3)); hst = state1.cpu().pin_memory()
     h_move = torch.empty(B, n, dtype=f64).pin_memory()
     h_stat = torch.empty(B, dtype=torch.int32).pin_memory()
-    # earlier chunks get the higher stream priority: their CTAs are scheduled first, so the chunks finish
-    # (and their results go back over PCIe) one after the other instead of all together at the end
-    prio = os.environ.get("MOP_BENCH_E2E_PRIO", "1") == "1"
-    streams = [torch.cuda.Stream(dev, priority=(-min(5, nstream - 1 - i) if prio else 0)) for i in range(nstream)]
-    # device-side Hessian storage of the e2e path: one packed slab per chunk (stays resident after the step)
-    dHp = torch.empty(B, ntri, dtype=f64, device=dev)
-    dbuf = [dict(x1=torch.empty(cb, n, dtype=f64, device=dev),
-                 g1=torch.empty(cb, n, dtype=f64, device=dev), x0=torch.empty(cb, n, dtype=f64, device=dev),
-                 g0=torch.empty(cb, n, dtype=f64, device=dev), Be=torch.empty(cb, dtype=f64, device=dev),
-                 st=torch.empty(cb, ops.RSIRFO_STATE, dtype=f64, device=dev), outs={}) for _ in range(nstream)]
-    h2d = (hH.numel() + hx1.numel() * 4 + hBe.numel() + hst.numel()) * 8
+    pipe = HostStepPipeline(B, n, method_id, device=dev, chunks=sizes,
+                            nstream=int(os.environ.get("MOP_BENCH_E2E_STREAMS", "4")))
+    sizes = [int(v) for v in np.diff(pipe.bounds)]
+    nstream = len(pipe.streams)
     d2h = h_move.numel() * 8 + h_stat.numel() * 4
 
     def e2e_step():
-        for c in range(nchunk):
-            s = streams[c % nstream]; d = dbuf[c % nstream]
-            lo, hi = int(bounds[c]), int(bounds[c + 1]); m = hi - lo; sl = slice(lo, hi)
-            with torch.cuda.stream(s):
-                dH, dx1, dg1, dx0, dg0 = dHp[sl], d["x1"][:m], d["g1"][:m], d["x0"][:m], d["g0"][:m]
-                dBe, dst = d["Be"][:m], d["st"][:m]
-                # vectors first: they ride behind the previous chunk's Hessian copy instead of delaying this chunk
-                dx1.copy_(hx1[sl], non_blocking=True); dg1.copy_(hg1[sl], non_blocking=True)
-                dx0.copy_(hx0[sl], non_blocking=True); dg0.copy_(hg0[sl], non_blocking=True)
-                dBe.copy_(hBe[sl], non_blocking=True); dst.copy_(hst[sl], non_blocking=True)
-                dH.copy_(hH[sl], non_blocking=True)
-                o = ops.rsirfo_step(dH, dx1, dg1, dg1, dst, method=method_id, x_prev=dx0, g_prev=dg0, Be=dBe,
-                                    out=d["outs"].get(m), packed=True)
-                d["outs"][m] = o
-                h_move[sl].copy_(o["move"], non_blocking=True)
-                h_stat[sl].copy_(o["status"], non_blocking=True)
-        for s in streams:
-            s.synchronize()
+        pipe.step(hx1, hg1, hg1, hst, h_move, h_stat, hH=hH, hx_prev=hx0, hg_prev=hg0, hBe=hBe)
 
     for _ in range(2):
         e2e_step()
@@ -344,7 +311,8 @@ def run_b200(args, rank, world, local_rank):
     ref_mv = out["move"].cpu().numpy()
     e2e_diff = float(np.max(np.linalg.norm(h_move.numpy() - ref_mv, axis=1) / np.linalg.norm(ref_mv, axis=1)))
     # lazy read-back of the updated Hessians (once, outside the timed loop): must equal the resident path's
-    H_e2e = ops.unpack_lower(dHp, n)
+    H_e2e = pipe.hessians()
+    h2d = pipe.h2d_bytes
     H_res = Hs[(W + K - 1) % ncopy]
     e2e_hdiff = float(((H_e2e - H_res).flatten(1).norm(dim=1) / H_res.flatten(1).norm(dim=1)).max())
     e2e_ok = bool(np.isfinite(h_move.numpy()).all() and e2e_diff < 1e-12 and e2e_hdiff < 1e-12)
@@ -436,9 +404,11 @@ def run_b200(args, rank, world, local_rank):
             "parity_vs_oracle": worst, "eigh": "auto",
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": f"pinned host buffers through mop_rsirfo_step_packed: Hessian batch in as packed lower triangles "
-                            f"every step, moves + status out; updated Hessians stay on the device (read back once after "
-                            f"the loop for the check); chunks of {sizes} structures on {nstream} streams",
+                    "note": f"pinned host buffers through multioptpy_b200.host_pipeline.HostStepPipeline.step: Hessian batch in as "
+                            f"packed lower triangles every step (chunks of {sizes} structures on {nstream} streams, "
+                            f"mop_rsirfo_step_packed_begin per chunk while the next chunk is in flight, "
+                            f"mop_rsirfo_step_packed_finish once), moves + status out; updated Hessians stay on the device "
+                            f"(read back once after the loop for the check)",
                     "matches_resident_path": e2e_ok, "max_rel_diff_vs_resident": e2e_diff,
                     "hessian_max_rel_diff_vs_resident": e2e_hdiff},
             "e2e_hessian_resident": {"value": e2e_res_val, "unit": UNIT,

@@ -169,6 +169,21 @@ int mop_rsirfo_step_packed(int B, int n, int method, int saddle_order, int neb_m
                            const double* Bg, const double* g, const double* x_prev, const double* g_prev,
                            const double* Be, double* state, double* move_out, double* eigvals_out, double* pred_out,
                            int32_t* status, void* work, size_t work_bytes, void* stream);
+/* The packed step as TWO calls, for a batch that streams in from host memory chunk by chunk (the host-buffer
+ * pipeline multioptpy_b200/host_pipeline.py; RSIRFO.run of Optimizer/rsirfo.py:285-490 for every structure).
+ * All pointers address the whole batch of B structures.  _begin: Hessian update, write-back, TR/ROT projection and
+ * tridiagonalisation of structures [b0, b0 + bc) - one call per chunk, each on the stream that carried the chunk's
+ * copies.  _finish: spectrum, eigenvectors, RS-I-RFO step and the robust fallbacks of all B, on a stream that waits
+ * for every _begin.  Same workspace (mop_rsirfo_workspace_bytes(B, n, MOP_EIGH_TRIDIAG)) for all calls of a step;
+ * results identical to mop_rsirfo_step_packed. */
+int mop_rsirfo_step_packed_begin(int B, int b0, int bc, int n, int method, double* H_packed, const double* Hbias_packed,
+                                 const double* x, const double* Bg, const double* g, const double* x_prev,
+                                 const double* g_prev, double* state, int32_t* status, void* work, size_t work_bytes,
+                                 void* stream);
+int mop_rsirfo_step_packed_finish(int B, int n, int saddle_order, int neb_mode, double trust_min, double trust_max,
+                                  double* H_packed, const double* Hbias_packed, const double* x, const double* Bg,
+                                  const double* Be, double* state, double* move_out, double* eigvals_out,
+                                  double* pred_out, int32_t* status, void* work, size_t work_bytes, void* stream);
 /* The same step for a batch whose structures use DIFFERENT update methods, method_per [B] int32 on the device
  * (a NEB chain: rsirfo_block_fsb at the ends, rsirfo_block_bofill inside, Optimizer/rfo_neb.py:116-121). */
 int mop_rsirfo_step_mixed(int B, int n, const int32_t* method_per, int saddle_order, int neb_mode, double trust_min,
@@ -392,6 +407,13 @@ int mop_neb_ayala(int nimg, int first, int nloc, int n, const double* x_halo, co
                   const double* g_halo, const double* tau, double* H, double* gamma_out, void* stream);
 int mop_neb_limit_tr(int nimg, int first, int nloc, int n, int fix_init_edge, int fix_end_edge,
                      int apply_step_limit, const double* x_halo, const double* g, double* delta, void* stream);
+/* Image redistribution at equal arc length: distribute_geometry (Interpolation/linear_interpolation.py:308-336) on
+ * the path lengths of calc_path_length_list (Utils/calc_tools.py:853-862) - the `align_distances` strategy of
+ * NEB._align_geometries (neb.py:649-760).  x_chain [nimg][natoms][3] is the WHOLE chain (a sharded chain is
+ * all-gathered first: neb_halo.gather_chain), x_out [nloc][natoms][3] receives the new images first .. first+nloc-1,
+ * path_length_out [nimg] (or null) the running path length.  x_out must not alias x_chain. */
+int mop_neb_redistribute(int nimg, int natoms, int first, int nloc, const double* x_chain, double* x_out,
+                         double* path_length_out, void* stream);
 /* FIRE optimizer of the NEB driver (Optimizer/fire_neb.py:38-92).  mop_neb_fire_blend: per-atom velocity / force
  * blend vneb_out [nloc][natoms][3] and the power sum v_prev . F accumulated into the device scalar power_accum
  * (zeroed by the caller, all-reduced over ranks when the chain is sharded; prev_velocity = NULL on the first

@@ -79,6 +79,19 @@ class RFOOptimizer:
         move = torch.where(self.end_mask[:, None], -rfo, (1.0 - r) * fire_move - r * rfo)
         return move, vnew
 
+    def align_geometries(self, x, optimize_num, align_distances=0, **other_strategies):
+        """NEB._align_geometries (neb.py:649-760) for this rank's images x (nloc, n): every `align_distances`
+        iterations the chain is redistributed at equal arc length (one all-gather of the chain + one kernel).  The
+        other strategies of the reference's table are not built: a non-zero interval for one of them raises."""
+        on = [k for k, v in other_strategies.items() if v]
+        if on:
+            raise ops.MopError(f"NEB alignment strategies {on} are not implemented on the device (only align_distances)")
+        if optimize_num <= 0 or align_distances < 1 or optimize_num % align_distances != 0:
+            return x
+        from ..Interpolation.linear_interpolation import distribute_geometry_sharded
+        xg = x.reshape(self.nloc, self.natoms, 3).contiguous()
+        return distribute_geometry_sharded(xg, self.nimg, self.first).reshape(self.nloc, self.n)
+
     def time_halo(self, x, E, g, reps=10):
         """Device time of the halo exchange alone (ms, median-free mean over reps)."""
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -37,6 +37,8 @@ SIGNATURES = {
                              _p, _p, _p, _p, _sz, _p]),
     "mop_rsirfo_step_packed": (_i, [_i, _i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                     _p, _sz, _p]),
+    "mop_rsirfo_step_packed_begin": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mop_rsirfo_step_packed_finish": (_i, [_i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mop_rsirfo_step_mixed": (_i, [_i, _i, _p, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _sz, _p]),
     "mop_pack_lower": (_i, [_i, _i, _p, _p, _p]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "mop_bneb_force": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mop_neb_ayala": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "mop_neb_limit_tr": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mop_neb_redistribute": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "mop_neb_fire_blend": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p]),
     "mop_neb_fire_advance": (_i, [_i, _i, _d, _i, _p, _p, _p, _p, _p, _p]),
     "mop_outer_trust_radius": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _p]),

@@ -248,11 +248,17 @@ extern "C" int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_
 // projects gradient and effective Hessian (rsirfo.py:337,349-358) and tridiagonalises on the triangle in shared
 // memory - the projected Hessian never exists in HBM; the spectrum kernel finishes the step.  packed: H / Hbias are
 // packed lower triangles.  Hp, gp, rest: the workspace carve of mop_rsirfo_step (status already zeroed).
+// phase & 1: front end + tridiagonalisation of structures [b0, b0 + bc); phase & 2: spectrum, step and fallbacks of all B
+// (mop_rsirfo_step_packed_begin / _finish run the two phases as separate calls: chunks of a batch that arrives from the
+// host are reduced while the next chunk is still in flight, the spectrum kernel then runs once with the whole batch
+// resident - it needs seven CTAs per SM to hide its dependent chains and cannot share an SM with the reduction).
 static int rsirfo_step_fused(int B, int n, int method, const int32_t* method_per, int saddle_order, int neb_mode, double trust_min,
                              double trust_max, int packed, double* H, const double* Hbias, const double* x,
                              const double* Bg, const double* g, const double* x_prev, const double* g_prev,
                              const double* Be, double* state, double* move_out, double* eigvals_out, double* pred_out,
-                             int32_t* status, double* Hp, double* gp, char* rest, cudaStream_t stream) {
+                             int32_t* status, double* Hp, double* gp, char* rest, cudaStream_t stream, int phase = 3,
+                             int b0 = 0, int bc = -1) {
+  if (bc < 0) bc = B;
   const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
   const size_t nv = align256(sizeof(double) * (size_t)B * n);
   const size_t jac = align256(mop_jacobi_workspace_bytes(B, n));
@@ -268,10 +274,17 @@ static int rsirfo_step_fused(int B, int n, int method, const int32_t* method_per
   double* pt = pd + 2 * bn;
   double* pg = pd + 3 * bn;
   int* pflag = (int*)(pd + 4 * bn);
-  int rc = mop_launch_front_tridiag_blk(B, n, x_prev ? method : MOP_UPD_NONE, x_prev ? method_per : nullptr, 1, 0, packed, H, Hbias, x, x_prev, g,
-                                        g_prev, Bg, state, MOP_RSIRFO_STATE, gp, status, Vh, pd, pe, pt, pg, pflag,
-                                        stream);
-  if (rc != MOP_OK) return rc;
+  int rc = MOP_OK;
+  if (phase & 1) {
+    const size_t hs = packed ? (size_t)n * (n + 1) / 2 : (size_t)n * n, o = (size_t)b0, on = o * n;
+    rc = mop_launch_front_tridiag_blk(bc, n, x_prev ? method : MOP_UPD_NONE, (x_prev && method_per) ? method_per + o : nullptr, 1,
+                                      0, packed, H + o * hs, Hbias ? Hbias + o * hs : nullptr, x + on,
+                                      x_prev ? x_prev + on : nullptr, g + on, g_prev ? g_prev + on : nullptr, Bg + on,
+                                      state + o * MOP_RSIRFO_STATE, MOP_RSIRFO_STATE, gp + on, status + o,
+                                      Vh + o * n * n, pd + on, pe + on, pt + on, pg + on, pflag + o, stream);
+    if (rc != MOP_OK) return rc;
+  }
+  if (!(phase & 2)) return MOP_OK;
   rc = mop_launch_spectrum_step(B, n, saddle_order, neb_mode, trust_min, trust_max, Vh, zbuf, Dm, pd, pe, pt, pg, pflag,
                                 Bg, Be, state, move_out, eigvals_out, pred_out, status, stream);
   if (rc != MOP_OK) return rc;
@@ -446,6 +459,63 @@ extern "C" int mop_rsirfo_step_packed(int B, int n, int method, int saddle_order
   return rsirfo_step_fused(B, n, method, nullptr, saddle_order, neb_mode, trust_min, trust_max, 1, H_packed, Hbias_packed, x, Bg,
                            g, x_prev, g_prev, Be, state, move_out, eigvals_out, pred_out, status, (double*)w,
                            (double*)(w + nn), w + nn + nv, stream);
+}
+
+// The packed step in two calls, for a batch that is streamed in from the host chunk by chunk (see rsirfo_step_fused).
+// Every pointer addresses the WHOLE batch of B structures; _begin works on structures [b0, b0 + bc) only and may be
+// issued on a stream of its own per chunk, _finish follows once on a stream that waits for all of them.
+static int packed_args_ok(const char* who, int B, int n, int saddle_order, const void* H, const void* x, const void* Bg,
+                          const void* g, const void* state, const void* status, const void* work, const void* x_prev,
+                          const void* g_prev, size_t work_bytes) {
+  if (!(B >= 0 && n > 0 && n % 3 == 0)) { mop_set_error("%s: n must be a positive multiple of 3", who); return MOP_ERR_INVALID; }
+  if (!(H && x && Bg && g && state && status && work)) { mop_set_error("%s: null device pointer", who); return MOP_ERR_INVALID; }
+  if (!(saddle_order >= 0 && saddle_order < n)) { mop_set_error("%s: bad saddle_order", who); return MOP_ERR_INVALID; }
+  if ((x_prev == nullptr) != (g_prev == nullptr)) { mop_set_error("%s: x_prev and g_prev must both be given or both be NULL", who); return MOP_ERR_INVALID; }
+  if (B > 0 && (!mop_spectrum_step_supported(n) || !mop_tridiag_supported(n))) {
+    mop_set_error("%s: n = %d is outside the shared-memory path (3 .. 160)", who, n);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  if (work_bytes < mop_rsirfo_workspace_bytes(B, n, MOP_EIGH_TRIDIAG)) {
+    mop_set_error("%s: workspace too small (%zu < %zu bytes)", who, work_bytes, mop_rsirfo_workspace_bytes(B, n, MOP_EIGH_TRIDIAG));
+    return MOP_ERR_WORKSPACE;
+  }
+  return MOP_OK;
+}
+
+extern "C" int mop_rsirfo_step_packed_begin(int B, int b0, int bc, int n, int method, double* H_packed,
+                                            const double* Hbias_packed, const double* x, const double* Bg, const double* g,
+                                            const double* x_prev, const double* g_prev, double* state, int32_t* status,
+                                            void* work, size_t work_bytes, void* stream_) {
+  int rc = packed_args_ok("mop_rsirfo_step_packed_begin", B, n, 0, H_packed, x, Bg, g, state, status, work, x_prev, g_prev, work_bytes);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(b0 >= 0 && bc >= 0 && b0 + bc <= B, "mop_rsirfo_step_packed_begin: chunk outside the batch");
+  if (bc == 0) return MOP_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  char* w = (char*)work;
+  MOP_CHECK_CUDA(cudaMemsetAsync(status + b0, 0, sizeof(int32_t) * (size_t)bc, stream));
+  return rsirfo_step_fused(B, n, method, nullptr, 0, 0, 0.0, 0.0, 1, H_packed, Hbias_packed, x, Bg, g, x_prev, g_prev, nullptr,
+                           state, nullptr, nullptr, nullptr, status, (double*)w, (double*)(w + nn), w + nn + nv, stream, 1, b0,
+                           bc);
+}
+
+extern "C" int mop_rsirfo_step_packed_finish(int B, int n, int saddle_order, int neb_mode, double trust_min,
+                                             double trust_max, double* H_packed, const double* Hbias_packed, const double* x,
+                                             const double* Bg, const double* Be, double* state, double* move_out,
+                                             double* eigvals_out, double* pred_out, int32_t* status, void* work,
+                                             size_t work_bytes, void* stream_) {
+  int rc = packed_args_ok("mop_rsirfo_step_packed_finish", B, n, saddle_order, H_packed, x, Bg, Bg, state, status, work, nullptr,
+                          nullptr, work_bytes);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(move_out, "mop_rsirfo_step_packed_finish: move_out required");
+  if (B == 0) return MOP_OK;
+  const size_t nn = align256(sizeof(double) * (size_t)B * n * n);
+  const size_t nv = align256(sizeof(double) * (size_t)B * n);
+  char* w = (char*)work;
+  return rsirfo_step_fused(B, n, MOP_UPD_NONE, nullptr, saddle_order, neb_mode, trust_min, trust_max, 1, H_packed, Hbias_packed,
+                           x, Bg, nullptr, nullptr, nullptr, Be, state, move_out, eigvals_out, pred_out, status, (double*)w,
+                           (double*)(w + nn), w + nn + nv, (cudaStream_t)stream_, 2);
 }
 
 // RSIRFO.run for a batch whose structures use DIFFERENT update methods (method_per [B], device): a NEB chain runs

@@ -288,6 +288,76 @@ __global__ void __launch_bounds__(256) k_neb_fire_advance(size_t total, double d
   }
 }
 
+// Image redistribution at equal arc length (Interpolation/linear_interpolation.py:308-336 distribute_geometry with
+// Utils/calc_tools.py:853-862 calc_path_length_list; the `align_distances` strategy of NEB._align_geometries,
+// neb.py:649-760).  One CTA for the whole chain: warp per segment for the centroid-free segment lengths, thread 0 for
+// the running path length (the reference's own summation order), warp per output image for the segment search
+// (first j with s_j <= i L / (M - 1) <= s_j+1) and the linear interpolation.  Writes images [first, first + nloc).
+__global__ void __launch_bounds__(256) k_neb_redistribute(int nimg, int natoms, int first, int nloc,
+                                                          const double* __restrict__ x, double* __restrict__ xout,
+                                                          double* __restrict__ plen_out) {
+  extern __shared__ double pl[];  // nimg running path lengths
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int n = 3 * natoms;
+  for (int i = wid; i < nimg - 1; i += nw) {
+    const double* xi = x + (size_t)i * n;
+    const double* xj = xi + n;
+    double si[3] = {0, 0, 0}, sj[3] = {0, 0, 0};
+    for (int a = lane; a < natoms; a += 32)
+      for (int c = 0; c < 3; ++c) {
+        si[c] += xi[3 * a + c];
+        sj[c] += xj[3 * a + c];
+      }
+    for (int c = 0; c < 3; ++c) {
+      si[c] = warp_sum(si[c]) / natoms;
+      sj[c] = warp_sum(sj[c]) / natoms;
+    }
+    double q = 0.0;
+    for (int a = lane; a < natoms; a += 32)
+      for (int c = 0; c < 3; ++c) {
+        const double d = (xj[3 * a + c] - sj[c]) - (xi[3 * a + c] - si[c]);
+        q = fma(d, d, q);
+      }
+    q = warp_sum(q);
+    if (lane == 0) pl[i + 1] = sqrt(q);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    pl[0] = 0.0;
+    for (int i = 1; i < nimg; ++i) pl[i] = pl[i - 1] + pl[i];
+  }
+  __syncthreads();
+  if (plen_out)
+    for (int i = tid; i < nimg; i += blockDim.x) plen_out[i] = pl[i];
+  const double total = pl[nimg - 1];
+  const double node_dist = total / (nimg - 1);
+  for (int i = first + wid; i < first + nloc; i += nw) {
+    double* o = xout + (size_t)(i - first) * n;
+    int j = -1;       // source segment; -1: copy image `src`
+    int src = i;
+    if (!(total < 1e-8) && i > 0 && i < nimg - 1) {
+      const double dist = i * node_dist;
+      src = nimg - 1;  // "not found" safeguard of the reference
+      for (int j0 = 0; j0 < nimg - 1 && j < 0; j0 += 32) {
+        const int jj = j0 + lane;
+        const bool hit = jj < nimg - 1 && pl[jj] <= dist && dist <= pl[jj + 1];
+        const unsigned m = __ballot_sync(MOP_FULL_MASK, hit);
+        if (m) j = j0 + __ffs(m) - 1;
+      }
+      if (j >= 0) {
+        const double dt = (dist - pl[j]) / (pl[j + 1] - pl[j]);
+        const double* xa = x + (size_t)j * n;
+        const double* xb = xa + n;
+        for (int e = lane; e < n; e += 32) o[e] = xa[e] + (xb[e] - xa[e]) * dt;
+      }
+    }
+    if (j < 0) {
+      const double* xs = x + (size_t)src * n;
+      for (int e = lane; e < n; e += 32) o[e] = xs[e];
+    }
+  }
+}
+
 }  // namespace mop
 
 extern "C" int mop_bneb_force(int nimg, int first, int nloc, int n, const double* x_halo,
@@ -351,6 +421,18 @@ extern "C" int mop_neb_fire_advance(int nloc, int n, double dt, int reset, const
   const int grid = (int)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184);
   mop::k_neb_fire_advance<<<grid, 256, 0, (cudaStream_t)stream>>>(tot, dt, reset, vneb, force, prev_velocity,
                                                                  velocity_out, delta_out);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+extern "C" int mop_neb_redistribute(int nimg, int natoms, int first, int nloc, const double* x_chain, double* x_out,
+                                    double* path_length_out, void* stream) {
+  MOP_REQUIRE(nimg >= 2 && natoms > 0 && nloc >= 0 && first >= 0 && first + nloc <= nimg,
+              "mop_neb_redistribute: bad image range or natoms");
+  MOP_REQUIRE(x_chain && x_out && x_chain != x_out, "mop_neb_redistribute: x_chain and a distinct x_out required");
+  MOP_REQUIRE(nimg <= 16384, "mop_neb_redistribute: at most 16384 images");
+  mop::k_neb_redistribute<<<1, 256, sizeof(double) * (size_t)nimg, (cudaStream_t)stream>>>(nimg, natoms, first, nloc, x_chain,
+                                                                                          x_out, path_length_out);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }

@@ -67,17 +67,20 @@ __device__ __forceinline__ int sturm_eval(const double2* __restrict__ de, int s,
   int esum = 0;
   int k = s + 1;
   for (; k + 7 < t; k += 8) {
-    int hprev = __double2hiint(p);
+    // the nine signs (the iterate before the chunk, then the eight new ones) are shifted into one word - one
+    // funnel shift per row - and the sign changes counted once per chunk: popc(w ^ (w >> 1)) over eight pairs
+    unsigned sg = (unsigned)__double2hiint(p) >> 31;
+    int hprev = 0;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const double2 q = de[k + u];
       const double pn = fma(q.x - x, p, -(q.y * pm1));
-      const int hn = __double2hiint(pn);
-      cnt += (unsigned)(hprev ^ hn) >> 31;
-      hprev = hn;
+      hprev = __double2hiint(pn);
+      sg = __funnelshift_l((unsigned)hprev, sg, 1);
       pm1 = p;
       p = pn;
     }
+    cnt += __popc((sg ^ (sg >> 1)) & 0xffu);
     const unsigned ex = ((unsigned)hprev >> 20) & 0x7ffu;
     if (ex - 723u > 700u) {  // |p| outside [2^-300, 2^400]: rare, even per warp
       const double a = fmax(fabs(p), fabs(pm1));

@@ -1,6 +1,7 @@
 """Neighbour-image halo for a NEB chain sharded over ranks (the only collective of the path,
 SURVEY §8e): every rank owns a contiguous block of images and needs the coordinates, energy
-and gradient of the image just before and just after its block.  Implemented with
+and gradient of the image just before and just after its block; image redistribution (every
+`align_distances` iterations) needs the whole chain once: ``gather_chain``.  Implemented with
 ``torch.distributed`` point-to-point batches — NCCL over NVLink on GPUs, gloo on CPU tensors
 for the host-side tests.  Message size: (2 n + 1) doubles per side (~1.5 KB at N = 30)."""
 from __future__ import annotations
@@ -45,3 +46,18 @@ def exchange_halo(x, E, g, group=None):
     if rank < world - 1:
         xh[-1], gh[-1], Eh[-1] = recv_right[:n], recv_right[n:2 * n], recv_right[2 * n]
     return xh, Eh, gh
+
+
+def gather_chain(x, nimg, group=None):
+    """x (nloc, ...) of this rank's contiguous image block -> the whole chain (nimg, ...) on every rank (all_gather;
+    blocks as in ``image_partition``).  46 KB at config 3: one NCCL all-gather per redistribution."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x
+    world = dist.get_world_size(group)
+    blocks = image_partition(nimg, world)
+    maxloc = max(nl for _, nl in blocks)          # blocks differ by at most one image: pad to equal messages
+    send = torch.zeros((maxloc,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    send[: x.shape[0]] = x
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    return torch.cat([recv[r][:nl] for r, (_, nl) in enumerate(blocks)], dim=0)

@@ -523,6 +523,22 @@ def neb_limit_tr(nimg, first, x_halo, g, delta, fix_init_edge=False, fix_end_edg
     return delta
 
 
+def neb_redistribute(x_chain, first=0, nloc=None, want_path_length=False):
+    """distribute_geometry on the whole chain x_chain (nimg, natoms, 3): images first .. first+nloc-1 at equal arc
+    length (new tensor); optionally the running path length (nimg,)."""
+    lib = _lib.load()
+    nimg, natoms, _ = x_chain.shape
+    _chk(x_chain, "x_chain", (nimg, natoms, 3))
+    nloc = nimg - first if nloc is None else nloc
+    out = torch.empty(nloc, natoms, 3, dtype=torch.float64, device=x_chain.device)
+    pl = torch.empty(nimg, dtype=torch.float64, device=x_chain.device) if want_path_length else None
+    with torch.cuda.device(x_chain.device):
+        rc = lib.mop_neb_redistribute(int(nimg), int(natoms), int(first), int(nloc), _ptr(x_chain), _ptr(out), _ptr(pl),
+                                      _stream(x_chain.device))
+    _lib.check(rc, "mop_neb_redistribute")
+    return (out, pl) if want_path_length else out
+
+
 def lindh_hessian(xyz, atom_params, want_kdiag: bool = False):
     """Lindh model Hessian without the ill-posed K term: (B, 3N, 3N) projected; atom_params (N, 6) or
     (B, N, 6).  Returns (H, kdiag or None, counts, status)."""

@@ -1122,7 +1122,39 @@ def gen_modelhess_d3():
     np.savez_compressed(os.path.join(GOLD, "modelhess_d3.npz"), **blob)
 
 
-SETS = {"bias2": gen_bias2, "modelhess_d3": gen_modelhess_d3, "keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+
+def gen_redistribute():
+    """distribute_geometry (Interpolation/linear_interpolation.py:308) on NEB chains: the config-3 shape, an unevenly
+    spaced chain, a chain with a repeated image (zero-length segment), three images, a collapsed chain."""
+    try:
+        LI = ref_shim.ref("Interpolation.linear_interpolation")
+    except Exception:   # the module imports scipy-only helpers; fall back to the two functions' own module deps
+        raise
+    CT = ref_shim.ref("Utils.calc_tools")
+    cases = {}
+    X, _, _ = neb_chain(64, 30, 11)
+    cases["c3_64x30"] = X.reshape(64, 30, 3)
+    X, _, _ = neb_chain(17, 9, 12)
+    X = X.reshape(17, 9, 3)
+    t = np.linspace(0.0, 1.0, 17) ** 2.5          # crowded near the first image
+    cases["uneven_17x9"] = np.stack([(1 - u) * X[0] + u * X[-1] for u in t]) + 0.02 * np.random.default_rng(5).normal(size=X.shape)
+    Y = X.copy(); Y[6] = Y[5]
+    cases["repeat_17x9"] = Y
+    cases["three_3x5"] = neb_chain(3, 5, 13)[0].reshape(3, 5, 3)
+    cases["collapsed_6x4"] = np.repeat(neb_chain(2, 4, 14)[0].reshape(2, 4, 3)[:1], 6, axis=0)
+    blob = {"names": np.array(list(cases))}
+    for name, X in cases.items():
+        with quiet():
+            out = LI.distribute_geometry([x.copy() for x in X])
+            pl = CT.calc_path_length_list([x.copy() for x in X])
+        blob[f"{name}/X"] = X
+        blob[f"{name}/out"] = np.array(out)
+        blob[f"{name}/path_length"] = np.array(pl)
+    np.savez_compressed(os.path.join(GOLD, "neb_redistribute.npz"), **blob)
+    print("neb_redistribute.npz", len(cases), "cases")
+
+
+SETS = {"redistribute": gen_redistribute, "bias2": gen_bias2, "modelhess_d3": gen_modelhess_d3, "keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo, "rsprfo_reject": gen_rsprfo_reject, "rankdef": gen_rankdef, "potkeys": gen_potkeys, "neb_full": gen_neb_full}
 
 if __name__ == "__main__":

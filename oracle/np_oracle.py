@@ -2001,3 +2001,37 @@ def keep_egh(coord, kind, f1, f2, k, p):
     g = torch.func.jacrev(f)(geom)
     H = torch.func.hessian(f)(geom).reshape(geom.numel(), geom.numel())
     return float(E), g.numpy(), H.numpy()
+
+
+def path_length_list(X):
+    """Running path length of a chain X (M, N, 3), centroid-free (Utils/calc_tools.py:853-862)."""
+    pl = [0.0]
+    for i in range(len(X) - 1):
+        a = X[i + 1] - np.mean(X[i + 1], axis=0)
+        b = X[i] - np.mean(X[i], axis=0)
+        pl.append(pl[-1] + np.linalg.norm(a - b))
+    return np.array(pl)
+
+
+def distribute_geometry(X):
+    """Images at equal arc length on the piecewise-linear path (Interpolation/linear_interpolation.py:308-336)."""
+    X = np.asarray(X, dtype=np.float64)
+    M = len(X)
+    pl = path_length_list(X)
+    total = pl[-1]
+    if total < 1e-8:
+        return X.copy()
+    node = total / (M - 1)
+    out = [X[0]]
+    for i in range(1, M - 1):
+        dist = i * node
+        hit = [j for j in range(M - 1) if pl[j] <= dist <= pl[j + 1]]
+        if hit:
+            j = hit[0]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                dt = (dist - pl[j]) / (pl[j + 1] - pl[j])
+            out.append(X[j] + (X[j + 1] - X[j]) * dt)
+        else:
+            out.append(X[-1])
+    out.append(X[-1])
+    return np.array(out)

@@ -330,3 +330,53 @@ def test_rsirfo_packed_storage_vs_oracle(natoms, method, bias):
         assert rel(mv1[b], m) < RTOL, b
         assert rel(Hfull[b], o.hessian) < RTOL, b
         assert np.array_equal(Hfull[b], Hfull[b].T)
+
+
+@pytest.mark.gpu
+def test_host_pipeline_two_phase_vs_oracle_and_single_call():
+    """HostStepPipeline (pinned host buffers, chunked copies, mop_rsirfo_step_packed_begin per chunk +
+    mop_rsirfo_step_packed_finish once): two steps vs the oracle (1e-10) and BIT-identical to the one-call
+    mop_rsirfo_step_packed on the same inputs; uneven chunks incl. a single-structure chunk."""
+    import torch
+    from multioptpy_b200 import ops, synthetic
+    from multioptpy_b200.host_pipeline import HostStepPipeline, pack_lower_host
+    B, natoms, method = 7, 12, "rsirfo_bfgs"
+    n = 3 * natoms
+    mid = ops.resolve_update_method(method)
+    x0, H0, g0, rngs = synthetic.batch(91, B, natoms)
+    dev = "cuda:0"
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pipe = HostStepPipeline(B, n, mid, device=dev, chunks=[1, 4, 2], nstream=2)
+    hst = ops.new_rsirfo_state(B, 0.5, "cpu").pin_memory()
+    h_move = torch.empty(B, n, dtype=torch.float64).pin_memory()
+    h_stat = torch.empty(B, dtype=torch.int32).pin_memory()
+    hx0, hg0 = pin(x0), pin(g0)
+    pipe.step(hx0, hg0, hg0, hst, h_move, h_stat, hH=pin(pack_lower_host(H0)), hBe=pin(np.zeros(B)), state_back=True)
+    mv0 = h_move.numpy().copy()
+    # the same step through the single-call packed entry
+    Pd = ops.pack_lower(T(H0)); std = ops.new_rsirfo_state(B, 0.5, dev)
+    zero = torch.zeros(B, dtype=torch.float64, device=dev)
+    o0 = ops.rsirfo_step(Pd, T(x0), T(g0), T(g0), std, method=mid, Be=zero, packed=True)
+    assert np.array_equal(o0["move"].cpu().numpy(), mv0)
+    x1 = np.empty_like(x0); g1 = np.empty_like(g0); oracles = []
+    for b in range(B):
+        o = O.RSIRFOOracle(method=method, saddle_order=0)
+        o.set_hessian(H0[b].copy())
+        m = o.run(x0[b], g0[b], g0[b], None, None, 0.0)
+        assert rel(mv0[b], m) < RTOL, b
+        x1[b], g1[b] = synthetic.second_point(x0[b], H0[b], g0[b], m, rngs[b])
+        oracles.append(o)
+    hx1, hg1 = pin(x1), pin(g1)
+    # second step on the RESIDENT Hessians (hH = None), update active
+    pipe.step(hx1, hg1, hg1, hst, h_move, h_stat, hx_prev=hx0, hg_prev=hg0, hBe=pin(np.full(B, -1e-3)), state_back=True)
+    o1 = ops.rsirfo_step(Pd, T(x1), T(g1), T(g1), std, method=mid, x_prev=T(x0), g_prev=T(g0), Be=zero - 1e-3, packed=True)
+    assert np.array_equal(o1["move"].cpu().numpy(), h_move.numpy())
+    assert np.array_equal(o1["status"].cpu().numpy(), h_stat.numpy())
+    assert torch.equal(std.cpu(), hst)
+    Hfull = pipe.hessians().cpu().numpy()
+    for b, o in enumerate(oracles):
+        m = o.run(x1[b], g1[b], g1[b], x0[b], g0[b], -1e-3)
+        assert rel(h_move.numpy()[b], m) < RTOL, b
+        assert rel(Hfull[b], o.hessian) < RTOL, b
+    assert (h_stat.numpy() & ops.ST_UPDATED).all()

@@ -192,3 +192,64 @@ def test_neb_on_disk_formats_roundtrip(tmp_path):
     assert txt[4] == f"Cl   {x[0]:>17.12f}   {x[1]:>17.12f}   {x[2]:>17.12f}"      # the reference's f-string, verbatim layout
     e, xyz, cm = fileio.read_xyz_sample(paths[1])
     assert e == ["C", "H", "Cl"] and cm == (0, 1) and np.abs(xyz - G[1]).max() < 5e-13
+
+
+# ---- image redistribution (align_distances): Interpolation/linear_interpolation.py:308-336 -------------------------
+def test_oracle_redistribute_vs_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "neb_redistribute.npz"))
+    for name in z["names"]:
+        X = z[f"{name}/X"]
+        assert rel(O.path_length_list(X), z[f"{name}/path_length"]) < 1e-14, name
+        assert rel(O.distribute_geometry(X), z[f"{name}/out"]) < 1e-13, name
+
+
+@pytest.mark.gpu
+def test_gpu_redistribute_vs_reference(golden_dir):
+    from multioptpy_b200 import ops
+    from multioptpy_b200.Interpolation.linear_interpolation import distribute_geometry
+    z = np.load(os.path.join(golden_dir, "neb_redistribute.npz"))
+    for name in z["names"]:
+        X = z[f"{name}/X"]
+        xd = torch.from_numpy(X).to("cuda:0")
+        out, pl = ops.neb_redistribute(xd, want_path_length=True)
+        assert rel(pl.cpu().numpy(), z[f"{name}/path_length"]) < 1e-13, name
+        assert rel(out.cpu().numpy(), z[f"{name}/out"]) < RTOL, name
+        # a rank's slice of the chain equals the slice of the full result
+        part = ops.neb_redistribute(xd, 1, len(X) - 2)
+        assert torch.equal(part, out[1:-1]), name
+        lst = distribute_geometry([x for x in X])           # list in -> list out, like the reference
+        assert isinstance(lst, list) and rel(np.array(lst), z[f"{name}/out"]) < RTOL, name
+    # a straight, equally spaced chain is a fixed point (a bent chain is not: the chords cut its corners)
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=(30, 3)), rng.normal(size=(30, 3))
+    X = np.stack([a + t * (b - a) for t in np.linspace(0.0, 1.0, 64)])
+    again = ops.neb_redistribute(torch.from_numpy(X).to("cuda:0")).cpu().numpy()
+    assert rel(again, X) < 1e-12
+
+
+def _gather_worker(rank, world, port, nimg, q):
+    import torch.distributed as dist
+    from multioptpy_b200.neb_halo import gather_chain, image_partition
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X = torch.arange(nimg * 4 * 3, dtype=torch.float64).reshape(nimg, 4, 3)
+    first, nloc = image_partition(nimg, world)[rank]
+    chain = gather_chain(X[first:first + nloc].clone(), nimg)
+    q.put((rank, bool(torch.equal(chain, X))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_chain_gloo(world):
+    """The all-gather that precedes a redistribution of a sharded chain (uneven blocks at world 3)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gather_worker, args=(r, world, port, 7, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
