@@ -6,7 +6,8 @@ pipeline is built around its trip over PCIe:
 
 * the batch is cut into chunks of whole waves of the fused front-end / tridiagonalisation kernel (2 CTAs x 148
   SMs = 296 structures), the short remainder chunk first so that compute starts early;
-* chunk c travels on stream c mod S (pinned host memory, ``cudaMemcpyAsync``) and is reduced by
+* the vectors of the whole batch (geometry, gradients, state: 2.5 MB) go first in one copy each, then chunk c of
+  the Hessians travels on stream c mod S (pinned host memory, ``cudaMemcpyAsync``) and is reduced by
   ``mop_rsirfo_step_packed_begin`` on the same stream while chunk c + 1 is still in flight;
 * ``mop_rsirfo_step_packed_finish`` then runs the spectrum / step kernel ONCE for the whole batch (it hides its
   dependent chains behind seven resident CTAs per SM and cannot share an SM with the reduction, whose two CTAs
@@ -94,25 +95,31 @@ class HostStepPipeline:
         start = torch.cuda.Event(); start.record(main)
         nb = 0
         with torch.cuda.device(self.dev):
+            # the vectors of the WHOLE batch first (2.5 MB, seven copies instead of seven per chunk), then the Hessian
+            # chunks back to back on the copy engine
+            s0 = self.streams[0]
+            s0.wait_event(start)
+            with torch.cuda.stream(s0):
+                pairs = [(self.dx, hx), (self.dg, hg), (self.dstate, hstate)]
+                if not same_g:
+                    pairs.append((self.dBg, hBg))
+                if hx_prev is not None:
+                    pairs += [(self.dxp, hx_prev), (self.dgp, hg_prev)]
+                if hBe is not None:
+                    pairs.append((self.dBe, hBe))
+                for dst, src in pairs:
+                    dst.copy_(src, non_blocking=True)
+                    nb += src.numel() * src.element_size()
+                vec_ready = torch.cuda.Event(); vec_ready.record(s0)
+            dBg = self.dg if same_g else self.dBg
             for c in range(len(self.bounds) - 1):
                 s = self.streams[c % len(self.streams)]
                 lo, hi = int(self.bounds[c]), int(self.bounds[c + 1]); sl = slice(lo, hi)
-                s.wait_event(start)
+                s.wait_event(vec_ready)
                 with torch.cuda.stream(s):
-                    # vectors first: they ride behind the previous chunk's Hessian copy instead of delaying this chunk
-                    pairs = [(self.dx, hx), (self.dg, hg), (self.dstate, hstate)]
-                    if not same_g:
-                        pairs.append((self.dBg, hBg))
-                    if hx_prev is not None:
-                        pairs += [(self.dxp, hx_prev), (self.dgp, hg_prev)]
-                    if hBe is not None:
-                        pairs.append((self.dBe, hBe))
                     if hH is not None:
-                        pairs.append((self.dH, hH))
-                    for dst, src in pairs:
-                        dst[sl].copy_(src[sl], non_blocking=True)
-                        nb += src[sl].numel() * src.element_size()
-                    dBg = self.dg if same_g else self.dBg
+                        self.dH[sl].copy_(hH[sl], non_blocking=True)
+                        nb += hH[sl].numel() * 8
                     rc = lib.mop_rsirfo_step_packed_begin(
                         B, lo, hi - lo, n, self.method, _ptr(self.dH), None, _ptr(self.dx), _ptr(dBg), _ptr(self.dg),
                         _ptr(self.dxp) if hx_prev is not None else None, _ptr(self.dgp) if hx_prev is not None else None,
@@ -121,7 +128,6 @@ class HostStepPipeline:
                     self.events[c].record(s)
             for ev in self.events:
                 main.wait_event(ev)
-            dBg = self.dg if same_g else self.dBg
             rc = lib.mop_rsirfo_step_packed_finish(
                 B, n, self.saddle_order, int(self.neb_mode), self.trust_min, self.trust_max, _ptr(self.dH), None,
                 _ptr(self.dx), _ptr(dBg), _ptr(self.dBe) if hBe is not None else None, _ptr(self.dstate), _ptr(self.move),
