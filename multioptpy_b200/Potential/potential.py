@@ -33,7 +33,14 @@ _ACTIVATION = {
 }
 _HANDLED = {"AFIR_gamma", "keep_pot_spring_const", "keep_pot_v2_spring_const", "keep_angle_spring_const",
             "keep_dihedral_angle_spring_const", "anharmonic_keep_pot_spring_const", "well_pot_wall_energy",
-            "keep_out_of_plain_angle_spring_const", "repulsive_potential_well_scale"}
+            "keep_out_of_plain_angle_spring_const", "repulsive_potential_well_scale", "keep_angle_v2_spring_const",
+            "keep_dihedral_angle_v2_spring_const", "keep_out_of_plain_angle_v2_spring_const"}
+
+
+def centroid_term(kind, fragments, k, p):
+    """One fragment-centroid restraint (kinds 9 - 11): all atoms in `atoms`, the fragment sizes in q."""
+    atoms = [a - 1 for f in fragments for a in f]
+    return (kind, atoms, [], float(k), float(p), [float(len(f)) for f in fragments])
 
 
 def lj_pair_terms(element_list, fragm_1, fragm_2, well, dist, unit):
@@ -161,6 +168,19 @@ class BiasPotentialCalculation:
                     phi0 = float(torch.deg2rad(torch.tensor(float(force_data["keep_out_of_plain_angle_angle"][i]), dtype=torch.float64)))
                     terms.append((ops.BIAS_KEEP_OOP, [a - 1 for a in force_data["keep_out_of_plain_angle_atom_pairs"][i]],
                                   [], float(k), phi0))
+        rad = lambda deg: float(torch.deg2rad(torch.tensor(float(deg), dtype=torch.float64)))
+        for i, k in enumerate(force_data.get("keep_angle_v2_spring_const", [])):             # potential.py:758-772
+            if 0.0 not in k:
+                fr = [force_data[f"keep_angle_v2_fragm{j}"][i] for j in (1, 2, 3)]
+                terms.append(centroid_term(ops.BIAS_KEEP_ANGLE_V2, fr, k[0], force_data["keep_angle_v2_angle"][i][0]))
+        for i, k in enumerate(force_data.get("keep_dihedral_angle_v2_spring_const", [])):    # potential.py:812-827
+            if 0.0 not in k:
+                fr = [force_data[f"keep_dihedral_angle_v2_fragm{j}"][i] for j in (1, 2, 3, 4)]
+                terms.append(centroid_term(ops.BIAS_KEEP_DIHEDRAL_V2, fr, k[0], rad(force_data["keep_dihedral_angle_v2_angle"][i][0])))
+        for i, k in enumerate(force_data.get("keep_out_of_plain_angle_v2_spring_const", [])):  # potential.py:862-880
+            if 0.0 not in k:
+                fr = [force_data[f"keep_out_of_plain_angle_v2_fragm{j}"][i] for j in (1, 2, 3, 4)]
+                terms.append(centroid_term(ops.BIAS_KEEP_OOP_V2, fr, k[0], rad(force_data["keep_out_of_plain_angle_v2_angle"][i][0])))
         if terms:
             dev = torch.device(self.device)
             xyz = torch.as_tensor(np.ascontiguousarray(geom)).reshape(1, N, 3).to(dev)

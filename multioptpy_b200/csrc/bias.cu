@@ -16,6 +16,13 @@
 //   kind 8  StructKeepOutofPlainAnglePotential (keep_outofplain_angle_potential.py:6-146)  E = 1/2 k (phi - phi0)^2,
 //           phi = atan2(a1 . n, sqrt(|a1|^2 - (a1 . n)^2)) the elevation of a1 over the plane (a2, a3); zero when the
 //           plane is undefined (|a2 x a3|^2 < 1e-8)
+//   kind 9  StructKeepAnglePotentialv2 (keep_angle_potential.py:226-478)  the angle between three fragment CENTROIDS;
+//           within 1e-3 rad of 0 / pi it continues 1/2 k (theta - theta0)^2 by a quadratic in cos(theta) matched in value
+//           and slope at the cut (Gauss-Newton curvature), except at an exactly linear / collapsed theta0 where the
+//           fifth-order expansion of kind 3 is the energy itself
+//   kind 10 StructKeepDihedralAnglePotentialv2 (keep_dihedral_angle_potential.py:156-257)  kind 4 on four centroids
+//   kind 11 StructKeepOutofPlainAnglePotentialv2 (keep_outofplain_angle_potential.py:148-290)  kind 8 on four centroids
+//           (kinds 9-11: q[g] = number of atoms of fragment g, the fragments one after the other in `atoms`)
 // The reference differentiates calc_energy with torch.func.jacrev / hessian on the CPU
 // (Potential/potential.py:127-137); here thread (term, coordinate pair) evaluates the same expression once in
 // hyper-dual arithmetic.  Results are ADDED to E, grad, hess (the aggregator sums all bias terms).
@@ -48,6 +55,17 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     return HD{xyz[3 * t.atoms[pos] + comp], c == ca ? 1.0 : 0.0, c == cb ? 1.0 : 0.0, 0.0};
   };
   const double BOHR2ANG = 0.52917721067;
+  // point g of an angle / dihedral / out-of-plane term: atom g (kinds 3, 4, 8) or the centroid of fragment g (9-11)
+  const bool grouped = t.kind >= 9;
+  int goff[5] = {0, 0, 0, 0, 0};
+  if (grouped)
+    for (int g = 0; g < 4; ++g) goff[g + 1] = goff[g] + (int)t.q[g];
+  auto P = [&](int g, int comp) -> HD {
+    if (!grouped) return X(g, comp);
+    HD sum = hd_const(0.0);
+    for (int a = goff[g]; a < goff[g + 1]; ++a) sum = sum + X(a, comp);
+    return (1.0 / (goff[g + 1] - goff[g])) * sum;
+  };
   if (t.kind == 1 || t.kind == 2) {
     HD v[3];
     for (int c = 0; c < 3; ++c) {
@@ -95,12 +113,13 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     if (r.f < d) return t.k * wall(xl);
     return t.k * (hd_const(2.875) - 3.75 * xl);
   }
-  if (t.kind == 8) {
+  if (t.kind == 8 || t.kind == 11) {
     HD a1[3], a2[3], a3[3], nn[3];
     for (int c = 0; c < 3; ++c) {
-      a1[c] = X(1, c) - X(0, c);
-      a2[c] = X(2, c) - X(0, c);
-      a3[c] = X(3, c) - X(0, c);
+      const HD p0 = P(0, c);
+      a1[c] = P(1, c) - p0;
+      a2[c] = P(2, c) - p0;
+      a3[c] = P(3, c) - p0;
     }
     hd_cross(a2, a3, nn);
     const HD nsq = hd_dot(nn, nn);
@@ -113,12 +132,13 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     return (0.5 * t.k) * (diff * diff);
   }
   const double PI = 3.141592653589793;
-  if (t.kind == 4) {
+  if (t.kind == 4 || t.kind == 10) {
     HD b1[3], b2[3], b3[3], n1[3], n2[3], m1[3];
     for (int c = 0; c < 3; ++c) {
-      b1[c] = X(1, c) - X(0, c);
-      b2[c] = X(2, c) - X(1, c);
-      b3[c] = X(3, c) - X(2, c);
+      const HD p1 = P(1, c), p2 = P(2, c);
+      b1[c] = p1 - P(0, c);
+      b2[c] = p2 - p1;
+      b3[c] = P(3, c) - p2;
     }
     hd_cross(b1, b2, n1);
     hd_cross(b2, b3, n2);
@@ -143,12 +163,13 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     diff = diff - hd_const(2.0 * PI * rint(diff.f / (2.0 * PI)));  // wrap to [-pi, pi]; torch.round = half to even
     return ((0.5 * t.k) * (diff * diff)) * s1 * s2;
   }
-  // kind 3
+  // kinds 3, 9
   const double theta0 = t.p * (PI / 180.0);
   HD v1[3], v2[3];
   for (int c = 0; c < 3; ++c) {
-    v1[c] = X(0, c) - X(1, c);
-    v2[c] = X(2, c) - X(1, c);
+    const HD pv = P(1, c);
+    v1[c] = P(0, c) - pv;
+    v2[c] = P(2, c) - pv;
   }
   const HD n1 = hd_sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
   const HD n2 = hd_sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
@@ -165,6 +186,31 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     return delta * term;
   };
   const bool near0 = u.f > ucp, nearpi = u.f < ucn;
+  if (t.kind == 9) {
+    auto quad = [&](double th_cut, double ucut) -> HD {  // value + slope at the cut, curvature k (dtheta/du)^2
+      const double dth = -1.0 / sin(th_cut);
+      const double val = 0.5 * t.k * (th_cut - theta0) * (th_cut - theta0);
+      const double d1 = t.k * (th_cut - theta0) * dth, d2 = t.k * (dth * dth);
+      const HD du = u - hd_const(ucut);
+      return hd_const(val) + d1 * du + (0.5 * d2) * (du * du);
+    };
+    if (fabs(theta0) < 1e-8) {
+      if (near0) return (0.5 * t.k) * taylor(hd_const(1.0) - u);
+      if (nearpi) return quad(PI - 1e-3, ucn);
+      const HD th = hd_acos(hd_clamp(u, -1.0, ucp));
+      return (0.5 * t.k) * (th * th);
+    }
+    if (fabs(theta0 - PI) < 1e-8) {
+      if (nearpi) return (0.5 * t.k) * taylor(hd_const(1.0) + u);
+      if (near0) return quad(1e-3, ucp);
+      const HD d = hd_acos(hd_clamp(u, ucn, 1.0)) - hd_const(theta0);
+      return (0.5 * t.k) * (d * d);
+    }
+    if (near0) return quad(1e-3, ucp);
+    if (nearpi) return quad(PI - 1e-3, ucn);
+    const HD d = hd_acos(u) - hd_const(theta0);
+    return (0.5 * t.k) * (d * d);
+  }
   HD theta_minus;  // theta - theta0 (or its stand-in), energy = 1/2 k (.)^2
   if (fabs(theta0) < 1e-8) {                 // branch A
     if (near0) return (0.5 * t.k) * taylor(hd_const(1.0) - u);
@@ -194,7 +240,8 @@ __global__ void __launch_bounds__(128) k_bias_terms(int N, const BiasTerm* __res
   const int b = blockIdx.y, n = 3 * N;
   if (threadIdx.x == 0) t = terms[blockIdx.x];
   __syncthreads();
-  const int m = t.kind == 3 ? 3 : ((t.kind == 4 || t.kind == 8) ? 4 : ((t.kind == 5 || t.kind == 6) ? 2 : t.n1 + t.n2));
+  const int m = t.kind >= 9 ? (int)(t.q[0] + t.q[1] + t.q[2] + t.q[3])
+                            : (t.kind == 3 ? 3 : ((t.kind == 4 || t.kind == 8) ? 4 : ((t.kind == 5 || t.kind == 6) ? 2 : t.n1 + t.n2)));
   const int nc = 3 * m;
   const double* xyz = xyz_all + (size_t)b * n;
   for (int w = threadIdx.x; w < nc * nc; w += blockDim.x) {

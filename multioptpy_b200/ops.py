@@ -783,6 +783,7 @@ BIAS_KEEP, BIAS_KEEP_V2, BIAS_KEEP_ANGLE, BIAS_KEEP_DIHEDRAL = 1, 2, 3, 4   # ki
 # kind 5: k = eps (Hartree), p = sigma (Bohr); kind 6: k, p = r0 (Angstrom), q[0] = well depth; kind 7: k = wall energy
 # (Hartree), q = the four limits (Bohr); kind 8: atoms centre, probe, plane 1, plane 2; p = phi0 in RADIANS
 BIAS_LJ_PAIR, BIAS_ANHARMONIC_KEEP, BIAS_WELL, BIAS_KEEP_OOP = 5, 6, 7, 8
+BIAS_KEEP_ANGLE_V2, BIAS_KEEP_DIHEDRAL_V2, BIAS_KEEP_OOP_V2 = 9, 10, 11   # fragment centroids: q = fragment sizes
 BIAS_MAXA = 64
 
 

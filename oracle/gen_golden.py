@@ -808,12 +808,19 @@ def gen_bias2():
     an = ref_shim.ref("Potential.anharmonic_keep_potential")
     sw = ref_shim.ref("Potential.switching_potential")
     oop = ref_shim.ref("Potential.keep_outofplain_angle_potential")
+    ang = ref_shim.ref("Potential.keep_angle_potential")
+    dih = ref_shim.ref("Potential.keep_dihedral_angle_potential")
     elems, xyz = read_xyz(os.path.join(ref_shim.REF_ROOT, "test/aldol_rxn.xyz"))
     N = len(elems)
     cen = lambda f: xyz[[a - 1 for a in f]].mean(axis=0)
     f1w, f2w = [1, 2, 3, 4], [5, 6, 7, 8, 9]
     dw = np.linalg.norm(cen(f1w) - cen(f2w)) * 0.52917721067      # centroid distance in Angstrom
     flat = xyz.copy(); flat[2] = flat[0] + 1.7 * (flat[1] - flat[0])          # atoms 1, 2, 3 collinear: undefined plane
+    flat2 = xyz.copy(); flat2[2] = flat2[1] + 0.8 * (flat2[1] - flat2[0])     # 1 - 2 - 3 exactly linear, vertex 2
+    perp = np.cross(xyz[1] - xyz[0], [0.3, -0.2, 0.9]); perp /= np.linalg.norm(perp)
+    near_pi = flat2.copy(); near_pi[2] = near_pi[2] + 4e-4 * np.linalg.norm(flat2[2] - flat2[1]) * perp      # 4e-4 rad off linear
+    near_pi2 = flat2.copy(); near_pi2[2] = near_pi2[2] + 2e-4 * np.linalg.norm(flat2[2] - flat2[1]) * perp    # (exactly linear: u clamps, all derivatives 0)
+    near_0 = xyz.copy(); near_0[2] = near_0[1] + 1.3 * (near_0[0] - near_0[1]) + 5e-4 * 1.3 * np.linalg.norm(near_0[0] - near_0[1]) * perp
     cases = [
         ("lj_scale", dict(cls="lj_scale", well=1.3, dist=0.9, f1=[1, 2, 3], f2=[5, 6, 10, 11]), xyz),
         ("lj_value", dict(cls="lj_value", well=2.5, dist=3.2, f1=[1, 4], f2=[6, 7, 8]), xyz),
@@ -827,6 +834,16 @@ def gen_bias2():
         ("oop_gen", dict(cls="oop", k=0.3, atoms=[1, 2, 3, 5], angle=12.0), xyz),
         ("oop_neg", dict(cls="oop", k=0.2, atoms=[5, 6, 7, 10], angle=-25.0), xyz),
         ("oop_undefined", dict(cls="oop", k=0.3, atoms=[1, 5, 2, 3], angle=10.0), flat),
+        # fragment-centroid (v2) restraints: general angle, exactly linear theta0 = 180 in its expansion region and in its
+        # regular region, theta0 = 0, the quadratic continuations near pi and near 0, dihedral and out-of-plane angle
+        ("angle_v2_gen", dict(cls="ang2", k=0.3, f=[[1, 2], [5], [6, 7, 8]], angle=100.0), xyz),
+        ("angle_v2_lin180", dict(cls="ang2", k=0.25, f=[[1], [2], [3]], angle=180.0), near_pi2),
+        ("angle_v2_lin180_bent", dict(cls="ang2", k=0.25, f=[[1, 4], [2], [3, 9]], angle=180.0), xyz),
+        ("angle_v2_zero", dict(cls="ang2", k=0.2, f=[[1], [5, 6], [3]], angle=0.0), xyz),
+        ("angle_v2_near_pi", dict(cls="ang2", k=0.3, f=[[1], [2], [3]], angle=120.0), near_pi),
+        ("angle_v2_near_0", dict(cls="ang2", k=0.3, f=[[1], [2], [3]], angle=30.0), near_0),
+        ("dihedral_v2", dict(cls="dih2", k=0.2, f=[[1, 2], [3], [5, 6], [7]], angle=35.0), xyz),
+        ("oop_v2", dict(cls="oop2", k=0.3, f=[[1], [2, 3], [5], [6, 7]], angle=12.0), xyz),
     ]
     blob = {"names": np.array([c[0] for c in cases]), "elements": np.array(elems)}
     for name, cfg, geom in cases:
@@ -843,6 +860,23 @@ def gen_bias2():
                                                    anharmonic_keep_pot_atom_pairs=cfg["pair"], anharmonic_keep_pot_distance=cfg["dist"])
         elif cfg["cls"] == "well":
             pot = sw.WellPotential(well_pot_wall_energy=cfg["wall"], well_pot_fragm_1=cfg["f1"], well_pot_fragm_2=cfg["f2"], well_pot_limit_dist=cfg["lim"])
+        elif cfg["cls"] == "ang2":
+            f = cfg["f"]
+            pot = ang.StructKeepAnglePotentialv2(keep_angle_v2_spring_const=cfg["k"], keep_angle_v2_angle=cfg["angle"],
+                                                 keep_angle_v2_fragm1=f[0], keep_angle_v2_fragm2=f[1], keep_angle_v2_fragm3=f[2])
+            par = torch.tensor([cfg["k"], cfg["angle"]], dtype=torch.float64)     # process_keep_angle_v2, potential.py:328-344
+        elif cfg["cls"] == "dih2":
+            f = cfg["f"]
+            pot = dih.StructKeepDihedralAnglePotentialv2(keep_dihedral_angle_v2_spring_const=cfg["k"], keep_dihedral_angle_v2_angle=cfg["angle"],
+                                                         keep_dihedral_angle_v2_fragm1=f[0], keep_dihedral_angle_v2_fragm2=f[1],
+                                                         keep_dihedral_angle_v2_fragm3=f[2], keep_dihedral_angle_v2_fragm4=f[3])
+            par = torch.tensor([cfg["k"], cfg["angle"]], dtype=torch.float64)
+        elif cfg["cls"] == "oop2":
+            f = cfg["f"]
+            pot = oop.StructKeepOutofPlainAnglePotentialv2(keep_out_of_plain_angle_v2_spring_const=cfg["k"], keep_out_of_plain_angle_v2_angle=cfg["angle"],
+                                                           keep_out_of_plain_angle_v2_fragm1=f[0], keep_out_of_plain_angle_v2_fragm2=f[1],
+                                                           keep_out_of_plain_angle_v2_fragm3=f[2], keep_out_of_plain_angle_v2_fragm4=f[3])
+            par = torch.tensor([cfg["k"], cfg["angle"]], dtype=torch.float64)
         else:
             pot = oop.StructKeepOutofPlainAnglePotential(keep_out_of_plain_angle_spring_const=cfg["k"],
                                                          keep_out_of_plain_angle_atom_pairs=cfg["atoms"], keep_out_of_plain_angle_angle=cfg["angle"])

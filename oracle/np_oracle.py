@@ -1940,8 +1940,10 @@ def _bias2_energy_torch(geom, kind, f1, f2, k, p, q):
     """calc_energy of one atom pair of LJRepulsivePotentialScale / Value (kind 5: k = eps, p = sigma, both already in
     atomic units; LJ_repulsive_potential.py:42-62,97-114), StructAnharmonicKeepPotential (kind 6;
     anharmonic_keep_potential.py:14-27), WellPotential (kind 7: k = wall energy in Hartree, q = limits in Bohr;
-    switching_potential.py:14-67) and StructKeepOutofPlainAnglePotential (kind 8: p = phi0 in radians;
-    keep_outofplain_angle_potential.py:33-146), restated on a torch tensor (atoms 0-based)."""
+    switching_potential.py:14-67), StructKeepOutofPlainAnglePotential (kind 8: p = phi0 in radians;
+    keep_outofplain_angle_potential.py:33-146) and the fragment-centroid restraints StructKeepAnglePotentialv2 /
+    StructKeepDihedralAnglePotentialv2 / StructKeepOutofPlainAnglePotentialv2 (kinds 9 - 11), restated on a torch
+    tensor (atoms 0-based)."""
     import math
     import torch
     if kind == 5:
@@ -1964,8 +1966,58 @@ def _bias2_energy_torch(geom, kind, f1, f2, k, p, q):
         if r < d:
             return k * (2.0 - 20.0 * xl ** 3 + 30.0 * xl ** 4 - 12.0 * xl ** 5)
         return k * (-3.75 * xl + 2.875)
-    ci, i1, i2, i3 = f1
-    a1, a2, a3 = geom[i1] - geom[ci], geom[i2] - geom[ci], geom[i3] - geom[ci]
+    if kind in (9, 10, 11):   # fragment-centroid angle / dihedral / out-of-plane angle: q = fragment sizes, f1 = all atoms
+        off = np.concatenate([[0], np.cumsum([int(v) for v in q])])
+        cen = [geom[list(f1[off[g]:off[g + 1]])].mean(dim=0) for g in range(len(q)) if int(q[g]) > 0]
+    if kind == 9:             # StructKeepAnglePotentialv2 (keep_angle_potential.py:293-478): p = theta0 in DEGREES
+        th0 = p * (math.pi / 180.0)
+        v1, v2 = cen[0] - cen[1], cen[2] - cen[1]
+        u = torch.clamp(torch.dot(v1, v2) / torch.clamp(torch.linalg.norm(v1) * torch.linalg.norm(v2), min=1e-12), -1.0, 1.0)
+        cut = 1e-3
+        ucp, ucn = math.cos(cut), math.cos(math.pi - cut)
+        co = [128.0 / 1575.0, 4.0 / 35.0, 8.0 / 45.0, 1.0 / 3.0, 2.0]
+
+        def taylor(delta):
+            term = co[0]
+            for c in co[1:]:
+                term = c + delta * term
+            return delta * term
+
+        def quad(th_cut, ucut):
+            dth = -1.0 / math.sin(th_cut)
+            return 0.5 * k * (th_cut - th0) ** 2 + k * (th_cut - th0) * dth * (u - ucut) + 0.5 * k * dth ** 2 * (u - ucut) ** 2
+        if abs(th0) < 1e-8:
+            if u > ucp:
+                return 0.5 * k * taylor(1.0 - u)
+            return quad(math.pi - cut, ucn) if u < ucn else 0.5 * k * torch.acos(torch.clamp(u, -1.0, ucp)) ** 2
+        if abs(th0 - math.pi) < 1e-8:
+            if u < ucn:
+                return 0.5 * k * taylor(1.0 + u)
+            return quad(cut, ucp) if u > ucp else 0.5 * k * (torch.acos(torch.clamp(u, ucn, 1.0)) - th0) ** 2
+        if u > ucp:
+            return quad(cut, ucp)
+        return quad(math.pi - cut, ucn) if u < ucn else 0.5 * k * (torch.acos(u) - th0) ** 2
+    if kind == 10:            # StructKeepDihedralAnglePotentialv2 (keep_dihedral_angle_potential.py:186-257): p in radians
+        b1, b2, b3 = cen[1] - cen[0], cen[2] - cen[1], cen[3] - cen[2]
+        n1, n2 = torch.linalg.cross(b1, b2), torch.linalg.cross(b2, b3)
+        n1sq, n2sq = torch.sum(n1 ** 2), torch.sum(n2 ** 2)
+
+        def sw(val):
+            t = torch.clamp((val - 1e-10) / (1e-8 - 1e-10), 0.0, 1.0)
+            return t * t * (3.0 - 2.0 * t)
+        n1h = n1 / torch.clamp(torch.sqrt(n1sq), min=1e-12)
+        n2h = n2 / torch.clamp(torch.sqrt(n2sq), min=1e-12)
+        b2h = b2 / torch.clamp(torch.linalg.norm(b2), min=1e-12)
+        x = torch.sum(n1h * n2h)
+        y = torch.sum(torch.linalg.cross(n1h, n2h) * b2h)
+        diff = torch.atan2(y, x) - p
+        diff = diff - 2.0 * math.pi * torch.round(diff / (2.0 * math.pi))
+        return 0.5 * k * diff ** 2 * sw(n1sq) * sw(n2sq)
+    if kind == 11:
+        a1, a2, a3 = cen[1] - cen[0], cen[2] - cen[0], cen[3] - cen[0]
+    else:
+        ci, i1, i2, i3 = f1
+        a1, a2, a3 = geom[i1] - geom[ci], geom[i2] - geom[ci], geom[i3] - geom[ci]
     n = torch.linalg.cross(a2, a3)
     nsq = torch.sum(n ** 2)
     if nsq < 1e-8:

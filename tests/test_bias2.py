@@ -38,6 +38,12 @@ def force_data_for(cfg):
     if c == "well":
         return {"well_pot_wall_energy": [cfg["wall"]], "well_pot_fragm_1": [cfg["f1"]], "well_pot_fragm_2": [cfg["f2"]],
                 "well_pot_limit_dist": [cfg["lim"]]}
+    if c in ("ang2", "dih2", "oop2"):     # fragment-centroid restraints (potential.py:758-772,812-827,862-880)
+        stem = {"ang2": "keep_angle_v2", "dih2": "keep_dihedral_angle_v2", "oop2": "keep_out_of_plain_angle_v2"}[c]
+        fd = {f"{stem}_spring_const": [[cfg["k"]]], f"{stem}_angle": [[cfg["angle"]]]}
+        for j, f in enumerate(cfg["f"]):
+            fd[f"{stem}_fragm{j + 1}"] = [f]
+        return fd
     return {"keep_out_of_plain_angle_spring_const": [cfg["k"]], "keep_out_of_plain_angle_atom_pairs": [cfg["atoms"]],
             "keep_out_of_plain_angle_angle": [cfg["angle"]]}
 
@@ -58,6 +64,10 @@ def oracle_terms(cfg, elems):
         return [(7, [a - 1 for a in cfg["f1"]], [a - 1 for a in cfg["f2"]], cfg["wall"] / tables.HARTREE2KJMOL, 0.0,
                  [v / B2A for v in cfg["lim"]])]
     phi0 = float(torch.deg2rad(torch.tensor(cfg["angle"], dtype=torch.float64)))
+    if c in ("ang2", "dih2", "oop2"):
+        atoms = [a - 1 for f in cfg["f"] for a in f]
+        sizes = [float(len(f)) for f in cfg["f"]]
+        return [({"ang2": 9, "dih2": 10, "oop2": 11}[c], atoms, [], cfg["k"], cfg["angle"] if c == "ang2" else phi0, sizes)]
     return [(8, [a - 1 for a in cfg["atoms"]], [], cfg["k"], phi0, [])]
 
 
