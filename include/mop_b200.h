@@ -85,6 +85,7 @@ enum {
 #define MOP_ST_NO_HISTORY (1 << 13)     /* first call: no previous point, update skipped  */
 #define MOP_ST_UPD_REJECTED (1 << 14)   /* P-RFO: updated spectrum > 1e6, update reverted (rsprfo.py:1247) */
 #define MOP_ST_ALPHA_UNSTABLE (1 << 16) /* alpha loop did not end on its rounding-free exits: the secular root is ill-conditioned, the reference's own step is summation-order dependent (rfo_secular.cuh) */
+#define MOP_ST_CONSTR_CONVERGED (1 << 17) /* CRSIRFO: subspace gradient below the threshold, zero step returned (crsirfo.py:108-118) */
 #define MOP_ST_LINDH_NO_K (1 << 15)     /* Lindh: non-zero gradient but no internal gradient, K term omitted */
 
 /* eigensolver selection */
@@ -229,6 +230,23 @@ int mop_rsirfo_spectral_step(int B, int n, int saddle_order, int neb_mode, doubl
                              const double* Bg, const double* Be, double* state, double* move_out,
                              double* eigvals_out, double* pred_out, int32_t* status, void* work,
                              size_t work_bytes, void* stream);
+
+/* ---- (2e) constrained RS-I-RFO: the subspace projection of CRSIRFO.run ---------------
+ * Replaces CRSIRFO._get_null_space_basis + the projections of CRSIRFO.run (Optimizer/crsirfo.py:16-45,88-100).
+ * C [B][k][n]: the raw constraint rows of constraints_obj._get_all_constraint_vectors (1 <= k <= 12); they are
+ * normalised, their span truncated by the reference's singular-value rule (svd_threshold, default 1e-5) and
+ * projected out of g (+ H shake when shake [B][n], the SHAKE displacement, is longer than 1e-6) and of sym(H):
+ * gp_out [B][n], Hp_out [B][n][n] (the constrained directions carry the eigenvalue ||sym(H)||_F + 1 and no
+ * gradient), rank_out [B].  mop_rsirfo_spectral_step(Hp, gp, Bg = gp, ...) is then the rest of CRSIRFO.run;
+ * mop_crsirfo_finalize applies its explicit convergence test (|gp| < grad_threshold: zero step, state restored from
+ * state_before with only the "previous point" fields set, status = MOP_ST_CONSTR_CONVERGED).
+ * mop_add_inplace: dst += src (the reference adds the bias Hessian INTO self.hessian, crsirfo.py:76,86). */
+int mop_constraint_project(int B, int n, int k, double svd_threshold, const double* C, const double* H, const double* g,
+                           const double* shake, double* Hp_out, double* gp_out, int32_t* rank_out, void* stream);
+int mop_crsirfo_finalize(int B, int n, double grad_threshold, const double* gp, const double* Be,
+                         const double* state_before, double* state, double* move, double* pred, int32_t* status,
+                         void* stream);
+int mop_add_inplace(size_t count, double* dst, const double* src, void* stream);
 
 /* ---- (3a) connectivity tables ------------------------------------------------
  * Replaces BondConnectivity.connectivity_table (Utils/bond_connectivity.py:7-134):

@@ -39,6 +39,9 @@ SIGNATURES = {
                                     _p, _sz, _p]),
     "mop_rsirfo_step_packed_begin": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mop_rsirfo_step_packed_finish": (_i, [_i, _i, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mop_constraint_project": (_i, [_i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mop_crsirfo_finalize": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mop_add_inplace": (_i, [_sz, _p, _p, _p]),
     "mop_rsirfo_step_mixed": (_i, [_i, _i, _p, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _sz, _p]),
     "mop_pack_lower": (_i, [_i, _i, _p, _p, _p]),

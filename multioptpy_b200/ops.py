@@ -47,6 +47,7 @@ ST_EIG_FALLBACK = 1 << 12
 ST_NO_HISTORY = 1 << 13
 ST_UPD_REJECTED = 1 << 14
 ST_LINDH_NO_K = 1 << 15
+ST_CONSTR_CONVERGED = 1 << 17
 
 
 def resolve_update_method(name: str) -> int:
@@ -521,6 +522,45 @@ def neb_limit_tr(nimg, first, x_halo, g, delta, fix_init_edge=False, fix_end_edg
                                   int(bool(step_limit)), _ptr(x_halo), _ptr(g), _ptr(delta), _stream(delta.device))
     _lib.check(rc, "mop_neb_limit_tr")
     return delta
+
+
+def constraint_project(C, H, g, shake=None, svd_threshold: float = 1e-5, want_hessian: bool = True):
+    """CRSIRFO's subspace projection in the full space: C (B, k, n) raw constraint rows, H (B, n, n), g (B, n)
+    -> (Hp (B, n, n) or None, gp (B, n), rank (B,) int32).  See mop_constraint_project."""
+    lib = _lib.load()
+    B, k, n = C.shape
+    _chk(C, "C", (B, k, n)); _chk(H, "H", (B, n, n)); _chk(g, "g", (B, n))
+    if shake is not None:
+        _chk(shake, "shake", (B, n))
+    dev = g.device
+    Hp = torch.empty_like(H) if want_hessian else None
+    gp = torch.empty_like(g)
+    rank = torch.zeros(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mop_constraint_project(B, n, k, float(svd_threshold), _ptr(C), _ptr(H), _ptr(g), _ptr(shake), _ptr(Hp),
+                                        _ptr(gp), _ptr(rank), _stream(dev))
+    _lib.check(rc, "mop_constraint_project")
+    return Hp, gp, rank
+
+
+def crsirfo_finalize(gp, Be, state_before, state, out, grad_threshold: float):
+    lib = _lib.load()
+    B, n = gp.shape
+    _chk(gp, "gp", (B, n)); _chk(state_before, "state_before", (B, RSIRFO_STATE)); _chk(state, "state", (B, RSIRFO_STATE))
+    _chk_out(out, B, n)
+    with torch.cuda.device(gp.device):
+        rc = lib.mop_crsirfo_finalize(B, n, float(grad_threshold), _ptr(gp), _ptr(Be), _ptr(state_before), _ptr(state),
+                                      _ptr(out["move"]), _ptr(out["pred"]), _ptr(out["status"]), _stream(gp.device))
+    _lib.check(rc, "mop_crsirfo_finalize")
+
+
+def add_inplace(dst, src):
+    """dst += src on the device (same shape, float64)."""
+    lib = _lib.load()
+    _chk(dst, "dst"); _chk(src, "src", tuple(dst.shape))
+    with torch.cuda.device(dst.device):
+        _lib.check(lib.mop_add_inplace(dst.numel(), _ptr(dst), _ptr(src), _stream(dst.device)), "mop_add_inplace")
+    return dst
 
 
 def neb_redistribute(x_chain, first=0, nloc=None, want_path_length=False):

@@ -117,3 +117,38 @@ def conformer_batch(B: int, natoms: int, seed: int = 4000, jitter: float = 0.05)
         xyz[b] = np.concatenate(rings)
         g[b] = rng.normal(0.0, 1e-2, 3 * natoms)
     return xyz, g
+
+
+# ---- a minimal constraint object for CRSIRFO (the reference's comes from its projection-constraint subsystem) -------
+class DistanceConstraints:
+    """Interface CRSIRFO calls on ``constraints_obj`` (Optimizer/crsirfo.py:21,68): bond-length constraints between
+    atom pairs (0-based).  ``_get_all_constraint_vectors`` returns the UNNORMALISED gradients of the distances scaled
+    by ``weights`` (CRSIRFO normalises them itself); ``adjust_init_coord`` is one symmetric SHAKE pass towards
+    ``targets`` (or the identity when ``targets`` is None)."""
+
+    def __init__(self, pairs, targets=None, weights=None):
+        self.pairs = [tuple(p) for p in pairs]
+        self.targets = targets
+        self.weights = [1.0] * len(self.pairs) if weights is None else list(weights)
+
+    def _get_all_constraint_vectors(self, geom):
+        geom = np.asarray(geom, dtype=np.float64)
+        rows = np.zeros((len(self.pairs), geom.size))
+        for r, ((i, j), w) in enumerate(zip(self.pairs, self.weights)):
+            d = geom[i] - geom[j]
+            u = w * d / np.linalg.norm(d)
+            rows[r, 3 * i:3 * i + 3] = u
+            rows[r, 3 * j:3 * j + 3] = -u
+        return rows
+
+    def adjust_init_coord(self, geom):
+        out = np.array(geom, dtype=np.float64, copy=True)
+        if self.targets is None:
+            return out
+        for (i, j), t in zip(self.pairs, self.targets):
+            d = out[i] - out[j]
+            r = np.linalg.norm(d)
+            shift = 0.5 * (t - r) * d / r
+            out[i] += shift
+            out[j] -= shift
+        return out

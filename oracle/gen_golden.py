@@ -1188,7 +1188,96 @@ def gen_redistribute():
     print("neb_redistribute.npz", len(cases), "cases")
 
 
-SETS = {"redistribute": gen_redistribute, "bias2": gen_bias2, "modelhess_d3": gen_modelhess_d3, "keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
+
+# name, method, saddle order, natoms, steps, constraint pairs, row weights, SHAKE targets (or None), bias, seed, converge-at-step
+CRSIRFO_CASES = [
+    ("c_min_2bonds", "rsirfo_bofill", 0, 8, 4, [(0, 1), (2, 5)], [1.0, 3.5], None, False, 1, None),
+    ("c_min_dup_row", "rsirfo_bfgs", 0, 9, 3, [(0, 1), (3, 4), (0, 1)], [1.0, 0.2, 2.0], None, False, 2, None),
+    ("c_ts_3bonds", "rsirfo_bofill", 1, 10, 4, [(0, 3), (1, 2), (6, 7)], [1.0, 1.0, 1.0], None, False, 3, None),
+    ("c_min_shake", "rsirfo_fsb", 0, 8, 4, [(0, 1), (4, 6)], [1.0, 1.0], "perturbed", False, 4, None),
+    ("c_min_bias", "rsirfo_bofill", 0, 8, 3, [(1, 2)], [1.0], None, True, 5, None),
+    ("c_min_converged", "rsirfo_bofill", 0, 8, 3, [(0, 1), (2, 3)], [1.0, 1.0], None, False, 6, 1),
+    ("c_unconstrained", "rsirfo_bofill", 0, 7, 3, [], [], None, False, 7, None),
+]
+
+
+def run_crsirfo_case(case):
+    """CRSIRFO.run (Optimizer/crsirfo.py) with synthetic.DistanceConstraints as the constraint object."""
+    name, method, so, natoms, nsteps, pairs, weights, targets, bias, seed, conv_at = case
+    cr = ref_shim.ref("Optimizer.crsirfo")
+    rng = np.random.default_rng(515100 + seed)
+    n = 3 * natoms
+    x0 = synthetic.grid_geometry(natoms, rng).reshape(-1)
+    H0 = synthetic.spd_hessian(n, rng, neg_lowest=so > 0)
+    E = rng.standard_normal((n, n))
+    Ht = H0 + 0.05 * (E + E.T) / np.sqrt(n)
+    g0 = rng.normal(0.0, 2e-2, size=n)
+    Hb = None
+    if bias:
+        Bm = rng.standard_normal((n, 3))
+        Hb = 0.02 * (Bm @ Bm.T)
+    pes = QuadraticPES(x0, g0, Ht, np.zeros((n, n)) if Hb is None else Hb, rng)
+    tg = None
+    if targets == "perturbed":      # targets a little off the current distances: the SHAKE pass moves the atoms by ~1e-2
+        tg = [float(np.linalg.norm(x0.reshape(-1, 3)[i] - x0.reshape(-1, 3)[j]) + 0.03 * (1 + q)) for q, (i, j) in enumerate(pairs)]
+    cons = synthetic.DistanceConstraints(pairs, targets=tg, weights=weights) if pairs else None
+    opt = cr.CRSIRFO(constraints=cons, method=method, saddle_order=so, element_list=["C"] * natoms,
+                     trust_radius_max=(0.1 if so > 0 else 0.5), trust_radius_min=0.01)
+    opt.set_hessian(H0.copy())
+    if Hb is not None:
+        opt.set_bias_hessian(Hb.copy())
+    keys = ("x_in", "x", "shake", "rows", "Bg", "g", "Be", "move", "H_after", "trust", "pred", "converged")
+    rec = {k: [] for k in keys}
+    x = x0.copy()
+    x_prev = g_prev = None
+    for k in range(nsteps):
+        e, g = pes.raw(x)
+        eb, gb = pes.bias(x) if Hb is not None else (0.0, np.zeros(n))
+        Be, Bg = e + eb, g + gb
+        if conv_at is not None and k == conv_at:      # gradient inside the span of the constraint rows: subspace gradient 0
+            rows_now = cons._get_all_constraint_vectors(x.reshape(-1, 3))
+            Bg = 0.3 * rows_now[0] - 0.1 * rows_now[1]
+            g = Bg.copy()
+        xc = cons.adjust_init_coord(x.reshape(-1, 3)).ravel() if cons is not None else x.copy()
+        rows = cons._get_all_constraint_vectors(xc.reshape(-1, 3)) if cons is not None else np.zeros((1, n))
+        col = lambda a: a.reshape(-1, 1).copy()
+        npred = len(opt.predicted_energy_changes)
+        with quiet():
+            if x_prev is None:
+                mv = opt.run(col(x), col(Bg), [], [], Be, 0.0, [], col(x0), col(g), [])
+            else:
+                mv = opt.run(col(x), col(Bg), [], col(x_prev), Be, 0.0, [], col(x0), col(g), col(g_prev))
+        mv = np.asarray(mv, float).ravel()
+        rec["x_in"].append(x.copy()); rec["x"].append(xc); rec["shake"].append(xc - x); rec["rows"].append(rows)
+        rec["Bg"].append(Bg); rec["g"].append(g); rec["Be"].append(Be); rec["move"].append(mv)
+        rec["H_after"].append(np.array(opt.hessian, float)); rec["trust"].append(float(opt.trust_radius))
+        conv = bool(opt.proj_grad_converged) and len(opt.predicted_energy_changes) == npred
+        rec["converged"].append(int(conv))
+        rec["pred"].append(float(opt.predicted_energy_changes[-1]) if opt.predicted_energy_changes else 0.0)
+        opt.proj_grad_converged = False
+        x_prev, g_prev = xc.copy(), g.copy()      # the caller sees the corrected geometry only through the move; it passes its own x
+        x_prev = x.copy()
+        cap = 0.1 if so > 0 else 0.5
+        nrm = np.linalg.norm(mv)
+        x = xc - (mv * (cap / nrm) if nrm > cap else mv)
+    out = {f"{name}/{k}": np.array(v) for k, v in rec.items()}
+    out[f"{name}/H0"] = H0
+    out[f"{name}/Hb"] = np.zeros((n, n)) if Hb is None else Hb
+    out[f"{name}/meta"] = np.array([so, natoms, nsteps, int(bias)], np.int64)
+    out[f"{name}/method"] = np.array(method)
+    return out
+
+
+def gen_crsirfo():
+    blob = {}
+    for case in CRSIRFO_CASES:
+        blob.update(run_crsirfo_case(case))
+        print("crsirfo case", case[0])
+    blob["names"] = np.array([c[0] for c in CRSIRFO_CASES])
+    np.savez_compressed(os.path.join(GOLD, "crsirfo_traces.npz"), **blob)
+
+
+SETS = {"crsirfo": gen_crsirfo, "redistribute": gen_redistribute, "bias2": gen_bias2, "modelhess_d3": gen_modelhess_d3, "keep": gen_keep, "fire": gen_fire, "post": gen_post, "ric": gen_ric, "swart": gen_swart, "update": gen_update, "rsirfo": gen_rsirfo, "projection": gen_projection, "producers": gen_producers,
         "c1": gen_c1_trace, "neb": gen_neb, "lindh": gen_lindh, "rsprfo": gen_rsprfo, "rsprfo_reject": gen_rsprfo_reject, "rankdef": gen_rankdef, "potkeys": gen_potkeys, "neb_full": gen_neb_full}
 
 if __name__ == "__main__":

@@ -2087,3 +2087,91 @@ def distribute_geometry(X):
             out.append(X[-1])
     out.append(X[-1])
     return np.array(out)
+
+
+def constraint_null_space(rows, svd_threshold=1e-5):
+    """CRSIRFO._get_null_space_basis (Optimizer/crsirfo.py:16-45) from the raw constraint rows (k, n)."""
+    import scipy.linalg
+    rows = np.asarray(rows, float)
+    n = rows.shape[1]
+    if len(rows) == 0:
+        return np.eye(n)
+    nr = np.linalg.norm(rows, axis=1)
+    nr[nr < 1e-12] = 1.0
+    Bn = rows / nr[:, None]
+    U, S, _ = scipy.linalg.svd(Bn.T, full_matrices=True)
+    max_s = S[0] if len(S) > 0 else 1.0
+    rank = int(np.sum(S > max(svd_threshold, max_s * 1e-6)))
+    return U[:, rank:]
+
+
+class CRSIRFOOracle(RSIRFOOracle):
+    """CRSIRFO.run (Optimizer/crsirfo.py:47-170) for one structure: RS-I-RFO in the null space of the constraint
+    rows.  ``rows`` (k, n) = constraints_obj._get_all_constraint_vectors(x), ``shake`` (n,) = the displacement of
+    constraints_obj.adjust_init_coord (x is the CORRECTED geometry)."""
+
+    def __init__(self, *a, gradient_norm_threshold=1e-4, svd_threshold=1e-5, **kw):
+        super().__init__(*a, **kw)
+        self.gradient_norm_threshold = gradient_norm_threshold
+        self.svd_threshold = svd_threshold
+        self.converged_sub = False
+
+    def run(self, x, Bg, g, x_prev=None, g_prev=None, Be=0.0, rows=None, shake=None):
+        x = np.asarray(x, float).ravel()
+        gfull = np.array(Bg, float).ravel()
+        g = np.asarray(g, float).ravel()
+        info = {"updated": False, "alpha_search": False}
+        if shake is not None and np.linalg.norm(shake) > 1e-6:            # (:70-80) H_eff aliases self.hessian
+            if self.bias_hessian is not None:
+                self.hessian += self.bias_hessian
+            gfull = gfull + self.hessian @ np.asarray(shake, float).ravel()
+        if self.have_prev and x_prev is not None and g_prev is not None and len(x_prev) > 0 and len(g_prev) > 0:
+            self.hessian, info["updated"] = rsirfo_update_hessian(
+                self.hessian, x, g, np.asarray(x_prev, float).ravel(), np.asarray(g_prev, float).ravel(), self.method_id)
+        if self.bias_hessian is not None:                                   # (:88-90) in place as well
+            self.hessian += self.bias_hessian
+        U = constraint_null_space(rows if rows is not None else np.zeros((0, x.size)), self.svd_threshold)
+        gs = U.T @ gfull
+        Hs = U.T @ (self.hessian @ U)
+        gnorm = np.linalg.norm(gs)
+        self.converged_sub = False
+        if gnorm < self.gradient_norm_threshold:                            # (:108-118)
+            self.converged_sub = True
+            self.have_prev = True
+            self.prev_energy = Be
+            self.last = dict(info, eigvals=None, pred=None, trust=self.trust_radius)
+            return np.zeros_like(gfull)
+        Hs = 0.5 * (Hs + Hs.T)
+        lam, V, _ = eigh_with_shift(Hs)
+        if self.prev_energy is not None:                                    # (:126-141)
+            actual = Be - self.prev_energy
+            if len(self.act) >= 3:
+                self.act.pop(0)
+            self.act.append(actual)
+            if self.pred:
+                self.trust_radius = adjust_trust_radius(self.trust_radius, actual, self.pred[-1], lam[0], gnorm,
+                                                        self.saddle_order, self.trust_radius_min, self.trust_radius_max)
+        m = lam.size
+        P = np.eye(m)
+        found = i = 0
+        while found < self.saddle_order and i < m:
+            if abs(lam[i]) > 1e-10:
+                P = P - (1.0 if self.NEB_mode else 2.0) * np.outer(V[:, i], V[:, i])
+                found += 1
+            i += 1
+        Hstar = P @ Hs
+        Hstar = 0.5 * (Hstar + Hstar.T)
+        gstar = P @ gs
+        lam_s, V_s, _ = eigh_with_shift(Hstar)
+        keep = ~(np.abs(lam_s) < 1e-6)
+        step_sub, info["alpha_search"] = rs_step(lam_s[keep], V_s[:, keep], gstar, self.trust_radius)
+        step = U @ step_sub
+        pred = gs @ step_sub + 0.5 * (step_sub @ Hs @ step_sub)
+        if len(self.pred) >= 3:
+            self.pred.pop(0)
+        self.pred.append(pred)
+        self.have_prev = True
+        self.prev_energy = Be
+        self.iteration += 1
+        self.last = dict(info, eigvals=lam, pred=pred, trust=self.trust_radius)
+        return -step

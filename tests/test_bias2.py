@@ -100,7 +100,11 @@ def test_cuda_aggregator_matches_reference(golden_dir):
         bpc = BiasPotentialCalculation(device="cuda:0")
         bg, Be, Bg, bh = bpc.main(0.0, np.zeros_like(xyz), xyz, elems, force_data_for(cfg))
         Eref = float(z[f"{name}/E"])
-        assert abs(Be - Eref) <= RTOL * max(abs(Eref), 1e-300), name
+        # angle_v2_lin180 sits 2e-4 rad from its linear equilibrium: E = k (1 + cos) is 5e-9 Hartree, formed from
+        # 1 + u with u = -1 + 2e-8 - a relative rounding error of 1e-16 / 2e-8 in ANY evaluation order (gradient and
+        # Hessian are O(1e-4) and O(1) there and keep the 1e-10 bar)
+        etol = 1e-7 if name == "angle_v2_lin180" else RTOL
+        assert abs(Be - Eref) <= etol * max(abs(Eref), 1e-300), name
         if np.linalg.norm(z[f"{name}/g"]) == 0.0:
             assert np.all(bg == 0.0) and np.all(bh == 0.0), name
         else:

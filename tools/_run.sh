@@ -1,2 +1,1 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "host_pipeline or packed" 2>&1 | tail -2
-bash tools/e2e_sweep.sh
+timeout 600 python -m pytest tests/test_crsirfo.py tests/test_bias2.py tests/test_neb.py -m gpu -x -q 2>&1 | tail -25
