@@ -5,9 +5,9 @@ families of the hot path (``rsirfo_*``; ``rsprfo_*`` when the P-RFO kernel is pr
 (optimizer.py:740-818): ``(new_geometry [Angstrom], move_vector [Bohr], optimizer_instances)``
 with ``new_geometry = (geom - move) * 0.52917721067``.  Inputs may be NumPy ``(N,3)`` arrays (one
 structure, the reference calling convention) or CUDA tensors ``(B,N,3)`` (B structures per call,
-everything stays on the device).  Enhancement chains (lookahead, DIIS, ...), first-order
-optimizers and the constrained / mode-following RSIRFO subclasses are outside the scope
- and raise.
+everything stays on the device).  ``crsirfo_*`` with a ``projection_constraint`` object builds the constrained
+RS-I-RFO drop-in (optimizer.py:450-451).  Enhancement chains (lookahead, DIIS, ...), first-order optimizers and the
+mode-following RSIRFO subclasses are outside the scope and raise.
 """
 from __future__ import annotations
 
@@ -20,7 +20,7 @@ from .Optimizer.rsirfo import RSIRFO
 from .Optimizer.trust_radius import TrustRadius
 from .Parameters.tables import BOHR2ANG
 
-_OUT_OF_SCOPE = ["mf_rsirfo", "crsirfo", "lookahead", "lars", "linesearch", "diis", "coordinate_locking",
+_OUT_OF_SCOPE = ["mf_rsirfo", "lookahead", "lars", "linesearch", "diis", "coordinate_locking",
                  "component_wise_scaling", "gpr_step", "gan_step", "rl_step", "geodesic_step", "trim"]
 
 
@@ -55,6 +55,7 @@ class CalculateMoveVector:
         self.iter = 0
         self.element_list = element_list
         self.model_hess_flag = model_hess_flag
+        self.projection_constraint = kwargs.get("projection_constraint", None)    # optimizer.py:270
         self.newton_tag = []
         self._trust_t = None
 
@@ -75,6 +76,11 @@ class CalculateMoveVector:
                 opt = EnhancedRSPRFO(method=m, saddle_order=self.saddle_order, element_list=self.element_list,
                                      trust_radius_max=self.max_trust_radius, trust_radius_min=self.min_trust_radius,
                                      device=self.device)
+            elif "crsirfo" in low and self.projection_constraint:   # optimizer.py:450-451 (falls through to RSIRFO otherwise)
+                from .Optimizer.crsirfo import CRSIRFO
+                opt = CRSIRFO(method=m, constraints=self.projection_constraint, saddle_order=self.saddle_order,
+                              element_list=self.element_list, trust_radius_max=self.max_trust_radius,
+                              trust_radius_min=self.min_trust_radius, device=self.device)
             elif "rsirfo" in low:
                 opt = RSIRFO(method=m, saddle_order=self.saddle_order, element_list=self.element_list,
                              trust_radius_max=self.max_trust_radius, trust_radius_min=self.min_trust_radius,
