@@ -56,7 +56,7 @@ int mop_launch_front_tridiag_blk(int B, int n, int method, const int32_t* method
                                  const double* x, const double* xp, const double* g, const double* gprev,
                                  const double* Bg, const double* state, int state_stride, double* gp_out,
                                  int32_t* status, double* Vh, double* dd, double* ee, double* tau, double* gq, int* flag,
-                                 cudaStream_t stream);
+                                 double* hand, cudaStream_t stream);
 int mop_spectrum_step_supported(int n);
 int mop_launch_spectrum_step(int B, int n, int saddle_order, int neb_mode, double tmin, double tmax,
                              const double* Vh, double* Z, double* Dm, const double* pd, const double* pe,
@@ -281,7 +281,11 @@ static int rsirfo_step_fused(int B, int n, int method, const int32_t* method_per
                                       0, packed, H + o * hs, Hbias ? Hbias + o * hs : nullptr, x + on,
                                       x_prev ? x_prev + on : nullptr, g + on, g_prev ? g_prev + on : nullptr, Bg + on,
                                       state + o * MOP_RSIRFO_STATE, MOP_RSIRFO_STATE, gp + on, status + o,
-                                      Vh + o * n * n, pd + on, pe + on, pt + on, pg + on, pflag + o, stream);
+                                      Vh + o * n * n, pd + on, pe + on, pt + on, pg + on, pflag + o,
+                                      // staged reduction through the pivot slab (free until the spectrum kernel runs) when the
+                                      // whole batch is reduced at once; a chunk of a streamed batch (phase 1 alone) is about one
+                                      // wave of the first stage and would leave the denser later stages mostly empty
+                                      phase == 3 ? Dm + o * n * n : nullptr, stream);
     if (rc != MOP_OK) return rc;
   }
   if (!(phase & 2)) return MOP_OK;

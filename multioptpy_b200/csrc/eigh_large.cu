@@ -679,7 +679,7 @@ extern "C" int mop_priv_large_cluster(int cl) {
 int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, double* ee, double* tau,
                                int cluster_ctas, cudaStream_t stream);
 int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
-                           double* tau, double* gq, int* flag, cudaStream_t stream);
+                           double* tau, double* gq, int* flag, double* hand, cudaStream_t stream);
 
 int mop_large_supported(int n) { return n >= 3 && n <= mop::LG_MAX_N; }
 
@@ -742,7 +742,7 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     // cluster kernel; same outputs (reflector rows with explicit unit entries, d, e, tau)
     double* gq_dummy = a.pbuf;
     int* flag = (int*)(a.pbuf + (size_t)B * n);
-    int rc = mop_launch_tridiag_blk(B, n, a.A, nullptr, a.Vh, a.dd, a.ee, a.tau, gq_dummy, flag, stream);
+    int rc = mop_launch_tridiag_blk(B, n, a.A, nullptr, a.Vh, a.dd, a.ee, a.tau, gq_dummy, flag, a.A /* staged hand-over in place */, stream);
     if (rc != MOP_OK) return rc;
   } else {
     int rc = mop_launch_tridiag_cluster(B, n, a.A, a.Vh, a.dd, a.ee, a.tau, g_lg_cluster, stream);

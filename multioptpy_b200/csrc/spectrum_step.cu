@@ -740,7 +740,7 @@ int mop_launch_spectrum_step(int B, int n, int saddle_order, int neb_mode, doubl
 
 // ---- the shared-memory spectral path, 3 <= n <= 160: blocked tridiagonalisation + spectrum / step ------------------
 int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
-                           double* tau, double* gq, int* flag, cudaStream_t stream);
+                           double* tau, double* gq, int* flag, double* hand, cudaStream_t stream);
 
 int mop_tridiag_supported(int n) { return n >= 3 && n <= mop::SP_MAX_N; }
 // Vh | Dm | d, e, tau, gq | flag
@@ -770,7 +770,7 @@ int mop_launch_rsirfo_fused(int B, int n, int saddle_order, int neb_mode, double
   double* pt = pd + 2 * (size_t)B * n;
   double* pg = pd + 3 * (size_t)B * n;
   int* pflag = (int*)(pd + 4 * (size_t)B * n);
-  int rc = mop_launch_tridiag_blk(B, n, Hp, gp, Vh, pd, pe, pt, pg, pflag, stream);
+  int rc = mop_launch_tridiag_blk(B, n, Hp, gp, Vh, pd, pe, pt, pg, pflag, Dm /* free until the spectrum kernel */, stream);
   if (rc != MOP_OK) return rc;
   return mop_launch_spectrum_step(B, n, saddle_order, neb_mode, tmin, tmax, Vh, zbuf, Dm, pd, pe, pt, pg, pflag, Bg, Be,
                                   state, move, evals_out, pred, status, stream);

@@ -41,6 +41,15 @@ struct PkArgs {
   double* gq;        // [B][n] Q^T gp
   int* flag;         // [B] 0 normal, 1 zero matrix, 2 non-finite input
   long long* dbg;    // optional [B][16] phase cycles
+  // Staged reduction (see mop_launch_front_tridiag_blk): this launch reduces the trailing block of rows / columns
+  // row0 .. nfull-1 (n = nfull - row0 is the LOCAL size; d, e, tau, gq, Vh are indexed in the full matrix), starting
+  // from the state a previous stage left in `hin` (null: from A / the fused front end) and - when `hout` is set -
+  // stopping at the panel boundary `kstop` (local column, a multiple of TB_NB), where it leaves the trailing triangle,
+  // the raw next column and Q^T g of the rows >= kstop in `hout` for the next, smaller and more densely resident stage.
+  int nfull, row0, kstop;
+  const double* hin;   // [B][hstride]: packed triangle (n (n + 1) / 2, rounded up to even) | uu [n] | gq [n]
+  double* hout;
+  size_t hstride;
 };
 
 // Fused front end (FUSED kernels): the Hessian update, its write-back and the TR/ROT projection run on the triangle in
@@ -64,6 +73,7 @@ struct FrontArgs {
   int32_t* status;       // [B]
 };
 
+constexpr int TB_STAGE_MIN = 24;  // staged reduction: a stage is only split off while at least this many rows remain behind it
 constexpr int TB_NB = 6;   // reflectors per panel: 4 scalars + 2 * NB panel products = the 16 slots of one reduction
 constexpr int TB_WS = 10;  // doubles per row of the W panel: 80-byte rows, eight 128-bit row reads hit 32 banks once
 
@@ -587,8 +597,11 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
   double* pub = tot + 16 * NW;      // [4]  z_{k+1}, c_{k+1}
   double* s_rb = pub + 4;           // [64] block_sum_k<2> scratch
   int parity = 0, parity2 = 0;
-  const double* Ain = FUSED ? nullptr : a.A + (size_t)b * n * n;
-  double* Vh = a.Vh + (size_t)b * n * n;
+  const int nf = a.nfull ? a.nfull : n, r0 = a.row0;   // full size and offset of this stage in the full matrix
+  const size_t ob = (size_t)b * nf + r0;               // d, e, tau, gq of local row i live at ob + i
+  const bool resume = !FUSED && a.hin != nullptr;
+  const double* Ain = (FUSED || resume) ? nullptr : a.A + (size_t)b * n * n;
+  double* Vh = a.Vh + (size_t)b * nf * nf + (size_t)r0 * nf + r0;   // reflector k in row k: Vh[k * nf + i]
 
   double pn[2] = {0.0, 0.0};
   double gp_mine = 0.0;
@@ -597,6 +610,18 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
     fused_front<NW>(f, n, np, b, L, Wp, &gp_mine);
     for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
     for (int e = tid; e < n * (n + 1) / 2; e += THREADS) pn[0] = fma(L[e], L[e], pn[0]);
+  } else if (resume) {
+    // ---- continue a reduction an earlier stage handed over (its flagged structures are finished already) ----
+    if (a.flag[b] != 0) return;
+    for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
+    __syncthreads();
+    const double* h = a.hin + (size_t)b * a.hstride;
+    for (int e = tid; e < n * (n + 1) / 2; e += THREADS) L[e] = h[e];
+    for (int i = tid; i < n; i += THREADS) {
+      uu[i] = h[nl + i];
+      gq[i] = h[nl + n + i];
+    }
+    __syncthreads();
   } else {
     // everything behind the triangle starts finite (the batched symv multiplies a few words of it by zero)
     for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
@@ -611,24 +636,26 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
       }
     }
   }
-  __syncthreads();
-  for (int i = tid; i < n; i += THREADS) gq[i] = FUSED ? (i == tid ? gp_mine : 0.0) : (a.gp ? a.gp[(size_t)b * n + i] : 0.0);
-  block_sum_k<2>(pn, s_rb, parity2);
-  const double fro = sqrt(pn[0]);
-  const bool nonfinite = !isfinite(fro), trivial = nonfinite || fro == 0.0;
-  if (tid == 0) a.flag[b] = nonfinite ? 2 : (fro == 0.0 ? 1 : 0);
-  if (trivial || n <= 2) {
-    for (int i = tid; i < n; i += THREADS) {
-      a.dd[(size_t)b * n + i] = nonfinite ? NAN : (trivial ? 0.0 : L[tri0(i) + i]);
-      a.ee[(size_t)b * n + i] = (!trivial && i + 1 < n) ? L[tri0(i + 1) + i] : 0.0;
-      a.tau[(size_t)b * n + i] = 0.0;
-      a.gq[(size_t)b * n + i] = gq[i];
+  if (!resume) {
+    __syncthreads();
+    for (int i = tid; i < n; i += THREADS) gq[i] = FUSED ? (i == tid ? gp_mine : 0.0) : (a.gp ? a.gp[(size_t)b * n + i] : 0.0);
+    block_sum_k<2>(pn, s_rb, parity2);
+    const double fro = sqrt(pn[0]);
+    const bool nonfinite = !isfinite(fro), trivial = nonfinite || fro == 0.0;
+    if (tid == 0) a.flag[b] = nonfinite ? 2 : (fro == 0.0 ? 1 : 0);
+    if (trivial || n <= 2) {
+      for (int i = tid; i < n; i += THREADS) {
+        a.dd[ob + i] = nonfinite ? NAN : (trivial ? 0.0 : L[tri0(i) + i]);
+        a.ee[ob + i] = (!trivial && i + 1 < n) ? L[tri0(i + 1) + i] : 0.0;
+        a.tau[ob + i] = 0.0;
+        a.gq[ob + i] = gq[i];
+      }
+      return;
     }
-    return;
+    for (int i = tid; i < n; i += THREADS) uu[i] = i > 0 ? L[tri0(i)] : 0.0;  // raw column 0
+    if (tid == 0) a.dd[ob] = L[0];
+    __syncthreads();
   }
-  for (int i = tid; i < n; i += THREADS) uu[i] = i > 0 ? L[tri0(i)] : 0.0;  // raw column 0
-  if (tid == 0) a.dd[(size_t)b * n] = L[0];
-  __syncthreads();
 
   long long seg[5] = {0, 0, 0, 0, 0}, ts = DBG ? clock64() : 0;
 #define BSEG(q)                             \
@@ -814,13 +841,13 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
         const double un = ci - fma(vi, w0, wi);  // raw column k+1 after reflector k (d_{k+1} for the first row)
         Wp[i * WS + jj] = wi;
         L[Ti + k] = vi;
-        Vh[(size_t)k * n + i] = vi;
+        Vh[(size_t)k * nf + i] = vi;
         gq[i] = fma(-tk * vg, vi, gi);
         uu[i] = first ? 0.0 : un;
         if (first) {
-          a.ee[(size_t)b * n + k] = beta;
-          a.tau[(size_t)b * n + k] = tk;
-          a.dd[(size_t)b * n + k + 1] = un;
+          a.ee[ob + k] = beta;
+          a.tau[ob + k] = tk;
+          a.dd[ob + k + 1] = un;
         }
       }
     }
@@ -833,6 +860,24 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
       for (int l = 0; l < NB; ++l) Vi[l] = Wi[l] = 0.0;
       __syncthreads();
       BSEG(4);
+      if (a.hout && k0 == a.kstop) {
+        // ---- hand the trailing block over to the next stage: triangle of the rows / columns >= k0, raw column k0,
+        // Q^T g; the finished rows of Q^T g go to their final place ----
+        const int ks = k0, m = n - ks;
+        const size_t nlm = ((size_t)m * (m + 1) / 2 + 1) & ~(size_t)1;
+        double* h = a.hout + (size_t)b * a.hstride;
+        for (int r = ks + wid; r < n; r += NW) {
+          const double* src = L + tri0(r) + ks;
+          double* dst = h + tri0(r - ks);
+          for (int j = lane; j <= r - ks; j += 32) dst[j] = src[j];
+        }
+        for (int r = ks + tid; r < n; r += THREADS) {
+          h[nlm + r - ks] = uu[r];
+          h[nlm + m + r - ks] = gq[r];
+        }
+        for (int r = tid; r < ks; r += THREADS) a.gq[ob + r] = gq[r];
+        return;
+      }
     }
   }
   // e_{n-2} is the raw column n-2; the last diagonal element still lacks the reflectors of the open panel
@@ -840,13 +885,13 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
     const int i0 = n - 2, i1 = n - 1, jj = i0 - k0;
     double dl = L[tri0(i1) + i1];
     for (int l = 0; l < jj; ++l) dl -= 2.0 * L[tri0(i1) + k0 + l] * Wp[i1 * WS + l];
-    a.ee[(size_t)b * n + i0] = uu[i1];
-    a.tau[(size_t)b * n + i0] = 0.0;
-    a.dd[(size_t)b * n + i1] = dl;
-    a.ee[(size_t)b * n + i1] = 0.0;
-    a.tau[(size_t)b * n + i1] = 0.0;
+    a.ee[ob + i0] = uu[i1];
+    a.tau[ob + i0] = 0.0;
+    a.dd[ob + i1] = dl;
+    a.ee[ob + i1] = 0.0;
+    a.tau[ob + i1] = 0.0;
   }
-  for (int i2 = tid; i2 < n; i2 += THREADS) a.gq[(size_t)b * n + i2] = gq[i2];
+  for (int i2 = tid; i2 < n; i2 += THREADS) a.gq[ob + i2] = gq[i2];
   if (DBG && a.dbg && (tid == 0 || tid == 96))
     for (int q = 0; q < 5; ++q) a.dbg[(size_t)b * 16 + (tid == 0 ? 0 : 8) + q] = seg[q];
 #undef BSEG
@@ -883,34 +928,72 @@ static int dispatch_blk(int B, const mop::PkArgs& a, const mop::FrontArgs& f, cu
   }
 }
 
+// Staged reduction.  The column step is a latency chain whose cost barely depends on how many CTAs share the SM, and
+// the trailing matrix shrinks: whenever what is left fits a denser launch (m <= 120: three CTAs per SM, <= 88: five,
+// <= 64: eight, <= 32: sixteen) the reduction is handed over at the next panel boundary, through the two halves of an
+// n^2-double slab per structure (`hand`, [B][n][n]; it may alias the structure's own input matrix A: a CTA reads its A
+// before it writes its hand-over).  n = 150: columns 0-29 | 30-65 | 66-89 | 90-119 | 120-147.
+static int tb_stage_cols(int m) {  // columns a stage of local size m reduces before handing over (0: it finishes the job)
+  static const int fit[] = {120, 88, 64, 32};
+  for (int t : fit)
+    if (t < m) {
+      const int cols = ((m - t + mop::TB_NB - 1) / mop::TB_NB) * mop::TB_NB;
+      return (m - cols >= mop::TB_STAGE_MIN) ? cols : 0;
+    }
+  return 0;
+}
+
+template <bool FUSED>
+static int staged_blk(int B, mop::PkArgs a, const mop::FrontArgs& f, double* hand, cudaStream_t stream) {
+  const int n = a.n;
+  if (!hand || tb_stage_cols(n) == 0) return dispatch_blk<FUSED>(B, a, f, stream);
+  double* buf[2] = {hand, hand + (((size_t)n * n / 2) & ~(size_t)1)};
+  int c = 0, s = 0;
+  for (;; ++s) {
+    const int m = n - c, cols = tb_stage_cols(m);
+    const bool last = cols == 0;
+    a.n = m;
+    a.row0 = c;
+    a.kstop = cols;
+    a.hin = s ? buf[(s + 1) & 1] : nullptr;
+    a.hout = last ? nullptr : buf[s & 1];
+    a.hstride = (size_t)n * n;
+    const int rc = s ? dispatch_blk<false>(B, a, f, stream) : dispatch_blk<FUSED>(B, a, f, stream);
+    if (rc != MOP_OK || last) return rc;
+    c += cols;
+  }
+}
+
 // d, e, tau, gq: [B][n]; Vh: [B][n][n]; flag: [B]
+// hand: [B][n][n] scratch for the staged reduction (may be A itself; null: one launch)
 int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
-                           double* tau, double* gq, int* flag, cudaStream_t stream) {
+                           double* tau, double* gq, int* flag, double* hand, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   if (!mop_tridiag_blk_supported(n)) {
     mop_set_error("blocked tridiagonalisation: n = %d not supported (max 160)", n);
     return MOP_ERR_UNSUPPORTED;
   }
-  mop::PkArgs a{n, A, gp, Vh, dd, ee, tau, gq, flag, g_tb_dbg};
+  mop::PkArgs a{n, A, gp, Vh, dd, ee, tau, gq, flag, g_tb_dbg, n, 0, 0, nullptr, nullptr, 0};
   mop::FrontArgs f{};
-  return dispatch_blk<false>(B, a, f, stream);
+  return staged_blk<false>(B, a, f, a.dbg ? nullptr : hand, stream);
 }
 
 // Steps 1-3a of RSIRFO.run in one kernel: Hessian update (method, guards as mop_launch_hessian_update with mode 1),
 // write-back of H, TR/ROT projection of gradient (-> gp_out) and effective Hessian, tridiagonalisation of the latter.
-// packed != 0: H and Hbias are packed lower triangles [B][n (n + 1) / 2].
+// packed != 0: H and Hbias are packed lower triangles [B][n (n + 1) / 2].  hand: [B][n][n] doubles of scratch for the
+// staged reduction (null: one launch does the whole reduction).
 int mop_launch_front_tridiag_blk(int B, int n, int method, const int32_t* method_per, int guards, int grad_rule,
                                  int packed, double* H, const double* Hbias,
                                  const double* x, const double* xp, const double* g, const double* gprev,
                                  const double* Bg, const double* state, int state_stride, double* gp_out,
                                  int32_t* status, double* Vh, double* dd, double* ee, double* tau, double* gq, int* flag,
-                                 cudaStream_t stream) {
+                                 double* hand, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   if (!mop_tridiag_blk_supported(n) || n < 3) {
     mop_set_error("fused update + projection + tridiagonalisation: n = %d not supported (3 .. 160)", n);
     return MOP_ERR_UNSUPPORTED;
   }
-  mop::PkArgs a{n, nullptr, nullptr, Vh, dd, ee, tau, gq, flag, nullptr};
+  mop::PkArgs a{n, nullptr, nullptr, Vh, dd, ee, tau, gq, flag, nullptr, n, 0, 0, nullptr, nullptr, 0};
   mop::FrontArgs f{H, Hbias, x, xp, g, gprev, Bg, state, state_stride, method, guards, grad_rule, method_per, packed, gp_out, status};
-  return dispatch_blk<true>(B, a, f, stream);
+  return staged_blk<true>(B, a, f, hand, stream);
 }

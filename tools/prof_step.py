@@ -29,4 +29,16 @@ if dbg is not None:
     print("mean cycles per structure", d[:, :7].sum(1).mean())
     for q, nm in enumerate(names):
         print(f"  {nm:20s} mean {d[:, q].mean():10.0f}  p50 {np.median(d[:, q]):10.0f}  max {d[:, q].max():10.0f}")
+if os.environ.get("PROF"):   # per-kernel device times of one more step (torch.profiler)
+    from torch.profiler import profile, ProfilerActivity
+    H2 = T(H0); st2 = ops.new_rsirfo_state(B, 0.5, dev)
+    ops.rsirfo_step(H2, T(x0), T(g0), T(g0), st2, method=m, Be=zero)
+    xx1, gg1, xx0, gg0 = T(x1), T(g1), T(x0), T(g0)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        ops.rsirfo_step(H2, xx1, gg1, gg1, st2, method=m, x_prev=xx0, g_prev=gg0, Be=zero - 1e-3)
+        torch.cuda.synchronize()
+    for e in sorted(prof.events(), key=lambda e: e.time_range.start):
+        if e.device_time_total > 0:
+            print(f"{e.device_time_total/1e3:9.3f} ms  {e.name[:100]}")
 print("ok", int(out["status"].sum().item()))
