@@ -413,10 +413,11 @@ def run_b200(args, rank, world, local_rank):
                     "hessian_max_rel_diff_vs_resident": e2e_hdiff},
             "e2e_hessian_resident": {"value": e2e_res_val, "unit": UNIT,
                                      "h2d_bytes_per_step": 2 * B * n * 8, "d2h_bytes_per_step": B * n * 8},
-            "gpu_launches": 5 * K,   # fused update + projection + tridiagonalisation, spectrum + step, 3 (empty) fallback launches
+            # fused update + projection + staged tridiagonalisation (5 launches at n = 150), spectrum + step, 3 (empty) fallbacks
+            "gpu_launches": (int(_lib.load().mop_tridiag_stage_count(n)) + 4) * K,
             "roofline": {"bound": "fp64",
-                         "kernel": "k_tridiag_blk<5, fused> + k_spectrum_step = the timed step: Hessian update, write-back, "
-                                   "TR/ROT projection and blocked DMMA tridiagonalisation in one kernel, then spectrum, "
+                         "kernel": "k_tridiag_blk<5, fused> (+ its denser continuation stages <4>, <3>, <2>, <1>) + k_spectrum_step = the "
+                                   "timed step: Hessian update, write-back, TR/ROT projection and blocked DMMA tridiagonalisation, then spectrum, "
                                    "eigenvectors of T and the RFO step in the eigenbasis (the other launches of the step are "
                                    "empty fallbacks); duration = ms_per_step of the timed region",
                          "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s",

@@ -42,6 +42,7 @@ SIGNATURES = {
     "mop_constraint_project": (_i, [_i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mop_crsirfo_finalize": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mop_add_inplace": (_i, [_sz, _p, _p, _p]),
+    "mop_tridiag_stage_count": (_i, [_i]),
     "mop_rsirfo_step_mixed": (_i, [_i, _i, _p, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _sz, _p]),
     "mop_pack_lower": (_i, [_i, _i, _p, _p, _p]),

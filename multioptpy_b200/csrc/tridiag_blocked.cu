@@ -964,6 +964,13 @@ static int staged_blk(int B, mop::PkArgs a, const mop::FrontArgs& f, double* han
   }
 }
 
+// launches the staged reduction of an n x n matrix takes (1: not staged)
+extern "C" int mop_tridiag_stage_count(int n) {
+  int s = 1;
+  for (int m = n, cols; (cols = tb_stage_cols(m)) != 0; m -= cols) ++s;
+  return s;
+}
+
 // d, e, tau, gq: [B][n]; Vh: [B][n][n]; flag: [B]
 // hand: [B][n][n] scratch for the staged reduction (may be A itself; null: one launch)
 int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,

@@ -1,2 +1,1 @@
-python tools/prof_configs.py c4 24 2>&1 | grep -v Warn | head -14
-python tools/prof_configs.py sp 24 2>&1 | tail -10
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | grep -v Warning | tail -40

@@ -17,13 +17,14 @@ if [ "$part" = 1 ]; then
   cut -c1-300 gpurun_out/${P}_bench_reference_arm.json
 elif [ "$part" = 2 ]; then
   DIAG_B=1024 python tools/prof_step.py > gpurun_out/plain_prof.log 2>&1 &&
-    DIAG_B=1024 ncu --set full --clock-control none -k regex:"k_tridiag_blk|k_spectrum_step" -s 2 -c 2 \
+    DIAG_B=1024 ncu --set full --clock-control none -k regex:"k_tridiag_blk|k_spectrum_step" -s 6 -c 6 \
         -o gpurun_out/${P}_full python tools/prof_step.py > gpurun_out/ncu_full.log 2>&1
   CL=0 python tools/run_cluster_once.py 600 256 > gpurun_out/plain_cluster.log 2>&1 &&
     CL=0 ncu --set full --clock-control none -k regex:"k_lg_tridiag_blk|k_lg_trieig" -s 2 -c 2 \
         -o gpurun_out/${P}_c5 python tools/run_cluster_once.py 600 256 > gpurun_out/ncu_c5.log 2>&1
   ls -la gpurun_out/*.ncu-rep
 else
+  python tools/measure_rows.py > gpurun_out/${P}_row_table.md 2> gpurun_out/rows_err.log
   python tools/prof_producers.py > gpurun_out/plain_producers.log 2>&1 &&
     ncu --set full --clock-control none \
         -k regex:"k_swart|k_lindh|k_ric|k_model_hessian|k_afir|k_bias_terms|k_project_trrot" -c 12 \
