@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | grep -v Warning | tail -40
+python tools/prof_lindh_rows.py 2>&1 | grep -v Warn | tail -8

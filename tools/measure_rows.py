@@ -123,10 +123,13 @@ add("a14", "mop_swart_hessian (incl. projection)", B, gpu_ms(lambda: ops.swart_h
 
 B4, N4 = 8192, 24; n4 = 3 * N4
 el4 = synthetic.elements(N4, all_sulfur=True)
-xyz4 = T(geoms(B4, N4, seed=500))
+# config 4's own batch (S8-like crown-ring conformers).  Until round 2 this row used the dense all-sulfur GRID of the other
+# producer rows (every atom bonded to every neighbour: 99 bonds, 382 angles and a dihedral table that saturates its 1536
+# slots per structure - not a molecule): k_lindh takes 8.0 ms there against 1.8 ms on the conformers (tools/prof_lindh_rows.py).
+xyz4 = T(synthetic.conformer_batch(B4, N4, seed=4168)[0])
 prm = lindh_atom_params(el4)
 cpu = cpu_s(lambda: O.lindh_hessian_bkb(xyz4[0].cpu().numpy(), prm), reps=1)
-add("a15", "mop_lindh_hessian (force constants + B^T k B + projection)", B4, gpu_ms(lambda: ops.lindh_hessian(xyz4, prm)), 24 * n4 * n4, None, cpu, "config 4: 8192 x N=24")
+add("a15", "mop_lindh_hessian (force constants + B^T k B + projection)", B4, gpu_ms(lambda: ops.lindh_hessian(xyz4, prm)), 24 * n4 * n4, None, cpu, "config 4: 8192 x N=24 S8-like conformers (dense all-sulfur grid: 9.1 ms, dihedral table saturated)")
 f1 = torch.arange(0, N4 // 2, dtype=torch.int32, device=dev); f2 = torch.arange(N4 // 2, N4, dtype=torch.int32, device=dev)
 r32 = torch.tensor(radii_array(el4), dtype=torch.float32, device=dev); gam = torch.full((B4,), 100.0, dtype=torch.float64, device=dev)
 cpu = cpu_s(lambda: O.afir_egh(xyz4[0].cpu().numpy(), list(range(N4 // 2)), list(range(N4 // 2, N4)), radii_array(el4), 100.0), reps=1)
