@@ -614,12 +614,17 @@ int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, 
   // Cluster size: the column step is a latency chain, so throughput wants MANY small clusters (measured at n = 600,
   // 256 matrices: 102 / 75 / 69 ms per mop_eigh batch with 8 / 4 / 2 CTAs per matrix) and a small batch wants its
   // matrices spread over the whole GPU.
+  // A batch that does not fill the GPU takes the LARGEST cluster that still runs it as ONE wave (per-matrix latency
+  // 7.2 / 10.9 / 17 ms at 8 / 4 / 2 CTAs, n = 600): 32 matrices on 8-CTA clusters were two waves of 18 (14.4 ms), on
+  // 4-CTA clusters they are one (10.9 ms); 64 matrices: one wave of 2-CTA clusters instead of two of 4-CTA clusters.
   int CL = cluster_ctas;
-  if (CL != 1 && CL != 2 && CL != 4 && CL != 8) CL = 2 * B >= 148 ? 2 : (4 * B >= 148 ? 4 : 8);
+  if (CL != 1 && CL != 2 && CL != 4 && CL != 8) CL = 8 * B <= 148 ? 8 : (4 * B <= 148 ? 4 : 2);
   mop::TcArgs a{n, A, Vh, dd, ee, tau, g_tc_dbg, g_tc_ablate};
   // lower-triangle symv (half the L2 traffic) whenever the lane-private column sums fit the registers and the
   // cluster is small enough for the all-to-all of the per-CTA vectors
-  const bool sym = g_tc_sym && CL <= 4 && n % 2 == 0;
+  // (measured at n = 600: 2 CTAs 68.7 ms with / 73.9 without, 4 CTAs 80.4 with / 74.9 without per 256 matrices;
+  // 32 matrices on 4 CTAs 12.0 / 11.3 ms: the all-to-all of four per-CTA vectors costs more than the halved loads save)
+  const bool sym = g_tc_sym && CL <= 2 && n % 2 == 0;
   const size_t smem = sizeof(double) * mop::tc_smem_doubles(n, sym ? CL : 0);
   if (smem > 227 * 1024) {
     mop_set_error("blocked cluster tridiagonalisation: n = %d needs %zu bytes of shared memory", n, smem);
