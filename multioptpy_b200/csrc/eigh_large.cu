@@ -677,7 +677,7 @@ extern "C" int mop_priv_large_cluster(int cl) {
   return MOP_OK;
 }
 int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, double* ee, double* tau,
-                               int cluster_ctas, cudaStream_t stream);
+                               int cluster_ctas, double* gq_scratch, int* flag_scratch, cudaStream_t stream);
 int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
                            double* tau, double* gq, int* flag, double* hand, cudaStream_t stream);
 
@@ -745,7 +745,8 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     int rc = mop_launch_tridiag_blk(B, n, a.A, nullptr, a.Vh, a.dd, a.ee, a.tau, gq_dummy, flag, a.A /* staged hand-over in place */, stream);
     if (rc != MOP_OK) return rc;
   } else {
-    int rc = mop_launch_tridiag_cluster(B, n, a.A, a.Vh, a.dd, a.ee, a.tau, g_lg_cluster, stream);
+    int rc = mop_launch_tridiag_cluster(B, n, a.A, a.Vh, a.dd, a.ee, a.tau, g_lg_cluster, a.pbuf,
+                                        (int*)(a.pbuf + (size_t)B * n), stream);
     if (rc != MOP_OK) return rc;
   }
   {

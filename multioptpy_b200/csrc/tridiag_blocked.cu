@@ -964,6 +964,34 @@ static int staged_blk(int B, mop::PkArgs a, const mop::FrontArgs& f, double* han
   }
 }
 
+// Continue a reduction another kernel (the cluster tridiagonalisation, tridiag_cluster.cu) handed over: rows / columns
+// row0 .. nfull-1, state in region 0 of hand [B][hstride]; regions 1 and 2 (13312 doubles each) alternate between the
+// stages.  flag [B] must be zero, gq [B][nfull] is scratch (the rows >= row0 receive Q^T 0).
+int mop_launch_tridiag_blk_resume(int B, int nfull, int row0, double* hand, size_t hstride, double* Vh, double* dd,
+                                  double* ee, double* tau, double* gq, int* flag, cudaStream_t stream) {
+  constexpr size_t REGION = 13312;
+  if (B == 0) return MOP_OK;
+  if (nfull - row0 > 160 || nfull - row0 < 3 || row0 % mop::TB_NB != 0) {
+    mop_set_error("blocked tridiagonalisation: cannot resume %d rows at row %d", nfull - row0, row0);
+    return MOP_ERR_UNSUPPORTED;
+  }
+  mop::PkArgs a{nfull - row0, nullptr, nullptr, Vh, dd, ee, tau, gq, flag, nullptr, nfull, row0, 0, hand, nullptr, hstride};
+  mop::FrontArgs f{};
+  int c = row0;
+  for (int s = 0;; ++s) {
+    const int m = nfull - c, cols = tb_stage_cols(m);
+    const bool last = cols == 0;
+    a.n = m;
+    a.row0 = c;
+    a.kstop = cols;
+    a.hout = last ? nullptr : hand + REGION * (1 + (s & 1));
+    const int rc = dispatch_blk<false>(B, a, f, stream);
+    if (rc != MOP_OK || last) return rc;
+    a.hin = a.hout;
+    c += cols;
+  }
+}
+
 // launches the staged reduction of an n x n matrix takes (1: not staged)
 extern "C" int mop_tridiag_stage_count(int n) {
   int s = 1;

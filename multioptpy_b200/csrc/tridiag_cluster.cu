@@ -81,6 +81,12 @@ struct TcArgs {
   double* tau;  // [B][n]
   long long* dbg;  // optional [B][8] phase cycles (diagnostics)
   int ablate;      // diagnostics: bit0 no matrix loads, bit1 no column sums, bit2 no butterfly (results invalid)
+  // Hand-over to the shared-memory kernel: at the panel boundary kstop (n - kstop <= 160) the trailing lower triangle
+  // and the raw next column go to hout [B][hstride] in the layout k_tridiag_blk resumes from (tridiag_blocked.cu:
+  // packed triangle, rounded up to even | uu [m] | Q^T g [m] = 0) and the cluster exits.  0 / null: reduce to the end.
+  int kstop;
+  double* hout;
+  size_t hstride;
 };
 
 // sym_cl > 0: the symmetric variant with sym_cl CTAs per cluster (z slots per source CTA, row sums, per-warp column sums)
@@ -556,6 +562,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lg_tridiag_blk(TcArgs a) {
       tc_trailing_update<SYM>(A, Vp, Wp, n, np, k + 1, lane, gw, W);
       k0 = k + 1;
       cluster.sync();  // the updated rows are in L2 before anyone reads them
+      if (a.hout && k0 == a.kstop) {
+        const int m = n - k0;
+        const size_t nlm = ((size_t)m * (m + 1) / 2 + 1) & ~(size_t)1;
+        double* h = a.hout + (size_t)b * a.hstride;
+        for (int r = k0 + gw; r < n; r += W) {
+          const double* src = A + (size_t)r * n + k0;
+          double* dst = h + (((size_t)(r - k0) * (r - k0 + 1)) >> 1);
+          for (int j = lane; j <= r - k0; j += 32) dst[j] = __ldcg(src + j);
+        }
+        if (cr == 0)
+          for (int r = k0 + tid; r < n; r += THREADS) {
+            h[nlm + r - k0] = uu[r];
+            h[nlm + m + r - k0] = 0.0;
+          }
+        cluster.sync();  // nobody leaves while a peer may still store into its shared memory
+        return;
+      }
       if (SYM) {
         for (int i = k0 + tid; i < n; i += THREADS) diag[i] = __ldcg(A + (size_t)i * n + i);
         __syncthreads();
@@ -585,6 +608,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_lg_tridiag_blk(TcArgs a) {
 
 }  // namespace mop
 
+// tridiag_blocked.cu: continue a reduction from the state the cluster kernel left at hand [B][hstride] (region 0)
+constexpr size_t MOP_TB_RESUME_REGION = 13312;  // doubles per hand-over region: triangle of 160 rows + 2 x 160, rounded
+int mop_launch_tridiag_blk_resume(int B, int nfull, int row0, double* hand, size_t hstride, double* Vh, double* dd,
+                                  double* ee, double* tau, double* gq, int* flag, cudaStream_t stream);
+
 static long long* g_tc_dbg = nullptr;
 static int g_tc_ablate = 0;
 extern "C" int mop_priv_tridiag_cluster_ablate(int mask) {
@@ -604,8 +632,9 @@ extern "C" int mop_priv_tridiag_cluster_timing(void* buf) {
 int mop_tridiag_cluster_supported(int n) { return n >= 3 && n <= 1024; }
 
 // A: [B][n][n] symmetric working copies (destroyed); Vh: [B][n][n]; dd, ee, tau: [B][n].  cluster_ctas: 8 (or 4, 2, 1).
+// gq_scratch [B][n] doubles + flag_scratch [B] ints (or null: no hand-over to the shared-memory kernel)
 int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, double* ee, double* tau,
-                               int cluster_ctas, cudaStream_t stream) {
+                               int cluster_ctas, double* gq_scratch, int* flag_scratch, cudaStream_t stream) {
   if (B == 0) return MOP_OK;
   if (!mop_tridiag_cluster_supported(n)) {
     mop_set_error("blocked cluster tridiagonalisation: n = %d not supported (3 .. 1024)", n);
@@ -619,7 +648,21 @@ int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, 
   // 4-CTA clusters they are one (10.9 ms); 64 matrices: one wave of 2-CTA clusters instead of two of 4-CTA clusters.
   int CL = cluster_ctas;
   if (CL != 1 && CL != 2 && CL != 4 && CL != 8) CL = 8 * B <= 148 ? 8 : (4 * B <= 148 ? 4 : 2);
-  mop::TcArgs a{n, A, Vh, dd, ee, tau, g_tc_dbg, g_tc_ablate};
+  mop::TcArgs a{n, A, Vh, dd, ee, tau, g_tc_dbg, g_tc_ablate, 0, nullptr, 0};
+  // The last <= 160 rows go to the staged shared-memory kernel (2 - 16 matrices per SM instead of one cluster of SMs per
+  // matrix; every column there costs the cluster a fixed ~12 k cycles).  The hand-over buffers are the top rows of the
+  // matrix's own slab - finished, never read again - so the slab must be big enough that they stay clear of the rows
+  // >= kstop the copy reads.
+  int kstop = 0;
+  if (gq_scratch && flag_scratch && !g_tc_dbg && !g_tc_ablate) {
+    kstop = ((n - 160 + mop::TC_NB - 1) / mop::TC_NB) * mop::TC_NB;
+    if (kstop < mop::TC_NB || n - kstop < 24 || (size_t)kstop * n < 3 * MOP_TB_RESUME_REGION) kstop = 0;
+  }
+  if (kstop) {
+    a.kstop = kstop;
+    a.hout = A;
+    a.hstride = (size_t)n * n;
+  }
   // lower-triangle symv (half the L2 traffic) whenever the lane-private column sums fit the registers and the
   // cluster is small enough for the all-to-all of the per-CTA vectors
   // (measured at n = 600: 2 CTAs 68.7 ms with / 73.9 without, 4 CTAs 80.4 with / 74.9 without per 256 matrices;
@@ -646,5 +689,7 @@ int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   MOP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
-  return MOP_OK;
+  if (!kstop) return MOP_OK;
+  MOP_CHECK_CUDA(cudaMemsetAsync(flag_scratch, 0, sizeof(int) * (size_t)B, stream));
+  return mop_launch_tridiag_blk_resume(B, n, kstop, A, (size_t)n * n, Vh, dd, ee, tau, gq_scratch, flag_scratch, stream);
 }
