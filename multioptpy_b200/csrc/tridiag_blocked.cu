@@ -281,8 +281,20 @@ __device__ __forceinline__ void project_update_dmma(double* L, const double* T, 
 // Hessian, already written back), *gp_mine the projected gradient entry of row tid.  `fr` is the region behind the
 // triangle (free until the reduction starts; left dirty).  Whole CTA.
 template <int NW>
-__device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L, double* fr, double* gp_mine) {
+__device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L, double* fr, double* gp_mine,
+                            long long* dbg) {
   constexpr int THREADS = 32 * NW;
+  // optional phase clocks (diagnostics, tools/tb_segments.py front): dbg [16] per structure
+  long long fmark = dbg ? clock64() : 0;
+  int fslot = 0;
+#define FMARK()                                   \
+  do {                                            \
+    if (dbg && threadIdx.x == 0) {                \
+      const long long tn_ = clock64();            \
+      dbg[fslot++] = tn_ - fmark;                 \
+      fmark = tn_;                                \
+    }                                             \
+  } while (0)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const size_t nn = (size_t)n * n;
   double* H = f.H + (size_t)b * nn;   // (full-square layout; the packed layout is addressed where it is used)
@@ -346,6 +358,7 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
     }
   }
   __syncthreads();
+  FMARK();  // 0: s, y, guards
 
   // ---- one read of H: sym(H) into the triangle, u = H s (and H y) from the same loads ----------------------------
   const int ntri = (n * (n + 1)) >> 1;
@@ -391,6 +404,7 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
     front_half_pass<NW, false, false, 0>(H, n, L, vs, vy, vu, hy, lane, wid);
   }
   __syncthreads();
+  FMARK();  // 1: read of H
 
   if (upd) {
     // ---- scalars, coefficient matrix (hessian_update.py / block_hessian_update.py through update_coef.cuh) -------
@@ -454,6 +468,7 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
       }
     }
     __syncthreads();
+    FMARK();  // 2: coefficients + update on the triangle
     // ---- write H' back (the only write of the Hessian): full rows from the triangle, or the triangle itself ------
     if (f.packed) {
       double* Hpk = f.H + (size_t)b * ntri;
@@ -479,6 +494,7 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
   }
   __syncthreads();
 
+  FMARK();  // 3: write-back (+ bias)
   // ---- TR/ROT basis (classical Gram-Schmidt with drop, calc_tools.py:250-259), projected gradient -----------------
   double* T = fr;             // [6][np]
   double* Y = fr + 6 * np;    // [6][np]: raw vectors, then W = S T, then Y
@@ -515,6 +531,7 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
     Y[e] = 0.0;
   }
   __syncthreads();
+  FMARK();  // 4: basis + projected gradient
   // ---- W = S T: thread per row on the triangle (row part + column part), six vectors at once -------------------------
   if (tid < n) {
     const int i = tid;
@@ -557,8 +574,12 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
     }
   }
   __syncthreads();
+  FMARK();  // 5: W = S T, M, Y
   // ---- Hp = S - Y T^T - T Y^T: rank-12 update on the tensor cores ---------------------------------------------------
   project_update_dmma<NW>(L, T, Y, n, np, lane, wid);
+  __syncthreads();
+  FMARK();  // 6: rank-12 projection update
+#undef FMARK
   if (tid == 0 && f.status) f.status[b] = st;
   __syncthreads();
 }
@@ -607,7 +628,7 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
   double gp_mine = 0.0;
   if (FUSED) {
     // update + write-back + projection on the triangle (one read and one write of H, no projected Hessian in HBM)
-    fused_front<NW>(f, n, np, b, L, Wp, &gp_mine);
+    fused_front<NW>(f, n, np, b, L, Wp, &gp_mine, a.dbg ? a.dbg + (size_t)b * 16 : nullptr);
     for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
     for (int e = tid; e < n * (n + 1) / 2; e += THREADS) pn[0] = fma(L[e], L[e], pn[0]);
   } else if (resume) {
@@ -1028,7 +1049,7 @@ int mop_launch_front_tridiag_blk(int B, int n, int method, const int32_t* method
     mop_set_error("fused update + projection + tridiagonalisation: n = %d not supported (3 .. 160)", n);
     return MOP_ERR_UNSUPPORTED;
   }
-  mop::PkArgs a{n, nullptr, nullptr, Vh, dd, ee, tau, gq, flag, nullptr, n, 0, 0, nullptr, nullptr, 0};
+  mop::PkArgs a{n, nullptr, nullptr, Vh, dd, ee, tau, gq, flag, g_tb_dbg, n, 0, 0, nullptr, nullptr, 0};
   mop::FrontArgs f{H, Hbias, x, xp, g, gprev, Bg, state, state_stride, method, guards, grad_rule, method_per, packed, gp_out, status};
   return staged_blk<true>(B, a, f, hand, stream);
 }

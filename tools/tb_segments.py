@@ -20,3 +20,27 @@ for w, off in (("warp 0", 0), ("warp 3", 8)):
     print(w, "total cycles", tot, "per column", tot / (n - 2))
     for q, nm in enumerate(names):
         print(f"   {nm:26s} {d[:, off + q].mean():12.0f}  {100 * d[:, off + q].mean() / tot:5.1f} %")
+
+if len(sys.argv) > 3 and sys.argv[3] == "front":   # phase clocks of the fused front end (C2 step with the update active)
+    import bench
+    B = 1024; dev = torch.device("cuda:0")
+    x0, H0, g0, rngs = bench.make_inputs(B, 0)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    H = T(H0); st = ops.new_rsirfo_state(B, 0.5, dev); zero = torch.zeros(B, dtype=torch.float64, device=dev)
+    m = ops.resolve_update_method("rsirfo_bfgs")
+    out = ops.rsirfo_step(H, T(x0), T(g0), T(g0), st, method=m, Be=zero)
+    mv0 = out["move"].cpu().numpy()
+    x1 = np.empty_like(x0); g1 = np.empty_like(g0)
+    for b in range(B):
+        x1[b], g1[b] = synthetic.second_point(x0[b], H0[b], g0[b], mv0[b], rngs[b])
+    dbg.zero_()
+    lib.mop_priv_tridiag_blk_timing(dbg.data_ptr())
+    ops.rsirfo_step(H, T(x1), T(g1), T(g1), st, method=m, x_prev=T(x0), g_prev=T(g0), Be=zero - 1e-3)
+    torch.cuda.synchronize()
+    lib.mop_priv_tridiag_blk_timing(0)
+    d = dbg.cpu().numpy().astype(float)
+    names = ["s, y, guards", "read of H", "coefficients + update", "write-back", "basis + projected gradient", "W = S T, M, Y", "rank-12 update"]
+    tot = d[:, :7].sum(1).mean()
+    print("front end: total cycles", tot)
+    for q, nm in enumerate(names):
+        print(f"   {nm:28s} {d[:, q].mean():10.0f}  {100 * d[:, q].mean() / tot:5.1f} %")
