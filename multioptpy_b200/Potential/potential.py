@@ -1,7 +1,7 @@
 """Drop-in for ``multioptpy.Potential.potential.BiasPotentialCalculation`` (Potential/potential.py:53-202)
 restricted to the potentials built on the device: sums the bias energy / gradient / Hessian of every AFIR
 term, of the keep (distance, fragment distance, angle, dihedral, out-of-plane angle, anharmonic) restraints, of the
-fragment well potential and of the LJ repulsive potential (scale / value units) of ``force_data``; every other
+well potentials (fragment - fragment, atom - wall, atom - fixed point, atom - centre fragment) and of the LJ repulsive potential (scale / value units) of ``force_data``; every other
 potential the reference would activate raises ``MopError`` (``active_keys`` walks the reference's key list).
 The reference's side effects (.npy / .log files, :144,191-192) are not reproduced."""
 from __future__ import annotations
@@ -34,7 +34,8 @@ _ACTIVATION = {
 _HANDLED = {"AFIR_gamma", "keep_pot_spring_const", "keep_pot_v2_spring_const", "keep_angle_spring_const",
             "keep_dihedral_angle_spring_const", "anharmonic_keep_pot_spring_const", "well_pot_wall_energy",
             "keep_out_of_plain_angle_spring_const", "repulsive_potential_well_scale", "keep_angle_v2_spring_const",
-            "keep_dihedral_angle_v2_spring_const", "keep_out_of_plain_angle_v2_spring_const"}
+            "keep_dihedral_angle_v2_spring_const", "keep_out_of_plain_angle_v2_spring_const",
+            "wall_well_pot_wall_energy", "void_point_well_pot_wall_energy", "around_well_pot_wall_energy"}
 
 
 def centroid_term(kind, fragments, k, p):
@@ -156,6 +157,25 @@ class BiasPotentialCalculation:
                 lim = [float(v) / tables.BOHR2ANG for v in force_data["well_pot_limit_dist"][i]]
                 terms.append((ops.BIAS_WELL, [a - 1 for a in force_data["well_pot_fragm_1"][i]],
                               [a - 1 for a in force_data["well_pot_fragm_2"][i]], float(wv) / tables.HARTREE2KJMOL, 0.0, lim))
+        for i, wv in enumerate(force_data.get("wall_well_pot_wall_energy", [])):             # potential.py:700-708
+            if wv != 0.0:
+                lim = [float(v) / tables.BOHR2ANG for v in force_data["wall_well_pot_limit_dist"][i]]
+                axis = {"x": 0, "y": 1, "z": 2}[force_data["wall_well_pot_direction"][i]]
+                for a in force_data["wall_well_pot_target"][i]:
+                    terms.append((ops.BIAS_WELL_WALL, [a - 1], [axis], float(wv) / tables.HARTREE2KJMOL, 0.0, lim))
+        for i, wv in enumerate(force_data.get("void_point_well_pot_wall_energy", [])):       # potential.py:713-721
+            if wv != 0.0:
+                lim = [float(v) / tables.BOHR2ANG for v in force_data["void_point_well_pot_limit_dist"][i]]
+                # the reference stores the point as a float32 tensor (switching_potential.py:137)
+                pt = [float(np.float32(float(v))) for v in force_data["void_point_well_pot_coordinate"][i]]
+                for a in force_data["void_point_well_pot_target"][i]:
+                    terms.append((ops.BIAS_WELL_POINT, [a - 1], [], float(wv) / tables.HARTREE2KJMOL, 0.0, lim, pt))
+        for i, wv in enumerate(force_data.get("around_well_pot_wall_energy", [])):           # potential.py:727-735
+            if wv != 0.0:
+                lim = [float(v) / tables.BOHR2ANG for v in force_data["around_well_pot_limit_dist"][i]]
+                cen = [a - 1 for a in force_data["around_well_pot_center"][i]]
+                for a in force_data["around_well_pot_target"][i]:        # one fragment-well term per target atom
+                    terms.append((ops.BIAS_WELL, [a - 1], cen, float(wv) / tables.HARTREE2KJMOL, 0.0, lim))
         for i, wv in enumerate(force_data.get("repulsive_potential_well_scale", [])):        # potential.py:574-604
             if wv != 0.0:
                 terms += lj_pair_terms(element_list, force_data["repulsive_potential_Fragm_1"][i],

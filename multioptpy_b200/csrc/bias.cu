@@ -23,6 +23,9 @@
 //   kind 10 StructKeepDihedralAnglePotentialv2 (keep_dihedral_angle_potential.py:156-257)  kind 4 on four centroids
 //   kind 11 StructKeepOutofPlainAnglePotentialv2 (keep_outofplain_angle_potential.py:148-290)  kind 8 on four centroids
 //           (kinds 9-11: q[g] = number of atoms of fragment g, the fragments one after the other in `atoms`)
+//   kind 12 one target atom of WellPotentialVP (switching_potential.py:121-170): the well of kind 7 in the distance to a
+//           fixed point;  kind 13 one target atom of WellPotentialWall (:69-119): the well in |x_axis| (n2 = axis);
+//           WellPotentialAround (:172-224) is kind 7 per target atom (fragment 1 = the atom, fragment 2 = the centre atoms)
 // The reference differentiates calc_energy with torch.func.jacrev / hessian on the CPU
 // (Potential/potential.py:127-137); here thread (term, coordinate pair) evaluates the same expression once in
 // hyper-dual arithmetic.  Results are ADDED to E, grad, hess (the aggregator sums all bias terms).
@@ -37,8 +40,10 @@ struct BiasTerm {
   int n1, n2;             // atoms in fragment 1 / 2 (kind 1: 1, 1; kind 3 / 4: atoms i, j, k (, l) in `atoms`, n1 = 3 / 4)
   int atoms[BIAS_MAXA];   // 0-based
   double k, p;            // spring constant; r0 in Angstrom (kinds 1, 2), theta0 in degrees (kind 3), phi0 in radians (kind 4)
-  double q[4];            // kind 6: q[0] = well depth; kind 7: k = wall energy (Hartree), q = a, b, c, d (Bohr);
+  double q[4];            // kind 6: q[0] = well depth; kinds 7, 12, 13: k = wall energy (Hartree), q = a, b, c, d (Bohr);
                           // kind 5: k = eps (Hartree), p = sigma (Bohr); kind 8: p = phi0 in radians
+  double r3[3];           // kind 12: the void point (Bohr, already rounded to float32 as the reference stores it)
+  double pad_;
 };
 
 __device__ __forceinline__ HD hd_exp(HD x) { const double e = exp(x.f); return hd_unary(x, e, e, e); }
@@ -56,7 +61,7 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
   };
   const double BOHR2ANG = 0.52917721067;
   // point g of an angle / dihedral / out-of-plane term: atom g (kinds 3, 4, 8) or the centroid of fragment g (9-11)
-  const bool grouped = t.kind >= 9;
+  const bool grouped = t.kind >= 9 && t.kind <= 11;
   int goff[5] = {0, 0, 0, 0, 0};
   if (grouped)
     for (int g = 0; g < 4; ++g) goff[g + 1] = goff[g] + (int)t.q[g];
@@ -91,15 +96,25 @@ __device__ HD bias_energy(const BiasTerm& t, const double* xyz, int ca, int cb) 
     const HD om = hd_const(1.0) - ex;
     return t.q[0] * (om * om);
   }
-  if (t.kind == 7) {
-    HD v[3];
-    for (int c = 0; c < 3; ++c) {
-      HD s1 = hd_const(0.0), s2 = hd_const(0.0);
-      for (int a = 0; a < t.n1; ++a) s1 = s1 + X(a, c);
-      for (int a = 0; a < t.n2; ++a) s2 = s2 + X(t.n1 + a, c);
-      v[c] = (1.0 / t.n1) * s1 - (1.0 / t.n2) * s2;
+  if (t.kind == 7 || t.kind == 12 || t.kind == 13) {
+    HD r;
+    if (t.kind == 7) {
+      HD v[3];
+      for (int c = 0; c < 3; ++c) {
+        HD s1 = hd_const(0.0), s2 = hd_const(0.0);
+        for (int a = 0; a < t.n1; ++a) s1 = s1 + X(a, c);
+        for (int a = 0; a < t.n2; ++a) s2 = s2 + X(t.n1 + a, c);
+        v[c] = (1.0 / t.n1) * s1 - (1.0 / t.n2) * s2;
+      }
+      r = hd_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    } else if (t.kind == 12) {
+      HD v[3];
+      for (int c = 0; c < 3; ++c) v[c] = X(0, c) - hd_const(t.r3[c]);
+      r = hd_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    } else {
+      const HD x = X(0, t.n2);
+      r = x.f < 0.0 ? hd_const(0.0) - x : x;   // |x|: torch.linalg.norm of a scalar
     }
-    const HD r = hd_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     const double a = t.q[0], b = t.q[1], c = t.q[2], d = t.q[3];
     const HD xs = (0.5 / (b - a)) * r + hd_const(1.0 - 0.5 * b / (b - a));
     const HD xl = (0.5 / (c - d)) * r + hd_const(1.0 - 0.5 * c / (c - d));
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(128) k_bias_terms(int N, const BiasTerm* __res
   const int b = blockIdx.y, n = 3 * N;
   if (threadIdx.x == 0) t = terms[blockIdx.x];
   __syncthreads();
-  const int m = t.kind >= 9 ? (int)(t.q[0] + t.q[1] + t.q[2] + t.q[3])
+  const int m = (t.kind == 12 || t.kind == 13) ? 1 : t.kind >= 9 ? (int)(t.q[0] + t.q[1] + t.q[2] + t.q[3])
                             : (t.kind == 3 ? 3 : ((t.kind == 4 || t.kind == 8) ? 4 : ((t.kind == 5 || t.kind == 6) ? 2 : t.n1 + t.n2)));
   const int nc = 3 * m;
   const double* xyz = xyz_all + (size_t)b * n;

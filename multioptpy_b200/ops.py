@@ -824,6 +824,7 @@ BIAS_KEEP, BIAS_KEEP_V2, BIAS_KEEP_ANGLE, BIAS_KEEP_DIHEDRAL = 1, 2, 3, 4   # ki
 # (Hartree), q = the four limits (Bohr); kind 8: atoms centre, probe, plane 1, plane 2; p = phi0 in RADIANS
 BIAS_LJ_PAIR, BIAS_ANHARMONIC_KEEP, BIAS_WELL, BIAS_KEEP_OOP = 5, 6, 7, 8
 BIAS_KEEP_ANGLE_V2, BIAS_KEEP_DIHEDRAL_V2, BIAS_KEEP_OOP_V2 = 9, 10, 11   # fragment centroids: q = fragment sizes
+BIAS_WELL_POINT, BIAS_WELL_WALL = 12, 13   # well in the distance to a fixed point (r3) / in |x_axis| (frag2 = [axis])
 BIAS_MAXA = 64
 
 
@@ -833,14 +834,25 @@ def pack_bias_terms(terms, device):
     import numpy as _np
     lib = _lib.load()
     rec = int(lib.mop_bias_term_bytes())
-    dt = _np.dtype([("kind", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("atoms", "<i4", (BIAS_MAXA,)), ("pad", "<i4"), ("k", "<f8"), ("p", "<f8"), ("q", "<f8", (4,))])
+    dt = _np.dtype([("kind", "<i4"), ("n1", "<i4"), ("n2", "<i4"), ("atoms", "<i4", (BIAS_MAXA,)), ("pad", "<i4"), ("k", "<f8"), ("p", "<f8"), ("q", "<f8", (4,)),
+                    ("r3", "<f8", (3,)), ("pad2", "<f8")])
     if dt.itemsize != rec:
         raise MopError(f"bias term layout mismatch ({dt.itemsize} != {rec})")
     buf = _np.zeros(len(terms), dtype=dt)
     for i, term in enumerate(terms):
         kind, f1, f2, k, p = term[:5]
         q = list(term[5]) if len(term) > 5 else []
-        buf[i]["q"][: len(q)] = q
+        buf[i]["q"][: min(len(q), 4)] = q[:4]
+        if len(term) > 6:                      # kind 12: the point as a seventh entry, or behind the four limits in q
+            buf[i]["r3"][:] = term[6]
+        elif len(q) >= 7:
+            buf[i]["r3"][:] = q[4:7]
+        if kind == BIAS_WELL_WALL:            # the axis travels in n2, no second fragment
+            f1, f2 = list(f1), []
+            buf[i]["kind"], buf[i]["n1"], buf[i]["n2"] = kind, 1, int(term[2][0])
+            buf[i]["atoms"][:1] = f1
+            buf[i]["k"], buf[i]["p"] = k, p
+            continue
         at = list(f1) + list(f2)
         if len(at) > BIAS_MAXA:
             raise MopError("bias term: more than 64 atoms")

@@ -816,6 +816,9 @@ def gen_bias2():
     f1w, f2w = [1, 2, 3, 4], [5, 6, 7, 8, 9]
     dw = np.linalg.norm(cen(f1w) - cen(f2w)) * 0.52917721067      # centroid distance in Angstrom
     flat = xyz.copy(); flat[2] = flat[0] + 1.7 * (flat[1] - flat[0])          # atoms 1, 2, 3 collinear: undefined plane
+    def lims_for(dists_bohr):     # [a, b, c, d] in Angstrom: the middle target inside the flat part, the others on the two switching walls
+        ds = np.sort(np.asarray(dists_bohr)) * 0.52917721067
+        return [float(ds[0] - 0.2), float(ds[0] + 0.15), float(ds[2] - 0.15), float(ds[2] + 0.2)]
     flat2 = xyz.copy(); flat2[2] = flat2[1] + 0.8 * (flat2[1] - flat2[0])     # 1 - 2 - 3 exactly linear, vertex 2
     perp = np.cross(xyz[1] - xyz[0], [0.3, -0.2, 0.9]); perp /= np.linalg.norm(perp)
     near_pi = flat2.copy(); near_pi[2] = near_pi[2] + 4e-4 * np.linalg.norm(flat2[2] - flat2[1]) * perp      # 4e-4 rad off linear
@@ -844,6 +847,14 @@ def gen_bias2():
         ("angle_v2_near_0", dict(cls="ang2", k=0.3, f=[[1], [2], [3]], angle=30.0), near_0),
         ("dihedral_v2", dict(cls="dih2", k=0.2, f=[[1, 2], [3], [5, 6], [7]], angle=35.0), xyz),
         ("oop_v2", dict(cls="oop2", k=0.3, f=[[1], [2, 3], [5], [6, 7]], angle=12.0), xyz),
+        # the other wells of switching_potential.py: |y| of three atoms against a wall pair, three atoms around a fixed
+        # point (stored as float32 by the reference), three atoms around the centroid of a centre fragment; the limits
+        # are placed around the middle distance so that the targets fall into different regions of the well
+        ("wall_well", dict(cls="wallw", wall=30.0, direction="y", targets=[1, 4, 7], lim=lims_for(np.abs(xyz[[0, 3, 6], 1]))), xyz),
+        ("vp_well", dict(cls="vpw", wall=35.0, point=[0.3, -1.2, 0.7123456789], targets=[2, 5, 9],
+                         lim=lims_for(np.linalg.norm(xyz[[1, 4, 8]] - np.float32([0.3, -1.2, 0.7123456789]).astype(float), axis=1))), xyz),
+        ("around_well", dict(cls="arw", wall=25.0, center=[1, 2, 3], targets=[6, 8, 10],
+                             lim=lims_for(np.linalg.norm(xyz[[5, 7, 9]] - xyz[[0, 1, 2]].mean(axis=0), axis=1))), xyz),
     ]
     blob = {"names": np.array([c[0] for c in cases]), "elements": np.array(elems)}
     for name, cfg, geom in cases:
@@ -860,6 +871,15 @@ def gen_bias2():
                                                    anharmonic_keep_pot_atom_pairs=cfg["pair"], anharmonic_keep_pot_distance=cfg["dist"])
         elif cfg["cls"] == "well":
             pot = sw.WellPotential(well_pot_wall_energy=cfg["wall"], well_pot_fragm_1=cfg["f1"], well_pot_fragm_2=cfg["f2"], well_pot_limit_dist=cfg["lim"])
+        elif cfg["cls"] == "wallw":
+            pot = sw.WellPotentialWall(wall_well_pot_wall_energy=cfg["wall"], wall_well_pot_direction=cfg["direction"],
+                                       wall_well_pot_limit_dist=cfg["lim"], wall_well_pot_target=cfg["targets"])
+        elif cfg["cls"] == "vpw":
+            pot = sw.WellPotentialVP(void_point_well_pot_wall_energy=cfg["wall"], void_point_well_pot_coordinate=list(cfg["point"]),
+                                     void_point_well_pot_limit_dist=cfg["lim"], void_point_well_pot_target=cfg["targets"])
+        elif cfg["cls"] == "arw":
+            pot = sw.WellPotentialAround(around_well_pot_wall_energy=cfg["wall"], around_well_pot_center=cfg["center"],
+                                         around_well_pot_limit_dist=cfg["lim"], around_well_pot_target=cfg["targets"])
         elif cfg["cls"] == "ang2":
             f = cfg["f"]
             pot = ang.StructKeepAnglePotentialv2(keep_angle_v2_spring_const=cfg["k"], keep_angle_v2_angle=cfg["angle"],

@@ -1952,8 +1952,14 @@ def _bias2_energy_torch(geom, kind, f1, f2, k, p, q):
     if kind == 6:
         r = torch.linalg.norm(geom[f1[0]] - geom[f2[0]])
         return q[0] * (1.0 - torch.exp(-math.sqrt(k / (2 * q[0])) * (r - p / BOHR2ANG))) ** 2
-    if kind == 7:
-        r = torch.linalg.norm(geom[list(f1)].sum(dim=0) / len(f1) - geom[list(f2)].sum(dim=0) / len(f2))
+    if kind in (7, 12, 13):
+        if kind == 7:      # WellPotential, and WellPotentialAround per target atom (switching_potential.py:14-67,172-224)
+            r = torch.linalg.norm(geom[list(f1)].sum(dim=0) / len(f1) - geom[list(f2)].sum(dim=0) / len(f2))
+        elif kind == 12:   # WellPotentialVP (:121-170): p3 = the point, float32-rounded by the reference
+            r = torch.linalg.norm(geom[f1[0]] - torch.tensor(list(q[4:7]), dtype=torch.float64))
+        else:              # WellPotentialWall (:69-119): f2[0] = axis
+            r = abs(torch.linalg.norm(geom[f1[0]][f2[0]]))
+        q = q[:4]
         a, b, c, d = q
         xs = 0.5 / (b - a) * r + (1.0 - 0.5 * b / (b - a))
         xl = 0.5 / (c - d) * r + (1.0 - 0.5 * c / (c - d))

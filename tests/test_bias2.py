@@ -38,6 +38,15 @@ def force_data_for(cfg):
     if c == "well":
         return {"well_pot_wall_energy": [cfg["wall"]], "well_pot_fragm_1": [cfg["f1"]], "well_pot_fragm_2": [cfg["f2"]],
                 "well_pot_limit_dist": [cfg["lim"]]}
+    if c == "wallw":
+        return {"wall_well_pot_wall_energy": [cfg["wall"]], "wall_well_pot_direction": [cfg["direction"]],
+                "wall_well_pot_limit_dist": [cfg["lim"]], "wall_well_pot_target": [cfg["targets"]]}
+    if c == "vpw":
+        return {"void_point_well_pot_wall_energy": [cfg["wall"]], "void_point_well_pot_coordinate": [cfg["point"]],
+                "void_point_well_pot_limit_dist": [cfg["lim"]], "void_point_well_pot_target": [cfg["targets"]]}
+    if c == "arw":
+        return {"around_well_pot_wall_energy": [cfg["wall"]], "around_well_pot_center": [cfg["center"]],
+                "around_well_pot_limit_dist": [cfg["lim"]], "around_well_pot_target": [cfg["targets"]]}
     if c in ("ang2", "dih2", "oop2"):     # fragment-centroid restraints (potential.py:758-772,812-827,862-880)
         stem = {"ang2": "keep_angle_v2", "dih2": "keep_dihedral_angle_v2", "oop2": "keep_out_of_plain_angle_v2"}[c]
         fd = {f"{stem}_spring_const": [[cfg["k"]]], f"{stem}_angle": [[cfg["angle"]]]}
@@ -63,6 +72,14 @@ def oracle_terms(cfg, elems):
     if c == "well":
         return [(7, [a - 1 for a in cfg["f1"]], [a - 1 for a in cfg["f2"]], cfg["wall"] / tables.HARTREE2KJMOL, 0.0,
                  [v / B2A for v in cfg["lim"]])]
+    if c in ("wallw", "vpw", "arw"):
+        k, lim = cfg["wall"] / tables.HARTREE2KJMOL, [v / B2A for v in cfg["lim"]]
+        if c == "wallw":
+            return [(13, [a - 1], [{"x": 0, "y": 1, "z": 2}[cfg["direction"]]], k, 0.0, lim) for a in cfg["targets"]]
+        if c == "vpw":
+            pt = [float(np.float32(v)) for v in cfg["point"]]
+            return [(12, [a - 1], [], k, 0.0, lim + pt) for a in cfg["targets"]]
+        return [(7, [a - 1], [b - 1 for b in cfg["center"]], k, 0.0, lim) for a in cfg["targets"]]
     phi0 = float(torch.deg2rad(torch.tensor(cfg["angle"], dtype=torch.float64)))
     if c in ("ang2", "dih2", "oop2"):
         atoms = [a - 1 for f in cfg["f"] for a in f]
