@@ -304,6 +304,18 @@ int mop_hessian_ts_modify(int B, int n, const double* H, const double* evals, co
                           int32_t* modified, void* stream);
 int mop_hessian_clip_eigvals(int B, int n, const double* evals, const double* evecs, double* out, void* stream);
 
+/* "sr": ShortRangeCorrectionHessian.main (ModelHessian/shortrange.py:9-346, approx_hessian.py:100-102): the second
+ * derivatives of the short-range Coulomb kernel (1 - erf(omega r)) / r over the NON-bonded atom pairs (bonded:
+ * distance <= 1.1 (R_i + R_j), BondConnectivity) within 15 Bohr, weighted q_i q_j cx_sr scaling_factor, TR/ROT-
+ * projected, added to H and symmetrised: out = sym(H + P C P).  radii = covalent radii in Bohr, charges =
+ * 0.2 (mean Pauling electronegativity - electronegativity) per atom ([natoms] with stride 0 or [B][natoms]);
+ * defaults of the reference: omega 0.2, cx_sr 0.78, scaling_factor 0.5. */
+size_t mop_hessian_sr_workspace_bytes(int B, int natoms);
+int mop_hessian_sr_correction(int B, int natoms, const double* xyz, const double* radii, int radii_stride,
+                              const double* charges, int charges_stride, double omega, double cx_sr,
+                              double scaling_factor, const double* H, double* out, void* work, size_t work_bytes,
+                              void* stream);
+
 /* ---- effective Hessian for fixed atoms ---------------------------------------------------------------------------
  * Replaces HessianManager.calc_eff_hess_for_fix_atoms_and_set_hess (optimization.py:1325-1343,1358-1362):
  * H -= H[:, f] pinv(H[f, f] + 1e-10 I) H[f, :] with f the 3 n_fix coordinates of force_data["fix_atoms"], applied by the

@@ -43,6 +43,8 @@ SIGNATURES = {
     "mop_crsirfo_finalize": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mop_add_inplace": (_i, [_sz, _p, _p, _p]),
     "mop_tridiag_stage_count": (_i, [_i]),
+    "mop_hessian_sr_workspace_bytes": (_sz, [_i, _i]),
+    "mop_hessian_sr_correction": (_i, [_i, _i, _p, _p, _i, _p, _i, _d, _d, _d, _p, _p, _p, _sz, _p]),
     "mop_rsirfo_step_mixed": (_i, [_i, _i, _p, _i, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _sz, _p]),
     "mop_pack_lower": (_i, [_i, _i, _p, _p, _p]),

@@ -209,3 +209,127 @@ extern "C" int mop_fix_atoms_schur(int B, int n, int m, const int32_t* fix_coord
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// "sr": ShortRangeCorrectionHessian (ModelHessian/shortrange.py:9-346) - second derivatives of the short-range Coulomb
+// kernel (1 - erf(w r)) / r between NON-bonded atom pairs (BondConnectivity, 1.1 x the covalent radii) with
+// electronegativity charges, TR/ROT-projected, added to the base Hessian and symmetrised.  One CTA per structure, one
+// thread per 3 x 3 block: an off-diagonal block is minus the pair block, a diagonal block the sum of the atom's pair
+// blocks in ascending partner order (the order the reference's double loop adds them in).
+#include "connectivity.cuh"
+
+namespace mop {
+
+__device__ __forceinline__ void sr_pair_block(const double* xi, const double* xj, double ri, double rj, double qf,
+                                              double omega, double cutoff, double* blk) {
+  for (int e = 0; e < 9; ++e) blk[e] = 0.0;
+  const double dist = np_dist(xj, xi);
+  if (dist <= __dmul_rn(__dadd_rn(rj, ri), 1.1)) return;   // bonded (bond_connectivity.py:34-40)
+  double rv[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
+  const double r = sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+  if (r > cutoff) return;
+  const double PI = 3.141592653589793;
+  double d1, d2;
+  if (r < 1e-10) {
+    d1 = -2.0 * omega * omega * omega / (3.0 * sqrt(PI));
+    d2 = 0.0;
+  } else {
+    const double ef = erf(omega * r), ex = exp(-(omega * r) * (omega * r));
+    d1 = 2.0 * omega * ex / (sqrt(PI) * r) + (ef - 1.0) / (r * r);
+    const double xf = ex / sqrt(PI);
+    d2 = 2.0 * (2.0 * ef - 1.0) / (r * r * r) + 4.0 * omega * xf / (r * r) + 2.0 * (omega * omega * omega) * xf;
+  }
+  const double u[3] = {rv[0] / r, rv[1] / r, rv[2] / r};
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) {
+      const double o = u[a] * u[c];
+      blk[3 * a + c] = qf * (d2 * o + d1 / r * ((a == c ? 1.0 : 0.0) - o));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_sr_correction(int N, const double* __restrict__ xyz_all, const double* __restrict__ rad_all, int rad_stride,
+                const double* __restrict__ chg_all, int chg_stride, double omega, double cfac, double cutoff,
+                double* __restrict__ C_all) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, n = 3 * N;
+  double* xyz = sm;
+  double* rad = xyz + 3 * N;
+  double* chg = rad + N;
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) xyz[i] = xyz_all[(size_t)b * 3 * N + i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    rad[i] = rad_all[(size_t)b * rad_stride + i];
+    chg[i] = chg_all[(size_t)b * chg_stride + i];
+  }
+  __syncthreads();
+  double* C = C_all + (size_t)b * n * n;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int i = e / N, j = e - i * N;
+    double blk[9], acc[9];
+    if (i != j) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;   // the reference evaluates the pair (lo, hi)
+      sr_pair_block(xyz + 3 * lo, xyz + 3 * hi, rad[lo], rad[hi], chg[lo] * chg[hi] * cfac, omega, cutoff, blk);
+      for (int q = 0; q < 9; ++q) acc[q] = 0.0 - blk[q];
+    } else {
+      for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+      for (int k = 0; k < N; ++k) {
+        if (k == i) continue;
+        const int lo = i < k ? i : k, hi = i < k ? k : i;
+        sr_pair_block(xyz + 3 * lo, xyz + 3 * hi, rad[lo], rad[hi], chg[lo] * chg[hi] * cfac, omega, cutoff, blk);
+        for (int q = 0; q < 9; ++q) acc[q] += blk[q];
+      }
+    }
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) C[(size_t)(3 * i + a) * n + 3 * j + c] = acc[3 * a + c];
+  }
+}
+
+// out = 1/2 ((H + C) + (H + C)^T)
+__global__ void __launch_bounds__(256) k_add_sym(int n, const double* __restrict__ H, const double* __restrict__ C,
+                                                 double* __restrict__ out) {
+  const size_t b = blockIdx.y, nn = (size_t)n * n;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = e / n, j = e - i * n, t = j * n + i;
+    out[b * nn + e] = 0.5 * ((H[b * nn + e] + C[b * nn + e]) + (H[b * nn + t] + C[b * nn + t]));
+  }
+}
+
+}  // namespace mop
+
+int mop_launch_project_trrot(int B, int n, const double* H, const double* Hbias, const double* x, const double* g,
+                             double* Hp_out, double* gp_out, int32_t* status, int grad_rule, cudaStream_t stream);
+
+// ShortRangeCorrectionHessian.main for a batch: out = sym(H + P^T C P).  radii: covalent radii (Bohr) [natoms] (stride 0) or
+// [B][natoms]; charges: 0.2 (mean electronegativity - electronegativity) per atom, same strides; work: 2 B n^2 doubles.
+extern "C" size_t mop_hessian_sr_workspace_bytes(int B, int natoms) {
+  return B > 0 && natoms > 0 ? sizeof(double) * 2 * (size_t)B * 9 * natoms * natoms : 0;
+}
+
+extern "C" int mop_hessian_sr_correction(int B, int natoms, const double* xyz, const double* radii, int radii_stride,
+                                         const double* charges, int charges_stride, double omega, double cx_sr,
+                                         double scaling_factor, const double* H, double* out, void* work,
+                                         size_t work_bytes, void* stream_) {
+  MOP_REQUIRE(B >= 0 && natoms > 0 && xyz && radii && charges && H && out, "mop_hessian_sr_correction: bad arguments");
+  MOP_REQUIRE((radii_stride == 0 || radii_stride == natoms) && (charges_stride == 0 || charges_stride == natoms),
+              "mop_hessian_sr_correction: strides must be 0 or natoms");
+  if (B == 0) return MOP_OK;
+  if (!work || work_bytes < mop_hessian_sr_workspace_bytes(B, natoms)) {
+    mop_set_error("mop_hessian_sr_correction: workspace too small");
+    return MOP_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int n = 3 * natoms;
+  double* C = (double*)work;
+  double* Cp = C + (size_t)B * n * n;
+  const size_t smem = sizeof(double) * 5 * (size_t)natoms;
+  mop::k_sr_correction<<<B, 256, smem, stream>>>(natoms, xyz, radii, radii_stride, charges, charges_stride, omega,
+                                                 cx_sr * scaling_factor, 15.0, C);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  int rc = mop_launch_project_trrot(B, n, C, nullptr, xyz, nullptr, Cp, nullptr, nullptr, 0, stream);
+  if (rc != MOP_OK) return rc;
+  dim3 grid(64, B);
+  mop::k_add_sym<<<grid, 256, 0, stream>>>(n, H, Cp, out);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}

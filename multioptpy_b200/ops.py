@@ -446,6 +446,24 @@ def hessian_clip_eigvals(H):
     return out
 
 
+def hessian_sr_correction(H, xyz, radii, charges, omega: float = 0.2, cx_sr: float = 0.78, scaling_factor: float = 0.5):
+    """The "sr" modifier of ApproxHessian.main (ModelHessian/shortrange.py): out = sym(H + P C P).  radii (covalent,
+    Bohr) and charges (N,) or (B, N)."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    _chk(xyz, "xyz", (B, N, 3)); _chk(H, "H", (B, 3 * N, 3 * N))
+    r, rs = _radii_arg(radii, B, N, xyz.device)
+    c, cs = _radii_arg(charges, B, N, xyz.device)
+    out = torch.empty_like(H)
+    nbytes = lib.mop_hessian_sr_workspace_bytes(B, N)
+    work = workspace(xyz.device, nbytes)
+    with torch.cuda.device(xyz.device):
+        rc = lib.mop_hessian_sr_correction(B, N, _ptr(xyz), _ptr(r), rs, _ptr(c), cs, float(omega), float(cx_sr),
+                                           float(scaling_factor), _ptr(H), _ptr(out), _ptr(work), nbytes, _stream(xyz.device))
+    _lib.check(rc, "mop_hessian_sr_correction")
+    return out
+
+
 def afir(xyz, frag1, frag2, radii_f32, gamma, want_grad: bool = True, want_hess: bool = True):
     """AFIR energy / gradient / Hessian.  xyz (B, N, 3); frag1/frag2 0-based int32 index tensors;
     radii_f32 (N,) float32 Bohr; gamma (B,) kJ/mol.  Returns (E (B,), grad (B, 3N), H (B, 3N, 3N))."""

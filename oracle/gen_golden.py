@@ -1155,7 +1155,8 @@ MODELHESS_EXTRA = {   # exactly linear and near-linear molecules: the skip / dam
     "hccf_bent": (["H", "C", "C", "F"], np.array([[-3.15, 0.03, 0.0], [-1.14, 0.0, 0.0], [1.14, 0.0, 0.01], [3.5, -0.02, 0.0]])),
     "h2o2": (["O", "O", "H", "H"], np.array([[1.6, 0.0, -4.0], [1.6, 0.46, -2.64], [2.43, 0.05, -2.32], [0.79, -0.52, -4.02]]) / 0.52917721067),
 }
-MODELHESS_TYPES = ["fischerd3old", "fischerd3", "fischerts", "fischerclip", "fischerd3oldtsclip", "fischerd3clip"]
+MODELHESS_TYPES = ["fischerd3old", "fischerd3", "fischerts", "fischerclip", "fischerd3oldtsclip", "fischerd3clip", "fischersr",
+                   "fischerd3oldtssrclip"]
 
 
 def gen_modelhess_d3():

@@ -2181,3 +2181,45 @@ class CRSIRFOOracle(RSIRFOOracle):
         self.iteration += 1
         self.last = dict(info, eigvals=lam, pred=pred, trust=self.trust_radius)
         return -step
+
+
+PAULING_EN = {'H': 2.20, 'He': 0.00, 'Li': 0.98, 'Be': 1.57, 'B': 2.04, 'C': 2.55, 'N': 3.04, 'O': 3.44, 'F': 3.98, 'Ne': 0.00,
+              'Na': 0.93, 'Mg': 1.31, 'Al': 1.61, 'Si': 1.90, 'P': 2.19, 'S': 2.58, 'Cl': 3.16, 'Ar': 0.00, 'K': 0.82,
+              'Ca': 1.00, 'Sc': 1.36, 'Ti': 1.54, 'V': 1.63, 'Cr': 1.66, 'Mn': 1.55, 'Fe': 1.83, 'Co': 1.88, 'Ni': 1.91,
+              'Cu': 1.90, 'Zn': 1.65, 'Ga': 1.81, 'Ge': 2.01, 'As': 2.18, 'Se': 2.55, 'Br': 2.96, 'Kr': 0.00}
+
+
+def sr_charges(elems):
+    """estimate_atomic_charges (ModelHessian/shortrange.py:148-184): 0.2 (mean electronegativity - electronegativity)."""
+    en = [PAULING_EN.get(e, 2.0) for e in elems]
+    avg = sum(en) / len(en)
+    return np.array([0.2 * (avg - v) for v in en])
+
+
+def sr_hessian(H, xyz, elems, radii, omega=0.2, cx_sr=0.78, scaling=0.5, cutoff=15.0):
+    """ShortRangeCorrectionHessian.main (ModelHessian/shortrange.py:186-346): short-range Coulomb second derivatives of
+    the non-bonded pairs, TR/ROT-projected, added to H, symmetrised.  radii = covalent radii (Bohr)."""
+    from scipy.special import erf
+    xyz = np.asarray(xyz, float)
+    N = len(xyz)
+    q = sr_charges(elems)
+    C = np.zeros((3 * N, 3 * N))
+    for i in range(N):
+        for j in range(i + 1, N):
+            if np.linalg.norm(xyz[j] - xyz[i]) <= (radii[j] + radii[i]) * 1.1:
+                continue
+            rv = xyz[j] - xyz[i]
+            r = np.linalg.norm(rv)
+            if r > cutoff:
+                continue
+            ef, ex = erf(omega * r), np.exp(-(omega * r) ** 2)
+            d1 = 2 * omega * ex / (np.sqrt(np.pi) * r) + (ef - 1.0) / r ** 2
+            d2 = 2 * (2 * ef - 1) / r ** 3 + 4 * omega * (ex / np.sqrt(np.pi)) / r ** 2 + 2 * omega ** 3 * (ex / np.sqrt(np.pi))
+            u = rv / r
+            blk = q[i] * q[j] * cx_sr * scaling * (d2 * np.outer(u, u) + d1 / r * (np.eye(3) - np.outer(u, u)))
+            C[3 * i:3 * i + 3, 3 * i:3 * i + 3] += blk
+            C[3 * j:3 * j + 3, 3 * j:3 * j + 3] += blk
+            C[3 * i:3 * i + 3, 3 * j:3 * j + 3] -= blk
+            C[3 * j:3 * j + 3, 3 * i:3 * i + 3] -= blk
+    out = H + project_hessian_trrot(C, xyz.reshape(-1))
+    return 0.5 * (out + out.T)

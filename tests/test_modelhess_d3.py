@@ -34,6 +34,8 @@ def oracle_hessian(kind, xyz, elems):
         H = O.fischer_hessian(xyz, np.array([covalent_radius(e) for e in elems]))
     if "ts" in kind:
         H = O.ts_hessian(H)
+    if "sr" in kind:
+        H = O.sr_hessian(H, xyz, elems, np.array([covalent_radius(e) for e in elems]))
     if "clip" in kind:
         H = O.clip_hessian(H)
     return H
@@ -61,7 +63,7 @@ def test_dispatch_raises_for_unsupported_types():
     from multioptpy_b200.ModelHessian.approx_hessian import ApproxHessian
     from multioptpy_b200._lib import MopError
     x = np.zeros((3, 3))
-    for t in ("fischerd4", "fischersr", "lindh2007d3", "gfnff"):
+    for t in ("fischerd4", "schlegel", "lindh2007d3", "gfnff"):
         with pytest.raises(MopError):
             ApproxHessian(device="cuda:0").main(x, ["O", "C", "O"], np.zeros((3, 3)), t)
 
