@@ -414,7 +414,7 @@ def run_b200(args, rank, world, local_rank):
             "e2e_hessian_resident": {"value": e2e_res_val, "unit": UNIT,
                                      "h2d_bytes_per_step": 2 * B * n * 8, "d2h_bytes_per_step": B * n * 8},
             # fused update + projection + staged tridiagonalisation (5 launches at n = 150), spectrum + step, 3 (empty) fallbacks
-            "gpu_launches": (int(_lib.load().mop_tridiag_stage_count(n)) + 4) * K,
+            "gpu_launches": ((int(_lib.load().mop_tridiag_stage_count(n)) if B > 296 else 1) + 4) * K,
             "roofline": {"bound": "fp64",
                          "kernel": "k_tridiag_blk<5, fused> (+ its denser continuation stages <4>, <3>, <2>, <1>) + k_spectrum_step = the "
                                    "timed step: Hessian update, write-back, TR/ROT projection and blocked DMMA tridiagonalisation, then spectrum, "

@@ -154,7 +154,8 @@ int mop_eigh(int B, int n, int algo, const double* A, double* evals, double* eve
  * caller computes x_new = x - move, optimizer.py:798).
  * x_prev / g_prev may be NULL (no history).  Hbias may be NULL. */
 /* Kernel launches of the (staged) shared-memory tridiagonalisation inside mop_rsirfo_step / mop_eigh for n <= 160: the
- * reduction is handed to denser launches as the trailing block shrinks (5 at n = 150, 3 at n = 72, 1 at n <= 47). */
+ * reduction is handed to denser launches as the trailing block shrinks (5 at n = 150, 3 at n = 72, 1 at n <= 47); batches
+ * of at most 296 structures (two CTAs per SM) are reduced in one launch. */
 int mop_tridiag_stage_count(int n);
 size_t mop_rsirfo_workspace_bytes(int B, int n, int algo);
 int mop_rsirfo_step(int B, int n, int method, int saddle_order, int neb_mode, int eigh_algo,

@@ -967,7 +967,9 @@ static int tb_stage_cols(int m) {  // columns a stage of local size m reduces be
 template <bool FUSED>
 static int staged_blk(int B, mop::PkArgs a, const mop::FrontArgs& f, double* hand, cudaStream_t stream) {
   const int n = a.n;
-  if (!hand || tb_stage_cols(n) == 0) return dispatch_blk<FUSED>(B, a, f, stream);
+  // a batch that leaves SMs idle anyway (<= two CTAs per SM: a NEB chain of 64 images) gains nothing from denser stages
+  // and would pay their launches and hand-overs
+  if (!hand || B <= 2 * 148 || tb_stage_cols(n) == 0) return dispatch_blk<FUSED>(B, a, f, stream);
   double* buf[2] = {hand, hand + (((size_t)n * n / 2) & ~(size_t)1)};
   int c = 0, s = 0;
   for (;; ++s) {
