@@ -225,7 +225,7 @@ int mop_rsprfo_step(int B, int n, int method, int saddle_order, int eigh_algo, d
  * The part of RSIRFO.run after the projections (Optimizer/rsirfo.py:358-490): one
  * shared-memory-resident kernel per structure that tridiagonalises Hp, finds the
  * spectrum, solves the RFO secular equation in the eigenbasis and transforms the step
- * back (n <= 158); structures with tight eigenvalue clusters are redone by the Jacobi
+ * back (n <= 160); structures with tight eigenvalue clusters are redone by the Jacobi
  * path.  Hp [B][n][n] must be symmetric; gp = projected gradient, Bg = raw biased
  * gradient (its norm drives the inner trust-radius rule, rsirfo.py:312,835). */
 size_t mop_rsirfo_spectral_workspace_bytes(int B, int n);

@@ -9,7 +9,8 @@ convergence test (``mop_crsirfo_finalize``).  The Hessian update is RSIRFO's own
 ``constraints`` is the reference's constraint object: ``_get_all_constraint_vectors(geom (N, 3)) -> (k, 3N)`` and
 ``adjust_init_coord(geom (N, 3)) -> (N, 3)`` (SHAKE-like correction) are called on the HOST per structure, exactly as
 the reference calls them; in tensor mode precomputed rows can be passed instead (``constraint_vectors=``, and the
-corrected geometry as ``geom_num_list`` with ``shake_displacement=``).  At most 12 constraint rows.
+corrected geometry as ``geom_num_list`` with ``shake_displacement=``).  At most 12 constraint rows; 3N <= 160 (the
+shared-memory spectrum / step kernels - larger systems raise ``MopError``).
 
 Reproduced quirks: the bias Hessian is added INTO ``self.hessian`` (crsirfo.py:76,86 ``+=`` on an alias) - once per
 call, twice when the SHAKE correction fires; ``eigvals`` of the last step are the subspace spectrum (the ``rank``

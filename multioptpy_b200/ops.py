@@ -268,7 +268,7 @@ def rsirfo_step(H, x, Bg, g, state, *, method: int, saddle_order: int = 0, neb_m
 
 def rsirfo_spectral_step(Hp, gp, Bg, state, *, saddle_order: int = 0, neb_mode: bool = False, Be=None,
                          trust_min: float = 0.01, trust_max: float = 0.5, out=None):
-    """RSIRFO.run after the projections: fused tridiagonal eigensolve + RFO step (n <= 158)."""
+    """RSIRFO.run after the projections: fused tridiagonal eigensolve + RFO step (n <= 160)."""
     lib = _lib.load()
     B, n = gp.shape
     dev = gp.device
