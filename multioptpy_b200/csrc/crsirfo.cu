@@ -255,8 +255,8 @@ k_crsirfo_finalize(int n, double thr, const double* __restrict__ gp_all, const d
 }  // namespace mop
 
 extern "C" int mop_add_inplace(size_t count, double* dst, const double* src, void* stream) {
-  MOP_REQUIRE(dst && src, "mop_add_inplace: null pointer");
   if (count == 0) return MOP_OK;
+  MOP_REQUIRE(dst && src, "mop_add_inplace: null pointer");
   const size_t blocks = (count + 255) / 256;
   mop::k_add_inplace<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, (cudaStream_t)stream>>>(count, dst, src);
   MOP_CHECK_CUDA(cudaGetLastError());
@@ -267,8 +267,8 @@ extern "C" int mop_constraint_project(int B, int n, int k, double svd_threshold,
                                       const double* g, const double* shake, double* Hp_out, double* gp_out,
                                       int32_t* rank_out, void* stream) {
   MOP_REQUIRE(B >= 0 && n > 0 && k >= 1 && k <= mop::CR_KMAX, "mop_constraint_project: 1 <= k <= 12 constraint rows required");
+  if (B == 0) return MOP_OK;   // (an empty batch has no buffers)
   MOP_REQUIRE(C && H && g && gp_out, "mop_constraint_project: C, H, g, gp_out required");
-  if (B == 0) return MOP_OK;
   const size_t smem = mop::cr_smem_bytes(n, k);
   if (smem > 220 * 1024) {
     mop_set_error("mop_constraint_project: n = %d with k = %d rows needs %zu bytes of shared memory", n, k, smem);
@@ -284,8 +284,9 @@ extern "C" int mop_constraint_project(int B, int n, int k, double svd_threshold,
 extern "C" int mop_crsirfo_finalize(int B, int n, double grad_threshold, const double* gp, const double* Be,
                                     const double* state_before, double* state, double* move, double* pred,
                                     int32_t* status, void* stream) {
-  MOP_REQUIRE(B >= 0 && n > 0 && gp && state_before && state && move, "mop_crsirfo_finalize: bad arguments");
+  MOP_REQUIRE(B >= 0 && n > 0, "mop_crsirfo_finalize: bad arguments");
   if (B == 0) return MOP_OK;
+  MOP_REQUIRE(gp && state_before && state && move, "mop_crsirfo_finalize: null pointer");
   mop::k_crsirfo_finalize<<<B, 128, 0, (cudaStream_t)stream>>>(n, grad_threshold, gp, Be, state_before, state, move, pred, status);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;

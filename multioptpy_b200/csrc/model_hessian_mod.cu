@@ -310,10 +310,11 @@ extern "C" int mop_hessian_sr_correction(int B, int natoms, const double* xyz, c
                                          const double* charges, int charges_stride, double omega, double cx_sr,
                                          double scaling_factor, const double* H, double* out, void* work,
                                          size_t work_bytes, void* stream_) {
-  MOP_REQUIRE(B >= 0 && natoms > 0 && xyz && radii && charges && H && out, "mop_hessian_sr_correction: bad arguments");
+  MOP_REQUIRE(B >= 0 && natoms > 0, "mop_hessian_sr_correction: bad arguments");
   MOP_REQUIRE((radii_stride == 0 || radii_stride == natoms) && (charges_stride == 0 || charges_stride == natoms),
               "mop_hessian_sr_correction: strides must be 0 or natoms");
-  if (B == 0) return MOP_OK;
+  if (B == 0) return MOP_OK;   // (an empty batch has no buffers)
+  MOP_REQUIRE(xyz && radii && charges && H && out, "mop_hessian_sr_correction: null pointer");
   if (!work || work_bytes < mop_hessian_sr_workspace_bytes(B, natoms)) {
     mop_set_error("mop_hessian_sr_correction: workspace too small");
     return MOP_ERR_WORKSPACE;

@@ -429,8 +429,9 @@ extern "C" int mop_neb_redistribute(int nimg, int natoms, int first, int nloc, c
                                     double* path_length_out, void* stream) {
   MOP_REQUIRE(nimg >= 2 && natoms > 0 && nloc >= 0 && first >= 0 && first + nloc <= nimg,
               "mop_neb_redistribute: bad image range or natoms");
-  MOP_REQUIRE(x_chain && x_out && x_chain != x_out, "mop_neb_redistribute: x_chain and a distinct x_out required");
   MOP_REQUIRE(nimg <= 16384, "mop_neb_redistribute: at most 16384 images");
+  if (nloc == 0 && !path_length_out) return MOP_OK;   // (a rank without images has no output buffer)
+  MOP_REQUIRE(x_chain && (nloc == 0 || (x_out && x_chain != x_out)), "mop_neb_redistribute: x_chain and a distinct x_out required");
   mop::k_neb_redistribute<<<1, 256, sizeof(double) * (size_t)nimg, (cudaStream_t)stream>>>(nimg, natoms, first, nloc, x_chain,
                                                                                           x_out, path_length_out);
   MOP_CHECK_CUDA(cudaGetLastError());

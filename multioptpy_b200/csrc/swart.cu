@@ -475,9 +475,9 @@ extern "C" int mop_swart_hessian(int B, int natoms, const double* xyz, const dou
                                  double* H_out, double* Hraw_out, int32_t* status, void* work, size_t work_bytes,
                                  void* stream_) {
   MOP_REQUIRE(B >= 0 && natoms > 0, "mop_swart_hessian: B >= 0 and natoms > 0 required");
-  MOP_REQUIRE(xyz && radii && H_out, "mop_swart_hessian: xyz, radii, H_out required");
   MOP_REQUIRE(radii_stride == 0 || radii_stride == natoms, "mop_swart_hessian: radii_stride must be 0 or natoms");
-  if (B == 0) return MOP_OK;
+  if (B == 0) return MOP_OK;   // (an empty batch has no buffers)
+  MOP_REQUIRE(xyz && radii && H_out, "mop_swart_hessian: xyz, radii, H_out required");
   double* Hraw = Hraw_out;
   if (!Hraw) {
     if (!work || work_bytes < mop_swart_workspace_bytes(B, natoms)) {

@@ -1,5 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python bench.py 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('value',d['value'],'e2e',d['e2e']['value'],'launches',d['gpu_launches'])
-for k,v in d['per_config'].items(): print(k, v.get('value'), v.get('ms_per_iteration', v.get('ms_per_step')))"
+timeout 600 python -m pytest tests/test_edge_new.py -m gpu -x -q 2>&1 | tail -15
