@@ -1,1 +1,2 @@
-python tools/two_stream_probe.py 2>&1 | tail -5
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -1
