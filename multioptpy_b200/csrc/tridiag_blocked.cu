@@ -277,6 +277,44 @@ __device__ __forceinline__ void project_update_dmma(double* L, const double* T, 
   }
 }
 
+// ---- TMA bulk copies of the packed triangle (cp.async.bulk, SASS UBLKCP): HBM and shared memory hold the same layout, so
+// the 90.6 KB of a structure (n = 150) move as ONE asynchronous copy each way instead of 71 load / store rounds per
+// thread.  The copy engine needs 16-byte aligned addresses and sizes; n (n + 1) / 2 is odd for n = 1, 2 (mod 4), so every
+// other structure starts on an 8-byte boundary: the kernel then places the triangle one double into its (even-sized)
+// shared-memory slot, which gives source and destination the same phase, and the one element in front of the first
+// 16-byte boundary / behind the last travels by a plain load or store.
+__device__ __forceinline__ unsigned tb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tb_bulk_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tb_smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tb_smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(tb_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tb_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = tb_smem_addr(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tb_bulk_store(double* dst, const double* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tb_smem_addr(src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source may be overwritten from here on
+}
+// split of a packed triangle of ntri doubles at address p into [head | 16-byte aligned body of an even count | tail]
+__device__ __forceinline__ void tb_bulk_split(const void* p, int ntri, int* head, int* body) {
+  *head = (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1);
+  *body = (ntri - *head) & ~1;
+}
+
 // The fused front end.  On return L holds the projected effective Hessian sym(P^T (H' + Hbias) P) (H' = the updated
 // Hessian, already written back), *gp_mine the projected gradient entry of row tid.  `fr` is the region behind the
 // triangle (free until the reduction starts; left dirty).  Whole CTA.
@@ -366,7 +404,24 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
     // packed lower triangle in HBM = the shared-memory layout: a straight coalesced copy, then u = H s as a
     // thread-per-row symv on the triangle
     const double* Hpk = f.H + (size_t)b * ntri;
-    for (int e = tid; e < ntri; e += THREADS) L[e] = Hpk[e];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const bool bulk = ((reinterpret_cast<uintptr_t>(Hpk) ^ reinterpret_cast<uintptr_t>(L)) & 15) == 0;   // same 16-byte phase
+    if (bulk) {
+      int head, body;
+      tb_bulk_split(Hpk, ntri, &head, &body);
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tb_smem_addr(&s_mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      __syncthreads();
+      if (tid == 0) tb_bulk_load(L + head, Hpk + head, (unsigned)body * 8u, &s_mbar);
+      if (tid == 32 % THREADS && head) L[0] = Hpk[0];
+      if (tid == 64 % THREADS && head + body < ntri) L[ntri - 1] = Hpk[ntri - 1];
+      tb_mbar_wait(&s_mbar, 0);
+    } else {
+      for (int e = tid; e < ntri; e += THREADS) L[e] = Hpk[e];
+    }
     __syncthreads();
     if (upd && tid < n) {
       const int i = tid;
@@ -472,7 +527,17 @@ __device__ void fused_front(const FrontArgs& f, int n, int np, int b, double* L,
     // ---- write H' back (the only write of the Hessian): full rows from the triangle, or the triangle itself ------
     if (f.packed) {
       double* Hpk = f.H + (size_t)b * ntri;
-      for (int e = tid; e < ntri; e += THREADS) Hpk[e] = L[e];
+      if (((reinterpret_cast<uintptr_t>(Hpk) ^ reinterpret_cast<uintptr_t>(L)) & 15) == 0) {
+        int head, body;
+        tb_bulk_split(Hpk, ntri, &head, &body);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the update above -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) tb_bulk_store(Hpk + head, L + head, (unsigned)body * 8u);
+        if (tid == 32 % THREADS && head) Hpk[0] = L[0];
+        if (tid == 64 % THREADS && head + body < ntri) Hpk[ntri - 1] = L[ntri - 1];
+      } else {
+        for (int e = tid; e < ntri; e += THREADS) Hpk[e] = L[e];
+      }
     } else {
       for (int i = wid; i < n; i += NW) {
         double* row = H + (size_t)i * n;
@@ -609,7 +674,10 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
   const int np = (n + 3) & ~3;
   const size_t nl = ((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1;
   double* L = sm;                   // packed lower triangle, row i at i (i + 1) / 2
-  double* Wp = L + nl;              // [n][WS] W panel (directly behind L: symv reads past row n-1 land here, times 0)
+  if (FUSED && f.packed && ((n * (n + 1) / 2) & 1) &&
+      (reinterpret_cast<uintptr_t>(f.H + (size_t)b * (n * (n + 1) / 2)) & 15))
+    L = sm + 1;                     // odd triangle on an 8-byte boundary: same 16-byte phase as its HBM image (TMA bulk copies)
+  double* Wp = sm + nl;             // [n][WS] W panel (directly behind L: symv reads past row n-1 land here, times 0)
   double* uu = Wp + (size_t)n * WS; // [NU] raw updated column (16-byte aligned: nl and n WS are even)
   double* zrow = uu + NU;           // [np] row-part sums of the symv (permuted lane map)
   double* gq = zrow + np;           // [np] Q^T g
