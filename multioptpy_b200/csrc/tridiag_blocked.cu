@@ -705,10 +705,26 @@ __global__ void __launch_bounds__(32 * NW, TbMinBlocks<NW>::value) k_tridiag_blk
     for (int i = tid; i < (int)(tb_smem_doubles(n, NW) - nl); i += THREADS) Wp[i] = 0.0;
     __syncthreads();
     const double* h = a.hin + (size_t)b * a.hstride;
-    for (int e = tid; e < n * (n + 1) / 2; e += THREADS) L[e] = h[e];
-    for (int i = tid; i < n; i += THREADS) {
-      uu[i] = h[nl + i];
-      gq[i] = h[nl + n + i];
+    if ((reinterpret_cast<uintptr_t>(h) & 15) == 0) {   // the hand-over triangle (even-sized slot, 16-byte aligned): one TMA bulk copy
+      __shared__ __align__(8) unsigned long long s_hbar;
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tb_smem_addr(&s_hbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      __syncthreads();
+      if (tid == 0) tb_bulk_load(L, h, (unsigned)nl * 8u, &s_hbar);
+      for (int i = tid; i < n; i += THREADS) {
+        uu[i] = h[nl + i];
+        gq[i] = h[nl + n + i];
+      }
+      tb_mbar_wait(&s_hbar, 0);
+    } else {
+      for (int e = tid; e < n * (n + 1) / 2; e += THREADS) L[e] = h[e];
+      for (int i = tid; i < n; i += THREADS) {
+        uu[i] = h[nl + i];
+        gq[i] = h[nl + n + i];
+      }
     }
     __syncthreads();
   } else {

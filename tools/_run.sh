@@ -1,3 +1,5 @@
-python tools/prof_packed.py > gpurun_out/plain_packed.log 2>&1 && tail -1 gpurun_out/plain_packed.log &&
-ncu --clock-control none -k k_tridiag_blk -s 5 -c 1 --metrics gpu__time_duration.sum,l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum,l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --csv --log-file gpurun_out/r2_tma_packed.csv python tools/prof_packed.py > gpurun_out/ncu_packed.log 2>&1
-tail -8 gpurun_out/r2_tma_packed.csv | cut -c1-260
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],d['e2e']['matches_resident_path'])
+for k,v in d['per_config'].items(): print(k, v.get('value'), v.get('ms_per_iteration', v.get('ms_per_step')), v.get('parity_vs_oracle'))"
