@@ -333,7 +333,8 @@ def test_rsirfo_packed_storage_vs_oracle(natoms, method, bias):
 
 
 @pytest.mark.gpu
-def test_host_pipeline_two_phase_vs_oracle_and_single_call():
+@pytest.mark.parametrize("natoms", [12, 11])   # 11: an odd triangle (561 doubles) - chunks start on 8-byte boundaries (TMA phase match)
+def test_host_pipeline_two_phase_vs_oracle_and_single_call(natoms):
     """HostStepPipeline (pinned host buffers, chunked copies, mop_rsirfo_step_packed_begin per chunk +
     mop_rsirfo_step_packed_finish once): two steps vs the oracle (1e-10) and equal to the one-call
     mop_rsirfo_step_packed on the same inputs to rounding (the one-call path reduces in stages whose warps sum their
@@ -342,7 +343,7 @@ def test_host_pipeline_two_phase_vs_oracle_and_single_call():
     import torch
     from multioptpy_b200 import ops, synthetic
     from multioptpy_b200.host_pipeline import HostStepPipeline, pack_lower_host
-    B, natoms, method = 7, 12, "rsirfo_bfgs"
+    B, method = 7, "rsirfo_bfgs"
     n = 3 * natoms
     mid = ops.resolve_update_method(method)
     x0, H0, g0, rngs = synthetic.batch(91, B, natoms)
