@@ -98,6 +98,7 @@ PRIVATE_SIGNATURES = {
     "mop_priv_latency": (_i, [_p, _p]),
     "mop_priv_barrier_latency": (_i, [_i, _p, _p]),
     "mop_priv_spectrum_timing": (_i, [_p]),
+    "mop_priv_large_timing": (_i, [_p]),
     "mop_priv_tridiag_blk_timing": (_i, [_p]),
     "mop_priv_tridiag_cluster_timing": (_i, [_p]),
     "mop_priv_large_cluster": (_i, [_i]),

@@ -681,6 +681,13 @@ int mop_launch_tridiag_cluster(int B, int n, double* A, double* Vh, double* dd, 
 int mop_launch_tridiag_blk(int B, int n, const double* A, const double* gp, double* Vh, double* dd, double* ee,
                            double* tau, double* gq, int* flag, double* hand, cudaStream_t stream);
 
+// diagnostics (csrc/mop_private.h): device buffer [2][B][4] receiving the phase clocks of k_lg_trieig (second half)
+static long long* g_lg_dbg = nullptr;
+extern "C" int mop_priv_large_timing(void* buf) {
+  g_lg_dbg = (long long*)buf;
+  return MOP_OK;
+}
+
 int mop_large_supported(int n) { return n >= 3 && n <= mop::LG_MAX_N; }
 
 size_t mop_large_workspace_bytes(int B, int n) {
@@ -729,7 +736,7 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
   a.evals = evals;
   a.evecs = nullptr;
   a.status = status;
-  a.dbg = nullptr;
+  a.dbg = g_lg_dbg;
   a.ablate = 0;
   {
     dim3 grid((n + 31) / 32, (n + 31) / 32, B);
@@ -750,6 +757,8 @@ static int lg_factor(int B, int n, const double* A, double* evals, int32_t* stat
     if (rc != MOP_OK) return rc;
   }
   {
+    // (a 640-thread instantiation with two CTAs per SM - 256 matrices of order 600 as one wave instead of two - was
+    // measured slower: 48 registers spill the Sturm loop, 10.0 ms against 9.2 ms; tools/trieig_phases.py)
     const int thr = n <= 160 ? 160 : mop::LG_EIG_THREADS;
     const size_t smem = sizeof(double) * (12 * (size_t)np + (thr / 32) * 64 + 2) + sizeof(int) * 7 * (size_t)np;
     if (thr == 160) {

@@ -19,6 +19,7 @@ int mop_priv_barrier_latency(int threads, double* out, void* stream);
 int mop_priv_spectrum_timing(void* buf);
 int mop_priv_tridiag_blk_timing(void* buf);
 int mop_priv_tridiag_cluster_timing(void* buf);
+int mop_priv_large_timing(void* buf);   /* k_lg_trieig: [2][B][4] int64, second half = eigenvalues | vectors | cluster fix */
 /* cluster tridiagonalisation: CTAs per matrix (1, 2, 4, 8; 0 = by batch size), lower-triangle symv on / off,
  * ablation mask (results invalid) */
 int mop_priv_large_cluster(int cluster_ctas);
