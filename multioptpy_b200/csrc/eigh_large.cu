@@ -424,7 +424,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 160 ? 7 : (THREADS <= 256
         }
         S[rr * lds + i] = 1.0;
         const double sc = 1.0 / sqrt(1.0 + au + ad);
-        for (int k = s; k < t; ++k) S[k * lds + i] *= sc;
+        for (int k0 = s; k0 < t; k0 += 8) {   // eight independent loads in flight per lane (the plain loop was one round trip per row)
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = (k0 + u < t) ? S[(k0 + u) * lds + i] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (k0 + u < t) S[(k0 + u) * lds + i] = v[u] * sc;
+        }
         if (!isfinite(sc) || sc == 0.0) s_fallback = 1;
         nrm_up[i] = au;
         nrm_dn[i] = ad;
