@@ -360,78 +360,73 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 160 ? 7 : (THREADS <= 256
           S[k * lds + i] = r;
           if (k + 1 < t) q = fma(-e2[k], r, d[k + 1] - l);
         }
-        q = d[t - 1] - l;
-        for (int k = t - 1; k >= s; --k) {
-          if (fabs(q) < piv) q = (q <= 0.0) ? -piv : piv;
-          const double r = fast_rcp(q);
-          Dm[k * lds + i] = r;
-          if (k > s) q = fma(-e2[k - 1], r, d[k - 1] - l);
-        }
-        // twist index: gamma_k = D+_k - e2_k / D-_{k+1}
+        // backward sweep with the twist search fused in: gamma_k = |D+_k - e2_k / D-_{k+1}| needs the forward reciprocal
+        // of row k-1 (eight loads in flight) and the backward reciprocal of row k+1, which is the previous iteration's r
         double best = INFINITY;
         int rr = s;
-        for (int k0 = s; k0 < t; k0 += 8) {
-          double rm[8], sp[8];
+        {
+          double q = d[t - 1] - l, rm = 0.0;
+          for (int k0 = t - 1; k0 >= s; k0 -= 8) {
+            double sp[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            rm[u] = (k0 + u + 1 < t) ? Dm[(k0 + u + 1) * lds + i] : 0.0;
-            sp[u] = (k0 + u > s && k0 + u < t) ? S[(k0 + u - 1) * lds + i] : 0.0;
-          }
+            for (int u = 0; u < 8; ++u) sp[u] = (k0 - u > s) ? S[(k0 - u - 1) * lds + i] : 0.0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u;
-            if (k < t) {
-              double dp = d[k] - l;
-              if (k > s) dp = fma(-e2[k - 1], sp[u], dp);
-              const double gam = fabs(fma(-e2[k], rm[u], dp));
-              if (gam < best) {
-                best = gam;
-                rr = k;
+            for (int u = 0; u < 8; ++u) {
+              const int k = k0 - u;
+              if (k >= s) {
+                double dp = d[k] - l;
+                if (k > s) dp = fma(-e2[k - 1], sp[u], dp);
+                const double gam = fabs(fma(-e2[k], rm, dp));   // e2[t-1] == 0 closes the block
+                if (gam <= best) {   // descending scan, ties to the smaller index: the first minimum of an ascending scan
+                  best = gam;
+                  rr = k;
+                }
+                if (fabs(q) < piv) q = (q <= 0.0) ? -piv : piv;
+                const double r = fast_rcp(q);
+                Dm[k * lds + i] = r;
+                rm = r;
+                if (k > s) q = fma(-e2[k - 1], r, d[k - 1] - l);
               }
             }
           }
         }
         twist[i] = rr;
-        // z_r = 1; z_k = -e_k z_{k+1} / D+_k (k < r); z_k = -e_{k-1} z_{k-1} / D-_k (k > r)
-        double z = 1.0, au = 0.0;
-        for (int k0 = rr - 1; k0 >= s; k0 -= 8) {
-          double f[8];
+        // z_r = 1; z_k = -e_k z_{k+1} / D+_k (k < r); z_k = -e_{k-1} z_{k-1} / D-_k (k > r): the recurrences run twice - a
+        // read-only pass for the norm, then the pass that stores the NORMALISED vector (one write of S instead of a
+        // write, a read and a second write)
+        double au = 0.0, ad = 0.0, sc = 1.0;
+        for (int pass = 0; pass < 2; ++pass) {
+          double z = 1.0;
+          for (int k0 = rr - 1; k0 >= s; k0 -= 8) {
+            double f[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) f[u] = (k0 - u >= s) ? -(e[k0 - u] * S[(k0 - u) * lds + i]) : 0.0;
+            for (int u = 0; u < 8; ++u) f[u] = (k0 - u >= s) ? -(e[k0 - u] * S[(k0 - u) * lds + i]) : 0.0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (k0 - u >= s) {
-              z *= f[u];
-              S[(k0 - u) * lds + i] = z;
-              au = fma(z, z, au);
+            for (int u = 0; u < 8; ++u) {
+              if (k0 - u >= s) {
+                z *= f[u];
+                if (pass) S[(k0 - u) * lds + i] = z * sc;
+                else au = fma(z, z, au);
+              }
             }
           }
-        }
-        z = 1.0;
-        double ad = 0.0;
-        for (int k0 = rr + 1; k0 < t; k0 += 8) {
-          double f[8];
+          z = 1.0;
+          for (int k0 = rr + 1; k0 < t; k0 += 8) {
+            double f[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) f[u] = (k0 + u < t) ? -(e[k0 + u - 1] * Dm[(k0 + u) * lds + i]) : 0.0;
+            for (int u = 0; u < 8; ++u) f[u] = (k0 + u < t) ? -(e[k0 + u - 1] * Dm[(k0 + u) * lds + i]) : 0.0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (k0 + u < t) {
-              z *= f[u];
-              S[(k0 + u) * lds + i] = z;
-              ad = fma(z, z, ad);
+            for (int u = 0; u < 8; ++u) {
+              if (k0 + u < t) {
+                z *= f[u];
+                if (pass) S[(k0 + u) * lds + i] = z * sc;
+                else ad = fma(z, z, ad);
+              }
             }
           }
+          if (!pass) sc = 1.0 / sqrt(1.0 + au + ad);
         }
-        S[rr * lds + i] = 1.0;
-        const double sc = 1.0 / sqrt(1.0 + au + ad);
-        for (int k0 = s; k0 < t; k0 += 8) {   // eight independent loads in flight per lane (the plain loop was one round trip per row)
-          double v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = (k0 + u < t) ? S[(k0 + u) * lds + i] : 0.0;
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (k0 + u < t) S[(k0 + u) * lds + i] = v[u] * sc;
-        }
+        S[rr * lds + i] = sc;
         if (!isfinite(sc) || sc == 0.0) s_fallback = 1;
         nrm_up[i] = au;
         nrm_dn[i] = ad;
